@@ -1,0 +1,206 @@
+/*
+ * s2s_b200.h -- C ABI of libs2s_b200.so: the B200 (sm_100a) implementation of the
+ * seq2seq attention-ASR training hot path of Ajay-Wong/seq2seq-attention-asr.
+ *
+ * The reference has no FFI/plugin interface of its own (it is pure Lua on Torch7).  The
+ * boundary this library sits behind is the Torch7 nn.Module protocol of the reference's custom
+ * modules; every entry point below names the reference method (file:line under the reference
+ * tree) it replaces.  The LuaJIT-FFI binding a maintainer adds is shown in INTEGRATION.md and
+ * lives in seq2seq-attention-asr_b200/lua/.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types.  Every pointer named `const float*` / `float*` /
+ *     `const int*` is a DEVICE pointer unless the name ends in `_host`.
+ *   - fp32, row-major, batch-first: annotations h [B, Lmax, A], features X [B, Lmax, D],
+ *     labels [B, Tmax] (0-based class ids), lengths [B] / tlens [B] (valid frames / labels per
+ *     utterance; NULL = all Lmax / Tmax).  Single-utterance ("SGD mode") calls are B = 1.
+ *   - every function returns 0 on success, non-zero on error; the message is available from
+ *     s2s_last_error() (thread-local).  Nothing throws, nothing frees caller memory, no caller
+ *     pointer is retained after the call returns (except the stream given to the context).
+ *   - all work is enqueued on the context's stream; calls are asynchronous w.r.t. the host
+ *     unless stated otherwise.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef S2S_B200_H
+#define S2S_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define S2S_VERSION 100
+
+typedef struct s2s_ctx s2s_ctx;
+
+/* Mirrors the `model.*` fields set by timit/model_chorowski_baseline.lua:14-46 (and
+ * librispeech/model_chorowski_baseline.lua).  A (annotation depth) = 2*H. */
+typedef struct s2s_model_cfg {
+    int D;   /* inputFrameSize        (123)  model_chorowski_baseline.lua:15 */
+    int H;   /* hiddenFrameSize = outputFrameSize (256)  :16-17              */
+    int NL;  /* bidirectional encoder layers (3)  :22-31                     */
+    int S;   /* scoreDepth            (512)  :37                             */
+    int ST;  /* stateDepth            (256)  :41                             */
+    int V;   /* outputDepth           (62)   :43                             */
+    int K;   /* hybridAttendFeatureMaps (0 = content-only)  :40              */
+    int KF;  /* hybridAttendFilterSize (10)  :39                             */
+    int M;   /* mlpDepth              (64)   :44                             */
+    int MW;  /* maxout window         (7)    :56                             */
+} s2s_model_cfg;
+
+/* flags for the loss / gradient seed (timit/timit.lua:268-281) */
+#define S2S_NORMALIZE_NLL   1   /* nll /= T_b            (timit.lua:270-272) */
+#define S2S_NORMALIZE_GRAD  2   /* dlogp = -labelmask/T_b (timit.lua:279-281) */
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* `stream` is a cudaStream_t (NULL = the library creates its own non-blocking stream). */
+int  s2s_ctx_create(int device, void* stream, s2s_ctx** out);
+int  s2s_ctx_destroy(s2s_ctx* ctx);
+int  s2s_ctx_set_stream(s2s_ctx* ctx, void* stream);
+int  s2s_ctx_synchronize(s2s_ctx* ctx);
+const char* s2s_last_error(void);
+int  s2s_version(void);
+/* number of kernels launched by this context since creation (bench.py `gpu_launches`) */
+int64_t s2s_ctx_launch_count(s2s_ctx* ctx);
+/* enable (1) / disable (0) CUDA-graph replay of s2s_model_fwdbwd for repeated shapes */
+int  s2s_ctx_set_graphs(s2s_ctx* ctx, int enable);
+
+/* ---- flat parameter layout (what module:getParameters() flattens to; timit/timit.lua:172) -- */
+int64_t s2s_param_count(const s2s_model_cfg* cfg);
+/* writes (offset, rows, cols) triples in flat order into out_host[3*max]; returns the count */
+int     s2s_param_segments(const s2s_model_cfg* cfg, int64_t* out_host, int max);
+/* offset of the first decoder (nn.Attention) parameter = W_V */
+int64_t s2s_decoder_param_offset(const s2s_model_cfg* cfg);
+
+/* ---- nn.TemporalConvolutionZeroBias, kW = 1 (TemporalConvolutionZeroBias.lua:37-54) -------- */
+/* updateOutput:  y[rows,out] = x[rows,in] . W[out,in]^T   (bias pinned to zero, :38)           */
+int s2s_tconv_zb_forward(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out, float* y);
+/* updateGradInput + accGradParameters: dx[rows,in] = dy . W (overwritten; NULL = skip),
+ * dW[out,in] += scale * dy^T . x (NULL = skip); gradBias stays zero (:52-53)                   */
+int s2s_tconv_zb_backward(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out,
+                          const float* dy, float* dx, float* dW, float scale);
+
+/* ---- nn.LinearZeroBias (LinearZeroBias.lua:31-74) ------------------------------------------ */
+int s2s_linear_zb_forward(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out, float* y);
+int s2s_linear_zb_backward(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out,
+                           const float* dy, float* dx, float* dW, float scale);
+
+/* ---- nn.RNN(nn.GRU(in,out), reverse) over whole utterances (RNN.lua:120-201, GRU.lua:8-51) -- */
+/* W: the three LinearZeroBias weights (z, r, h~) each [H, H+Din], concat order {prev_h, x}
+ * (GRU.lua:22-26), contiguous in that order.  ndir = 1: one direction given by `reverse`;
+ * ndir = 2: W holds forward then reverse weights (6 matrices) and the outputs land in the two
+ * halves of y as JoinTable(2,2) does (model_chorowski_baseline.lua:24).
+ * x [B,Lmax,Din] (row stride ldx), y [B,Lmax,ndir*H].  State needed by backward is kept in
+ * `save` (caller-provided, s2s_gru_seq_save_floats(...) floats). */
+int64_t s2s_gru_seq_save_floats(int B, int Lmax, int H, int ndir);
+int s2s_gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int reverse,
+                        const float* x, int ldx, const int* lengths, int B, int Lmax,
+                        float* y, float* save);
+/* dy [B,Lmax,ndir*H] -> dx [B,Lmax,Din] (overwritten; NULL = skip); dW accumulated (same layout as W) */
+int s2s_gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, int ndir, int reverse,
+                         const float* x, int ldx, const int* lengths, int B, int Lmax,
+                         const float* y, const float* save, const float* dy, float* dx);
+
+/* ---- nn.Attention (Attention.lua:305-327) = Vh + nn.RNNAttention(nn.Recurrent(decoder_base_)) */
+/* updateOutput: teacher-forced decoder over Tmax steps (RNNAttention.lua:144-185).
+ * P = flat parameter vector of the WHOLE model (decoder segments located through cfg).
+ * dropmask: NULL or [B,Tmax,ST+A] multiplicative mask on {s,c} before the Maxout
+ * (model_chorowski_baseline_dropout.lua:56).  lambda = monotonic-alignment penalty weight
+ * (MonotonicAlignment.lua:19-77).  logp [B,Tmax,V].  Forward state (alpha, s, c, Ws, Vh, ...)
+ * is kept inside ctx for the matching backward and for s2s_attention_get. */
+int s2s_attention_forward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P,
+                          const float* h, const int* lengths, int B, int Lmax,
+                          const int* labels, const int* tlens, int Tmax,
+                          const float* dropmask, float lambda, float* logp);
+/* updateGradInput (+ parameter gradients, which the reference accumulates inside
+ * updateGradInput: Attention.lua:325, Recurrent.lua:148).  Must follow the forward with the
+ * same arguments.  dlogp [B,Tmax,V]; G (flat, whole model) is ACCUMULATED; dh [B,Lmax,A]
+ * overwritten. */
+int s2s_attention_backward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, float* G,
+                           const float* h, const int* lengths, int B, int Lmax,
+                           const int* labels, const int* tlens, int Tmax,
+                           const float* dropmask, float lambda, const float* dlogp, float* dh);
+/* introspection used by the reference's callers (Attention.lua:214-250, timit/timit.lua:521) */
+#define S2S_GET_ALPHA    0   /* decoder:alpha()   [B,Tmax,Lmax] */
+#define S2S_GET_WS       1   /* decoder:Ws()      [B,Tmax,S]    */
+#define S2S_GET_VH       2   /* decoder.Vh.output [B,Lmax,S]    */
+#define S2S_GET_PENALTY  3   /* decoder:penalty() [B,Tmax]      */
+#define S2S_GET_STATE    4   /* s_t               [B,Tmax,ST]   */
+#define S2S_GET_CONTEXT  5   /* c_t               [B,Tmax,A]    */
+int s2s_attention_get(s2s_ctx* ctx, int what, float* dst);
+
+/* One decoder step with explicit hidden state in/out = decoder_base:forward (Attention.lua:366,402),
+ * the building block of Attention:BeamSearch.  Vh must have been computed (s2s_tconv_zb_forward
+ * with W_V).  yprev[B] = previous label (-1 = zeros_y, RNNAttention.lua:173); alpha_prev / s_prev
+ * NULL = zeros (Recurrent.lua:112). */
+int s2s_attention_step(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P,
+                       const float* h, const float* Vh, const int* lengths, int B, int Lmax,
+                       const int* yprev, const float* alpha_prev, const float* s_prev,
+                       float* alpha, float* s, float* logp);
+/* Attention:BeamSearch (Attention.lua:332-438) for one utterance, beams batched on the device.
+ * h [L,A]; writes up to maxlen labels to out_host; returns the length through n_out_host. */
+int s2s_beam_search(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, const float* h, int L,
+                    int eos, int beam, int maxlen, int* out_host, int* n_out_host, float* logp_out_host);
+
+/* ---- whole model: encoder -> nn.Attention -> loss (timit/timit.lua:262-282) ------------------ */
+/* forward only: nll [B] (device), logp [B,Tmax,V] (NULL = not wanted) */
+int s2s_model_forward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P,
+                      const float* X, const int* lengths, int B, int Lmax,
+                      const int* labels, const int* tlens, int Tmax,
+                      const float* dropmask, float lambda, int flags, float* nll, float* logp);
+/* forward + backward of a minibatch; G (flat) is ACCUMULATED (caller zeroes it, as
+ * autoencoder:zeroGradParameters() does, timit.lua:233); dX NULL or [B,Lmax,D]. */
+int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, float* G,
+                     const float* X, const int* lengths, int B, int Lmax,
+                     const int* labels, const int* tlens, int Tmax,
+                     const float* dropmask, float lambda, int flags,
+                     float* nll, float* logp, float* dX);
+/* encoder annotations of the last model call [B,Lmax,A] (encoder.output, timit.lua:397) */
+int s2s_model_get_annotations(s2s_ctx* ctx, float* dst);
+
+/* ---- weight noise (WeightNoise.lua:17-35, AdaptiveWeightNoise.lua:27-104) ------------------- */
+/* eps: injected N(0,1) buffer [n] for parity; NULL = Philox counter RNG seeded by (seed, call counter) */
+int s2s_weightnoise_sample(s2s_ctx* ctx, const float* w, const float* eps, uint64_t seed, float sigma, int64_t n, float* sample);
+/* weight = [mu ; s = log sigma^2] (2n) */
+int s2s_awn_sample(s2s_ctx* ctx, const float* weight, const float* eps, uint64_t seed, int64_t n, float* sample);
+/* L = lambda*KL + nll (AdaptiveWeightNoise.lua:63-80); result written to *L_host (synchronises) */
+int s2s_awn_forward(s2s_ctx* ctx, const float* weight, int64_t n, double lambda, double nll, double* L_host);
+/* gradWeight [2n] overwritten (AdaptiveWeightNoise.lua:82-104); g = dNLL/dw [n] */
+int s2s_awn_accgrad(s2s_ctx* ctx, const float* weight, const float* g, int64_t n, double lambda, float* gradWeight);
+
+/* ---- gradient step (timit/timit.lua:291-348, TrainUtils.lua:52-104, optim.adadelta) ---------- */
+/* g /= batch ; norm ; clip to maxnorm ; g += wd*p ; g += noise_sigma*N(0,1).  The pre-clip norm is
+ * written to *gradnorm_host (synchronises) unless NULL. */
+int s2s_grad_finalize(s2s_ctx* ctx, float* g, const float* p, int64_t n, int batch, double maxnorm, double wd,
+                      const float* noise, uint64_t seed, double noise_sigma, double* gradnorm_host);
+int s2s_adadelta(s2s_ctx* ctx, float* x, const float* g, float* v, float* a, int64_t n, double rho, double eps);
+/* TrainUtils.columnNormConstraint on one weight matrix (per-ROW L2 norm; TrainUtils.lua:63-85).
+ * *nan_host = 1 if a NaN row norm was seen (the reference error()s, :61). */
+int s2s_rownorm_constraint(s2s_ctx* ctx, float* W, int64_t rows, int64_t cols, double maxval, int* nan_host);
+/* columnNormConstraintGraph over every weight matrix of the model (timit.lua:346-348) */
+int s2s_model_rownorm_constraint(s2s_ctx* ctx, const s2s_model_cfg* cfg, float* P, double maxval, int* nan_host);
+
+/* ---- test hooks (not part of the reference surface) ----------------------------------------- */
+/* C = alpha * op(A) . op(B) + beta * C (+ bias[n]);  op(A) = A[M,K] (tA=0) or A[K,M]^T (tA=1);
+ * op(B) = B[K,N] (tB=0) or B[N,K]^T (tB=1).  impl: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 */
+int s2s_gemm_f32(s2s_ctx* ctx, int impl, int tA, int tB, int M, int N, int K, float alpha,
+                 const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc, const float* bias);
+/* one attention scoring step (score + softmax + context), forward: the K1 microbenchmark kernel */
+int s2s_attn_step_forward(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w,
+                          const int* lengths, int B, int Lmax, int S, int A, float* alpha, float* c);
+/* backward of the same step (K2): given dc [B,A], dalpha_in [B,Lmax] (NULL = 0) -> dq [B,S], de [B,Lmax] */
+int s2s_attn_step_backward(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w,
+                           const int* lengths, int B, int Lmax, int S, int A, const float* alpha,
+                           const float* dc, const float* dalpha_in, float* dq, float* de);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2S_B200_H */

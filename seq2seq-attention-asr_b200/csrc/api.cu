@@ -1,0 +1,193 @@
+// api.cu -- extern "C" entry points of libs2s_b200.so (declared in include/s2s_b200.h).
+// Each wrapper validates arguments, resets the per-call scratch arena and forwards to the engine.
+#include "attention.cuh"
+#include "common.cuh"
+#include "decoder.cuh"
+#include "gru_seq.cuh"
+#include "model.cuh"
+
+using namespace s2s;
+
+namespace s2s {
+int beam_search_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, int L, int eos, int beam, int maxlen,
+                     int* out_host, int* n_out_host, float* logp_out_host);
+int attention_step_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const float* Vh, const int* lengths, int B, int Lmax,
+                        const int* yprev, const float* alpha_prev, const float* s_prev, float* alpha, float* s, float* logp);
+}
+
+extern "C" {
+
+int s2s_ctx_destroy(s2s_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->arena.release();
+    ctx->persist.release();
+    if (ctx->counters) cudaFree(ctx->counters);
+    for (int i = 0; i < 2; i++) if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->dec;
+    delete ctx->model;
+    delete ctx;
+    return 0;
+}
+
+// ---- TemporalConvolutionZeroBias / LinearZeroBias ------------------------------------------------
+static int dense_fwd(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out, float* y) {
+    S2S_REQUIRE(ctx && x && W && y, "null argument");
+    S2S_REQUIRE(rows > 0 && rows < (1ll << 31) && in > 0 && out > 0, "bad shape rows=%ld in=%d out=%d", (long)rows, in, out);
+    ctx->arena.reset();
+    return gemm_f32(ctx, false, true, (int)rows, out, in, 1.f, x, in, W, in, 0.f, y, out);
+}
+static int dense_bwd(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out, const float* dy, float* dx, float* dW, float scale) {
+    S2S_REQUIRE(ctx && x && W && dy, "null argument");
+    S2S_REQUIRE(rows > 0 && rows < (1ll << 31) && in > 0 && out > 0, "bad shape rows=%ld in=%d out=%d", (long)rows, in, out);
+    ctx->arena.reset();
+    if (dx) S2S_TRY(gemm_f32(ctx, false, false, (int)rows, in, out, 1.f, dy, out, W, in, 0.f, dx, in));
+    if (dW) S2S_TRY(gemm_f32(ctx, true, false, out, in, (int)rows, scale, dy, out, x, in, 1.f, dW, in, nullptr, GemmBatch(), rows >= 4096 ? 8 : 1));
+    return 0;
+}
+int s2s_tconv_zb_forward(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out, float* y) { return dense_fwd(ctx, x, rows, in, W, out, y); }
+int s2s_tconv_zb_backward(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out, const float* dy, float* dx, float* dW, float scale) {
+    return dense_bwd(ctx, x, rows, in, W, out, dy, dx, dW, scale);
+}
+int s2s_linear_zb_forward(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out, float* y) { return dense_fwd(ctx, x, rows, in, W, out, y); }
+int s2s_linear_zb_backward(s2s_ctx* ctx, const float* x, int64_t rows, int in, const float* W, int out, const float* dy, float* dx, float* dW, float scale) {
+    return dense_bwd(ctx, x, rows, in, W, out, dy, dx, dW, scale);
+}
+
+// ---- nn.RNN(nn.GRU) ---------------------------------------------------------------------------
+int64_t s2s_gru_seq_save_floats(int B, int Lmax, int H, int ndir) { return (int64_t)B * Lmax * ndir * 4 * H; }
+int s2s_gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int reverse, const float* x, int ldx,
+                        const int* lengths, int B, int Lmax, float* y, float* save) {
+    S2S_REQUIRE(ctx && W && x && y && save, "gru_seq_forward: null argument");
+    S2S_REQUIRE(B > 0 && Lmax > 0 && Din > 0 && ldx >= Din, "gru_seq_forward: bad shape");
+    ctx->arena.reset();
+    return gru_seq_forward(ctx, W, Din, H, ndir, reverse, x, ldx, lengths, B, Lmax, y, save);
+}
+int s2s_gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, int ndir, int reverse, const float* x, int ldx,
+                         const int* lengths, int B, int Lmax, const float* y, const float* save, const float* dy, float* dx) {
+    S2S_REQUIRE(ctx && W && dW && x && y && save && dy, "gru_seq_backward: null argument");
+    S2S_REQUIRE(B > 0 && Lmax > 0 && Din > 0 && ldx >= Din, "gru_seq_backward: bad shape");
+    S2S_REQUIRE(dx == nullptr || ldx == Din, "gru_seq_backward: dx requires a dense x (ldx == Din)");
+    ctx->arena.reset();
+    return gru_seq_backward(ctx, W, dW, Din, H, ndir, reverse, x, ldx, lengths, B, Lmax, y, save, dy, dx);
+}
+
+// ---- nn.Attention -----------------------------------------------------------------------------
+int s2s_attention_forward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, const float* h, const int* lengths, int B, int Lmax,
+                          const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda, float* logp) {
+    S2S_REQUIRE(ctx && P && h && labels && logp, "attention_forward: null argument");
+    Layout Y;
+    S2S_TRY(make_layout(cfg, &Y));
+    ctx->arena.reset();
+    ctx->persist.reset();
+    if (ctx->model) ctx->model->valid = false;
+    return decoder_forward(ctx, Y, P, h, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, logp);
+}
+int s2s_attention_backward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, float* G, const float* h, const int* lengths, int B,
+                           int Lmax, const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda,
+                           const float* dlogp, float* dh) {
+    S2S_REQUIRE(ctx && P && G && h && labels && dlogp && dh, "attention_backward: null argument");
+    Layout Y;
+    S2S_TRY(make_layout(cfg, &Y));
+    ctx->arena.reset();
+    return decoder_backward(ctx, Y, P, G, h, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, dlogp, dh);
+}
+int s2s_attention_get(s2s_ctx* ctx, int what, float* dst) {
+    S2S_REQUIRE(ctx && dst, "attention_get: null argument");
+    S2S_REQUIRE(ctx->dec && ctx->dec->valid, "attention_get: no forward state on this context");
+    DecoderState& d = *ctx->dec;
+    const size_t BT = (size_t)d.B * d.T;
+    const Layout& Y = d.Y;
+    cudaStream_t st = ctx->stream;
+    switch (what) {
+        case S2S_GET_ALPHA: S2S_CUDA(cudaMemcpyAsync(dst, d.alpha, BT * d.Lmax * 4, cudaMemcpyDeviceToDevice, st)); break;
+        case S2S_GET_WS: S2S_CUDA(cudaMemcpyAsync(dst, d.q, BT * Y.S * 4, cudaMemcpyDeviceToDevice, st)); break;
+        case S2S_GET_VH: S2S_CUDA(cudaMemcpyAsync(dst, d.Vh, (size_t)d.B * d.Lmax * Y.S * 4, cudaMemcpyDeviceToDevice, st)); break;
+        case S2S_GET_PENALTY: S2S_CUDA(cudaMemcpyAsync(dst, d.pen, BT * 4, cudaMemcpyDeviceToDevice, st)); break;
+        case S2S_GET_STATE:
+            S2S_CUDA(cudaMemcpy2DAsync(dst, (size_t)Y.ST * 4, d.sc, (size_t)(Y.ST + Y.A) * 4, (size_t)Y.ST * 4, BT, cudaMemcpyDeviceToDevice, st));
+            break;
+        case S2S_GET_CONTEXT:
+            S2S_CUDA(cudaMemcpy2DAsync(dst, (size_t)Y.A * 4, d.sc + Y.ST, (size_t)(Y.ST + Y.A) * 4, (size_t)Y.A * 4, BT, cudaMemcpyDeviceToDevice, st));
+            break;
+        default: return fail("attention_get: unknown selector %d", what);
+    }
+    return 0;
+}
+int s2s_attention_step(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, const float* h, const float* Vh, const int* lengths, int B,
+                       int Lmax, const int* yprev, const float* alpha_prev, const float* s_prev, float* alpha, float* s, float* logp) {
+    S2S_REQUIRE(ctx && P && h && Vh && alpha && s && logp, "attention_step: null argument");
+    Layout Y;
+    S2S_TRY(make_layout(cfg, &Y));
+    ctx->arena.reset();
+    return attention_step_impl(ctx, Y, P, h, Vh, lengths, B, Lmax, yprev, alpha_prev, s_prev, alpha, s, logp);
+}
+int s2s_beam_search(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, const float* h, int L, int eos, int beam, int maxlen,
+                    int* out_host, int* n_out_host, float* logp_out_host) {
+    S2S_REQUIRE(ctx && P && h && out_host && n_out_host, "beam_search: null argument");
+    Layout Y;
+    S2S_TRY(make_layout(cfg, &Y));
+    ctx->arena.reset();
+    return beam_search_impl(ctx, Y, P, h, L, eos, beam, maxlen, out_host, n_out_host, logp_out_host);
+}
+
+// ---- whole model -------------------------------------------------------------------------------
+int s2s_model_forward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, const float* X, const int* lengths, int B, int Lmax,
+                      const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda, int flags, float* nll, float* logp) {
+    S2S_REQUIRE(ctx && P && X && labels, "model_forward: null argument");
+    Layout Y;
+    S2S_TRY(make_layout(cfg, &Y));
+    ctx->arena.reset();
+    ctx->persist.reset();
+    return model_forward(ctx, Y, P, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, nll, logp);
+}
+int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, float* G, const float* X, const int* lengths, int B, int Lmax,
+                     const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda, int flags, float* nll,
+                     float* logp, float* dX) {
+    S2S_REQUIRE(ctx && P && G && X && labels, "model_fwdbwd: null argument");
+    Layout Y;
+    S2S_TRY(make_layout(cfg, &Y));
+    ctx->arena.reset();
+    ctx->persist.reset();
+    S2S_TRY(model_forward(ctx, Y, P, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, nll, logp));
+    return model_backward(ctx, Y, P, G, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, dX);
+}
+int s2s_model_get_annotations(s2s_ctx* ctx, float* dst) {
+    S2S_REQUIRE(ctx && dst, "model_get_annotations: null argument");
+    S2S_REQUIRE(ctx->model && ctx->model->valid, "model_get_annotations: no forward state on this context");
+    ModelState& m = *ctx->model;
+    S2S_CUDA(cudaMemcpyAsync(dst, m.acts[m.Y.NL], (size_t)m.B * m.Lmax * m.Y.A * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+// ---- test hooks --------------------------------------------------------------------------------
+int s2s_gemm_f32(s2s_ctx* ctx, int impl, int tA, int tB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                 int ldb, float beta, float* C, int ldc, const float* bias) {
+    S2S_REQUIRE(ctx && A && B && C, "gemm: null argument");
+    ctx->arena.reset();
+    return gemm_f32(ctx, tA != 0, tB != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, GemmBatch(), 1, impl);
+}
+int s2s_attn_step_forward(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w, const int* lengths, int B, int Lmax,
+                          int S, int A, float* alpha, float* c) {
+    S2S_REQUIRE(ctx && Vh && h && q && w && alpha && c, "attn_step_forward: null argument");
+    ctx->arena.reset();
+    AttnScratch sc;
+    S2S_TRY(attn_scratch_alloc(ctx, ctx->arena, B, Lmax, S, A, 0, false, &sc));
+    AttnLoc loc;
+    return attn_step_fwd(ctx, sc, Vh, h, q, S, w, lengths, B, Lmax, S, A, loc, alpha, Lmax, c, A, nullptr, 0, 0.f, nullptr, 0);
+}
+int s2s_attn_step_backward(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w, const int* lengths, int B,
+                           int Lmax, int S, int A, const float* alpha, const float* dc, const float* dalpha_in, float* dq, float* de) {
+    S2S_REQUIRE(ctx && Vh && h && q && w && alpha && dc && dq && de, "attn_step_backward: null argument");
+    ctx->arena.reset();
+    AttnScratch sc;
+    S2S_TRY(attn_scratch_alloc(ctx, ctx->arena, B, Lmax, S, A, 0, true, &sc));
+    AttnLoc loc;
+    return attn_step_bwd(ctx, sc, Vh, h, q, S, w, lengths, B, Lmax, S, A, loc, alpha, Lmax, dc, A, dalpha_in, Lmax, nullptr, 0, 0.f,
+                         dq, S, de, Lmax, nullptr, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,651 @@
+// attention.cu -- the location-aware / content attention step of nn.Attention as three fused,
+// HBM-bound sm_100a kernels.
+//
+// Reference semantics (per utterance, per decoder step; Attention.lua:65-135):
+//     Z[l,:] = q + Vh[l,:] (+ U F[l,:])        e[l] = w . tanh(Z[l,:])
+//     alpha  = softmax_l(e)                     c    = sum_l alpha[l] h[l,:]
+// The reference materialises ~20 [L,S] temporaries per step; here one launch reads Vh and h exactly
+// once per step (the algorithmic minimum, A_f = 4 B (L S + L A + 2L + S + A) bytes):
+//
+//   attn_fwd_kernel   grid (ceil(Lmax/32), B): a CTA owns 32 encoder frames of one utterance.
+//                     The h tile is fetched by ONE 1-D bulk-TMA copy (cp.async.bulk -> smem,
+//                     mbarrier complete_tx) issued before the scoring phase so it lands while the
+//                     warps stream Vh rows through registers (128-bit ld.global.nc, L1 no-allocate)
+//                     and reduce e[l] with warp shuffles.  Chunk-local softmax statistics and the
+//                     partial context are combined flash-decoding style by the LAST CTA of the
+//                     utterance to arrive (atomic ticket), so there is no second launch.
+//   attn_bwd_kernel   same tiling, single pass: because de = alpha (dalpha - <alpha,dalpha>) is
+//                     affine in the not-yet-known dot product, each chunk accumulates the two
+//                     vectors P1 = sum_l alpha dalpha g_l and P2 = sum_l alpha g_l
+//                     (g_l = w (1 - tanh^2 Z_l)); the last CTA forms dq = P1 - dot P2 and de.
+//   attn_dvh_kernel   deferred accumulation: dVh = sum_t de_t g_t in one pass after the time loop
+//                     (replaces the reference's per-step [L,S]+[L,A] read-modify-write,
+//                     RNNAttention.lua:247), tanh recomputed instead of stored.
+//
+// The location term is folded: U (W_F * alpha_pad + b_F) = UW * alpha_pad + Ub with UW = U W_F
+// ([KF,S], built once per call), i.e. KF instead of K FMAs per element and no F temporary.
+#include "attention.cuh"
+
+namespace s2s {
+
+constexpr int ATT_MAXCH = 128;   // Lmax <= 4096
+constexpr int LOC_MAXKF = 16;
+
+struct AttnFwdParams {
+    const float *Vh, *h, *q, *w;
+    int64_t ldq;
+    const int* lengths;
+    int B, Lmax, nch;
+    // location
+    int KF, padl;
+    const float *uw, *alpha_prev;
+    int64_t ld_aprev;
+    // scratch
+    float *E, *part_ms, *part_c;
+    unsigned* counters;
+    // outputs
+    float *alpha, *c, *pen;
+    int64_t ld_alpha, ld_c, ld_pen;
+    float lambda;
+    const float* app;   // alpha_{t-1} for the penalty
+    int64_t ld_app;
+};
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4fma(float s, float4 a, float4 b) { return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w)); }
+
+template <int NS, int NA, bool LOC>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_kernel(const AttnFwdParams p) {
+    constexpr int S = NS * 128, A = NA * 128;
+    constexpr int GROUPS = 8 / NA;              // row groups in the context phase
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* hs = reinterpret_cast<float*>(smem_raw);                 // [ATT_R][A]
+    float* uw_s = hs + ATT_R * A;                                    // [KF][S]        (LOC)
+    float* ap_s = uw_s + (LOC ? p.KF * S : 0);                       // [ATT_R+KF-1]   (LOC)
+    __shared__ float e_s[ATT_R], p_s[ATT_R];
+    __shared__ __align__(16) float red[1024];
+    __shared__ float scl_s[ATT_MAXCH];
+    __shared__ float wred[8];
+    __shared__ uint64_t bar;
+    __shared__ int is_last;
+
+    const int b = blockIdx.y, ch = blockIdx.x;
+    const int Lb = p.lengths ? p.lengths[b] : p.Lmax;
+    const int l0 = ch * ATT_R;
+    if (l0 >= Lb) return;
+    const int nrows = min(ATT_R, Lb - l0);
+    const int nchb = (Lb + ATT_R - 1) / ATT_R;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned bytes = (unsigned)nrows * A * 4u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(hs, p.h + ((size_t)b * p.Lmax + l0) * A, bytes, &bar);
+    }
+    if (LOC) {
+        for (int i = tid; i < p.KF * S; i += ATT_THREADS) uw_s[i] = p.uw[i];
+        for (int x = tid; x < ATT_R + p.KF - 1; x += ATT_THREADS) {
+            int l = l0 + x - p.padl;
+            ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
+        }
+        __syncthreads();
+    }
+
+    // ---- scoring: warp per row, 4 rows per warp, all Vh loads issued up front -----------------
+    float4 qv[NS], wv[NS];
+    {
+        const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
+#pragma unroll
+        for (int i = 0; i < NS; i++) { qv[i] = ldg4(qb + i * 128); wv[i] = ldg4(p.w + lane * 4 + i * 128); }
+    }
+    const float* vbase = p.Vh + ((size_t)b * p.Lmax + l0) * S + lane * 4;
+    float4 v[4][NS];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int r = warp + 8 * j;
+        if (r < nrows) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) v[j][i] = ldg_stream(vbase + (size_t)r * S + i * 128);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int r = warp + 8 * j;
+        if (r < nrows) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                float4 z = f4add(v[j][i], qv[i]);
+                if (LOC) {
+                    for (int jj = 0; jj < p.KF; jj++) {
+                        const float a = ap_s[r + jj];
+                        const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
+                        z = f4fma(a, u, z);
+                    }
+                }
+                acc = fmaf(wv[i].x, tanh_acc(z.x), acc);
+                acc = fmaf(wv[i].y, tanh_acc(z.y), acc);
+                acc = fmaf(wv[i].z, tanh_acc(z.z), acc);
+                acc = fmaf(wv[i].w, tanh_acc(z.w), acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) e_s[r] = acc;
+        }
+    }
+    __syncthreads();
+
+    // ---- chunk-local softmax statistics ---------------------------------------------------------
+    {
+        const float ev = lane < nrows ? e_s[lane] : -INFINITY;
+        const float m = warp_max(ev);
+        const float pv = lane < nrows ? expf(ev - m) : 0.f;
+        const float ssum = warp_sum(pv);
+        if (warp == 0) {
+            p_s[lane] = pv;
+            if (lane < nrows) p.E[(size_t)b * p.Lmax + l0 + lane] = ev;
+            if (lane == 0) {
+                p.part_ms[((size_t)b * p.nch + ch) * 2 + 0] = m;
+                p.part_ms[((size_t)b * p.nch + ch) * 2 + 1] = ssum;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- partial context from the TMA-staged h tile ---------------------------------------------
+    mbar_wait(&bar, 0);
+    {
+        const int g = tid / (A / 4), c4 = tid % (A / 4);
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* hs4 = reinterpret_cast<const float4*>(hs);
+        for (int r = g; r < nrows; r += GROUPS) acc4 = f4fma(p_s[r], hs4[r * (A / 4) + c4], acc4);
+        if (GROUPS > 1) {
+            float4* red4 = reinterpret_cast<float4*>(red);
+            red4[g * (A / 4) + c4] = acc4;
+            __syncthreads();
+            if (tid < A / 4) {
+                float4 s4 = red4[tid];
+#pragma unroll
+                for (int gg = 1; gg < GROUPS; gg++) s4 = f4add(s4, red4[gg * (A / 4) + tid]);
+                *reinterpret_cast<float4*>(p.part_c + ((size_t)b * p.nch + ch) * A + tid * 4) = s4;
+            }
+        } else {
+            *reinterpret_cast<float4*>(p.part_c + ((size_t)b * p.nch + ch) * A + tid * 4) = acc4;
+        }
+    }
+
+    // ---- ticket: the last CTA of this utterance combines ---------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(&p.counters[b], 1u);
+        is_last = (prev == (unsigned)(nchb - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    float M = -INFINITY;
+    for (int c = lane; c < nchb; c += 32) M = fmaxf(M, ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2));
+    M = warp_max(M);
+    float den = 0.f;
+    for (int c = lane; c < nchb; c += 32) {
+        const float mc = ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2);
+        const float sc = ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2 + 1);
+        den += sc * expf(mc - M);
+    }
+    den = warp_sum(den);
+    const float inv = 1.0f / den;
+    if (warp == 0)
+        for (int c = lane; c < nchb; c += 32) scl_s[c] = expf(ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2) - M) * inv;
+    __syncthreads();
+
+    float penacc = 0.f;
+    for (int l = tid; l < p.Lmax; l += ATT_THREADS) {
+        float a = 0.f;
+        if (l < Lb) {
+            a = expf(ldcg1(p.E + (size_t)b * p.Lmax + l) - M) * inv;
+            if (p.pen) {
+                const float ap = p.app ? p.app[(size_t)b * p.ld_app + l] : 0.f;
+                penacc += (float)(Lb - l) * (a - ap);
+            }
+        }
+        p.alpha[(size_t)b * p.ld_alpha + l] = a;
+    }
+    for (int a4 = tid; a4 < A / 4; a4 += ATT_THREADS) {
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < nchb; c++) acc4 = f4fma(scl_s[c], ldcg4(p.part_c + ((size_t)b * p.nch + c) * A + a4 * 4), acc4);
+        *reinterpret_cast<float4*>(p.c + (size_t)b * p.ld_c + a4 * 4) = acc4;
+    }
+    if (p.pen) {
+        penacc = warp_sum(penacc);
+        if (lane == 0) wred[warp] = penacc;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; i++) t += wred[i];
+            p.pen[(size_t)b * p.ld_pen] = p.lambda * fmaxf(t, 0.f);
+        }
+    }
+    if (tid == 0) p.counters[b] = 0u;
+}
+
+// =================================================================================================
+struct AttnBwdParams {
+    const float *Vh, *h, *q, *w;
+    int64_t ldq;
+    const int* lengths;
+    int B, Lmax, nch;
+    int KF, padl;
+    const float *uw, *alpha_prev;
+    int64_t ld_aprev;
+    const float *alpha, *dc, *dalpha_in, *pen;
+    int64_t ld_alpha, ld_dc, ld_dain, ld_pen;
+    float lambda;
+    float *dalpha_s, *part_P, *part_dot, *V1;
+    unsigned* counters;
+    float *dq, *de, *dalpha_prev;
+    int64_t ld_dq, ld_de, ld_dap;
+};
+
+template <int NS, int NA, bool LOC>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_kernel(const AttnBwdParams p) {
+    constexpr int S = NS * 128, A = NA * 128;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* red = reinterpret_cast<float*>(smem_raw);            // [8][2][S]
+    float* uw_s = red + 8 * 2 * S;                               // [KF][S]      (LOC)
+    float* ap_s = uw_s + (LOC ? p.KF * S : 0);                   // [ATT_R+KF-1] (LOC)
+    __shared__ float dot_s[8];
+    __shared__ int is_last;
+
+    const int b = blockIdx.y, ch = blockIdx.x;
+    const int Lb = p.lengths ? p.lengths[b] : p.Lmax;
+    const int l0 = ch * ATT_R;
+    if (l0 >= Lb) return;
+    const int nrows = min(ATT_R, Lb - l0);
+    const int nchb = (Lb + ATT_R - 1) / ATT_R;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (LOC) {
+        for (int i = tid; i < p.KF * S; i += ATT_THREADS) uw_s[i] = p.uw[i];
+        for (int x = tid; x < ATT_R + p.KF - 1; x += ATT_THREADS) {
+            int l = l0 + x - p.padl;
+            ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
+        }
+        __syncthreads();
+    }
+
+    float4 qv[NS], wv[NS], dcv[NA];
+    {
+        const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
+#pragma unroll
+        for (int i = 0; i < NS; i++) { qv[i] = ldg4(qb + i * 128); wv[i] = ldg4(p.w + lane * 4 + i * 128); }
+        const float* db = p.dc + (size_t)b * p.ld_dc + lane * 4;
+#pragma unroll
+        for (int i = 0; i < NA; i++) dcv[i] = ldg4(db + i * 128);
+    }
+    const float pen_g = (p.pen && p.lambda != 0.f && p.pen[(size_t)b * p.ld_pen] > 0.f) ? p.lambda : 0.f;
+
+    float4 P1[NS], P2[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) { P1[i] = make_float4(0.f, 0.f, 0.f, 0.f); P2[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    float dotp = 0.f;
+
+    const float* hbase = p.h + ((size_t)b * p.Lmax + l0) * A + lane * 4;
+    const float* vbase = p.Vh + ((size_t)b * p.Lmax + l0) * S + lane * 4;
+    // software pipeline: the loads of row j+1 are in flight while row j is reduced
+    float4 hv[2][NA], vv[2][NS];
+    if (warp < nrows) {
+#pragma unroll
+        for (int i = 0; i < NA; i++) hv[0][i] = ldg_stream(hbase + (size_t)warp * A + i * 128);
+#pragma unroll
+        for (int i = 0; i < NS; i++) vv[0][i] = ldg_stream(vbase + (size_t)warp * S + i * 128);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int r = warp + 8 * j;
+        if (r >= nrows) break;
+        const int cur = j & 1, nxt = cur ^ 1;
+        if (j < 3 && r + 8 < nrows) {
+#pragma unroll
+            for (int i = 0; i < NA; i++) hv[nxt][i] = ldg_stream(hbase + (size_t)(r + 8) * A + i * 128);
+#pragma unroll
+            for (int i = 0; i < NS; i++) vv[nxt][i] = ldg_stream(vbase + (size_t)(r + 8) * S + i * 128);
+        }
+        const int l = l0 + r;
+        float da = 0.f;
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+            da = fmaf(hv[cur][i].x, dcv[i].x, da); da = fmaf(hv[cur][i].y, dcv[i].y, da);
+            da = fmaf(hv[cur][i].z, dcv[i].z, da); da = fmaf(hv[cur][i].w, dcv[i].w, da);
+        }
+        da = warp_sum(da);
+        if (p.dalpha_in) da += p.dalpha_in[(size_t)b * p.ld_dain + l];
+        da += pen_g * (float)(Lb - l);
+        const float a = p.alpha[(size_t)b * p.ld_alpha + l];
+        const float x = a * da;
+        dotp += x;
+        if (lane == 0) p.dalpha_s[(size_t)b * p.Lmax + l] = da;
+        float v1[LOC ? LOC_MAXKF : 1];
+        if (LOC) {
+#pragma unroll
+            for (int jj = 0; jj < LOC_MAXKF; jj++) v1[jj] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            float4 z = f4add(vv[cur][i], qv[i]);
+            if (LOC) {
+                for (int jj = 0; jj < p.KF; jj++) {
+                    const float ap = ap_s[r + jj];
+                    const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
+                    z = f4fma(ap, u, z);
+                }
+            }
+            float4 g;
+            { float t = tanh_acc(z.x); g.x = wv[i].x * (1.f - t * t); }
+            { float t = tanh_acc(z.y); g.y = wv[i].y * (1.f - t * t); }
+            { float t = tanh_acc(z.z); g.z = wv[i].z * (1.f - t * t); }
+            { float t = tanh_acc(z.w); g.w = wv[i].w * (1.f - t * t); }
+            P1[i] = f4fma(x, g, P1[i]);
+            P2[i] = f4fma(a, g, P2[i]);
+            if (LOC) {
+#pragma unroll
+                for (int jj = 0; jj < LOC_MAXKF; jj++) {
+                    if (jj < p.KF) {
+                        const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
+                        v1[jj] += g.x * u.x + g.y * u.y + g.z * u.z + g.w * u.w;
+                    }
+                }
+            }
+        }
+        if (LOC) {
+            // 16 values over 32 lanes: transpose-reduce; lane (x & 15) ends with value index (x & 15)
+#pragma unroll
+            for (int s = 8; s >= 1; s >>= 1) {
+#pragma unroll
+                for (int i = 0; i < s; i++) {
+                    const float send = (lane & s) ? v1[i] : v1[i + s];
+                    const float keep = (lane & s) ? v1[i + s] : v1[i];
+                    v1[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+            }
+            v1[0] += __shfl_xor_sync(0xffffffffu, v1[0], 16);
+            if (lane < p.KF) p.V1[((size_t)b * p.Lmax + l) * p.KF + lane] = v1[0];
+        }
+    }
+
+    // ---- cross-warp reduction of P1 / P2 / dot ---------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        *reinterpret_cast<float4*>(red + (warp * 2 + 0) * S + lane * 4 + i * 128) = P1[i];
+        *reinterpret_cast<float4*>(red + (warp * 2 + 1) * S + lane * 4 + i * 128) = P2[i];
+    }
+    if (lane == 0) dot_s[warp] = dotp;
+    __syncthreads();
+    for (int idx = tid; idx < 2 * S; idx += ATT_THREADS) {
+        float s = 0.f;
+#pragma unroll
+        for (int wg = 0; wg < 8; wg++) s += red[wg * 2 * S + idx];
+        p.part_P[((size_t)b * p.nch + ch) * 2 * S + idx] = s;
+    }
+    if (tid == 0) {
+        float s = 0.f;
+        for (int wg = 0; wg < 8; wg++) s += dot_s[wg];
+        p.part_dot[(size_t)b * p.nch + ch] = s;
+    }
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(&p.counters[b], 1u);
+        is_last = (prev == (unsigned)(nchb - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    float dot = 0.f;
+    for (int c = lane; c < nchb; c += 32) dot += ldcg1(p.part_dot + (size_t)b * p.nch + c);
+    dot = warp_sum(dot);
+    for (int i = tid; i < S; i += ATT_THREADS) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = 0; c < nchb; c++) {
+            s1 += ldcg1(p.part_P + ((size_t)b * p.nch + c) * 2 * S + i);
+            s2 += ldcg1(p.part_P + ((size_t)b * p.nch + c) * 2 * S + S + i);
+        }
+        p.dq[(size_t)b * p.ld_dq + i] = s1 - dot * s2;
+    }
+    for (int l = tid; l < p.Lmax; l += ATT_THREADS) {
+        float d = 0.f;
+        if (l < Lb) d = p.alpha[(size_t)b * p.ld_alpha + l] * (ldcg1(p.dalpha_s + (size_t)b * p.Lmax + l) - dot);
+        p.de[(size_t)b * p.ld_de + l] = d;
+    }
+    if (p.dalpha_prev) {
+        for (int l = tid; l < p.Lmax; l += ATT_THREADS) {
+            float d = 0.f;
+            if (l < Lb) {
+                d = -pen_g * (float)(Lb - l);
+                if (LOC) {
+                    for (int jj = 0; jj < p.KF; jj++) {
+                        const int x = l - jj + p.padl;      // frame whose window position jj looks at l
+                        if (x >= 0 && x < Lb) {
+                            const float dex = p.alpha[(size_t)b * p.ld_alpha + x] * (ldcg1(p.dalpha_s + (size_t)b * p.Lmax + x) - dot);
+                            d = fmaf(dex, ldcg1(p.V1 + ((size_t)b * p.Lmax + x) * p.KF + jj), d);
+                        }
+                    }
+                }
+            }
+            p.dalpha_prev[(size_t)b * p.ld_dap + l] = d;
+        }
+    }
+    if (tid == 0) p.counters[b] = 0u;
+}
+
+// =================================================================================================
+// deferred dVh / dw_e / dUW: thread per score column, DVH_R frames per CTA held in registers,
+// time loop outermost so q_t is read once per step.
+struct DvhParams {
+    const float *Vh, *q_all, *de_all, *w;
+    const int *lengths, *tlens;
+    int B, Lmax, T, S;
+    int KF, padl;
+    const float *uw, *alpha_all;    // alpha_all [B,T,Lmax]: alpha_t (alpha_{t-1} is row t-1; zeros for t = 0)
+    float *dVh, *dwe, *duw;
+};
+
+template <bool LOC>
+__global__ void __launch_bounds__(128)
+attn_dvh_kernel(const DvhParams p) {
+    extern __shared__ float sm[];
+    float* de_s = sm;                                         // [T][DVH_R]
+    float* ap_s = de_s + p.T * DVH_R;                         // [T][DVH_R+KF-1]  (LOC)
+    const int b = blockIdx.y, l0 = blockIdx.x * DVH_R, i = blockIdx.z * 128 + threadIdx.x;
+    const int Lb = p.lengths ? p.lengths[b] : p.Lmax;
+    const int Tb = p.tlens ? min(p.tlens[b], p.T) : p.T;
+    const int S = p.S;
+    float* out = p.dVh + ((size_t)b * p.Lmax + l0) * S + i;
+    if (l0 >= Lb) {
+        for (int r = 0; r < DVH_R && l0 + r < p.Lmax; r++) out[(size_t)r * S] = 0.f;
+        return;
+    }
+    const int nrows = min(DVH_R, Lb - l0);
+    for (int e = threadIdx.x; e < Tb * DVH_R; e += 128) {
+        const int t = e / DVH_R, r = e % DVH_R;
+        de_s[e] = r < nrows ? p.de_all[((size_t)b * p.T + t) * p.Lmax + l0 + r] : 0.f;
+    }
+    const int W = DVH_R + p.KF - 1;
+    if (LOC) {
+        for (int e = threadIdx.x; e < Tb * W; e += 128) {
+            const int t = e / W, x = e % W, l = l0 + x - p.padl;
+            ap_s[e] = (t > 0 && l >= 0 && l < Lb) ? p.alpha_all[((size_t)b * p.T + t - 1) * p.Lmax + l] : 0.f;
+        }
+    }
+    __syncthreads();
+
+    float v[DVH_R], acc[DVH_R];
+    const float* vb = p.Vh + ((size_t)b * p.Lmax + l0) * S + i;
+#pragma unroll
+    for (int r = 0; r < DVH_R; r++) { v[r] = r < nrows ? vb[(size_t)r * S] : 0.f; acc[r] = 0.f; }
+    const float wi = p.w[i];
+    float dw = 0.f;
+    float uwr[LOC ? LOC_MAXKF : 1], duwr[LOC ? LOC_MAXKF : 1];
+    if (LOC) {
+#pragma unroll
+        for (int jj = 0; jj < LOC_MAXKF; jj++) { uwr[jj] = jj < p.KF ? p.uw[jj * S + i] : 0.f; duwr[jj] = 0.f; }
+    }
+    const float* qb = p.q_all + (size_t)b * p.T * S + i;
+    for (int t = 0; t < Tb; t++) {
+        const float q = qb[(size_t)t * S];
+#pragma unroll
+        for (int r = 0; r < DVH_R; r++) {
+            const float d = de_s[t * DVH_R + r];
+            float z = q + v[r];
+            if (LOC) {
+#pragma unroll
+                for (int jj = 0; jj < LOC_MAXKF; jj++)
+                    if (jj < p.KF) z = fmaf(uwr[jj], ap_s[t * W + r + jj], z);
+            }
+            const float th = tanh_acc(z);
+            const float dz = d * wi * (1.f - th * th);
+            acc[r] += dz;
+            dw = fmaf(d, th, dw);
+            if (LOC) {
+#pragma unroll
+                for (int jj = 0; jj < LOC_MAXKF; jj++)
+                    if (jj < p.KF) duwr[jj] = fmaf(dz, ap_s[t * W + r + jj], duwr[jj]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < DVH_R; r++)
+        if (l0 + r < p.Lmax) out[(size_t)r * S] = r < nrows ? acc[r] : 0.f;
+    atomicAdd(p.dwe + i, dw);
+    if (LOC) {
+#pragma unroll
+        for (int jj = 0; jj < LOC_MAXKF; jj++)
+            if (jj < p.KF) atomicAdd(p.duw + jj * S + i, duwr[jj]);
+    }
+}
+
+// =================================================================================================
+// host wrappers
+// =================================================================================================
+int attn_scratch_alloc(s2s_ctx* ctx, Arena& arena, int B, int Lmax, int S, int A, int KF, bool backward, AttnScratch* sc) {
+    S2S_REQUIRE(Lmax <= ATT_MAXCH * ATT_R, "Lmax=%d exceeds the attention kernel limit %d", Lmax, ATT_MAXCH * ATT_R);
+    S2S_REQUIRE(B <= 4096, "B=%d exceeds the ticket-counter capacity 4096", B);
+    sc->nch = ceil_div(Lmax, ATT_R);
+    S2S_ALLOC(sc->E, arena, float, (size_t)B * Lmax);
+    S2S_ALLOC(sc->part_ms, arena, float, (size_t)B * sc->nch * 2);
+    S2S_ALLOC(sc->part_c, arena, float, (size_t)B * sc->nch * A);
+    if (backward) {
+        S2S_ALLOC(sc->dalpha, arena, float, (size_t)B * Lmax);
+        S2S_ALLOC(sc->part_P, arena, float, (size_t)B * sc->nch * 2 * S);
+        S2S_ALLOC(sc->part_dot, arena, float, (size_t)B * sc->nch);
+        if (KF > 0) S2S_ALLOC(sc->V1, arena, float, (size_t)B * Lmax * KF);
+    }
+    sc->counters = ctx->counters;
+    return 0;
+}
+
+template <int NS, int NA, bool LOC>
+static int launch_fwd(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
+    size_t smem = (size_t)ATT_R * NA * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
+    static bool attr_set = false;   // per instantiation
+    static size_t attr_smem = 0;
+    if (!attr_set || smem > attr_smem) {
+        S2S_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NS, NA, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true; attr_smem = smem;
+    }
+    attn_fwd_kernel<NS, NA, LOC><<<dim3(p.nch, p.B), ATT_THREADS, smem, ctx->stream>>>(p);
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+template <int NS, int NA, bool LOC>
+static int launch_bwd(s2s_ctx* ctx, const AttnBwdParams& p, int KF) {
+    size_t smem = (size_t)8 * 2 * NS * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
+    static bool attr_set = false;
+    static size_t attr_smem = 0;
+    if (!attr_set || smem > attr_smem) {
+        S2S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<NS, NA, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true; attr_smem = smem;
+    }
+    attn_bwd_kernel<NS, NA, LOC><<<dim3(p.nch, p.B), ATT_THREADS, smem, ctx->stream>>>(p);
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+#define ATT_DISPATCH(FN, LOCV, ...)                                                               \
+    do {                                                                                          \
+        const int ns__ = S / 128, na__ = A / 128;                                                 \
+        if (ns__ == 1 && na__ == 1) return FN<1, 1, LOCV>(__VA_ARGS__);                           \
+        if (ns__ == 1 && na__ == 2) return FN<1, 2, LOCV>(__VA_ARGS__);                           \
+        if (ns__ == 2 && na__ == 1) return FN<2, 1, LOCV>(__VA_ARGS__);                           \
+        if (ns__ == 2 && na__ == 2) return FN<2, 2, LOCV>(__VA_ARGS__);                           \
+        if (ns__ == 2 && na__ == 4) return FN<2, 4, LOCV>(__VA_ARGS__);                           \
+        if (ns__ == 4 && na__ == 2) return FN<4, 2, LOCV>(__VA_ARGS__);                           \
+        if (ns__ == 4 && na__ == 4) return FN<4, 4, LOCV>(__VA_ARGS__);                           \
+        return fail("attention kernels: unsupported (S=%d, A=%d); supported S,A in {128,256,512} with |log2(S/A)|<=1", S, A); \
+    } while (0)
+
+static int check_dims(int S, int A, int KF) {
+    S2S_REQUIRE(S % 128 == 0 && A % 128 == 0 && S >= 128 && A >= 128, "attention kernels need S and A to be multiples of 128 (S=%d A=%d)", S, A);
+    S2S_REQUIRE(KF >= 0 && KF <= LOC_MAXKF, "location filter size %d not supported (max %d)", KF, LOC_MAXKF);
+    return 0;
+}
+
+int attn_step_fwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const float* h, const float* q, int64_t ldq, const float* w,
+                  const int* lengths, int B, int Lmax, int S, int A, const AttnLoc& loc, float* alpha, int64_t ld_alpha, float* c,
+                  int64_t ld_c, float* pen, int64_t ld_pen, float lambda, const float* app, int64_t ld_app) {
+    S2S_TRY(check_dims(S, A, loc.KF));
+    AttnFwdParams p;
+    p.Vh = Vh; p.h = h; p.q = q; p.w = w; p.ldq = ldq; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.nch = sc.nch;
+    p.KF = loc.KF; p.padl = loc.padl; p.uw = loc.uw; p.alpha_prev = loc.alpha_prev; p.ld_aprev = loc.ld_aprev;
+    p.E = sc.E; p.part_ms = sc.part_ms; p.part_c = sc.part_c; p.counters = sc.counters;
+    p.alpha = alpha; p.c = c; p.pen = pen; p.ld_alpha = ld_alpha; p.ld_c = ld_c; p.ld_pen = ld_pen; p.lambda = lambda;
+    p.app = app; p.ld_app = ld_app;
+    if (loc.KF > 0) ATT_DISPATCH(launch_fwd, true, ctx, p, loc.KF);
+    else ATT_DISPATCH(launch_fwd, false, ctx, p, 0);
+}
+
+int attn_step_bwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const float* h, const float* q, int64_t ldq, const float* w,
+                  const int* lengths, int B, int Lmax, int S, int A, const AttnLoc& loc, const float* alpha, int64_t ld_alpha,
+                  const float* dc, int64_t ld_dc, const float* dalpha_in, int64_t ld_dain, const float* pen, int64_t ld_pen,
+                  float lambda, float* dq, int64_t ld_dq, float* de, int64_t ld_de, float* dalpha_prev, int64_t ld_dap) {
+    S2S_TRY(check_dims(S, A, loc.KF));
+    S2S_REQUIRE(sc.dalpha && sc.part_P, "attention scratch was not allocated for backward");
+    AttnBwdParams p;
+    p.Vh = Vh; p.h = h; p.q = q; p.w = w; p.ldq = ldq; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.nch = sc.nch;
+    p.KF = loc.KF; p.padl = loc.padl; p.uw = loc.uw; p.alpha_prev = loc.alpha_prev; p.ld_aprev = loc.ld_aprev;
+    p.alpha = alpha; p.dc = dc; p.dalpha_in = dalpha_in; p.pen = pen;
+    p.ld_alpha = ld_alpha; p.ld_dc = ld_dc; p.ld_dain = ld_dain; p.ld_pen = ld_pen; p.lambda = lambda;
+    p.dalpha_s = sc.dalpha; p.part_P = sc.part_P; p.part_dot = sc.part_dot; p.V1 = sc.V1; p.counters = sc.counters;
+    p.dq = dq; p.de = de; p.dalpha_prev = dalpha_prev; p.ld_dq = ld_dq; p.ld_de = ld_de; p.ld_dap = ld_dap;
+    if (loc.KF > 0) ATT_DISPATCH(launch_bwd, true, ctx, p, loc.KF);
+    else ATT_DISPATCH(launch_bwd, false, ctx, p, 0);
+}
+
+int attn_dvh(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* de_all, const float* w, const int* lengths,
+             const int* tlens, int B, int Lmax, int T, int S, const AttnLoc& loc, float* dVh, float* dwe, float* duw) {
+    S2S_REQUIRE(S % 128 == 0, "attn_dvh: S must be a multiple of 128");
+    DvhParams p;
+    p.Vh = Vh; p.q_all = q_all; p.de_all = de_all; p.w = w; p.lengths = lengths; p.tlens = tlens;
+    p.B = B; p.Lmax = Lmax; p.T = T; p.S = S; p.KF = loc.KF; p.padl = loc.padl; p.uw = loc.uw; p.alpha_all = loc.alpha_prev;
+    p.dVh = dVh; p.dwe = dwe; p.duw = duw;
+    size_t smem = ((size_t)T * DVH_R + (loc.KF > 0 ? (size_t)T * (DVH_R + loc.KF - 1) : 0)) * 4;
+    S2S_REQUIRE(smem <= 200 * 1024, "attn_dvh: T=%d too large for the shared-memory staging", T);
+    dim3 grid(ceil_div(Lmax, DVH_R), B, S / 128);
+    if (loc.KF > 0) {
+        S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_dvh_kernel<true><<<grid, 128, smem, ctx->stream>>>(p);
+    } else {
+        if (smem > 48 * 1024) S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_dvh_kernel<false><<<grid, 128, smem, ctx->stream>>>(p);
+    }
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+}  // namespace s2s

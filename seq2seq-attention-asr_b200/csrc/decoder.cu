@@ -1,0 +1,732 @@
+// decoder.cu -- nn.Attention = Vh precompute + nn.RNNAttention(nn.Recurrent(decoder_base_)), teacher
+// forced, forward and backward (Attention.lua:39-211,305-327; RNNAttention.lua:144-253;
+// Recurrent.lua:104-151; GRU.lua:22-30; Maxout.lua:14-19; model_chorowski_baseline.lua:48-59).
+//
+// What is sequential in t stays in the time loop (Ws s_{t-1}, the attention step, c->u, the decoder
+// GRU); everything teacher forcing makes independent of the recurrence is hoisted into time-batched
+// GEMMs over M = B*T rows: the y_{t-1} input path, the Maxout MLP + LogSoftMax, and every weight
+// gradient.  The per-step [L,S]/[L,A] gradient read-modify-write of RNNAttention.lua:247 is replaced
+// by the deferred accumulation kernels of attention.cu.
+#include "decoder.cuh"
+#include "model.cuh"
+
+namespace s2s {
+
+// =================================================================================================
+// dense_small: Y[b, n] = epi( sum_k X[b,k] W[n,k] )  for a handful of rows b (the minibatch) --
+// the per-step matrix-vector products of the decoder.  The X tile (32 rows x K) is staged in shared
+// memory once per CTA; every warp owns one output unit n, keeps its weight row in registers, and the
+// 32 per-row partial sums are reduced with a 31-shuffle transpose-reduction.
+// =================================================================================================
+enum { EPI_LINEAR = 0, EPI_GRU_ZR = 1, EPI_GRU_H = 2 };
+struct DenseEpi {
+    int mode = EPI_LINEAR;
+    const float* bias = nullptr;
+    const float* add = nullptr; int64_t ld_add = 0;
+    float* out = nullptr; int64_t ld_out = 0;
+    float* out2 = nullptr; int64_t ld_out2 = 0; int n2_start = 0;   // second copy of columns n >= n2_start
+    // GRU epilogues
+    int ST = 0;
+    float* gates = nullptr; int64_t ld_gates = 0;          // z | r | h~
+    const float* sprev = nullptr; int64_t ld_sprev = 0;
+    float* rh_out = nullptr; int64_t ld_rh = 0;
+    float* s_out = nullptr; int64_t ld_s = 0;
+    float* s_out2 = nullptr; int64_t ld_s2 = 0;
+};
+
+template <int KV>
+__global__ void __launch_bounds__(256)
+dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const float* __restrict__ W, int ldw, int N, const DenseEpi e) {
+    extern __shared__ __align__(16) float xs[];   // [32][K]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.x * 8 + warp;
+    const int K4 = K >> 2;
+    float4 w[KV];
+    if (n < N) {
+#pragma unroll
+        for (int i = 0; i < KV; i++) {
+            const int k4 = lane + i * 32;
+            w[i] = k4 < K4 ? ldg4(W + (size_t)n * ldw + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int nb = min(32, B - b0);
+        __syncthreads();
+        for (int idx = tid; idx < nb * K4; idx += 256) {
+            const int bb = idx / K4, k4 = idx - bb * K4;
+            reinterpret_cast<float4*>(xs)[bb * K4 + k4] = *reinterpret_cast<const float4*>(X + (size_t)(b0 + bb) * ldx + k4 * 4);
+        }
+        __syncthreads();
+        if (n >= N) continue;
+        float acc[32];
+#pragma unroll
+        for (int bb = 0; bb < 32; bb++) {
+            float a = 0.f;
+            if (bb < nb) {
+#pragma unroll
+                for (int i = 0; i < KV; i++) {
+                    const int k4 = lane + i * 32;
+                    if (k4 < K4) {
+                        const float4 x = reinterpret_cast<const float4*>(xs)[bb * K4 + k4];
+                        a = fmaf(w[i].x, x.x, a); a = fmaf(w[i].y, x.y, a); a = fmaf(w[i].z, x.z, a); a = fmaf(w[i].w, x.w, a);
+                    }
+                }
+            }
+            acc[bb] = a;
+        }
+        // transpose-reduce: lane bb ends with the full dot product for row b0 + bb
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+            for (int i = 0; i < s; i++) {
+                const float send = (lane & s) ? acc[i] : acc[i + s];
+                const float keep = (lane & s) ? acc[i + s] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+        }
+        if (lane < nb) {
+            const int b = b0 + lane;
+            float v = acc[0];
+            if (e.mode == EPI_LINEAR) {
+                if (e.bias) v += e.bias[n];
+                if (e.add) v += e.add[(size_t)b * e.ld_add + n];
+                e.out[(size_t)b * e.ld_out + n] = v;
+                if (e.out2 && n >= e.n2_start) e.out2[(size_t)b * e.ld_out2 + n - e.n2_start] = v;
+            } else if (e.mode == EPI_GRU_ZR) {
+                const float g = sigmoid_acc(v);                        // GRU.lua:23-24
+                e.gates[(size_t)b * e.ld_gates + n] = g;
+                if (n >= e.ST) e.rh_out[(size_t)b * e.ld_rh + n - e.ST] = g * e.sprev[(size_t)b * e.ld_sprev + n - e.ST];   // GRU.lua:25
+            } else {
+                const float hc = tanh_acc(v);                          // GRU.lua:26
+                const float z = e.gates[(size_t)b * e.ld_gates + n];
+                const float sp = e.sprev[(size_t)b * e.ld_sprev + n];
+                const float s = (1.f - z) * sp + z * hc;               // GRU.lua:27-30
+                e.gates[(size_t)b * e.ld_gates + 2 * e.ST + n] = hc;
+                e.s_out[(size_t)b * e.ld_s + n] = s;
+                if (e.s_out2) e.s_out2[(size_t)b * e.ld_s2 + n] = s;
+            }
+        }
+    }
+}
+
+static int dense_small(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, const float* W, int ldw, int N, const DenseEpi& e) {
+    S2S_REQUIRE(K % 4 == 0 && ldw % 4 == 0 && ldx % 4 == 0, "dense_small: K (%d), ldw (%d), ldx (%ld) must be multiples of 4", K, ldw, (long)ldx);
+    S2S_REQUIRE(K <= 1024, "dense_small: K=%d > 1024 not supported", K);
+    const int kv = ceil_div(K, 128);
+    const size_t smem = (size_t)32 * K * 4;
+    dim3 grid(ceil_div(N, 8));
+#define DS_LAUNCH(KVV)                                                                                          \
+    do {                                                                                                        \
+        static size_t attr = 0;                                                                                 \
+        if (smem > 48 * 1024 && smem > attr) {                                                                  \
+            S2S_CUDA(cudaFuncSetAttribute(dense_small_kernel<KVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr = smem;                                                                                        \
+        }                                                                                                       \
+        dense_small_kernel<KVV><<<grid, 256, smem, ctx->stream>>>(X, ldx, B, K, W, ldw, N, e);                  \
+    } while (0)
+    if (kv <= 1) DS_LAUNCH(1);
+    else if (kv <= 2) DS_LAUNCH(2);
+    else if (kv <= 4) DS_LAUNCH(4);
+    else if (kv <= 6) DS_LAUNCH(6);
+    else DS_LAUNCH(8);
+#undef DS_LAUNCH
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// =================================================================================================
+// elementwise / gather kernels
+// =================================================================================================
+// y_in[b,t,:] = b_y + W_y[:, y_{t-1}]   (Linear(V,ST) on the one-hot previous label, Attention.lua:149;
+// zeros_y at t = 0, RNNAttention.lua:172-176)
+__global__ void yin_gather_kernel(const float* __restrict__ Wy, const float* __restrict__ by, const int* __restrict__ labels,
+                                  int B, int T, int ST, int V, float* __restrict__ yin) {
+    const int bt = blockIdx.x, t = bt % T, b = bt / T;
+    int y = t > 0 ? labels[(size_t)b * T + t - 1] : -1;
+    if (y >= V) y = -1;
+    for (int i = threadIdx.x; i < ST; i += blockDim.x)
+        yin[(size_t)bt * ST + i] = by[i] + (y >= 0 ? Wy[(size_t)i * V + y] : 0.f);
+}
+// dWy[:, y_{t-1}] += dyin[b,t,:]
+__global__ void wy_scatter_kernel(const float* __restrict__ dyin, const int* __restrict__ labels, int B, int T, int ST, int V, float* __restrict__ dWy) {
+    const int bt = blockIdx.x, t = bt % T, b = bt / T;
+    if (t == 0) return;
+    const int y = labels[(size_t)b * T + t - 1];
+    if (y < 0 || y >= V) return;
+    for (int i = threadIdx.x; i < ST; i += blockDim.x) atomicAdd(dWy + (size_t)i * V + y, dyin[(size_t)bt * ST + i]);
+}
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ m, float* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * m[i];
+}
+// Maxout: groups of MW consecutive units (Maxout.lua:15-19); first maximum wins on ties
+__global__ void maxout_fwd_kernel(const float* __restrict__ pre, int64_t rows, int M, int MW, float* __restrict__ mo, int* __restrict__ midx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * M) return;
+    const float* p = pre + i * MW;
+    int best = 0; float bv = p[0];
+    for (int j = 1; j < MW; j++) if (p[j] > bv) { bv = p[j]; best = j; }
+    mo[i] = bv; midx[i] = best;
+}
+__global__ void maxout_bwd_kernel(const float* __restrict__ dmo, const int* __restrict__ midx, int64_t rows, int M, int MW, float* __restrict__ dm) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * M) return;
+    const int best = midx[i]; const float g = dmo[i];
+    for (int j = 0; j < MW; j++) dm[i * MW + j] = j == best ? g : 0.f;
+}
+// LogSoftMax over V (warp per row), in place + copy
+__global__ void logsoftmax_kernel(float* __restrict__ x, int64_t rows, int V, float* __restrict__ copy) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* r = x + row * V;
+    float m = -INFINITY;
+    for (int i = lane; i < V; i += 32) m = fmaxf(m, r[i]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < V; i += 32) s += expf(r[i] - m);
+    s = warp_sum(s);
+    const float lz = m + logf(s);
+    for (int i = lane; i < V; i += 32) { const float v = r[i] - lz; r[i] = v; if (copy) copy[row * V + i] = v; }
+}
+// dlogits = dlogp - exp(logp) * sum(dlogp)
+// (rows t >= T_b are padding: their gradient is forced to zero)
+__global__ void logsoftmax_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ dlogp, int64_t rows, int V,
+                                      const int* __restrict__ tlens, int T, float* __restrict__ dlogits) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    if (tlens && (int)(row % T) >= tlens[row / T]) {
+        for (int i = lane; i < V; i += 32) dlogits[row * V + i] = 0.f;
+        return;
+    }
+    float s = 0.f;
+    for (int i = lane; i < V; i += 32) s += dlogp[row * V + i];
+    s = warp_sum(s);
+    for (int i = lane; i < V; i += 32) dlogits[row * V + i] = dlogp[row * V + i] - expf(logp[row * V + i]) * s;
+}
+// decoder GRU backward, elementwise part 1 (GRU.lua:27-30 reversed)
+//   ds = ds_mlp + ds_carry ; dah = ds z (1-hc^2) ; daz = ds (hc - sp) z (1-z) ; dsu[:, :ST] = ds (1-z)
+__global__ void gru_bwd_e1_kernel(const float* __restrict__ dsc, int64_t ld_dsc, const float* __restrict__ ds_carry,
+                                  const float* __restrict__ gates, int64_t ld_g, const float* __restrict__ su, int64_t ld_su,
+                                  int B, int ST, float* __restrict__ dA, int64_t ld_dA, float* __restrict__ dsu) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * ST) return;
+    const int b = idx / ST, j = idx - b * ST;
+    const float ds = dsc[(size_t)b * ld_dsc + j] + ds_carry[idx];
+    const float z = gates[(size_t)b * ld_g + j], hc = gates[(size_t)b * ld_g + 2 * ST + j], sp = su[(size_t)b * ld_su + j];
+    dA[(size_t)b * ld_dA + 2 * ST + j] = ds * z * (1.f - hc * hc);
+    dA[(size_t)b * ld_dA + j] = ds * (hc - sp) * z * (1.f - z);
+    dsu[(size_t)b * 2 * ST + j] = ds * (1.f - z);
+}
+// part 2: drh = drhu[:, :ST] ; dar = drh sp r (1-r) ; dsu[:, :ST] += drh r ; dsu[:, ST:] = drhu[:, ST:]
+__global__ void gru_bwd_e2_kernel(const float* __restrict__ drhu, const float* __restrict__ gates, int64_t ld_g,
+                                  const float* __restrict__ su, int64_t ld_su, int B, int ST,
+                                  float* __restrict__ dA, int64_t ld_dA, float* __restrict__ dsu) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * ST) return;
+    const int b = idx / ST, j = idx - b * ST;
+    const float drh = drhu[(size_t)b * 2 * ST + j];
+    const float r = gates[(size_t)b * ld_g + ST + j], sp = su[(size_t)b * ld_su + j];
+    dA[(size_t)b * ld_dA + ST + j] = drh * sp * r * (1.f - r);
+    dsu[(size_t)b * 2 * ST + j] += drh * r;
+    dsu[(size_t)b * 2 * ST + ST + j] = drhu[(size_t)b * 2 * ST + ST + j];
+}
+// UW[j][i] = sum_m U[i,m] WF[m,j] ; qbias[i] = bs[i] + sum_m U[i,m] bF[m]
+__global__ void loc_fold_kernel(const float* __restrict__ U, const float* __restrict__ WF, const float* __restrict__ bF,
+                                const float* __restrict__ bs, int S, int K, int KF, float* __restrict__ uw, float* __restrict__ qbias) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    float ub = 0.f;
+    for (int m = 0; m < K; m++) ub = fmaf(U[(size_t)i * K + m], bF[m], ub);
+    qbias[i] = bs[i] + ub;
+    for (int j = 0; j < KF; j++) {
+        float a = 0.f;
+        for (int m = 0; m < K; m++) a = fmaf(U[(size_t)i * K + m], WF[(size_t)m * KF + j], a);
+        uw[(size_t)j * S + i] = a;
+    }
+}
+// gradients of the folded location parameters back to U, WF, bF:
+//   dU[i,m] += sum_j dUW[j][i] WF[m,j] + dUb[i] bF[m] ; dWF[m,j] += sum_i U[i,m] dUW[j][i] ; dbF[m] += sum_i U[i,m] dUb[i]
+__global__ void loc_unfold_kernel(const float* __restrict__ U, const float* __restrict__ WF, const float* __restrict__ bF,
+                                  const float* __restrict__ duw, const float* __restrict__ dub, int S, int K, int KF,
+                                  float* __restrict__ dU, float* __restrict__ dWF, float* __restrict__ dbF) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const float db = dub[i];
+    for (int m = 0; m < K; m++) {
+        float a = db * bF[m];
+        for (int j = 0; j < KF; j++) a = fmaf(duw[(size_t)j * S + i], WF[(size_t)m * KF + j], a);
+        dU[(size_t)i * K + m] += a;
+        const float u = U[(size_t)i * K + m];
+        atomicAdd(dbF + m, u * db);
+        for (int j = 0; j < KF; j++) atomicAdd(dWF + (size_t)m * KF + j, u * duw[(size_t)j * S + i]);
+    }
+}
+
+static void pad_lr(int kf, int* pl) { *pl = (kf % 2 == 1) ? (kf - 1) / 2 : kf / 2; }   // Attention.lua:77-85
+
+// =================================================================================================
+// forward
+// =================================================================================================
+int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax,
+                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out) {
+    const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V, M = Y.M, MW = Y.MW, KF = Y.K > 0 ? Y.KF : 0;
+    S2S_REQUIRE(B > 0 && Lmax > 0 && T > 0, "decoder_forward: empty batch (B=%d Lmax=%d T=%d)", B, Lmax, T);
+    S2S_REQUIRE(ST % 4 == 0 && A % 4 == 0, "decoder: ST and A must be multiples of 4");
+    if (!ctx->dec) ctx->dec = new DecoderState();
+    DecoderState& d = *ctx->dec;
+    d.valid = false; d.B = B; d.Lmax = Lmax; d.T = T; d.Y = Y; d.lambda = lambda; d.has_drop = dropmask != nullptr;
+    Arena& pa = ctx->persist;
+    const size_t BT = (size_t)B * T;
+    S2S_ALLOC(d.Vh, pa, float, (size_t)B * Lmax * S);
+    S2S_ALLOC(d.alpha, pa, float, BT * Lmax);
+    S2S_ALLOC(d.sc, pa, float, BT * (ST + A));
+    S2S_ALLOC(d.q, pa, float, BT * S);
+    S2S_ALLOC(d.pen, pa, float, BT);
+    S2S_ALLOC(d.cin, pa, float, BT * ST);
+    S2S_ALLOC(d.yin, pa, float, BT * ST);
+    S2S_ALLOC(d.su, pa, float, BT * 2 * ST);
+    S2S_ALLOC(d.rhu, pa, float, BT * 2 * ST);
+    S2S_ALLOC(d.gates, pa, float, BT * 3 * ST);
+    S2S_ALLOC(d.mo, pa, float, BT * M);
+    S2S_ALLOC(d.midx, pa, int, BT * M);
+    S2S_ALLOC(d.logp, pa, float, BT * V);
+    if (dropmask) S2S_ALLOC(d.scm, pa, float, BT * (ST + A)); else d.scm = d.sc;
+    S2S_ALLOC(d.qbias, pa, float, S);
+    if (KF > 0) S2S_ALLOC(d.uw, pa, float, (size_t)KF * S); else d.uw = nullptr;
+    S2S_TRY(attn_scratch_alloc(ctx, pa, B, Lmax, S, A, KF, false, &d.att));
+    Arena& ar = ctx->arena;
+    float *uy, *mpre, *zeros;
+    S2S_ALLOC(uy, ar, float, BT * ST);
+    S2S_ALLOC(mpre, ar, float, BT * M * MW);
+    S2S_ALLOC(zeros, ar, float, (size_t)B * ST);
+    cudaStream_t st = ctx->stream;
+
+    // Vh = TemporalConvolutionZeroBias(A,S,1)(h)   (Attention.lua:44; bias pinned to zero)
+    S2S_TRY(gemm_f32(ctx, false, true, B * Lmax, S, A, 1.f, h, A, P + Y.WV.off, A, 0.f, d.Vh, S));
+    // location fold / q bias
+    int padl = 0;
+    if (KF > 0) {
+        pad_lr(KF, &padl);
+        loc_fold_kernel<<<ceil_div(S, 128), 128, 0, st>>>(P + Y.U.off, P + Y.WF.off, P + Y.bF.off, P + Y.bs.off, S, Y.K, KF, d.uw, d.qbias);
+        S2S_LAUNCH_CHECK(ctx);
+    } else {
+        S2S_CUDA(cudaMemcpyAsync(d.qbias, P + Y.bs.off, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    // teacher-forced input path, hoisted out of the loop: y_in (Attention.lua:149) and its share of
+    // Linear(2ST,ST) (Attention.lua:151): uy = W_j[:, ST:] y_in + b_j
+    yin_gather_kernel<<<(unsigned)BT, 128, 0, st>>>(P + Y.Wy.off, P + Y.by.off, labels, B, T, ST, V, d.yin);
+    S2S_LAUNCH_CHECK(ctx);
+    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, ST, ST, 1.f, d.yin, ST, P + Y.Wj.off + ST, 2 * ST, 0.f, uy, ST, P + Y.bj.off));
+    S2S_CUDA(cudaMemsetAsync(zeros, 0, (size_t)B * ST * sizeof(float), st));
+    S2S_CUDA(cudaMemsetAsync(d.su, 0, BT * 2 * ST * sizeof(float), st));     // s_0 = 0 (Recurrent.lua:112)
+
+    const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST;
+    for (int t = 0; t < T; t++) {
+        const float* sprev = t ? d.sc + (size_t)(t - 1) * (ST + A) : zeros;
+        const int64_t ldsp = t ? ldsc : ST;
+        {   // q_t = W_s s_{t-1} + b_s   (Attention.lua:65-67)
+            DenseEpi e; e.bias = d.qbias; e.out = d.q + (size_t)t * S; e.ld_out = (int64_t)T * S;
+            S2S_TRY(dense_small(ctx, sprev, ldsp, B, ST, P + Y.Ws.off, ST, S, e));
+        }
+        {   // attention step (Attention.lua:95-135)
+            AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw;
+            loc.alpha_prev = t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr; loc.ld_aprev = (int64_t)T * Lmax;
+            S2S_TRY(attn_step_fwd(ctx, d.att, d.Vh, h, d.q + (size_t)t * S, (int64_t)T * S, P + Y.we.off, lengths, B, Lmax, S, A, loc,
+                                  d.alpha + (size_t)t * Lmax, (int64_t)T * Lmax, d.sc + (size_t)t * (ST + A) + ST, ldsc,
+                                  d.pen + t, T, lambda, t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr, (int64_t)T * Lmax));
+        }
+        {   // c_in = W_c c_t + b_c   (Attention.lua:150)
+            DenseEpi e; e.bias = P + Y.bc.off; e.out = d.cin + (size_t)t * ST; e.ld_out = (int64_t)T * ST;
+            S2S_TRY(dense_small(ctx, d.sc + (size_t)t * (ST + A) + ST, ldsc, B, A, P + Y.Wc.off, A, ST, e));
+        }
+        {   // u_t = W_j[:, :ST] c_in + uy_t   (Attention.lua:151) -> second halves of {s,u} and {r*s,u}
+            DenseEpi e; e.add = uy + (size_t)t * ST; e.ld_add = (int64_t)T * ST;
+            e.out = d.su + (size_t)t * 2 * ST + ST; e.ld_out = ldsu;
+            e.out2 = d.rhu + (size_t)t * 2 * ST + ST; e.ld_out2 = ldsu; e.n2_start = 0;
+            S2S_TRY(dense_small(ctx, d.cin + (size_t)t * ST, (int64_t)T * ST, B, ST, P + Y.Wj.off, 2 * ST, ST, e));
+        }
+        {   // z, r = sigmoid(G_{z,r} {s_{t-1}, u})   (GRU.lua:22-24) ; r * s_{t-1}  (:25)
+            DenseEpi e; e.mode = EPI_GRU_ZR; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
+            e.sprev = d.su + (size_t)t * 2 * ST; e.ld_sprev = ldsu; e.rh_out = d.rhu + (size_t)t * 2 * ST; e.ld_rh = ldsu;
+            S2S_TRY(dense_small(ctx, d.su + (size_t)t * 2 * ST, ldsu, B, 2 * ST, P + Y.Gz.off, 2 * ST, 2 * ST, e));
+        }
+        {   // h~ = tanh(G_h {r*s_{t-1}, u}) ; s_t = (1-z) s_{t-1} + z h~   (GRU.lua:26-30)
+            DenseEpi e; e.mode = EPI_GRU_H; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
+            e.sprev = d.su + (size_t)t * 2 * ST; e.ld_sprev = ldsu;
+            e.s_out = d.sc + (size_t)t * (ST + A); e.ld_s = ldsc;
+            e.s_out2 = t + 1 < T ? d.su + (size_t)(t + 1) * 2 * ST : nullptr; e.ld_s2 = ldsu;
+            S2S_TRY(dense_small(ctx, d.rhu + (size_t)t * 2 * ST, ldsu, B, 2 * ST, P + Y.Gh.off, 2 * ST, ST, e));
+        }
+    }
+
+    // decoder MLP, time-batched: JoinTable{s,c} -> [Dropout] -> Maxout -> Linear -> LogSoftMax
+    // (model_chorowski_baseline.lua:53-59, model_chorowski_baseline_dropout.lua:56)
+    if (dropmask) {
+        const int64_t n = (int64_t)BT * (ST + A);
+        mul_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(d.sc, dropmask, d.scm, n);
+        S2S_LAUNCH_CHECK(ctx);
+    }
+    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, M * MW, ST + A, 1.f, d.scm, ST + A, P + Y.Wm.off, ST + A, 0.f, mpre, M * MW, P + Y.bm.off));
+    maxout_fwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(mpre, (int64_t)BT, M, MW, d.mo, d.midx);
+    S2S_LAUNCH_CHECK(ctx);
+    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, V, M, 1.f, d.mo, M, P + Y.Wo.off, M, 0.f, d.logp, V, P + Y.bo.off));
+    logsoftmax_kernel<<<(unsigned)ceil_div64((int64_t)BT, 8), 256, 0, st>>>(d.logp, (int64_t)BT, V, logp_out);
+    S2S_LAUNCH_CHECK(ctx);
+    d.valid = true;
+    return 0;
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, const float* h, const int* lengths, int B, int Lmax,
+                     const int* labels, const int* tlens, int T, const float* dropmask, float lambda, const float* dlogp, float* dh) {
+    S2S_REQUIRE(ctx->dec && ctx->dec->valid, "attention backward called without a preceding forward on this context");
+    DecoderState& d = *ctx->dec;
+    S2S_REQUIRE(d.B == B && d.Lmax == Lmax && d.T == T && d.Y.n == Y.n, "attention backward: shapes differ from the preceding forward");
+    S2S_REQUIRE((dropmask != nullptr) == d.has_drop, "attention backward: dropmask presence differs from the forward");
+    const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V, M = Y.M, MW = Y.MW, KF = Y.K > 0 ? Y.KF : 0;
+    const size_t BT = (size_t)B * T;
+    const int iBT = (int)BT;
+    cudaStream_t st = ctx->stream;
+    Arena& ar = ctx->arena;
+    const bool carry_alpha = KF > 0 || lambda != 0.f;
+
+    float *dlogits, *dmo, *dm, *dsc, *dA, *du_all, *dcin_all, *dc_all, *dq_all, *de_all, *dyin, *dVh;
+    float *ds_carry, *dsu, *drhu, *dac[2] = {nullptr, nullptr}, *GhT, *GzrT, *WjcT, *WcT, *WsT, *duw = nullptr;
+    S2S_ALLOC(dlogits, ar, float, BT * V);
+    S2S_ALLOC(dmo, ar, float, BT * M);
+    S2S_ALLOC(dm, ar, float, BT * M * MW);
+    S2S_ALLOC(dsc, ar, float, BT * (ST + A));
+    S2S_ALLOC(dA, ar, float, BT * 3 * ST);
+    S2S_ALLOC(du_all, ar, float, BT * ST);
+    S2S_ALLOC(dcin_all, ar, float, BT * ST);
+    S2S_ALLOC(dc_all, ar, float, BT * A);
+    S2S_ALLOC(dq_all, ar, float, BT * S);
+    S2S_ALLOC(de_all, ar, float, BT * Lmax);
+    S2S_ALLOC(dyin, ar, float, BT * ST);
+    S2S_ALLOC(dVh, ar, float, (size_t)B * Lmax * S);
+    S2S_ALLOC(ds_carry, ar, float, (size_t)B * ST);
+    S2S_ALLOC(dsu, ar, float, (size_t)B * 2 * ST);
+    S2S_ALLOC(drhu, ar, float, (size_t)B * 2 * ST);
+    if (carry_alpha) { S2S_ALLOC(dac[0], ar, float, (size_t)B * Lmax); S2S_ALLOC(dac[1], ar, float, (size_t)B * Lmax); }
+    S2S_ALLOC(GhT, ar, float, (size_t)2 * ST * ST);
+    S2S_ALLOC(GzrT, ar, float, (size_t)2 * ST * 2 * ST);
+    S2S_ALLOC(WjcT, ar, float, (size_t)ST * ST);
+    S2S_ALLOC(WcT, ar, float, (size_t)A * ST);
+    S2S_ALLOC(WsT, ar, float, (size_t)ST * S);
+    if (KF > 0) { S2S_ALLOC(duw, ar, float, (size_t)KF * S); S2S_CUDA(cudaMemsetAsync(duw, 0, (size_t)KF * S * sizeof(float), st)); }
+    AttnScratch att;
+    S2S_TRY(attn_scratch_alloc(ctx, ar, B, Lmax, S, A, KF, true, &att));
+
+    // transposed copies of the recurrent-chain weights so every in-loop product is K-contiguous
+    S2S_TRY(transpose_f32(ctx, P + Y.Gh.off, ST, 2 * ST, 2 * ST, GhT, ST));          // GhT [2ST, ST]
+    S2S_TRY(transpose_f32(ctx, P + Y.Gz.off, 2 * ST, 2 * ST, 2 * ST, GzrT, 2 * ST)); // rows: z then r (contiguous segments)
+    S2S_TRY(transpose_f32(ctx, P + Y.Wj.off, ST, ST, 2 * ST, WjcT, ST));             // (W_j[:, :ST])^T
+    S2S_TRY(transpose_f32(ctx, P + Y.Wc.off, ST, A, A, WcT, ST));                    // WcT [A, ST]
+    S2S_TRY(transpose_f32(ctx, P + Y.Ws.off, S, ST, ST, WsT, S));                    // WsT [ST, S]
+
+    // ---- time-batched MLP backward (model_chorowski_baseline.lua:53-59 reversed) ----------------
+    logsoftmax_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT, 8), 256, 0, st>>>(d.logp, dlogp, (int64_t)BT, V, tlens, T, dlogits);
+    S2S_LAUNCH_CHECK(ctx);
+    S2S_TRY(gemm_f32(ctx, true, false, V, M, iBT, 1.f, dlogits, V, d.mo, M, 1.f, G + Y.Wo.off, M));
+    S2S_TRY(colsum_add(ctx, dlogits, BT, V, V, G + Y.bo.off));
+    S2S_TRY(gemm_f32(ctx, false, false, iBT, M, V, 1.f, dlogits, V, P + Y.Wo.off, M, 0.f, dmo, M));
+    maxout_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(dmo, d.midx, (int64_t)BT, M, MW, dm);
+    S2S_LAUNCH_CHECK(ctx);
+    S2S_TRY(gemm_f32(ctx, true, false, M * MW, ST + A, iBT, 1.f, dm, M * MW, d.scm, ST + A, 1.f, G + Y.Wm.off, ST + A, nullptr, GemmBatch(), 4));
+    S2S_TRY(colsum_add(ctx, dm, BT, M * MW, M * MW, G + Y.bm.off));
+    S2S_TRY(gemm_f32(ctx, false, false, iBT, ST + A, M * MW, 1.f, dm, M * MW, P + Y.Wm.off, ST + A, 0.f, dsc, ST + A));
+    if (dropmask) {
+        const int64_t n = (int64_t)BT * (ST + A);
+        mul_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(dsc, dropmask, dsc, n);
+        S2S_LAUNCH_CHECK(ctx);
+    }
+
+    // ---- time loop, t = T-1 .. 0 (RNNAttention.lua:233) -------------------------------------------
+    S2S_CUDA(cudaMemsetAsync(ds_carry, 0, (size_t)B * ST * sizeof(float), st));      // Recurrent.lua:134
+    if (carry_alpha) S2S_CUDA(cudaMemsetAsync(dac[0], 0, (size_t)B * Lmax * sizeof(float), st));
+    int padl = 0;
+    if (KF > 0) pad_lr(KF, &padl);
+    const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST, lddA = (int64_t)T * 3 * ST;
+    const int eb = ceil_div(B * ST, 256);
+    for (int t = T - 1; t >= 0; t--) {
+        const int cur = (T - 1 - t) & 1;
+        gru_bwd_e1_kernel<<<eb, 256, 0, st>>>(dsc + (size_t)t * (ST + A), ldsc, ds_carry, d.gates + (size_t)t * 3 * ST, ldg,
+                                               d.su + (size_t)t * 2 * ST, ldsu, B, ST, dA + (size_t)t * 3 * ST, lddA, dsu);
+        S2S_LAUNCH_CHECK(ctx);
+        {   // d{r*s, u} = dah . G_h
+            DenseEpi e; e.out = drhu; e.ld_out = 2 * ST;
+            S2S_TRY(dense_small(ctx, dA + (size_t)t * 3 * ST + 2 * ST, lddA, B, ST, GhT, ST, 2 * ST, e));
+        }
+        gru_bwd_e2_kernel<<<eb, 256, 0, st>>>(drhu, d.gates + (size_t)t * 3 * ST, ldg, d.su + (size_t)t * 2 * ST, ldsu, B, ST,
+                                               dA + (size_t)t * 3 * ST, lddA, dsu);
+        S2S_LAUNCH_CHECK(ctx);
+        {   // d{s_{t-1}, u} += {daz, dar} . G_{z,r}
+            DenseEpi e; e.add = dsu; e.ld_add = 2 * ST; e.out = dsu; e.ld_out = 2 * ST;
+            e.out2 = du_all + (size_t)t * ST; e.ld_out2 = (int64_t)T * ST; e.n2_start = ST;
+            S2S_TRY(dense_small(ctx, dA + (size_t)t * 3 * ST, lddA, B, 2 * ST, GzrT, 2 * ST, 2 * ST, e));
+        }
+        {   // dc_in = du . W_j[:, :ST]
+            DenseEpi e; e.out = dcin_all + (size_t)t * ST; e.ld_out = (int64_t)T * ST;
+            S2S_TRY(dense_small(ctx, dsu + ST, 2 * ST, B, ST, WjcT, ST, ST, e));
+        }
+        {   // dc_t = dc_mlp + dc_in . W_c
+            DenseEpi e; e.add = dsc + (size_t)t * (ST + A) + ST; e.ld_add = ldsc; e.out = dc_all + (size_t)t * A; e.ld_out = (int64_t)T * A;
+            S2S_TRY(dense_small(ctx, dcin_all + (size_t)t * ST, (int64_t)T * ST, B, ST, WcT, ST, A, e));
+        }
+        {   // attention step backward
+            AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw;
+            loc.alpha_prev = t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr; loc.ld_aprev = (int64_t)T * Lmax;
+            S2S_TRY(attn_step_bwd(ctx, att, d.Vh, h, d.q + (size_t)t * S, (int64_t)T * S, P + Y.we.off, lengths, B, Lmax, S, A, loc,
+                                  d.alpha + (size_t)t * Lmax, (int64_t)T * Lmax, dc_all + (size_t)t * A, (int64_t)T * A,
+                                  carry_alpha ? dac[cur] : nullptr, Lmax, d.pen + t, T, lambda,
+                                  dq_all + (size_t)t * S, (int64_t)T * S, de_all + (size_t)t * Lmax, (int64_t)T * Lmax,
+                                  carry_alpha ? dac[cur ^ 1] : nullptr, Lmax));
+        }
+        {   // ds_{t-1} = dsu[:, :ST] + dq . W_s
+            DenseEpi e; e.add = dsu; e.ld_add = 2 * ST; e.out = ds_carry; e.ld_out = ST;
+            S2S_TRY(dense_small(ctx, dq_all + (size_t)t * S, (int64_t)T * S, B, S, WsT, S, ST, e));
+        }
+    }
+
+    // ---- deferred weight gradients over M = B*T rows ----------------------------------------------
+    // decoder GRU (GRU.lua:23-26): dG_{z,r} += {daz,dar}^T {s,u} ; dG_h += dah^T {r*s,u}
+    S2S_TRY(gemm_f32(ctx, true, false, 2 * ST, 2 * ST, iBT, 1.f, dA, 3 * ST, d.su, 2 * ST, 1.f, G + Y.Gz.off, 2 * ST, nullptr, GemmBatch(), 4));
+    S2S_TRY(gemm_f32(ctx, true, false, ST, 2 * ST, iBT, 1.f, dA + 2 * ST, 3 * ST, d.rhu, 2 * ST, 1.f, G + Y.Gh.off, 2 * ST, nullptr, GemmBatch(), 4));
+    // Linear(2ST,ST) on {c_in, y_in} (Attention.lua:151)
+    S2S_TRY(gemm_f32(ctx, true, false, ST, ST, iBT, 1.f, du_all, ST, d.cin, ST, 1.f, G + Y.Wj.off, 2 * ST, nullptr, GemmBatch(), 4));
+    S2S_TRY(gemm_f32(ctx, true, false, ST, ST, iBT, 1.f, du_all, ST, d.yin, ST, 1.f, G + Y.Wj.off + ST, 2 * ST, nullptr, GemmBatch(), 4));
+    S2S_TRY(colsum_add(ctx, du_all, BT, ST, ST, G + Y.bj.off));
+    // Linear(A,ST) on c (Attention.lua:150)
+    S2S_TRY(gemm_f32(ctx, true, false, ST, A, iBT, 1.f, dcin_all, ST, d.sc + ST, ST + A, 1.f, G + Y.Wc.off, A, nullptr, GemmBatch(), 4));
+    S2S_TRY(colsum_add(ctx, dcin_all, BT, ST, ST, G + Y.bc.off));
+    // Linear(V,ST) on the one-hot label (Attention.lua:149)
+    S2S_TRY(gemm_f32(ctx, false, false, iBT, ST, ST, 1.f, du_all, ST, P + Y.Wj.off + ST, 2 * ST, 0.f, dyin, ST));
+    S2S_TRY(colsum_add(ctx, dyin, BT, ST, ST, G + Y.by.off));
+    wy_scatter_kernel<<<(unsigned)BT, 128, 0, st>>>(dyin, labels, B, T, ST, V, G + Y.Wy.off);
+    S2S_LAUNCH_CHECK(ctx);
+    // Ws (Attention.lua:66): dW_s += dq^T s_{t-1} ; db_s += sum dq
+    S2S_TRY(gemm_f32(ctx, true, false, S, ST, iBT, 1.f, dq_all, S, d.su, 2 * ST, 1.f, G + Y.Ws.off, ST, nullptr, GemmBatch(), 4));
+    S2S_TRY(colsum_add(ctx, dq_all, BT, S, S, G + Y.bs.off));
+
+    // ---- deferred dVh / dw_e (/ dUW) then the Vh convolution backward -----------------------------
+    {
+        AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw; loc.alpha_prev = d.alpha;
+        S2S_TRY(attn_dvh(ctx, d.Vh, d.q, de_all, P + Y.we.off, lengths, tlens, B, Lmax, T, S, loc, dVh, G + Y.we.off, duw));
+    }
+    if (KF > 0) {
+        float* dub;
+        S2S_ALLOC(dub, ar, float, S);
+        S2S_CUDA(cudaMemsetAsync(dub, 0, S * sizeof(float), st));
+        S2S_TRY(colsum_add(ctx, dq_all, BT, S, S, dub));
+        loc_unfold_kernel<<<ceil_div(S, 128), 128, 0, st>>>(P + Y.U.off, P + Y.WF.off, P + Y.bF.off, duw, dub, S, Y.K, KF,
+                                                            G + Y.U.off, G + Y.WF.off, G + Y.bF.off);
+        S2S_LAUNCH_CHECK(ctx);
+    }
+    // TemporalConvolutionZeroBias backward (TemporalConvolutionZeroBias.lua:42-54): gradBias stays zero
+    const int BL = B * Lmax;
+    S2S_TRY(gemm_f32(ctx, true, false, S, A, BL, 1.f, dVh, S, h, A, 1.f, G + Y.WV.off, A, nullptr, GemmBatch(), 8));
+    S2S_TRY(gemm_f32(ctx, false, false, BL, A, S, 1.f, dVh, S, P + Y.WV.off, A, 0.f, dh, A));
+    // context path, deferred: dh[b,l,:] += sum_t alpha_t[b,l] dc_t[b,:]   (Attention.lua:132-134)
+    {
+        GemmBatch gb; gb.count = B; gb.sA = (int64_t)T * Lmax; gb.sB = (int64_t)T * A; gb.sC = (int64_t)Lmax * A;
+        S2S_TRY(gemm_f32(ctx, true, false, Lmax, A, T, 1.f, d.alpha, Lmax, dc_all, A, 1.f, dh, A, nullptr, gb, 1, 1));
+    }
+    return 0;
+}
+
+}  // namespace s2s
+
+// =================================================================================================
+// single decoder step with explicit hidden state (decoder_base:forward, Attention.lua:366,402) and
+// Attention:BeamSearch (Attention.lua:332-438) with the beams batched on the device
+// =================================================================================================
+namespace s2s {
+
+__global__ void yin_step_kernel(const float* __restrict__ Wy, const float* __restrict__ by, const int* __restrict__ yprev,
+                                int ST, int V, float* __restrict__ yin) {
+    const int b = blockIdx.x;
+    int y = yprev ? yprev[b] : -1;
+    if (y >= V) y = -1;
+    for (int i = threadIdx.x; i < ST; i += blockDim.x) yin[(size_t)b * ST + i] = by[i] + (y >= 0 ? Wy[(size_t)i * V + y] : 0.f);
+}
+
+int attention_step_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const float* Vh, const int* lengths, int B, int Lmax,
+                        const int* yprev, const float* alpha_prev, const float* s_prev, float* alpha, float* s, float* logp) {
+    const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V, M = Y.M, MW = Y.MW, KF = Y.K > 0 ? Y.KF : 0;
+    S2S_REQUIRE(M % 4 == 0, "attention_step: mlpDepth must be a multiple of 4");
+    Arena& ar = ctx->arena;
+    cudaStream_t st = ctx->stream;
+    float *zeros, *q, *qbias, *uw = nullptr, *sc, *yin, *uy, *cin, *su, *rhu, *gates, *mpre, *mo;
+    int* midx;
+    S2S_ALLOC(zeros, ar, float, (size_t)B * ST);
+    S2S_ALLOC(q, ar, float, (size_t)B * S);
+    S2S_ALLOC(qbias, ar, float, S);
+    if (KF > 0) S2S_ALLOC(uw, ar, float, (size_t)KF * S);
+    S2S_ALLOC(sc, ar, float, (size_t)B * (ST + A));
+    S2S_ALLOC(yin, ar, float, (size_t)B * ST);
+    S2S_ALLOC(uy, ar, float, (size_t)B * ST);
+    S2S_ALLOC(cin, ar, float, (size_t)B * ST);
+    S2S_ALLOC(su, ar, float, (size_t)B * 2 * ST);
+    S2S_ALLOC(rhu, ar, float, (size_t)B * 2 * ST);
+    S2S_ALLOC(gates, ar, float, (size_t)B * 3 * ST);
+    S2S_ALLOC(mpre, ar, float, (size_t)B * M * MW);
+    S2S_ALLOC(mo, ar, float, (size_t)B * M);
+    S2S_ALLOC(midx, ar, int, (size_t)B * M);
+    AttnScratch att;
+    S2S_TRY(attn_scratch_alloc(ctx, ar, B, Lmax, S, A, KF, false, &att));
+    int padl = 0;
+    if (KF > 0) {
+        pad_lr(KF, &padl);
+        loc_fold_kernel<<<ceil_div(S, 128), 128, 0, st>>>(P + Y.U.off, P + Y.WF.off, P + Y.bF.off, P + Y.bs.off, S, Y.K, KF, uw, qbias);
+        S2S_LAUNCH_CHECK(ctx);
+    } else {
+        S2S_CUDA(cudaMemcpyAsync(qbias, P + Y.bs.off, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (!s_prev) { S2S_CUDA(cudaMemsetAsync(zeros, 0, (size_t)B * ST * sizeof(float), st)); s_prev = zeros; }
+    S2S_CUDA(cudaMemcpy2DAsync(su, (size_t)2 * ST * 4, s_prev, (size_t)ST * 4, (size_t)ST * 4, B, cudaMemcpyDeviceToDevice, st));
+    yin_step_kernel<<<B, 128, 0, st>>>(P + Y.Wy.off, P + Y.by.off, yprev, ST, V, yin);
+    S2S_LAUNCH_CHECK(ctx);
+    { DenseEpi e; e.bias = P + Y.bj.off; e.out = uy; e.ld_out = ST; S2S_TRY(dense_small(ctx, yin, ST, B, ST, P + Y.Wj.off + ST, 2 * ST, ST, e)); }
+    { DenseEpi e; e.bias = qbias; e.out = q; e.ld_out = S; S2S_TRY(dense_small(ctx, s_prev, ST, B, ST, P + Y.Ws.off, ST, S, e)); }
+    {
+        AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = uw; loc.alpha_prev = alpha_prev; loc.ld_aprev = Lmax;
+        S2S_TRY(attn_step_fwd(ctx, att, Vh, h, q, S, P + Y.we.off, lengths, B, Lmax, S, A, loc, alpha, Lmax, sc + ST, ST + A, nullptr, 0, 0.f, nullptr, 0));
+    }
+    { DenseEpi e; e.bias = P + Y.bc.off; e.out = cin; e.ld_out = ST; S2S_TRY(dense_small(ctx, sc + ST, ST + A, B, A, P + Y.Wc.off, A, ST, e)); }
+    { DenseEpi e; e.add = uy; e.ld_add = ST; e.out = su + ST; e.ld_out = 2 * ST; e.out2 = rhu + ST; e.ld_out2 = 2 * ST; e.n2_start = 0;
+      S2S_TRY(dense_small(ctx, cin, ST, B, ST, P + Y.Wj.off, 2 * ST, ST, e)); }
+    { DenseEpi e; e.mode = EPI_GRU_ZR; e.ST = ST; e.gates = gates; e.ld_gates = 3 * ST; e.sprev = su; e.ld_sprev = 2 * ST; e.rh_out = rhu; e.ld_rh = 2 * ST;
+      S2S_TRY(dense_small(ctx, su, 2 * ST, B, 2 * ST, P + Y.Gz.off, 2 * ST, 2 * ST, e)); }
+    { DenseEpi e; e.mode = EPI_GRU_H; e.ST = ST; e.gates = gates; e.ld_gates = 3 * ST; e.sprev = su; e.ld_sprev = 2 * ST;
+      e.s_out = sc; e.ld_s = ST + A; e.s_out2 = s; e.ld_s2 = ST;
+      S2S_TRY(dense_small(ctx, rhu, 2 * ST, B, 2 * ST, P + Y.Gh.off, 2 * ST, ST, e)); }
+    { DenseEpi e; e.bias = P + Y.bm.off; e.out = mpre; e.ld_out = M * MW; S2S_TRY(dense_small(ctx, sc, ST + A, B, ST + A, P + Y.Wm.off, ST + A, M * MW, e)); }
+    maxout_fwd_kernel<<<(unsigned)ceil_div64((int64_t)B * M, 256), 256, 0, st>>>(mpre, B, M, MW, mo, midx);
+    S2S_LAUNCH_CHECK(ctx);
+    { DenseEpi e; e.bias = P + Y.bo.off; e.out = logp; e.ld_out = V; S2S_TRY(dense_small(ctx, mo, M, B, M, P + Y.Wo.off, M, V, e)); }
+    logsoftmax_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(logp, B, V, nullptr);
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+__global__ void replicate_rows_kernel(const float* __restrict__ src, int64_t n, int copies, float* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = src[i];
+    for (int c = 0; c < copies; c++) dst[(size_t)c * n + i] = v;
+}
+// gather beam states: dst[k] = src[sel[k]]
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ sel, int width, float* __restrict__ dst) {
+    const int k = blockIdx.x, s = sel[k];
+    for (int i = threadIdx.x; i < width; i += blockDim.x) dst[(size_t)k * width + i] = src[(size_t)s * width + i];
+}
+
+int beam_search_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, int L, int eos, int beam, int maxlen,
+                     int* out_host, int* n_out_host, float* logp_out_host) {
+    S2S_REQUIRE(L > 0 && beam > 0 && beam <= 64 && maxlen > 0, "beam_search: bad arguments (L=%d beam=%d maxlen=%d)", L, beam, maxlen);
+    const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V;
+    const int K0 = beam < V ? beam : V;
+    cudaStream_t st = ctx->stream;
+    // long-lived buffers of this call come from the persistent arena (attention_step_impl resets nothing
+    // but bumps ctx->arena on every step, so the per-step scratch is rewound manually)
+    ctx->persist.reset();
+    if (ctx->dec) ctx->dec->valid = false;
+    if (ctx->model) ctx->model->valid = false;
+    Arena& pa = ctx->persist;
+    float *hK, *VhK, *alpha[2], *sst[2], *lp;
+    int *ysel, *ssel;
+    S2S_ALLOC(hK, pa, float, (size_t)K0 * L * A);
+    S2S_ALLOC(VhK, pa, float, (size_t)K0 * L * S);
+    for (int i = 0; i < 2; i++) { S2S_ALLOC(alpha[i], pa, float, (size_t)K0 * L); S2S_ALLOC(sst[i], pa, float, (size_t)K0 * ST); }
+    S2S_ALLOC(lp, pa, float, (size_t)K0 * V);
+    S2S_ALLOC(ysel, pa, int, K0);
+    S2S_ALLOC(ssel, pa, int, K0);
+    replicate_rows_kernel<<<(unsigned)ceil_div64((int64_t)L * A, 256), 256, 0, st>>>(h, (int64_t)L * A, K0, hK);
+    S2S_LAUNCH_CHECK(ctx);
+    S2S_TRY(gemm_f32(ctx, false, true, K0 * L, S, A, 1.f, hK, A, P + Y.WV.off, A, 0.f, VhK, S));       // Attention.lua:355
+
+    struct Hyp { std::vector<int> y; float p; };
+    std::vector<Hyp> beams, fin;
+    std::vector<float> lph((size_t)K0 * V);
+    std::vector<int> hy(K0), hs(K0);
+    auto topk = [&](const float* v, int n, int k, std::vector<int>& idx) {   // descending, lowest index first on ties
+        idx.clear();
+        std::vector<char> used(n, 0);
+        for (int a = 0; a < k; a++) {
+            int best = -1;
+            for (int i = 0; i < n; i++) if (!used[i] && (best < 0 || v[i] > v[best])) best = i;
+            used[best] = 1; idx.push_back(best);
+        }
+    };
+    // first step from the zero state (Attention.lua:366-387)
+    ctx->arena.reset();
+    S2S_TRY(attention_step_impl(ctx, Y, P, hK, VhK, nullptr, 1, L, nullptr, nullptr, nullptr, alpha[0], sst[0], lp));
+    S2S_CUDA(cudaMemcpyAsync(lph.data(), lp, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+    S2S_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> idx;
+    topk(lph.data(), V, K0, idx);
+    int cur = 0;
+    {
+        int nb = 0;
+        for (int k = 0; k < K0; k++) {
+            Hyp hyp; hyp.y.push_back(idx[k]); hyp.p = lph[idx[k]];
+            if (idx[k] == eos) fin.push_back(hyp);
+            else { beams.push_back(hyp); hs[nb] = 0; hy[nb] = idx[k]; nb++; }
+        }
+        if (nb > 0) {
+            S2S_CUDA(cudaMemcpyAsync(ssel, hs.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+            S2S_CUDA(cudaMemcpyAsync(ysel, hy.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+            gather_rows_kernel<<<nb, 128, 0, st>>>(alpha[0], ssel, L, alpha[1]);
+            S2S_LAUNCH_CHECK(ctx);
+            gather_rows_kernel<<<nb, 128, 0, st>>>(sst[0], ssel, ST, sst[1]);
+            S2S_LAUNCH_CHECK(ctx);
+            cur = 1;
+        }
+    }
+    int count = 0;
+    while ((int)fin.size() < K0 && count < maxlen && !beams.empty()) {                 // Attention.lua:390
+        count++;
+        const int nb = (int)beams.size();
+        ctx->arena.reset();
+        S2S_TRY(attention_step_impl(ctx, Y, P, hK, VhK, nullptr, nb, L, ysel, alpha[cur], sst[cur], alpha[cur ^ 1], sst[cur ^ 1], lp));
+        S2S_CUDA(cudaMemcpyAsync(lph.data(), lp, (size_t)nb * V * 4, cudaMemcpyDeviceToHost, st));
+        S2S_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < nb; k++) for (int j = 0; j < V; j++) lph[(size_t)k * V + j] += beams[k].p;     // :404
+        const int want = K0 - (int)fin.size();
+        const int kk = want < nb * V ? want : nb * V;
+        topk(lph.data(), nb * V, kk, idx);                                               // :406-408
+        std::vector<Hyp> nxt;
+        int nn = 0;
+        for (int k = 0; k < kk; k++) {
+            const int i = idx[k] / V, j = idx[k] % V;
+            Hyp hyp = beams[i]; hyp.y.push_back(j); hyp.p = lph[(size_t)i * V + j];
+            if (j == eos || count == maxlen) fin.push_back(hyp);                          // :418-421
+            else { nxt.push_back(hyp); hs[nn] = i; hy[nn] = j; nn++; }
+        }
+        beams.swap(nxt);
+        if (nn > 0) {
+            S2S_CUDA(cudaMemcpyAsync(ssel, hs.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
+            S2S_CUDA(cudaMemcpyAsync(ysel, hy.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
+            gather_rows_kernel<<<nn, 128, 0, st>>>(alpha[cur ^ 1], ssel, L, alpha[cur]);
+            S2S_LAUNCH_CHECK(ctx);
+            gather_rows_kernel<<<nn, 128, 0, st>>>(sst[cur ^ 1], ssel, ST, sst[cur]);
+            S2S_LAUNCH_CHECK(ctx);
+            S2S_CUDA(cudaStreamSynchronize(st));   // hs/hy are reused by the next iteration
+        }
+    }
+    *n_out_host = 0;
+    if (!fin.empty()) {
+        size_t best = 0;
+        for (size_t k = 1; k < fin.size(); k++) if (fin[k].p > fin[best].p) best = k;       // :435
+        *n_out_host = (int)fin[best].y.size();
+        for (size_t i = 0; i < fin[best].y.size(); i++) out_host[i] = fin[best].y[i];
+        if (logp_out_host) *logp_out_host = fin[best].p;
+    }
+    return 0;
+}
+
+}  // namespace s2s

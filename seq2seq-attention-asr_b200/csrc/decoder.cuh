@@ -1,0 +1,40 @@
+// decoder.cuh -- state of the teacher-forced attention decoder (nn.Attention) kept between
+// updateOutput and updateGradInput, plus the entry points used by model.cu / api.cu.
+#pragma once
+#include "attention.cuh"
+#include "common.cuh"
+
+namespace s2s {
+
+struct DecoderState {
+    bool valid = false;
+    int B = 0, Lmax = 0, T = 0;
+    Layout Y;
+    float lambda = 0.f;
+    bool has_drop = false;
+    // saved by forward (persist arena); all [B, T, .] unless noted
+    float* Vh = nullptr;      // [B, Lmax, S]            Attention.lua:44
+    float* alpha = nullptr;   // [B, T, Lmax]            decoder:alpha()
+    float* sc = nullptr;      // [B, T, ST+A]            {s_t, c_t}  (JoinTable order of model_chorowski_baseline.lua:53-54)
+    float* q = nullptr;       // [B, T, S]               decoder:Ws()  (includes b_s, and U b_F on the location path)
+    float* pen = nullptr;     // [B, T]
+    float* cin = nullptr;     // [B, T, ST]
+    float* yin = nullptr;     // [B, T, ST]
+    float* su = nullptr;      // [B, T, 2ST]             {s_{t-1}, u_t}   (GRU.lua:22 concat order)
+    float* rhu = nullptr;     // [B, T, 2ST]             {r * s_{t-1}, u_t}
+    float* gates = nullptr;   // [B, T, 3ST]             z | r | h~
+    float* mo = nullptr;      // [B, T, M]
+    int* midx = nullptr;      // [B, T, M]
+    float* scm = nullptr;     // [B, T, ST+A] masked copy (dropout) or == sc
+    float* logp = nullptr;    // [B, T, V]
+    float* uw = nullptr;      // [KF, S]   U W_F   (location path)
+    float* qbias = nullptr;   // [S]       b_s (+ U b_F)
+    AttnScratch att;
+};
+
+int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax,
+                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out);
+int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, const float* h, const int* lengths, int B, int Lmax,
+                     const int* labels, const int* tlens, int T, const float* dropmask, float lambda, const float* dlogp, float* dh);
+
+}  // namespace s2s

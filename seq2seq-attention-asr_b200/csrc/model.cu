@@ -1,0 +1,85 @@
+// model.cu -- timit/model_chorowski_baseline.lua:20-75 end to end: 3 x bidirectional nn.RNN(nn.GRU)
+// encoder (JoinTable(2,2){fwd, rev}) -> nn.Attention decoder -> per-utterance NLL and its gradient
+// seed (timit/timit.lua:262-282).
+#include "model.cuh"
+
+#include "gru_seq.cuh"
+
+namespace s2s {
+
+// nll[b] = -sum_{t<T_b} logp[b,t,y_t]  (/T_b with S2S_NORMALIZE_NLL)     timit.lua:269-272
+__global__ void nll_kernel(const float* __restrict__ logp, const int* __restrict__ labels, const int* __restrict__ tlens,
+                           int T, int V, int flags, float* __restrict__ nll) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int Tb = tlens ? min(tlens[b], T) : T;
+    float acc = 0.f;
+    for (int t = lane; t < Tb; t += 32) {
+        const int y = labels[(size_t)b * T + t];
+        if (y >= 0 && y < V) acc -= logp[((size_t)b * T + t) * V + y];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) nll[b] = (flags & S2S_NORMALIZE_NLL) ? acc / (float)max(Tb, 1) : acc;
+}
+// dlogp = -labelmask (/T_b with S2S_NORMALIZE_GRAD), zero for t >= T_b      timit.lua:278-281
+__global__ void nll_seed_kernel(const int* __restrict__ labels, const int* __restrict__ tlens, int T, int V, int flags,
+                                float* __restrict__ dlogp) {
+    const int bt = blockIdx.x, b = bt / T, t = bt % T;
+    const int Tb = tlens ? min(tlens[b], T) : T;
+    const int y = labels[bt];
+    const float g = (t < Tb) ? ((flags & S2S_NORMALIZE_GRAD) ? -1.f / (float)Tb : -1.f) : 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) dlogp[(size_t)bt * V + v] = (v == y) ? g : 0.f;
+}
+
+int model_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* X, const int* lengths, int B, int Lmax,
+                  const int* labels, const int* tlens, int T, const float* dropmask, float lambda, int flags, float* nll, float* logp) {
+    S2S_REQUIRE(B > 0 && Lmax > 0 && T > 0, "model_forward: empty batch");
+    if (!ctx->model) ctx->model = new ModelState();
+    ModelState& m = *ctx->model;
+    m.valid = false; m.B = B; m.Lmax = Lmax; m.T = T; m.Y = Y;
+    const int H = Y.H, A = Y.A;
+    m.acts[0] = X;
+    for (int l = 0; l < Y.NL; l++) {
+        const int din = l == 0 ? Y.D : A;
+        float* out;
+        S2S_ALLOC(out, ctx->persist, float, (size_t)B * Lmax * A);
+        S2S_ALLOC(m.saves[l], ctx->persist, float, (size_t)B * Lmax * 2 * 4 * H);
+        // both directions in one launch; outputs land in the two halves (model_chorowski_baseline.lua:22-24)
+        S2S_TRY(gru_seq_forward(ctx, P + Y.enc[l][0][0].off, din, H, 2, 0, m.acts[l], din, lengths, B, Lmax, out, m.saves[l]));
+        m.acts[l + 1] = out;
+    }
+    float* lp = logp;
+    if (!lp) { S2S_ALLOC(m.logp, ctx->persist, float, (size_t)B * T * Y.V); lp = m.logp; }
+    S2S_TRY(decoder_forward(ctx, Y, P, m.acts[Y.NL], lengths, B, Lmax, labels, tlens, T, dropmask, lambda, lp));
+    if (nll) {
+        nll_kernel<<<B, 32, 0, ctx->stream>>>(lp, labels, tlens, T, Y.V, flags, nll);
+        S2S_LAUNCH_CHECK(ctx);
+    }
+    m.valid = true;
+    return 0;
+}
+
+int model_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, const float* X, const int* lengths, int B, int Lmax,
+                   const int* labels, const int* tlens, int T, const float* dropmask, float lambda, int flags, float* dX) {
+    S2S_REQUIRE(ctx->model && ctx->model->valid, "model backward called without a preceding forward on this context");
+    ModelState& m = *ctx->model;
+    S2S_REQUIRE(m.B == B && m.Lmax == Lmax && m.T == T && m.Y.n == Y.n && m.acts[0] == X, "model backward: arguments differ from the preceding forward");
+    const int H = Y.H, A = Y.A;
+    float *dlogp, *dcur;
+    S2S_ALLOC(dlogp, ctx->arena, float, (size_t)B * T * Y.V);
+    S2S_ALLOC(dcur, ctx->arena, float, (size_t)B * Lmax * A);
+    nll_seed_kernel<<<B * T, 64, 0, ctx->stream>>>(labels, tlens, T, Y.V, flags, dlogp);
+    S2S_LAUNCH_CHECK(ctx);
+    S2S_TRY(decoder_backward(ctx, Y, P, G, m.acts[Y.NL], lengths, B, Lmax, labels, tlens, T, dropmask, lambda, dlogp, dcur));
+    for (int l = Y.NL - 1; l >= 0; l--) {
+        const int din = l == 0 ? Y.D : A;
+        float* dprev = nullptr;
+        if (l > 0) S2S_ALLOC(dprev, ctx->arena, float, (size_t)B * Lmax * A);
+        else dprev = dX;
+        S2S_TRY(gru_seq_backward(ctx, P + Y.enc[l][0][0].off, G + Y.enc[l][0][0].off, din, H, 2, 0, m.acts[l], din, lengths, B, Lmax,
+                                 m.acts[l + 1], m.saves[l], dcur, dprev));
+        dcur = dprev;
+    }
+    return 0;
+}
+
+}  // namespace s2s

@@ -1,0 +1,284 @@
+"""Functional host API over the C ABI: every function takes torch CUDA tensors (fp32 / int32,
+contiguous), passes their raw device pointers to libs2s_b200.so and returns torch tensors.
+
+Nothing here computes: it is argument marshalling only.  The reference-facing module surface
+(nn.Attention, nn.RNN, ...) is in nn.py and is built on these calls.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ModelCfg, S2SError, check
+
+# timit/model_chorowski_baseline.lua:14-46 defaults
+CHOROWSKI_TIMIT = dict(D=123, H=256, NL=3, S=512, ST=256, V=62, K=0, KF=10, M=64, MW=7)
+
+NORMALIZE_NLL = 1
+NORMALIZE_GRAD = 2
+GET_ALPHA, GET_WS, GET_VH, GET_PENALTY, GET_STATE, GET_CONTEXT = range(6)
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def _f(t):
+    assert t is None or t.dtype == torch.float32, "expected float32"
+    return _p(t)
+
+
+def _i(t):
+    assert t is None or t.dtype == torch.int32, "expected int32"
+    return _p(t)
+
+
+class Context:
+    """s2s_ctx bound to a device and (by default) to torch's current stream on it."""
+
+    def __init__(self, device=0, stream="torch"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise S2SError("no CUDA device: libs2s_b200 has no CPU fallback")
+        self.device = torch.device("cuda", device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream(self.device).cuda_stream if stream == "torch" else stream
+            check(self.lib.s2s_ctx_create(int(device), C.c_void_p(s) if s else None, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.s2s_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self.lib.s2s_ctx_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.s2s_ctx_launch_count(self.h))
+
+    def set_graphs(self, enable):
+        check(self.lib.s2s_ctx_set_graphs(self.h, int(bool(enable))))
+
+    def new(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+
+# ---- layout ----------------------------------------------------------------------------------------
+def param_count(cfg):
+    return int(_lib.load().s2s_param_count(C.byref(ModelCfg.from_dict(cfg))))
+
+
+def param_segments(cfg):
+    buf = (C.c_int64 * (3 * 128))()
+    n = _lib.load().s2s_param_segments(C.byref(ModelCfg.from_dict(cfg)), buf, 128)
+    return [(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)]
+
+
+def decoder_param_offset(cfg):
+    return int(_lib.load().s2s_decoder_param_offset(C.byref(ModelCfg.from_dict(cfg))))
+
+
+# ---- dense ------------------------------------------------------------------------------------------
+def gemm(ctx, A, B, tA=False, tB=False, alpha=1.0, beta=0.0, C_out=None, bias=None, impl=0):
+    M = A.shape[1] if tA else A.shape[0]
+    K = A.shape[0] if tA else A.shape[1]
+    N = B.shape[0] if tB else B.shape[1]
+    if C_out is None:
+        C_out = ctx.zeros(M, N)
+    check(ctx.lib.s2s_gemm_f32(ctx.h, impl, int(tA), int(tB), M, N, K, alpha, _f(A), A.stride(0), _f(B), B.stride(0), beta,
+                               _f(C_out), C_out.stride(0), _f(bias)))
+    return C_out
+
+
+def tconv_zb_forward(ctx, x, W):
+    rows = x.numel() // x.shape[-1]
+    y = ctx.new(*x.shape[:-1], W.shape[0])
+    check(ctx.lib.s2s_tconv_zb_forward(ctx.h, _f(x), rows, x.shape[-1], _f(W), W.shape[0], _f(y)))
+    return y
+
+
+def tconv_zb_backward(ctx, x, W, dy, dW=None, scale=1.0, need_dx=True):
+    rows = x.numel() // x.shape[-1]
+    dx = ctx.new(*x.shape) if need_dx else None
+    check(ctx.lib.s2s_tconv_zb_backward(ctx.h, _f(x), rows, x.shape[-1], _f(W), W.shape[0], _f(dy), _f(dx), _f(dW), scale))
+    return dx
+
+
+# ---- GRU sequence ---------------------------------------------------------------------------------------
+def gru_seq_forward(ctx, W, x, lengths=None, ndir=1, reverse=False):
+    """W: [ndir*3, H, H+Din] (z, r, h~ per direction); x [B, Lmax, Din] -> y [B, Lmax, ndir*H], save"""
+    B, L, Din = x.shape
+    H = W.shape[-2]
+    assert W.shape[-1] == H + Din and W.numel() == ndir * 3 * H * (H + Din)
+    y = ctx.new(B, L, ndir * H)
+    save = ctx.new(int(ctx.lib.s2s_gru_seq_save_floats(B, L, H, ndir)))
+    check(ctx.lib.s2s_gru_seq_forward(ctx.h, _f(W), Din, H, ndir, int(reverse), _f(x), Din, _i(lengths), B, L, _f(y), _f(save)))
+    return y, save
+
+
+def gru_seq_backward(ctx, W, x, y, save, dy, lengths=None, ndir=1, reverse=False, dW=None):
+    B, L, Din = x.shape
+    H = W.shape[-2]
+    if dW is None:
+        dW = torch.zeros_like(W)
+    dx = ctx.new(B, L, Din)
+    check(ctx.lib.s2s_gru_seq_backward(ctx.h, _f(W), _f(dW), Din, H, ndir, int(reverse), _f(x), Din, _i(lengths), B, L,
+                                       _f(y), _f(save), _f(dy), _f(dx)))
+    return dx, dW
+
+
+# ---- attention decoder ---------------------------------------------------------------------------------
+def attention_forward(ctx, cfg, P, h, labels, lengths=None, tlens=None, dropmask=None, lam=0.0):
+    B, L, A = h.shape
+    T = labels.shape[1]
+    logp = ctx.new(B, T, cfg["V"])
+    check(ctx.lib.s2s_attention_forward(ctx.h, C.byref(ModelCfg.from_dict(cfg)), _f(P), _f(h), _i(lengths), B, L, _i(labels), _i(tlens), T,
+                                        _f(dropmask), lam, _f(logp)))
+    return logp
+
+
+def attention_backward(ctx, cfg, P, G, h, labels, dlogp, lengths=None, tlens=None, dropmask=None, lam=0.0):
+    B, L, A = h.shape
+    T = labels.shape[1]
+    dh = ctx.new(B, L, A)
+    check(ctx.lib.s2s_attention_backward(ctx.h, C.byref(ModelCfg.from_dict(cfg)), _f(P), _f(G), _f(h), _i(lengths), B, L, _i(labels),
+                                         _i(tlens), T, _f(dropmask), lam, _f(dlogp), _f(dh)))
+    return dh
+
+
+def attention_get(ctx, what, shape):
+    out = ctx.new(*shape)
+    check(ctx.lib.s2s_attention_get(ctx.h, what, _f(out)))
+    return out
+
+
+def attention_step(ctx, cfg, P, h, Vh, yprev=None, alpha_prev=None, s_prev=None, lengths=None):
+    B, L, A = h.shape
+    alpha = ctx.new(B, L); s = ctx.new(B, cfg["ST"]); logp = ctx.new(B, cfg["V"])
+    check(ctx.lib.s2s_attention_step(ctx.h, C.byref(ModelCfg.from_dict(cfg)), _f(P), _f(h), _f(Vh), _i(lengths), B, L, _i(yprev),
+                                     _f(alpha_prev), _f(s_prev), _f(alpha), _f(s), _f(logp)))
+    return alpha, s, logp
+
+
+def beam_search(ctx, cfg, P, h, eos, beam=5, maxlen=None):
+    """Attention:BeamSearch for one utterance h [L, A]; returns (labels list, total log-prob)"""
+    L = h.shape[0]
+    maxlen = maxlen or L
+    out = (C.c_int * (maxlen + 2))()
+    n = C.c_int(0)
+    lp = C.c_float(0)
+    check(ctx.lib.s2s_beam_search(ctx.h, C.byref(ModelCfg.from_dict(cfg)), _f(P), _f(h), L, int(eos), int(beam), int(maxlen),
+                                  out, C.byref(n), C.byref(lp)))
+    return [out[i] for i in range(n.value)], float(lp.value)
+
+
+# ---- whole model ----------------------------------------------------------------------------------------
+def model_forward(ctx, cfg, P, X, labels, lengths=None, tlens=None, dropmask=None, lam=0.0, flags=0, want_logp=True):
+    B, L, D = X.shape
+    T = labels.shape[1]
+    nll = ctx.new(B)
+    logp = ctx.new(B, T, cfg["V"]) if want_logp else None
+    check(ctx.lib.s2s_model_forward(ctx.h, C.byref(ModelCfg.from_dict(cfg)), _f(P), _f(X), _i(lengths), B, L, _i(labels), _i(tlens), T,
+                                    _f(dropmask), lam, flags, _f(nll), _f(logp)))
+    return nll, logp
+
+
+def model_fwdbwd(ctx, cfg, P, G, X, labels, lengths=None, tlens=None, dropmask=None, lam=0.0, flags=0, nll=None, logp=None, dX=None):
+    """G is accumulated (zero it first, as autoencoder:zeroGradParameters() does)."""
+    B, L, D = X.shape
+    T = labels.shape[1]
+    if nll is None:
+        nll = ctx.new(B)
+    check(ctx.lib.s2s_model_fwdbwd(ctx.h, C.byref(ModelCfg.from_dict(cfg)), _f(P), _f(G), _f(X), _i(lengths), B, L, _i(labels), _i(tlens), T,
+                                   _f(dropmask), lam, flags, _f(nll), _f(logp), _f(dX)))
+    return nll
+
+
+def model_annotations(ctx, B, L, A):
+    out = ctx.new(B, L, A)
+    check(ctx.lib.s2s_model_get_annotations(ctx.h, _f(out)))
+    return out
+
+
+# ---- noise / optimiser --------------------------------------------------------------------------------
+def weightnoise_sample(ctx, w, sigma, eps=None, seed=0):
+    out = torch.empty_like(w)
+    check(ctx.lib.s2s_weightnoise_sample(ctx.h, _f(w), _f(eps), seed, sigma, w.numel(), _f(out)))
+    return out
+
+
+def awn_sample(ctx, weight, eps=None, seed=0):
+    n = weight.numel() // 2
+    out = ctx.new(n)
+    check(ctx.lib.s2s_awn_sample(ctx.h, _f(weight), _f(eps), seed, n, _f(out)))
+    return out
+
+
+def awn_forward(ctx, weight, lam, nll):
+    L = C.c_double(0)
+    check(ctx.lib.s2s_awn_forward(ctx.h, _f(weight), weight.numel() // 2, lam, nll, C.byref(L)))
+    return float(L.value)
+
+
+def awn_accgrad(ctx, weight, g, lam):
+    gw = torch.empty_like(weight)
+    check(ctx.lib.s2s_awn_accgrad(ctx.h, _f(weight), _f(g), g.numel(), lam, _f(gw)))
+    return gw
+
+
+def grad_finalize(ctx, g, p, batch, maxnorm, wd=0.0, noise=None, seed=0, noise_sigma=0.0, want_norm=True):
+    nrm = C.c_double(0)
+    check(ctx.lib.s2s_grad_finalize(ctx.h, _f(g), _f(p), g.numel(), batch, maxnorm, wd, _f(noise), seed, noise_sigma,
+                                    C.byref(nrm) if want_norm else None))
+    return float(nrm.value) if want_norm else None
+
+
+def adadelta(ctx, x, g, v, a, rho=0.95, eps=1e-8):
+    check(ctx.lib.s2s_adadelta(ctx.h, _f(x), _f(g), _f(v), _f(a), x.numel(), rho, eps))
+
+
+def rownorm_constraint(ctx, W, maxval=1.0):
+    flag = C.c_int(0)
+    check(ctx.lib.s2s_rownorm_constraint(ctx.h, _f(W), W.shape[0], W.shape[1], maxval, C.byref(flag)))
+    return flag.value
+
+
+def model_rownorm_constraint(ctx, cfg, P, maxval=1.0):
+    flag = C.c_int(0)
+    check(ctx.lib.s2s_model_rownorm_constraint(ctx.h, C.byref(ModelCfg.from_dict(cfg)), _f(P), maxval, C.byref(flag)))
+    return flag.value
+
+
+# ---- kernel-level hooks (microbenchmarks) -------------------------------------------------------------
+def attn_step_forward(ctx, Vh, h, q, w, lengths=None, alpha=None, c=None):
+    B, L, S = Vh.shape
+    A = h.shape[2]
+    alpha = ctx.new(B, L) if alpha is None else alpha
+    c = ctx.new(B, A) if c is None else c
+    check(ctx.lib.s2s_attn_step_forward(ctx.h, _f(Vh), _f(h), _f(q), _f(w), _i(lengths), B, L, S, A, _f(alpha), _f(c)))
+    return alpha, c
+
+
+def attn_step_backward(ctx, Vh, h, q, w, alpha, dc, dalpha_in=None, lengths=None, dq=None, de=None):
+    B, L, S = Vh.shape
+    A = h.shape[2]
+    dq = ctx.new(B, S) if dq is None else dq
+    de = ctx.new(B, L) if de is None else de
+    check(ctx.lib.s2s_attn_step_backward(ctx.h, _f(Vh), _f(h), _f(q), _f(w), _i(lengths), B, L, S, A, _f(alpha), _f(dc), _f(dalpha_in),
+                                         _f(dq), _f(de)))
+    return dq, de

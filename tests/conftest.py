@@ -38,3 +38,24 @@ def orc64():
     from oracle.oracle import Oracle, build
     build()
     return Oracle("f64")
+
+
+@pytest.fixture(scope="session")
+def s2s():
+    import s2s_b200
+    return s2s_b200
+
+
+@pytest.fixture(scope="session")
+def gctx(s2s):
+    """One library context on cuda:0 for the whole GPU test session."""
+    ctx = s2s.Context(0)
+    yield ctx
+    ctx.close()
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| (scale of the reference)"""
+    import numpy as np
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))

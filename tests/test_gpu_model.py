@@ -1,0 +1,152 @@
+"""GPU parity of nn.Attention and the whole Chorowski model (forward, per-utterance NLL, every
+gradient) against the CPU oracle run per utterance exactly like timit/timit.lua:240-289.
+All calls go through the C ABI.  Bound: <= 1e-4 relative (fp32), stated by north_star."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import init_params
+from tests.util import dev, make_batch, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+MID = dict(D=13, H=128, NL=2, S=128, ST=64, V=11, K=0, KF=4, M=8, MW=3)
+
+
+def _seg_errs(cfg, orc, G, Gref):
+    from oracle.oracle import segment_names
+    out = {}
+    for (off, rows, cols), name in zip(orc.param_segments(cfg), segment_names(cfg)):
+        a, b = G[off:off + rows * cols], Gref[off:off + rows * cols]
+        scale = max(np.abs(b).max(), 1e-6 * np.abs(Gref).max())
+        out[name] = float(np.abs(a - b).max() / scale)
+    return out
+
+
+@pytest.mark.parametrize("K,KF,lam,drop", [(0, 4, 0.0, False), (0, 4, 0.0, True), (3, 4, 0.0, False), (4, 5, 0.0, False),
+                                           (2, 10, 0.02, False), (0, 4, 0.05, False)])
+def test_attention_module_matches_oracle(s2s, gctx, orc64, K, KF, lam, drop):
+    cfg = dict(MID, K=K, KF=KF)
+    B, L, T = 4, 45, 7
+    P = init_params(cfg, seed=5, dtype=np.float64, oracle=orc64) * 1.5
+    rng = np.random.default_rng(1)
+    A = 2 * cfg["H"]
+    h = rng.standard_normal((B, L, A)) * 0.7
+    _, lengths, labels, tlens = make_batch(cfg, B, L, T, seed=2)
+    dm = ((rng.random((B, T, cfg["ST"] + A)) > 0.5) / 0.5) if drop else None
+    dlogp = rng.standard_normal((B, T, cfg["V"]))
+    for b in range(B):
+        h[b, lengths[b]:] = 0; dlogp[b, tlens[b]:] = 0
+    Pd, hd = dev(P, torch.float32), dev(h, torch.float32)
+    ld, yd, td = dev(lengths), dev(labels), dev(tlens)
+    dmd = dev(dm, torch.float32) if drop else None
+    logp = s2s.attention_forward(gctx, cfg, Pd, hd, yd, lengths=ld, tlens=td, dropmask=dmd, lam=lam)
+    alpha = s2s.attention_get(gctx, s2s.GET_ALPHA, (B, T, L)).cpu().numpy()
+    pen = s2s.attention_get(gctx, s2s.GET_PENALTY, (B, T)).cpu().numpy()
+    G = torch.zeros_like(Pd)
+    dh = s2s.attention_backward(gctx, cfg, Pd, G, hd, yd, dev(dlogp, torch.float32), lengths=ld, tlens=td, dropmask=dmd, lam=lam)
+    logp = logp.cpu().numpy(); dh = dh.cpu().numpy(); G = G.cpu().numpy()
+    Gref = np.zeros_like(P)
+    for b in range(B):
+        Lb, Tb = lengths[b], tlens[b]
+        dmb = dm[b, :Tb] if drop else None
+        ref = orc64.attention_forward(cfg, P, h[b, :Lb], labels[b, :Tb], lam=lam, dropmask=dmb)
+        assert rel_err(logp[b, :Tb], ref["logp"]) < TOL
+        assert rel_err(alpha[b, :Tb, :Lb], ref["alpha"]) < TOL
+        assert np.abs(pen[b, :Tb] - ref["pen"]).max() < TOL * max(1.0, np.abs(ref["pen"]).max())
+        Gb, dhb = orc64.attention_backward(cfg, P, h[b, :Lb], labels[b, :Tb], dlogp[b, :Tb], lam=lam, dropmask=dmb)
+        Gref += Gb
+        assert rel_err(dh[b, :Lb], dhb) < TOL
+        assert np.abs(dh[b, Lb:]).max() == 0.0 if Lb < L else True
+    errs = _seg_errs(cfg, orc64, G, Gref)
+    bad = {k: v for k, v in errs.items() if v > TOL}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("K,KF", [(0, 4), (3, 6)])
+def test_model_fwdbwd_matches_oracle(s2s, gctx, orc64, K, KF):
+    cfg = dict(MID, K=K, KF=KF)
+    B, L, T = 5, 40, 6
+    P = init_params(cfg, seed=11, dtype=np.float64, oracle=orc64) * 1.5
+    X, lengths, labels, tlens = make_batch(cfg, B, L, T, seed=3)
+    ref = orc64.model_fwdbwd(cfg, P, X, lengths, labels, tlens, normalize_nll=True, nthreads=4)
+    Pd = dev(P, torch.float32); G = torch.zeros_like(Pd)
+    Xd, ld, yd, td = dev(X), dev(lengths), dev(labels), dev(tlens)
+    logp = gctx.new(B, T, cfg["V"]); dX = gctx.new(B, L, cfg["D"])
+    nll = s2s.model_fwdbwd(gctx, cfg, Pd, G, Xd, yd, lengths=ld, tlens=td, flags=s2s.NORMALIZE_NLL, logp=logp, dX=dX)
+    annot = s2s.model_annotations(gctx, B, L, 2 * cfg["H"]).cpu().numpy()
+    assert rel_err(nll.cpu().numpy(), ref["nll"]) < TOL
+    logp = logp.cpu().numpy(); dX = dX.cpu().numpy()
+    for b in range(B):
+        Lb, Tb = lengths[b], tlens[b]
+        assert rel_err(annot[b, :Lb], ref["annot"][b, :Lb]) < TOL
+        assert rel_err(logp[b, :Tb], ref["logp"][b, :Tb]) < TOL
+        assert rel_err(dX[b, :Lb], ref["dX"][b, :Lb]) < TOL
+    errs = _seg_errs(cfg, orc64, G.cpu().numpy(), ref["G"])
+    bad = {k: v for k, v in errs.items() if v > TOL}
+    assert not bad, bad
+    # forward-only entry gives the same loss
+    nll2, _ = s2s.model_forward(gctx, cfg, Pd, Xd, yd, lengths=ld, tlens=td, flags=s2s.NORMALIZE_NLL)
+    assert torch.equal(nll2, nll)
+
+
+def test_batch_equals_per_utterance(s2s, gctx, orc64):
+    # invariant lifted from the reference notebooks (Attention.ipynb:1202/1763): a batch gives the
+    # same rows as utterance-at-a-time ("SGD mode") calls
+    cfg = dict(MID)
+    B, L, T = 3, 33, 5
+    P = dev(init_params(cfg, seed=2, dtype=np.float64, oracle=orc64), torch.float32)
+    X, lengths, labels, tlens = make_batch(cfg, B, L, T, seed=8)
+    nll_b, logp_b = s2s.model_forward(gctx, cfg, P, dev(X), dev(labels), lengths=dev(lengths), tlens=dev(tlens))
+    for b in range(B):
+        Lb, Tb = int(lengths[b]), int(tlens[b])
+        nll_1, logp_1 = s2s.model_forward(gctx, cfg, P, dev(X[b:b + 1, :Lb]), dev(labels[b:b + 1, :Tb]))
+        assert rel_err(logp_1[0].cpu().numpy(), logp_b[b, :Tb].cpu().numpy()) < 1e-5
+        assert abs(float(nll_1[0]) - float(nll_b[b])) < 1e-4 * abs(float(nll_b[b]))
+
+
+def test_optimizer_and_noise_match_oracle(s2s, gctx, orc32, orc64):
+    rng = np.random.default_rng(0)
+    n = 10007
+    w = rng.standard_normal(n).astype(np.float32) * 0.1; eps = rng.standard_normal(n).astype(np.float32)
+    assert rel_err(s2s.weightnoise_sample(gctx, dev(w), 0.075, eps=dev(eps)).cpu().numpy(), orc64.weightnoise_sample(w, eps, 0.075)) < 1e-6
+    weight = np.concatenate([w, np.log(0.075 ** 2) + 0.1 * rng.standard_normal(n)]).astype(np.float32)
+    assert rel_err(s2s.awn_sample(gctx, dev(weight), eps=dev(eps)).cpu().numpy(), orc64.awn_sample(weight, eps)) < 1e-5
+    Lg = s2s.awn_forward(gctx, dev(weight), 1.0, 3.25); Lr = orc64.awn_forward(weight, 1.0, 3.25)
+    assert abs(Lg - Lr) < 1e-5 * abs(Lr)
+    g = rng.standard_normal(n).astype(np.float32)
+    assert rel_err(s2s.awn_accgrad(gctx, dev(weight), dev(g), 1.0).cpu().numpy(), orc64.awn_accgrad(weight, g, 1.0)) < 1e-5
+    # gradient step: /B, clip, weight decay, injected noise, adadelta, row-norm constraint
+    gd = dev(g.copy()); noise = rng.standard_normal(n).astype(np.float32)
+    nrm = s2s.grad_finalize(gctx, gd, dev(w), 8, 0.5, wd=1e-3, noise=dev(noise), noise_sigma=0.01)
+    gr = g.astype(np.float64).copy()
+    nr = orc64.grad_finalize(gr, w, 8, 0.5, 1e-3, noise, 0.01)
+    assert abs(nrm - nr) < 1e-5 * nr and rel_err(gd.cpu().numpy(), gr) < 1e-5
+    x, v, a = dev(w.copy()), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    xr, vr, ar = w.astype(np.float64).copy(), np.zeros(n), np.zeros(n)
+    for _ in range(3):
+        s2s.adadelta(gctx, x, gd, v, a); orc64.adadelta(xr, gr, vr, ar)
+    assert rel_err(x.cpu().numpy(), xr) < 1e-5
+    Wm = (rng.standard_normal((37, 53)) * rng.uniform(0.01, 0.4, (37, 1))).astype(np.float32)
+    Wd = dev(Wm.copy()); Wr = Wm.astype(np.float64).copy()
+    assert s2s.rownorm_constraint(gctx, Wd, 1.0) == 0 and orc64.rownorm_constraint(Wr, 1.0) == 0
+    assert rel_err(Wd.cpu().numpy(), Wr) < 1e-6
+    Wn = Wm.copy(); Wn[3, 4] = np.nan
+    assert s2s.rownorm_constraint(gctx, dev(Wn), 1.0) == 1
+    # Philox sampler: right moments
+    z = (s2s.weightnoise_sample(gctx, torch.zeros(1 << 20, device="cuda"), 1.0, seed=7)).cpu().numpy()
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+
+
+def test_beam_search_matches_oracle(s2s, gctx, orc32, orc64):
+    cfg = dict(MID, K=3, KF=4)
+    P = init_params(cfg, seed=21, dtype=np.float64, oracle=orc64) * 3.0
+    rng = np.random.default_rng(4)
+    for trial in range(3):
+        L = 20 + 7 * trial
+        h = rng.standard_normal((L, 2 * cfg["H"]))
+        ref_y, ref_lp = orc64.beam_search(cfg, P, h, eos=cfg["V"] - 1, K=4, maxlen=12)
+        y, lp = s2s.beam_search(gctx, cfg, dev(P, torch.float32), dev(h, torch.float32), eos=cfg["V"] - 1, beam=4, maxlen=12)
+        assert list(ref_y) == y            # bit-exact label sequence
+        assert abs(lp - ref_lp) < 1e-3 * max(1.0, abs(ref_lp))
