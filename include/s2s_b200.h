@@ -57,7 +57,7 @@ typedef struct s2s_model_cfg {
 #define S2S_NORMALIZE_GRAD  2   /* dlogp = -labelmask/T_b (timit.lua:279-281) */
 
 /* ---- context ------------------------------------------------------------------------------ */
-/* `stream` is a cudaStream_t (NULL = the library creates its own non-blocking stream). */
+/* `stream` is a cudaStream_t; NULL = the legacy default stream (cutorch's default, timit/timit.lua:39). */
 int  s2s_ctx_create(int device, void* stream, s2s_ctx** out);
 int  s2s_ctx_destroy(s2s_ctx* ctx);
 int  s2s_ctx_set_stream(s2s_ctx* ctx, void* stream);

@@ -49,6 +49,8 @@ struct AttnFwdParams {
     float lambda;
     const float* app;   // alpha_{t-1} for the penalty
     int64_t ld_app;
+    const int* tlens;   // padded decoder steps (tstep >= T_b) record no penalty
+    int tstep;
 };
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -99,7 +101,7 @@ attn_fwd_kernel(const AttnFwdParams p) {
     {
         const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
 #pragma unroll
-        for (int i = 0; i < NS; i++) { qv[i] = ldg4(qb + i * 128); wv[i] = ldg4(p.w + lane * 4 + i * 128); }
+        for (int i = 0; i < NS; i++) { qv[i] = ldg4(qb + i * 128); wv[i] = ldg4_any(p.w + lane * 4 + i * 128); }
     }
     const float* vbase = p.Vh + ((size_t)b * p.Lmax + l0) * S + lane * 4;
     float4 v[4][NS];
@@ -226,7 +228,8 @@ attn_fwd_kernel(const AttnFwdParams p) {
         if (tid == 0) {
             float t = 0.f;
             for (int i = 0; i < 8; i++) t += wred[i];
-            p.pen[(size_t)b * p.ld_pen] = p.lambda * fmaxf(t, 0.f);
+            const bool padded = p.tlens && p.tstep >= p.tlens[b];
+            p.pen[(size_t)b * p.ld_pen] = padded ? 0.f : p.lambda * fmaxf(t, 0.f);
         }
     }
     if (tid == 0) p.counters[b] = 0u;
@@ -282,7 +285,7 @@ attn_bwd_kernel(const AttnBwdParams p) {
     {
         const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
 #pragma unroll
-        for (int i = 0; i < NS; i++) { qv[i] = ldg4(qb + i * 128); wv[i] = ldg4(p.w + lane * 4 + i * 128); }
+        for (int i = 0; i < NS; i++) { qv[i] = ldg4(qb + i * 128); wv[i] = ldg4_any(p.w + lane * 4 + i * 128); }
         const float* db = p.dc + (size_t)b * p.ld_dc + lane * 4;
 #pragma unroll
         for (int i = 0; i < NA; i++) dcv[i] = ldg4(db + i * 128);
@@ -598,14 +601,14 @@ static int check_dims(int S, int A, int KF) {
 
 int attn_step_fwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const float* h, const float* q, int64_t ldq, const float* w,
                   const int* lengths, int B, int Lmax, int S, int A, const AttnLoc& loc, float* alpha, int64_t ld_alpha, float* c,
-                  int64_t ld_c, float* pen, int64_t ld_pen, float lambda, const float* app, int64_t ld_app) {
+                  int64_t ld_c, float* pen, int64_t ld_pen, float lambda, const float* app, int64_t ld_app, const int* tlens, int tstep) {
     S2S_TRY(check_dims(S, A, loc.KF));
     AttnFwdParams p;
     p.Vh = Vh; p.h = h; p.q = q; p.w = w; p.ldq = ldq; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.nch = sc.nch;
     p.KF = loc.KF; p.padl = loc.padl; p.uw = loc.uw; p.alpha_prev = loc.alpha_prev; p.ld_aprev = loc.ld_aprev;
     p.E = sc.E; p.part_ms = sc.part_ms; p.part_c = sc.part_c; p.counters = sc.counters;
     p.alpha = alpha; p.c = c; p.pen = pen; p.ld_alpha = ld_alpha; p.ld_c = ld_c; p.ld_pen = ld_pen; p.lambda = lambda;
-    p.app = app; p.ld_app = ld_app;
+    p.app = app; p.ld_app = ld_app; p.tlens = tlens; p.tstep = tstep;
     if (loc.KF > 0) ATT_DISPATCH(launch_fwd, true, ctx, p, loc.KF);
     else ATT_DISPATCH(launch_fwd, false, ctx, p, 0);
 }

@@ -34,7 +34,7 @@ struct AttnLoc {                 // location-aware term (Attention.lua:75-99), f
 int attn_step_fwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const float* h, const float* q, int64_t ldq,
                   const float* w, const int* lengths, int B, int Lmax, int S, int A, const AttnLoc& loc,
                   float* alpha, int64_t ld_alpha, float* c, int64_t ld_c, float* pen, int64_t ld_pen, float lambda,
-                  const float* alpha_prev_pen, int64_t ld_app);
+                  const float* alpha_prev_pen, int64_t ld_app, const int* tlens = nullptr, int tstep = 0);
 
 // backward step (single pass over h and Vh):
 //   dalpha = h.dc + dalpha_in ; de = alpha (dalpha - <alpha,dalpha>) ; dq = sum_l de_l w (1 - tanh^2 Z_l)

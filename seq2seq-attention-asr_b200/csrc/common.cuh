@@ -145,6 +145,12 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
     return r;
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 4 consecutive floats from a pointer that may not be 16-byte aligned (segments of the flat parameter
+// vector start at arbitrary float offsets, e.g. after the 1-element bias of the `e` convolution)
+__device__ __forceinline__ float4 ldg4_any(const float* p) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+    return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
 // L2-coherent loads for data produced by other CTAs of the same launch
 __device__ __forceinline__ float ldcg1(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }

@@ -182,8 +182,8 @@ int s2s_ctx_create(int device, void* stream, s2s_ctx** out) {
     s2s_ctx* c = new s2s_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
-    else { S2S_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    c->stream = (cudaStream_t)stream;   // NULL = the legacy default stream (what cutorch uses, timit/timit.lua:39)
+    c->own_stream = false;
     for (int i = 0; i < 2; i++) S2S_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
     for (int i = 0; i < 4; i++) S2S_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
     S2S_CUDA(cudaMalloc((void**)&c->counters, 4096 * sizeof(unsigned)));
@@ -194,9 +194,7 @@ int s2s_ctx_create(int device, void* stream, s2s_ctx** out) {
 
 int s2s_ctx_set_stream(s2s_ctx* ctx, void* stream) {
     S2S_REQUIRE(ctx, "ctx is NULL");
-    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
-    if (stream) ctx->stream = (cudaStream_t)stream;
-    else { S2S_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    ctx->stream = (cudaStream_t)stream;
     return 0;
 }
 int s2s_ctx_synchronize(s2s_ctx* ctx) {

@@ -46,7 +46,7 @@ dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const
 #pragma unroll
         for (int i = 0; i < KV; i++) {
             const int k4 = lane + i * 32;
-            w[i] = k4 < K4 ? ldg4(W + (size_t)n * ldw + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[i] = k4 < K4 ? ldg4_any(W + (size_t)n * ldw + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     for (int b0 = 0; b0 < B; b0 += 32) {
@@ -110,7 +110,7 @@ dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const
 }
 
 static int dense_small(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, const float* W, int ldw, int N, const DenseEpi& e) {
-    S2S_REQUIRE(K % 4 == 0 && ldw % 4 == 0 && ldx % 4 == 0, "dense_small: K (%d), ldw (%d), ldx (%ld) must be multiples of 4", K, ldw, (long)ldx);
+    S2S_REQUIRE(K % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "dense_small: K (%d) and ldx (%ld) must be multiples of 4 and X 16-byte aligned", K, (long)ldx);
     S2S_REQUIRE(K <= 1024, "dense_small: K=%d > 1024 not supported", K);
     const int kv = ceil_div(K, 128);
     const size_t smem = (size_t)32 * K * 4;
@@ -335,7 +335,7 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
             loc.alpha_prev = t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr; loc.ld_aprev = (int64_t)T * Lmax;
             S2S_TRY(attn_step_fwd(ctx, d.att, d.Vh, h, d.q + (size_t)t * S, (int64_t)T * S, P + Y.we.off, lengths, B, Lmax, S, A, loc,
                                   d.alpha + (size_t)t * Lmax, (int64_t)T * Lmax, d.sc + (size_t)t * (ST + A) + ST, ldsc,
-                                  d.pen + t, T, lambda, t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr, (int64_t)T * Lmax));
+                                  d.pen + t, T, lambda, t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr, (int64_t)T * Lmax, tlens, t));
         }
         {   // c_in = W_c c_t + b_c   (Attention.lua:150)
             DenseEpi e; e.bias = P + Y.bc.off; e.out = d.cin + (size_t)t * ST; e.ld_out = (int64_t)T * ST;

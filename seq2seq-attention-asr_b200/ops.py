@@ -47,7 +47,7 @@ class Context:
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             s = torch.cuda.current_stream(self.device).cuda_stream if stream == "torch" else stream
-            check(self.lib.s2s_ctx_create(int(device), C.c_void_p(s) if s else None, C.byref(h)))
+            check(self.lib.s2s_ctx_create(int(device), C.c_void_p(int(s or 0)), C.byref(h)))
         self.h = h
 
     def close(self):

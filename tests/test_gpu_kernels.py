@@ -67,7 +67,7 @@ def test_attn_step_forward_backward(s2s, gctx, B, L, S, A):
     dq_g, de_g = s2s.attn_step_backward(gctx, dVh, dh, dq_, dw, dev(alpha_ref, torch.float32), dev(dc, torch.float32),
                                         dalpha_in=dev(dain, torch.float32), lengths=dl)
     assert rel_err(de_g.cpu().numpy(), de_ref) < TOL
-    assert rel_err(dq_g.cpu().numpy(), dq_ref) < TOL
+    assert rel_err(dq_g.cpu().numpy(), dq_ref, floor=1e-2) < TOL   # L = 1 gives de = 0 exactly: absolute floor
 
 
 @pytest.mark.parametrize("H,Din,B,L,ndir,reverse", [(128, 20, 5, 37, 1, False), (128, 20, 5, 37, 1, True), (256, 123, 6, 50, 2, False),

@@ -2,9 +2,10 @@
 import numpy as np
 
 
-def rel_err(a, b):
+def rel_err(a, b, floor=1e-6):
+    """max |a-b| over max |b| (the reference's scale; `floor` guards references that are exactly zero)"""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
 
 
 def make_batch(cfg, B, Lmax, Tmax, seed, ragged=True):
