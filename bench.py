@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- Chorowski TIMIT forward+backward(+gradient step) throughput on 1..8 B200.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  N > 1 is launched by torch.distributed.run (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
+
+Workload ("step"): one pass of the training hot path over one synthetic minibatch of BASELINE.json
+configs[1]: timit/model_chorowski_baseline.lua, batch 32 PER GPU (weak scaling), L = 300 log-mel
+frames of D = 123, T = 50 labels of V = 62, content-only attention (the shipped default, K = 0):
+zero grads -> encoder/decoder forward -> per-utterance NLL -> backward -> [all-reduce of the flat
+gradient over NCCL] -> /B, clip, adadelta, row-norm constraint (timit/timit.lua:233-348).
+  value   : frames/s with inputs resident in HBM (CUDA events on the launching stream, per-step events,
+            L2 flushed between steps by a 256 MiB write outside the event pairs; max over ranks)
+  e2e     : the same metric through the public host API with HOST buffers (pinned): H2D of the
+            batch and D2H of the per-utterance NLL inside the timed region
+  roofline: the kernel class with the largest share of the step, timed live with CUDA events by the
+            library's profiling hook on an instrumented extra pass (s2s_ctx_profile)
+  cpu_baseline: the CPU oracle (a C restatement of the reference; Torch7 cannot run here) on a
+            bounded sample of the same workload, all host threads
+`--impl reference` times that CPU oracle alone (the reference's own implementation is Lua/Torch7 and
+cannot be installed in this image: see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(D=123, H=256, NL=3, S=512, ST=256, V=62, K=0, KF=10, M=64, MW=7)
+B_PER_GPU, L, T = 32, 300, 50
+METRIC = "chorowski_timit_fwd_bwd_frames_per_sec"
+WORKLOAD = ("cfg2: timit/model_chorowski_baseline.lua (3x biGRU-256 encoder, content attention K=0, GRU-256 decoder, "
+            "maxout 64x7), batch 32/GPU, L=300, D=123, T=50, V=62; step = zero-grad + fwd + NLL + bwd + "
+            "[all-reduce] + /B + clip + adadelta + row-norm")
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def synth(seed, B):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((B, L, CFG["D"])).astype(np.float32)
+    labels = rng.integers(0, CFG["V"] - 1, (B, T)).astype(np.int32)
+    labels[:, -1] = CFG["V"] - 1
+    lengths = np.full(B, L, np.int32)
+    tlens = np.full(B, T, np.int32)
+    return X, labels, lengths, tlens
+
+
+# -------------------------------------------------------------------------------------------------
+def cpu_oracle_run(nutt, nthreads, reps=1):
+    """frames/s of the CPU oracle (fp32, OpenMP over utterances) on `nutt` utterances of the workload"""
+    from oracle.oracle import Oracle, build, init_params
+    build()
+    o = Oracle("f32")
+    P = init_params(CFG, seed=1234, dtype=np.float32, oracle=Oracle("f64"))
+    X, labels, lengths, tlens = synth(99, nutt)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        o.model_fwdbwd(CFG, P, X, lengths, labels, tlens, nthreads=nthreads, want=())
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return nutt * L / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_threads()
+    nthreads = max(1, min(cores, 32))
+    nutt = nthreads   # one utterance per thread per step: a bounded sample of the batch-32 workload
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_run(nutt, nthreads)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_oracle_run(nutt, nthreads)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = nutt * L / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_arm": "CPU oracle (oracle/s2s_oracle.c, C restatement of the Torch7 path; "
+                   "the Lua reference cannot be installed: no LuaJIT/Torch7 in the image)"},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": nthreads, "kind": "port",
+                         "sample": f"{nutt} utterances (L={L}, T={T}) per step, fwd+bwd, OpenMP over utterances"},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.dev)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import s2s_b200 as s2s
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = s2s.Context(local)
+    B = B_PER_GPU
+    n = s2s.param_count(CFG)
+
+    P = torch.from_numpy(s2s.init_params(CFG, seed=1234)).to(dev)
+    G = torch.zeros(n, device=dev)
+    v_state = torch.zeros(n, device=dev); a_state = torch.zeros(n, device=dev)
+    Xh, yh, lh, th = synth(1000 + rank, B)
+    X = torch.from_numpy(Xh).to(dev); y = torch.from_numpy(yh).to(dev)
+    ln = torch.from_numpy(lh).to(dev); tl = torch.from_numpy(th).to(dev)
+    nll = torch.zeros(B, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(Xd, yd, lnd, tld):
+        G.zero_()                                                     # zeroGradParameters (timit.lua:233)
+        s2s.model_fwdbwd(ctx, CFG, P, G, Xd, yd, lengths=lnd, tlens=tld, flags=s2s.NORMALIZE_NLL, nll=nll)
+        if world > 1:
+            dist.all_reduce(G)                                        # data-parallel gradient sum over NVLink
+        s2s.grad_finalize(ctx, G, P, B * world, 1e20, want_norm=False)   # /B, norm, clip (timit.lua:292-302)
+        s2s.adadelta(ctx, P, G, v_state, a_state, rho=0.95, eps=1e-8)    # optim.adadelta (timit.lua:338-342)
+        s2s.model_rownorm_constraint(ctx, CFG, P, 1.0)                   # timit.lua:346-348
+        return nll
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(X, y, ln, tl)
+    barrier()
+
+    # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps ------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = ctx.launches
+    barrier()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        step(X, y, ln, tl)
+        b.record()
+    barrier()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    frames = B * L * world
+    value = frames / (ms / 1e3)
+
+    # ---- e2e: host buffers -> H2D -> step -> D2H(nll), wall clock with device sync, max over ranks ------
+    Xp = torch.from_numpy(Xh).pin_memory(); yp = torch.from_numpy(yh).pin_memory()
+    lp = torch.from_numpy(lh).pin_memory(); tp = torch.from_numpy(th).pin_memory()
+    Xd = torch.empty_like(X); yd = torch.empty_like(y); lnd = torch.empty_like(ln); tld = torch.empty_like(tl)
+    nll_h = torch.empty(B, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        Xd.copy_(Xp, non_blocking=True); yd.copy_(yp, non_blocking=True)
+        lnd.copy_(lp, non_blocking=True); tld.copy_(tp, non_blocking=True)
+        step(Xd, yd, lnd, tld)
+        nll_h.copy_(nll, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(nll_h.sum())
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = Xp.numel() * 4 + yp.numel() * 4 + lp.numel() * 4 + tp.numel() * 4
+    d2h = nll_h.numel() * 4
+
+    # ---- roofline: instrumented extra pass (graphs off), per-kernel-class CUDA events ------------------
+    roof = None
+    classes = {}
+    if rank == 0:
+        hbm, tf, how = peaks()
+        ctx.set_graphs(False)
+        ctx.profile(True)
+        ev2 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        nprof = 3
+        ev2[0].record()
+        for _ in range(nprof):
+            step(X, y, ln, tl)
+        ev2[1].record()
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        ctx.set_graphs(True)
+        total_ms = ev2[0].elapsed_time(ev2[1]) / nprof
+        for k, (kms, cnt, work) in prof.items():
+            if cnt == 0:
+                continue
+            per_launch_ms = kms / cnt
+            ach = work / cnt / (per_launch_ms * 1e-3)
+            if k == "gemm":
+                classes[k] = {"bound": "tensor", "ms_per_step": kms / nprof, "launches_per_step": cnt / nprof, "achieved": ach / 1e12,
+                              "peak": tf, "unit": "TFLOP/s", "frac": ach / 1e12 / tf, "share": kms / nprof / total_ms,
+                              "note": "exact-fp32 SIMT FFMA path (not tensor cores)"}
+            else:
+                classes[k] = {"bound": "hbm", "ms_per_step": kms / nprof, "launches_per_step": cnt / nprof, "achieved": ach / 1e9,
+                              "peak": hbm, "unit": "GB/s", "frac": ach / 1e9 / hbm, "share": kms / nprof / total_ms}
+        top = max(classes, key=lambda k: classes[k]["ms_per_step"])
+        c = classes[top]
+        roof = {"kernel": top, "bound": c["bound"], "achieved": c["achieved"], "peak": c["peak"], "unit": c["unit"], "frac": c["frac"],
+                "traffic": None, "peak_source": how, "share_of_step": c["share"], "instrumented_step_ms": total_ms}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_threads()
+        nthreads = max(1, min(cores, 32))
+        nutt = nthreads * (2 if nthreads <= 16 else 1)
+        val, dt = cpu_oracle_run(nutt, nthreads)
+        cpu = {"value": val, "unit": "frames/s", "cores": nthreads, "kind": "port",
+               "sample": f"{nutt} utterances (L={L}, T={T}) fwd+bwd once, fp32 C oracle, OpenMP over utterances, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "flushed between timed steps (256 MiB write outside the per-step event pairs)"},
+            "e2e": {"value": frames / (e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": classes,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,21 @@ int64_t s2s_ctx_launch_count(s2s_ctx* ctx);
 /* enable (1) / disable (0) CUDA-graph replay of s2s_model_fwdbwd for repeated shapes */
 int  s2s_ctx_set_graphs(s2s_ctx* ctx, int enable);
 
+/* Per-kernel-class device timing with CUDA events on the context's stream (bench.py roofline).
+ * enable != 0 clears the counters and starts recording; read synchronises the stream and returns, per
+ * class, the summed kernel time [ms], the launch count and the algorithmic work (bytes for the
+ * HBM-bound classes, FLOPs for S2S_PROF_GEMM) the launches were asked to do. */
+#define S2S_PROF_ATTN_FWD    0
+#define S2S_PROF_ATTN_BWD    1
+#define S2S_PROF_ATTN_DVH    2
+#define S2S_PROF_GRU_FWD     3
+#define S2S_PROF_GRU_BWD     4
+#define S2S_PROF_GEMM        5
+#define S2S_PROF_DENSE_SMALL 6
+#define S2S_PROF_N           7
+int  s2s_ctx_profile(s2s_ctx* ctx, int enable);
+int  s2s_ctx_profile_read(s2s_ctx* ctx, double* ms_host, int64_t* count_host, double* work_host);
+
 /* ---- flat parameter layout (what module:getParameters() flattens to; timit/timit.lua:172) -- */
 int64_t s2s_param_count(const s2s_model_cfg* cfg);
 /* writes (offset, rows, cols) triples in flat order into out_host[3*max]; returns the count */

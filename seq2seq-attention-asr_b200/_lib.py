@@ -57,6 +57,8 @@ def load():
         "s2s_version": (i32, []),
         "s2s_ctx_launch_count": (i64, [vp]),
         "s2s_ctx_set_graphs": (i32, [vp, i32]),
+        "s2s_ctx_profile": (i32, [vp, i32]),
+        "s2s_ctx_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(f64)]),
         "s2s_param_count": (i64, [cfgp]),
         "s2s_param_segments": (i32, [cfgp, vp, i32]),
         "s2s_decoder_param_offset": (i64, [cfgp]),

@@ -6,6 +6,8 @@
 #include "gru_seq.cuh"
 #include "model.cuh"
 
+#include <string.h>
+
 using namespace s2s;
 
 namespace s2s {
@@ -15,12 +17,19 @@ int attention_step_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const flo
                         const int* yprev, const float* alpha_prev, const float* s_prev, float* alpha, float* s, float* logp);
 }
 
+static void graph_drop(s2s_ctx* ctx) {
+    if (ctx->graph.exec) { cudaGraphExecDestroy(ctx->graph.exec); ctx->graph.exec = nullptr; }
+    ctx->graph.key.clear(); ctx->graph.seen = 0; ctx->graph.launches = 0; ctx->graph.nocapture = false;
+    ctx->arena.frozen = false; ctx->persist.frozen = false;
+}
+
 extern "C" {
 
 int s2s_ctx_destroy(s2s_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->graph.exec) cudaGraphExecDestroy(ctx->graph.exec);
     ctx->arena.release();
     ctx->persist.release();
     if (ctx->counters) cudaFree(ctx->counters);
@@ -63,6 +72,7 @@ int s2s_gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, 
                         const int* lengths, int B, int Lmax, float* y, float* save) {
     S2S_REQUIRE(ctx && W && x && y && save, "gru_seq_forward: null argument");
     S2S_REQUIRE(B > 0 && Lmax > 0 && Din > 0 && ldx >= Din, "gru_seq_forward: bad shape");
+    graph_drop(ctx);
     ctx->arena.reset();
     return gru_seq_forward(ctx, W, Din, H, ndir, reverse, x, ldx, lengths, B, Lmax, y, save);
 }
@@ -71,6 +81,7 @@ int s2s_gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H
     S2S_REQUIRE(ctx && W && dW && x && y && save && dy, "gru_seq_backward: null argument");
     S2S_REQUIRE(B > 0 && Lmax > 0 && Din > 0 && ldx >= Din, "gru_seq_backward: bad shape");
     S2S_REQUIRE(dx == nullptr || ldx == Din, "gru_seq_backward: dx requires a dense x (ldx == Din)");
+    graph_drop(ctx);
     ctx->arena.reset();
     return gru_seq_backward(ctx, W, dW, Din, H, ndir, reverse, x, ldx, lengths, B, Lmax, y, save, dy, dx);
 }
@@ -81,6 +92,7 @@ int s2s_attention_forward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P
     S2S_REQUIRE(ctx && P && h && labels && logp, "attention_forward: null argument");
     Layout Y;
     S2S_TRY(make_layout(cfg, &Y));
+    graph_drop(ctx);
     ctx->arena.reset();
     ctx->persist.reset();
     if (ctx->model) ctx->model->valid = false;
@@ -122,6 +134,7 @@ int s2s_attention_step(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, c
     S2S_REQUIRE(ctx && P && h && Vh && alpha && s && logp, "attention_step: null argument");
     Layout Y;
     S2S_TRY(make_layout(cfg, &Y));
+    graph_drop(ctx);
     ctx->arena.reset();
     return attention_step_impl(ctx, Y, P, h, Vh, lengths, B, Lmax, yprev, alpha_prev, s_prev, alpha, s, logp);
 }
@@ -130,6 +143,7 @@ int s2s_beam_search(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, cons
     S2S_REQUIRE(ctx && P && h && out_host && n_out_host, "beam_search: null argument");
     Layout Y;
     S2S_TRY(make_layout(cfg, &Y));
+    graph_drop(ctx);
     ctx->arena.reset();
     return beam_search_impl(ctx, Y, P, h, L, eos, beam, maxlen, out_host, n_out_host, logp_out_host);
 }
@@ -140,20 +154,78 @@ int s2s_model_forward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, co
     S2S_REQUIRE(ctx && P && X && labels, "model_forward: null argument");
     Layout Y;
     S2S_TRY(make_layout(cfg, &Y));
+    graph_drop(ctx);
     ctx->arena.reset();
     ctx->persist.reset();
     return model_forward(ctx, Y, P, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, nll, logp);
 }
+
+// One forward+backward is ~800 dependent launches of a few microseconds each: replaying them as a CUDA
+// graph removes the host launch cost.  Call 1 with a new signature runs eagerly (sizes the arenas, sets
+// kernel attributes); call 2 is captured on an internal stream (the legacy default stream cannot be
+// captured) and instantiated; later calls replay.  The arenas are bump allocators rewound per call, so
+// every scratch pointer recorded in the graph is the pointer the eager path would use.
 int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, float* G, const float* X, const int* lengths, int B, int Lmax,
                      const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda, int flags, float* nll,
                      float* logp, float* dX) {
     S2S_REQUIRE(ctx && P && G && X && labels, "model_fwdbwd: null argument");
     Layout Y;
     S2S_TRY(make_layout(cfg, &Y));
-    ctx->arena.reset();
-    ctx->persist.reset();
-    S2S_TRY(model_forward(ctx, Y, P, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, nll, logp));
-    return model_backward(ctx, Y, P, G, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, dX);
+    auto run = [&]() -> int {
+        ctx->arena.reset();
+        ctx->persist.reset();
+        S2S_TRY(model_forward(ctx, Y, P, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, nll, logp));
+        return model_backward(ctx, Y, P, G, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, dX);
+    };
+    if (!ctx->graphs || ctx->prof.on) {
+        if (ctx->graph.exec) graph_drop(ctx);
+        return run();
+    }
+    uint32_t lam_bits; memcpy(&lam_bits, &lambda, 4);
+    std::vector<uint64_t> key = {(uint64_t)cfg->D, (uint64_t)cfg->H, (uint64_t)cfg->NL, (uint64_t)cfg->S, (uint64_t)cfg->ST, (uint64_t)cfg->V,
+                                 (uint64_t)cfg->K, (uint64_t)cfg->KF, (uint64_t)cfg->M, (uint64_t)cfg->MW, (uint64_t)B, (uint64_t)Lmax, (uint64_t)Tmax,
+                                 (uint64_t)lam_bits, (uint64_t)flags, (uint64_t)P, (uint64_t)G, (uint64_t)X, (uint64_t)lengths, (uint64_t)labels,
+                                 (uint64_t)tlens, (uint64_t)dropmask, (uint64_t)nll, (uint64_t)logp, (uint64_t)dX, (uint64_t)ctx->stream};
+    if (key != ctx->graph.key) { graph_drop(ctx); ctx->graph.key = key; }
+    cudaStream_t user = ctx->stream, side = ctx->side[0];
+    if (!ctx->graph.exec) {
+        if (ctx->graph.nocapture || ctx->graph.seen++ == 0) return run();   // first sighting: eager warm-up
+        // capture on the internal stream
+        ctx->arena.frozen = true; ctx->persist.frozen = true;         // a cudaMalloc inside a capture is an error
+        const int64_t l0 = ctx->launches;
+        cudaGraph_t graph = nullptr;
+        ctx->stream = side;
+        cudaError_t e = cudaStreamBeginCapture(side, cudaStreamCaptureModeThreadLocal);
+        int rc = 1;
+        if (e == cudaSuccess) {
+            rc = run();
+            e = cudaStreamEndCapture(side, &graph);
+        }
+        ctx->stream = user;
+        ctx->graph.launches = ctx->launches - l0;
+        ctx->launches = l0;
+        if (rc != 0 || e != cudaSuccess || !graph) {
+            std::string why = rc != 0 ? last_error() : std::string(cudaGetErrorString(e));
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            graph_drop(ctx);
+            ctx->graph.key = key; ctx->graph.nocapture = true;        // do not retry capturing this signature
+            S2S_TRY(run());
+            return 0;
+        }
+        e = cudaGraphInstantiate(&ctx->graph.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { ctx->graph.exec = nullptr; graph_drop(ctx); return fail("cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+    }
+    // fork from the caller's stream, replay, join
+    S2S_CUDA(cudaEventRecord(ctx->ev[0], user));
+    S2S_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
+    S2S_CUDA(cudaGraphLaunch(ctx->graph.exec, side));
+    S2S_CUDA(cudaEventRecord(ctx->ev[1], side));
+    S2S_CUDA(cudaStreamWaitEvent(user, ctx->ev[1], 0));
+    ctx->launches += ctx->graph.launches;
+    // forward state recorded by the capture pass stays valid: same shapes, same arena pointers
+    return 0;
 }
 int s2s_model_get_annotations(s2s_ctx* ctx, float* dst) {
     S2S_REQUIRE(ctx && dst, "model_get_annotations: null argument");

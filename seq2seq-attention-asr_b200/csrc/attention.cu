@@ -562,7 +562,12 @@ static int launch_fwd(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
         S2S_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NS, NA, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true; attr_smem = smem;
     }
+    prof_begin(ctx, S2S_PROF_ATTN_FWD);
     attn_fwd_kernel<NS, NA, LOC><<<dim3(p.nch, p.B), ATT_THREADS, smem, ctx->stream>>>(p);
+    {   // algorithmic bytes A_f = 4 B (L S + L A + 2L + S + A)   
+        const double S = NS * 128.0, A = NA * 128.0, L = p.Lmax;
+        prof_end(ctx, S2S_PROF_ATTN_FWD, 4.0 * p.B * (L * S + L * A + 2 * L + S + A));
+    }
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -575,7 +580,12 @@ static int launch_bwd(s2s_ctx* ctx, const AttnBwdParams& p, int KF) {
         S2S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<NS, NA, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true; attr_smem = smem;
     }
+    prof_begin(ctx, S2S_PROF_ATTN_BWD);
     attn_bwd_kernel<NS, NA, LOC><<<dim3(p.nch, p.B), ATT_THREADS, smem, ctx->stream>>>(p);
+    {   // A_b,min = 4 B (L S + L A + 6L + 2S + 2A)   (deferred accumulation)
+        const double S = NS * 128.0, A = NA * 128.0, L = p.Lmax;
+        prof_end(ctx, S2S_PROF_ATTN_BWD, 4.0 * p.B * (L * S + L * A + 6 * L + 2 * S + 2 * A));
+    }
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -640,6 +650,7 @@ int attn_dvh(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* de_
     size_t smem = ((size_t)T * DVH_R + (loc.KF > 0 ? (size_t)T * (DVH_R + loc.KF - 1) : 0)) * 4;
     S2S_REQUIRE(smem <= 200 * 1024, "attn_dvh: T=%d too large for the shared-memory staging", T);
     dim3 grid(ceil_div(Lmax, DVH_R), B, S / 128);
+    prof_begin(ctx, S2S_PROF_ATTN_DVH);
     if (loc.KF > 0) {
         S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_dvh_kernel<true><<<grid, 128, smem, ctx->stream>>>(p);
@@ -647,6 +658,7 @@ int attn_dvh(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* de_
         if (smem > 48 * 1024) S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_dvh_kernel<false><<<grid, 128, smem, ctx->stream>>>(p);
     }
+    prof_end(ctx, S2S_PROF_ATTN_DVH, 4.0 * B * ((double)2 * Lmax * S + (double)T * S + (double)T * Lmax));   // one read of Vh, one write of dVh
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -49,6 +49,24 @@ struct Arena {
     template <typename T> T* get(size_t n) { return (T*)alloc(n * sizeof(T)); }
 };
 
+struct ProfRec { int cls; cudaEvent_t a, b; };
+struct Prof {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    double work[S2S_PROF_N] = {0};
+    int64_t count[S2S_PROF_N] = {0};
+};
+
+// cached CUDA graph of one s2s_model_fwdbwd call signature (shapes + every pointer argument)
+struct GraphCache {
+    std::vector<uint64_t> key;
+    int seen = 0;                  // eager calls with this key so far
+    bool nocapture = false;        // capture failed once for this key: stay eager
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;          // kernel launches recorded in the graph
+};
+
 struct DecoderState;   // decoder.cu
 struct ModelState;     // model.cu
 
@@ -69,6 +87,8 @@ struct s2s_ctx {
     s2s::ModelState* model = nullptr;
     unsigned* counters = nullptr;   // zero-initialised device counters for last-block-done patterns
     uint64_t rng_calls = 0;
+    s2s::Prof prof;
+    s2s::GraphCache graph;
 };
 
 namespace s2s {
@@ -80,6 +100,10 @@ namespace s2s {
         if (e__ != cudaSuccess)                                                                 \
             return ::s2s::fail("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
     } while (0)
+
+// event-timed scope around one kernel launch (no-ops unless s2s_ctx_profile is on)
+void prof_begin(s2s_ctx* ctx, int cls);
+void prof_end(s2s_ctx* ctx, int cls, double work);
 
 #define S2S_ALLOC(ptr, arena, T, n)                                                             \
     do {                                                                                        \

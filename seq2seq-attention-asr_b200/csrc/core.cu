@@ -54,6 +54,25 @@ void Arena::release() {
     frozen = false;
 }
 
+static cudaEvent_t prof_event(s2s_ctx* ctx) {
+    if (!ctx->prof.pool.empty()) { cudaEvent_t e = ctx->prof.pool.back(); ctx->prof.pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(s2s_ctx* ctx, int cls) {
+    if (!ctx->prof.on) return;
+    ProfRec r; r.cls = cls; r.a = prof_event(ctx); r.b = prof_event(ctx);
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->prof.recs.push_back(r);
+}
+void prof_end(s2s_ctx* ctx, int cls, double work) {
+    if (!ctx->prof.on || ctx->prof.recs.empty()) return;
+    cudaEventRecord(ctx->prof.recs.back().b, ctx->stream);
+    ctx->prof.work[cls] += work;
+    ctx->prof.count[cls] += 1;
+}
+
 // Flat layout.  Reference sources for every segment:
 //   encoder GRUs        timit/model_chorowski_baseline.lua:22-31, GRU.lua:23-26
 //   Vh                  Attention.lua:44      Ws  Attention.lua:66
@@ -206,6 +225,27 @@ int64_t s2s_ctx_launch_count(s2s_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int s2s_ctx_set_graphs(s2s_ctx* ctx, int enable) {
     S2S_REQUIRE(ctx, "ctx is NULL");
     ctx->graphs = enable != 0;
+    return 0;
+}
+
+int s2s_ctx_profile(s2s_ctx* ctx, int enable) {
+    S2S_REQUIRE(ctx, "ctx is NULL");
+    S2S_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->prof.recs) { ctx->prof.pool.push_back(r.a); ctx->prof.pool.push_back(r.b); }
+    ctx->prof.recs.clear();
+    for (int i = 0; i < S2S_PROF_N; i++) { ctx->prof.work[i] = 0; ctx->prof.count[i] = 0; }
+    ctx->prof.on = enable != 0;
+    return 0;
+}
+int s2s_ctx_profile_read(s2s_ctx* ctx, double* ms_host, int64_t* count_host, double* work_host) {
+    S2S_REQUIRE(ctx && ms_host && count_host && work_host, "profile_read: null argument");
+    S2S_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < S2S_PROF_N; i++) { ms_host[i] = 0; count_host[i] = ctx->prof.count[i]; work_host[i] = ctx->prof.work[i]; }
+    for (auto& r : ctx->prof.recs) {
+        float ms = 0.f;
+        S2S_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_host[r.cls] += ms;
+    }
     return 0;
 }
 

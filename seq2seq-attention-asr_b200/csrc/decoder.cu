@@ -115,6 +115,7 @@ static int dense_small(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, 
     const int kv = ceil_div(K, 128);
     const size_t smem = (size_t)32 * K * 4;
     dim3 grid(ceil_div(N, 8));
+    prof_begin(ctx, S2S_PROF_DENSE_SMALL);
 #define DS_LAUNCH(KVV)                                                                                          \
     do {                                                                                                        \
         static size_t attr = 0;                                                                                 \
@@ -130,6 +131,7 @@ static int dense_small(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, 
     else if (kv <= 6) DS_LAUNCH(6);
     else DS_LAUNCH(8);
 #undef DS_LAUNCH
+    prof_end(ctx, S2S_PROF_DENSE_SMALL, 4.0 * ((double)N * K + (double)B * K + (double)B * N));
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }

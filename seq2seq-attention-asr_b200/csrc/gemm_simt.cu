@@ -150,6 +150,7 @@ int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, c
     }
     if (K == 0) return 0;
     int z = splitk > 1 ? splitk : batch.count;
+    prof_begin(ctx, S2S_PROF_GEMM);
     // pick the tile so the grid covers the SMs: big tiles only when they still give >= 1 wave
     long tiles128 = (long)ceil_div(M, 128) * ceil_div(N, 128) * z;
     if (tiles128 >= ctx->sm_count) {
@@ -161,6 +162,7 @@ int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, c
         gemm_simt_kernel<64, 64, 4, 4><<<grid, 256, 0, ctx->stream>>>(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias,
                                                                      batch.sA, batch.sB, batch.sC, splitk);
     }
+    prof_end(ctx, S2S_PROF_GEMM, 2.0 * M * N * (double)K * batch.count);
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }

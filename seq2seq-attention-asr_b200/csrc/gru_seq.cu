@@ -8,11 +8,13 @@
 //   * the x-columns of the three weights are time-batched into ONE GEMM per layer
 //     (xp = X . W[:, H:]^T for both directions, N = ndir*3H) -- the reference never batches over time;
 //   * the recurrence runs in one launch per layer: a cluster of CS = H/32 CTAs owns one group of
-//     GRU_BG utterances of one direction; CTA c owns hidden units [32c, 32c+32) and keeps its
+//     BG (4..8) utterances of one direction; CTA c owns hidden units [32c, 32c+32) and keeps its
 //     3 x 32 rows of the recurrent weights in REGISTERS for all L steps (96 floats per thread);
 //     h_{t-1} and r*h_{t-1} live in shared memory and are exchanged every step through distributed
-//     shared memory (st.shared::cluster) + two cluster barriers -- no HBM round trip for the state,
-//     no kernel launch per step;
+//     shared memory: each CTA broadcasts its 32-unit slice with 16-byte st.async stores that signal
+//     the receiver's mbarrier (complete_tx), so the exchange costs one DSMEM hop and never waits for
+//     the global stores of the saved activations -- no HBM round trip for the state, no cluster-wide
+//     fence, no kernel launch per step;
 //   * forward/reverse directions and batch groups are independent clusters of the same launch
 //     (2 dirs x 8 groups x 8 CTAs = 128 SMs at the Chorowski TIMIT batch of 32);
 //   * backward mirrors it with the transposed weights in registers and emits the gate
@@ -21,6 +23,7 @@
 //   * per-utterance lengths: a step is inactive for utterance b once s >= L_b; the reverse direction
 //     starts at L_b - 1, so padded batches reproduce the reference's per-utterance results.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gru_seq.cuh"
@@ -34,8 +37,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+// 16-byte store into another CTA's shared memory that also signals that CTA's mbarrier
+// (complete_tx of 16 bytes): data + arrival in one message, no cluster-wide fence.
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                   "r"(__float_as_uint(v.w)), "r"(remote_mbar) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -64,304 +71,425 @@ struct GruSeqParams {
     const float* dy;       // [B, Lmax, ndir*H]
     float* dA;             // [B, Lmax, ndir*3H]: daz | dar | dah   (same column order as xp)
     float* hp_all;         // [B, Lmax, ndir, H]
+    int dbg;               // timing experiments only (S2S_GRU_DBG): 1 = skip the DSMEM exchange, 2 = skip the mat-vec loops
 };
+
+// Broadcast this CTA's [BG][32] slice (staged in local shared memory) into columns
+// [32*crank, 32*crank+32) of buffer `buf_a` ([BG][H]) of EVERY CTA of the cluster: warp w sends to rank w,
+// lane -> 16-byte chunks (utterance, 4 units).  At most two 16-byte st.async per thread.
+template <int H, int BG>
+__device__ __forceinline__ void bcast_slice(const float (*stage)[32], uint32_t buf_a, uint32_t bar_a, unsigned crank, int warp, int lane) {
+    constexpr int CS = H / 32;
+    if (warp < CS) {
+        const uint32_t rbar = mapa_rank(bar_a, warp);
+#pragma unroll
+        for (int ch = lane; ch < BG * 8; ch += 32) {
+            const int b = ch >> 3, off = (ch & 7) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(&stage[b][off]);
+            st_async_v4(mapa_rank(buf_a + (uint32_t)(b * H + crank * 32 + off) * 4u, warp), v, rbar);
+        }
+    }
+}
+// Transposed butterfly reduction: every lane holds NV partial sums (NV a power of two <= 32); afterwards
+// lane l holds the complete sum number (l mod NV).  NV - 1 + log2(32/NV) shuffles instead of 5 NV.
+template <int NV>
+__device__ __forceinline__ float bfly(float (&v)[NV], int lane) {
+#pragma unroll
+    for (int s = NV / 2; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const float send = (lane & s) ? v[i] : v[i + s];
+            const float keep = (lane & s) ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int o = NV; o < 32; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float c) {
+    c = fmaf(a.x, b.x, c); c = fmaf(a.y, b.y, c); c = fmaf(a.z, b.z, c); return fmaf(a.w, b.w, c);
+}
+
+// Mat-vec mapping shared by forward and backward.  Lanes split K (lane owns k = 4 lane + 128 i), warps own
+// rows: phase 1 = 64 rows (ROWS = 8 per warp), phase 2 = 32 rows (ROWS = 4 per warp).  The K-slice of the
+// state vector is loaded ONCE per thread and phase (NI LDS.128 per utterance) and reused for all of the
+// warp's rows, so the per-step shared-memory traffic is BG*H*4 bytes per WARP instead of per row; the partial
+// sums of a warp are reduced with the transposed butterfly, which also hands each (row, utterance) result to
+// its own lane: the value for (row l/4 [ROWS = 8] or (l%16)/4 [ROWS = 4], utterance b_lo + l%4) ends in lane l.
+// Groups of more than 4 utterances are processed as two halves; NB = utterances in this half (1..4).
+template <int H, int ROWS, int NB>
+__device__ __forceinline__ float matvec(const float4 (&w)[ROWS][H / 128], const float (*src)[H], int b_lo, int lane) {
+    constexpr int NI = H / 128;
+    constexpr int NBP = NB == 1 ? 1 : (NB == 2 ? 2 : 4);
+    constexpr int NV = ROWS * NBP;
+    float4 x[NB][NI];
+#pragma unroll
+    for (int bb = 0; bb < NB; bb++)
+#pragma unroll
+        for (int i = 0; i < NI; i++) x[bb][i] = *reinterpret_cast<const float4*>(&src[b_lo + bb][lane * 4 + 128 * i]);
+    float acc[NV];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+#pragma unroll
+        for (int bb = 0; bb < NBP; bb++) {
+            float a = 0.f;
+            if (bb < NB) {
+#pragma unroll
+                for (int i = 0; i < NI; i++) a = dot4(w[r][i], x[bb][i], a);
+            }
+            acc[r * NBP + bb] = a;
+        }
+    float tot = bfly<NV>(acc, lane);
+    if (NBP < 4) {   // hand (row, utterance) to the lane layout used by the callers
+        const int row = ROWS == 8 ? (lane >> 2) : ((lane & 15) >> 2);
+        tot = __shfl_sync(0xffffffffu, tot, (row * NBP + (lane & 3)) & 31);
+    }
+    return tot;
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int H>
+template <int H, int BG>
 __global__ void __launch_bounds__(256, 1)
 gru_seq_fwd_kernel(const GruSeqParams p) {
-    constexpr int CS = H / 32;         // cluster size
-    constexpr int N1 = H / 16;         // float4 chunks per thread, phase 1 (4 k-quarters)
-    constexpr int N2 = H / 32;         // float4 chunks per thread, phase 2 (8 k-eighths)
-    __shared__ __align__(16) float hbuf[GRU_BG][H];
-    __shared__ __align__(16) float rhbuf[GRU_BG][H];
-    __shared__ float zbuf[GRU_BG][32];
+    constexpr int NI = H / 128;
+    constexpr int NH = (BG + 3) / 4;          // halves of up to 4 utterances
+    constexpr int NB2 = BG - 4 > 0 ? BG - 4 : 1;   // utterances in the second half
+    constexpr unsigned TX = BG * H * 4;       // bytes every CTA receives per exchange
+    constexpr int CS = H / 32;
+    __shared__ __align__(16) float hbuf[BG][H];
+    __shared__ __align__(16) float rhbuf[BG][H];
+    __shared__ __align__(16) float stage[BG][32];
+    __shared__ float zbuf[BG][32];
+    __shared__ uint64_t barA, barB;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned crank = cg::this_cluster().block_rank();
     const int cluster_id = blockIdx.x / CS;
-    const int ngroups = (p.B + GRU_BG - 1) / GRU_BG;
+    const int ngroups = (p.B + BG - 1) / BG;
     const int dir = cluster_id / ngroups, grp = cluster_id % ngroups;
     const bool rev = p.ndir == 2 ? dir == 1 : p.reverse0 != 0;
-    const int b0 = grp * GRU_BG;
+    const int b0 = grp * BG;
     const int H3 = 3 * H;
 
-    // ---- recurrent weights -> registers -----------------------------------------------------
-    const int r1 = tid >> 2, kq = tid & 3;          // phase 1: 64 rows (z: 0-31, r: 32-63) x 4 k-quarters
-    const int g1 = r1 >> 5, ju1 = r1 & 31;
-    const int r2 = tid >> 3, k8 = tid & 7;          // phase 2: 32 rows (h~) x 8 k-eighths
-    float4 w1[N1], w2[N2];
+    // ---- recurrent weights -> registers (coalesced: lane owns k = 4 lane + 128 i) -------------------
+    const int g1 = warp >> 2;                      // phase-1 gate of this warp's rows: 0 = z, 1 = r
+    float4 w1[8][NI], w2[4][NI];
     {
         const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw;
-        const float* row1 = Wd + ((size_t)g1 * H + crank * 32 + ju1) * p.ldw;
 #pragma unroll
-        for (int i = 0; i < N1; i++) {
-            const float* s = row1 + kq * 4 + 16 * i;
-            w1[i] = make_float4(s[0], s[1], s[2], s[3]);
+        for (int r = 0; r < 8; r++) {
+            const float* row = Wd + ((size_t)g1 * H + crank * 32 + 8 * (warp & 3) + r) * p.ldw;
+#pragma unroll
+            for (int i = 0; i < NI; i++) { const float* s = row + lane * 4 + 128 * i; w1[r][i] = make_float4(s[0], s[1], s[2], s[3]); }
         }
-        const float* row2 = Wd + ((size_t)2 * H + crank * 32 + r2) * p.ldw;
 #pragma unroll
-        for (int i = 0; i < N2; i++) {
-            const float* s = row2 + k8 * 4 + 32 * i;
-            w2[i] = make_float4(s[0], s[1], s[2], s[3]);
+        for (int r = 0; r < 4; r++) {
+            const float* row = Wd + ((size_t)2 * H + crank * 32 + 4 * warp + r) * p.ldw;
+#pragma unroll
+            for (int i = 0; i < NI; i++) { const float* s = row + lane * 4 + 128 * i; w2[r][i] = make_float4(s[0], s[1], s[2], s[3]); }
         }
     }
-    for (int i = tid; i < GRU_BG * H; i += 256) { (&hbuf[0][0])[i] = 0.f; (&rhbuf[0][0])[i] = 0.f; }   // Recurrent.lua:13,112
+    for (int i = tid; i < BG * H; i += 256) { (&hbuf[0][0])[i] = 0.f; (&rhbuf[0][0])[i] = 0.f; }   // Recurrent.lua:13,112
+    if (tid == 0) { mbar_init(&barA, 1); mbar_init(&barB, 1); fence_mbar_init(); }
 
-    // finalizer roles: phase 1 -> (row r1, utterance kq); phase 2 -> lanes k8 < 4: (unit r2, utterance k8)
-    const int bf1 = b0 + kq;
-    const int Lf1 = bf1 < p.B ? (p.lengths ? p.lengths[bf1] : p.Lmax) : 0;
-    const int bf2 = b0 + (k8 & 3);
-    const int Lf2 = (k8 < 4 && bf2 < p.B) ? (p.lengths ? p.lengths[bf2] : p.Lmax) : 0;
+    // finalizer roles (see matvec8 / matvec4)
+    const int ju1 = 8 * (warp & 3) + (lane >> 2);          // phase-1 unit within this CTA's slice
+    const int ju2 = 4 * warp + ((lane & 15) >> 2);         // phase-2 unit (lanes < 16)
+    const int j1 = crank * 32 + ju1, j2 = crank * 32 + ju2;
+    int Lf[NH];                                            // length of the utterance this lane finalises, per half
+#pragma unroll
+    for (int hf = 0; hf < NH; hf++) {
+        const int bl = 4 * hf + (lane & 3), b = b0 + bl;
+        Lf[hf] = (bl < BG && b < p.B) ? (p.lengths ? p.lengths[b] : p.Lmax) : 0;
+    }
     int Lgrp = 0;
 #pragma unroll
-    for (int b = 0; b < GRU_BG; b++)
+    for (int b = 0; b < BG; b++)
         if (b0 + b < p.B) Lgrp = max(Lgrp, p.lengths ? p.lengths[b0 + b] : p.Lmax);
 
     const uint32_t hbuf_a = smem_u32(&hbuf[0][0]), rhbuf_a = smem_u32(&rhbuf[0][0]);
-    const int j1 = crank * 32 + ju1, j2 = crank * 32 + r2;
-    cluster_sync_all();
+    const uint32_t barA_a = smem_u32(&barA), barB_a = smem_u32(&barB);
+    cluster_sync_all();   // every CTA of the cluster is resident and has initialised its barriers / buffers
 
     // input projections are independent of the recurrence: step s+1's values are fetched while step s runs
-    auto load_xp1 = [&](int s) -> float {
-        if (s >= Lf1) return 0.f;
-        const int t = rev ? Lf1 - 1 - s : s;
-        return __ldg(p.xp + ((size_t)bf1 * p.Lmax + t) * (p.ndir * H3) + dir * H3 + g1 * H + j1);
+    auto load_xp = [&](int s, int hf, int gate, int j) -> float {
+        if (s >= Lf[hf]) return 0.f;
+        const int t = rev ? Lf[hf] - 1 - s : s;
+        return __ldg(p.xp + ((size_t)(b0 + 4 * hf + (lane & 3)) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + gate * H + j);
     };
-    auto load_xp2 = [&](int s) -> float {
-        if (s >= Lf2) return 0.f;
-        const int t = rev ? Lf2 - 1 - s : s;
-        return __ldg(p.xp + ((size_t)bf2 * p.Lmax + t) * (p.ndir * H3) + dir * H3 + 2 * H + j2);
-    };
-    float xp1n = load_xp1(0), xp2n = load_xp2(0);
+    float xp1n[NH], xp2n[NH];
+#pragma unroll
+    for (int hf = 0; hf < NH; hf++) { xp1n[hf] = load_xp(0, hf, g1, j1); xp2n[hf] = lane < 16 ? load_xp(0, hf, 2, j2) : 0.f; }
+    unsigned parity = 0;
     for (int s = 0; s < Lgrp; s++) {
-        const bool act1 = s < Lf1, act2 = s < Lf2;
-        const int t1 = rev ? Lf1 - 1 - s : s, t2 = rev ? Lf2 - 1 - s : s;
-        const float xp1 = xp1n, xp2 = xp2n;
-        xp1n = load_xp1(s + 1); xp2n = load_xp2(s + 1);
+        float xp1[NH], xp2[NH];
+#pragma unroll
+        for (int hf = 0; hf < NH; hf++) {
+            xp1[hf] = xp1n[hf]; xp2[hf] = xp2n[hf];
+            xp1n[hf] = load_xp(s + 1, hf, g1, j1);
+            xp2n[hf] = lane < 16 ? load_xp(s + 1, hf, 2, j2) : 0.f;
+        }
+        if (tid == 0 && !(p.dbg & 1)) { mbar_expect_tx(&barA, TX); mbar_expect_tx(&barB, TX); }
 
         // ---- phase 1: z, r ------------------------------------------------------------------
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float tot1[NH];
 #pragma unroll
-        for (int i = 0; i < N1; i++) {
-#pragma unroll
-            for (int b = 0; b < GRU_BG; b++) {
-                const float4 x = *reinterpret_cast<const float4*>(&hbuf[b][kq * 4 + 16 * i]);
-                acc[b] = fmaf(w1[i].x, x.x, acc[b]); acc[b] = fmaf(w1[i].y, x.y, acc[b]);
-                acc[b] = fmaf(w1[i].z, x.z, acc[b]); acc[b] = fmaf(w1[i].w, x.w, acc[b]);
-            }
+        for (int hf = 0; hf < NH; hf++) {
+            tot1[hf] = 0.f;
+            if (!(p.dbg & 2)) tot1[hf] = hf == 0 ? matvec<H, 8, (BG < 4 ? BG : 4)>(w1, hbuf, 0, lane) : matvec<H, 8, NB2>(w1, hbuf, 4, lane);
         }
-        {
-            const float tot = reduce4_transpose(acc, lane);
-            if (act1) {
-                const float g = sigmoid_acc(tot + xp1);                               // GRU.lua:23-24
-                float* sv = p.save + (((size_t)bf1 * p.Lmax + t1) * p.ndir + dir) * 4 * H;
-                sv[g1 * H + j1] = g;
+#pragma unroll
+        for (int hf = 0; hf < NH; hf++) {
+            const float tot = tot1[hf];
+            const int bl = 4 * hf + (lane & 3);
+            if (bl < BG) {
+                const bool act = s < Lf[hf];
+                const int t = rev ? Lf[hf] - 1 - s : s;
+                const float g = sigmoid_acc(tot + xp1[hf]);                            // GRU.lua:23-24
+                float* sv = p.save + (((size_t)(b0 + bl) * p.Lmax + t) * p.ndir + dir) * 4 * H;
                 if (g1 == 0) {
-                    zbuf[kq][ju1] = g;
+                    zbuf[bl][ju1] = g;
                 } else {
-                    const float rh = g * hbuf[kq][j1];                                // GRU.lua:25
-                    sv[3 * H + j1] = rh;
-                    const uint32_t off = rhbuf_a + (uint32_t)(kq * H + j1) * 4u;
-#pragma unroll
-                    for (int c = 0; c < CS; c++) st_cluster_f32(mapa_rank(off, c), rh);
+                    const float rh = g * hbuf[bl][j1];                                 // GRU.lua:25
+                    stage[bl][ju1] = rh;
+                    if (act) sv[3 * H + j1] = rh;
                 }
+                if (act) sv[g1 * H + j1] = g;
             }
         }
-        cluster_sync_all();
+        __syncthreads();
+        if (!(p.dbg & 1)) {
+            bcast_slice<H, BG>(stage, rhbuf_a, barA_a, crank, warp, lane);
+            mbar_wait(&barA, parity);
+        }
 
         // ---- phase 2: h~, h' ------------------------------------------------------------------
-        float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+        float tot2[NH];
 #pragma unroll
-        for (int i = 0; i < N2; i++) {
-#pragma unroll
-            for (int b = 0; b < GRU_BG; b++) {
-                const float4 x = *reinterpret_cast<const float4*>(&rhbuf[b][k8 * 4 + 32 * i]);
-                acc2[b] = fmaf(w2[i].x, x.x, acc2[b]); acc2[b] = fmaf(w2[i].y, x.y, acc2[b]);
-                acc2[b] = fmaf(w2[i].z, x.z, acc2[b]); acc2[b] = fmaf(w2[i].w, x.w, acc2[b]);
-            }
+        for (int hf = 0; hf < NH; hf++) {
+            tot2[hf] = 0.f;
+            if (!(p.dbg & 2)) tot2[hf] = hf == 0 ? matvec<H, 4, (BG < 4 ? BG : 4)>(w2, rhbuf, 0, lane) : matvec<H, 4, NB2>(w2, rhbuf, 4, lane);
         }
 #pragma unroll
-        for (int b = 0; b < GRU_BG; b++) acc2[b] += __shfl_xor_sync(0xffffffffu, acc2[b], 4);
-        {
-            const float tot = reduce4_transpose(acc2, lane);
-            if (act2) {
-                const int bb = k8 & 3;
-                const float hc = tanh_acc(tot + xp2);                                 // GRU.lua:26
-                const float z = zbuf[bb][r2], hp = hbuf[bb][j2];
-                const float hn = (1.f - z) * hp + z * hc;                             // GRU.lua:27-30
-                p.save[(((size_t)bf2 * p.Lmax + t2) * p.ndir + dir) * 4 * H + 2 * H + j2] = hc;
-                p.y[((size_t)bf2 * p.Lmax + t2) * (p.ndir * H) + dir * H + j2] = hn;
-                const uint32_t off = hbuf_a + (uint32_t)(bb * H + j2) * 4u;
-#pragma unroll
-                for (int c = 0; c < CS; c++) st_cluster_f32(mapa_rank(off, c), hn);
+        for (int hf = 0; hf < NH; hf++) {
+            const float tot = tot2[hf];
+            const int bl = 4 * hf + (lane & 3);
+            if (lane < 16 && bl < BG) {
+                const bool act = s < Lf[hf];
+                const int t = rev ? Lf[hf] - 1 - s : s;
+                const float hp = hbuf[bl][j2];
+                float hn = hp;                                                         // inactive: state frozen
+                if (act) {
+                    const float hc = tanh_acc(tot + xp2[hf]);                          // GRU.lua:26
+                    const float z = zbuf[bl][ju2];
+                    hn = (1.f - z) * hp + z * hc;                                      // GRU.lua:27-30
+                    const size_t row = (size_t)(b0 + bl) * p.Lmax + t;
+                    p.save[(row * p.ndir + dir) * 4 * H + 2 * H + j2] = hc;
+                    p.y[row * (p.ndir * H) + dir * H + j2] = hn;
+                }
+                stage[bl][ju2] = hn;
             }
         }
-        cluster_sync_all();
+        __syncthreads();
+        if (!(p.dbg & 1)) {
+            bcast_slice<H, BG>(stage, hbuf_a, barB_a, crank, warp, lane);
+            mbar_wait(&barB, parity);
+        }
+        parity ^= 1;
     }
+    cluster_sync_all();   // no CTA exits while a peer may still address its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-template <int H>
+template <int H, int BG>
 __global__ void __launch_bounds__(256, 1)
 gru_seq_bwd_kernel(const GruSeqParams p) {
     constexpr int CS = H / 32;
-    constexpr int N1 = H / 16;
-    constexpr int N2 = H / 32;
-    __shared__ __align__(16) float ahbuf[GRU_BG][H];   // dah (all units)
-    __shared__ __align__(16) float azbuf[GRU_BG][H];   // daz
-    __shared__ __align__(16) float arbuf[GRU_BG][H];   // dar
-    __shared__ float stash_r[GRU_BG][32], stash_hp[GRU_BG][32];
-    __shared__ float part1[GRU_BG][32], part2[GRU_BG][32];
+    constexpr int NI = H / 128;
+    constexpr int NH = (BG + 3) / 4;
+    constexpr int NB2 = BG - 4 > 0 ? BG - 4 : 1;
+    constexpr unsigned TX = BG * H * 4;
+    __shared__ __align__(16) float ahbuf[BG][H];   // dah (all units)
+    __shared__ __align__(16) float azbuf[BG][H];   // daz
+    __shared__ __align__(16) float arbuf[BG][H];   // dar
+    __shared__ __align__(16) float stage_h[BG][32], stage_z[BG][32], stage_r[BG][32];
+    __shared__ float stash_r[BG][32], stash_hp[BG][32];
+    __shared__ float part1[BG][32], part2[BG][32];
+    __shared__ uint64_t barA, barB;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned crank = cg::this_cluster().block_rank();
     const int cluster_id = blockIdx.x / CS;
-    const int ngroups = (p.B + GRU_BG - 1) / GRU_BG;
+    const int ngroups = (p.B + BG - 1) / BG;
     const int dir = cluster_id / ngroups, grp = cluster_id % ngroups;
     const bool rev = p.ndir == 2 ? dir == 1 : p.reverse0 != 0;
-    const int b0 = grp * GRU_BG;
+    const int b0 = grp * BG;
     const int H3 = 3 * H;
 
-    // transposed recurrent weights -> registers.  phase 1 rows: g1 = 0 -> W_h^T (on dah), 1 -> W_z^T (on daz);
-    // phase 2 rows: W_r^T (on dar).  Row i = input unit owned by this CTA, reduction over output units j.
-    const int r1 = tid >> 2, kq = tid & 3;
-    const int g1 = r1 >> 5, ju1 = r1 & 31;
-    const int r2 = tid >> 3, k8 = tid & 7;
-    float4 w1[N1], w2[N2];
+    // transposed recurrent weights -> registers.  phase 1 rows (8 per warp): warps 0-3 -> W_h^T (applied to
+    // dah), warps 4-7 -> W_z^T (applied to daz); phase 2 rows (4 per warp): W_r^T (applied to dar).  Row =
+    // input unit owned by this CTA, reduction over the output units j = 4 lane + 128 i + e.
+    const int g1 = warp >> 2;
+    float4 w1[8][NI], w2[4][NI];
     {
         const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw;
-        const float* Wg = Wd + (size_t)(g1 == 0 ? 2 : 0) * H * p.ldw + crank * 32 + ju1;
+        const float* Wg = Wd + (size_t)(g1 == 0 ? 2 : 0) * H * p.ldw + crank * 32 + 8 * (warp & 3);
 #pragma unroll
-        for (int i = 0; i < N1; i++) {
-            const int j = kq * 4 + 16 * i;
-            w1[i] = make_float4(Wg[(size_t)j * p.ldw], Wg[(size_t)(j + 1) * p.ldw], Wg[(size_t)(j + 2) * p.ldw], Wg[(size_t)(j + 3) * p.ldw]);
-        }
-        const float* Wr = Wd + (size_t)H * p.ldw + crank * 32 + r2;
+        for (int r = 0; r < 8; r++)
 #pragma unroll
-        for (int i = 0; i < N2; i++) {
-            const int j = k8 * 4 + 32 * i;
-            w2[i] = make_float4(Wr[(size_t)j * p.ldw], Wr[(size_t)(j + 1) * p.ldw], Wr[(size_t)(j + 2) * p.ldw], Wr[(size_t)(j + 3) * p.ldw]);
-        }
+            for (int i = 0; i < NI; i++) {
+                const size_t j = lane * 4 + 128 * i;
+                w1[r][i] = make_float4(Wg[j * p.ldw + r], Wg[(j + 1) * p.ldw + r], Wg[(j + 2) * p.ldw + r], Wg[(j + 3) * p.ldw + r]);
+            }
+        const float* Wr = Wd + (size_t)H * p.ldw + crank * 32 + 4 * warp;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                const size_t j = lane * 4 + 128 * i;
+                w2[r][i] = make_float4(Wr[j * p.ldw + r], Wr[(j + 1) * p.ldw + r], Wr[(j + 2) * p.ldw + r], Wr[(j + 3) * p.ldw + r]);
+            }
     }
-    for (int i = tid; i < GRU_BG * H; i += 256) { (&ahbuf[0][0])[i] = 0.f; (&azbuf[0][0])[i] = 0.f; (&arbuf[0][0])[i] = 0.f; }
+    for (int i = tid; i < BG * H; i += 256) { (&ahbuf[0][0])[i] = 0.f; (&azbuf[0][0])[i] = 0.f; (&arbuf[0][0])[i] = 0.f; }
+    if (tid == 0) { mbar_init(&barA, 1); mbar_init(&barB, 1); fence_mbar_init(); }
 
-    // elementwise owner role (= phase-2 finalizer): lanes k8 < 4 own (unit r2, utterance k8)
-    const bool owner = k8 < 4;
-    const int bo = b0 + (k8 & 3);
-    const int Lo = (owner && bo < p.B) ? (p.lengths ? p.lengths[bo] : p.Lmax) : 0;
-    const int bf1 = b0 + kq;
-    const int Lf1 = bf1 < p.B ? (p.lengths ? p.lengths[bf1] : p.Lmax) : 0;
+    // roles: owner (elementwise part + carry) = phase-2 finaliser: lanes < 16 -> (unit ju2, utterance lane%4) per half
+    const int ju1 = 8 * (warp & 3) + (lane >> 2);
+    const int ju2 = 4 * warp + ((lane & 15) >> 2);
+    const int j1 = crank * 32 + ju1, j2 = crank * 32 + ju2;
+    const bool owner_lane = lane < 16;
+    int Lf[NH];
+#pragma unroll
+    for (int hf = 0; hf < NH; hf++) {
+        const int bl = 4 * hf + (lane & 3), b = b0 + bl;
+        Lf[hf] = (bl < BG && b < p.B) ? (p.lengths ? p.lengths[b] : p.Lmax) : 0;
+    }
     int Lgrp = 0;
 #pragma unroll
-    for (int b = 0; b < GRU_BG; b++)
+    for (int b = 0; b < BG; b++)
         if (b0 + b < p.B) Lgrp = max(Lgrp, p.lengths ? p.lengths[b0 + b] : p.Lmax);
 
     const uint32_t ah_a = smem_u32(&ahbuf[0][0]), az_a = smem_u32(&azbuf[0][0]), ar_a = smem_u32(&arbuf[0][0]);
-    const int j1 = crank * 32 + ju1, j2 = crank * 32 + r2;
-    float carry = 0.f;          // dE/dh flowing to the previous recurrence step (owner threads)
+    const uint32_t barA_a = smem_u32(&barA), barB_a = smem_u32(&barB);
+    float carry[NH];            // dE/dh flowing to the previous recurrence step (owner lanes)
+#pragma unroll
+    for (int hf = 0; hf < NH; hf++) carry[hf] = 0.f;
     cluster_sync_all();
 
     // saved activations / incoming gradients do not depend on the recurrence: prefetch one step ahead
     struct Pre { float z, r, hc, hp, dy; };
-    auto load_pre = [&](int s) -> Pre {
+    auto load_pre = [&](int s, int hf) -> Pre {
         Pre q = {0.f, 0.f, 0.f, 0.f, 0.f};
-        if (s < 0 || s >= Lo) return q;
-        const int t = rev ? Lo - 1 - s : s;
-        const size_t row = (size_t)bo * p.Lmax + t;
+        if (!owner_lane || s < 0 || s >= Lf[hf]) return q;
+        const int t = rev ? Lf[hf] - 1 - s : s;
+        const int b = b0 + 4 * hf + (lane & 3);
+        const size_t row = (size_t)b * p.Lmax + t;
         const float* sv = p.save + (row * p.ndir + dir) * 4 * H;
         q.z = __ldg(sv + j2); q.r = __ldg(sv + H + j2); q.hc = __ldg(sv + 2 * H + j2);
         if (s > 0) {                                                                  // RNN.lua:186-192
             const int tp = rev ? t + 1 : t - 1;
-            q.hp = __ldg(p.y + ((size_t)bo * p.Lmax + tp) * (p.ndir * H) + dir * H + j2);
+            q.hp = __ldg(p.y + ((size_t)b * p.Lmax + tp) * (p.ndir * H) + dir * H + j2);
         }
         q.dy = __ldg(p.dy + row * (p.ndir * H) + dir * H + j2);
         return q;
     };
-    Pre nxt = load_pre(Lgrp - 1);
-    for (int s = Lgrp - 1; s >= 0; s--) {                                           // RNN.lua:183
-        const bool acto = s < Lo, act1 = s < Lf1;
-        const int to = rev ? Lo - 1 - s : s, t1 = rev ? Lf1 - 1 - s : s;
-        float dhp_part = 0.f;
-        const Pre cur = nxt;
-        nxt = load_pre(s - 1);
-        // ---- elementwise part (owners) ---------------------------------------------------------
-        if (acto) {
-            const int bb = k8 & 3;
-            const size_t row = (size_t)bo * p.Lmax + to;
-            const float z = cur.z, r = cur.r, hc = cur.hc, hp = cur.hp;
-            const float dh = cur.dy + carry;                                          // RNN.lua:193-194
-            const float dah = dh * z * (1.f - hc * hc);
-            const float daz = dh * (hc - hp) * z * (1.f - z);
-            dhp_part = dh * (1.f - z);
-            float* da = p.dA + row * (p.ndir * H3) + dir * H3;
-            da[j2] = daz; da[2 * H + j2] = dah;
-            p.hp_all[(row * p.ndir + dir) * H + j2] = hp;
-            stash_r[bb][r2] = r; stash_hp[bb][r2] = hp;
-            const uint32_t o = (uint32_t)(bb * H + j2) * 4u;
+    Pre nxt[NH];
 #pragma unroll
-            for (int c = 0; c < CS; c++) { st_cluster_f32(mapa_rank(ah_a + o, c), dah); st_cluster_f32(mapa_rank(az_a + o, c), daz); }
+    for (int hf = 0; hf < NH; hf++) nxt[hf] = load_pre(Lgrp - 1, hf);
+    unsigned parity = 0;
+    for (int s = Lgrp - 1; s >= 0; s--) {                                           // RNN.lua:183
+        float dhp_part[NH];
+        if (tid == 0 && !(p.dbg & 1)) { mbar_expect_tx(&barA, 2 * TX); mbar_expect_tx(&barB, TX); }
+        // ---- elementwise part (owners) ---------------------------------------------------------
+#pragma unroll
+        for (int hf = 0; hf < NH; hf++) {
+            const Pre cur = nxt[hf];
+            nxt[hf] = load_pre(s - 1, hf);
+            dhp_part[hf] = 0.f;
+            const int bl = 4 * hf + (lane & 3);
+            if (owner_lane && bl < BG) {
+                float dah = 0.f, daz = 0.f;
+                if (s < Lf[hf]) {
+                    const int t = rev ? Lf[hf] - 1 - s : s;
+                    const size_t row = (size_t)(b0 + bl) * p.Lmax + t;
+                    const float z = cur.z, r = cur.r, hc = cur.hc, hp = cur.hp;
+                    const float dh = cur.dy + carry[hf];                              // RNN.lua:193-194
+                    dah = dh * z * (1.f - hc * hc);
+                    daz = dh * (hc - hp) * z * (1.f - z);
+                    dhp_part[hf] = dh * (1.f - z);
+                    float* da = p.dA + row * (p.ndir * H3) + dir * H3;
+                    da[j2] = daz; da[2 * H + j2] = dah;
+                    p.hp_all[(row * p.ndir + dir) * H + j2] = hp;
+                    stash_r[bl][ju2] = r; stash_hp[bl][ju2] = hp;
+                }
+                stage_h[bl][ju2] = dah; stage_z[bl][ju2] = daz;
+            }
         }
-        cluster_sync_all();
+        __syncthreads();
+        if (!(p.dbg & 1)) {
+            bcast_slice<H, BG>(stage_h, ah_a, barA_a, crank, warp, lane);
+            bcast_slice<H, BG>(stage_z, az_a, barA_a, crank, warp, lane);
+            mbar_wait(&barA, parity);
+        }
 
         // ---- phase 1: d(r*h) = W_h[:, :H]^T dah ; W_z[:, :H]^T daz -------------------------------
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        {
-            const float (*src)[H] = g1 == 0 ? ahbuf : azbuf;
+        const float (*src1)[H] = g1 == 0 ? ahbuf : azbuf;
+        float tot1[NH];
 #pragma unroll
-            for (int i = 0; i < N1; i++) {
+        for (int hf = 0; hf < NH; hf++) {
+            tot1[hf] = 0.f;
+            if (!(p.dbg & 2)) tot1[hf] = hf == 0 ? matvec<H, 8, (BG < 4 ? BG : 4)>(w1, src1, 0, lane) : matvec<H, 8, NB2>(w1, src1, 4, lane);
+        }
 #pragma unroll
-                for (int b = 0; b < GRU_BG; b++) {
-                    const float4 x = *reinterpret_cast<const float4*>(&src[b][kq * 4 + 16 * i]);
-                    acc[b] = fmaf(w1[i].x, x.x, acc[b]); acc[b] = fmaf(w1[i].y, x.y, acc[b]);
-                    acc[b] = fmaf(w1[i].z, x.z, acc[b]); acc[b] = fmaf(w1[i].w, x.w, acc[b]);
+        for (int hf = 0; hf < NH; hf++) {
+            const float tot = tot1[hf];
+            const int bl = 4 * hf + (lane & 3);
+            if (bl < BG) {
+                const bool act = s < Lf[hf];
+                const int t = rev ? Lf[hf] - 1 - s : s;
+                if (g1 == 0) {
+                    float dar = 0.f, pr = 0.f;
+                    if (act) {
+                        const float r = stash_r[bl][ju1], hp = stash_hp[bl][ju1];
+                        dar = tot * hp * r * (1.f - r);
+                        pr = tot * r;
+                        p.dA[((size_t)(b0 + bl) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + H + j1] = dar;
+                    }
+                    part1[bl][ju1] = pr;
+                    stage_r[bl][ju1] = dar;
+                } else {
+                    part2[bl][ju1] = act ? tot : 0.f;
                 }
             }
         }
-        {
-            const float tot = reduce4_transpose(acc, lane);
-            if (g1 == 0) {
-                float dar = 0.f, pr = 0.f;
-                if (act1) {
-                    const float r = stash_r[kq][ju1], hp = stash_hp[kq][ju1];
-                    dar = tot * hp * r * (1.f - r);
-                    pr = tot * r;
-                    p.dA[((size_t)bf1 * p.Lmax + t1) * (p.ndir * H3) + dir * H3 + H + j1] = dar;
-                }
-                part1[kq][ju1] = pr;
-                const uint32_t o = ar_a + (uint32_t)(kq * H + j1) * 4u;
-#pragma unroll
-                for (int c = 0; c < CS; c++) st_cluster_f32(mapa_rank(o, c), dar);
-            } else {
-                part2[kq][ju1] = act1 ? tot : 0.f;
-            }
+        __syncthreads();
+        if (!(p.dbg & 1)) {
+            bcast_slice<H, BG>(stage_r, ar_a, barB_a, crank, warp, lane);
+            mbar_wait(&barB, parity);
         }
-        cluster_sync_all();
 
         // ---- phase 2: W_r[:, :H]^T dar ; carry ---------------------------------------------------
-        float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+        float tot2[NH];
 #pragma unroll
-        for (int i = 0; i < N2; i++) {
-#pragma unroll
-            for (int b = 0; b < GRU_BG; b++) {
-                const float4 x = *reinterpret_cast<const float4*>(&arbuf[b][k8 * 4 + 32 * i]);
-                acc2[b] = fmaf(w2[i].x, x.x, acc2[b]); acc2[b] = fmaf(w2[i].y, x.y, acc2[b]);
-                acc2[b] = fmaf(w2[i].z, x.z, acc2[b]); acc2[b] = fmaf(w2[i].w, x.w, acc2[b]);
-            }
+        for (int hf = 0; hf < NH; hf++) {
+            tot2[hf] = 0.f;
+            if (!(p.dbg & 2)) tot2[hf] = hf == 0 ? matvec<H, 4, (BG < 4 ? BG : 4)>(w2, arbuf, 0, lane) : matvec<H, 4, NB2>(w2, arbuf, 4, lane);
         }
 #pragma unroll
-        for (int b = 0; b < GRU_BG; b++) acc2[b] += __shfl_xor_sync(0xffffffffu, acc2[b], 4);
-        {
-            const float tot = reduce4_transpose(acc2, lane);
-            if (acto) carry = dhp_part + part1[k8 & 3][r2] + part2[k8 & 3][r2] + tot;
+        for (int hf = 0; hf < NH; hf++) {
+            const float tot = tot2[hf];
+            const int bl = 4 * hf + (lane & 3);
+            if (owner_lane && bl < BG && s < Lf[hf]) carry[hf] = dhp_part[hf] + part1[bl][ju2] + part2[bl][ju2] + tot;
         }
-        // (the next iteration's owner writes to ah/az happen after every CTA passed the barrier above;
-        //  part1/part2/stash are re-written only after the next barrier A)
+        parity ^= 1;
     }
+    cluster_sync_all();
 }
 
 // rows t >= L_b of a [B, Lmax, W] tensor := 0 (padding must not leak NaNs into the time-batched GEMMs)
@@ -378,10 +506,10 @@ int zero_tail_rows(s2s_ctx* ctx, float* x, const int* lengths, int B, int Lmax, 
     return 0;
 }
 
-template <int H>
-static int launch_cluster(s2s_ctx* ctx, bool backward, const GruSeqParams& p) {
+template <int H, int BG>
+static int launch_cluster_bg(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int* max_clusters) {
     constexpr int CS = H / 32;
-    const int ngroups = ceil_div(p.B, GRU_BG);
+    const int ngroups = ceil_div(p.B, BG);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS * ngroups * p.ndir);
     cfg.blockDim = dim3(256);
@@ -391,10 +519,44 @@ static int launch_cluster(s2s_ctx* ctx, bool backward, const GruSeqParams& p) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (backward) S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<H>, p));
-    else S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_fwd_kernel<H>, p));
+    if (max_clusters) {   // occupancy query only
+        if (backward) S2S_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, gru_seq_bwd_kernel<H, BG>, &cfg));
+        else S2S_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, gru_seq_fwd_kernel<H, BG>, &cfg));
+        return 0;
+    }
+    prof_begin(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD);
+    if (backward) S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<H, BG>, p));
+    else S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_fwd_kernel<H, BG>, p));
+    {   // algorithmic bytes per launch: fwd reads xp (3H) and writes y (H) + save (4H) per direction;
+        // bwd reads save z,r,h~ (3H) + h_prev (H) + dy (H) and writes dA (3H) + h_prev (H)
+        const double per = backward ? 9.0 * H : 8.0 * H;
+        prof_end(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD, 4.0 * p.B * p.Lmax * p.ndir * per);
+    }
     S2S_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// Utterances per cluster: the smallest group size whose cluster count fits in ONE wave (a cluster that
+// does not fit runs after the others and doubles the time of this latency-bound kernel).  The number of
+// co-resident clusters is queried once per (H, direction) -- 15 clusters of 8 CTAs on a 148-SM B200.
+template <int H>
+static int launch_cluster(s2s_ctx* ctx, bool backward, const GruSeqParams& p) {
+    static int max_active[2] = {0, 0};
+    if (max_active[backward] == 0) {
+        int n = 0;
+        S2S_TRY((launch_cluster_bg<H, 4>(ctx, backward, p, &n)));
+        max_active[backward] = n > 0 ? n : 1;
+    }
+    const int cap = max_active[backward];
+    int bg = 4;
+    while (bg < 8 && p.ndir * ceil_div(p.B, bg) > cap) bg++;
+    switch (bg) {
+        case 4: return launch_cluster_bg<H, 4>(ctx, backward, p, nullptr);
+        case 5: return launch_cluster_bg<H, 5>(ctx, backward, p, nullptr);
+        case 6: return launch_cluster_bg<H, 6>(ctx, backward, p, nullptr);
+        case 7: return launch_cluster_bg<H, 7>(ctx, backward, p, nullptr);
+        default: return launch_cluster_bg<H, 8>(ctx, backward, p, nullptr);
+    }
 }
 
 int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int reverse, const float* x, int ldx,
@@ -413,6 +575,7 @@ int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int 
     GruSeqParams p = {};
     p.W = W; p.ldw = ldw; p.xp = xp; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.ndir = ndir; p.reverse0 = reverse;
     p.y = y; p.save = save;
+    { const char* e = getenv("S2S_GRU_DBG"); p.dbg = e ? atoi(e) : 0; }
     if (H == 128) return launch_cluster<128>(ctx, false, p);
     return launch_cluster<256>(ctx, false, p);
 }
@@ -432,6 +595,7 @@ int gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, in
     GruSeqParams p = {};
     p.W = W; p.ldw = ldw; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.ndir = ndir; p.reverse0 = reverse;
     p.y = const_cast<float*>(y); p.save = const_cast<float*>(save); p.dy = dy; p.dA = dA; p.hp_all = hp_all;
+    { const char* e = getenv("S2S_GRU_DBG"); p.dbg = e ? atoi(e) : 0; }
     if (H == 128) S2S_TRY(launch_cluster<128>(ctx, true, p));
     else S2S_TRY(launch_cluster<256>(ctx, true, p));
     // time-batched gradients (K = B*L) instead of one rank-1 update per frame (LinearZeroBias.lua:67-74)

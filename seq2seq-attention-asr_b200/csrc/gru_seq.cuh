@@ -4,7 +4,6 @@
 
 namespace s2s {
 
-constexpr int GRU_BG = 4;   // utterances per cluster
 
 // y [B,Lmax,ndir*H]; save [B,Lmax,ndir,4H] (z | r | h~ | r*h_prev)
 int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int reverse, const float* x, int ldx,

@@ -71,6 +71,18 @@ class Context:
     def set_graphs(self, enable):
         check(self.lib.s2s_ctx_set_graphs(self.h, int(bool(enable))))
 
+    PROF_CLASSES = ("attn_fwd", "attn_bwd", "attn_dvh", "gru_fwd", "gru_bwd", "gemm", "dense_small")
+
+    def profile(self, enable=True):
+        check(self.lib.s2s_ctx_profile(self.h, int(bool(enable))))
+
+    def profile_read(self):
+        """{class: (ms, launches, algorithmic work)} since profile(True)"""
+        n = len(self.PROF_CLASSES)
+        ms = (C.c_double * n)(); cnt = (C.c_int64 * n)(); work = (C.c_double * n)()
+        check(self.lib.s2s_ctx_profile_read(self.h, ms, cnt, work))
+        return {k: (ms[i], cnt[i], work[i]) for i, k in enumerate(self.PROF_CLASSES)}
+
     def new(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
@@ -282,3 +294,31 @@ def attn_step_backward(ctx, Vh, h, q, w, alpha, dc, dalpha_in=None, lengths=None
     check(ctx.lib.s2s_attn_step_backward(ctx.h, _f(Vh), _f(h), _f(q), _f(w), _i(lengths), B, L, S, A, _f(alpha), _f(dc), _f(dalpha_in),
                                          _f(dq), _f(de)))
     return dq, de
+
+
+# ---- parameter initialisation (module:reset(stdv) rules) -------------------------------------------------
+def segment_names(cfg):
+    """Names of the flat-layout segments in order (see csrc/core.cu make_layout)."""
+    names = [f"enc{l}{d}.W{g}" for l in range(cfg["NL"]) for d in ("f", "r") for g in ("z", "r", "h")]
+    names += ["WV", "bV", "Ws", "bs"]
+    if cfg["K"] > 0:
+        names += ["WF", "bF", "U", "bU"]
+    names += ["we", "be", "Wy", "by", "Wc", "bc", "Wj", "bj", "Gz", "Gr", "Gh", "Wm", "bm", "Wo", "bo"]
+    return names
+
+
+def init_params(cfg, seed=1234):
+    """U(+-1/sqrt(fan_in)) for every weight and live bias, as reset() does in LinearZeroBias.lua:12-29 and
+    TemporalConvolutionZeroBias.lua:21-35 (stock nn.Linear / nn.TemporalConvolution use the same bound for
+    the bias); the dead biases of the ZeroBias convolutions stay 0.  Returns a float32 numpy vector."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    P = np.zeros(param_count(cfg), dtype=np.float32)
+    fan_in = 1
+    for (off, rows, cols), name in zip(param_segments(cfg), segment_names(cfg)):
+        if cols > 1 or name == "we":
+            fan_in = cfg["KF"] if name == "WF" else cols
+            P[off:off + rows * cols] = rng.uniform(-1, 1, rows * cols) / np.sqrt(fan_in)
+        elif name not in ("bV", "bU", "be"):
+            P[off:off + rows] = rng.uniform(-1, 1, rows) / np.sqrt(fan_in)
+    return P
