@@ -189,37 +189,85 @@ attn_fwd_kernel(const AttnFwdParams p) {
     if (!is_last) return;
     __threadfence();
 
+    // every warp: chunk statistics -> registers (<= 4 chunks per lane), one L2 round trip
+    float mc[ATT_MAXCH / 32], sc_[ATT_MAXCH / 32];
+#pragma unroll
+    for (int u = 0; u < ATT_MAXCH / 32; u++) {
+        const int c = lane + 32 * u;
+        mc[u] = c < nchb ? ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2) : -INFINITY;
+        sc_[u] = c < nchb ? ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2 + 1) : 0.f;
+    }
     float M = -INFINITY;
-    for (int c = lane; c < nchb; c += 32) M = fmaxf(M, ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2));
+#pragma unroll
+    for (int u = 0; u < ATT_MAXCH / 32; u++) M = fmaxf(M, mc[u]);
     M = warp_max(M);
     float den = 0.f;
-    for (int c = lane; c < nchb; c += 32) {
-        const float mc = ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2);
-        const float sc = ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2 + 1);
-        den += sc * expf(mc - M);
-    }
+#pragma unroll
+    for (int u = 0; u < ATT_MAXCH / 32; u++) den += sc_[u] * expf(mc[u] - M);
     den = warp_sum(den);
     const float inv = 1.0f / den;
-    if (warp == 0)
-        for (int c = lane; c < nchb; c += 32) scl_s[c] = expf(ldcg1(p.part_ms + ((size_t)b * p.nch + c) * 2) - M) * inv;
+    if (warp == 0) {
+#pragma unroll
+        for (int u = 0; u < ATT_MAXCH / 32; u++)
+            if (lane + 32 * u < nchb) scl_s[lane + 32 * u] = expf(mc[u] - M) * inv;
+    }
     __syncthreads();
 
     float penacc = 0.f;
-    for (int l = tid; l < p.Lmax; l += ATT_THREADS) {
-        float a = 0.f;
-        if (l < Lb) {
-            a = expf(ldcg1(p.E + (size_t)b * p.Lmax + l) - M) * inv;
-            if (p.pen) {
-                const float ap = p.app ? p.app[(size_t)b * p.ld_app + l] : 0.f;
-                penacc += (float)(Lb - l) * (a - ap);
+    for (int l0a = 0; l0a < p.Lmax; l0a += 4 * ATT_THREADS) {
+        float ev[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int l = l0a + u * ATT_THREADS + tid;
+            ev[u] = l < Lb ? ldcg1(p.E + (size_t)b * p.Lmax + l) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int l = l0a + u * ATT_THREADS + tid;
+            if (l < p.Lmax) {
+                float a = 0.f;
+                if (l < Lb) {
+                    a = expf(ev[u] - M) * inv;
+                    if (p.pen) {
+                        const float ap = p.app ? p.app[(size_t)b * p.ld_app + l] : 0.f;
+                        penacc += (float)(Lb - l) * (a - ap);
+                    }
+                }
+                p.alpha[(size_t)b * p.ld_alpha + l] = a;
             }
         }
-        p.alpha[(size_t)b * p.ld_alpha + l] = a;
     }
-    for (int a4 = tid; a4 < A / 4; a4 += ATT_THREADS) {
+    {   // context: thread -> (chunk group cg, float4 column); 8 independent loads in flight per thread
+        constexpr int CG = ATT_THREADS / (A / 4);            // chunk groups (2 for A = 512)
+        const int a4 = tid % (A / 4), cg = tid / (A / 4);
         float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = 0; c < nchb; c++) acc4 = f4fma(scl_s[c], ldcg4(p.part_c + ((size_t)b * p.nch + c) * A + a4 * 4), acc4);
-        *reinterpret_cast<float4*>(p.c + (size_t)b * p.ld_c + a4 * 4) = acc4;
+        for (int c0 = cg; c0 < nchb; c0 += 8 * CG) {
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int c = c0 + u * CG;
+                t[u] = c < nchb ? ldcg4(p.part_c + ((size_t)b * p.nch + c) * A + a4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int c = c0 + u * CG;
+                if (c < nchb) acc4 = f4fma(scl_s[c], t[u], acc4);
+            }
+        }
+        if (CG > 1) {
+            float4* red4 = reinterpret_cast<float4*>(red);
+            __syncthreads();
+            red4[cg * (A / 4) + a4] = acc4;
+            __syncthreads();
+            if (tid < A / 4) {
+                float4 s4 = red4[tid];
+#pragma unroll
+                for (int gg = 1; gg < CG; gg++) s4 = f4add(s4, red4[gg * (A / 4) + tid]);
+                *reinterpret_cast<float4*>(p.c + (size_t)b * p.ld_c + tid * 4) = s4;
+            }
+        } else {
+            *reinterpret_cast<float4*>(p.c + (size_t)b * p.ld_c + a4 * 4) = acc4;
+        }
     }
     if (p.pen) {
         penacc = warp_sum(penacc);
@@ -254,14 +302,18 @@ struct AttnBwdParams {
 };
 
 template <int NS, int NA, bool LOC>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_kernel(const AttnBwdParams p) {
     constexpr int S = NS * 128, A = NA * 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* red = reinterpret_cast<float*>(smem_raw);            // [8][2][S]
+    float* hs = reinterpret_cast<float*>(smem_raw);              // [ATT_R][A]   h tile (bulk TMA)
+    float* red = hs + ATT_R * A;                                 // [8][2][S] / w, dc staging before the reduction
+    float* w_s = red;                                            // [S]  (aliases red: dead before the reduction)
+    float* dc_s = red + S;                                       // [A]
     float* uw_s = red + 8 * 2 * S;                               // [KF][S]      (LOC)
     float* ap_s = uw_s + (LOC ? p.KF * S : 0);                   // [ATT_R+KF-1] (LOC)
     __shared__ float dot_s[8];
+    __shared__ uint64_t bar;
     __shared__ int is_last;
 
     const int b = blockIdx.y, ch = blockIdx.x;
@@ -272,23 +324,27 @@ attn_bwd_kernel(const AttnBwdParams p) {
     const int nchb = (Lb + ATT_R - 1) / ATT_R;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned bytes = (unsigned)nrows * A * 4u;
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(hs, p.h + ((size_t)b * p.Lmax + l0) * A, bytes, &bar);
+    }
+    for (int i = tid; i < S; i += ATT_THREADS) w_s[i] = p.w[i];
+    for (int i = tid; i < A; i += ATT_THREADS) dc_s[i] = p.dc[(size_t)b * p.ld_dc + i];
     if (LOC) {
         for (int i = tid; i < p.KF * S; i += ATT_THREADS) uw_s[i] = p.uw[i];
         for (int x = tid; x < ATT_R + p.KF - 1; x += ATT_THREADS) {
             int l = l0 + x - p.padl;
             ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
         }
-        __syncthreads();
     }
-
-    float4 qv[NS], wv[NS], dcv[NA];
+    float4 qv[NS];
     {
         const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
 #pragma unroll
-        for (int i = 0; i < NS; i++) { qv[i] = ldg4(qb + i * 128); wv[i] = ldg4_any(p.w + lane * 4 + i * 128); }
-        const float* db = p.dc + (size_t)b * p.ld_dc + lane * 4;
-#pragma unroll
-        for (int i = 0; i < NA; i++) dcv[i] = ldg4(db + i * 128);
+        for (int i = 0; i < NS; i++) qv[i] = ldg4(qb + i * 128);
     }
     const float pen_g = (p.pen && p.lambda != 0.f && p.pen[(size_t)b * p.ld_pen] > 0.f) ? p.lambda : 0.f;
 
@@ -297,16 +353,15 @@ attn_bwd_kernel(const AttnBwdParams p) {
     for (int i = 0; i < NS; i++) { P1[i] = make_float4(0.f, 0.f, 0.f, 0.f); P2[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
     float dotp = 0.f;
 
-    const float* hbase = p.h + ((size_t)b * p.Lmax + l0) * A + lane * 4;
     const float* vbase = p.Vh + ((size_t)b * p.Lmax + l0) * S + lane * 4;
-    // software pipeline: the loads of row j+1 are in flight while row j is reduced
-    float4 hv[2][NA], vv[2][NS];
+    // Vh rows stream through registers, one row ahead; h rows come from the TMA-staged tile
+    float4 vv[2][NS];
     if (warp < nrows) {
-#pragma unroll
-        for (int i = 0; i < NA; i++) hv[0][i] = ldg_stream(hbase + (size_t)warp * A + i * 128);
 #pragma unroll
         for (int i = 0; i < NS; i++) vv[0][i] = ldg_stream(vbase + (size_t)warp * S + i * 128);
     }
+    __syncthreads();            // w_s / dc_s / uw_s / ap_s staged
+    mbar_wait(&bar, 0);         // h tile landed
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int r = warp + 8 * j;
@@ -314,16 +369,15 @@ attn_bwd_kernel(const AttnBwdParams p) {
         const int cur = j & 1, nxt = cur ^ 1;
         if (j < 3 && r + 8 < nrows) {
 #pragma unroll
-            for (int i = 0; i < NA; i++) hv[nxt][i] = ldg_stream(hbase + (size_t)(r + 8) * A + i * 128);
-#pragma unroll
             for (int i = 0; i < NS; i++) vv[nxt][i] = ldg_stream(vbase + (size_t)(r + 8) * S + i * 128);
         }
         const int l = l0 + r;
         float da = 0.f;
 #pragma unroll
         for (int i = 0; i < NA; i++) {
-            da = fmaf(hv[cur][i].x, dcv[i].x, da); da = fmaf(hv[cur][i].y, dcv[i].y, da);
-            da = fmaf(hv[cur][i].z, dcv[i].z, da); da = fmaf(hv[cur][i].w, dcv[i].w, da);
+            const float4 hv = *reinterpret_cast<const float4*>(hs + (size_t)r * A + lane * 4 + i * 128);
+            const float4 dv = *reinterpret_cast<const float4*>(dc_s + lane * 4 + i * 128);
+            da = fmaf(hv.x, dv.x, da); da = fmaf(hv.y, dv.y, da); da = fmaf(hv.z, dv.z, da); da = fmaf(hv.w, dv.w, da);
         }
         da = warp_sum(da);
         if (p.dalpha_in) da += p.dalpha_in[(size_t)b * p.ld_dain + l];
@@ -347,11 +401,12 @@ attn_bwd_kernel(const AttnBwdParams p) {
                     z = f4fma(ap, u, z);
                 }
             }
+            const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + i * 128);
             float4 g;
-            { float t = tanh_acc(z.x); g.x = wv[i].x * (1.f - t * t); }
-            { float t = tanh_acc(z.y); g.y = wv[i].y * (1.f - t * t); }
-            { float t = tanh_acc(z.z); g.z = wv[i].z * (1.f - t * t); }
-            { float t = tanh_acc(z.w); g.w = wv[i].w * (1.f - t * t); }
+            { float t = tanh_acc(z.x); g.x = wv.x * (1.f - t * t); }
+            { float t = tanh_acc(z.y); g.y = wv.y * (1.f - t * t); }
+            { float t = tanh_acc(z.z); g.z = wv.z * (1.f - t * t); }
+            { float t = tanh_acc(z.w); g.w = wv.w * (1.f - t * t); }
             P1[i] = f4fma(x, g, P1[i]);
             P2[i] = f4fma(a, g, P2[i]);
             if (LOC) {
@@ -380,7 +435,8 @@ attn_bwd_kernel(const AttnBwdParams p) {
         }
     }
 
-    // ---- cross-warp reduction of P1 / P2 / dot ---------------------------------------------------
+    // ---- cross-warp reduction of P1 / P2 / dot (red aliases w_s / dc_s: wait until every warp is done) ----
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < NS; i++) {
         *reinterpret_cast<float4*>(red + (warp * 2 + 0) * S + lane * 4 + i * 128) = P1[i];
@@ -410,21 +466,42 @@ attn_bwd_kernel(const AttnBwdParams p) {
     if (!is_last) return;
     __threadfence();
 
+    // ---- last CTA of the utterance: dq, de, d alpha_{t-1}; independent loads batched 8 deep -------------
     float dot = 0.f;
-    for (int c = lane; c < nchb; c += 32) dot += ldcg1(p.part_dot + (size_t)b * p.nch + c);
+#pragma unroll
+    for (int u = 0; u < ATT_MAXCH / 32; u++) {
+        const int c = lane + 32 * u;
+        dot += c < nchb ? ldcg1(p.part_dot + (size_t)b * p.nch + c) : 0.f;
+    }
     dot = warp_sum(dot);
     for (int i = tid; i < S; i += ATT_THREADS) {
         float s1 = 0.f, s2 = 0.f;
-        for (int c = 0; c < nchb; c++) {
-            s1 += ldcg1(p.part_P + ((size_t)b * p.nch + c) * 2 * S + i);
-            s2 += ldcg1(p.part_P + ((size_t)b * p.nch + c) * 2 * S + S + i);
+        for (int c0 = 0; c0 < nchb; c0 += 8) {
+            float t1[8], t2[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const bool ok = c0 + u < nchb;
+                t1[u] = ok ? ldcg1(p.part_P + ((size_t)b * p.nch + c0 + u) * 2 * S + i) : 0.f;
+                t2[u] = ok ? ldcg1(p.part_P + ((size_t)b * p.nch + c0 + u) * 2 * S + S + i) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { s1 += t1[u]; s2 += t2[u]; }
         }
         p.dq[(size_t)b * p.ld_dq + i] = s1 - dot * s2;
     }
-    for (int l = tid; l < p.Lmax; l += ATT_THREADS) {
-        float d = 0.f;
-        if (l < Lb) d = p.alpha[(size_t)b * p.ld_alpha + l] * (ldcg1(p.dalpha_s + (size_t)b * p.Lmax + l) - dot);
-        p.de[(size_t)b * p.ld_de + l] = d;
+    for (int l0a = 0; l0a < p.Lmax; l0a += 4 * ATT_THREADS) {
+        float av[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int l = l0a + u * ATT_THREADS + tid;
+            av[u] = l < Lb ? p.alpha[(size_t)b * p.ld_alpha + l] : 0.f;
+            dv[u] = l < Lb ? ldcg1(p.dalpha_s + (size_t)b * p.Lmax + l) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int l = l0a + u * ATT_THREADS + tid;
+            if (l < p.Lmax) p.de[(size_t)b * p.ld_de + l] = l < Lb ? av[u] * (dv[u] - dot) : 0.f;
+        }
     }
     if (p.dalpha_prev) {
         for (int l = tid; l < p.Lmax; l += ATT_THREADS) {
@@ -573,7 +650,7 @@ static int launch_fwd(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
 }
 template <int NS, int NA, bool LOC>
 static int launch_bwd(s2s_ctx* ctx, const AttnBwdParams& p, int KF) {
-    size_t smem = (size_t)8 * 2 * NS * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
+    size_t smem = (size_t)ATT_R * NA * 128 * 4 + (size_t)8 * 2 * NS * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
     static bool attr_set = false;
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {
