@@ -14,11 +14,14 @@ namespace s2s {
 
 // =================================================================================================
 // dense_small: Y[b, n] = epi( sum_k X[b,k] W[n,k] )  for a handful of rows b (the minibatch) --
-// the per-step matrix-vector products of the decoder.  The X tile (32 rows x K) is staged in shared
-// memory once per CTA; every warp owns one output unit n, keeps its weight row in registers, and the
-// 32 per-row partial sums are reduced with a 31-shuffle transpose-reduction.
+// the per-step matrix-vector products of the decoder (Linear / LinearZeroBias of Attention.lua:65-67,
+// 149-151 and the decoder GRU, GRU.lua:22-30, applied to B rows at once).
+// Mapping: lane = minibatch row, warp = one eighth of K.  Each lane keeps ITS row's K-slice in registers
+// (loaded once, straight from global), the CTA's NT weight rows are staged in shared memory and read as
+// warp-uniform broadcasts (one pass per LDS.128), so there is no shuffle reduction and no re-read of X;
+// the eight K-slices are summed through shared memory and the GRU gate math is fused into the epilogue.
 // =================================================================================================
-enum { EPI_LINEAR = 0, EPI_GRU_ZR = 1, EPI_GRU_H = 2 };
+enum { EPI_LINEAR = 0, EPI_GRU_ZR = 1, EPI_GRU_H = 2, EPI_BWD_DRHU = 3, EPI_BWD_DS = 4 };
 struct DenseEpi {
     int mode = EPI_LINEAR;
     const float* bias = nullptr;
@@ -32,79 +35,91 @@ struct DenseEpi {
     float* rh_out = nullptr; int64_t ld_rh = 0;
     float* s_out = nullptr; int64_t ld_s = 0;
     float* s_out2 = nullptr; int64_t ld_s2 = 0;
+    // backward epilogues (decoder GRU, GRU.lua:22-30 reversed)
+    float* dA = nullptr; int64_t ld_dA = 0;                // daz | dar | dah of the step being written
+    float* dsu = nullptr;                                  // [B, 2ST] d{s_{t-1}, u}
+    const float* dsc = nullptr; int64_t ld_dsc = 0;        // d{s,c} from the MLP for the step being prepared
+    const float* gates_n = nullptr; const float* su_n = nullptr;   // gates / {s,u} of the step being prepared (EPI_BWD_DS)
 };
 
-template <int KV>
-__global__ void __launch_bounds__(256)
-dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const float* __restrict__ W, int ldw, int N, const DenseEpi e) {
-    extern __shared__ __align__(16) float xs[];   // [32][K]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n = blockIdx.x * 8 + warp;
-    const int K4 = K >> 2;
-    float4 w[KV];
-    if (n < N) {
-#pragma unroll
-        for (int i = 0; i < KV; i++) {
-            const int k4 = lane + i * 32;
-            w[i] = k4 < K4 ? ldg4_any(W + (size_t)n * ldw + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ void dense_epilogue(const DenseEpi& e, int b, int n, float v) {
+    if (e.mode == EPI_LINEAR) {
+        if (e.bias) v += e.bias[n];
+        if (e.add) v += e.add[(size_t)b * e.ld_add + n];
+        e.out[(size_t)b * e.ld_out + n] = v;
+        if (e.out2 && n >= e.n2_start) e.out2[(size_t)b * e.ld_out2 + n - e.n2_start] = v;
+    } else if (e.mode == EPI_GRU_ZR) {
+        const float g = sigmoid_acc(v);                                // GRU.lua:23-24
+        e.gates[(size_t)b * e.ld_gates + n] = g;
+        if (n >= e.ST) e.rh_out[(size_t)b * e.ld_rh + n - e.ST] = g * e.sprev[(size_t)b * e.ld_sprev + n - e.ST];   // GRU.lua:25
+    } else if (e.mode == EPI_GRU_H) {
+        const float hc = tanh_acc(v);                                  // GRU.lua:26
+        const float z = e.gates[(size_t)b * e.ld_gates + n];
+        const float sp = e.sprev[(size_t)b * e.ld_sprev + n];
+        const float s = (1.f - z) * sp + z * hc;                       // GRU.lua:27-30
+        e.gates[(size_t)b * e.ld_gates + 2 * e.ST + n] = hc;
+        e.s_out[(size_t)b * e.ld_s + n] = s;
+        if (e.s_out2) e.s_out2[(size_t)b * e.ld_s2 + n] = s;
+    } else if (e.mode == EPI_BWD_DRHU) {
+        // v = (dah . G_h)[n]: n < ST -> d(r*s_{t-1}); n >= ST -> the candidate gate's share of du
+        if (n < e.ST) {
+            const float r = e.gates[(size_t)b * e.ld_gates + e.ST + n], sp = e.sprev[(size_t)b * e.ld_sprev + n];
+            e.dA[(size_t)b * e.ld_dA + e.ST + n] = v * sp * r * (1.f - r);     // dar
+            e.dsu[(size_t)b * 2 * e.ST + n] += v * r;
+        } else {
+            e.dsu[(size_t)b * 2 * e.ST + n] = v;
         }
+    } else {   // EPI_BWD_DS: v = (dq . W_s)[n]; ds_{t-1} complete -> elementwise GRU backward of step t-1
+        const float ds = v + e.dsu[(size_t)b * 2 * e.ST + n] + e.dsc[(size_t)b * e.ld_dsc + n];
+        const float z = e.gates_n[(size_t)b * e.ld_gates + n], hc = e.gates_n[(size_t)b * e.ld_gates + 2 * e.ST + n];
+        const float sp = e.su_n[(size_t)b * e.ld_sprev + n];
+        e.dA[(size_t)b * e.ld_dA + 2 * e.ST + n] = ds * z * (1.f - hc * hc);        // dah
+        e.dA[(size_t)b * e.ld_dA + n] = ds * (hc - sp) * z * (1.f - z);            // daz
+        e.dsu[(size_t)b * 2 * e.ST + n] = ds * (1.f - z);
+    }
+}
+
+template <int KS4>
+__global__ void __launch_bounds__(256)
+dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const float* __restrict__ W, int ldw, int N, int NT, const DenseEpi e) {
+    constexpr int KP4 = 8 * KS4;                     // padded K in float4 units
+    extern __shared__ __align__(16) float sm[];
+    float4* ws4 = reinterpret_cast<float4*>(sm);     // [NT][KP4]
+    float* part = sm + (size_t)NT * KP4 * 4;         // [8][NT][32]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * NT;
+    for (int idx = tid; idx < NT * KP4; idx += 256) {
+        const int c = idx / KP4, k4 = idx - c * KP4, n = n0 + c;
+        ws4[idx] = (n < N && k4 * 4 < K) ? ldg4_any(W + (size_t)n * ldw + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int b0 = 0; b0 < B; b0 += 32) {
-        const int nb = min(32, B - b0);
-        __syncthreads();
-        for (int idx = tid; idx < nb * K4; idx += 256) {
-            const int bb = idx / K4, k4 = idx - bb * K4;
-            reinterpret_cast<float4*>(xs)[bb * K4 + k4] = *reinterpret_cast<const float4*>(X + (size_t)(b0 + bb) * ldx + k4 * 4);
+        const int b = b0 + lane;
+        float4 x[KS4];
+#pragma unroll
+        for (int i = 0; i < KS4; i++) {
+            const int k = (warp * KS4 + i) * 4;
+            x[i] = (b < B && k < K) ? *reinterpret_cast<const float4*>(X + (size_t)b * ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
-        if (n >= N) continue;
-        float acc[32];
+#pragma unroll 2
+        for (int c = 0; c < NT; c++) {
+            const float4* wr = ws4 + c * KP4 + warp * KS4;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int bb = 0; bb < 32; bb++) {
-            float a = 0.f;
-            if (bb < nb) {
-#pragma unroll
-                for (int i = 0; i < KV; i++) {
-                    const int k4 = lane + i * 32;
-                    if (k4 < K4) {
-                        const float4 x = reinterpret_cast<const float4*>(xs)[bb * K4 + k4];
-                        a = fmaf(w[i].x, x.x, a); a = fmaf(w[i].y, x.y, a); a = fmaf(w[i].z, x.z, a); a = fmaf(w[i].w, x.w, a);
-                    }
-                }
+            for (int i = 0; i < KS4; i++) {
+                const float4 w4 = wr[i];
+                if (i & 1) { a1 = fmaf(w4.x, x[i].x, a1); a1 = fmaf(w4.y, x[i].y, a1); a1 = fmaf(w4.z, x[i].z, a1); a1 = fmaf(w4.w, x[i].w, a1); }
+                else { a0 = fmaf(w4.x, x[i].x, a0); a0 = fmaf(w4.y, x[i].y, a0); a0 = fmaf(w4.z, x[i].z, a0); a0 = fmaf(w4.w, x[i].w, a0); }
             }
-            acc[bb] = a;
+            part[(warp * NT + c) * 32 + lane] = a0 + a1;
         }
-        // transpose-reduce: lane bb ends with the full dot product for row b0 + bb
+        __syncthreads();
+        for (int o = tid; o < NT * 32; o += 256) {
+            const int c = o >> 5, bb = o & 31, n = n0 + c, br = b0 + bb;
+            float v = 0.f;
 #pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) {
-#pragma unroll
-            for (int i = 0; i < s; i++) {
-                const float send = (lane & s) ? acc[i] : acc[i + s];
-                const float keep = (lane & s) ? acc[i + s] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-            }
-        }
-        if (lane < nb) {
-            const int b = b0 + lane;
-            float v = acc[0];
-            if (e.mode == EPI_LINEAR) {
-                if (e.bias) v += e.bias[n];
-                if (e.add) v += e.add[(size_t)b * e.ld_add + n];
-                e.out[(size_t)b * e.ld_out + n] = v;
-                if (e.out2 && n >= e.n2_start) e.out2[(size_t)b * e.ld_out2 + n - e.n2_start] = v;
-            } else if (e.mode == EPI_GRU_ZR) {
-                const float g = sigmoid_acc(v);                        // GRU.lua:23-24
-                e.gates[(size_t)b * e.ld_gates + n] = g;
-                if (n >= e.ST) e.rh_out[(size_t)b * e.ld_rh + n - e.ST] = g * e.sprev[(size_t)b * e.ld_sprev + n - e.ST];   // GRU.lua:25
-            } else {
-                const float hc = tanh_acc(v);                          // GRU.lua:26
-                const float z = e.gates[(size_t)b * e.ld_gates + n];
-                const float sp = e.sprev[(size_t)b * e.ld_sprev + n];
-                const float s = (1.f - z) * sp + z * hc;               // GRU.lua:27-30
-                e.gates[(size_t)b * e.ld_gates + 2 * e.ST + n] = hc;
-                e.s_out[(size_t)b * e.ld_s + n] = s;
-                if (e.s_out2) e.s_out2[(size_t)b * e.ld_s2 + n] = s;
-            }
+            for (int wg = 0; wg < 8; wg++) v += part[(wg * NT + c) * 32 + bb];
+            if (n < N && br < B) dense_epilogue(e, br, n, v);
         }
     }
 }
@@ -112,24 +127,28 @@ dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const
 static int dense_small(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, const float* W, int ldw, int N, const DenseEpi& e) {
     S2S_REQUIRE(K % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "dense_small: K (%d) and ldx (%ld) must be multiples of 4 and X 16-byte aligned", K, (long)ldx);
     S2S_REQUIRE(K <= 1024, "dense_small: K=%d > 1024 not supported", K);
-    const int kv = ceil_div(K, 128);
-    const size_t smem = (size_t)32 * K * 4;
-    dim3 grid(ceil_div(N, 8));
+    const int ks4 = ceil_div(K, 32);
+    const int NT = N >= 512 ? 8 : 4;
+    dim3 grid(ceil_div(N, NT));
     prof_begin(ctx, S2S_PROF_DENSE_SMALL);
-#define DS_LAUNCH(KVV)                                                                                          \
+#define DS_LAUNCH(KS)                                                                                           \
     do {                                                                                                        \
+        const size_t smem = ((size_t)NT * 8 * KS * 4 + (size_t)8 * NT * 32) * 4;                                \
         static size_t attr = 0;                                                                                 \
         if (smem > 48 * 1024 && smem > attr) {                                                                  \
-            S2S_CUDA(cudaFuncSetAttribute(dense_small_kernel<KVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            S2S_CUDA(cudaFuncSetAttribute(dense_small_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr = smem;                                                                                        \
         }                                                                                                       \
-        dense_small_kernel<KVV><<<grid, 256, smem, ctx->stream>>>(X, ldx, B, K, W, ldw, N, e);                  \
+        dense_small_kernel<KS><<<grid, 256, smem, ctx->stream>>>(X, ldx, B, K, W, ldw, N, NT, e);               \
     } while (0)
-    if (kv <= 1) DS_LAUNCH(1);
-    else if (kv <= 2) DS_LAUNCH(2);
-    else if (kv <= 4) DS_LAUNCH(4);
-    else if (kv <= 6) DS_LAUNCH(6);
-    else DS_LAUNCH(8);
+    if (ks4 <= 1) DS_LAUNCH(1);
+    else if (ks4 <= 2) DS_LAUNCH(2);
+    else if (ks4 <= 4) DS_LAUNCH(4);
+    else if (ks4 <= 8) DS_LAUNCH(8);
+    else if (ks4 <= 12) DS_LAUNCH(12);
+    else if (ks4 <= 16) DS_LAUNCH(16);
+    else if (ks4 <= 24) DS_LAUNCH(24);
+    else DS_LAUNCH(32);
 #undef DS_LAUNCH
     prof_end(ctx, S2S_PROF_DENSE_SMALL, 4.0 * ((double)N * K + (double)B * K + (double)B * N));
     S2S_LAUNCH_CHECK(ctx);
@@ -296,11 +315,13 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
     S2S_ALLOC(d.logp, pa, float, BT * V);
     if (dropmask) S2S_ALLOC(d.scm, pa, float, BT * (ST + A)); else d.scm = d.sc;
     S2S_ALLOC(d.qbias, pa, float, S);
+    S2S_ALLOC(d.Wjc, pa, float, (size_t)ST * A);
     if (KF > 0) S2S_ALLOC(d.uw, pa, float, (size_t)KF * S); else d.uw = nullptr;
     S2S_TRY(attn_scratch_alloc(ctx, pa, B, Lmax, S, A, KF, false, &d.att));
     Arena& ar = ctx->arena;
-    float *uy, *mpre, *zeros;
+    float *uy, *mpre, *zeros, *bjc;
     S2S_ALLOC(uy, ar, float, BT * ST);
+    S2S_ALLOC(bjc, ar, float, ST);
     S2S_ALLOC(mpre, ar, float, BT * M * MW);
     S2S_ALLOC(zeros, ar, float, (size_t)B * ST);
     cudaStream_t st = ctx->stream;
@@ -316,11 +337,15 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
     } else {
         S2S_CUDA(cudaMemcpyAsync(d.qbias, P + Y.bs.off, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    // teacher-forced input path, hoisted out of the loop: y_in (Attention.lua:149) and its share of
-    // Linear(2ST,ST) (Attention.lua:151): uy = W_j[:, ST:] y_in + b_j
+    // The two input Linears on the context (Attention.lua:150-151) have no nonlinearity between them:
+    //   u = W_j {W_c c + b_c, y_in} + b_j = (W_j[:, :ST] W_c) c + W_j[:, ST:] y_in + (W_j[:, :ST] b_c + b_j)
+    // so the time loop needs ONE product on c_t; c_in itself (needed for dW_j) is recomputed time-batched.
+    S2S_TRY(gemm_f32(ctx, false, false, ST, A, ST, 1.f, P + Y.Wj.off, 2 * ST, P + Y.Wc.off, A, 0.f, d.Wjc, A, nullptr, GemmBatch(), 1, 1));
+    S2S_TRY(gemm_f32(ctx, false, true, 1, ST, ST, 1.f, P + Y.bc.off, ST, P + Y.Wj.off, 2 * ST, 0.f, bjc, ST, P + Y.bj.off, GemmBatch(), 1, 1));
+    // teacher-forced input path, hoisted out of the loop: y_in (Attention.lua:149) and its share of u
     yin_gather_kernel<<<(unsigned)BT, 128, 0, st>>>(P + Y.Wy.off, P + Y.by.off, labels, B, T, ST, V, d.yin);
     S2S_LAUNCH_CHECK(ctx);
-    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, ST, ST, 1.f, d.yin, ST, P + Y.Wj.off + ST, 2 * ST, 0.f, uy, ST, P + Y.bj.off));
+    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, ST, ST, 1.f, d.yin, ST, P + Y.Wj.off + ST, 2 * ST, 0.f, uy, ST, bjc));
     S2S_CUDA(cudaMemsetAsync(zeros, 0, (size_t)B * ST * sizeof(float), st));
     S2S_CUDA(cudaMemsetAsync(d.su, 0, BT * 2 * ST * sizeof(float), st));     // s_0 = 0 (Recurrent.lua:112)
 
@@ -339,15 +364,11 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
                                   d.alpha + (size_t)t * Lmax, (int64_t)T * Lmax, d.sc + (size_t)t * (ST + A) + ST, ldsc,
                                   d.pen + t, T, lambda, t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr, (int64_t)T * Lmax, tlens, t));
         }
-        {   // c_in = W_c c_t + b_c   (Attention.lua:150)
-            DenseEpi e; e.bias = P + Y.bc.off; e.out = d.cin + (size_t)t * ST; e.ld_out = (int64_t)T * ST;
-            S2S_TRY(dense_small(ctx, d.sc + (size_t)t * (ST + A) + ST, ldsc, B, A, P + Y.Wc.off, A, ST, e));
-        }
-        {   // u_t = W_j[:, :ST] c_in + uy_t   (Attention.lua:151) -> second halves of {s,u} and {r*s,u}
+        {   // u_t = (W_j[:, :ST] W_c) c_t + uy_t   (Attention.lua:150-151) -> second halves of {s,u} and {r*s,u}
             DenseEpi e; e.add = uy + (size_t)t * ST; e.ld_add = (int64_t)T * ST;
             e.out = d.su + (size_t)t * 2 * ST + ST; e.ld_out = ldsu;
             e.out2 = d.rhu + (size_t)t * 2 * ST + ST; e.ld_out2 = ldsu; e.n2_start = 0;
-            S2S_TRY(dense_small(ctx, d.cin + (size_t)t * ST, (int64_t)T * ST, B, ST, P + Y.Wj.off, 2 * ST, ST, e));
+            S2S_TRY(dense_small(ctx, d.sc + (size_t)t * (ST + A) + ST, ldsc, B, A, d.Wjc, A, ST, e));
         }
         {   // z, r = sigmoid(G_{z,r} {s_{t-1}, u})   (GRU.lua:22-24) ; r * s_{t-1}  (:25)
             DenseEpi e; e.mode = EPI_GRU_ZR; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
@@ -363,6 +384,8 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
         }
     }
 
+    // c_in = W_c c + b_c for all steps (Attention.lua:150): only the backward needs it
+    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, ST, A, 1.f, d.sc + ST, ST + A, P + Y.Wc.off, A, 0.f, d.cin, ST, P + Y.bc.off));
     // decoder MLP, time-batched: JoinTable{s,c} -> [Dropout] -> Maxout -> Linear -> LogSoftMax
     // (model_chorowski_baseline.lua:53-59, model_chorowski_baseline_dropout.lua:56)
     if (dropmask) {
@@ -397,7 +420,7 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     const bool carry_alpha = KF > 0 || lambda != 0.f;
 
     float *dlogits, *dmo, *dm, *dsc, *dA, *du_all, *dcin_all, *dc_all, *dq_all, *de_all, *dyin, *dVh;
-    float *ds_carry, *dsu, *drhu, *dac[2] = {nullptr, nullptr}, *GhT, *GzrT, *WjcT, *WcT, *WsT, *duw = nullptr;
+    float *ds_carry, *dsu, *dac[2] = {nullptr, nullptr}, *GhT, *GzrT, *WjcT, *WsT, *duw = nullptr;
     S2S_ALLOC(dlogits, ar, float, BT * V);
     S2S_ALLOC(dmo, ar, float, BT * M);
     S2S_ALLOC(dm, ar, float, BT * M * MW);
@@ -412,12 +435,10 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     S2S_ALLOC(dVh, ar, float, (size_t)B * Lmax * S);
     S2S_ALLOC(ds_carry, ar, float, (size_t)B * ST);
     S2S_ALLOC(dsu, ar, float, (size_t)B * 2 * ST);
-    S2S_ALLOC(drhu, ar, float, (size_t)B * 2 * ST);
     if (carry_alpha) { S2S_ALLOC(dac[0], ar, float, (size_t)B * Lmax); S2S_ALLOC(dac[1], ar, float, (size_t)B * Lmax); }
     S2S_ALLOC(GhT, ar, float, (size_t)2 * ST * ST);
     S2S_ALLOC(GzrT, ar, float, (size_t)2 * ST * 2 * ST);
-    S2S_ALLOC(WjcT, ar, float, (size_t)ST * ST);
-    S2S_ALLOC(WcT, ar, float, (size_t)A * ST);
+    S2S_ALLOC(WjcT, ar, float, (size_t)A * ST);
     S2S_ALLOC(WsT, ar, float, (size_t)ST * S);
     if (KF > 0) { S2S_ALLOC(duw, ar, float, (size_t)KF * S); S2S_CUDA(cudaMemsetAsync(duw, 0, (size_t)KF * S * sizeof(float), st)); }
     AttnScratch att;
@@ -426,8 +447,7 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     // transposed copies of the recurrent-chain weights so every in-loop product is K-contiguous
     S2S_TRY(transpose_f32(ctx, P + Y.Gh.off, ST, 2 * ST, 2 * ST, GhT, ST));          // GhT [2ST, ST]
     S2S_TRY(transpose_f32(ctx, P + Y.Gz.off, 2 * ST, 2 * ST, 2 * ST, GzrT, 2 * ST)); // rows: z then r (contiguous segments)
-    S2S_TRY(transpose_f32(ctx, P + Y.Wj.off, ST, ST, 2 * ST, WjcT, ST));             // (W_j[:, :ST])^T
-    S2S_TRY(transpose_f32(ctx, P + Y.Wc.off, ST, A, A, WcT, ST));                    // WcT [A, ST]
+    S2S_TRY(transpose_f32(ctx, d.Wjc, ST, A, A, WjcT, ST));                          // (W_j[:, :ST] W_c)^T  [A, ST]
     S2S_TRY(transpose_f32(ctx, P + Y.Ws.off, S, ST, ST, WsT, S));                    // WsT [ST, S]
 
     // ---- time-batched MLP backward (model_chorowski_baseline.lua:53-59 reversed) ----------------
@@ -454,30 +474,25 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     if (KF > 0) pad_lr(KF, &padl);
     const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST, lddA = (int64_t)T * 3 * ST;
     const int eb = ceil_div(B * ST, 256);
+    // elementwise GRU backward of the LAST step (ds_carry = 0); later steps get it fused into the W_s product
+    gru_bwd_e1_kernel<<<eb, 256, 0, st>>>(dsc + (size_t)(T - 1) * (ST + A), ldsc, ds_carry, d.gates + (size_t)(T - 1) * 3 * ST, ldg,
+                                           d.su + (size_t)(T - 1) * 2 * ST, ldsu, B, ST, dA + (size_t)(T - 1) * 3 * ST, lddA, dsu);
+    S2S_LAUNCH_CHECK(ctx);
     for (int t = T - 1; t >= 0; t--) {
         const int cur = (T - 1 - t) & 1;
-        gru_bwd_e1_kernel<<<eb, 256, 0, st>>>(dsc + (size_t)t * (ST + A), ldsc, ds_carry, d.gates + (size_t)t * 3 * ST, ldg,
-                                               d.su + (size_t)t * 2 * ST, ldsu, B, ST, dA + (size_t)t * 3 * ST, lddA, dsu);
-        S2S_LAUNCH_CHECK(ctx);
-        {   // d{r*s, u} = dah . G_h
-            DenseEpi e; e.out = drhu; e.ld_out = 2 * ST;
+        {   // d{r*s, u} = dah . G_h ; dar ; dsu[:, :ST] += d(r*s) r
+            DenseEpi e; e.mode = EPI_BWD_DRHU; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
+            e.sprev = d.su + (size_t)t * 2 * ST; e.ld_sprev = ldsu; e.dA = dA + (size_t)t * 3 * ST; e.ld_dA = lddA; e.dsu = dsu;
             S2S_TRY(dense_small(ctx, dA + (size_t)t * 3 * ST + 2 * ST, lddA, B, ST, GhT, ST, 2 * ST, e));
         }
-        gru_bwd_e2_kernel<<<eb, 256, 0, st>>>(drhu, d.gates + (size_t)t * 3 * ST, ldg, d.su + (size_t)t * 2 * ST, ldsu, B, ST,
-                                               dA + (size_t)t * 3 * ST, lddA, dsu);
-        S2S_LAUNCH_CHECK(ctx);
         {   // d{s_{t-1}, u} += {daz, dar} . G_{z,r}
             DenseEpi e; e.add = dsu; e.ld_add = 2 * ST; e.out = dsu; e.ld_out = 2 * ST;
             e.out2 = du_all + (size_t)t * ST; e.ld_out2 = (int64_t)T * ST; e.n2_start = ST;
             S2S_TRY(dense_small(ctx, dA + (size_t)t * 3 * ST, lddA, B, 2 * ST, GzrT, 2 * ST, 2 * ST, e));
         }
-        {   // dc_in = du . W_j[:, :ST]
-            DenseEpi e; e.out = dcin_all + (size_t)t * ST; e.ld_out = (int64_t)T * ST;
-            S2S_TRY(dense_small(ctx, dsu + ST, 2 * ST, B, ST, WjcT, ST, ST, e));
-        }
-        {   // dc_t = dc_mlp + dc_in . W_c
+        {   // dc_t = dc_mlp + du . (W_j[:, :ST] W_c)
             DenseEpi e; e.add = dsc + (size_t)t * (ST + A) + ST; e.ld_add = ldsc; e.out = dc_all + (size_t)t * A; e.ld_out = (int64_t)T * A;
-            S2S_TRY(dense_small(ctx, dcin_all + (size_t)t * ST, (int64_t)T * ST, B, ST, WcT, ST, A, e));
+            S2S_TRY(dense_small(ctx, dsu + ST, 2 * ST, B, ST, WjcT, ST, A, e));
         }
         {   // attention step backward
             AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw;
@@ -488,8 +503,10 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
                                   dq_all + (size_t)t * S, (int64_t)T * S, de_all + (size_t)t * Lmax, (int64_t)T * Lmax,
                                   carry_alpha ? dac[cur ^ 1] : nullptr, Lmax));
         }
-        {   // ds_{t-1} = dsu[:, :ST] + dq . W_s
-            DenseEpi e; e.add = dsu; e.ld_add = 2 * ST; e.out = ds_carry; e.ld_out = ST;
+        if (t > 0) {   // ds_{t-1} = dsu[:, :ST] + dq . W_s + ds_mlp[t-1], then the elementwise GRU backward of step t-1
+            DenseEpi e; e.mode = EPI_BWD_DS; e.ST = ST; e.dsu = dsu; e.dsc = dsc + (size_t)(t - 1) * (ST + A); e.ld_dsc = ldsc;
+            e.gates_n = d.gates + (size_t)(t - 1) * 3 * ST; e.ld_gates = ldg; e.su_n = d.su + (size_t)(t - 1) * 2 * ST; e.ld_sprev = ldsu;
+            e.dA = dA + (size_t)(t - 1) * 3 * ST; e.ld_dA = lddA;
             S2S_TRY(dense_small(ctx, dq_all + (size_t)t * S, (int64_t)T * S, B, S, WsT, S, ST, e));
         }
     }
@@ -502,7 +519,8 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     S2S_TRY(gemm_f32(ctx, true, false, ST, ST, iBT, 1.f, du_all, ST, d.cin, ST, 1.f, G + Y.Wj.off, 2 * ST, nullptr, GemmBatch(), 4));
     S2S_TRY(gemm_f32(ctx, true, false, ST, ST, iBT, 1.f, du_all, ST, d.yin, ST, 1.f, G + Y.Wj.off + ST, 2 * ST, nullptr, GemmBatch(), 4));
     S2S_TRY(colsum_add(ctx, du_all, BT, ST, ST, G + Y.bj.off));
-    // Linear(A,ST) on c (Attention.lua:150)
+    // Linear(A,ST) on c (Attention.lua:150): dc_in = du . W_j[:, :ST], time-batched
+    S2S_TRY(gemm_f32(ctx, false, false, iBT, ST, ST, 1.f, du_all, ST, P + Y.Wj.off, 2 * ST, 0.f, dcin_all, ST));
     S2S_TRY(gemm_f32(ctx, true, false, ST, A, iBT, 1.f, dcin_all, ST, d.sc + ST, ST + A, 1.f, G + Y.Wc.off, A, nullptr, GemmBatch(), 4));
     S2S_TRY(colsum_add(ctx, dcin_all, BT, ST, ST, G + Y.bc.off));
     // Linear(V,ST) on the one-hot label (Attention.lua:149)

@@ -29,6 +29,7 @@ struct DecoderState {
     float* logp = nullptr;    // [B, T, V]
     float* uw = nullptr;      // [KF, S]   U W_F   (location path)
     float* qbias = nullptr;   // [S]       b_s (+ U b_F)
+    float* Wjc = nullptr;     // [ST, A]   W_j[:, :ST] . W_c  (the two input Linears of Attention.lua:150-151 folded)
     AttnScratch att;
 };
 

@@ -134,7 +134,7 @@ gemm_simt_kernel(bool tA, bool tB, int M, int N, int K, float alpha, const float
 }
 
 int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
-                const float* B, int ldb, float beta, float* C, int ldc, const float* bias, bool* handled);
+                const float* B, int ldb, float beta, float* C, int ldc, const float* bias, bool* handled, bool force);
 
 int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
              int ldb, float beta, float* C, int ldc, const float* bias, GemmBatch batch, int splitk, int impl) {
@@ -142,9 +142,9 @@ int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, c
     S2S_REQUIRE(K >= 0, "gemm: K<0");
     S2S_REQUIRE(!(splitk > 1 && batch.count > 1), "gemm: split-K and batching are exclusive");
     S2S_REQUIRE(!(splitk > 1 && beta != 1.f), "gemm: split-K requires beta == 1 (accumulate)");
-    if (impl != 1 && batch.count == 1 && splitk == 1) {
+    if (impl != 1 && batch.count == 1) {
         bool handled = false;
-        S2S_TRY(gemm_tc_f32(ctx, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &handled));
+        S2S_TRY(gemm_tc_f32(ctx, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &handled, impl == 2));
         if (handled) return 0;
         S2S_REQUIRE(impl != 2, "gemm: tcgen05 path requested but shape/alignment not supported (M=%d N=%d K=%d)", M, N, K);
     }

@@ -112,8 +112,11 @@ def gemm(ctx, A, B, tA=False, tB=False, alpha=1.0, beta=0.0, C_out=None, bias=No
     N = B.shape[0] if tB else B.shape[1]
     if C_out is None:
         C_out = ctx.zeros(M, N)
-    check(ctx.lib.s2s_gemm_f32(ctx.h, impl, int(tA), int(tB), M, N, K, alpha, _f(A), A.stride(0), _f(B), B.stride(0), beta,
-                               _f(C_out), C_out.stride(0), _f(bias)))
+    def ptr(t):   # row-strided 2-D views are allowed here (leading dimension = stride(0))
+        assert t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1
+        return C.c_void_p(t.data_ptr())
+    check(ctx.lib.s2s_gemm_f32(ctx.h, impl, int(tA), int(tB), M, N, K, alpha, ptr(A), A.stride(0), ptr(B), B.stride(0), beta,
+                               ptr(C_out), C_out.stride(0), _f(bias)))
     return C_out
 
 

@@ -1,0 +1,36 @@
+"""tcgen05 (3xTF32) GEMM against float64: must hold the fp32 parity bound with margin."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import dev, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 128, 64), (300, 200, 96), (1000, 1536, 512), (9600, 512, 512), (130, 70, 36)])
+def test_gemm_tcgen05_3xtf32(s2s, gctx, M, N, K):
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    ref = 0.5 * (A.astype(np.float64) @ B.astype(np.float64).T) + 2.0 * C0 + bias
+    Cd = dev(C0)
+    s2s.gemm(gctx, dev(A), dev(B), tA=False, tB=True, alpha=0.5, beta=2.0, C_out=Cd, bias=dev(bias), impl=2)
+    torch.cuda.synchronize()
+    assert rel_err(Cd.cpu().numpy(), ref) < 2e-5
+
+
+def test_gemm_tcgen05_strided_operands(s2s, gctx):
+    # the encoder projection reads the x-columns of the GRU weights: B = W[:, H:] with row pitch H + Din
+    rng = np.random.default_rng(5)
+    M, N, K, H = 640, 384, 256, 128
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = rng.standard_normal((N, H + K)).astype(np.float32)
+    ref = A.astype(np.float64) @ W[:, H:].astype(np.float64).T
+    Wd = dev(W)
+    Cd = torch.zeros(M, N, device="cuda")
+    s2s.gemm(gctx, dev(A), Wd[:, H:], tA=False, tB=True, C_out=Cd, impl=2)
+    torch.cuda.synchronize()
+    assert rel_err(Cd.cpu().numpy(), ref) < 2e-5
