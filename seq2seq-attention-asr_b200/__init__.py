@@ -7,7 +7,7 @@ protocol (updateOutput / updateGradInput / accGradParameters) of Attention.lua, 
 The directory name contains hyphens; import it with
     importlib.import_module("seq2seq-attention-asr_b200")      or      import s2s_b200
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, dp, nn, ops  # noqa: F401
 from ._lib import LIB_PATH, ModelCfg, S2SError, declared_symbols, load  # noqa: F401
 from .ops import *  # noqa: F401,F403
 from .ops import CHOROWSKI_TIMIT, Context  # noqa: F401

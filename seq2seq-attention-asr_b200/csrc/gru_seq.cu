@@ -242,14 +242,16 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
             tot1[hf] = 0.f;
             if (!(p.dbg & 2)) tot1[hf] = hf == 0 ? matvec<H, 8, (BG < 4 ? BG : 4)>(w1, hbuf, 0, lane) : matvec<H, 8, NB2>(w1, hbuf, 4, lane);
         }
+        float g1v[NH];
+#pragma unroll
+        for (int hf = 0; hf < NH; hf++) g1v[hf] = sigmoid_acc(tot1[hf] + xp1[hf]);    // GRU.lua:23-24 (both halves in flight)
 #pragma unroll
         for (int hf = 0; hf < NH; hf++) {
-            const float tot = tot1[hf];
             const int bl = 4 * hf + (lane & 3);
             if (bl < BG) {
                 const bool act = s < Lf[hf];
                 const int t = rev ? Lf[hf] - 1 - s : s;
-                const float g = sigmoid_acc(tot + xp1[hf]);                            // GRU.lua:23-24
+                const float g = g1v[hf];
                 float* sv = p.save + (((size_t)(b0 + bl) * p.Lmax + t) * p.ndir + dir) * 4 * H;
                 if (g1 == 0) {
                     zbuf[bl][ju1] = g;
@@ -274,9 +276,11 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
             tot2[hf] = 0.f;
             if (!(p.dbg & 2)) tot2[hf] = hf == 0 ? matvec<H, 4, (BG < 4 ? BG : 4)>(w2, rhbuf, 0, lane) : matvec<H, 4, NB2>(w2, rhbuf, 4, lane);
         }
+        float hcv[NH];
+#pragma unroll
+        for (int hf = 0; hf < NH; hf++) hcv[hf] = tanh_acc(tot2[hf] + xp2[hf]);       // GRU.lua:26 (both halves in flight)
 #pragma unroll
         for (int hf = 0; hf < NH; hf++) {
-            const float tot = tot2[hf];
             const int bl = 4 * hf + (lane & 3);
             if (lane < 16 && bl < BG) {
                 const bool act = s < Lf[hf];
@@ -284,7 +288,7 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
                 const float hp = hbuf[bl][j2];
                 float hn = hp;                                                         // inactive: state frozen
                 if (act) {
-                    const float hc = tanh_acc(tot + xp2[hf]);                          // GRU.lua:26
+                    const float hc = hcv[hf];
                     const float z = zbuf[bl][ju2];
                     hn = (1.f - z) * hp + z * hc;                                      // GRU.lua:27-30
                     const size_t row = (size_t)(b0 + bl) * p.Lmax + t;
@@ -550,6 +554,7 @@ static int launch_cluster(s2s_ctx* ctx, bool backward, const GruSeqParams& p) {
     const int cap = max_active[backward];
     int bg = 4;
     while (bg < 8 && p.ndir * ceil_div(p.B, bg) > cap) bg++;
+    { const char* e = getenv("S2S_GRU_BG"); if (e && atoi(e) >= 4 && atoi(e) <= 8) bg = atoi(e); }
     switch (bg) {
         case 4: return launch_cluster_bg<H, 4>(ctx, backward, p, nullptr);
         case 5: return launch_cluster_bg<H, 5>(ctx, backward, p, nullptr);

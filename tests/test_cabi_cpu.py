@@ -1,0 +1,66 @@
+"""CPU-side checks of the boundary: the shared library loads, exports every symbol declared in
+include/s2s_b200.h, agrees with the oracle on the flat parameter layout, and fails loudly (never falls
+back) when there is no CUDA device.  No compute call is made here."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol(s2s):
+    lib = s2s.load()
+    names = s2s.declared_symbols()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.s2s_version() == 100
+
+
+def test_layout_matches_oracle(s2s, orc64):
+    from oracle.oracle import CHOROWSKI_TIMIT, segment_names
+    for cfg in (CHOROWSKI_TIMIT, dict(CHOROWSKI_TIMIT, K=16, KF=10), dict(D=13, H=128, NL=2, S=128, ST=64, V=11, K=3, KF=4, M=8, MW=3)):
+        assert s2s.param_count(cfg) == orc64.param_count(cfg)
+        assert s2s.decoder_param_offset(cfg) > 0
+        segs = s2s.param_segments(cfg)
+        assert [tuple(int(v) for v in r) for r in orc64.param_segments(cfg)] == [tuple(r) for r in segs]
+        assert s2s.segment_names(cfg) == segment_names(cfg)
+    assert s2s.param_count(CHOROWSKI_TIMIT) == 4356735          # SURVEY App. A parameter census
+    assert s2s.param_count(dict(CHOROWSKI_TIMIT, K=16, KF=10)) == 4365615
+
+
+def test_invalid_cfg_is_an_error(s2s):
+    assert s2s.param_count(dict(D=0, H=1, NL=1, S=1, ST=1, V=2, K=0, KF=1, M=1, MW=1)) == -1
+    assert b"invalid model cfg" in s2s.load().s2s_last_error()
+
+
+def test_no_cpu_fallback(s2s):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(s2s.S2SError, match="no CUDA device"):
+        s2s.Context(0)
+    h = C.c_void_p()
+    assert s2s.load().s2s_ctx_create(0, None, C.byref(h)) != 0
+    assert b"no CPU fallback" in s2s.load().s2s_last_error()
+
+
+def test_product_package_does_not_import_the_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "seq2seq-attention-asr_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".lua")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the oracle's", "").lower() or f in ("_never_",), f"{f} mentions the oracle"
+
+
+def test_init_params_rules(s2s):
+    cfg = dict(D=13, H=128, NL=1, S=128, ST=64, V=11, K=2, KF=4, M=8, MW=3)
+    P = s2s.init_params(cfg, seed=3)
+    for (off, rows, cols), name in zip(s2s.param_segments(cfg), s2s.segment_names(cfg)):
+        seg = P[off:off + rows * cols]
+        if name in ("bV", "bU", "be"):
+            assert not seg.any()                                  # dead biases stay zero
+        elif cols > 1:
+            fan = cfg["KF"] if name == "WF" else cols
+            assert np.abs(seg).max() <= 1 / np.sqrt(fan) + 1e-7 and seg.std() > 0

@@ -1,0 +1,77 @@
+"""The reference-facing module surface (nn.Attention, nn.RNN(nn.GRU), nn.TemporalConvolutionZeroBias, ...)
+through forward/backward, in single-utterance ("SGD") and batch mode, against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import dev, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def test_rnn_gru_module_sgd_and_batch(s2s, gctx, orc64):
+    nn = s2s.nn
+    rng = np.random.default_rng(0)
+    gru = nn.GRU(gctx, 24, 128)
+    W = gru.weight.cpu().numpy().astype(np.float64)
+    for reverse in (False, True):
+        rnn = nn.RNN(gctx, gru, reverse)
+        x = rng.standard_normal((31, 24))
+        y_ref, gates = orc64.gru_seq_forward(W[0], W[1], W[2], x, reverse=reverse)
+        y = rnn.forward(dev(x, torch.float32))                       # 2-D = one utterance
+        assert y.shape == (31, 128) and rel_err(y.cpu().numpy(), y_ref) < TOL
+        dy = rng.standard_normal((31, 128))
+        gru.zeroGradParameters()
+        dx = rnn.backward(dev(x, torch.float32), dev(dy, torch.float32))
+        dx_ref, dWz, dWr, dWh = orc64.gru_seq_backward(W[0], W[1], W[2], x, y_ref, gates, dy, reverse=reverse)
+        assert rel_err(dx.cpu().numpy(), dx_ref) < TOL
+        assert rel_err(gru.gradWeight.cpu().numpy(), np.stack([dWz, dWr, dWh])) < TOL
+        xb = np.stack([x, x[::-1].copy()])                           # 3-D = batch; rows equal the SGD-mode result
+        yb = rnn.forward(dev(xb, torch.float32))
+        assert rel_err(yb[0].cpu().numpy(), y_ref) < TOL
+
+
+def test_attention_module_sgd_equals_batch(s2s, gctx, orc64):
+    # the reference notebook's invariant (Attention.ipynb:1202/1763): batch rows == SGD-mode result
+    nn = s2s.nn
+    rng = np.random.default_rng(1)
+    att = nn.Attention(gctx, None, None, 128, 4, 3, 64, 256, 11, False, 0.0, mlpDepth=8, maxoutWindow=3)
+    L, T, V = 37, 5, 11
+    h = rng.standard_normal((2, L, 256)) * 0.5
+    lab = rng.integers(0, V, (2, T))
+    y = np.eye(V)[lab]
+    out_b = att.forward([dev(h, torch.float32), dev(y, torch.float32)])
+    alpha_b = att.alpha()
+    P = att.flat.cpu().numpy().astype(np.float64)
+    for b in range(2):
+        out_s = att.forward([dev(h[b], torch.float32), dev(y[b], torch.float32)])
+        assert out_s.shape == (T, V)
+        assert rel_err(out_s.cpu().numpy(), out_b[b].cpu().numpy()) < 1e-5
+        ref = orc64.attention_forward(att.cfg, P, h[b], lab[b])
+        assert rel_err(out_s.cpu().numpy(), ref["logp"]) < TOL
+        assert rel_err(att.alpha().cpu().numpy(), ref["alpha"]) < TOL
+        assert rel_err(alpha_b[b].cpu().numpy(), ref["alpha"]) < TOL
+    # backward accumulates parameter gradients inside updateGradInput (Attention.lua:325)
+    att.zeroGradParameters()
+    dlogp = rng.standard_normal((T, V))
+    att.forward([dev(h[0], torch.float32), dev(y[0], torch.float32)])
+    dh, _ = att.backward([dev(h[0], torch.float32), dev(y[0], torch.float32)], dev(dlogp, torch.float32))
+    G_ref, dh_ref = orc64.attention_backward(att.cfg, P, h[0], lab[0], dlogp)
+    assert rel_err(dh.cpu().numpy(), dh_ref) < TOL
+    assert rel_err(att.gradFlat.cpu().numpy(), G_ref) < TOL
+    with pytest.raises(s2s.S2SError):
+        att.forward([dev(h[0, 0], torch.float32), dev(y[0], torch.float32)])      # "x must be 2d or 3d"
+
+
+def test_tconv_zero_bias_module(s2s, gctx):
+    nn = s2s.nn
+    m = nn.TemporalConvolutionZeroBias(gctx, 5, 4, 1)
+    m.weight.copy_(torch.arange(1, 21, dtype=torch.float32).view(4, 5))
+    y = m.forward(torch.ones(10, 5, device="cuda"))
+    assert np.array_equal(y.cpu().numpy(), np.tile([15, 40, 65, 90], (10, 1)).astype(np.float32))   # Attention.ipynb:123-154
+    m.backward(torch.ones(10, 5, device="cuda"), torch.ones(10, 4, device="cuda"))
+    assert float(m.gradBias.abs().sum()) == 0.0 and float(m.bias.abs().sum()) == 0.0
+    assert np.allclose(m.gradWeight.cpu().numpy(), 10.0)
+    with pytest.raises(s2s.S2SError):
+        nn.TemporalConvolutionZeroBias(gctx, 5, 4, 3)
