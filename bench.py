@@ -109,7 +109,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(json.dumps(line))
 
 
 # -------------------------------------------------------------------------------------------------
@@ -159,7 +159,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def dbg(msg):
+    if os.environ.get("S2S_BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
+    if os.environ.get("S2S_BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["S2S_BENCH_DEBUG"]), exit=True)
     import torch
     import torch.distributed as dist
     import s2s_b200 as s2s
@@ -174,6 +182,7 @@ def run_ours(args):
     else:
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    dbg("process group up")
     ctx = s2s.Context(local)
     B = B_PER_GPU
     n = s2s.param_count(CFG)
@@ -199,9 +208,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
         step(X, y, ln, tl)
+        torch.cuda.synchronize()
+        dbg(f"warmup step {i} done")
     barrier()
+    dbg("warmup barrier passed")
 
     # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps ------------------------
     sampler = ClockSampler(local)
@@ -217,6 +229,7 @@ def run_ours(args):
         b.record()
     barrier()
     launches = ctx.launches - launches0
+    dbg("timed region done")
     clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -258,26 +271,28 @@ def run_ours(args):
     # ---- roofline: instrumented extra pass (graphs off), per-kernel-class CUDA events ------------------
     roof = None
     classes = {}
+    hbm, tf, how = peaks()
+    ctx.set_graphs(False)
     if rank == 0:
-        hbm, tf, how = peaks()
-        ctx.set_graphs(False)
         ctx.profile(True)
-        ev2 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        nprof = 3
-        # Eager launches of microsecond kernels are host-bound: an event pair around such a launch would also time the
-        # host gap.  A spin kernel keeps the GPU behind the host while the step is enqueued, so every (event, kernel,
-        # event) triple executes back to back and the events bracket GPU execution only.
-        total_ms = 0.0
-        for _ in range(nprof):
-            torch.cuda._sleep(int(60e6))          # ~30 ms of spinning, not inside any event pair
-            ev2[0].record()
-            step(X, y, ln, tl)
-            ev2[1].record()
-            torch.cuda.synchronize()
-            total_ms += ev2[0].elapsed_time(ev2[1]) / nprof
+    ev2 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    nprof = 3
+    # Eager launches of microsecond kernels are host-bound: an event pair around such a launch would also time the
+    # host gap.  A spin kernel keeps the GPU behind the host while the step is enqueued, so every (event, kernel,
+    # event) triple executes back to back and the events bracket GPU execution only.  Every rank runs the pass
+    # (the step contains the all-reduce); only rank 0 records.
+    total_ms = 0.0
+    for _ in range(nprof):
+        torch.cuda._sleep(int(60e6))          # ~30 ms of spinning, not inside any event pair
+        ev2[0].record()
+        step(X, y, ln, tl)
+        ev2[1].record()
+        torch.cuda.synchronize()
+        total_ms += ev2[0].elapsed_time(ev2[1]) / nprof
+    ctx.set_graphs(True)
+    if rank == 0:
         prof = ctx.profile_read()
         ctx.profile(False)
-        ctx.set_graphs(True)
         for k, (kms, cnt, work) in prof.items():
             if cnt == 0:
                 continue
@@ -286,7 +301,7 @@ def run_ours(args):
             if k == "gemm":
                 classes[k] = {"bound": "tensor", "ms_per_step": kms / nprof, "launches_per_step": cnt / nprof, "achieved": ach / 1e12,
                               "peak": tf, "unit": "TFLOP/s", "frac": ach / 1e12 / tf, "share": kms / nprof / total_ms,
-                              "note": "exact-fp32 SIMT FFMA path (not tensor cores)"}
+                              "note": "fp32-equivalent FLOPs; large products run 3xTF32 on tcgen05 (3 tensor-core passes per product), small ones exact-fp32 SIMT"}
             else:
                 classes[k] = {"bound": "hbm", "ms_per_step": kms / nprof, "launches_per_step": cnt / nprof, "achieved": ach / 1e9,
                               "peak": hbm, "unit": "GB/s", "frac": ach / 1e9 / hbm, "share": kms / nprof / total_ms}
@@ -318,12 +333,20 @@ def run_ours(args):
             "kernels": classes,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit_json(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON); anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (line + "\n").encode())
+
+    globals()["emit_json"] = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
