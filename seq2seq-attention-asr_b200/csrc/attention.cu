@@ -80,6 +80,7 @@ attn_fwd_kernel(const AttnFwdParams p) {
     const int nchb = (Lb + ATT_R - 1) / ATT_R;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    pdl_trigger();
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     __syncthreads();
     if (tid == 0) {
@@ -89,20 +90,14 @@ attn_fwd_kernel(const AttnFwdParams p) {
     }
     if (LOC) {
         for (int i = tid; i < p.KF * S; i += ATT_THREADS) uw_s[i] = p.uw[i];
-        for (int x = tid; x < ATT_R + p.KF - 1; x += ATT_THREADS) {
-            int l = l0 + x - p.padl;
-            ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
-        }
-        __syncthreads();
     }
 
     // ---- scoring: warp per row, 4 rows per warp, all Vh loads issued up front -----------------
+    // (h, Vh, w and the folded location weights are inputs of the whole decoder call, so their loads are issued
+    //  BEFORE the programmatic-dependency wait and overlap the tail of the previous kernel of the chain)
     float4 qv[NS], wv[NS];
-    {
-        const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
 #pragma unroll
-        for (int i = 0; i < NS; i++) { qv[i] = ldg4(qb + i * 128); wv[i] = ldg4_any(p.w + lane * 4 + i * 128); }
-    }
+    for (int i = 0; i < NS; i++) wv[i] = ldg4_any(p.w + lane * 4 + i * 128);
     const float* vbase = p.Vh + ((size_t)b * p.Lmax + l0) * S + lane * 4;
     float4 v[4][NS];
 #pragma unroll
@@ -112,6 +107,19 @@ attn_fwd_kernel(const AttnFwdParams p) {
 #pragma unroll
             for (int i = 0; i < NS; i++) v[j][i] = ldg_stream(vbase + (size_t)r * S + i * 128);
         }
+    }
+    pdl_wait();                                      // q_t (and alpha_{t-1}) come from the kernels just before this one
+    if (LOC) {
+        for (int x = tid; x < ATT_R + p.KF - 1; x += ATT_THREADS) {
+            int l = l0 + x - p.padl;
+            ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
+        }
+        __syncthreads();
+    }
+    {
+        const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
+#pragma unroll
+        for (int i = 0; i < NS; i++) qv[i] = __ldcg(reinterpret_cast<const float4*>(qb + i * 128));
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -324,6 +332,7 @@ attn_bwd_kernel(const AttnBwdParams p) {
     const int nchb = (Lb + ATT_R - 1) / ATT_R;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    pdl_trigger();
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     __syncthreads();
     if (tid == 0) {
@@ -331,8 +340,8 @@ attn_bwd_kernel(const AttnBwdParams p) {
         mbar_expect_tx(&bar, bytes);
         bulk_g2s(hs, p.h + ((size_t)b * p.Lmax + l0) * A, bytes, &bar);
     }
+    // call-level inputs first (overlaps the previous kernel of the chain), then wait for dc_t / d alpha_t
     for (int i = tid; i < S; i += ATT_THREADS) w_s[i] = p.w[i];
-    for (int i = tid; i < A; i += ATT_THREADS) dc_s[i] = p.dc[(size_t)b * p.ld_dc + i];
     if (LOC) {
         for (int i = tid; i < p.KF * S; i += ATT_THREADS) uw_s[i] = p.uw[i];
         for (int x = tid; x < ATT_R + p.KF - 1; x += ATT_THREADS) {
@@ -346,6 +355,8 @@ attn_bwd_kernel(const AttnBwdParams p) {
 #pragma unroll
         for (int i = 0; i < NS; i++) qv[i] = ldg4(qb + i * 128);
     }
+    pdl_wait();
+    for (int i = tid; i < A; i += ATT_THREADS) dc_s[i] = __ldcg(p.dc + (size_t)b * p.ld_dc + i);
     const float pen_g = (p.pen && p.lambda != 0.f && p.pen[(size_t)b * p.ld_pen] > 0.f) ? p.lambda : 0.f;
 
     float4 P1[NS], P2[NS];
@@ -640,7 +651,7 @@ static int launch_fwd(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
         attr_set = true; attr_smem = smem;
     }
     prof_begin(ctx, S2S_PROF_ATTN_FWD);
-    attn_fwd_kernel<NS, NA, LOC><<<dim3(p.nch, p.B), ATT_THREADS, smem, ctx->stream>>>(p);
+    S2S_CUDA(launch_kernel(attn_fwd_kernel<NS, NA, LOC>, dim3(p.nch, p.B), dim3(ATT_THREADS), smem, ctx->stream, ctx->pdl, p));
     {   // algorithmic bytes A_f = 4 B (L S + L A + 2L + S + A)   
         const double S = NS * 128.0, A = NA * 128.0, L = p.Lmax;
         prof_end(ctx, S2S_PROF_ATTN_FWD, 4.0 * p.B * (L * S + L * A + 2 * L + S + A));
@@ -658,7 +669,7 @@ static int launch_bwd(s2s_ctx* ctx, const AttnBwdParams& p, int KF) {
         attr_set = true; attr_smem = smem;
     }
     prof_begin(ctx, S2S_PROF_ATTN_BWD);
-    attn_bwd_kernel<NS, NA, LOC><<<dim3(p.nch, p.B), ATT_THREADS, smem, ctx->stream>>>(p);
+    S2S_CUDA(launch_kernel(attn_bwd_kernel<NS, NA, LOC>, dim3(p.nch, p.B), dim3(ATT_THREADS), smem, ctx->stream, ctx->pdl, p));
     {   // A_b,min = 4 B (L S + L A + 6L + 2S + 2A)   (deferred accumulation)
         const double S = NS * 128.0, A = NA * 128.0, L = p.Lmax;
         prof_end(ctx, S2S_PROF_ATTN_BWD, 4.0 * p.B * (L * S + L * A + 6 * L + 2 * S + 2 * A));

@@ -81,6 +81,7 @@ struct s2s_ctx {
     int sm_count = 148;
     int64_t launches = 0;
     bool graphs = true;
+    bool pdl = true;           // programmatic dependent launch for the decoder's per-step kernel chain (S2S_PDL=0 disables)
     s2s::Arena arena;          // per-call scratch (reset at the start of each top-level call)
     s2s::Arena persist;        // state that survives between forward and backward
     s2s::DecoderState* dec = nullptr;
@@ -179,6 +180,13 @@ __device__ __forceinline__ float4 ldg4_any(const float* p) {
 __device__ __forceinline__ float ldcg1(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may
+// start while its predecessor in the stream is still running; everything it does before pdl_wait() must not
+// depend on (or overwrite inputs of) recent kernels.  pdl_wait() returns once the predecessor grid has completed
+// and its writes are visible; both calls are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk) --------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -207,6 +215,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 #endif  // __CUDACC__
+
+// launch with (pdl = true) or without the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,6 +1,7 @@
 // core.cu -- context lifetime, workspace arena, flat parameter layout and small utility kernels.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -200,6 +201,7 @@ int s2s_ctx_create(int device, void* stream, s2s_ctx** out) {
     S2S_REQUIRE(prop.major >= 10, "device %d is sm_%d%d; libs2s_b200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
     s2s_ctx* c = new s2s_ctx();
     c->device = device;
+    { const char* e = getenv("S2S_PDL"); if (e) c->pdl = atoi(e) != 0; }
     c->sm_count = prop.multiProcessorCount;
     c->stream = (cudaStream_t)stream;   // NULL = the legacy default stream (what cutorch uses, timit/timit.lua:39)
     c->own_stream = false;

@@ -88,17 +88,20 @@ dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const
     float* part = sm + (size_t)NT * KP4 * 4;         // [8][NT][32]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * NT;
+    pdl_trigger();                                   // let the next kernel of the chain start its own prologue
+    // prologue independent of the previous kernel: stage this CTA's weight rows (parameters / per-call copies)
     for (int idx = tid; idx < NT * KP4; idx += 256) {
         const int c = idx / KP4, k4 = idx - c * KP4, n = n0 + c;
         ws4[idx] = (n < N && k4 * 4 < K) ? ldg4_any(W + (size_t)n * ldw + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    pdl_wait();                                      // X (and everything the epilogue touches) is produced upstream
     for (int b0 = 0; b0 < B; b0 += 32) {
         const int b = b0 + lane;
         float4 x[KS4];
 #pragma unroll
         for (int i = 0; i < KS4; i++) {
             const int k = (warp * KS4 + i) * 4;
-            x[i] = (b < B && k < K) ? *reinterpret_cast<const float4*>(X + (size_t)b * ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[i] = (b < B && k < K) ? __ldcg(reinterpret_cast<const float4*>(X + (size_t)b * ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
 #pragma unroll 2
@@ -139,7 +142,7 @@ static int dense_small(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, 
             S2S_CUDA(cudaFuncSetAttribute(dense_small_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr = smem;                                                                                        \
         }                                                                                                       \
-        dense_small_kernel<KS><<<grid, 256, smem, ctx->stream>>>(X, ldx, B, K, W, ldw, N, NT, e);               \
+        S2S_CUDA(launch_kernel(dense_small_kernel<KS>, grid, dim3(256), smem, ctx->stream, ctx->pdl, X, ldx, B, K, W, ldw, N, NT, e)); \
     } while (0)
     if (ks4 <= 1) DS_LAUNCH(1);
     else if (ks4 <= 2) DS_LAUNCH(2);
