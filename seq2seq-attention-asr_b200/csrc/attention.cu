@@ -56,14 +56,15 @@ struct AttnFwdParams {
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4fma(float s, float4 a, float4 b) { return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w)); }
 
-template <int NS, int NA, bool LOC>
-__global__ void __launch_bounds__(ATT_THREADS)
+template <int NS, int NA, bool LOC, int RIF>
+__global__ void __launch_bounds__(ATT_THREADS, RIF == 2 ? 3 : 2)
 attn_fwd_kernel(const AttnFwdParams p) {
     constexpr int S = NS * 128, A = NA * 128;
     constexpr int GROUPS = 8 / NA;              // row groups in the context phase
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* hs = reinterpret_cast<float*>(smem_raw);                 // [ATT_R][A]
-    float* uw_s = hs + ATT_R * A;                                    // [KF][S]        (LOC)
+    float* w_s = hs + ATT_R * A;                                     // [S]
+    float* uw_s = w_s + S;                                           // [KF][S]        (LOC)
     float* ap_s = uw_s + (LOC ? p.KF * S : 0);                       // [ATT_R+KF-1]   (LOC)
     __shared__ float e_s[ATT_R], p_s[ATT_R];
     __shared__ __align__(16) float red[1024];
@@ -92,16 +93,15 @@ attn_fwd_kernel(const AttnFwdParams p) {
         for (int i = tid; i < p.KF * S; i += ATT_THREADS) uw_s[i] = p.uw[i];
     }
 
-    // ---- scoring: warp per row, 4 rows per warp, all Vh loads issued up front -----------------
-    // (h, Vh, w and the folded location weights are inputs of the whole decoder call, so their loads are issued
-    //  BEFORE the programmatic-dependency wait and overlap the tail of the previous kernel of the chain)
-    float4 qv[NS], wv[NS];
-#pragma unroll
-    for (int i = 0; i < NS; i++) wv[i] = ldg4_any(p.w + lane * 4 + i * 128);
+    // ---- scoring: warp per row, 4 rows per warp processed as two pairs (keeps the kernel under 85 registers so
+    // three CTAs share an SM: 24 warps of loads in flight, and the 320-CTA grid of the B=32, L=300 step is one wave).
+    // h, Vh, w and the folded location weights are inputs of the whole decoder call, so their loads are issued
+    // BEFORE the programmatic-dependency wait and may overlap the tail of the previous kernel of the chain.
+    for (int i = tid; i < S; i += ATT_THREADS) w_s[i] = p.w[i];
     const float* vbase = p.Vh + ((size_t)b * p.Lmax + l0) * S + lane * 4;
-    float4 v[4][NS];
+    float4 v[RIF][NS];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < RIF; j++) {
         const int r = warp + 8 * j;
         if (r < nrows) {
 #pragma unroll
@@ -114,35 +114,50 @@ attn_fwd_kernel(const AttnFwdParams p) {
             int l = l0 + x - p.padl;
             ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
         }
-        __syncthreads();
     }
+    float4 qv[NS];
     {
         const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
 #pragma unroll
         for (int i = 0; i < NS; i++) qv[i] = __ldcg(reinterpret_cast<const float4*>(qb + i * 128));
     }
+    __syncthreads();                                 // w_s (uw_s, ap_s) staged
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int r = warp + 8 * j;
-        if (r < nrows) {
-            float acc = 0.f;
+    for (int pr = 0; pr < 4 / RIF; pr++) {
 #pragma unroll
-            for (int i = 0; i < NS; i++) {
-                float4 z = f4add(v[j][i], qv[i]);
-                if (LOC) {
-                    for (int jj = 0; jj < p.KF; jj++) {
-                        const float a = ap_s[r + jj];
-                        const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
-                        z = f4fma(a, u, z);
+        for (int j = 0; j < RIF; j++) {
+            const int r = warp + 8 * (RIF * pr + j);
+            if (r < nrows) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < NS; i++) {
+                    float4 z = f4add(v[j][i], qv[i]);
+                    if (LOC) {
+                        for (int jj = 0; jj < p.KF; jj++) {
+                            const float a = ap_s[r + jj];
+                            const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
+                            z = f4fma(a, u, z);
+                        }
                     }
+                    const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + i * 128);
+                    acc = fmaf(wv.x, tanh_acc(z.x), acc);
+                    acc = fmaf(wv.y, tanh_acc(z.y), acc);
+                    acc = fmaf(wv.z, tanh_acc(z.z), acc);
+                    acc = fmaf(wv.w, tanh_acc(z.w), acc);
                 }
-                acc = fmaf(wv[i].x, tanh_acc(z.x), acc);
-                acc = fmaf(wv[i].y, tanh_acc(z.y), acc);
-                acc = fmaf(wv[i].z, tanh_acc(z.z), acc);
-                acc = fmaf(wv[i].w, tanh_acc(z.w), acc);
+                acc = warp_sum(acc);
+                if (lane == 0) e_s[r] = acc;
             }
-            acc = warp_sum(acc);
-            if (lane == 0) e_s[r] = acc;
+        }
+        if (RIF == 2 && pr == 0) {   // second pair of rows
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int r = warp + 8 * (2 + j);
+                if (r < nrows) {
+#pragma unroll
+                    for (int i = 0; i < NS; i++) v[j][i] = ldg_stream(vbase + (size_t)r * S + i * 128);
+                }
+            }
         }
     }
     __syncthreads();
@@ -310,15 +325,17 @@ struct AttnBwdParams {
 };
 
 template <int NS, int NA, bool LOC>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 3)
 attn_bwd_kernel(const AttnBwdParams p) {
     constexpr int S = NS * 128, A = NA * 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int HS = (ATT_R * A > 8 * 2 * S) ? ATT_R * A : 8 * 2 * S;
     float* hs = reinterpret_cast<float*>(smem_raw);              // [ATT_R][A]   h tile (bulk TMA)
-    float* red = hs + ATT_R * A;                                 // [8][2][S] / w, dc staging before the reduction
-    float* w_s = red;                                            // [S]  (aliases red: dead before the reduction)
-    float* dc_s = red + S;                                       // [A]
-    float* uw_s = red + 8 * 2 * S;                               // [KF][S]      (LOC)
+    float* red = hs;                                             // [8][2][S]    cross-warp reduction, aliases the (then dead) h tile
+    float* w_s = hs + HS;                                        // [S]
+    float* dc_s = w_s + S;                                       // [A]
+    float* q_s = dc_s + A;                                       // [S]
+    float* uw_s = q_s + S;                                       // [KF][S]      (LOC)
     float* ap_s = uw_s + (LOC ? p.KF * S : 0);                   // [ATT_R+KF-1] (LOC)
     __shared__ float dot_s[8];
     __shared__ uint64_t bar;
@@ -349,12 +366,7 @@ attn_bwd_kernel(const AttnBwdParams p) {
             ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
         }
     }
-    float4 qv[NS];
-    {
-        const float* qb = p.q + (size_t)b * p.ldq + lane * 4;
-#pragma unroll
-        for (int i = 0; i < NS; i++) qv[i] = ldg4(qb + i * 128);
-    }
+    for (int i = tid; i < S; i += ATT_THREADS) q_s[i] = p.q[(size_t)b * p.ldq + i];
     pdl_wait();
     for (int i = tid; i < A; i += ATT_THREADS) dc_s[i] = __ldcg(p.dc + (size_t)b * p.ld_dc + i);
     const float pen_g = (p.pen && p.lambda != 0.f && p.pen[(size_t)b * p.ld_pen] > 0.f) ? p.lambda : 0.f;
@@ -365,23 +377,17 @@ attn_bwd_kernel(const AttnBwdParams p) {
     float dotp = 0.f;
 
     const float* vbase = p.Vh + ((size_t)b * p.Lmax + l0) * S + lane * 4;
-    // Vh rows stream through registers, one row ahead; h rows come from the TMA-staged tile
-    float4 vv[2][NS];
-    if (warp < nrows) {
-#pragma unroll
-        for (int i = 0; i < NS; i++) vv[0][i] = ldg_stream(vbase + (size_t)warp * S + i * 128);
-    }
-    __syncthreads();            // w_s / dc_s / uw_s / ap_s staged
+    // Vh rows stream through registers one at a time (three CTAs per SM hide the latency); h rows come from the
+    // TMA-staged tile
+    float4 vv[NS];
+    __syncthreads();            // w_s / dc_s / q_s / uw_s / ap_s staged
     mbar_wait(&bar, 0);         // h tile landed
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 4; j++) {
         const int r = warp + 8 * j;
         if (r >= nrows) break;
-        const int cur = j & 1, nxt = cur ^ 1;
-        if (j < 3 && r + 8 < nrows) {
 #pragma unroll
-            for (int i = 0; i < NS; i++) vv[nxt][i] = ldg_stream(vbase + (size_t)(r + 8) * S + i * 128);
-        }
+        for (int i = 0; i < NS; i++) vv[i] = ldg_stream(vbase + (size_t)r * S + i * 128);
         const int l = l0 + r;
         float da = 0.f;
 #pragma unroll
@@ -404,7 +410,7 @@ attn_bwd_kernel(const AttnBwdParams p) {
         }
 #pragma unroll
         for (int i = 0; i < NS; i++) {
-            float4 z = f4add(vv[cur][i], qv[i]);
+            float4 z = f4add(vv[i], *reinterpret_cast<const float4*>(q_s + lane * 4 + i * 128));
             if (LOC) {
                 for (int jj = 0; jj < p.KF; jj++) {
                     const float ap = ap_s[r + jj];
@@ -446,7 +452,7 @@ attn_bwd_kernel(const AttnBwdParams p) {
         }
     }
 
-    // ---- cross-warp reduction of P1 / P2 / dot (red aliases w_s / dc_s: wait until every warp is done) ----
+    // ---- cross-warp reduction of P1 / P2 / dot (red aliases the h tile: wait until every warp is done with it) ----
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NS; i++) {
@@ -641,17 +647,17 @@ int attn_scratch_alloc(s2s_ctx* ctx, Arena& arena, int B, int Lmax, int S, int A
     return 0;
 }
 
-template <int NS, int NA, bool LOC>
-static int launch_fwd(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
-    size_t smem = (size_t)ATT_R * NA * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
+template <int NS, int NA, bool LOC, int RIF>
+static int launch_fwd_rif(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
+    size_t smem = (size_t)ATT_R * NA * 128 * 4 + (size_t)NS * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
     static bool attr_set = false;   // per instantiation
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {
-        S2S_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NS, NA, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S2S_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NS, NA, LOC, RIF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true; attr_smem = smem;
     }
     prof_begin(ctx, S2S_PROF_ATTN_FWD);
-    S2S_CUDA(launch_kernel(attn_fwd_kernel<NS, NA, LOC>, dim3(p.nch, p.B), dim3(ATT_THREADS), smem, ctx->stream, ctx->pdl, p));
+    S2S_CUDA(launch_kernel(attn_fwd_kernel<NS, NA, LOC, RIF>, dim3(p.nch, p.B), dim3(ATT_THREADS), smem, ctx->stream, ctx->pdl, p));
     {   // algorithmic bytes A_f = 4 B (L S + L A + 2L + S + A)   
         const double S = NS * 128.0, A = NA * 128.0, L = p.Lmax;
         prof_end(ctx, S2S_PROF_ATTN_FWD, 4.0 * p.B * (L * S + L * A + 2 * L + S + A));
@@ -659,9 +665,17 @@ static int launch_fwd(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
+// Small grids (the L2-resident decoder step) are latency-bound: three light CTAs per SM.  Large grids are
+// bandwidth-bound: two CTAs per SM with all four rows of every warp in flight (measured 84-91% of HBM peak).
+template <int NS, int NA, bool LOC>
+static int launch_fwd(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
+    if ((long)p.nch * p.B >= 6L * ctx->sm_count) return launch_fwd_rif<NS, NA, LOC, 4>(ctx, p, KF);
+    return launch_fwd_rif<NS, NA, LOC, 2>(ctx, p, KF);
+}
 template <int NS, int NA, bool LOC>
 static int launch_bwd(s2s_ctx* ctx, const AttnBwdParams& p, int KF) {
-    size_t smem = (size_t)ATT_R * NA * 128 * 4 + (size_t)8 * 2 * NS * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
+    size_t hsz = (size_t)ATT_R * NA * 128 > (size_t)16 * NS * 128 ? (size_t)ATT_R * NA * 128 : (size_t)16 * NS * 128;
+    size_t smem = (hsz + (size_t)2 * NS * 128 + (size_t)NA * 128) * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
     static bool attr_set = false;
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {

@@ -81,7 +81,8 @@ struct s2s_ctx {
     int sm_count = 148;
     int64_t launches = 0;
     bool graphs = true;
-    bool pdl = true;           // programmatic dependent launch for the decoder's per-step kernel chain (S2S_PDL=0 disables)
+    bool pdl = false;          // programmatic dependent launch for the decoder's per-step kernel chain (S2S_PDL=1 enables;
+                               // measured neutral-to-negative under CUDA-graph replay, so off by default)
     s2s::Arena arena;          // per-call scratch (reset at the start of each top-level call)
     s2s::Arena persist;        // state that survives between forward and backward
     s2s::DecoderState* dec = nullptr;
