@@ -120,6 +120,18 @@ int s2s_gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H
                          const float* x, int ldx, const int* lengths, int B, int Lmax,
                          const float* y, const float* save, const float* dy, float* dx);
 
+/* ---- nn.RNN(nn.LSTM(in,out,peepholes), reverse) over whole utterances (LSTM.lua:6-136, RNN.lua:120-201) ---- */
+/* P: flat LSTM parameters in the order the module's parameters() yields: for gate in (i, f, g, o):
+ * Wx[out,in], bx[out], Wh[out,out], bh[out], and -- with peepholes, except for g -- Wc[out,out], bc[out]
+ * (full-matrix peepholes on prev_c for i,f and on next_c for o; LSTM.lua:25-50).  save: s2s_lstm_seq_save_floats floats. */
+int64_t s2s_lstm_param_count(int in, int out, int peepholes);
+int64_t s2s_lstm_seq_save_floats(int B, int Lmax, int H);
+int s2s_lstm_seq_forward(s2s_ctx* ctx, const float* P, int Din, int H, int peepholes, int reverse,
+                         const float* x, int ldx, const int* lengths, int B, int Lmax, float* y, float* save);
+int s2s_lstm_seq_backward(s2s_ctx* ctx, const float* P, float* dP, int Din, int H, int peepholes, int reverse,
+                          const float* x, int ldx, const int* lengths, int B, int Lmax,
+                          const float* y, const float* save, const float* dy, float* dx);
+
 /* ---- nn.Attention (Attention.lua:305-327) = Vh + nn.RNNAttention(nn.Recurrent(decoder_base_)) */
 /* updateOutput: teacher-forced decoder over Tmax steps (RNNAttention.lua:144-185).
  * P = flat parameter vector of the WHOLE model (decoder segments located through cfg).

@@ -69,6 +69,10 @@ def load():
         "s2s_gru_seq_save_floats": (i64, [i32, i32, i32, i32]),
         "s2s_gru_seq_forward": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp]),
         "s2s_gru_seq_backward": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
+        "s2s_lstm_param_count": (i64, [i32, i32, i32]),
+        "s2s_lstm_seq_save_floats": (i64, [i32, i32, i32]),
+        "s2s_lstm_seq_forward": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp]),
+        "s2s_lstm_seq_backward": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
         "s2s_attention_forward": (i32, [vp, cfgp, vp, vp, vp, i32, i32, vp, vp, i32, vp, f32, vp]),
         "s2s_attention_backward": (i32, [vp, cfgp, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, f32, vp, vp]),
         "s2s_attention_get": (i32, [vp, i32, vp]),

@@ -753,3 +753,12 @@ int beam_search_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const float*
 }
 
 }  // namespace s2s
+
+namespace s2s {
+// plain linear use of the small-batch product kernel by other translation units (lstm_seq.cu)
+int dense_small_linear(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, const float* W, int ldw, int N, const float* bias,
+                       const float* add, int64_t ld_add, float* out, int64_t ld_out) {
+    DenseEpi e; e.bias = bias; e.add = add; e.ld_add = ld_add; e.out = out; e.ld_out = ld_out;
+    return dense_small(ctx, X, ldx, B, K, W, ldw, N, e);
+}
+}  // namespace s2s

@@ -116,6 +116,28 @@ class GRU(Module):
         return [self.weight[i] for i in range(3)], [self.gradWeight[i] for i in range(3)]
 
 
+class LSTM(Module):
+    """Parameter holder in the reference's order (LSTM.lua:25-60): per gate Linear(in,out)+Linear(out,out), both with
+    bias, plus full-matrix peepholes when requested."""
+
+    def __init__(self, ctx, diminput, dimoutput, peepholes=False):
+        super().__init__(ctx)
+        assert diminput is not None, "diminput must be specified"
+        assert dimoutput is not None, "dimoutput must be specified"
+        self.diminput, self.dimoutput, self.peepholes = diminput, dimoutput, bool(peepholes)
+        n = ops.lstm_param_count(diminput, dimoutput, self.peepholes)
+        self.weight = ctx.new(n)
+        self.gradWeight = ctx.zeros(n)
+        self.reset()
+
+    def reset(self, stdv=None):
+        stdv = stdv or 1.0 / math.sqrt(self.dimoutput)
+        self.weight.uniform_(-stdv, stdv)
+
+    def parameters(self):
+        return [self.weight], [self.gradWeight]
+
+
 class RNN(Module):
     def __init__(self, ctx, recurrent, reverse=False):
         super().__init__(ctx)
@@ -131,7 +153,11 @@ class RNN(Module):
         if input.dim() not in (2, 3):
             raise ops.S2SError("input must be 2d or 3d")
         x = input.contiguous().view(-1, input.shape[-2], input.shape[-1]) if input.dim() == 2 else input.contiguous()
-        y, self._save = ops.gru_seq_forward(self.ctx, self.recurrent.weight, x, lengths=lengths, ndir=1, reverse=self.reverse)
+        if isinstance(self.recurrent, LSTM):
+            y, self._save = ops.lstm_seq_forward(self.ctx, self.recurrent.weight, x, self.dimoutput, peepholes=self.recurrent.peepholes,
+                                                 lengths=lengths, reverse=self.reverse)
+        else:
+            y, self._save = ops.gru_seq_forward(self.ctx, self.recurrent.weight, x, lengths=lengths, ndir=1, reverse=self.reverse)
         self._y, self._lengths = y, lengths
         self.output = y[0] if input.dim() == 2 else y
         return self.output
@@ -140,8 +166,13 @@ class RNN(Module):
         assert getattr(self, "_save", None) is not None, "backward called before forward"
         x = input.contiguous().view(-1, input.shape[-2], input.shape[-1])
         dy = gradOutput.contiguous().view(x.shape[0], x.shape[1], -1)
-        dx, _ = ops.gru_seq_backward(self.ctx, self.recurrent.weight, x, self._y, self._save, dy, lengths=self._lengths, ndir=1,
-                                     reverse=self.reverse, dW=self.recurrent.gradWeight)
+        if isinstance(self.recurrent, LSTM):
+            dx, _ = ops.lstm_seq_backward(self.ctx, self.recurrent.weight, x, self._y, self._save, dy, self.dimoutput,
+                                          peepholes=self.recurrent.peepholes, lengths=self._lengths, reverse=self.reverse,
+                                          dP=self.recurrent.gradWeight)
+        else:
+            dx, _ = ops.gru_seq_backward(self.ctx, self.recurrent.weight, x, self._y, self._save, dy, lengths=self._lengths, ndir=1,
+                                         reverse=self.reverse, dW=self.recurrent.gradWeight)
         self.gradInput = dx[0] if input.dim() == 2 else dx
         return self.gradInput
 

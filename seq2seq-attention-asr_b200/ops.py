@@ -157,6 +157,30 @@ def gru_seq_backward(ctx, W, x, y, save, dy, lengths=None, ndir=1, reverse=False
     return dx, dW
 
 
+# ---- LSTM sequence --------------------------------------------------------------------------------------
+def lstm_param_count(din, H, peepholes):
+    return int(_lib.load().s2s_lstm_param_count(din, H, int(peepholes)))
+
+
+def lstm_seq_forward(ctx, P, x, H, peepholes=False, lengths=None, reverse=False):
+    B, L, Din = x.shape
+    assert P.numel() == lstm_param_count(Din, H, peepholes)
+    y = ctx.new(B, L, H)
+    save = ctx.new(int(ctx.lib.s2s_lstm_seq_save_floats(B, L, H)))
+    check(ctx.lib.s2s_lstm_seq_forward(ctx.h, _f(P), Din, H, int(peepholes), int(reverse), _f(x), Din, _i(lengths), B, L, _f(y), _f(save)))
+    return y, save
+
+
+def lstm_seq_backward(ctx, P, x, y, save, dy, H, peepholes=False, lengths=None, reverse=False, dP=None):
+    B, L, Din = x.shape
+    if dP is None:
+        dP = torch.zeros_like(P)
+    dx = ctx.new(B, L, Din)
+    check(ctx.lib.s2s_lstm_seq_backward(ctx.h, _f(P), _f(dP), Din, H, int(peepholes), int(reverse), _f(x), Din, _i(lengths), B, L,
+                                        _f(y), _f(save), _f(dy), _f(dx)))
+    return dx, dP
+
+
 # ---- attention decoder ---------------------------------------------------------------------------------
 def attention_forward(ctx, cfg, P, h, labels, lengths=None, tlens=None, dropmask=None, lam=0.0):
     B, L, A = h.shape

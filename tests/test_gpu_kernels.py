@@ -109,3 +109,31 @@ def test_tconv_zb_known_answer_cell(s2s, gctx):
     dx = s2s.tconv_zb_backward(gctx, dev(np.ones((10, 5), np.float32)), W, dy, dW=dW)
     assert np.allclose(dx.cpu().numpy(), np.tile(np.arange(1, 21).reshape(4, 5).sum(0), (10, 1)))
     assert np.allclose(dW.cpu().numpy(), 10.0)
+
+
+@pytest.mark.parametrize("H,Din,B,L,peep,reverse", [(128, 20, 4, 23, False, False), (128, 20, 4, 23, True, False), (64, 36, 5, 17, True, True),
+                                                    (256, 123, 3, 12, False, True)])
+def test_lstm_seq_matches_oracle(s2s, gctx, orc64, H, Din, B, L, peep, reverse):
+    # nn.RNN(nn.LSTM(in, out, peepholes), reverse): LSTM.lua:6-136 (two biases per gate, full-matrix peepholes)
+    rng = np.random.default_rng(H + Din + B + int(peep))
+    n = orc64.lstm_param_count(Din, H, peep)
+    assert s2s.lstm_param_count(Din, H, peep) == n
+    P = rng.uniform(-1, 1, n) / np.sqrt(H) * 1.2
+    x = rng.standard_normal((B, L, Din))
+    lengths = rng.integers(max(1, L // 2), L + 1, B).astype(np.int32); lengths[0] = L
+    dy = rng.standard_normal((B, L, H))
+    for b in range(B):
+        x[b, lengths[b]:] = 0; dy[b, lengths[b]:] = 0
+    y_ref = np.zeros((B, L, H)); dx_ref = np.zeros_like(x); dP_ref = np.zeros_like(P)
+    for b in range(B):
+        Lb = lengths[b]
+        yb, cb, ab = orc64.lstm_seq_forward(P, Din, H, peep, x[b, :Lb], reverse=reverse)
+        y_ref[b, :Lb] = yb
+        dxb, dPb = orc64.lstm_seq_backward(P, Din, H, peep, x[b, :Lb], yb, cb, ab, dy[b, :Lb], reverse=reverse)
+        dx_ref[b, :Lb] = dxb; dP_ref += dPb
+    Pd, xd, ld = dev(P, torch.float32), dev(x, torch.float32), dev(lengths)
+    y, save = s2s.lstm_seq_forward(gctx, Pd, xd, H, peepholes=peep, lengths=ld, reverse=reverse)
+    assert rel_err(y.cpu().numpy(), y_ref) < TOL
+    dx, dP = s2s.lstm_seq_backward(gctx, Pd, xd, y, save, dev(dy, torch.float32), H, peepholes=peep, lengths=ld, reverse=reverse)
+    assert rel_err(dx.cpu().numpy(), dx_ref) < TOL
+    assert rel_err(dP.cpu().numpy(), dP_ref) < TOL
