@@ -74,22 +74,41 @@ struct GruSeqParams {
     int dbg;               // timing experiments only (S2S_GRU_DBG): 1 = skip the DSMEM exchange, 2 = skip the mat-vec loops
 };
 
-// Broadcast this CTA's [BG][32] slice (staged in local shared memory) into columns
-// [32*crank, 32*crank+32) of buffer `buf_a` ([BG][H]) of EVERY CTA of the cluster: warp w sends to rank w,
-// lane -> 16-byte chunks (utterance, 4 units).  At most two 16-byte st.async per thread.
-template <int H, int BG>
-__device__ __forceinline__ void bcast_slice(const float (*stage)[32], uint32_t buf_a, uint32_t bar_a, unsigned crank, int warp, int lane) {
-    constexpr int CS = H / 32;
-    if (warp < CS) {
-        const uint32_t rbar = mapa_rank(bar_a, warp);
+// Geometry of one cluster.  UC hidden units per CTA (cluster of H/UC CTAs), BG utterances per cluster.
+//   UC = 32: clusters of 8 (portable), butterflies of 8 rows x 4 utterances -> groups of 4 utterances are optimal
+//   UC = 16: clusters of 16 (non-portable), butterflies of 4 rows x 8 utterances -> 8 utterances in one pass;
+//            used when the UC = 32 layout would need more clusters than fit in one wave (B = 32: 16 > 15).
+template <int H, int UC, int BG>
+struct Geo {
+    static constexpr int CS = H / UC;            // CTAs per cluster
+    static constexpr int R1 = UC / 4;            // phase-1 rows per warp (2 UC rows over 8 warps)
+    static constexpr int R2 = UC / 8;            // phase-2 rows per warp
+    static constexpr int NBP = 32 / R1;          // utterances per butterfly pass (4 or 8)
+    static constexpr int NH = (BG + NBP - 1) / NBP;          // passes
+    static constexpr int NB0 = BG < NBP ? BG : NBP;          // utterances in pass 0
+    static constexpr int NB1 = BG > NBP ? BG - NBP : 1;      // utterances in pass 1 (if any)
+    static constexpr int NI = H / 128;
+    static constexpr unsigned TX = BG * H * 4;   // bytes every CTA receives per exchange
+};
+
+// Broadcast this CTA's [BG][UC] slice (staged in local shared memory) into columns [UC*crank, UC*crank+UC) of
+// buffer `buf_a` ([BG][H]) of EVERY CTA of the cluster with 16-byte st.async stores that signal the receiver's
+// mbarrier: warp w serves ranks w, w+8, ...; lane -> 16-byte chunks (utterance, 4 units).
+template <int H, int UC, int BG>
+__device__ __forceinline__ void bcast_slice(const float (*stage)[UC], uint32_t buf_a, uint32_t bar_a, unsigned crank, int warp, int lane) {
+    constexpr int CS = H / UC, CPB = UC / 4;
 #pragma unroll
-        for (int ch = lane; ch < BG * 8; ch += 32) {
-            const int b = ch >> 3, off = (ch & 7) * 4;
+    for (int d = warp; d < CS; d += 8) {
+        const uint32_t rbar = mapa_rank(bar_a, d);
+#pragma unroll
+        for (int ch = lane; ch < BG * CPB; ch += 32) {
+            const int b = ch / CPB, off = (ch % CPB) * 4;
             const float4 v = *reinterpret_cast<const float4*>(&stage[b][off]);
-            st_async_v4(mapa_rank(buf_a + (uint32_t)(b * H + crank * 32 + off) * 4u, warp), v, rbar);
+            st_async_v4(mapa_rank(buf_a + (uint32_t)(b * H + crank * UC + off) * 4u, d), v, rbar);
         }
     }
 }
+
 // Transposed butterfly reduction: every lane holds NV partial sums (NV a power of two <= 32); afterwards
 // lane l holds the complete sum number (l mod NV).  NV - 1 + log2(32/NV) shuffles instead of 5 NV.
 template <int NV>
@@ -113,17 +132,17 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float c)
 }
 
 // Mat-vec mapping shared by forward and backward.  Lanes split K (lane owns k = 4 lane + 128 i), warps own
-// rows: phase 1 = 64 rows (ROWS = 8 per warp), phase 2 = 32 rows (ROWS = 4 per warp).  The K-slice of the
-// state vector is loaded ONCE per thread and phase (NI LDS.128 per utterance) and reused for all of the
-// warp's rows, so the per-step shared-memory traffic is BG*H*4 bytes per WARP instead of per row; the partial
-// sums of a warp are reduced with the transposed butterfly, which also hands each (row, utterance) result to
-// its own lane: the value for (row l/4 [ROWS = 8] or (l%16)/4 [ROWS = 4], utterance b_lo + l%4) ends in lane l.
-// Groups of more than 4 utterances are processed as two halves; NB = utterances in this half (1..4).
-template <int H, int ROWS, int NB>
+// rows: phase 1 = 2 UC rows (ROWS = R1 per warp), phase 2 = UC rows (ROWS = R2 per warp).  The K-slice of the
+// state vector is loaded ONCE per thread and phase (NI LDS.128 per utterance) and reused for all of the warp's
+// rows, so the per-step shared-memory traffic is BG*H*4 bytes per WARP instead of per row; the partial sums of a
+// warp are reduced with the transposed butterfly, which also hands each (row, utterance) result to its own lane:
+// with G = ROWS * NBP (32 in phase 1, 16 in phase 2), lane l ends with (row (l % G) / NBP, utterance b_lo + l % NBP).
+// NB = utterances present in this pass (<= NBP).
+template <int H, int ROWS, int NB, int NBP>
 __device__ __forceinline__ float matvec(const float4 (&w)[ROWS][H / 128], const float (*src)[H], int b_lo, int lane) {
     constexpr int NI = H / 128;
-    constexpr int NBP = NB == 1 ? 1 : (NB == 2 ? 2 : 4);
-    constexpr int NV = ROWS * NBP;
+    constexpr int NBX = NB == 1 ? 1 : (NB == 2 ? 2 : (NB <= 4 ? 4 : 8));    // padded to a power of two
+    constexpr int NV = ROWS * NBX;
     float4 x[NB][NI];
 #pragma unroll
     for (int bb = 0; bb < NB; bb++)
@@ -133,37 +152,108 @@ __device__ __forceinline__ float matvec(const float4 (&w)[ROWS][H / 128], const 
 #pragma unroll
     for (int r = 0; r < ROWS; r++)
 #pragma unroll
-        for (int bb = 0; bb < NBP; bb++) {
+        for (int bb = 0; bb < NBX; bb++) {
             float a = 0.f;
             if (bb < NB) {
 #pragma unroll
                 for (int i = 0; i < NI; i++) a = dot4(w[r][i], x[bb][i], a);
             }
-            acc[r * NBP + bb] = a;
+            acc[r * NBX + bb] = a;
         }
     float tot = bfly<NV>(acc, lane);
-    if (NBP < 4) {   // hand (row, utterance) to the lane layout used by the callers
-        const int row = ROWS == 8 ? (lane >> 2) : ((lane & 15) >> 2);
-        tot = __shfl_sync(0xffffffffu, tot, (row * NBP + (lane & 3)) & 31);
+    if (NBX < NBP) {   // hand (row, utterance) to the canonical lane layout
+        const int idx = lane % (ROWS * NBP);
+        tot = __shfl_sync(0xffffffffu, tot, ((idx / NBP) * NBX + (idx % NBP)) & 31);
     }
     return tot;
+}
+
+// Two passes (groups of more than NBP utterances) as ONE instruction stream: both K-slices are loaded, both sets of
+// partial sums are formed, and the two butterflies advance stage by stage together, so their shuffle latencies overlap
+// instead of adding up (with two warps per scheduler the passes are latency-bound, not throughput-bound).
+template <int H, int ROWS, int NB0, int NB1, int NBP>
+__device__ __forceinline__ void matvec_pair(const float4 (&w)[ROWS][H / 128], const float (*src)[H], int lane, float& tot0, float& tot1) {
+    constexpr int NI = H / 128;
+    constexpr int NX0 = NB0 == 1 ? 1 : (NB0 == 2 ? 2 : (NB0 <= 4 ? 4 : 8));
+    constexpr int NX1 = NB1 == 1 ? 1 : (NB1 == 2 ? 2 : (NB1 <= 4 ? 4 : 8));
+    constexpr int NV0 = ROWS * NX0, NV1 = ROWS * NX1;
+    float4 x0[NB0][NI], x1[NB1][NI];
+#pragma unroll
+    for (int bb = 0; bb < NB0; bb++)
+#pragma unroll
+        for (int i = 0; i < NI; i++) x0[bb][i] = *reinterpret_cast<const float4*>(&src[bb][lane * 4 + 128 * i]);
+#pragma unroll
+    for (int bb = 0; bb < NB1; bb++)
+#pragma unroll
+        for (int i = 0; i < NI; i++) x1[bb][i] = *reinterpret_cast<const float4*>(&src[NBP + bb][lane * 4 + 128 * i]);
+    float a0[NV0], a1[NV1];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+#pragma unroll
+        for (int bb = 0; bb < NX0; bb++) {
+            float a = 0.f;
+            if (bb < NB0) {
+#pragma unroll
+                for (int i = 0; i < NI; i++) a = dot4(w[r][i], x0[bb][i], a);
+            }
+            a0[r * NX0 + bb] = a;
+        }
+#pragma unroll
+        for (int bb = 0; bb < NX1; bb++) {
+            float a = 0.f;
+            if (bb < NB1) {
+#pragma unroll
+                for (int i = 0; i < NI; i++) a = dot4(w[r][i], x1[bb][i], a);
+            }
+            a1[r * NX1 + bb] = a;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        if (s < NV0) {
+#pragma unroll
+            for (int i = 0; i < s; i++) {
+                if (i + s < NV0) {
+                    const float send = (lane & s) ? a0[i] : a0[i + s];
+                    const float keep = (lane & s) ? a0[i + s] : a0[i];
+                    a0[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+            }
+        }
+        if (s < NV1) {
+#pragma unroll
+            for (int i = 0; i < s; i++) {
+                if (i + s < NV1) {
+                    const float send = (lane & s) ? a1[i] : a1[i + s];
+                    const float keep = (lane & s) ? a1[i + s] : a1[i];
+                    a1[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+            }
+        }
+    }
+    float r0 = a0[0], r1 = a1[0];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        if (o >= NV0) r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        if (o >= NV1) r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+    }
+    if (NX0 < NBP) { const int idx = lane % (ROWS * NBP); r0 = __shfl_sync(0xffffffffu, r0, ((idx / NBP) * NX0 + (idx % NBP)) & 31); }
+    if (NX1 < NBP) { const int idx = lane % (ROWS * NBP); r1 = __shfl_sync(0xffffffffu, r1, ((idx / NBP) * NX1 + (idx % NBP)) & 31); }
+    tot0 = r0; tot1 = r1;
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int H, int BG>
+template <int H, int UC, int BG>
 __global__ void __launch_bounds__(256, 1)
 gru_seq_fwd_kernel(const GruSeqParams p) {
-    constexpr int NI = H / 128;
-    constexpr int NH = (BG + 3) / 4;          // halves of up to 4 utterances
-    constexpr int NB2 = BG - 4 > 0 ? BG - 4 : 1;   // utterances in the second half
-    constexpr unsigned TX = BG * H * 4;       // bytes every CTA receives per exchange
-    constexpr int CS = H / 32;
+    using G = Geo<H, UC, BG>;
+    constexpr int CS = G::CS, R1 = G::R1, R2 = G::R2, NBP = G::NBP, NH = G::NH, NI = G::NI;
     __shared__ __align__(16) float hbuf[BG][H];
     __shared__ __align__(16) float rhbuf[BG][H];
-    __shared__ __align__(16) float stage[BG][32];
-    __shared__ float zbuf[BG][32];
+    __shared__ __align__(16) float stage[BG][UC];
+    __shared__ float zbuf[BG][UC];
     __shared__ uint64_t barA, barB;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -177,18 +267,18 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
 
     // ---- recurrent weights -> registers (coalesced: lane owns k = 4 lane + 128 i) -------------------
     const int g1 = warp >> 2;                      // phase-1 gate of this warp's rows: 0 = z, 1 = r
-    float4 w1[8][NI], w2[4][NI];
+    float4 w1[R1][NI], w2[R2][NI];
     {
         const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw;
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const float* row = Wd + ((size_t)g1 * H + crank * 32 + 8 * (warp & 3) + r) * p.ldw;
+        for (int r = 0; r < R1; r++) {
+            const float* row = Wd + ((size_t)g1 * H + crank * UC + R1 * (warp & 3) + r) * p.ldw;
 #pragma unroll
             for (int i = 0; i < NI; i++) { const float* s = row + lane * 4 + 128 * i; w1[r][i] = make_float4(s[0], s[1], s[2], s[3]); }
         }
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const float* row = Wd + ((size_t)2 * H + crank * 32 + 4 * warp + r) * p.ldw;
+        for (int r = 0; r < R2; r++) {
+            const float* row = Wd + ((size_t)2 * H + crank * UC + R2 * warp + r) * p.ldw;
 #pragma unroll
             for (int i = 0; i < NI; i++) { const float* s = row + lane * 4 + 128 * i; w2[r][i] = make_float4(s[0], s[1], s[2], s[3]); }
         }
@@ -196,14 +286,15 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
     for (int i = tid; i < BG * H; i += 256) { (&hbuf[0][0])[i] = 0.f; (&rhbuf[0][0])[i] = 0.f; }   // Recurrent.lua:13,112
     if (tid == 0) { mbar_init(&barA, 1); mbar_init(&barB, 1); fence_mbar_init(); }
 
-    // finalizer roles (see matvec8 / matvec4)
-    const int ju1 = 8 * (warp & 3) + (lane >> 2);          // phase-1 unit within this CTA's slice
-    const int ju2 = 4 * warp + ((lane & 15) >> 2);         // phase-2 unit (lanes < 16)
-    const int j1 = crank * 32 + ju1, j2 = crank * 32 + ju2;
-    int Lf[NH];                                            // length of the utterance this lane finalises, per half
+    // finalizer roles (see matvec)
+    const int bbl = lane % NBP;                                 // utterance within a pass
+    const int ju1 = R1 * (warp & 3) + lane / NBP;               // phase-1 unit within this CTA's slice
+    const int ju2 = R2 * warp + (lane & 15) / NBP;              // phase-2 unit (lanes < 16)
+    const int j1 = crank * UC + ju1, j2 = crank * UC + ju2;
+    int Lf[NH];                                                 // length of the utterance this lane finalises, per pass
 #pragma unroll
     for (int hf = 0; hf < NH; hf++) {
-        const int bl = 4 * hf + (lane & 3), b = b0 + bl;
+        const int bl = NBP * hf + bbl, b = b0 + bl;
         Lf[hf] = (bl < BG && b < p.B) ? (p.lengths ? p.lengths[b] : p.Lmax) : 0;
     }
     int Lgrp = 0;
@@ -219,7 +310,7 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
     auto load_xp = [&](int s, int hf, int gate, int j) -> float {
         if (s >= Lf[hf]) return 0.f;
         const int t = rev ? Lf[hf] - 1 - s : s;
-        return __ldg(p.xp + ((size_t)(b0 + 4 * hf + (lane & 3)) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + gate * H + j);
+        return __ldg(p.xp + ((size_t)(b0 + NBP * hf + bbl) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + gate * H + j);
     };
     float xp1n[NH], xp2n[NH];
 #pragma unroll
@@ -233,21 +324,22 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
             xp1n[hf] = load_xp(s + 1, hf, g1, j1);
             xp2n[hf] = lane < 16 ? load_xp(s + 1, hf, 2, j2) : 0.f;
         }
-        if (tid == 0 && !(p.dbg & 1)) { mbar_expect_tx(&barA, TX); mbar_expect_tx(&barB, TX); }
+        if (tid == 0 && !(p.dbg & 1)) { mbar_expect_tx(&barA, G::TX); mbar_expect_tx(&barB, G::TX); }
 
         // ---- phase 1: z, r ------------------------------------------------------------------
         float tot1[NH];
 #pragma unroll
-        for (int hf = 0; hf < NH; hf++) {
-            tot1[hf] = 0.f;
-            if (!(p.dbg & 2)) tot1[hf] = hf == 0 ? matvec<H, 8, (BG < 4 ? BG : 4)>(w1, hbuf, 0, lane) : matvec<H, 8, NB2>(w1, hbuf, 4, lane);
+        for (int hf = 0; hf < NH; hf++) tot1[hf] = 0.f;
+        if (!(p.dbg & 2)) {
+            if (NH == 1) tot1[0] = matvec<H, R1, G::NB0, NBP>(w1, hbuf, 0, lane);
+            else matvec_pair<H, R1, G::NB0, G::NB1, NBP>(w1, hbuf, lane, tot1[0], tot1[NH - 1]);
         }
         float g1v[NH];
 #pragma unroll
-        for (int hf = 0; hf < NH; hf++) g1v[hf] = sigmoid_acc(tot1[hf] + xp1[hf]);    // GRU.lua:23-24 (both halves in flight)
+        for (int hf = 0; hf < NH; hf++) g1v[hf] = sigmoid_acc(tot1[hf] + xp1[hf]);    // GRU.lua:23-24 (both passes in flight)
 #pragma unroll
         for (int hf = 0; hf < NH; hf++) {
-            const int bl = 4 * hf + (lane & 3);
+            const int bl = NBP * hf + bbl;
             if (bl < BG) {
                 const bool act = s < Lf[hf];
                 const int t = rev ? Lf[hf] - 1 - s : s;
@@ -265,23 +357,24 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
         }
         __syncthreads();
         if (!(p.dbg & 1)) {
-            bcast_slice<H, BG>(stage, rhbuf_a, barA_a, crank, warp, lane);
+            bcast_slice<H, UC, BG>(stage, rhbuf_a, barA_a, crank, warp, lane);
             mbar_wait(&barA, parity);
         }
 
         // ---- phase 2: h~, h' ------------------------------------------------------------------
         float tot2[NH];
 #pragma unroll
-        for (int hf = 0; hf < NH; hf++) {
-            tot2[hf] = 0.f;
-            if (!(p.dbg & 2)) tot2[hf] = hf == 0 ? matvec<H, 4, (BG < 4 ? BG : 4)>(w2, rhbuf, 0, lane) : matvec<H, 4, NB2>(w2, rhbuf, 4, lane);
+        for (int hf = 0; hf < NH; hf++) tot2[hf] = 0.f;
+        if (!(p.dbg & 2)) {
+            if (NH == 1) tot2[0] = matvec<H, R2, G::NB0, NBP>(w2, rhbuf, 0, lane);
+            else matvec_pair<H, R2, G::NB0, G::NB1, NBP>(w2, rhbuf, lane, tot2[0], tot2[NH - 1]);
         }
         float hcv[NH];
 #pragma unroll
-        for (int hf = 0; hf < NH; hf++) hcv[hf] = tanh_acc(tot2[hf] + xp2[hf]);       // GRU.lua:26 (both halves in flight)
+        for (int hf = 0; hf < NH; hf++) hcv[hf] = tanh_acc(tot2[hf] + xp2[hf]);       // GRU.lua:26 (both passes in flight)
 #pragma unroll
         for (int hf = 0; hf < NH; hf++) {
-            const int bl = 4 * hf + (lane & 3);
+            const int bl = NBP * hf + bbl;
             if (lane < 16 && bl < BG) {
                 const bool act = s < Lf[hf];
                 const int t = rev ? Lf[hf] - 1 - s : s;
@@ -300,7 +393,7 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
         }
         __syncthreads();
         if (!(p.dbg & 1)) {
-            bcast_slice<H, BG>(stage, hbuf_a, barB_a, crank, warp, lane);
+            bcast_slice<H, UC, BG>(stage, hbuf_a, barB_a, crank, warp, lane);
             mbar_wait(&barB, parity);
         }
         parity ^= 1;
@@ -311,20 +404,17 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-template <int H, int BG>
+template <int H, int UC, int BG>
 __global__ void __launch_bounds__(256, 1)
 gru_seq_bwd_kernel(const GruSeqParams p) {
-    constexpr int CS = H / 32;
-    constexpr int NI = H / 128;
-    constexpr int NH = (BG + 3) / 4;
-    constexpr int NB2 = BG - 4 > 0 ? BG - 4 : 1;
-    constexpr unsigned TX = BG * H * 4;
+    using G = Geo<H, UC, BG>;
+    constexpr int CS = G::CS, R1 = G::R1, R2 = G::R2, NBP = G::NBP, NH = G::NH, NI = G::NI;
     __shared__ __align__(16) float ahbuf[BG][H];   // dah (all units)
     __shared__ __align__(16) float azbuf[BG][H];   // daz
     __shared__ __align__(16) float arbuf[BG][H];   // dar
-    __shared__ __align__(16) float stage_h[BG][32], stage_z[BG][32], stage_r[BG][32];
-    __shared__ float stash_r[BG][32], stash_hp[BG][32];
-    __shared__ float part1[BG][32], part2[BG][32];
+    __shared__ __align__(16) float stage_h[BG][UC], stage_z[BG][UC], stage_r[BG][UC];
+    __shared__ float stash_r[BG][UC], stash_hp[BG][UC];
+    __shared__ float part1[BG][UC], part2[BG][UC];
     __shared__ uint64_t barA, barB;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -336,24 +426,24 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
     const int b0 = grp * BG;
     const int H3 = 3 * H;
 
-    // transposed recurrent weights -> registers.  phase 1 rows (8 per warp): warps 0-3 -> W_h^T (applied to
-    // dah), warps 4-7 -> W_z^T (applied to daz); phase 2 rows (4 per warp): W_r^T (applied to dar).  Row =
+    // transposed recurrent weights -> registers.  phase 1 rows (R1 per warp): warps 0-3 -> W_h^T (applied to
+    // dah), warps 4-7 -> W_z^T (applied to daz); phase 2 rows (R2 per warp): W_r^T (applied to dar).  Row =
     // input unit owned by this CTA, reduction over the output units j = 4 lane + 128 i + e.
     const int g1 = warp >> 2;
-    float4 w1[8][NI], w2[4][NI];
+    float4 w1[R1][NI], w2[R2][NI];
     {
         const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw;
-        const float* Wg = Wd + (size_t)(g1 == 0 ? 2 : 0) * H * p.ldw + crank * 32 + 8 * (warp & 3);
+        const float* Wg = Wd + (size_t)(g1 == 0 ? 2 : 0) * H * p.ldw + crank * UC + R1 * (warp & 3);
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int r = 0; r < R1; r++)
 #pragma unroll
             for (int i = 0; i < NI; i++) {
                 const size_t j = lane * 4 + 128 * i;
                 w1[r][i] = make_float4(Wg[j * p.ldw + r], Wg[(j + 1) * p.ldw + r], Wg[(j + 2) * p.ldw + r], Wg[(j + 3) * p.ldw + r]);
             }
-        const float* Wr = Wd + (size_t)H * p.ldw + crank * 32 + 4 * warp;
+        const float* Wr = Wd + (size_t)H * p.ldw + crank * UC + R2 * warp;
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int r = 0; r < R2; r++)
 #pragma unroll
             for (int i = 0; i < NI; i++) {
                 const size_t j = lane * 4 + 128 * i;
@@ -363,15 +453,16 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
     for (int i = tid; i < BG * H; i += 256) { (&ahbuf[0][0])[i] = 0.f; (&azbuf[0][0])[i] = 0.f; (&arbuf[0][0])[i] = 0.f; }
     if (tid == 0) { mbar_init(&barA, 1); mbar_init(&barB, 1); fence_mbar_init(); }
 
-    // roles: owner (elementwise part + carry) = phase-2 finaliser: lanes < 16 -> (unit ju2, utterance lane%4) per half
-    const int ju1 = 8 * (warp & 3) + (lane >> 2);
-    const int ju2 = 4 * warp + ((lane & 15) >> 2);
-    const int j1 = crank * 32 + ju1, j2 = crank * 32 + ju2;
+    // roles: owner (elementwise part + carry) = phase-2 finaliser: lanes < 16 -> (unit ju2, utterance lane % NBP) per pass
+    const int bbl = lane % NBP;
+    const int ju1 = R1 * (warp & 3) + lane / NBP;
+    const int ju2 = R2 * warp + (lane & 15) / NBP;
+    const int j1 = crank * UC + ju1, j2 = crank * UC + ju2;
     const bool owner_lane = lane < 16;
     int Lf[NH];
 #pragma unroll
     for (int hf = 0; hf < NH; hf++) {
-        const int bl = 4 * hf + (lane & 3), b = b0 + bl;
+        const int bl = NBP * hf + bbl, b = b0 + bl;
         Lf[hf] = (bl < BG && b < p.B) ? (p.lengths ? p.lengths[b] : p.Lmax) : 0;
     }
     int Lgrp = 0;
@@ -392,7 +483,7 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
         Pre q = {0.f, 0.f, 0.f, 0.f, 0.f};
         if (!owner_lane || s < 0 || s >= Lf[hf]) return q;
         const int t = rev ? Lf[hf] - 1 - s : s;
-        const int b = b0 + 4 * hf + (lane & 3);
+        const int b = b0 + NBP * hf + bbl;
         const size_t row = (size_t)b * p.Lmax + t;
         const float* sv = p.save + (row * p.ndir + dir) * 4 * H;
         q.z = __ldg(sv + j2); q.r = __ldg(sv + H + j2); q.hc = __ldg(sv + 2 * H + j2);
@@ -409,14 +500,14 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
     unsigned parity = 0;
     for (int s = Lgrp - 1; s >= 0; s--) {                                           // RNN.lua:183
         float dhp_part[NH];
-        if (tid == 0 && !(p.dbg & 1)) { mbar_expect_tx(&barA, 2 * TX); mbar_expect_tx(&barB, TX); }
+        if (tid == 0 && !(p.dbg & 1)) { mbar_expect_tx(&barA, 2 * G::TX); mbar_expect_tx(&barB, G::TX); }
         // ---- elementwise part (owners) ---------------------------------------------------------
 #pragma unroll
         for (int hf = 0; hf < NH; hf++) {
             const Pre cur = nxt[hf];
             nxt[hf] = load_pre(s - 1, hf);
             dhp_part[hf] = 0.f;
-            const int bl = 4 * hf + (lane & 3);
+            const int bl = NBP * hf + bbl;
             if (owner_lane && bl < BG) {
                 float dah = 0.f, daz = 0.f;
                 if (s < Lf[hf]) {
@@ -437,8 +528,8 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
         }
         __syncthreads();
         if (!(p.dbg & 1)) {
-            bcast_slice<H, BG>(stage_h, ah_a, barA_a, crank, warp, lane);
-            bcast_slice<H, BG>(stage_z, az_a, barA_a, crank, warp, lane);
+            bcast_slice<H, UC, BG>(stage_h, ah_a, barA_a, crank, warp, lane);
+            bcast_slice<H, UC, BG>(stage_z, az_a, barA_a, crank, warp, lane);
             mbar_wait(&barA, parity);
         }
 
@@ -446,14 +537,15 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
         const float (*src1)[H] = g1 == 0 ? ahbuf : azbuf;
         float tot1[NH];
 #pragma unroll
-        for (int hf = 0; hf < NH; hf++) {
-            tot1[hf] = 0.f;
-            if (!(p.dbg & 2)) tot1[hf] = hf == 0 ? matvec<H, 8, (BG < 4 ? BG : 4)>(w1, src1, 0, lane) : matvec<H, 8, NB2>(w1, src1, 4, lane);
+        for (int hf = 0; hf < NH; hf++) tot1[hf] = 0.f;
+        if (!(p.dbg & 2)) {   // (the paired variant measured slower here: register pressure)
+            tot1[0] = matvec<H, R1, G::NB0, NBP>(w1, src1, 0, lane);
+            if (NH > 1) tot1[NH - 1] = matvec<H, R1, G::NB1, NBP>(w1, src1, NBP, lane);
         }
 #pragma unroll
         for (int hf = 0; hf < NH; hf++) {
             const float tot = tot1[hf];
-            const int bl = 4 * hf + (lane & 3);
+            const int bl = NBP * hf + bbl;
             if (bl < BG) {
                 const bool act = s < Lf[hf];
                 const int t = rev ? Lf[hf] - 1 - s : s;
@@ -474,22 +566,22 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
         }
         __syncthreads();
         if (!(p.dbg & 1)) {
-            bcast_slice<H, BG>(stage_r, ar_a, barB_a, crank, warp, lane);
+            bcast_slice<H, UC, BG>(stage_r, ar_a, barB_a, crank, warp, lane);
             mbar_wait(&barB, parity);
         }
 
         // ---- phase 2: W_r[:, :H]^T dar ; carry ---------------------------------------------------
         float tot2[NH];
 #pragma unroll
-        for (int hf = 0; hf < NH; hf++) {
-            tot2[hf] = 0.f;
-            if (!(p.dbg & 2)) tot2[hf] = hf == 0 ? matvec<H, 4, (BG < 4 ? BG : 4)>(w2, arbuf, 0, lane) : matvec<H, 4, NB2>(w2, arbuf, 4, lane);
+        for (int hf = 0; hf < NH; hf++) tot2[hf] = 0.f;
+        if (!(p.dbg & 2)) {   // (the paired variant measured slower here: register pressure)
+            tot2[0] = matvec<H, R2, G::NB0, NBP>(w2, arbuf, 0, lane);
+            if (NH > 1) tot2[NH - 1] = matvec<H, R2, G::NB1, NBP>(w2, arbuf, NBP, lane);
         }
 #pragma unroll
         for (int hf = 0; hf < NH; hf++) {
-            const float tot = tot2[hf];
-            const int bl = 4 * hf + (lane & 3);
-            if (owner_lane && bl < BG && s < Lf[hf]) carry[hf] = dhp_part[hf] + part1[bl][ju2] + part2[bl][ju2] + tot;
+            const int bl = NBP * hf + bbl;
+            if (owner_lane && bl < BG && s < Lf[hf]) carry[hf] = dhp_part[hf] + part1[bl][ju2] + part2[bl][ju2] + tot2[hf];
         }
         parity ^= 1;
     }
@@ -510,9 +602,9 @@ int zero_tail_rows(s2s_ctx* ctx, float* x, const int* lengths, int B, int Lmax, 
     return 0;
 }
 
-template <int H, int BG>
-static int launch_cluster_bg(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int* max_clusters) {
-    constexpr int CS = H / 32;
+template <int H, int UC, int BG>
+static int launch_cluster_geo(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int* max_clusters) {
+    constexpr int CS = H / UC;
     const int ngroups = ceil_div(p.B, BG);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS * ngroups * p.ndir);
@@ -523,14 +615,23 @@ static int launch_cluster_bg(s2s_ctx* ctx, bool backward, const GruSeqParams& p,
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (CS > 8) {   // clusters of 16 are "non-portable": opt in once per kernel
+        static bool set[2] = {false, false};
+        if (!set[backward]) {
+            if (backward) S2S_CUDA(cudaFuncSetAttribute(gru_seq_bwd_kernel<H, UC, BG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            else S2S_CUDA(cudaFuncSetAttribute(gru_seq_fwd_kernel<H, UC, BG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            set[backward] = true;
+        }
+    }
     if (max_clusters) {   // occupancy query only
-        if (backward) S2S_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, gru_seq_bwd_kernel<H, BG>, &cfg));
-        else S2S_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, gru_seq_fwd_kernel<H, BG>, &cfg));
+        cudaError_t e = backward ? cudaOccupancyMaxActiveClusters(max_clusters, gru_seq_bwd_kernel<H, UC, BG>, &cfg)
+                                 : cudaOccupancyMaxActiveClusters(max_clusters, gru_seq_fwd_kernel<H, UC, BG>, &cfg);
+        if (e != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
         return 0;
     }
     prof_begin(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD);
-    if (backward) S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<H, BG>, p));
-    else S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_fwd_kernel<H, BG>, p));
+    if (backward) S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<H, UC, BG>, p));
+    else S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_fwd_kernel<H, UC, BG>, p));
     {   // algorithmic bytes per launch: fwd reads xp (3H) and writes y (H) + save (4H) per direction;
         // bwd reads save z,r,h~ (3H) + h_prev (H) + dy (H) and writes dA (3H) + h_prev (H)
         const double per = backward ? 9.0 * H : 8.0 * H;
@@ -540,27 +641,48 @@ static int launch_cluster_bg(s2s_ctx* ctx, bool backward, const GruSeqParams& p,
     return 0;
 }
 
-// Utterances per cluster: the smallest group size whose cluster count fits in ONE wave (a cluster that
-// does not fit runs after the others and doubles the time of this latency-bound kernel).  The number of
-// co-resident clusters is queried once per (H, direction) -- 15 clusters of 8 CTAs on a 148-SM B200.
+// Cluster geometry: a cluster that does not fit in the first wave runs after the others and doubles the time of this
+// latency-bound kernel, so the launch is sized to ONE wave.  Co-resident cluster counts are queried once (15 clusters
+// of 8 CTAs / 8 clusters of 16 CTAs on a 148-SM B200).  Preference: groups of 4 utterances on clusters of 8; else
+// 8 utterances on clusters of 16 (one butterfly pass); else larger groups on clusters of 8 (two passes).
 template <int H>
 static int launch_cluster(s2s_ctx* ctx, bool backward, const GruSeqParams& p) {
-    static int max_active[2] = {0, 0};
-    if (max_active[backward] == 0) {
+    static int cap8[2] = {0, 0}, cap16[2] = {-1, -1};
+    if (cap8[backward] == 0) {
         int n = 0;
-        S2S_TRY((launch_cluster_bg<H, 4>(ctx, backward, p, &n)));
-        max_active[backward] = n > 0 ? n : 1;
+        S2S_TRY((launch_cluster_geo<H, 32, 4>(ctx, backward, p, &n)));
+        cap8[backward] = n > 0 ? n : 1;
     }
-    const int cap = max_active[backward];
-    int bg = 4;
-    while (bg < 8 && p.ndir * ceil_div(p.B, bg) > cap) bg++;
+    int bg = 4, uc = 32;
+    { const char* e = getenv("S2S_GRU_UC"); if (e) uc = atoi(e) == 16 ? -16 : -32; }   // experiments: force a geometry
+    if (p.ndir * ceil_div(p.B, 4) > cap8[backward] && uc == -16) {   // measured: no faster than two-pass groups on clusters of 8 -> opt-in only
+        if (H == 256) {
+            if (cap16[backward] < 0) {
+                int n = 0;
+                S2S_TRY((launch_cluster_geo<256, 16, 8>(ctx, backward, p, &n)));
+                cap16[backward] = n;
+            }
+            if (p.ndir * ceil_div(p.B, 8) <= cap16[backward] || uc == -16) uc = 16;
+        }
+    }
+    if (uc == 16 && H == 256) {
+        bg = 5;
+        while (bg < 8 && p.ndir * ceil_div(p.B, bg) > cap16[backward]) bg++;
+        switch (bg) {
+            case 5: return launch_cluster_geo<256, 16, 5>(ctx, backward, p, nullptr);
+            case 6: return launch_cluster_geo<256, 16, 6>(ctx, backward, p, nullptr);
+            case 7: return launch_cluster_geo<256, 16, 7>(ctx, backward, p, nullptr);
+            default: return launch_cluster_geo<256, 16, 8>(ctx, backward, p, nullptr);
+        }
+    }
+    while (bg < 8 && p.ndir * ceil_div(p.B, bg) > cap8[backward]) bg++;
     { const char* e = getenv("S2S_GRU_BG"); if (e && atoi(e) >= 4 && atoi(e) <= 8) bg = atoi(e); }
     switch (bg) {
-        case 4: return launch_cluster_bg<H, 4>(ctx, backward, p, nullptr);
-        case 5: return launch_cluster_bg<H, 5>(ctx, backward, p, nullptr);
-        case 6: return launch_cluster_bg<H, 6>(ctx, backward, p, nullptr);
-        case 7: return launch_cluster_bg<H, 7>(ctx, backward, p, nullptr);
-        default: return launch_cluster_bg<H, 8>(ctx, backward, p, nullptr);
+        case 4: return launch_cluster_geo<H, 32, 4>(ctx, backward, p, nullptr);
+        case 5: return launch_cluster_geo<H, 32, 5>(ctx, backward, p, nullptr);
+        case 6: return launch_cluster_geo<H, 32, 6>(ctx, backward, p, nullptr);
+        case 7: return launch_cluster_geo<H, 32, 7>(ctx, backward, p, nullptr);
+        default: return launch_cluster_geo<H, 32, 8>(ctx, backward, p, nullptr);
     }
 }
 
