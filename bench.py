@@ -49,6 +49,21 @@ def peaks():
         return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(cls):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel class, from the committed `ncu --set full`
+    capture (profiles/r01_ncu_full.json); None when there is no capture for it."""
+    names = {"attn_fwd": "attn_fwd_kernel", "attn_bwd": "attn_bwd_kernel", "attn_dvh": "attn_dvh_kernel", "gru_fwd": "gru_seq_fwd_kernel",
+             "gru_bwd": "gru_seq_bwd_kernel", "gemm": "gemm_tc_kernel", "dense_small": "dense_small_kernel"}
+    try:
+        rows = [r for r in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full.json"))) if r["kernel"].startswith(names[cls])]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [r["dram__bytes_read.sum"] * unit[r["dram__bytes_read.sum.unit"]] + r["dram__bytes_write.sum"] * unit[r["dram__bytes_write.sum.unit"]]
+                for r in rows]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -308,7 +323,11 @@ def run_ours(args):
         top = max(classes, key=lambda k: classes[k]["ms_per_step"])
         c = classes[top]
         roof = {"kernel": top, "bound": c["bound"], "achieved": c["achieved"], "peak": c["peak"], "unit": c["unit"], "frac": c["frac"],
-                "traffic": None, "peak_source": how, "share_of_step": c["share"], "instrumented_step_ms": total_ms}
+                "traffic": ncu_traffic(top), "traffic_source": "profiles/r01_ncu_full.json (ncu --set full, bytes per launch)",
+                "algorithmic_bytes_per_launch": prof[top][2] / max(prof[top][1], 1),
+                "peak_source": how, "share_of_step": c["share"], "instrumented_step_ms": total_ms,
+                "note": "the recurrence kernels are latency-bound (two dependent mat-vec phases per frame, DSMEM exchange): "
+                        "us/frame-step is the figure of merit; attention kernels: see `kernels` and profiles/r01_attn_sweep.json"}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -------------------------
     cpu = None
