@@ -120,6 +120,14 @@ int s2s_gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H
                          const float* x, int ldx, const int* lengths, int B, int Lmax,
                          const float* y, const float* save, const float* dy, float* dx);
 
+/* ---- nn.GRU as a single-step module (GRU.lua:8-51 via nn.Recurrent, Recurrent.lua:104-151) ----------------- */
+/* updateOutput({x, prev_h}) -> h ; hprev NULL = zeros (Recurrent.lua:110-112); gates [B,3H] (z | r | h~) kept by the caller */
+int s2s_gru_step_forward(s2s_ctx* ctx, const float* W, int Din, int H, const float* x, const float* hprev, int B,
+                         float* hnext, float* gates);
+/* updateGradInput: dhnext -> dx [B,Din], dhprev [B,H] (overwritten); dW accumulated */
+int s2s_gru_step_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, const float* x, const float* hprev, int B,
+                          const float* gates, const float* dhnext, float* dx, float* dhprev);
+
 /* ---- nn.RNN(nn.LSTM(in,out,peepholes), reverse) over whole utterances (LSTM.lua:6-136, RNN.lua:120-201) ---- */
 /* P: flat LSTM parameters in the order the module's parameters() yields: for gate in (i, f, g, o):
  * Wx[out,in], bx[out], Wh[out,out], bh[out], and -- with peepholes, except for g -- Wc[out,out], bc[out]
@@ -198,6 +206,10 @@ int s2s_awn_sample(s2s_ctx* ctx, const float* weight, const float* eps, uint64_t
 int s2s_awn_forward(s2s_ctx* ctx, const float* weight, int64_t n, double lambda, double nll, double* L_host);
 /* gradWeight [2n] overwritten (AdaptiveWeightNoise.lua:82-104); g = dNLL/dw [n] */
 int s2s_awn_accgrad(s2s_ctx* ctx, const float* weight, const float* g, int64_t n, double lambda, float* gradWeight);
+
+/* nn.Dropout mask for {s,c} (model_chorowski_baseline_dropout.lua:56): 0 with probability p, else 1/(1-p)
+ * (Torch nn.Dropout v2 scaling); Philox counter RNG seeded by (seed, call counter). */
+int s2s_dropout_mask(s2s_ctx* ctx, float p, uint64_t seed, int64_t n, float* mask);
 
 /* ---- gradient step (timit/timit.lua:291-348, TrainUtils.lua:52-104, optim.adadelta) ---------- */
 /* g /= batch ; norm ; clip to maxnorm ; g += wd*p ; g += noise_sigma*N(0,1).  The pre-clip norm is

@@ -311,3 +311,25 @@ int s2s_model_rownorm_constraint(s2s_ctx* ctx, const s2s_model_cfg* cfg, float* 
 }
 
 }  // extern "C"
+
+// ---- nn.Dropout mask (model_chorowski_baseline_dropout.lua:56; Torch nn.Dropout v2: keep with prob 1-p, scale 1/(1-p)) ----
+namespace s2s {
+__global__ void dropout_mask_kernel(float p, uint64_t seed, uint64_t stream, int64_t n, float* __restrict__ mask) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = g * 4;
+    if (i0 >= n) return;
+    uint32_t u[4];
+    philox4(seed, stream, (uint64_t)g, u);
+    const float scale = 1.f / (1.f - p);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (i0 + j < n) mask[i0 + j] = ((float)u[j] * 2.3283064365386963e-10f >= p) ? scale : 0.f;
+}
+}  // namespace s2s
+
+extern "C" int s2s_dropout_mask(s2s_ctx* ctx, float p, uint64_t seed, int64_t n, float* mask) {
+    S2S_REQUIRE(ctx && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments (p=%f)", (double)p);
+    s2s::dropout_mask_kernel<<<(unsigned)s2s::ceil_div64(s2s::ceil_div64(n, 4), 256), 256, 0, ctx->stream>>>(p, seed, ctx->rng_calls++, n, mask);
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}

@@ -23,6 +23,9 @@ int s2s_linear_zb_backward(s2s_ctx*, const float* x, int64_t rows, int in_, cons
 int64_t s2s_gru_seq_save_floats(int B, int Lmax, int H, int ndir);
 int s2s_gru_seq_forward(s2s_ctx*, const float* W, int Din, int H, int ndir, int reverse, const float* x, int ldx, const int* lengths, int B, int Lmax, float* y, float* save);
 int s2s_gru_seq_backward(s2s_ctx*, const float* W, float* dW, int Din, int H, int ndir, int reverse, const float* x, int ldx, const int* lengths, int B, int Lmax, const float* y, const float* save, const float* dy, float* dx);
+int s2s_gru_step_forward(s2s_ctx*, const float* W, int Din, int H, const float* x, const float* hprev, int B, float* hnext, float* gates);
+int s2s_gru_step_backward(s2s_ctx*, const float* W, float* dW, int Din, int H, const float* x, const float* hprev, int B, const float* gates, const float* dhnext, float* dx, float* dhprev);
+int s2s_dropout_mask(s2s_ctx*, float p, uint64_t seed, int64_t n, float* mask);
 int s2s_attention_forward(s2s_ctx*, const s2s_model_cfg*, const float* P, const float* h, const int* lengths, int B, int Lmax, const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda, float* logp);
 int s2s_attention_backward(s2s_ctx*, const s2s_model_cfg*, const float* P, float* G, const float* h, const int* lengths, int B, int Lmax, const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda, const float* dlogp, float* dh);
 int s2s_attention_get(s2s_ctx*, int what, float* dst);

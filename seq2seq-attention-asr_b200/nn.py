@@ -115,6 +115,23 @@ class GRU(Module):
     def parameters(self):
         return [self.weight[i] for i in range(3)], [self.gradWeight[i] for i in range(3)]
 
+    # single-step protocol through nn.Recurrent: input {x, prev_h} -> h (Recurrent.lua:104-127, GRU.lua:22-38)
+    def updateOutput(self, input):
+        x, hp = (input if isinstance(input, (list, tuple)) else (input, None))
+        self._batched = x.dim() == 2
+        xb = x.contiguous() if self._batched else x.contiguous().unsqueeze(0)
+        hpb = None if hp is None else (hp.contiguous() if self._batched else hp.contiguous().unsqueeze(0))
+        hn, self._gates = ops.gru_step_forward(self.ctx, self.weight, xb, hpb)
+        self._x, self._hp = xb, hpb
+        self.output = hn if self._batched else hn[0]
+        return self.output
+
+    def updateGradInput(self, input, gradOutput):
+        dhn = gradOutput.contiguous() if self._batched else gradOutput.contiguous().unsqueeze(0)
+        dx, dhp, _ = ops.gru_step_backward(self.ctx, self.weight, self._x, self._hp, self._gates, dhn, dW=self.gradWeight)
+        self.gradInput = [dx, dhp] if self._batched else [dx[0], dhp[0]]
+        return self.gradInput
+
 
 class LSTM(Module):
     """Parameter holder in the reference's order (LSTM.lua:25-60): per gate Linear(in,out)+Linear(out,out), both with

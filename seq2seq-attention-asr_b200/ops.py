@@ -157,6 +157,30 @@ def gru_seq_backward(ctx, W, x, y, save, dy, lengths=None, ndir=1, reverse=False
     return dx, dW
 
 
+def gru_step_forward(ctx, W, x, hprev=None):
+    B, Din = x.shape
+    H = W.shape[-2]
+    hn = ctx.new(B, H); gates = ctx.new(B, 3 * H)
+    check(ctx.lib.s2s_gru_step_forward(ctx.h, _f(W), Din, H, _f(x), _f(hprev), B, _f(hn), _f(gates)))
+    return hn, gates
+
+
+def gru_step_backward(ctx, W, x, hprev, gates, dhn, dW=None):
+    B, Din = x.shape
+    H = W.shape[-2]
+    if dW is None:
+        dW = torch.zeros_like(W)
+    dx = ctx.new(B, Din); dhp = ctx.new(B, H)
+    check(ctx.lib.s2s_gru_step_backward(ctx.h, _f(W), _f(dW), Din, H, _f(x), _f(hprev), B, _f(gates), _f(dhn), _f(dx), _f(dhp)))
+    return dx, dhp, dW
+
+
+def dropout_mask(ctx, shape, p, seed=0):
+    m = ctx.new(*shape)
+    check(ctx.lib.s2s_dropout_mask(ctx.h, p, seed, m.numel(), _f(m)))
+    return m
+
+
 # ---- LSTM sequence --------------------------------------------------------------------------------------
 def lstm_param_count(din, H, peepholes):
     return int(_lib.load().s2s_lstm_param_count(din, H, int(peepholes)))

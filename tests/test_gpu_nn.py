@@ -75,3 +75,36 @@ def test_tconv_zero_bias_module(s2s, gctx):
     assert np.allclose(m.gradWeight.cpu().numpy(), 10.0)
     with pytest.raises(s2s.S2SError):
         nn.TemporalConvolutionZeroBias(gctx, 5, 4, 3)
+
+
+def test_gru_single_step_module(s2s, gctx, orc64):
+    # nn.GRU stepped by hand with an explicit previous state (GRU.lua:22-38 through nn.Recurrent)
+    nn = s2s.nn
+    rng = np.random.default_rng(3)
+    Din, H, B = 123, 64, 5
+    gru = nn.GRU(gctx, Din, H)
+    W = gru.weight.cpu().numpy().astype(np.float64)
+    x = rng.standard_normal((B, Din)); hp = rng.standard_normal((B, H)); dhn = rng.standard_normal((B, H))
+    hn = gru.forward([dev(x, torch.float32), dev(hp, torch.float32)])
+    dx, dhp = gru.backward([dev(x, torch.float32), dev(hp, torch.float32)], dev(dhn, torch.float32))
+    dW_ref = np.zeros_like(W)
+    for b in range(B):
+        h_ref, z, r, hc = orc64.gru_step_forward(W[0], W[1], W[2], x[b], hp[b])
+        assert rel_err(hn[b].cpu().numpy(), h_ref) < TOL
+        dxb, dhpb, dWz, dWr, dWh = orc64.gru_step_backward(W[0], W[1], W[2], x[b], hp[b], z, r, hc, dhn[b])
+        assert rel_err(dx[b].cpu().numpy(), dxb) < TOL and rel_err(dhp[b].cpu().numpy(), dhpb) < TOL
+        dW_ref += np.stack([dWz, dWr, dWh])
+    assert rel_err(gru.gradWeight.cpu().numpy(), dW_ref) < TOL
+    # zero initial state when prev_h is omitted (Recurrent.lua:110-112)
+    h0 = gru.forward(dev(x[0], torch.float32))
+    h0_ref, *_ = orc64.gru_step_forward(W[0], W[1], W[2], x[0], np.zeros(H))
+    assert rel_err(h0.cpu().numpy(), h0_ref) < TOL
+
+
+def test_dropout_mask_statistics(s2s, gctx):
+    m = s2s.dropout_mask(gctx, (1 << 20,), 0.5, seed=11).cpu().numpy()
+    vals = np.unique(m)
+    assert set(vals.tolist()) == {0.0, 2.0}
+    assert abs((m == 0).mean() - 0.5) < 5e-3
+    m2 = s2s.dropout_mask(gctx, (1 << 20,), 0.2, seed=11).cpu().numpy()
+    assert abs((m2 == 0).mean() - 0.2) < 5e-3 and abs(m2.max() - 1.25) < 1e-6
