@@ -36,6 +36,9 @@ sys.path.insert(0, ROOT)
 CFG = dict(D=123, H=256, NL=3, S=512, ST=256, V=62, K=0, KF=10, M=64, MW=7)
 B_PER_GPU, L, T = 32, 300, 50
 METRIC = "chorowski_timit_fwd_bwd_frames_per_sec"
+WORKLOAD_CFG3 = ("cfg3: timit/model_chorowski_baseline_dropout.lua (cfg2 model + Dropout(0.5) on {s,c}) with AdaptiveWeightNoise "
+                 "(lambda=1, sigma_init=0.075), batch 32/GPU, L=300, T=50; step = AWN sample (one per shard) + dropout mask + zero-grad + "
+                 "fwd + NLL + bwd + [all-reduce] + /B + clip + AWN forward/backward + adadelta over {mu, log sigma^2} + row-norm")
 WORKLOAD = ("cfg2: timit/model_chorowski_baseline.lua (3x biGRU-256 encoder, content attention K=0, GRU-256 decoder, "
             "maxout 64x7), batch 32/GPU, L=300, D=123, T=50, V=62; step = zero-grad + fwd + NLL + bwd + "
             "[all-reduce] + /B + clip + adadelta + row-norm")
@@ -211,7 +214,33 @@ def run_ours(args):
     nll = torch.zeros(B, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    cfg3 = args.config == "cfg3"
+    if cfg3:
+        # AdaptiveWeightNoise.lua:8-25: weight = {mu, s = log sigma^2}, s initialised to log(sigma_init^2) (timit.lua:35-36,198-205)
+        W2 = torch.cat([P, torch.full((n,), float(np.log(0.075 ** 2)), device=dev)])
+        gW2 = torch.zeros(2 * n, device=dev)
+        v2 = torch.zeros(2 * n, device=dev); a2 = torch.zeros(2 * n, device=dev)
+        Pn = torch.empty(n, device=dev)
+        mask = torch.empty(B, T, CFG["ST"] + 2 * CFG["H"], device=dev)
+        counter = [0]
+
+    def step_cfg3(Xd, yd, lnd, tld):
+        counter[0] += 1
+        seed = (counter[0] << 8) | rank                              # a different sample per rank and step
+        s2s.awn_sample(ctx, W2, seed=seed, out=Pn)                    # parameters:copy(AWN:Sample())   (timit.lua:247-253)
+        s2s.dropout_mask(ctx, mask.shape, 0.5, seed=seed, out=mask)   # nn.Dropout on {s,c}  (model_chorowski_baseline_dropout.lua:56)
+        G.zero_()
+        s2s.model_fwdbwd(ctx, CFG, Pn, G, Xd, yd, lengths=lnd, tlens=tld, dropmask=mask, flags=s2s.NORMALIZE_NLL, nll=nll)
+        s2s.dp.allreduce_gradients(G)
+        s2s.grad_finalize(ctx, G, Pn, B * world, 1e20, want_norm=False)
+        s2s.awn_accgrad(ctx, W2, G, 1.0, out=gW2)                     # AWN:backward(nll, gradients)    (timit.lua:318-327)
+        s2s.adadelta(ctx, W2, gW2, v2, a2)                            # optimMethod(optimfunc, adaparameters, ...)  (:336)
+        s2s.model_rownorm_constraint(ctx, CFG, W2[:n], 1.0)           # the graph's weights are views of mu here (:346-348)
+        return nll
+
     def step(Xd, yd, lnd, tld):
+        if cfg3:
+            return step_cfg3(Xd, yd, lnd, tld)
         G.zero_()                                                     # zeroGradParameters (timit.lua:233)
         s2s.model_fwdbwd(ctx, CFG, P, G, Xd, yd, lengths=lnd, tlens=tld, flags=s2s.NORMALIZE_NLL, nll=nll)
         s2s.dp.allreduce_gradients(G)                                 # data-parallel gradient sum over NVLink (no-op at N = 1)
@@ -343,7 +372,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD_CFG3 if cfg3 else WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "flushed between timed steps (256 MiB write outside the per-step event pairs)"},
             "e2e": {"value": frames / (e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
@@ -372,6 +401,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2 = the metric's configuration (default); cfg3 = dropout model + AdaptiveWeightNoise (BASELINE.json configs[2])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,20 +1,29 @@
 // gemm_tc.cu -- tcgen05 / TMEM GEMM for the large time-batched projections:
-//     C[M,N] = alpha * A[M,K] . B[N,K]^T (+ beta C) (+ bias[n])        fp32 in, fp32 out
+//     C[M,N] = alpha * op(A) . op(B) (+ beta C) (+ bias[n])        fp32 in, fp32 out
 // (the x-columns of the GRU gates over all frames, LinearZeroBias.lua:42; Vh = h W_V^T,
-// TemporalConvolutionZeroBias.lua:39; their data/weight gradients after a transpose of the operand.)
+// TemporalConvolutionZeroBias.lua:39; their data and weight gradients.)
 //
 // Precision: the reference computes these products in fp32 BLAS and the parity bound is 1e-4, which a
-// single TF32 pass (10-bit mantissa, ~5e-4) misses.  Each operand is therefore split in shared memory into
-// hi = top 19 bits (exactly representable in TF32) and lo = x - hi, and three tensor-core products
-// A_hi B_hi + A_hi B_lo + A_lo B_hi are accumulated in the fp32 TMEM accumulator ("3xTF32", error ~2^-21).
+// single TF32 pass (10-bit mantissa, ~5e-4) misses.  Each operand x is therefore split into
+// hi = top 19 bits of x (exactly representable in TF32) and lo = x - hi, and three tensor-core products
+// A_lo B_hi + A_hi B_lo + A_hi B_hi are accumulated in the fp32 TMEM accumulator ("3xTF32", error ~2^-21).
 //
-// Structure (one 128x128 output tile per CTA, K consumed in 32-float = 128-byte slabs):
-//   warp 0     TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) of the fp32 A and B slabs -> smem, 3 stages
-//   warps 2-5  split pass: raw slab -> {hi (in place), lo}; fence.proxy.async; arrive on the `conv` barrier;
-//              later the epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> alpha/beta/bias -> global
-//   warp 1     TMEM allocation (128 columns) and the single-thread tcgen05.mma.cta_group::1.kind::tf32 issue
-//              loop (M=128, N=128, K=8 per instruction, 12 instructions per slab); tcgen05.commit frees the stage
-//              and finally signals the epilogue.
+// The split is done ONCE per operand by a streaming pre-pass (split_kernel / transpose_split_kernel) that
+// also brings M- or N-contiguous operands to the K-contiguous form the tensor core wants, so the GEMM kernel
+// itself is a pure TMA -> tcgen05.mma pipeline (the first version split inside shared memory, which cost more
+// shared-memory bandwidth than the MMAs themselves and re-split every slab once per tile that used it).
+//
+// Kernel: persistent, one CTA per SM, 128 x 256 output tiles, K consumed in 32-float (= 128-byte swizzle row)
+// slabs, two 96 KB stages {A_hi, A_lo, B_hi, B_lo}:
+//   warp 0      TMA producer: 4 cp.async.bulk.tensor.2d (SWIZZLE_128B) per slab
+//   warp 1      TMEM allocation (512 columns = two 128x256 fp32 accumulators) and the single-thread
+//               tcgen05.mma.cta_group::1.kind::tf32 issue loop (M=128, N=256, K=8; 12 instructions per slab);
+//               tcgen05.commit frees the stage / publishes the accumulator
+//   warps 2-9   epilogue: tcgen05.ld (32 lanes x 32 columns) -> smem transpose -> coalesced stores, overlapped
+//               with the next segment's main loop through the second accumulator
+// Scheduling: tiles are dealt round-robin to the CTAs; the tiles left over after the last full round are cut
+// along K into equal shares ("stream-K" tail) whose partial sums are added with atomics, so that e.g. 150 tiles
+// on 148 SMs cost ~1.25 tile times instead of 2.  Weight gradients (few tiles, K = B*L) are all tail.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -22,12 +31,48 @@
 namespace s2s {
 
 namespace tc {
-constexpr int BM = 128, BN = 128, BK = 32;          // BK floats = 128 bytes = one swizzle row
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB per operand slab
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, B_hi, B_lo
-constexpr int THREADS = 192;
-constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BN = 256, BK = 32;          // BK floats = 128 bytes = one swizzle row
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 4;                // 16 KB
+constexpr int B_BYTES = BN * BK * 4;                // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi, A_lo, B_hi, B_lo = 96 KB
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int SCR_FLOATS = 32 * 33;                 // per-warp transpose scratch
+constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * SCR_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MIN_SHARE = 4;                        // a stream-K share is at least this many slabs
+
+struct Sched {
+    int tiles_m, tiles_n, nk;     // tile grid and slabs per tile
+    int G;                        // CTAs
+    int R;                        // full rounds: tiles [0, R*G) are done whole, tile i*G + g by CTA g
+    int rem;                      // tiles left for the stream-K tail
+    int Gp;                       // CTAs that take a share of the tail
+};
+struct Span { int tm, tn, kb0, kb1; };
+
+// i-th segment of CTA g; false when the CTA has no more work.  All three roles enumerate the same sequence.
+__device__ __forceinline__ bool get_seg(const Sched& s, int g, int i, Span& seg) {
+    int tile, kb0, kb1;
+    if (i < s.R) {
+        tile = i * s.G + g; kb0 = 0; kb1 = s.nk;
+    } else {
+        if (s.rem == 0 || g >= s.Gp) return false;
+        const long long U = (long long)s.rem * s.nk;
+        const long long u0 = U * g / s.Gp, u1 = U * (g + 1) / s.Gp;
+        if (u1 <= u0) return false;
+        const int t0 = (int)(u0 / s.nk);
+        const int t = t0 + (i - s.R);
+        if ((long long)t * s.nk >= u1) return false;
+        const long long lo = (long long)t * s.nk;
+        kb0 = (int)((u0 > lo ? u0 : lo) - lo);
+        const long long hi = lo + s.nk;
+        kb1 = (int)((u1 < hi ? u1 : hi) - lo);
+        tile = s.R * s.G + t;
+    }
+    seg.tm = tile / s.tiles_n; seg.tn = tile - seg.tm * s.tiles_n; seg.kb0 = kb0; seg.kb1 = kb1;
+    return true;
+}
 
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity) {
     // a mis-programmed pipeline must fail loudly instead of hanging the GPU
@@ -50,7 +95,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D = f32, A = B = tf32, both K-major, N = 128, M = 128
+// instruction descriptor: D = f32, A = B = tf32, both K-major, N = 256, M = 128
 __device__ __forceinline__ uint32_t make_idesc() {
     uint32_t d = 0;
     d |= 1u << 4;                       // c_format = F32
@@ -81,35 +126,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }  // namespace tc
 
 __global__ void __launch_bounds__(tc::THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
-               float alpha, float beta, float* __restrict__ C, int ldc, const float* __restrict__ bias, int splitk) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const tc::Sched sched,
+               int M, int N, float alpha, float beta, float* __restrict__ C, int ldc, const float* __restrict__ bias) {
     using namespace tc;
+    Span seg;
+    if (!get_seg(sched, blockIdx.x, 0, seg)) return;       // nothing dealt to this CTA (uniform per CTA)
+
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                 // [STAGES]  TMA bytes landed
-    uint64_t* conv = bars + STAGES;        // [STAGES]  hi/lo split done (4 warp arrivals)
-    uint64_t* empty = bars + 2 * STAGES;   // [STAGES]  MMAs that read the stage have completed
-    uint64_t* tmem_full = bars + 3 * STAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    float* scr_all = reinterpret_cast<float*>(base + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * SCR_FLOATS * 4);
+    uint64_t* full = bars;                      // [STAGES]  TMA bytes landed
+    uint64_t* empty = bars + STAGES;            // [STAGES]  MMAs that read the stage have retired
+    uint64_t* tmem_full = bars + 2 * STAGES;    // [2]       accumulator complete
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]   accumulator drained by the epilogue warps
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    // split-K (weight gradients: K = B*L is long, the output small): slab range of this CTA; partial tiles are
-    // accumulated into C with atomics (requires beta == 1 semantics, enforced by the host)
-    const int nk_all = (K + BK - 1) / BK;
-    const int per = (nk_all + splitk - 1) / splitk;
-    const int kb0 = blockIdx.z * per;
-    const int nk = min(per, nk_all - kb0);
-    if (nk <= 0) return;
+    const int g = blockIdx.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -118,101 +161,183 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
+        // ---- TMA producer -----------------------------------------------------------------------------------
         if (lane == 0) {
-            for (int kb = 0; kb < nk; kb++) {
-                const int s = kb % STAGES, it = kb / STAGES;
-                if (it > 0) mbar_wait_bounded(&empty[s], (it - 1) & 1);
-                unsigned char* st = base + (size_t)s * STAGE_BYTES;
-                mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-                tma_load_2d(st, &mapA, (kb0 + kb) * BK, m0, &full[s]);                    // A slab -> A_hi slot (raw)
-                tma_load_2d(st + 2 * TILE_BYTES, &mapB, (kb0 + kb) * BK, n0, &full[s]);   // B slab -> B_hi slot (raw)
+            int it = 0;
+            for (int i = 0; get_seg(sched, g, i, seg); i++) {
+                const int m0 = seg.tm * BM, n0 = seg.tn * BN;
+                for (int kb = seg.kb0; kb < seg.kb1; kb++, it++) {
+                    const int s = it % STAGES, ph = it / STAGES;
+                    if (ph > 0) mbar_wait_bounded(&empty[s], (ph - 1) & 1);
+                    unsigned char* st = base + (size_t)s * STAGE_BYTES;
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    tma_load_2d(st, &mapAh, kb * BK, m0, &full[s]);
+                    tma_load_2d(st + A_BYTES, &mapAl, kb * BK, m0, &full[s]);
+                    tma_load_2d(st + 2 * A_BYTES, &mapBh, kb * BK, n0, &full[s]);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, kb * BK, n0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
+        // ---- MMA issue --------------------------------------------------------------------------------------
         if (lane == 0) {
             const uint32_t idesc = make_idesc();
-            for (int kb = 0; kb < nk; kb++) {
-                const int s = kb % STAGES, it = kb / STAGES;
-                mbar_wait_bounded(&conv[s], it & 1);
+            int it = 0;
+            for (int i = 0; get_seg(sched, g, i, seg); i++) {
+                const int acc = i & 1;
+                if (i >= 2) mbar_wait_bounded(&tmem_empty[acc], ((i >> 1) - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(base + (size_t)s * STAGE_BYTES);
-                const uint64_t dAh = make_desc(sa), dAl = make_desc(sa + TILE_BYTES);
-                const uint64_t dBh = make_desc(sa + 2 * TILE_BYTES), dBl = make_desc(sa + 3 * TILE_BYTES);
+                const uint32_t td = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = seg.kb0; kb < seg.kb1; kb++, it++) {
+                    const int s = it % STAGES, ph = it / STAGES;
+                    mbar_wait_bounded(&full[s], ph & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(base + (size_t)s * STAGE_BYTES);
+                    const uint64_t dAh = make_desc(sa), dAl = make_desc(sa + A_BYTES);
+                    const uint64_t dBh = make_desc(sa + 2 * A_BYTES), dBl = make_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 8; k++) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);            // 32 bytes per K = 8 step inside the swizzle row
-                    umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, (kb | k) != 0);
-                    umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1);
-                    umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, 1);
+                    for (int k = 0; k < BK / 8; k++) {
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);            // 32 bytes per K = 8 step inside the swizzle row
+                        umma_tf32(td, dAl + adv, dBh + adv, idesc, (kb != seg.kb0 || k != 0) ? 1u : 0u);
+                        umma_tf32(td, dAh + adv, dBl + adv, idesc, 1);
+                        umma_tf32(td, dAh + adv, dBh + adv, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);                                           // stage reusable once these MMAs retire
                 }
-                umma_commit(&empty[s]);                                           // stage reusable once these MMAs retire
+                umma_commit(&tmem_full[acc]);
             }
-            umma_commit(tmem_full);
         }
     } else {
-        // ---- split pass (warps 2-5) ------------------------------------------------------------------------
-        const int ct = threadIdx.x - 64;      // 0..127
-        for (int kb = 0; kb < nk; kb++) {
-            const int s = kb % STAGES, it = kb / STAGES;
-            mbar_wait_bounded(&full[s], it & 1);
-            float4* st = reinterpret_cast<float4*>(base + (size_t)s * STAGE_BYTES);
-            constexpr int V4 = TILE_BYTES / 16;          // float4 per slab
-#pragma unroll 4
-            for (int i = ct; i < 2 * V4; i += 128) {
-                const int op = i / V4, j = i - op * V4;  // operand 0 = A, 1 = B
-                float4* hi = st + (size_t)op * 2 * V4 + j;
-                float4* lo = hi + V4;
-                const float4 v = *hi;
-                float4 h;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                *hi = h;
-                *lo = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-            }
-            fence_proxy_async();              // generic-proxy writes -> visible to the tensor-core (async) proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&conv[s]);
-        }
-        // ---- epilogue --------------------------------------------------------------------------------------
-        mbar_wait_bounded(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue (warps 2..9): warp e reads TMEM lane quarter (warp & 3), column half (e >> 2) ----------
+        const int e = warp - 2;
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-        // all MMAs have retired, so the pipeline stages are free: each warp transposes its 32x32 accumulator
-        // chunks through a private padded scratch so that every global store covers one 128-byte row segment
-        float* scr = reinterpret_cast<float*>(base) + (size_t)(warp - 2) * 32 * 33;
+        const int half = e >> 2;
+        float* scr = scr_all + (size_t)e * SCR_FLOATS;
+        const bool vec_ok = (ldc & 3) == 0 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+        for (int i = 0; get_seg(sched, g, i, seg); i++) {
+            const int acc = i & 1;
+            const int m0 = seg.tm * BM, n0 = seg.tn * BN;
+            const bool direct = seg.kb0 == 0 && seg.kb1 == sched.nk;
+            mbar_wait_bounded(&tmem_full[acc], (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+                if (n0 + c0 >= N) break;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
 #pragma unroll
-            for (int j = 0; j < 32; j++) scr[lane * 33 + j] = __uint_as_float(r[j]);
-            __syncwarp();
-            const int n = n0 + c0 + lane;
-            const float bv = (bias && n < N) ? bias[n] : 0.f;
-            if (n < N) {
+                for (int j = 0; j < 32; j++) scr[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                if (vec_ok) {
+                    // 4 rows x 8 float4 per pass: 16-byte stores / vector reductions (REDG.F32x4: a quarter of the L2 atomic ops)
+                    const int rsub = lane >> 3, cq = (lane & 7) * 4;
+                    const int n = n0 + c0 + cq;
+                    if (n < N) {
+                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias && seg.kb0 == 0) bv = make_float4(bias[n], bias[n + 1], bias[n + 2], bias[n + 3]);
+#pragma unroll
+                        for (int rr = 0; rr < 32; rr += 4) {
+                            const int row = m0 + q * 32 + rr + rsub;
+                            if (row < M) {
+                                const float* sp = scr + (rr + rsub) * 33 + cq;
+                                float4 v = make_float4(alpha * sp[0] + bv.x, alpha * sp[1] + bv.y, alpha * sp[2] + bv.z, alpha * sp[3] + bv.w);
+                                float* cp = C + (size_t)row * ldc + n;
+                                if (direct) {
+                                    if (beta != 0.f) {
+                                        const float4 o = *reinterpret_cast<const float4*>(cp);
+                                        v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w;
+                                    }
+                                    *reinterpret_cast<float4*>(cp) = v;
+                                } else {
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    const int n = n0 + c0 + lane;
+                    if (n < N) {
+                        const float bv = (bias && seg.kb0 == 0) ? bias[n] : 0.f;
 #pragma unroll 4
-                for (int rr = 0; rr < 32; rr++) {
-                    const int row = m0 + q * 32 + rr;
-                    if (row < M) {
-                        float* cp = C + (size_t)row * ldc + n;
-                        if (splitk > 1) {
-                            atomicAdd(cp, alpha * scr[rr * 33 + lane] + (blockIdx.z == 0 ? bv : 0.f));
-                        } else {
-                            float v = alpha * scr[rr * 33 + lane] + bv;
-                            if (beta != 0.f) v += beta * (*cp);
-                            *cp = v;
+                        for (int rr = 0; rr < 32; rr++) {
+                            const int row = m0 + q * 32 + rr;
+                            if (row < M) {
+                                float* cp = C + (size_t)row * ldc + n;
+                                float v = alpha * scr[rr * 33 + lane] + bv;
+                                if (direct) {
+                                    if (beta != 0.f) v += beta * (*cp);
+                                    *cp = v;
+                                } else {
+                                    atomicAdd(cp, v);
+                                }
+                            }
                         }
                     }
                 }
+                __syncwarp();
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// ---- operand preparation ---------------------------------------------------------------------------------------
+// hi/lo split of a K-contiguous operand [rows, K] (pitch ld) into scratch with pitch Kp (multiple of 4);
+// hi == nullptr: only lo is written (the tensor core ignores the low 13 mantissa bits of the raw operand).
+__global__ void split_kernel(const float* __restrict__ src, int rows, int K, int ld, float* __restrict__ hi, float* __restrict__ lo, int Kp) {
+    const int k4 = Kp >> 2;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)rows * k4; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / k4), k = (int)(idx - (long long)r * k4) * 4;
+        const float* p = src + (size_t)r * ld + k;
+        float4 v;
+        if (vec && k + 3 < K) v = ldg_stream(p);
+        else {
+            v.x = k < K ? __ldg(p) : 0.f; v.y = k + 1 < K ? __ldg(p + 1) : 0.f;
+            v.z = k + 2 < K ? __ldg(p + 2) : 0.f; v.w = k + 3 < K ? __ldg(p + 3) : 0.f;
+        }
+        float4 h;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        const size_t o = (size_t)r * Kp + k;
+        if (hi) *reinterpret_cast<float4*>(hi + o) = h;
+        *reinterpret_cast<float4*>(lo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    }
+}
+// src is [K, rows] (pitch ld): transposed split into hi, lo [rows, Kp]
+__global__ void transpose_split_kernel(const float* __restrict__ src, int K, int rows, int ld, float* __restrict__ hi, float* __restrict__ lo, int Kp) {
+    __shared__ float t[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;          // source column = output row
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int k = blockIdx.y * 32 + i;
+        t[i][threadIdx.x] = (k < K && c < rows) ? __ldg(src + (size_t)k * ld + c) : 0.f;
+    }
+    __syncthreads();
+    const int k2 = blockIdx.y * 32 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r2 = blockIdx.x * 32 + i;
+        if (r2 < rows && k2 < Kp) {
+            const float v = t[threadIdx.x][i];             // zero beyond K
+            const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            hi[(size_t)r2 * Kp + k2] = h;
+            lo[(size_t)r2 * Kp + k2] = v - h;
+        }
+    }
+}
+__global__ void zero_tiles_kernel(float* __restrict__ C, int ldc, int M, int N, int tiles_n, int first_tile) {
+    const int tile = first_tile + blockIdx.x;
+    const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+    for (int idx = threadIdx.x; idx < tc::BM * tc::BN; idx += blockDim.x) {
+        const int r = tm * tc::BM + idx / tc::BN, c = tn * tc::BN + idx % tc::BN;
+        if (r < M && c < N) C[(size_t)r * ldc + c] = 0.f;
     }
 }
 
@@ -231,79 +356,103 @@ static PFN_encodeTiled get_encode() {
     }
     return fn;
 }
-// [rows, K] fp32, K contiguous, row pitch ld floats; box = 32 floats x 128 rows, 128-byte swizzle, OOB -> 0
-static bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld) {
+// [rows, K] fp32, K contiguous, row pitch ld floats; box = 32 floats x box_rows, 128-byte swizzle, OOB -> 0
+static bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 static int tc_enabled() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("S2S_TC"); v = e ? atoi(e) : 1; }
+    if (v < 0) v = env_int("S2S_TC", 1);
+    return v;
+}
+// S2S_TC_RAWHI=1 (default): a K-contiguous, 16-byte-aligned operand is used in place as the hi part (the tf32 MMA reads
+// only the top 19 bits); 0 = always materialise the masked hi copy.
+static int tc_rawhi() {
+    static int v = -1;
+    if (v < 0) v = env_int("S2S_TC_RAWHI", 1);
     return v;
 }
 
-// Handles C = alpha A B^T (+beta C)(+bias) when both operands are K-contiguous (tA = false, tB = true), 16-byte aligned
-// with 16-byte-multiple row pitches, and the problem is large enough to fill the tensor pipe.  Everything else stays on
-// the exact-fp32 SIMT kernel.
-static int tc_launch(s2s_ctx* ctx, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta,
-                     float* C, int ldc, const float* bias, int splitk, bool* handled);
+struct TcOp { const float* hi; const float* lo; int ld_hi, ld_lo; };
 
-// Large products in the other two operand orders are brought to the K-contiguous form by transposing the
-// M/N-contiguous operand(s) into scratch (a few tens of microseconds against hundreds saved):
-//   NN  C = A B        -> B^T                     (data gradients: dX = dA W_x, dh = dVh W_V)
-//   TN  C += A^T B     -> A^T and B^T, split-K    (weight gradients, K = B*L)
-int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
-                float beta, float* C, int ldc, const float* bias, bool* handled, bool force) {
-    *handled = false;
-    if (!tc_enabled() && !force) return 0;
-    if (K < 32 || M < 1 || N < 1) return 0;
-    if (!force && (double)M * N * K < 5e8) return 0;            // small products: launch-bound, keep exact SIMT
-    if (!tA && tB) return tc_launch(ctx, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, 1, handled);
-    if (force) return 0;                                        // the test hook exercises the native form only
+// src: K-contiguous [rows, K] (transposed == false) or [K, rows] (transposed == true), pitch ld
+static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, bool transposed, TcOp* op) {
     const int Kp = (K + 3) & ~3;
-    if (!tA && !tB) {
-        if ((lda & 3) || (reinterpret_cast<uintptr_t>(A) & 15)) return 0;
-        float* Bt;
-        S2S_ALLOC(Bt, ctx->arena, float, (size_t)N * Kp);
-        S2S_TRY(transpose_f32(ctx, B, K, N, ldb, Bt, Kp));
-        return tc_launch(ctx, M, N, K, alpha, A, lda, Bt, Kp, beta, C, ldc, bias, 1, handled);
+    float *hi = nullptr, *lo;
+    S2S_ALLOC(lo, ctx->arena, float, (size_t)rows * Kp);
+    const bool raw = !transposed && tc_rawhi() && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    if (!raw) S2S_ALLOC(hi, ctx->arena, float, (size_t)rows * Kp);
+    if (transposed) {
+        transpose_split_kernel<<<dim3(ceil_div(rows, 32), ceil_div(Kp, 32)), dim3(32, 8), 0, ctx->stream>>>(src, K, rows, ld, hi, lo, Kp);
+    } else {
+        const long long n4 = (long long)rows * (Kp >> 2);
+        int blocks = (int)((n4 + 255) / 256);
+        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+        split_kernel<<<blocks, 256, 0, ctx->stream>>>(src, rows, K, ld, hi, lo, Kp);
     }
-    if (tA && !tB) {
-        if (beta != 1.f) return 0;
-        float *At, *Bt;
-        S2S_ALLOC(At, ctx->arena, float, (size_t)M * Kp);
-        S2S_ALLOC(Bt, ctx->arena, float, (size_t)N * Kp);
-        S2S_TRY(transpose_f32(ctx, A, K, M, lda, At, Kp));
-        S2S_TRY(transpose_f32(ctx, B, K, N, ldb, Bt, Kp));
-        const int tiles = ceil_div(M, tc::BM) * ceil_div(N, tc::BN);
-        int sk = ctx->sm_count / (tiles > 0 ? tiles : 1);
-        if (sk < 1) sk = 1;
-        if (sk > 16) sk = 16;
-        return tc_launch(ctx, M, N, K, alpha, At, Kp, Bt, Kp, beta, C, ldc, bias, sk, handled);
-    }
+    S2S_LAUNCH_CHECK(ctx);
+    op->hi = raw ? src : hi; op->ld_hi = raw ? ld : Kp;
+    op->lo = lo; op->ld_lo = Kp;
     return 0;
 }
 
-static int tc_launch(s2s_ctx* ctx, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta,
-                     float* C, int ldc, const float* bias, int splitk, bool* handled) {
-    if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return 0;
-    CUtensorMap mapA, mapB;
-    if (!make_map(&mapA, A, M, K, lda) || !make_map(&mapB, B, N, K, ldb)) return 0;
+// C = alpha op(A) op(B) (+beta C)(+bias) on the tensor cores for the three operand orders the model uses:
+//   NT  C = A B^T      (forward projections)                 both operands already K-contiguous
+//   NN  C = A B        (data gradients: dX = dA W_x, dh = dVh W_V)      B transposed by the split pre-pass
+//   TN  C += A^T B     (weight gradients, K = B*L)                      both transposed by the split pre-pass
+// Small products stay on the exact-fp32 SIMT kernel (launch-bound anyway); `force` (test hook) lifts the size threshold.
+int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+                float beta, float* C, int ldc, const float* bias, bool* handled, bool force) {
+    using namespace tc;
+    *handled = false;
+    if (!tc_enabled() && !force) return 0;
+    if (K < 1 || M < 1 || N < 1) return 0;
+    if (tA && tB) return 0;
+    if (!force && (double)M * N * K < 5e8) return 0;
+    if (!get_encode()) return 0;
+
+    Sched sc;
+    sc.tiles_m = ceil_div(M, BM); sc.tiles_n = ceil_div(N, BN); sc.nk = ceil_div(K, BK);
+    sc.G = ctx->sm_count;
+    const int Tt = sc.tiles_m * sc.tiles_n;
+    sc.R = Tt / sc.G; sc.rem = Tt - sc.R * sc.G;
+    // tail: cut the left-over tiles along K into >= MIN_SHARE-slab shares; if that gives no more CTAs than tiles, or C
+    // cannot take atomic partial sums (beta other than 0 / 1), the tail is an ordinary partial round of whole tiles
+    const long long U = (long long)sc.rem * sc.nk;
+    sc.Gp = (int)(U / MIN_SHARE < sc.G ? U / MIN_SHARE : sc.G);
+    if (sc.Gp <= sc.rem || (beta != 0.f && beta != 1.f) || !env_int("S2S_TC_TAIL", 1)) sc.Gp = sc.rem;
+    const bool atomics = sc.Gp > sc.rem;
+
+    TcOp a, b;
+    S2S_TRY(tc_prepare(ctx, A, M, K, lda, tA, &a));                       // tA: A is [K, M]
+    S2S_TRY(tc_prepare(ctx, B, N, K, ldb, !tB, &b));                      // !tB: B is [K, N]
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if (!make_map(&mAh, a.hi, M, K, a.ld_hi, BM) || !make_map(&mAl, a.lo, M, K, a.ld_lo, BM) ||
+        !make_map(&mBh, b.hi, N, K, b.ld_hi, BN) || !make_map(&mBl, b.lo, N, K, b.ld_lo, BN))
+        return fail("gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", M, N, K);
     static bool attr = false;
     if (!attr) {
-        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
+        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr = true;
     }
+    if (atomics && beta == 0.f) {
+        zero_tiles_kernel<<<sc.rem, 256, 0, ctx->stream>>>(C, ldc, M, N, sc.tiles_n, sc.R * sc.G);
+        S2S_LAUNCH_CHECK(ctx);
+    }
     prof_begin(ctx, S2S_PROF_GEMM);
-    dim3 grid(ceil_div(N, tc::BN), ceil_div(M, tc::BM), splitk);
-    gemm_tc_kernel<<<grid, tc::THREADS, tc::SMEM, ctx->stream>>>(mapA, mapB, M, N, K, alpha, beta, C, ldc, bias, splitk);
+    gemm_tc_kernel<<<sc.G, THREADS, SMEM, ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
     prof_end(ctx, S2S_PROF_GEMM, 2.0 * M * N * (double)K);
     S2S_LAUNCH_CHECK(ctx);
     *handled = true;

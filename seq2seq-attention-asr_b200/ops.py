@@ -175,8 +175,8 @@ def gru_step_backward(ctx, W, x, hprev, gates, dhn, dW=None):
     return dx, dhp, dW
 
 
-def dropout_mask(ctx, shape, p, seed=0):
-    m = ctx.new(*shape)
+def dropout_mask(ctx, shape, p, seed=0, out=None):
+    m = ctx.new(*shape) if out is None else out
     check(ctx.lib.s2s_dropout_mask(ctx.h, p, seed, m.numel(), _f(m)))
     return m
 
@@ -285,9 +285,10 @@ def weightnoise_sample(ctx, w, sigma, eps=None, seed=0):
     return out
 
 
-def awn_sample(ctx, weight, eps=None, seed=0):
+def awn_sample(ctx, weight, eps=None, seed=0, out=None):
     n = weight.numel() // 2
-    out = ctx.new(n)
+    if out is None:
+        out = ctx.new(n)
     check(ctx.lib.s2s_awn_sample(ctx.h, _f(weight), _f(eps), seed, n, _f(out)))
     return out
 
@@ -298,8 +299,8 @@ def awn_forward(ctx, weight, lam, nll):
     return float(L.value)
 
 
-def awn_accgrad(ctx, weight, g, lam):
-    gw = torch.empty_like(weight)
+def awn_accgrad(ctx, weight, g, lam, out=None):
+    gw = torch.empty_like(weight) if out is None else out
     check(ctx.lib.s2s_awn_accgrad(ctx.h, _f(weight), _f(g), g.numel(), lam, _f(gw)))
     return gw
 
