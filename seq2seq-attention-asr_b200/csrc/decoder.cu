@@ -42,20 +42,22 @@ struct DenseEpi {
     const float* gates_n = nullptr; const float* su_n = nullptr;   // gates / {s,u} of the step being prepared (EPI_BWD_DS)
 };
 
+// Loads of activations go through L2 (ld.global.cg): in the fused chain kernel below they may have been written
+// earlier in the same launch by another CTA, and L1 is not coherent across SMs.
 __device__ __forceinline__ void dense_epilogue(const DenseEpi& e, int b, int n, float v) {
     if (e.mode == EPI_LINEAR) {
         if (e.bias) v += e.bias[n];
-        if (e.add) v += e.add[(size_t)b * e.ld_add + n];
+        if (e.add) v += __ldcg(e.add + (size_t)b * e.ld_add + n);
         e.out[(size_t)b * e.ld_out + n] = v;
         if (e.out2 && n >= e.n2_start) e.out2[(size_t)b * e.ld_out2 + n - e.n2_start] = v;
     } else if (e.mode == EPI_GRU_ZR) {
         const float g = sigmoid_acc(v);                                // GRU.lua:23-24
         e.gates[(size_t)b * e.ld_gates + n] = g;
-        if (n >= e.ST) e.rh_out[(size_t)b * e.ld_rh + n - e.ST] = g * e.sprev[(size_t)b * e.ld_sprev + n - e.ST];   // GRU.lua:25
+        if (n >= e.ST) e.rh_out[(size_t)b * e.ld_rh + n - e.ST] = g * __ldcg(e.sprev + (size_t)b * e.ld_sprev + n - e.ST);   // GRU.lua:25
     } else if (e.mode == EPI_GRU_H) {
         const float hc = tanh_acc(v);                                  // GRU.lua:26
-        const float z = e.gates[(size_t)b * e.ld_gates + n];
-        const float sp = e.sprev[(size_t)b * e.ld_sprev + n];
+        const float z = __ldcg(e.gates + (size_t)b * e.ld_gates + n);
+        const float sp = __ldcg(e.sprev + (size_t)b * e.ld_sprev + n);
         const float s = (1.f - z) * sp + z * hc;                       // GRU.lua:27-30
         e.gates[(size_t)b * e.ld_gates + 2 * e.ST + n] = hc;
         e.s_out[(size_t)b * e.ld_s + n] = s;
@@ -63,16 +65,16 @@ __device__ __forceinline__ void dense_epilogue(const DenseEpi& e, int b, int n, 
     } else if (e.mode == EPI_BWD_DRHU) {
         // v = (dah . G_h)[n]: n < ST -> d(r*s_{t-1}); n >= ST -> the candidate gate's share of du
         if (n < e.ST) {
-            const float r = e.gates[(size_t)b * e.ld_gates + e.ST + n], sp = e.sprev[(size_t)b * e.ld_sprev + n];
+            const float r = __ldcg(e.gates + (size_t)b * e.ld_gates + e.ST + n), sp = __ldcg(e.sprev + (size_t)b * e.ld_sprev + n);
             e.dA[(size_t)b * e.ld_dA + e.ST + n] = v * sp * r * (1.f - r);     // dar
-            e.dsu[(size_t)b * 2 * e.ST + n] += v * r;
+            e.dsu[(size_t)b * 2 * e.ST + n] = __ldcg(e.dsu + (size_t)b * 2 * e.ST + n) + v * r;
         } else {
             e.dsu[(size_t)b * 2 * e.ST + n] = v;
         }
     } else {   // EPI_BWD_DS: v = (dq . W_s)[n]; ds_{t-1} complete -> elementwise GRU backward of step t-1
-        const float ds = v + e.dsu[(size_t)b * 2 * e.ST + n] + e.dsc[(size_t)b * e.ld_dsc + n];
-        const float z = e.gates_n[(size_t)b * e.ld_gates + n], hc = e.gates_n[(size_t)b * e.ld_gates + 2 * e.ST + n];
-        const float sp = e.su_n[(size_t)b * e.ld_sprev + n];
+        const float ds = v + __ldcg(e.dsu + (size_t)b * 2 * e.ST + n) + __ldcg(e.dsc + (size_t)b * e.ld_dsc + n);
+        const float z = __ldcg(e.gates_n + (size_t)b * e.ld_gates + n), hc = __ldcg(e.gates_n + (size_t)b * e.ld_gates + 2 * e.ST + n);
+        const float sp = __ldcg(e.su_n + (size_t)b * e.ld_sprev + n);
         e.dA[(size_t)b * e.ld_dA + 2 * e.ST + n] = ds * z * (1.f - hc * hc);        // dah
         e.dA[(size_t)b * e.ld_dA + n] = ds * (hc - sp) * z * (1.f - z);            // daz
         e.dsu[(size_t)b * 2 * e.ST + n] = ds * (1.f - z);
@@ -154,6 +156,171 @@ static int dense_small(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, 
     else DS_LAUNCH(32);
 #undef DS_LAUNCH
     prof_end(ctx, S2S_PROF_DENSE_SMALL, 4.0 * ((double)N * K + (double)B * K + (double)B * N));
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// =================================================================================================
+// dense_chain: up to four DEPENDENT dense_small products in ONE launch.
+// Between two attention steps the decoder runs a chain of tiny products on the B minibatch rows
+//   forward :  u_t -> {z, r} -> h~ / s_t -> q_{t+1}
+//   backward:  [ds_{t} / GRU elementwise] -> d{r*s, u} -> d{s, u} -> dc_t
+// each of which needs the complete result of the previous one.  As separate launches each link costs a
+// launch + drain (~5.5 us for ~0.5 us of work).  Here a grid of CH_G co-resident CTAs (cooperative launch)
+// runs all links back to back: every CTA owns N/CH_G output columns of every link, stages those weight rows
+// for ALL links in shared memory up front, and the links are separated by a grid-wide barrier (one atomic
+// arrive + a generation word to spin on; ~1 us) instead of a kernel boundary.
+// =================================================================================================
+constexpr int CH_G = 128;          // CTAs (<= SM count: all co-resident)
+constexpr int CH_KS4 = 16;         // K <= 512
+constexpr int CH_NTMAX = 8;
+constexpr int CH_MAXPH = 4;
+struct ChainPhase {
+    const float* X; int64_t ldx; int K; const float* W; int ldw; int N; int NT; int ws_off4;   // ws_off4: float4 offset of this phase's rows
+    DenseEpi e;
+};
+struct ChainParams {
+    int nph, B;
+    unsigned* bar;                 // {arrival count, generation}
+    ChainPhase ph[CH_MAXPH];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all CTAs of the (cooperative) grid; gen is the caller's copy of the generation word, read before its first arrival
+__device__ __forceinline__ void chain_grid_barrier(unsigned* bar, unsigned& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned old = atomicAdd(&bar[0], 1u);
+        if (old == gridDim.x - 1) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(&bar[1], 1u);
+        } else {
+            const long long t0 = clock64();
+            while (ld_acquire_u32(&bar[1]) == gen) {
+                if (clock64() - t0 > 2000000000ll) __trap();     // a lost CTA must not hang the GPU
+            }
+        }
+        gen++;
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+dense_chain_kernel(const __grid_constant__ ChainParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float4* ws4 = reinterpret_cast<float4*>(sm);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int ws_total4 = 0;
+#pragma unroll
+    for (int ip = 0; ip < CH_MAXPH; ip++) {
+        if (ip < p.nph) {
+            const ChainPhase& ph = p.ph[ip];
+            const int KP4 = 8 * ((ph.K + 31) / 32);
+            const int n0 = blockIdx.x * ph.NT;
+            for (int idx = tid; idx < ph.NT * KP4; idx += 256) {
+                const int c = idx / KP4, k4 = idx - c * KP4, n = n0 + c;
+                ws4[ph.ws_off4 + idx] = (n < ph.N && k4 * 4 < ph.K) ? ldg4_any(ph.W + (size_t)n * ph.ldw + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            ws_total4 = ph.ws_off4 + ph.NT * KP4;
+        }
+    }
+    float* part = sm + (size_t)ws_total4 * 4;      // [8][CH_NTMAX][32]
+    unsigned gen = 0;
+    if (tid == 0) gen = ld_acquire_u32(&p.bar[1]);
+    __syncthreads();
+#pragma unroll
+    for (int ip = 0; ip < CH_MAXPH; ip++) {
+        if (ip >= p.nph) break;
+        if (ip > 0) chain_grid_barrier(p.bar, gen);
+        const ChainPhase& ph = p.ph[ip];
+        const int NT = ph.NT, K = ph.K, ks4 = (K + 31) / 32, KP4 = 8 * ks4;
+        const int n0 = blockIdx.x * NT;
+        if (n0 >= ph.N) continue;                 // no columns of this link for this CTA (it still joins the barriers)
+        for (int b0 = 0; b0 < p.B; b0 += 32) {
+            const int b = b0 + lane;
+            float4 x[CH_KS4];
+#pragma unroll
+            for (int i = 0; i < CH_KS4; i++) {
+                const int k = (warp * ks4 + i) * 4;
+                x[i] = (i < ks4 && b < p.B && k < K) ? __ldcg(reinterpret_cast<const float4*>(ph.X + (size_t)b * ph.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+            for (int c = 0; c < NT; c++) {
+                const float4* wr = ws4 + ph.ws_off4 + c * KP4 + warp * ks4;
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < CH_KS4; i++) {
+                    if (i < ks4) {
+                        const float4 w4 = wr[i];
+                        if (i & 1) { a1 = fmaf(w4.x, x[i].x, a1); a1 = fmaf(w4.y, x[i].y, a1); a1 = fmaf(w4.z, x[i].z, a1); a1 = fmaf(w4.w, x[i].w, a1); }
+                        else { a0 = fmaf(w4.x, x[i].x, a0); a0 = fmaf(w4.y, x[i].y, a0); a0 = fmaf(w4.z, x[i].z, a0); a0 = fmaf(w4.w, x[i].w, a0); }
+                    }
+                }
+                part[(warp * CH_NTMAX + c) * 32 + lane] = a0 + a1;
+            }
+            __syncthreads();
+            for (int o = tid; o < NT * 32; o += 256) {
+                const int c = o >> 5, bb = o & 31, n = n0 + c, br = b0 + bb;
+                float v = 0.f;
+#pragma unroll
+                for (int wg = 0; wg < 8; wg++) v += part[(wg * CH_NTMAX + c) * 32 + bb];
+                if (n < ph.N && br < p.B) dense_epilogue(ph.e, br, n, v);
+            }
+        }
+    }
+}
+
+struct ChainLink { const float* X; int64_t ldx; int K; const float* W; int ldw; int N; DenseEpi e; };
+
+static bool dense_chain_supported(const ChainLink* l, int n) {
+    static int enabled = -1;
+    // Measured on B200 (cfg2, CUDA-graph replay): one chain launch = 29.5 us against 4 x 5.5 us for the separate
+    // launches -- a kernel boundary inside a graph costs about as much as the grid barrier (~2 us), and with 128 CTAs
+    // each link re-reads the whole X from L2.  Kept as an opt-in (S2S_CHAIN=1) for experiments; default off.
+    if (enabled < 0) { const char* e = getenv("S2S_CHAIN"); enabled = e ? atoi(e) : 0; }
+    if (!enabled || n < 1 || n > CH_MAXPH) return false;
+    for (int i = 0; i < n; i++) {
+        if (l[i].K % 4 || l[i].K > 32 * CH_KS4 || l[i].ldx % 4 || (reinterpret_cast<uintptr_t>(l[i].X) & 15)) return false;
+        if (ceil_div(l[i].N, CH_G) > CH_NTMAX) return false;
+    }
+    return true;
+}
+// the links must be supported (dense_chain_supported); same per-link summation order as dense_small
+static int dense_chain(s2s_ctx* ctx, const ChainLink* l, int n, int B) {
+    ChainParams p = {};
+    p.nph = n; p.B = B; p.bar = ctx->counters + 4000;
+    int off4 = 0;
+    double work = 0;
+    for (int i = 0; i < n; i++) {
+        ChainPhase& ph = p.ph[i];
+        ph.X = l[i].X; ph.ldx = l[i].ldx; ph.K = l[i].K; ph.W = l[i].W; ph.ldw = l[i].ldw; ph.N = l[i].N; ph.e = l[i].e;
+        ph.NT = ceil_div(l[i].N, CH_G); ph.ws_off4 = off4;
+        off4 += ph.NT * 8 * ceil_div(l[i].K, 32);
+        work += 4.0 * ((double)l[i].N * l[i].K + (double)B * l[i].K + (double)B * l[i].N);
+    }
+    const size_t smem = (size_t)off4 * 16 + (size_t)8 * CH_NTMAX * 32 * 4;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        S2S_CUDA(cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CH_G); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // co-residency of all CTAs is required by the barrier
+    static int coop = -1;
+    if (coop < 0) { const char* e = getenv("S2S_CHAIN_COOP"); coop = e ? atoi(e) : 1; }
+    cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
+    prof_begin(ctx, S2S_PROF_DENSE_SMALL);
+    S2S_CUDA(cudaLaunchKernelEx(&cfg, dense_chain_kernel, p));
+    prof_end(ctx, S2S_PROF_DENSE_SMALL, work);
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -353,13 +520,11 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
     S2S_CUDA(cudaMemsetAsync(d.su, 0, BT * 2 * ST * sizeof(float), st));     // s_0 = 0 (Recurrent.lua:112)
 
     const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST;
+    {   // q_0 = W_s s_0 + b_s with s_0 = 0   (Attention.lua:65-67, Recurrent.lua:112)
+        DenseEpi e; e.bias = d.qbias; e.out = d.q; e.ld_out = (int64_t)T * S;
+        S2S_TRY(dense_small(ctx, zeros, ST, B, ST, P + Y.Ws.off, ST, S, e));
+    }
     for (int t = 0; t < T; t++) {
-        const float* sprev = t ? d.sc + (size_t)(t - 1) * (ST + A) : zeros;
-        const int64_t ldsp = t ? ldsc : ST;
-        {   // q_t = W_s s_{t-1} + b_s   (Attention.lua:65-67)
-            DenseEpi e; e.bias = d.qbias; e.out = d.q + (size_t)t * S; e.ld_out = (int64_t)T * S;
-            S2S_TRY(dense_small(ctx, sprev, ldsp, B, ST, P + Y.Ws.off, ST, S, e));
-        }
         {   // attention step (Attention.lua:95-135)
             AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw;
             loc.alpha_prev = t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr; loc.ld_aprev = (int64_t)T * Lmax;
@@ -367,23 +532,39 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
                                   d.alpha + (size_t)t * Lmax, (int64_t)T * Lmax, d.sc + (size_t)t * (ST + A) + ST, ldsc,
                                   d.pen + t, T, lambda, t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr, (int64_t)T * Lmax, tlens, t));
         }
+        // the dependent chain up to the next attention step: u_t -> {z, r} -> s_t -> q_{t+1}
+        ChainLink L[4];
+        int nl = 0;
         {   // u_t = (W_j[:, :ST] W_c) c_t + uy_t   (Attention.lua:150-151) -> second halves of {s,u} and {r*s,u}
-            DenseEpi e; e.add = uy + (size_t)t * ST; e.ld_add = (int64_t)T * ST;
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.add = uy + (size_t)t * ST; e.ld_add = (int64_t)T * ST;
             e.out = d.su + (size_t)t * 2 * ST + ST; e.ld_out = ldsu;
             e.out2 = d.rhu + (size_t)t * 2 * ST + ST; e.ld_out2 = ldsu; e.n2_start = 0;
-            S2S_TRY(dense_small(ctx, d.sc + (size_t)t * (ST + A) + ST, ldsc, B, A, d.Wjc, A, ST, e));
+            k.X = d.sc + (size_t)t * (ST + A) + ST; k.ldx = ldsc; k.K = A; k.W = d.Wjc; k.ldw = A; k.N = ST;
         }
         {   // z, r = sigmoid(G_{z,r} {s_{t-1}, u})   (GRU.lua:22-24) ; r * s_{t-1}  (:25)
-            DenseEpi e; e.mode = EPI_GRU_ZR; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.mode = EPI_GRU_ZR; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
             e.sprev = d.su + (size_t)t * 2 * ST; e.ld_sprev = ldsu; e.rh_out = d.rhu + (size_t)t * 2 * ST; e.ld_rh = ldsu;
-            S2S_TRY(dense_small(ctx, d.su + (size_t)t * 2 * ST, ldsu, B, 2 * ST, P + Y.Gz.off, 2 * ST, 2 * ST, e));
+            k.X = d.su + (size_t)t * 2 * ST; k.ldx = ldsu; k.K = 2 * ST; k.W = P + Y.Gz.off; k.ldw = 2 * ST; k.N = 2 * ST;
         }
         {   // h~ = tanh(G_h {r*s_{t-1}, u}) ; s_t = (1-z) s_{t-1} + z h~   (GRU.lua:26-30)
-            DenseEpi e; e.mode = EPI_GRU_H; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.mode = EPI_GRU_H; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
             e.sprev = d.su + (size_t)t * 2 * ST; e.ld_sprev = ldsu;
             e.s_out = d.sc + (size_t)t * (ST + A); e.ld_s = ldsc;
             e.s_out2 = t + 1 < T ? d.su + (size_t)(t + 1) * 2 * ST : nullptr; e.ld_s2 = ldsu;
-            S2S_TRY(dense_small(ctx, d.rhu + (size_t)t * 2 * ST, ldsu, B, 2 * ST, P + Y.Gh.off, 2 * ST, ST, e));
+            k.X = d.rhu + (size_t)t * 2 * ST; k.ldx = ldsu; k.K = 2 * ST; k.W = P + Y.Gh.off; k.ldw = 2 * ST; k.N = ST;
+        }
+        if (t + 1 < T) {   // q_{t+1} = W_s s_t + b_s   (Attention.lua:65-67)
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.bias = d.qbias; e.out = d.q + (size_t)(t + 1) * S; e.ld_out = (int64_t)T * S;
+            k.X = d.sc + (size_t)t * (ST + A); k.ldx = ldsc; k.K = ST; k.W = P + Y.Ws.off; k.ldw = ST; k.N = S;
+        }
+        if (dense_chain_supported(L, nl)) {
+            S2S_TRY(dense_chain(ctx, L, nl, B));
+        } else {
+            for (int i = 0; i < nl; i++) S2S_TRY(dense_small(ctx, L[i].X, L[i].ldx, B, L[i].K, L[i].W, L[i].ldw, L[i].N, L[i].e));
         }
     }
 
@@ -483,19 +664,38 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     S2S_LAUNCH_CHECK(ctx);
     for (int t = T - 1; t >= 0; t--) {
         const int cur = (T - 1 - t) & 1;
+        // the dependent chain between two attention backward steps:
+        //   [ds_t and the elementwise GRU backward of step t] -> d{r*s, u} -> d{s_{t-1}, u} -> dc_t
+        ChainLink L[4];
+        int nl = 0;
+        if (t < T - 1) {   // ds_t = dsu[:, :ST] + dq_{t+1} . W_s + ds_mlp[t], then the elementwise GRU backward of step t
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.mode = EPI_BWD_DS; e.ST = ST; e.dsu = dsu; e.dsc = dsc + (size_t)t * (ST + A); e.ld_dsc = ldsc;
+            e.gates_n = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg; e.su_n = d.su + (size_t)t * 2 * ST; e.ld_sprev = ldsu;
+            e.dA = dA + (size_t)t * 3 * ST; e.ld_dA = lddA;
+            k.X = dq_all + (size_t)(t + 1) * S; k.ldx = (int64_t)T * S; k.K = S; k.W = WsT; k.ldw = S; k.N = ST;
+        }
         {   // d{r*s, u} = dah . G_h ; dar ; dsu[:, :ST] += d(r*s) r
-            DenseEpi e; e.mode = EPI_BWD_DRHU; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.mode = EPI_BWD_DRHU; e.ST = ST; e.gates = d.gates + (size_t)t * 3 * ST; e.ld_gates = ldg;
             e.sprev = d.su + (size_t)t * 2 * ST; e.ld_sprev = ldsu; e.dA = dA + (size_t)t * 3 * ST; e.ld_dA = lddA; e.dsu = dsu;
-            S2S_TRY(dense_small(ctx, dA + (size_t)t * 3 * ST + 2 * ST, lddA, B, ST, GhT, ST, 2 * ST, e));
+            k.X = dA + (size_t)t * 3 * ST + 2 * ST; k.ldx = lddA; k.K = ST; k.W = GhT; k.ldw = ST; k.N = 2 * ST;
         }
         {   // d{s_{t-1}, u} += {daz, dar} . G_{z,r}
-            DenseEpi e; e.add = dsu; e.ld_add = 2 * ST; e.out = dsu; e.ld_out = 2 * ST;
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.add = dsu; e.ld_add = 2 * ST; e.out = dsu; e.ld_out = 2 * ST;
             e.out2 = du_all + (size_t)t * ST; e.ld_out2 = (int64_t)T * ST; e.n2_start = ST;
-            S2S_TRY(dense_small(ctx, dA + (size_t)t * 3 * ST, lddA, B, 2 * ST, GzrT, 2 * ST, 2 * ST, e));
+            k.X = dA + (size_t)t * 3 * ST; k.ldx = lddA; k.K = 2 * ST; k.W = GzrT; k.ldw = 2 * ST; k.N = 2 * ST;
         }
         {   // dc_t = dc_mlp + du . (W_j[:, :ST] W_c)
-            DenseEpi e; e.add = dsc + (size_t)t * (ST + A) + ST; e.ld_add = ldsc; e.out = dc_all + (size_t)t * A; e.ld_out = (int64_t)T * A;
-            S2S_TRY(dense_small(ctx, dsu + ST, 2 * ST, B, ST, WjcT, ST, A, e));
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.add = dsc + (size_t)t * (ST + A) + ST; e.ld_add = ldsc; e.out = dc_all + (size_t)t * A; e.ld_out = (int64_t)T * A;
+            k.X = dsu + ST; k.ldx = 2 * ST; k.K = ST; k.W = WjcT; k.ldw = ST; k.N = A;
+        }
+        if (dense_chain_supported(L, nl)) {
+            S2S_TRY(dense_chain(ctx, L, nl, B));
+        } else {
+            for (int i = 0; i < nl; i++) S2S_TRY(dense_small(ctx, L[i].X, L[i].ldx, B, L[i].K, L[i].W, L[i].ldw, L[i].N, L[i].e));
         }
         {   // attention step backward
             AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw;
@@ -505,12 +705,6 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
                                   carry_alpha ? dac[cur] : nullptr, Lmax, d.pen + t, T, lambda,
                                   dq_all + (size_t)t * S, (int64_t)T * S, de_all + (size_t)t * Lmax, (int64_t)T * Lmax,
                                   carry_alpha ? dac[cur ^ 1] : nullptr, Lmax));
-        }
-        if (t > 0) {   // ds_{t-1} = dsu[:, :ST] + dq . W_s + ds_mlp[t-1], then the elementwise GRU backward of step t-1
-            DenseEpi e; e.mode = EPI_BWD_DS; e.ST = ST; e.dsu = dsu; e.dsc = dsc + (size_t)(t - 1) * (ST + A); e.ld_dsc = ldsc;
-            e.gates_n = d.gates + (size_t)(t - 1) * 3 * ST; e.ld_gates = ldg; e.su_n = d.su + (size_t)(t - 1) * 2 * ST; e.ld_sprev = ldsu;
-            e.dA = dA + (size_t)(t - 1) * 3 * ST; e.ld_dA = lddA;
-            S2S_TRY(dense_small(ctx, dq_all + (size_t)t * S, (int64_t)T * S, B, S, WsT, S, ST, e));
         }
     }
 
