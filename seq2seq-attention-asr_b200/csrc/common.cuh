@@ -67,6 +67,9 @@ struct GraphCache {
     int64_t launches = 0;          // kernel launches recorded in the graph
 };
 
+// prepared (hi/lo-split, K-contiguous) GEMM operands that stay valid for the duration of a TcCacheScope (gemm_tc.cu)
+struct TcCacheEntry { const float* src; int K, cols, ld; bool transposed; const float* hi; const float* lo; int ld_hi, ld_lo; };
+
 struct DecoderState;   // decoder.cu
 struct ModelState;     // model.cu
 
@@ -91,6 +94,8 @@ struct s2s_ctx {
     uint64_t rng_calls = 0;
     s2s::Prof prof;
     s2s::GraphCache graph;
+    bool tc_cache_on = false;
+    std::vector<s2s::TcCacheEntry> tc_cache;
 };
 
 namespace s2s {
@@ -135,6 +140,15 @@ struct GemmBatch { int count = 1; int64_t sA = 0, sB = 0, sC = 0; };
 int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* B, int ldb, float beta, float* C, int ldc, const float* bias = nullptr,
              GemmBatch batch = GemmBatch(), int splitk = 1, int impl = 0);
+
+// While a scope is alive, operands prepared for the tcgen05 GEMM are remembered and reused by later gemm_f32 calls that
+// read the same matrix (or a column block of it, in the transposed forms).  The caller guarantees that the source
+// matrices are not modified inside the scope.
+struct TcCacheScope {
+    s2s_ctx* ctx;
+    explicit TcCacheScope(s2s_ctx* c) : ctx(c) { c->tc_cache.clear(); c->tc_cache_on = true; }
+    ~TcCacheScope() { ctx->tc_cache.clear(); ctx->tc_cache_on = false; }
+};
 
 // column sums: out[n] += sum_m X[m, n]   (bias gradients)
 int colsum_add(s2s_ctx* ctx, const float* X, int64_t M, int N, int ldx, float* out);

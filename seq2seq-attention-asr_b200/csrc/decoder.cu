@@ -81,6 +81,65 @@ __device__ __forceinline__ void dense_epilogue(const DenseEpi& e, int b, int n, 
     }
 }
 
+// The epilogue's activation operands, fetched BEFORE the dot products so their L2 round trip overlaps the main loop
+// (each launch of the decoder chain is a handful of dependent L2 latencies long; this removes one of them).
+struct EpiOps { float a, b, c, d, e; };
+__device__ __forceinline__ EpiOps dense_prefetch(const DenseEpi& e, int b, int n) {
+    EpiOps o = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (e.mode == EPI_LINEAR) {
+        if (e.add) o.a = __ldcg(e.add + (size_t)b * e.ld_add + n);
+    } else if (e.mode == EPI_GRU_ZR) {
+        if (n >= e.ST) o.a = __ldcg(e.sprev + (size_t)b * e.ld_sprev + n - e.ST);
+    } else if (e.mode == EPI_GRU_H) {
+        o.a = __ldcg(e.gates + (size_t)b * e.ld_gates + n);
+        o.b = __ldcg(e.sprev + (size_t)b * e.ld_sprev + n);
+    } else if (e.mode == EPI_BWD_DRHU) {
+        if (n < e.ST) {
+            o.a = __ldcg(e.gates + (size_t)b * e.ld_gates + e.ST + n);
+            o.b = __ldcg(e.sprev + (size_t)b * e.ld_sprev + n);
+            o.c = __ldcg(e.dsu + (size_t)b * 2 * e.ST + n);
+        }
+    } else {
+        o.a = __ldcg(e.dsu + (size_t)b * 2 * e.ST + n);
+        o.b = __ldcg(e.dsc + (size_t)b * e.ld_dsc + n);
+        o.c = __ldcg(e.gates_n + (size_t)b * e.ld_gates + n);
+        o.d = __ldcg(e.gates_n + (size_t)b * e.ld_gates + 2 * e.ST + n);
+        o.e = __ldcg(e.su_n + (size_t)b * e.ld_sprev + n);
+    }
+    return o;
+}
+__device__ __forceinline__ void dense_epilogue_pf(const DenseEpi& e, int b, int n, float v, const EpiOps& o) {
+    if (e.mode == EPI_LINEAR) {
+        if (e.bias) v += e.bias[n];
+        v += o.a;
+        e.out[(size_t)b * e.ld_out + n] = v;
+        if (e.out2 && n >= e.n2_start) e.out2[(size_t)b * e.ld_out2 + n - e.n2_start] = v;
+    } else if (e.mode == EPI_GRU_ZR) {
+        const float g = sigmoid_acc(v);                                // GRU.lua:23-24
+        e.gates[(size_t)b * e.ld_gates + n] = g;
+        if (n >= e.ST) e.rh_out[(size_t)b * e.ld_rh + n - e.ST] = g * o.a;   // GRU.lua:25
+    } else if (e.mode == EPI_GRU_H) {
+        const float hc = tanh_acc(v);                                  // GRU.lua:26
+        const float s = (1.f - o.a) * o.b + o.a * hc;                  // GRU.lua:27-30
+        e.gates[(size_t)b * e.ld_gates + 2 * e.ST + n] = hc;
+        e.s_out[(size_t)b * e.ld_s + n] = s;
+        if (e.s_out2) e.s_out2[(size_t)b * e.ld_s2 + n] = s;
+    } else if (e.mode == EPI_BWD_DRHU) {
+        if (n < e.ST) {
+            e.dA[(size_t)b * e.ld_dA + e.ST + n] = v * o.b * o.a * (1.f - o.a);     // dar
+            e.dsu[(size_t)b * 2 * e.ST + n] = o.c + v * o.a;
+        } else {
+            e.dsu[(size_t)b * 2 * e.ST + n] = v;
+        }
+    } else {
+        const float ds = v + o.a + o.b;
+        const float z = o.c, hc = o.d, sp = o.e;
+        e.dA[(size_t)b * e.ld_dA + 2 * e.ST + n] = ds * z * (1.f - hc * hc);        // dah
+        e.dA[(size_t)b * e.ld_dA + n] = ds * (hc - sp) * z * (1.f - z);            // daz
+        e.dsu[(size_t)b * 2 * e.ST + n] = ds * (1.f - z);
+    }
+}
+
 template <int KS4>
 __global__ void __launch_bounds__(256)
 dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const float* __restrict__ W, int ldw, int N, int NT, const DenseEpi e) {
@@ -105,6 +164,11 @@ dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const
             const int k = (warp * KS4 + i) * 4;
             x[i] = (b < B && k < K) ? __ldcg(reinterpret_cast<const float4*>(X + (size_t)b * ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        // this thread's epilogue output (NT * 32 <= 256: at most one per thread) and its operands
+        const int oc = tid >> 5, on = n0 + oc, obr = b0 + lane;
+        const bool ovalid = oc < NT && on < N && obr < B;
+        EpiOps ops = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (ovalid) ops = dense_prefetch(e, obr, on);
         __syncthreads();
 #pragma unroll 2
         for (int c = 0; c < NT; c++) {
@@ -119,12 +183,11 @@ dense_small_kernel(const float* __restrict__ X, int64_t ldx, int B, int K, const
             part[(warp * NT + c) * 32 + lane] = a0 + a1;
         }
         __syncthreads();
-        for (int o = tid; o < NT * 32; o += 256) {
-            const int c = o >> 5, bb = o & 31, n = n0 + c, br = b0 + bb;
+        if (ovalid) {
             float v = 0.f;
 #pragma unroll
-            for (int wg = 0; wg < 8; wg++) v += part[(wg * NT + c) * 32 + bb];
-            if (n < N && br < B) dense_epilogue(e, br, n, v);
+            for (int wg = 0; wg < 8; wg++) v += part[(wg * NT + oc) * 32 + lane];
+            dense_epilogue_pf(e, obr, on, v, ops);
         }
     }
 }

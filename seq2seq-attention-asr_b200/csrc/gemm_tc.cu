@@ -390,6 +390,18 @@ struct TcOp { const float* hi; const float* lo; int ld_hi, ld_lo; };
 // src: K-contiguous [rows, K] (transposed == false) or [K, rows] (transposed == true), pitch ld
 static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, bool transposed, TcOp* op) {
     const int Kp = (K + 3) & ~3;
+    if (ctx->tc_cache_on) {
+        for (const TcCacheEntry& c : ctx->tc_cache) {
+            if (c.transposed != transposed || c.K != K || c.ld != ld) continue;
+            const ptrdiff_t off = src - c.src;
+            // transposed: a block of `rows` source columns starting `off` columns into the cached matrix
+            if (transposed ? (off >= 0 && off + rows <= c.cols) : (off == 0 && rows <= c.cols)) {
+                const size_t r0 = transposed ? (size_t)off : 0;
+                op->hi = c.hi + r0 * c.ld_hi; op->lo = c.lo + r0 * c.ld_lo; op->ld_hi = c.ld_hi; op->ld_lo = c.ld_lo;
+                return 0;
+            }
+        }
+    }
     float *hi = nullptr, *lo;
     S2S_ALLOC(lo, ctx->arena, float, (size_t)rows * Kp);
     const bool raw = !transposed && tc_rawhi() && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
@@ -405,6 +417,7 @@ static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, b
     S2S_LAUNCH_CHECK(ctx);
     op->hi = raw ? src : hi; op->ld_hi = raw ? ld : Kp;
     op->lo = lo; op->ld_lo = Kp;
+    if (ctx->tc_cache_on) ctx->tc_cache.push_back(TcCacheEntry{src, K, rows, ld, transposed, op->hi, op->lo, op->ld_hi, op->ld_lo});
     return 0;
 }
 

@@ -727,6 +727,7 @@ int gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, in
     else S2S_TRY(launch_cluster<256>(ctx, true, p));
     // time-batched gradients (K = B*L) instead of one rank-1 update per frame (LinearZeroBias.lua:67-74)
     const int sk = 8;
+    TcCacheScope tc_scope(ctx);        // dA^T is prepared once by the x-column product and reused by the h-column blocks
     // x columns of all gates, both directions:  dW[:, H:] += dA^T X
     S2S_TRY(gemm_f32(ctx, true, false, N, Din, BL, 1.f, dA, N, x, ldx, 1.f, dW + H, ldw, nullptr, GemmBatch(), sk));
     for (int d = 0; d < ndir; d++) {
