@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--out", default=None)
 ap.add_argument("--noflush", action="store_true")
+ap.add_argument("--kf", type=int, default=0, help="location filter size (0 = content attention; 10 = the K=16, k=10 configuration folded to UW[10, S])")
 args = ap.parse_args()
 S = A = 512
 try:
@@ -35,9 +36,18 @@ for B in Bs:
         dc = torch.randn(B, A, device="cuda")
         alpha = torch.empty(B, L, device="cuda"); c = torch.empty(B, A, device="cuda")
         dq = torch.empty(B, S, device="cuda"); de = torch.empty(B, L, device="cuda")
+        if args.kf:
+            uw = torch.randn(args.kf, S, device="cuda") * 0.1
+            aprev = torch.softmax(torch.randn(B, L, device="cuda"), dim=1)
+            dap = torch.empty(B, L, device="cuda")
+            fwd = lambda: s2s.attn_step_forward_loc(ctx, Vh, h, q, w, uw, aprev, alpha=alpha, c=c)
+            bwd = lambda: s2s.attn_step_backward_loc(ctx, Vh, h, q, w, uw, aprev, alpha, dc, dq=dq, de=de, dalpha_prev=dap)
+        else:
+            fwd = lambda: s2s.attn_step_forward(ctx, Vh, h, q, w, alpha=alpha, c=c)
+            bwd = lambda: s2s.attn_step_backward(ctx, Vh, h, q, w, alpha, dc, dq=dq, de=de)
         for _ in range(3):
-            s2s.attn_step_forward(ctx, Vh, h, q, w, alpha=alpha, c=c)
-            s2s.attn_step_backward(ctx, Vh, h, q, w, alpha, dc, dq=dq, de=de)
+            fwd()
+            bwd()
         reps = 10
         # kernel time from the library's own CUDA events recorded around each launch on the launching
         # stream (s2s_ctx_profile): excludes the host-side ctypes marshalling of this script
@@ -45,21 +55,21 @@ for B in Bs:
         for _ in range(reps):
             if not args.noflush:
                 flush.fill_(1)
-            s2s.attn_step_forward(ctx, Vh, h, q, w, alpha=alpha, c=c)
+            fwd()
             if not args.noflush:
                 flush.fill_(2)
-            s2s.attn_step_backward(ctx, Vh, h, q, w, alpha, dc, dq=dq, de=de)
+            bwd()
         prof = ctx.profile_read()
         ctx.profile(False)
         tf, tb = prof["attn_fwd"][0], prof["attn_bwd"][0]
         tf /= reps; tb /= reps
         bytes_f = 4.0 * B * (L * S + L * A + 2 * L + S + A)
         bytes_b = 4.0 * B * (L * S + L * A + 6 * L + 2 * S + 2 * A)
-        r = dict(B=B, L=L, fwd_us=tf * 1e3, bwd_us=tb * 1e3, fwd_gbs=bytes_f / tf / 1e6, bwd_gbs=bytes_b / tb / 1e6,
+        r = dict(B=B, L=L, KF=args.kf, fwd_us=tf * 1e3, bwd_us=tb * 1e3, fwd_gbs=bytes_f / tf / 1e6, bwd_gbs=bytes_b / tb / 1e6,
                  fwd_frac=bytes_f / tf / 1e6 / peak, bwd_frac=bytes_b / tb / 1e6 / peak, mbytes=bytes_f / 1e6)
         rows.append(r)
         print(f"B={B:4d} L={L:5d} {bytes_f / 1e6:8.1f} MB  fwd {tf * 1e3:8.1f} us {r['fwd_gbs']:7.0f} GB/s ({r['fwd_frac']:.2f})   "
               f"bwd {tb * 1e3:8.1f} us {r['bwd_gbs']:7.0f} GB/s ({r['bwd_frac']:.2f})", flush=True)
         del Vh, h
 if args.out:
-    json.dump(dict(peak_gbs=peak, S=S, A=A, l2_flush=not args.noflush, rows=rows), open(args.out, "w"), indent=1)
+    json.dump(dict(peak_gbs=peak, S=S, A=A, KF=args.kf, l2_flush=not args.noflush, rows=rows), open(args.out, "w"), indent=1)

@@ -235,6 +235,15 @@ int s2s_attn_step_forward(s2s_ctx* ctx, const float* Vh, const float* h, const f
 int s2s_attn_step_backward(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w,
                            const int* lengths, int B, int Lmax, int S, int A, const float* alpha,
                            const float* dc, const float* dalpha_in, float* dq, float* de);
+/* location-aware variants (Attention.lua:75-99 with the two convolutions folded into UW [KF,S]):
+ * Z[l] = q + Vh[l] + sum_j UW[j] alpha_prev[l + j - pad_left]; the backward also returns d alpha_prev [B,Lmax] */
+int s2s_attn_step_forward_loc(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w,
+                              const int* lengths, int B, int Lmax, int S, int A, int KF, const float* uw,
+                              const float* alpha_prev, float* alpha, float* c);
+int s2s_attn_step_backward_loc(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w,
+                               const int* lengths, int B, int Lmax, int S, int A, int KF, const float* uw,
+                               const float* alpha_prev, const float* alpha, const float* dc, const float* dalpha_in,
+                               float* dq, float* de, float* dalpha_prev);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

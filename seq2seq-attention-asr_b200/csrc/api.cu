@@ -262,4 +262,29 @@ int s2s_attn_step_backward(s2s_ctx* ctx, const float* Vh, const float* h, const 
                          dq, S, de, Lmax, nullptr, 0);
 }
 
+// location-aware variants of the two hooks (cfg5 sweep with K = 16 feature maps folded into UW [KF, S]):
+// Z[l] = q + Vh[l] + sum_j UW[j] * alpha_prev[l + j - pad_left]   (Attention.lua:75-99)
+int s2s_attn_step_forward_loc(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w, const int* lengths, int B, int Lmax,
+                              int S, int A, int KF, const float* uw, const float* alpha_prev, float* alpha, float* c) {
+    S2S_REQUIRE(ctx && Vh && h && q && w && alpha && c && uw, "attn_step_forward_loc: null argument");
+    S2S_REQUIRE(KF >= 1 && KF <= 16, "attn_step_forward_loc: filter size %d out of range (1..16)", KF);
+    ctx->arena.reset();
+    AttnScratch sc;
+    S2S_TRY(attn_scratch_alloc(ctx, ctx->arena, B, Lmax, S, A, KF, false, &sc));
+    AttnLoc loc; loc.KF = KF; loc.padl = (KF % 2 == 1) ? (KF - 1) / 2 : KF / 2; loc.uw = uw; loc.alpha_prev = alpha_prev; loc.ld_aprev = Lmax;
+    return attn_step_fwd(ctx, sc, Vh, h, q, S, w, lengths, B, Lmax, S, A, loc, alpha, Lmax, c, A, nullptr, 0, 0.f, nullptr, 0);
+}
+int s2s_attn_step_backward_loc(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w, const int* lengths, int B,
+                               int Lmax, int S, int A, int KF, const float* uw, const float* alpha_prev, const float* alpha, const float* dc,
+                               const float* dalpha_in, float* dq, float* de, float* dalpha_prev) {
+    S2S_REQUIRE(ctx && Vh && h && q && w && alpha && dc && dq && de && uw && dalpha_prev, "attn_step_backward_loc: null argument");
+    S2S_REQUIRE(KF >= 1 && KF <= 16, "attn_step_backward_loc: filter size %d out of range (1..16)", KF);
+    ctx->arena.reset();
+    AttnScratch sc;
+    S2S_TRY(attn_scratch_alloc(ctx, ctx->arena, B, Lmax, S, A, KF, true, &sc));
+    AttnLoc loc; loc.KF = KF; loc.padl = (KF % 2 == 1) ? (KF - 1) / 2 : KF / 2; loc.uw = uw; loc.alpha_prev = alpha_prev; loc.ld_aprev = Lmax;
+    return attn_step_bwd(ctx, sc, Vh, h, q, S, w, lengths, B, Lmax, S, A, loc, alpha, Lmax, dc, A, dalpha_in, Lmax, nullptr, 0, 0.f,
+                         dq, S, de, Lmax, dalpha_prev, Lmax);
+}
+
 }  // extern "C"

@@ -56,8 +56,14 @@ struct AttnFwdParams {
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4fma(float s, float4 a, float4 b) { return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w)); }
 
-template <int NS, int NA, bool LOC, int RIF>
-__global__ void __launch_bounds__(ATT_THREADS, RIF == 2 ? 3 : 2)
+// packed fp32 pairs: FFMA2 (fma.rn.f32x2) does two FMAs per issue slot -- the location term is issue-bound
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+template <int NS, int NA, int LOC, int RIF>
+__global__ void __launch_bounds__(ATT_THREADS, (RIF == 2 && !LOC) ? 3 : 2)
 attn_fwd_kernel(const AttnFwdParams p) {
     constexpr int S = NS * 128, A = NA * 128;
     constexpr int GROUPS = 8 / NA;              // row groups in the context phase
@@ -65,7 +71,8 @@ attn_fwd_kernel(const AttnFwdParams p) {
     float* hs = reinterpret_cast<float*>(smem_raw);                 // [ATT_R][A]
     float* w_s = hs + ATT_R * A;                                     // [S]
     float* uw_s = w_s + S;                                           // [KF][S]        (LOC)
-    float* ap_s = uw_s + (LOC ? p.KF * S : 0);                       // [ATT_R+KF-1]   (LOC)
+    float2* ap_s = reinterpret_cast<float2*>(uw_s + (LOC ? p.KF * S : 0));   // [ATT_R+KF-1] {a, a} pairs   (LOC)
+    constexpr int KFT = LOC > 1 ? LOC : 0;                           // exact filter size known at compile time
     __shared__ float e_s[ATT_R], p_s[ATT_R];
     __shared__ __align__(16) float red[1024];
     __shared__ float scl_s[ATT_MAXCH];
@@ -112,7 +119,8 @@ attn_fwd_kernel(const AttnFwdParams p) {
     if (LOC) {
         for (int x = tid; x < ATT_R + p.KF - 1; x += ATT_THREADS) {
             int l = l0 + x - p.padl;
-            ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
+            const float a = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
+            ap_s[x] = make_float2(a, a);
         }
     }
     float4 qv[NS];
@@ -124,29 +132,75 @@ attn_fwd_kernel(const AttnFwdParams p) {
     __syncthreads();                                 // w_s (uw_s, ap_s) staged
 #pragma unroll
     for (int pr = 0; pr < 4 / RIF; pr++) {
+        if (LOC) {
+            // location term: the RIF rows of this pass share every UW load (one LDS.128 per (jj, column group) instead of
+            // one per row); alpha_{t-1} comes as broadcast {a, a} pairs so each row costs two FFMA2 per (jj, column group)
+            float acc[RIF];
 #pragma unroll
-        for (int j = 0; j < RIF; j++) {
-            const int r = warp + 8 * (RIF * pr + j);
-            if (r < nrows) {
-                float acc = 0.f;
+            for (int j = 0; j < RIF; j++) acc[j] = 0.f;
 #pragma unroll
-                for (int i = 0; i < NS; i++) {
-                    float4 z = f4add(v[j][i], qv[i]);
-                    if (LOC) {
-                        for (int jj = 0; jj < p.KF; jj++) {
-                            const float a = ap_s[r + jj];
-                            const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
-                            z = f4fma(a, u, z);
+            for (int i = 0; i < NS; i++) {
+                f2_t z[RIF][2];
+#pragma unroll
+                for (int j = 0; j < RIF; j++) {
+                    const float4 t = f4add(v[j][i], qv[i]);
+                    z[j][0] = pack2(t.x, t.y); z[j][1] = pack2(t.z, t.w);
+                }
+                if constexpr (KFT > 0) {
+#pragma unroll
+                    for (int jj = 0; jj < KFT; jj++) {
+                        const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(uw_s + jj * S + lane * 4 + i * 128);
+#pragma unroll
+                        for (int j = 0; j < RIF; j++) {
+                            const f2_t a = *reinterpret_cast<const f2_t*>(ap_s + warp + 8 * (RIF * pr + j) + jj);
+                            z[j][0] = ffma2(a, u.x, z[j][0]); z[j][1] = ffma2(a, u.y, z[j][1]);
                         }
                     }
-                    const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + i * 128);
-                    acc = fmaf(wv.x, tanh_acc(z.x), acc);
-                    acc = fmaf(wv.y, tanh_acc(z.y), acc);
-                    acc = fmaf(wv.z, tanh_acc(z.z), acc);
-                    acc = fmaf(wv.w, tanh_acc(z.w), acc);
+                } else {
+                    for (int jj = 0; jj < p.KF; jj++) {
+                        const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(uw_s + jj * S + lane * 4 + i * 128);
+#pragma unroll
+                        for (int j = 0; j < RIF; j++) {
+                            const f2_t a = *reinterpret_cast<const f2_t*>(ap_s + warp + 8 * (RIF * pr + j) + jj);
+                            z[j][0] = ffma2(a, u.x, z[j][0]); z[j][1] = ffma2(a, u.y, z[j][1]);
+                        }
+                    }
                 }
-                acc = warp_sum(acc);
-                if (lane == 0) e_s[r] = acc;
+                const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + i * 128);
+#pragma unroll
+                for (int j = 0; j < RIF; j++) {
+                    float4 t;
+                    unpack2(z[j][0], t.x, t.y); unpack2(z[j][1], t.z, t.w);
+                    acc[j] = fmaf(wv.x, tanh_acc(t.x), acc[j]);
+                    acc[j] = fmaf(wv.y, tanh_acc(t.y), acc[j]);
+                    acc[j] = fmaf(wv.z, tanh_acc(t.z), acc[j]);
+                    acc[j] = fmaf(wv.w, tanh_acc(t.w), acc[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RIF; j++) {
+                const int r = warp + 8 * (RIF * pr + j);
+                const float a = warp_sum(acc[j]);
+                if (r < nrows && lane == 0) e_s[r] = a;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RIF; j++) {
+                const int r = warp + 8 * (RIF * pr + j);
+                if (r < nrows) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < NS; i++) {
+                        const float4 z = f4add(v[j][i], qv[i]);
+                        const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + i * 128);
+                        acc = fmaf(wv.x, tanh_acc(z.x), acc);
+                        acc = fmaf(wv.y, tanh_acc(z.y), acc);
+                        acc = fmaf(wv.z, tanh_acc(z.z), acc);
+                        acc = fmaf(wv.w, tanh_acc(z.w), acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0) e_s[r] = acc;
+                }
             }
         }
         if (RIF == 2 && pr == 0) {   // second pair of rows
@@ -324,8 +378,8 @@ struct AttnBwdParams {
     int64_t ld_dq, ld_de, ld_dap;
 };
 
-template <int NS, int NA, bool LOC>
-__global__ void __launch_bounds__(ATT_THREADS, 3)
+template <int NS, int NA, int LOC>
+__global__ void __launch_bounds__(ATT_THREADS, LOC ? 2 : 3)
 attn_bwd_kernel(const AttnBwdParams p) {
     constexpr int S = NS * 128, A = NA * 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -336,7 +390,8 @@ attn_bwd_kernel(const AttnBwdParams p) {
     float* dc_s = w_s + S;                                       // [A]
     float* q_s = dc_s + A;                                       // [S]
     float* uw_s = q_s + S;                                       // [KF][S]      (LOC)
-    float* ap_s = uw_s + (LOC ? p.KF * S : 0);                   // [ATT_R+KF-1] (LOC)
+    float2* ap_s = reinterpret_cast<float2*>(uw_s + (LOC ? p.KF * S : 0));   // [ATT_R+KF-1] {a, a} pairs (LOC)
+    constexpr int KFT = LOC > 1 ? LOC : 0;
     __shared__ float dot_s[8];
     __shared__ uint64_t bar;
     __shared__ int is_last;
@@ -363,7 +418,8 @@ attn_bwd_kernel(const AttnBwdParams p) {
         for (int i = tid; i < p.KF * S; i += ATT_THREADS) uw_s[i] = p.uw[i];
         for (int x = tid; x < ATT_R + p.KF - 1; x += ATT_THREADS) {
             int l = l0 + x - p.padl;
-            ap_s[x] = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
+            const float a = (p.alpha_prev && l >= 0 && l < Lb) ? p.alpha_prev[(size_t)b * p.ld_aprev + l] : 0.f;
+            ap_s[x] = make_float2(a, a);
         }
     }
     for (int i = tid; i < S; i += ATT_THREADS) q_s[i] = p.q[(size_t)b * p.ldq + i];
@@ -379,76 +435,144 @@ attn_bwd_kernel(const AttnBwdParams p) {
     const float* vbase = p.Vh + ((size_t)b * p.Lmax + l0) * S + lane * 4;
     // Vh rows stream through registers one at a time (three CTAs per SM hide the latency); h rows come from the
     // TMA-staged tile
-    float4 vv[NS];
     __syncthreads();            // w_s / dc_s / q_s / uw_s / ap_s staged
     mbar_wait(&bar, 0);         // h tile landed
+    if constexpr (!LOC) {
+        float4 vv[NS];
 #pragma unroll 1
-    for (int j = 0; j < 4; j++) {
-        const int r = warp + 8 * j;
-        if (r >= nrows) break;
+        for (int j = 0; j < 4; j++) {
+            const int r = warp + 8 * j;
+            if (r >= nrows) break;
 #pragma unroll
-        for (int i = 0; i < NS; i++) vv[i] = ldg_stream(vbase + (size_t)r * S + i * 128);
-        const int l = l0 + r;
-        float da = 0.f;
+            for (int i = 0; i < NS; i++) vv[i] = ldg_stream(vbase + (size_t)r * S + i * 128);
+            const int l = l0 + r;
+            float da = 0.f;
 #pragma unroll
-        for (int i = 0; i < NA; i++) {
-            const float4 hv = *reinterpret_cast<const float4*>(hs + (size_t)r * A + lane * 4 + i * 128);
-            const float4 dv = *reinterpret_cast<const float4*>(dc_s + lane * 4 + i * 128);
-            da = fmaf(hv.x, dv.x, da); da = fmaf(hv.y, dv.y, da); da = fmaf(hv.z, dv.z, da); da = fmaf(hv.w, dv.w, da);
-        }
-        da = warp_sum(da);
-        if (p.dalpha_in) da += p.dalpha_in[(size_t)b * p.ld_dain + l];
-        da += pen_g * (float)(Lb - l);
-        const float a = p.alpha[(size_t)b * p.ld_alpha + l];
-        const float x = a * da;
-        dotp += x;
-        if (lane == 0) p.dalpha_s[(size_t)b * p.Lmax + l] = da;
-        float v1[LOC ? LOC_MAXKF : 1];
-        if (LOC) {
-#pragma unroll
-            for (int jj = 0; jj < LOC_MAXKF; jj++) v1[jj] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-            float4 z = f4add(vv[i], *reinterpret_cast<const float4*>(q_s + lane * 4 + i * 128));
-            if (LOC) {
-                for (int jj = 0; jj < p.KF; jj++) {
-                    const float ap = ap_s[r + jj];
-                    const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
-                    z = f4fma(ap, u, z);
-                }
+            for (int i = 0; i < NA; i++) {
+                const float4 hv = *reinterpret_cast<const float4*>(hs + (size_t)r * A + lane * 4 + i * 128);
+                const float4 dv = *reinterpret_cast<const float4*>(dc_s + lane * 4 + i * 128);
+                da = fmaf(hv.x, dv.x, da); da = fmaf(hv.y, dv.y, da); da = fmaf(hv.z, dv.z, da); da = fmaf(hv.w, dv.w, da);
             }
-            const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + i * 128);
-            float4 g;
-            { float t = tanh_acc(z.x); g.x = wv.x * (1.f - t * t); }
-            { float t = tanh_acc(z.y); g.y = wv.y * (1.f - t * t); }
-            { float t = tanh_acc(z.z); g.z = wv.z * (1.f - t * t); }
-            { float t = tanh_acc(z.w); g.w = wv.w * (1.f - t * t); }
-            P1[i] = f4fma(x, g, P1[i]);
-            P2[i] = f4fma(a, g, P2[i]);
-            if (LOC) {
+            da = warp_sum(da);
+            if (p.dalpha_in) da += p.dalpha_in[(size_t)b * p.ld_dain + l];
+            da += pen_g * (float)(Lb - l);
+            const float a = p.alpha[(size_t)b * p.ld_alpha + l];
+            const float x = a * da;
+            dotp += x;
+            if (lane == 0) p.dalpha_s[(size_t)b * p.Lmax + l] = da;
 #pragma unroll
-                for (int jj = 0; jj < LOC_MAXKF; jj++) {
-                    if (jj < p.KF) {
+            for (int i = 0; i < NS; i++) {
+                const float4 z = f4add(vv[i], *reinterpret_cast<const float4*>(q_s + lane * 4 + i * 128));
+                const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + i * 128);
+                float4 g;
+                { float t = tanh_acc(z.x); g.x = wv.x * (1.f - t * t); }
+                { float t = tanh_acc(z.y); g.y = wv.y * (1.f - t * t); }
+                { float t = tanh_acc(z.z); g.z = wv.z * (1.f - t * t); }
+                { float t = tanh_acc(z.w); g.w = wv.w * (1.f - t * t); }
+                P1[i] = f4fma(x, g, P1[i]);
+                P2[i] = f4fma(a, g, P2[i]);
+            }
+        }
+    } else {
+        // location path: two rows per pass share every UW load (the kernel is shared-memory-bandwidth bound otherwise:
+        // 2 KF LDS.128 per row and column group); alpha_{t-1} windows and the V1 partial sums live in registers
+        float4 vv[2][NS];
+#pragma unroll 1
+        for (int j = 0; j < 4; j += 2) {
+            const int r0 = warp + 8 * j;
+            if (r0 >= nrows) break;
+            const int r1 = r0 + 8;
+            const bool ok1 = r1 < nrows;
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                vv[0][i] = ldg_stream(vbase + (size_t)r0 * S + i * 128);
+                vv[1][i] = ok1 ? ldg_stream(vbase + (size_t)r1 * S + i * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float a2[2], x2[2];
+            constexpr int NV = KFT > 0 ? KFT : LOC_MAXKF;
+            float v1a[2][NV];                                  // V1 partial sums of the two rows
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int r = k ? r1 : r0;
+                const bool ok = k ? ok1 : true;
+                const int l = l0 + r;
+                float da = 0.f;
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < NA; i++) {
+                        const float4 hv = *reinterpret_cast<const float4*>(hs + (size_t)r * A + lane * 4 + i * 128);
+                        const float4 dv = *reinterpret_cast<const float4*>(dc_s + lane * 4 + i * 128);
+                        da = fmaf(hv.x, dv.x, da); da = fmaf(hv.y, dv.y, da); da = fmaf(hv.z, dv.z, da); da = fmaf(hv.w, dv.w, da);
+                    }
+                }
+                da = warp_sum(da);
+                float a = 0.f;
+                if (ok) {
+                    if (p.dalpha_in) da += p.dalpha_in[(size_t)b * p.ld_dain + l];
+                    da += pen_g * (float)(Lb - l);
+                    a = p.alpha[(size_t)b * p.ld_alpha + l];
+                    if (lane == 0) p.dalpha_s[(size_t)b * p.Lmax + l] = da;
+                } else {
+                    da = 0.f;
+                }
+                a2[k] = a; x2[k] = a * da;
+                dotp += x2[k];
+#pragma unroll
+                for (int jj = 0; jj < NV; jj++) v1a[k][jj] = 0.f;
+            }
+            const int r1c = ok1 ? r1 : r0;                     // a missing second row recomputes the first (its results are dropped)
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                const float4 qv = *reinterpret_cast<const float4*>(q_s + lane * 4 + i * 128);
+                float4 z0 = f4add(vv[0][i], qv), z1 = f4add(vv[1][i], qv);
+#pragma unroll
+                for (int jj = 0; jj < NV; jj++) {
+                    if (KFT > 0 || jj < p.KF) {
                         const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
-                        v1[jj] += g.x * u.x + g.y * u.y + g.z * u.z + g.w * u.w;
+                        z0 = f4fma(ap_s[r0 + jj].x, u, z0);             // broadcast loads: one wavefront each
+                        z1 = f4fma(ap_s[r1c + jj].x, u, z1);
+                    }
+                }
+                const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + i * 128);
+                float4 g0, g1;
+                { float t = tanh_acc(z0.x); g0.x = wv.x * (1.f - t * t); }
+                { float t = tanh_acc(z0.y); g0.y = wv.y * (1.f - t * t); }
+                { float t = tanh_acc(z0.z); g0.z = wv.z * (1.f - t * t); }
+                { float t = tanh_acc(z0.w); g0.w = wv.w * (1.f - t * t); }
+                { float t = tanh_acc(z1.x); g1.x = wv.x * (1.f - t * t); }
+                { float t = tanh_acc(z1.y); g1.y = wv.y * (1.f - t * t); }
+                { float t = tanh_acc(z1.z); g1.z = wv.z * (1.f - t * t); }
+                { float t = tanh_acc(z1.w); g1.w = wv.w * (1.f - t * t); }
+                P1[i] = f4fma(x2[0], g0, P1[i]); P1[i] = f4fma(x2[1], g1, P1[i]);
+                P2[i] = f4fma(a2[0], g0, P2[i]); P2[i] = f4fma(a2[1], g1, P2[i]);
+#pragma unroll
+                for (int jj = 0; jj < NV; jj++) {
+                    if (KFT > 0 || jj < p.KF) {
+                        const float4 u = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + i * 128);
+                        v1a[0][jj] = fmaf(g0.x, u.x, fmaf(g0.y, u.y, fmaf(g0.z, u.z, fmaf(g0.w, u.w, v1a[0][jj]))));
+                        v1a[1][jj] = fmaf(g1.x, u.x, fmaf(g1.y, u.y, fmaf(g1.z, u.z, fmaf(g1.w, u.w, v1a[1][jj]))));
                     }
                 }
             }
-        }
-        if (LOC) {
-            // 16 values over 32 lanes: transpose-reduce; lane (x & 15) ends with value index (x & 15)
 #pragma unroll
-            for (int s = 8; s >= 1; s >>= 1) {
+            for (int k = 0; k < 2; k++) {
+                float v1[LOC_MAXKF];
 #pragma unroll
-                for (int i = 0; i < s; i++) {
-                    const float send = (lane & s) ? v1[i] : v1[i + s];
-                    const float keep = (lane & s) ? v1[i + s] : v1[i];
-                    v1[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                for (int jj = 0; jj < LOC_MAXKF; jj++) v1[jj] = jj < NV ? v1a[k][jj < NV ? jj : 0] : 0.f;
+                // 16 values over 32 lanes: transpose-reduce; lane (x & 15) ends with value index (x & 15)
+#pragma unroll
+                for (int s = 8; s >= 1; s >>= 1) {
+#pragma unroll
+                    for (int i = 0; i < s; i++) {
+                        const float send = (lane & s) ? v1[i] : v1[i + s];
+                        const float keep = (lane & s) ? v1[i + s] : v1[i];
+                        v1[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                    }
                 }
+                v1[0] += __shfl_xor_sync(0xffffffffu, v1[0], 16);
+                const int r = k ? r1 : r0;
+                if ((k == 0 || ok1) && lane < p.KF) p.V1[((size_t)b * p.Lmax + l0 + r) * p.KF + lane] = v1[0];
             }
-            v1[0] += __shfl_xor_sync(0xffffffffu, v1[0], 16);
-            if (lane < p.KF) p.V1[((size_t)b * p.Lmax + l) * p.KF + lane] = v1[0];
         }
     }
 
@@ -647,9 +771,9 @@ int attn_scratch_alloc(s2s_ctx* ctx, Arena& arena, int B, int Lmax, int S, int A
     return 0;
 }
 
-template <int NS, int NA, bool LOC, int RIF>
+template <int NS, int NA, int LOC, int RIF>
 static int launch_fwd_rif(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
-    size_t smem = (size_t)ATT_R * NA * 128 * 4 + (size_t)NS * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
+    size_t smem = (size_t)ATT_R * NA * 128 * 4 + (size_t)NS * 128 * 4 + (LOC ? ((size_t)KF * NS * 128 + 2 * (ATT_R + KF)) * 4 : 0);
     static bool attr_set = false;   // per instantiation
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {
@@ -667,15 +791,17 @@ static int launch_fwd_rif(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
 }
 // Small grids (the L2-resident decoder step) are latency-bound: three light CTAs per SM.  Large grids are
 // bandwidth-bound: two CTAs per SM with all four rows of every warp in flight (measured 84-91% of HBM peak).
-template <int NS, int NA, bool LOC>
+template <int NS, int NA, int LOC>
 static int launch_fwd(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
-    if ((long)p.nch * p.B >= 6L * ctx->sm_count) return launch_fwd_rif<NS, NA, LOC, 4>(ctx, p, KF);
+    if constexpr (!LOC) {   // the location path keeps alpha_{t-1} windows in registers: two rows in flight only
+        if ((long)p.nch * p.B >= 6L * ctx->sm_count) return launch_fwd_rif<NS, NA, LOC, 4>(ctx, p, KF);
+    }
     return launch_fwd_rif<NS, NA, LOC, 2>(ctx, p, KF);
 }
-template <int NS, int NA, bool LOC>
+template <int NS, int NA, int LOC>
 static int launch_bwd(s2s_ctx* ctx, const AttnBwdParams& p, int KF) {
     size_t hsz = (size_t)ATT_R * NA * 128 > (size_t)16 * NS * 128 ? (size_t)ATT_R * NA * 128 : (size_t)16 * NS * 128;
-    size_t smem = (hsz + (size_t)2 * NS * 128 + (size_t)NA * 128) * 4 + (LOC ? ((size_t)KF * NS * 128 + ATT_R + KF) * 4 : 0);
+    size_t smem = (hsz + (size_t)2 * NS * 128 + (size_t)NA * 128) * 4 + (LOC ? ((size_t)KF * NS * 128 + 2 * (ATT_R + KF)) * 4 : 0);
     static bool attr_set = false;
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {
@@ -721,8 +847,9 @@ int attn_step_fwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const fl
     p.E = sc.E; p.part_ms = sc.part_ms; p.part_c = sc.part_c; p.counters = sc.counters;
     p.alpha = alpha; p.c = c; p.pen = pen; p.ld_alpha = ld_alpha; p.ld_c = ld_c; p.ld_pen = ld_pen; p.lambda = lambda;
     p.app = app; p.ld_app = ld_app; p.tlens = tlens; p.tstep = tstep;
-    if (loc.KF > 0) ATT_DISPATCH(launch_fwd, true, ctx, p, loc.KF);
-    else ATT_DISPATCH(launch_fwd, false, ctx, p, 0);
+    if (loc.KF == 10) ATT_DISPATCH(launch_fwd, 10, ctx, p, loc.KF);      // the reference's default filter size (Attention.lua:17)
+    else if (loc.KF > 0) ATT_DISPATCH(launch_fwd, 1, ctx, p, loc.KF);
+    else ATT_DISPATCH(launch_fwd, 0, ctx, p, 0);
 }
 
 int attn_step_bwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const float* h, const float* q, int64_t ldq, const float* w,
@@ -738,8 +865,9 @@ int attn_step_bwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const fl
     p.ld_alpha = ld_alpha; p.ld_dc = ld_dc; p.ld_dain = ld_dain; p.ld_pen = ld_pen; p.lambda = lambda;
     p.dalpha_s = sc.dalpha; p.part_P = sc.part_P; p.part_dot = sc.part_dot; p.V1 = sc.V1; p.counters = sc.counters;
     p.dq = dq; p.de = de; p.dalpha_prev = dalpha_prev; p.ld_dq = ld_dq; p.ld_de = ld_de; p.ld_dap = ld_dap;
-    if (loc.KF > 0) ATT_DISPATCH(launch_bwd, true, ctx, p, loc.KF);
-    else ATT_DISPATCH(launch_bwd, false, ctx, p, 0);
+    if (loc.KF == 10) ATT_DISPATCH(launch_bwd, 10, ctx, p, loc.KF);
+    else if (loc.KF > 0) ATT_DISPATCH(launch_bwd, 1, ctx, p, loc.KF);
+    else ATT_DISPATCH(launch_bwd, 0, ctx, p, 0);
 }
 
 int attn_dvh(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* de_all, const float* w, const int* lengths,

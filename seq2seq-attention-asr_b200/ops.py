@@ -348,6 +348,27 @@ def attn_step_backward(ctx, Vh, h, q, w, alpha, dc, dalpha_in=None, lengths=None
     return dq, de
 
 
+def attn_step_forward_loc(ctx, Vh, h, q, w, uw, alpha_prev, lengths=None, alpha=None, c=None):
+    B, L, S = Vh.shape
+    A = h.shape[2]
+    alpha = ctx.new(B, L) if alpha is None else alpha
+    c = ctx.new(B, A) if c is None else c
+    check(ctx.lib.s2s_attn_step_forward_loc(ctx.h, _f(Vh), _f(h), _f(q), _f(w), _i(lengths), B, L, S, A, uw.shape[0], _f(uw), _f(alpha_prev),
+                                            _f(alpha), _f(c)))
+    return alpha, c
+
+
+def attn_step_backward_loc(ctx, Vh, h, q, w, uw, alpha_prev, alpha, dc, dalpha_in=None, lengths=None, dq=None, de=None, dalpha_prev=None):
+    B, L, S = Vh.shape
+    A = h.shape[2]
+    dq = ctx.new(B, S) if dq is None else dq
+    de = ctx.new(B, L) if de is None else de
+    dalpha_prev = ctx.new(B, L) if dalpha_prev is None else dalpha_prev
+    check(ctx.lib.s2s_attn_step_backward_loc(ctx.h, _f(Vh), _f(h), _f(q), _f(w), _i(lengths), B, L, S, A, uw.shape[0], _f(uw), _f(alpha_prev),
+                                             _f(alpha), _f(dc), _f(dalpha_in), _f(dq), _f(de), _f(dalpha_prev)))
+    return dq, de, dalpha_prev
+
+
 # ---- parameter initialisation (module:reset(stdv) rules) -------------------------------------------------
 def segment_names(cfg):
     """Names of the flat-layout segments in order (see csrc/core.cu make_layout)."""

@@ -137,3 +137,43 @@ def test_lstm_seq_matches_oracle(s2s, gctx, orc64, H, Din, B, L, peep, reverse):
     dx, dP = s2s.lstm_seq_backward(gctx, Pd, xd, y, save, dev(dy, torch.float32), H, peepholes=peep, lengths=ld, reverse=reverse)
     assert rel_err(dx.cpu().numpy(), dx_ref) < TOL
     assert rel_err(dP.cpu().numpy(), dP_ref) < TOL
+
+
+@pytest.mark.parametrize("B,L,S,A,KF", [(3, 70, 512, 512, 10), (2, 300, 512, 512, 10), (4, 41, 256, 512, 5)])
+def test_attn_step_location_aware(s2s, gctx, B, L, S, A, KF):
+    # Z[l] = q + Vh[l] + sum_j UW[j] alpha_prev[l + j - pad_left]   (Attention.lua:75-99, both convolutions folded)
+    rng = np.random.default_rng(B + L + KF)
+    Vh = rng.standard_normal((B, L, S)); h = rng.standard_normal((B, L, A)); q = rng.standard_normal((B, S))
+    w = rng.standard_normal(S) / np.sqrt(S); uw = rng.standard_normal((KF, S))
+    lengths = rng.integers(max(KF, L // 3), L + 1, B).astype(np.int32); lengths[0] = L
+    ap = rng.uniform(0, 1, (B, L))
+    for b in range(B):
+        ap[b, lengths[b]:] = 0; ap[b] /= ap[b].sum()
+    padl = (KF - 1) // 2 if KF % 2 else KF // 2
+    dc = rng.standard_normal((B, A)); dain = rng.standard_normal((B, L)) * 0.1
+    alpha_ref = np.zeros((B, L)); c_ref = np.zeros((B, A)); dq_ref = np.zeros((B, S)); de_ref = np.zeros((B, L)); dap_ref = np.zeros((B, L))
+    for b in range(B):
+        Lb = lengths[b]
+        app = np.zeros(Lb + KF); app[padl:padl + Lb] = ap[b, :Lb]          # zero padding outside [0, L_b)
+        loc = sum(np.outer(app[j:j + Lb], uw[j]) for j in range(KF))
+        th = np.tanh(q[b][None, :] + Vh[b, :Lb] + loc)
+        e = th @ w
+        p = np.exp(e - e.max()); p /= p.sum()
+        alpha_ref[b, :Lb] = p; c_ref[b] = p @ h[b, :Lb]
+        da = h[b, :Lb] @ dc[b] + dain[b, :Lb]
+        de = p * (da - p @ da)
+        dZ = de[:, None] * w[None, :] * (1 - th * th)
+        dq_ref[b] = dZ.sum(0); de_ref[b, :Lb] = de
+        g = dZ @ uw.T                                                       # [Lb, KF]: d app[l + j] += g[l, j]
+        dapp = np.zeros(Lb + KF)
+        for j in range(KF):
+            dapp[j:j + Lb] += g[:, j]
+        dap_ref[b, :Lb] = dapp[padl:padl + Lb]
+    f32 = lambda x: dev(x, torch.float32)
+    dl = dev(lengths)
+    alpha, c = s2s.attn_step_forward_loc(gctx, f32(Vh), f32(h), f32(q), f32(w), f32(uw), f32(ap), lengths=dl)
+    assert rel_err(alpha.cpu().numpy(), alpha_ref) < TOL and rel_err(c.cpu().numpy(), c_ref) < TOL
+    dq_g, de_g, dap_g = s2s.attn_step_backward_loc(gctx, f32(Vh), f32(h), f32(q), f32(w), f32(uw), f32(ap), f32(alpha_ref), f32(dc),
+                                                   dalpha_in=f32(dain), lengths=dl, dalpha_prev=torch.zeros(B, L, device="cuda"))
+    assert rel_err(de_g.cpu().numpy(), de_ref) < TOL and rel_err(dq_g.cpu().numpy(), dq_ref) < TOL
+    assert rel_err(dap_g.cpu().numpy(), dap_ref) < TOL
