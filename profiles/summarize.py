@@ -14,7 +14,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__block_size", "launch__cluster_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum",
-        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
         "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
         "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_selected",
@@ -65,7 +66,7 @@ def full(tag, reps):
     json.dump(out, open(f"profiles/{tag}.json", "w"), indent=1)
     with open(f"profiles/{tag}.md", "w") as f:
         f.write(f"# ncu --set full summaries ({tag}); one row per captured launch\n\n")
-        f.write("| kernel | time | DRAM read | DRAM write | regs | grid x block | warps active % | DRAM thr % | SM thr % | top stalls (pc samples) |\n|---|---:|---:|---:|---:|---|---:|---:|---:|---|\n")
+        f.write("| kernel | time | DRAM read | DRAM write | regs | grid x block | warps active % | DRAM thr % | SM thr % | tensor pipe % (active / elapsed) | top stalls (pc samples) |\n|---|---:|---:|---:|---:|---|---:|---:|---:|---|---|\n")
         for d in out:
             def g(k, dflt=0.0):
                 return d.get(k, dflt)
@@ -78,7 +79,8 @@ def full(tag, reps):
             f.write(f"| `{d['kernel']}` | {t:.1f} us | {to_bytes('dram__bytes_read.sum') / 1e6:.2f} MB | {to_bytes('dram__bytes_write.sum') / 1e6:.2f} MB | "
                     f"{int(g('launch__registers_per_thread'))} | {int(g('launch__grid_size'))} x {int(g('launch__block_size'))} | "
                     f"{g('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
-                    f"{g('sm__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {top} |\n")
+                    f"{g('sm__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+                    f"{g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} / {g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):.1f} | {top} |\n")
     print(open(f"profiles/{tag}.md").read())
 
 

@@ -48,6 +48,7 @@ struct Sched {
     int R;                        // full rounds: tiles [0, R*G) are done whole, tile i*G + g by CTA g
     int rem;                      // tiles left for the stream-K tail
     int Gp;                       // CTAs that take a share of the tail
+    int dbg;                      // timing experiments (S2S_TC_DBG): 1 = no MMAs (TMA stream only), 2 = no TMA (MMA issue only)
 };
 struct Span { int tm, tn, kb0, kb1; };
 
@@ -170,6 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                     const int s = it % STAGES, ph = it / STAGES;
                     if (ph > 0) mbar_wait_bounded(&empty[s], (ph - 1) & 1);
                     unsigned char* st = base + (size_t)s * STAGE_BYTES;
+                    if (sched.dbg == 2) { mbar_arrive(&full[s]); continue; }
                     mbar_expect_tx(&full[s], STAGE_BYTES);
                     tma_load_2d(st, &mapAh, kb * BK, m0, &full[s]);
                     tma_load_2d(st + A_BYTES, &mapAl, kb * BK, m0, &full[s]);
@@ -195,6 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                     const uint32_t sa = smem_u32(base + (size_t)s * STAGE_BYTES);
                     const uint64_t dAh = make_desc(sa), dAl = make_desc(sa + A_BYTES);
                     const uint64_t dBh = make_desc(sa + 2 * A_BYTES), dBl = make_desc(sa + 2 * A_BYTES + B_BYTES);
+                    if (sched.dbg != 1)
 #pragma unroll
                     for (int k = 0; k < BK / 8; k++) {
                         const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);            // 32 bytes per K = 8 step inside the swizzle row
@@ -439,6 +442,7 @@ int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha
     Sched sc;
     sc.tiles_m = ceil_div(M, BM); sc.tiles_n = ceil_div(N, BN); sc.nk = ceil_div(K, BK);
     sc.G = ctx->sm_count;
+    sc.dbg = env_int("S2S_TC_DBG", 0);
     const int Tt = sc.tiles_m * sc.tiles_n;
     sc.R = Tt / sc.G; sc.rem = Tt - sc.R * sc.G;
     // tail: cut the left-over tiles along K into >= MIN_SHARE-slab shares; if that gives no more CTAs than tiles, or C
