@@ -1,5 +1,6 @@
 // lstm_seq.cu -- nn.RNN(nn.LSTM(diminput, dimoutput, peepholes), reverse) over whole utterances
-// (LSTM.lua:6-136, RNN.lua:120-201): first CUDA path (correct, time-batched where possible, not yet persistent).
+// (LSTM.lua:6-136, RNN.lua:120-201).  Without peepholes and for H in {128, 256} the recurrence runs in the persistent
+// cluster kernels of lstm_cluster.cu; the general path below (any H <= 256, full-matrix peepholes) launches per frame.
 //
 // Reference step (LSTM.lua:25-58): every gate is Linear(in->out)(x) + Linear(out->out)(h_prev) [+ Linear(out->out)(c)],
 // each Linear WITH bias; peepholes are FULL matrices on prev_c (input, forget gates) and next_c (output gate):
@@ -18,6 +19,10 @@ namespace s2s {
 int dense_small_linear(s2s_ctx* ctx, const float* X, int64_t ldx, int B, int K, const float* W, int ldw, int N, const float* bias,
                        const float* add, int64_t ld_add, float* out, int64_t ld_out);
 int zero_tail_rows(s2s_ctx* ctx, float* x, const int* lengths, int B, int Lmax, int W);
+int lstm_cluster_forward(s2s_ctx* ctx, const float* Whp, const float* xp, const int* lengths, int B, int Lmax, int H, int reverse,
+                         float* y, float* cseq, float* acts, bool* handled);
+int lstm_cluster_backward(s2s_ctx* ctx, const float* Whp, const int* lengths, int B, int Lmax, int H, int reverse, const float* y,
+                          const float* cseq, const float* acts, const float* dy, float* dA, float* hprev, float* cprev, bool* handled);
 
 struct LstmLayout {
     int in, H, peep;
@@ -188,6 +193,11 @@ int lstm_seq_forward(s2s_ctx* ctx, const float* P, int Din, int H, int peep, int
         S2S_TRY(zero_tail_rows(ctx, cseq, lengths, B, Lmax, H));
         S2S_TRY(zero_tail_rows(ctx, acts, lengths, B, Lmax, 4 * H));
     }
+    if (!peep) {   // persistent cluster recurrence (lstm_cluster.cu)
+        bool handled = false;
+        S2S_TRY(lstm_cluster_forward(ctx, Whp, xp, lengths, B, Lmax, H, reverse, y, cseq, acts, &handled));
+        if (handled) return 0;
+    }
     const int eb = ceil_div(B * H, 256);
     for (int s = 0; s < Lmax; s++) {
         S2S_TRY(dense_small_linear(ctx, hstate, H, B, H, Whp, H, 4 * H, nullptr, nullptr, 0, pre, 4 * H));
@@ -237,8 +247,10 @@ int lstm_seq_backward(s2s_ctx* ctx, const float* P, float* dP, int Din, int H, i
     S2S_CUDA(cudaMemsetAsync(cprev, 0, (size_t)BL * H * 4, st));
     S2S_CUDA(cudaMemsetAsync(dh, 0, (size_t)B * H * 4, st));
     S2S_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * H * 4, st));
+    bool cluster_done = false;
+    if (!peep) S2S_TRY(lstm_cluster_backward(ctx, Whp, lengths, B, Lmax, H, reverse, y, cseq, acts, dy, dA, hprev, cprev, &cluster_done));
     const int eb = ceil_div(B * H, 256);
-    for (int s = Lmax - 1; s >= 0; s--) {                                           // RNN.lua:183
+    for (int s = Lmax - 1; s >= 0 && !cluster_done; s--) {                          // RNN.lua:183
         LstmBStep p = {lengths, B, Lmax, H, reverse, s, peep, y, cseq, acts, dy, dh, dc, dc_add, dA, hprev, cprev};
         if (peep) {
             lstm_bwd_ko<<<eb, 256, 0, st>>>(p);

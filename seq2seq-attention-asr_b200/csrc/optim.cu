@@ -181,6 +181,28 @@ __global__ void rownorm_kernel(float* __restrict__ W, int64_t rows, int64_t cols
     }
 }
 
+// every weight matrix of the model in ONE launch: a table of (offset, rows, cols, first global row) segments; warp per row
+constexpr int RN_MAXSEG = 40;
+struct RownormTable { int nseg; int64_t off[RN_MAXSEG]; int rows[RN_MAXSEG]; int cols[RN_MAXSEG]; int first[RN_MAXSEG + 1]; };
+__global__ void rownorm_multi_kernel(float* __restrict__ P, const __grid_constant__ RownormTable t, float maxval, int* __restrict__ nan_flag) {
+    const int grow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (grow >= t.first[t.nseg]) return;
+    int sg = 0;
+    while (grow >= t.first[sg + 1]) sg++;
+    const int cols = t.cols[sg];
+    float* r = P + t.off[sg] + (int64_t)(grow - t.first[sg]) * cols;
+    float ss = 0.f;
+    for (int j = lane; j < cols; j += 32) ss = fmaf(r[j], r[j], ss);
+    ss = warp_sum(ss);
+    if (ss != ss) { if (lane == 0) atomicExch(nan_flag, 1); return; }           // TrainUtils.lua:55-62
+    const float norm = sqrtf(ss) + 1e-8f;
+    if (norm >= maxval) {
+        const float div = norm / maxval;
+        for (int j = lane; j < cols; j += 32) r[j] = r[j] / div;
+    }
+}
+
 static int grid1d(s2s_ctx* ctx, int64_t n, int per) {
     int64_t b = (n + per - 1) / per;
     int64_t cap = (int64_t)ctx->sm_count * 16;
@@ -298,11 +320,21 @@ int s2s_model_rownorm_constraint(s2s_ctx* ctx, const s2s_model_cfg* cfg, float* 
     S2S_ALLOC(flag, ctx->arena, int, 1);
     S2S_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
     // every module with a .weight reachable through apply2graph (TrainUtils.lua:137-184): all weight matrices
-    auto go = [&](const Seg& s) -> int { return s.rows ? rownorm_launch(ctx, P + s.off, s.rows, s.cols, maxval, flag) : 0; };
+    RownormTable t = {};
+    t.first[0] = 0;
+    auto go = [&](const Seg& s) -> int {
+        if (!s.rows) return 0;
+        S2S_REQUIRE(t.nseg < RN_MAXSEG, "model_rownorm_constraint: too many weight matrices");
+        t.off[t.nseg] = s.off; t.rows[t.nseg] = s.rows; t.cols[t.nseg] = s.cols; t.first[t.nseg + 1] = t.first[t.nseg] + s.rows;
+        t.nseg++;
+        return 0;
+    };
     for (int l = 0; l < Y.NL; l++) for (int d = 0; d < 2; d++) for (int g = 0; g < 3; g++) S2S_TRY(go(Y.enc[l][d][g]));
     S2S_TRY(go(Y.WV)); S2S_TRY(go(Y.Ws)); S2S_TRY(go(Y.WF)); S2S_TRY(go(Y.U)); S2S_TRY(go(Y.we));
     S2S_TRY(go(Y.Wy)); S2S_TRY(go(Y.Wc)); S2S_TRY(go(Y.Wj)); S2S_TRY(go(Y.Gz)); S2S_TRY(go(Y.Gr)); S2S_TRY(go(Y.Gh));
     S2S_TRY(go(Y.Wm)); S2S_TRY(go(Y.Wo));
+    rownorm_multi_kernel<<<(unsigned)ceil_div(t.first[t.nseg], 8), 256, 0, ctx->stream>>>(P, t, (float)maxval, flag);
+    S2S_LAUNCH_CHECK(ctx);
     if (nan_host) {
         S2S_CUDA(cudaMemcpyAsync(nan_host, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         S2S_CUDA(cudaStreamSynchronize(ctx->stream));

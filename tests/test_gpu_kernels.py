@@ -112,7 +112,10 @@ def test_tconv_zb_known_answer_cell(s2s, gctx):
 
 
 @pytest.mark.parametrize("H,Din,B,L,peep,reverse", [(128, 20, 4, 23, False, False), (128, 20, 4, 23, True, False), (64, 36, 5, 17, True, True),
-                                                    (256, 123, 3, 12, False, True)])
+                                                    (256, 123, 3, 12, False, True),
+                                                    # persistent cluster recurrence: groups of 2, 3 and 8 (two passes) utterances per cluster
+                                                    (128, 36, 20, 31, False, True), (128, 36, 40, 19, False, False), (128, 20, 70, 11, False, False),
+                                                    (256, 64, 20, 15, False, False), (256, 64, 33, 9, False, True)])
 def test_lstm_seq_matches_oracle(s2s, gctx, orc64, H, Din, B, L, peep, reverse):
     # nn.RNN(nn.LSTM(in, out, peepholes), reverse): LSTM.lua:6-136 (two biases per gate, full-matrix peepholes)
     rng = np.random.default_rng(H + Din + B + int(peep))
