@@ -223,6 +223,9 @@ int s2s_rownorm_constraint(s2s_ctx* ctx, float* W, int64_t rows, int64_t cols, d
 /* columnNormConstraintGraph over every weight matrix of the model (timit.lua:346-348) */
 int s2s_model_rownorm_constraint(s2s_ctx* ctx, const s2s_model_cfg* cfg, float* P, double maxval, int* nan_host);
 
+/* WagnerFischer(a, b) (utils.lua:3-27): edit distance between two host label sequences (PER / CER of decodes) */
+int s2s_edit_distance(const int* a, int na, const int* b, int nb, int* dist_host);
+
 /* ---- test hooks (not part of the reference surface) ----------------------------------------- */
 /* C = alpha * op(A) . op(B) + beta * C (+ bias[n]);  op(A) = A[M,K] (tA=0) or A[K,M]^T (tA=1);
  * op(B) = B[K,N] (tB=0) or B[N,K]^T (tB=1).  impl: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 */

@@ -95,6 +95,7 @@ def load():
         "s2s_gemm_f32": (i32, [vp, i32, i32, i32, i32, i32, i32, f32, vp, i32, vp, i32, f32, vp, i32, vp]),
         "s2s_attn_step_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
         "s2s_attn_step_backward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+        "s2s_edit_distance": (i32, [vp, i32, vp, i32, vp]),
         "s2s_attn_step_forward_loc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "s2s_attn_step_backward_loc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     }

@@ -1,5 +1,8 @@
 // api.cu -- extern "C" entry points of libs2s_b200.so (declared in include/s2s_b200.h).
 // Each wrapper validates arguments, resets the per-call scratch arena and forwards to the engine.
+#include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
 #include "attention.cuh"
 #include "common.cuh"
 #include "decoder.cuh"
@@ -208,6 +211,7 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
             std::string why = rc != 0 ? last_error() : std::string(cudaGetErrorString(e));
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
+            if (getenv("S2S_GRAPH_DBG")) fprintf(stderr, "[s2s] CUDA-graph capture of model_fwdbwd failed (%s); staying eager\n", why.c_str());
             graph_drop(ctx);
             ctx->graph.key = key; ctx->graph.nocapture = true;        // do not retry capturing this signature
             S2S_TRY(run());
@@ -260,6 +264,24 @@ int s2s_attn_step_backward(s2s_ctx* ctx, const float* Vh, const float* h, const 
     AttnLoc loc;
     return attn_step_bwd(ctx, sc, Vh, h, q, S, w, lengths, B, Lmax, S, A, loc, alpha, Lmax, dc, A, dalpha_in, Lmax, nullptr, 0, 0.f,
                          dq, S, de, Lmax, nullptr, 0);
+}
+
+// WagnerFischer(a, b) of utils.lua:3-27: Levenshtein distance between two label sequences (PER / CER scoring of decodes).
+// Host integers in, host integer out: the decodes this scores are already on the host (s2s_beam_search).
+int s2s_edit_distance(const int* a, int na, const int* b, int nb, int* dist_host) {
+    S2S_REQUIRE(dist_host && na >= 0 && nb >= 0 && (a || na == 0) && (b || nb == 0), "edit_distance: bad arguments");
+    std::vector<int> prev((size_t)na + 1), cur((size_t)na + 1);
+    for (int i = 0; i <= na; i++) prev[i] = i;
+    for (int j = 1; j <= nb; j++) {
+        cur[0] = j;
+        for (int i = 1; i <= na; i++) {
+            if (a[i - 1] == b[j - 1]) cur[i] = prev[i - 1];
+            else cur[i] = 1 + std::min(prev[i - 1], std::min(prev[i], cur[i - 1]));
+        }
+        std::swap(prev, cur);
+    }
+    *dist_host = prev[na];
+    return 0;
 }
 
 // location-aware variants of the two hooks (cfg5 sweep with K = 16 feature maps folded into UW [KF, S]):

@@ -348,6 +348,16 @@ def attn_step_backward(ctx, Vh, h, q, w, alpha, dc, dalpha_in=None, lengths=None
     return dq, de
 
 
+def edit_distance(a, b):
+    """WagnerFischer(a, b) of utils.lua:3-27 on two host label sequences."""
+    import numpy as np
+    from ._lib import load
+    a = np.ascontiguousarray(a, dtype=np.int32); b = np.ascontiguousarray(b, dtype=np.int32)
+    out = C.c_int(0)
+    check(load().s2s_edit_distance(a.ctypes.data_as(C.c_void_p), a.size, b.ctypes.data_as(C.c_void_p), b.size, C.byref(out)))
+    return int(out.value)
+
+
 def attn_step_forward_loc(ctx, Vh, h, q, w, uw, alpha_prev, lengths=None, alpha=None, c=None):
     B, L, S = Vh.shape
     A = h.shape[2]

@@ -64,3 +64,25 @@ def test_init_params_rules(s2s):
         elif cols > 1:
             fan = cfg["KF"] if name == "WF" else cols
             assert np.abs(seg).max() <= 1 / np.sqrt(fan) + 1e-7 and seg.std() > 0
+
+
+def test_edit_distance_matches_wagner_fischer():
+    # utils.lua:3-27 restated in Python; the C entry is host-only, so it runs without a GPU
+    import numpy as np
+    import s2s_b200 as s2s
+
+    def wf(a, b):
+        m, n = len(a) + 1, len(b) + 1
+        d = np.zeros((m, n), np.int64)
+        d[:, 0] = np.arange(m); d[0, :] = np.arange(n)
+        for j in range(1, n):
+            for i in range(1, m):
+                d[i, j] = d[i - 1, j - 1] if a[i - 1] == b[j - 1] else 1 + min(d[i - 1, j], d[i, j - 1], d[i - 1, j - 1])
+        return int(d[m - 1, n - 1])
+
+    rng = np.random.default_rng(0)
+    assert s2s.edit_distance([], []) == 0 and s2s.edit_distance([1, 2, 3], []) == 3 and s2s.edit_distance([], [4]) == 1
+    assert s2s.edit_distance([1, 2, 3], [1, 2, 3]) == 0 and s2s.edit_distance([1, 2, 3], [1, 3]) == 1
+    for _ in range(50):
+        a = rng.integers(0, 5, rng.integers(0, 30)); b = rng.integers(0, 5, rng.integers(0, 30))
+        assert s2s.edit_distance(a, b) == wf(list(a), list(b))
