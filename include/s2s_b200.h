@@ -128,6 +128,15 @@ int s2s_gru_step_forward(s2s_ctx* ctx, const float* W, int Din, int H, const flo
 int s2s_gru_step_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, const float* x, const float* hprev, int B,
                           const float* gates, const float* dhnext, float* dx, float* dhprev);
 
+/* ---- nn.LSTM as a single-step module (LSTM.lua:100-136): input {x, prev_h, prev_c} -> {next_h, next_c} ---------- */
+/* hprev / cprev NULL = zeros (LSTM.lua:108-109); acts [B,4H] (i | f | g | o) kept by the caller for the backward call */
+int s2s_lstm_step_forward(s2s_ctx* ctx, const float* P, int Din, int H, int peepholes, const float* x, const float* hprev,
+                          const float* cprev, int B, float* hnext, float* cnext, float* acts);
+/* dhnext, dcnext (NULL = zeros) -> dx [B,Din], dhprev, dcprev [B,H] (overwritten); dP accumulated */
+int s2s_lstm_step_backward(s2s_ctx* ctx, const float* P, float* dP, int Din, int H, int peepholes, const float* x,
+                           const float* hprev, const float* cprev, int B, const float* acts, const float* cnext,
+                           const float* dhnext, const float* dcnext, float* dx, float* dhprev, float* dcprev);
+
 /* ---- nn.RNN(nn.LSTM(in,out,peepholes), reverse) over whole utterances (LSTM.lua:6-136, RNN.lua:120-201) ---- */
 /* P: flat LSTM parameters in the order the module's parameters() yields: for gate in (i, f, g, o):
  * Wx[out,in], bx[out], Wh[out,out], bh[out], and -- with peepholes, except for g -- Wc[out,out], bc[out]

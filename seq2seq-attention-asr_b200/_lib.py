@@ -72,6 +72,8 @@ def load():
         "s2s_gru_step_forward": (i32, [vp, vp, i32, i32, vp, vp, i32, vp, vp]),
         "s2s_gru_step_backward": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp]),
         "s2s_dropout_mask": (i32, [vp, f32, u64, i64, vp]),
+        "s2s_lstm_step_forward": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
+        "s2s_lstm_step_backward": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
         "s2s_lstm_param_count": (i64, [i32, i32, i32]),
         "s2s_lstm_seq_save_floats": (i64, [i32, i32, i32]),
         "s2s_lstm_seq_forward": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp]),

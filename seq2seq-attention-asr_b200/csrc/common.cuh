@@ -221,8 +221,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// try_wait suspends the thread for a hardware-defined interval per poll; a phase that never completes (a programming
+// error in a producer) traps after ~2^26 polls instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    while (!mbar_try_wait(bar, parity)) { }
+    unsigned polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++polls > (1u << 26)) __trap();
+    }
 }
 // global -> shared bulk copy (TMA engine, 1-D): bytes multiple of 16, both addresses 16B-aligned
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {

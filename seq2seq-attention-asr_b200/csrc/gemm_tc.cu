@@ -442,14 +442,15 @@ int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha
     Sched sc;
     sc.tiles_m = ceil_div(M, BM); sc.tiles_n = ceil_div(N, BN); sc.nk = ceil_div(K, BK);
     sc.G = ctx->sm_count;
-    sc.dbg = env_int("S2S_TC_DBG", 0);
+    static const int dbg_mode = env_int("S2S_TC_DBG", 0), tail_on = env_int("S2S_TC_TAIL", 1);
+    sc.dbg = dbg_mode;
     const int Tt = sc.tiles_m * sc.tiles_n;
     sc.R = Tt / sc.G; sc.rem = Tt - sc.R * sc.G;
     // tail: cut the left-over tiles along K into >= MIN_SHARE-slab shares; if that gives no more CTAs than tiles, or C
     // cannot take atomic partial sums (beta other than 0 / 1), the tail is an ordinary partial round of whole tiles
     const long long U = (long long)sc.rem * sc.nk;
     sc.Gp = (int)(U / MIN_SHARE < sc.G ? U / MIN_SHARE : sc.G);
-    if (sc.Gp <= sc.rem || (beta != 0.f && beta != 1.f) || !env_int("S2S_TC_TAIL", 1)) sc.Gp = sc.rem;
+    if (sc.Gp <= sc.rem || (beta != 0.f && beta != 1.f) || !tail_on) sc.Gp = sc.rem;
     const bool atomics = sc.Gp > sc.rem;
 
     TcOp a, b;

@@ -154,6 +154,27 @@ class LSTM(Module):
     def parameters(self):
         return [self.weight], [self.gradWeight]
 
+    # single-step protocol (LSTM.lua:100-136): input {x, prev_h, prev_c} -> {next_h, next_c}
+    def updateOutput(self, input):
+        x = input[0]
+        hp = input[1] if len(input) > 1 else None
+        cp = input[2] if len(input) > 2 else None
+        self._batched = x.dim() == 2
+        up = (lambda t: None if t is None else (t.contiguous() if self._batched else t.contiguous().unsqueeze(0)))
+        self._x, self._hp, self._cp = up(x), up(hp), up(cp)
+        hn, cn, self._acts = ops.lstm_step_forward(self.ctx, self.weight, self._x, self.dimoutput, self._hp, self._cp, self.peepholes)
+        self._cn = cn
+        self.output = [hn, cn] if self._batched else [hn[0], cn[0]]
+        return self.output
+
+    def updateGradInput(self, input, gradOutput):
+        up = (lambda t: None if t is None else (t.contiguous() if self._batched else t.contiguous().unsqueeze(0)))
+        dhn = up(gradOutput[0]); dcn = up(gradOutput[1]) if len(gradOutput) > 1 else None
+        dx, dhp, dcp, _ = ops.lstm_step_backward(self.ctx, self.weight, self._x, self.dimoutput, self._hp, self._cp, self._acts, self._cn, dhn, dcn,
+                                                 self.peepholes, dP=self.gradWeight)
+        self.gradInput = [dx, dhp, dcp] if self._batched else [dx[0], dhp[0], dcp[0]]
+        return self.gradInput
+
 
 class RNN(Module):
     def __init__(self, ctx, recurrent, reverse=False):

@@ -181,6 +181,23 @@ def dropout_mask(ctx, shape, p, seed=0, out=None):
     return m
 
 
+def lstm_step_forward(ctx, P, x, H, hprev=None, cprev=None, peepholes=False):
+    B, Din = x.shape
+    hn = ctx.new(B, H); cn = ctx.new(B, H); acts = ctx.new(B, 4 * H)
+    check(ctx.lib.s2s_lstm_step_forward(ctx.h, _f(P), Din, H, int(peepholes), _f(x), _f(hprev), _f(cprev), B, _f(hn), _f(cn), _f(acts)))
+    return hn, cn, acts
+
+
+def lstm_step_backward(ctx, P, x, H, hprev, cprev, acts, cnext, dhn, dcn=None, peepholes=False, dP=None):
+    B, Din = x.shape
+    if dP is None:
+        dP = torch.zeros_like(P)
+    dx = ctx.new(B, Din); dhp = ctx.new(B, H); dcp = ctx.new(B, H)
+    check(ctx.lib.s2s_lstm_step_backward(ctx.h, _f(P), _f(dP), Din, H, int(peepholes), _f(x), _f(hprev), _f(cprev), B, _f(acts), _f(cnext),
+                                         _f(dhn), _f(dcn), _f(dx), _f(dhp), _f(dcp)))
+    return dx, dhp, dcp, dP
+
+
 # ---- LSTM sequence --------------------------------------------------------------------------------------
 def lstm_param_count(din, H, peepholes):
     return int(_lib.load().s2s_lstm_param_count(din, H, int(peepholes)))

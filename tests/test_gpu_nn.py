@@ -108,3 +108,33 @@ def test_dropout_mask_statistics(s2s, gctx):
     assert abs((m == 0).mean() - 0.5) < 5e-3
     m2 = s2s.dropout_mask(gctx, (1 << 20,), 0.2, seed=11).cpu().numpy()
     assert abs((m2 == 0).mean() - 0.2) < 5e-3 and abs(m2.max() - 1.25) < 1e-6
+
+
+@pytest.mark.parametrize("peep", [False, True])
+def test_lstm_single_step_module(s2s, gctx, peep):
+    # nn.LSTM stepped by hand with explicit {prev_h, prev_c} (LSTM.lua:100-136) against the float64 autograd restatement
+    from tests import torch_ref
+    nn = s2s.nn
+    rng = np.random.default_rng(11 + int(peep))
+    Din, H, B = 36, 64, 5
+    lstm = nn.LSTM(gctx, Din, H, peepholes=peep)
+    P = lstm.weight.cpu().double()
+    x = rng.standard_normal((B, Din)); hp = rng.standard_normal((B, H)) * 0.5; cp = rng.standard_normal((B, H)) * 0.5
+    dhn = rng.standard_normal((B, H)); dcn = rng.standard_normal((B, H))
+    f32 = lambda a: dev(a, torch.float32)
+    hn, cn = lstm.forward([f32(x), f32(hp), f32(cp)])
+    dx, dhp, dcp = lstm.backward([f32(x), f32(hp), f32(cp)], [f32(dhn), f32(dcn)])
+    Pt = P.clone().requires_grad_(True)
+    xt, hpt, cpt = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, hp, cp))
+    gates = torch_ref.lstm_unpack(Pt, Din, H, peep)
+    outs = [torch_ref.lstm_step(gates, xt[b], hpt[b], cpt[b]) for b in range(B)]
+    hr = torch.stack([o[0] for o in outs]); cr = torch.stack([o[1] for o in outs])
+    ((hr * torch.tensor(dhn)).sum() + (cr * torch.tensor(dcn)).sum()).backward()
+    assert rel_err(hn.cpu().numpy(), hr.detach().numpy()) < TOL and rel_err(cn.cpu().numpy(), cr.detach().numpy()) < TOL
+    assert rel_err(dx.cpu().numpy(), xt.grad.numpy()) < TOL
+    assert rel_err(dhp.cpu().numpy(), hpt.grad.numpy()) < TOL and rel_err(dcp.cpu().numpy(), cpt.grad.numpy()) < TOL
+    assert rel_err(lstm.gradWeight.cpu().numpy(), Pt.grad.numpy()) < TOL
+    # zero initial state when prev_h / prev_c are omitted (LSTM.lua:108-109)
+    h0, c0 = lstm.forward([f32(x[0])])
+    h0r, c0r = torch_ref.lstm_step(torch_ref.lstm_unpack(P, Din, H, peep), torch.tensor(x[0]), torch.zeros(H, dtype=torch.float64), torch.zeros(H, dtype=torch.float64))
+    assert rel_err(h0.cpu().numpy(), h0r.numpy()) < TOL and rel_err(c0.cpu().numpy(), c0r.numpy()) < TOL
