@@ -220,6 +220,18 @@ int s2s_awn_accgrad(s2s_ctx* ctx, const float* weight, const float* g, int64_t n
  * (Torch nn.Dropout v2 scaling); Philox counter RNG seeded by (seed, call counter). */
 int s2s_dropout_mask(s2s_ctx* ctx, float p, uint64_t seed, int64_t n, float* mask);
 
+/* ---- VGG front-end of librispeech/model_vgg.lua:23-54 (the encoder of BASELINE configs[3]) -----------------------
+ * 4 x [SpatialConvolutionMM 3x3 + ReLU] with SpatialMaxPooling(2,1,2,1) / (2,2,2,2), Transpose2 + View,
+ * 4 x [TemporalConvolution(k=1) + ReLU].  X [B,3,T,F] (planes, time, frequency) -> h [B, L, OUT], L = (T-8)/2.
+ * P: the flat encoder:parameters() order (conv1..4 {weight [nOut, nIn*9], bias}, then the four 1x1 layers {weight, bias}). */
+typedef struct s2s_vgg_cfg { int C1, C2, HID, OUT; } s2s_vgg_cfg;   /* 64, 128, 2048, 512 in model_vgg.lua */
+int64_t s2s_vgg_param_count(const s2s_vgg_cfg* cfg, int F);
+int s2s_vgg_out_len(int T);
+int s2s_vgg_forward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, const float* X, int B, int T, int F, float* h);
+/* dh [B,L,OUT] -> dP accumulated, dX [B,3,T,F] (nullable); needs the preceding s2s_vgg_forward on the same ctx */
+int s2s_vgg_backward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, float* dP, int B, int T, int F,
+                     const float* dh, float* dX);
+
 /* ---- gradient step (timit/timit.lua:291-348, TrainUtils.lua:52-104, optim.adadelta) ---------- */
 /* g /= batch ; norm ; clip to maxnorm ; g += wd*p ; g += noise_sigma*N(0,1).  The pre-clip norm is
  * written to *gradnorm_host (synchronises) unless NULL. */

@@ -15,6 +15,15 @@ HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "s2s_b200.h")
 CFG_FIELDS = ("D", "H", "NL", "S", "ST", "V", "K", "KF", "M", "MW")
 
 
+class VggCfg(C.Structure):
+    """s2s_vgg_cfg: planes of conv1-2 / conv3-4, width of the 1x1 stack, annotation depth (model_vgg.lua:24-54)"""
+    _fields_ = [(k, C.c_int) for k in ("C1", "C2", "HID", "OUT")]
+
+    @classmethod
+    def of(cls, cfg):
+        return cfg if isinstance(cfg, cls) else cls(*[int(cfg[k]) for k in ("C1", "C2", "HID", "OUT")])
+
+
 class ModelCfg(C.Structure):
     _fields_ = [(k, C.c_int) for k in CFG_FIELDS]
 
@@ -97,6 +106,10 @@ def load():
         "s2s_gemm_f32": (i32, [vp, i32, i32, i32, i32, i32, i32, f32, vp, i32, vp, i32, f32, vp, i32, vp]),
         "s2s_attn_step_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
         "s2s_attn_step_backward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+        "s2s_vgg_param_count": (i64, [vp, i32]),
+        "s2s_vgg_out_len": (i32, [i32]),
+        "s2s_vgg_forward": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+        "s2s_vgg_backward": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
         "s2s_edit_distance": (i32, [vp, i32, vp, i32, vp]),
         "s2s_attn_step_forward_loc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "s2s_attn_step_backward_loc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),

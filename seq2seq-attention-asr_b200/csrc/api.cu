@@ -26,6 +26,8 @@ static void graph_drop(s2s_ctx* ctx) {
     ctx->arena.frozen = false; ctx->persist.frozen = false;
 }
 
+namespace s2s { void vgg_state_free(s2s_ctx* ctx); }
+
 extern "C" {
 
 int s2s_ctx_destroy(s2s_ctx* ctx) {
@@ -41,6 +43,7 @@ int s2s_ctx_destroy(s2s_ctx* ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx->dec;
     delete ctx->model;
+    vgg_state_free(ctx);
     delete ctx;
     return 0;
 }

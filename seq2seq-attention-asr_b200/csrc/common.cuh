@@ -45,6 +45,9 @@ struct Arena {
     bool frozen = false;   // set while a CUDA graph that references arena memory exists
     void* alloc(size_t bytes);            // returns nullptr on failure (message in last_error)
     void reset() { for (auto& c : chunks) c.used = 0; }
+    // bump-pointer snapshot / restore: scratch of a loop iteration is handed back for the next one (same stream => ordered)
+    std::vector<size_t> mark() const { std::vector<size_t> m; for (auto& c : chunks) m.push_back(c.used); return m; }
+    void rewind(const std::vector<size_t>& m) { for (size_t i = 0; i < chunks.size(); i++) chunks[i].used = i < m.size() ? m[i] : 0; }
     void release();
     template <typename T> T* get(size_t n) { return (T*)alloc(n * sizeof(T)); }
 };
@@ -71,6 +74,7 @@ struct GraphCache {
 struct TcCacheEntry { const float* src; int K, cols, ld; bool transposed; const float* hi; const float* lo; int ld_hi, ld_lo; };
 
 struct DecoderState;   // decoder.cu
+struct VggState;       // vgg.cu
 struct ModelState;     // model.cu
 
 }  // namespace s2s
@@ -90,6 +94,7 @@ struct s2s_ctx {
     s2s::Arena persist;        // state that survives between forward and backward
     s2s::DecoderState* dec = nullptr;
     s2s::ModelState* model = nullptr;
+    s2s::VggState* vgg = nullptr;
     unsigned* counters = nullptr;   // zero-initialised device counters for last-block-done patterns
     uint64_t rng_calls = 0;
     s2s::Prof prof;

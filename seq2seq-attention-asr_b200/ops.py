@@ -365,6 +365,34 @@ def attn_step_backward(ctx, Vh, h, q, w, alpha, dc, dalpha_in=None, lengths=None
     return dq, de
 
 
+# ---- VGG front-end (librispeech/model_vgg.lua:23-54) ----------------------------------------------------------
+VGG_LIBRISPEECH = dict(C1=64, C2=128, HID=2048, OUT=512)
+
+
+def vgg_param_count(cfg, F):
+    c = _lib.VggCfg.of(cfg)
+    return int(_lib.load().s2s_vgg_param_count(C.byref(c), F))
+
+
+def vgg_forward(ctx, cfg, P, X):
+    """X [B, 3, T, F] -> annotations [B, (T-8)//2, OUT]"""
+    c = _lib.VggCfg.of(cfg)
+    B, _, T, F = X.shape
+    h = ctx.new(B, (T - 8) // 2, c.OUT)
+    check(ctx.lib.s2s_vgg_forward(ctx.h, C.byref(c), _f(P), _f(X), B, T, F, _f(h)))
+    return h
+
+
+def vgg_backward(ctx, cfg, P, X, dh, dP=None, need_dx=False):
+    c = _lib.VggCfg.of(cfg)
+    B, _, T, F = X.shape
+    if dP is None:
+        dP = torch.zeros_like(P)
+    dX = torch.empty_like(X) if need_dx else None
+    check(ctx.lib.s2s_vgg_backward(ctx.h, C.byref(c), _f(P), _f(dP), B, T, F, _f(dh), _f(dX)))
+    return dP, dX
+
+
 def edit_distance(a, b):
     """WagnerFischer(a, b) of utils.lua:3-27 on two host label sequences."""
     import numpy as np
