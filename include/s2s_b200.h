@@ -50,6 +50,9 @@ typedef struct s2s_model_cfg {
     int KF;  /* hybridAttendFilterSize (10)  :39                             */
     int M;   /* mlpDepth              (64)   :44                             */
     int MW;  /* maxout window         (7)    :56                             */
+    int MLP; /* decoder MLP stages: 0/1 = Maxout-Linear (:56-57); 2 = Maxout-Linear-Maxout-Linear
+                (librispeech/model_vgg.lua:76-80).  NL = 0 gives a decoder-only parameter vector
+                (annotations from another encoder, e.g. s2s_vgg_forward).                          */
 } s2s_model_cfg;
 
 /* flags for the loss / gradient seed (timit/timit.lua:268-281) */

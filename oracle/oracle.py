@@ -12,7 +12,8 @@ import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
 
-CFG_KEYS = ("D", "H", "NL", "S", "ST", "V", "K", "KF", "M", "MW")
+CFG_KEYS = ("D", "H", "NL", "S", "ST", "V", "K", "KF", "M", "MW", "MLP")
+CFG_DEFAULTS = {"MLP": 1}     # MLP: 1 = Maxout-Linear (TIMIT models), 2 = Maxout-Linear-Maxout-Linear (librispeech/model_vgg.lua:76-80)
 # timit/model_chorowski_baseline.lua:14-46 defaults
 CHOROWSKI_TIMIT = dict(D=123, H=256, NL=3, S=512, ST=256, V=62, K=0, KF=10, M=64, MW=7)
 
@@ -27,7 +28,7 @@ def build(force=False):
 
 
 def cfg_array(cfg):
-    return (C.c_int * len(CFG_KEYS))(*[int(cfg[k]) for k in CFG_KEYS])
+    return (C.c_int * len(CFG_KEYS))(*[int(cfg.get(k, CFG_DEFAULTS.get(k))) for k in CFG_KEYS])
 
 
 class Oracle:
@@ -258,5 +259,8 @@ def segment_names(cfg):
     names += ["WV", "bV", "Ws", "bs"]
     if cfg["K"] > 0:
         names += ["WF", "bF", "U", "bU"]
-    names += ["we", "be", "Wy", "by", "Wc", "bc", "Wj", "bj", "Gz", "Gr", "Gh", "Wm", "bm", "Wo", "bo"]
+    names += ["we", "be", "Wy", "by", "Wc", "bc", "Wj", "bj", "Gz", "Gr", "Gh", "Wm", "bm"]
+    if cfg.get("MLP", 1) == 2:                     # librispeech/model_vgg.lua:78-79
+        names += ["Wl", "bl", "Wm2", "bm2"]
+    names += ["Wo", "bo"]
     return names

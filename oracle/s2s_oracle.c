@@ -51,6 +51,8 @@ enum { CFG_D = 0,   /* inputFrameSize (123) */
        CFG_KF,      /* hybridAttendFilterSize (10) */
        CFG_M,       /* mlpDepth (64) */
        CFG_MW,      /* maxout window (7) */
+       CFG_MLP,     /* decoder MLP: 1 = Maxout-Linear (timit/model_chorowski_baseline.lua:56-57);
+                       2 = Maxout-Linear-Maxout-Linear (librispeech/model_vgg.lua:76-80) */
        CFG_N };
 
 /* Flat parameter layout (builder-defined; the Lua shim's parameters() returns tensors in this
@@ -59,9 +61,9 @@ enum { P_ENC = 0 /* enc: layer l, dir d, gate g -> P_ENC + (l*2+d)*3+g ; g: 0=z 
 #define MAXSEG 64
 typedef struct { int64_t off, rows, cols; } seg_t;
 typedef struct {
-    int D, H, NL, S, A, ST, V, K, KF, M, MW;
+    int D, H, NL, S, A, ST, V, K, KF, M, MW, MLP;
     seg_t enc[8][2][3];
-    seg_t WV, bV, Ws, bs, WF, bF, U, bU, we, be, Wy, by, Wc, bc, Wj, bj, Gz, Gr, Gh, Wm, bm, Wo, bo;
+    seg_t WV, bV, Ws, bs, WF, bF, U, bU, we, be, Wy, by, Wc, bc, Wj, bj, Gz, Gr, Gh, Wm, bm, Wl, bl, Wm2, bm2, Wo, bo;
     int64_t n;
 } layout_t;
 
@@ -71,6 +73,7 @@ static void make_layout(const int* cfg, layout_t* Y) {
     memset(Y, 0, sizeof(*Y));
     Y->D = cfg[CFG_D]; Y->H = cfg[CFG_H]; Y->NL = cfg[CFG_NL]; Y->S = cfg[CFG_S]; Y->A = 2 * Y->H;
     Y->ST = cfg[CFG_ST]; Y->V = cfg[CFG_V]; Y->K = cfg[CFG_K]; Y->KF = cfg[CFG_KF]; Y->M = cfg[CFG_M]; Y->MW = cfg[CFG_MW];
+    Y->MLP = cfg[CFG_MLP] == 2 ? 2 : 1;
     int64_t o = 0;
     for (int l = 0; l < Y->NL; l++) {
         int din = l == 0 ? Y->D : 2 * Y->H;                       /* model_chorowski_baseline.lua:22-31 */
@@ -88,7 +91,11 @@ static void make_layout(const int* cfg, layout_t* Y) {
     seg(&Y->Wj, &o, Y->ST, 2 * Y->ST); seg(&Y->bj, &o, Y->ST, 1); /* Attention.lua:151 */
     seg(&Y->Gz, &o, Y->ST, 2 * Y->ST); seg(&Y->Gr, &o, Y->ST, 2 * Y->ST); seg(&Y->Gh, &o, Y->ST, 2 * Y->ST); /* model:50 */
     seg(&Y->Wm, &o, Y->M * Y->MW, Y->ST + Y->A); seg(&Y->bm, &o, Y->M * Y->MW, 1); /* model:56, Maxout.lua:15 */
-    seg(&Y->Wo, &o, Y->V, Y->M); seg(&Y->bo, &o, Y->V, 1);        /* model:57 */
+    if (Y->MLP == 2) {                                             /* model_vgg.lua:78-79 */
+        seg(&Y->Wl, &o, Y->M, Y->M); seg(&Y->bl, &o, Y->M, 1);
+        seg(&Y->Wm2, &o, Y->M * Y->MW, Y->M); seg(&Y->bm2, &o, Y->M * Y->MW, 1);
+    }
+    seg(&Y->Wo, &o, Y->V, Y->M); seg(&Y->bo, &o, Y->V, 1);        /* model:57 / model_vgg.lua:80 */
     Y->n = o;
 }
 
@@ -101,7 +108,7 @@ EXPORT int orc_param_segments(const int* cfg, int64_t* out) {
     for (int l = 0; l < Y.NL; l++) for (int d = 0; d < 2; d++) for (int g = 0; g < 3; g++) PUT(Y.enc[l][d][g]);
     PUT(Y.WV); PUT(Y.bV); PUT(Y.Ws); PUT(Y.bs); PUT(Y.WF); PUT(Y.bF); PUT(Y.U); PUT(Y.bU); PUT(Y.we); PUT(Y.be);
     PUT(Y.Wy); PUT(Y.by); PUT(Y.Wc); PUT(Y.bc); PUT(Y.Wj); PUT(Y.bj); PUT(Y.Gz); PUT(Y.Gr); PUT(Y.Gh);
-    PUT(Y.Wm); PUT(Y.bm); PUT(Y.Wo); PUT(Y.bo);
+    PUT(Y.Wm); PUT(Y.bm); PUT(Y.Wl); PUT(Y.bl); PUT(Y.Wm2); PUT(Y.bm2); PUT(Y.Wo); PUT(Y.bo);
 #undef PUT
     return n;
 }
@@ -389,9 +396,9 @@ typedef struct {
     real *q;       /* [T,S]   ws output          */
     real *cin, *yin, *u;   /* [T,ST] each */
     real *gz, *gr, *gh;    /* [T,ST] decoder GRU gates */
-    real *mpre;    /* [T,M*MW] maxout pre-activation */
-    int  *midx;    /* [T,M]   argmax within window */
-    real *mo;      /* [T,M]   */
+    real *mpre;    /* [T,2,M*MW] maxout pre-activations (stage 1 | stage 2 when MLP == 2) */
+    int  *midx;    /* [T,2,M]   argmax within window */
+    real *mo;      /* [T,3,M]   maxout 1 | linear | maxout 2 */
     real *logp;    /* [T,V]   */
     real *F;       /* [T,L,K] location features (K>0) */
     real *pen;     /* [T] monotonic penalty value */
@@ -403,10 +410,10 @@ static dec_state* dec_alloc(const layout_t* Y, int L, int T) {
     AL(Vh, (size_t)L * Y->S); AL(alpha, (size_t)T * L); AL(s, (size_t)T * Y->ST); AL(c, (size_t)T * Y->A); AL(q, (size_t)T * Y->S);
     AL(cin, (size_t)T * Y->ST); AL(yin, (size_t)T * Y->ST); AL(u, (size_t)T * Y->ST);
     AL(gz, (size_t)T * Y->ST); AL(gr, (size_t)T * Y->ST); AL(gh, (size_t)T * Y->ST);
-    AL(mpre, (size_t)T * Y->M * Y->MW); AL(mo, (size_t)T * Y->M); AL(logp, (size_t)T * Y->V);
+    AL(mpre, (size_t)T * 2 * Y->M * Y->MW); AL(mo, (size_t)T * 3 * Y->M); AL(logp, (size_t)T * Y->V);
     AL(F, (size_t)T * L * Y->K); AL(pen, T);
 #undef AL
-    d->midx = (int*)calloc((size_t)T * Y->M, sizeof(int));
+    d->midx = (int*)calloc((size_t)T * 2 * Y->M, sizeof(int));
     return d;
 }
 static void dec_free(dec_state* d) {
@@ -473,8 +480,17 @@ static void dec_step_fwd(const layout_t* Y, const real* P, real lambda, const re
     for (int i = 0; i < M * MW; i++) mpre[i] = P[Y->bm.off + i] + dotr(P + Y->Wm.off + (size_t)i * (ST + A), sc, ST + A);
     for (int i = 0; i < M; i++) { int b = 0; for (int j = 1; j < MW; j++) if (mpre[i * MW + j] > mpre[i * MW + b]) b = j;   /* Maxout.lua:16-18 */
         midx[i] = b; mo[i] = mpre[i * MW + b]; }
+    const real* top = mo;
+    if (Y->MLP == 2) {                                             /* Linear(M,M) -> Maxout(M,M,7): model_vgg.lua:78-79 */
+        real* l1 = mo + M; real* mo2 = mo + 2 * M; real* mpre2 = mpre + M * MW; int* midx2 = midx + M;
+        for (int i = 0; i < M; i++) l1[i] = P[Y->bl.off + i] + dotr(P + Y->Wl.off + (size_t)i * M, mo, M);
+        for (int i = 0; i < M * MW; i++) mpre2[i] = P[Y->bm2.off + i] + dotr(P + Y->Wm2.off + (size_t)i * M, l1, M);
+        for (int i = 0; i < M; i++) { int b = 0; for (int j = 1; j < MW; j++) if (mpre2[i * MW + j] > mpre2[i * MW + b]) b = j;
+            midx2[i] = b; mo2[i] = mpre2[i * MW + b]; }
+        top = mo2;
+    }
     real lmx = -INFINITY;
-    for (int i = 0; i < V; i++) { logp[i] = P[Y->bo.off + i] + dotr(P + Y->Wo.off + (size_t)i * M, mo, M); if (logp[i] > lmx) lmx = logp[i]; }
+    for (int i = 0; i < V; i++) { logp[i] = P[Y->bo.off + i] + dotr(P + Y->Wo.off + (size_t)i * M, top, M); if (logp[i] > lmx) lmx = logp[i]; }
     double lse = 0; for (int i = 0; i < V; i++) lse += exp((double)(logp[i] - lmx));
     real lz = lmx + (real)log(lse);
     for (int i = 0; i < V; i++) logp[i] -= lz;
@@ -494,7 +510,7 @@ static void dec_forward(const layout_t* Y, const real* P, real lambda, const rea
                      d->alpha + (size_t)t * L, d->s + (size_t)t * ST, d->c + (size_t)t * A, d->q + (size_t)t * S,
                      d->F + (size_t)t * L * Y->K, d->cin + (size_t)t * ST, d->yin + (size_t)t * ST, d->u + (size_t)t * ST,
                      d->gz + (size_t)t * ST, d->gr + (size_t)t * ST, d->gh + (size_t)t * ST,
-                     d->mpre + (size_t)t * Y->M * Y->MW, d->midx + (size_t)t * Y->M, d->mo + (size_t)t * Y->M, d->logp + (size_t)t * Y->V,
+                     d->mpre + (size_t)t * 2 * Y->M * Y->MW, d->midx + (size_t)t * 2 * Y->M, d->mo + (size_t)t * 3 * Y->M, d->logp + (size_t)t * Y->V,
                      d->pen + t);
     }
 }
@@ -528,11 +544,22 @@ static void dec_backward(const layout_t* Y, const real* P, real* G, real lambda,
         real gs = 0; for (int i = 0; i < V; i++) gs += dlogp[(size_t)t * V + i];
         for (int i = 0; i < V; i++) dlog[i] = dlogp[(size_t)t * V + i] - (real)exp((double)d->logp[(size_t)t * V + i]) * gs;
         /* Linear M->V */
-        ger(G + Y->Wo.off, M, V, M, dlog, d->mo + (size_t)t * M); for (int i = 0; i < V; i++) G[Y->bo.off + i] += dlog[i];
+        const real* mo_t = d->mo + (size_t)t * 3 * M; const int* midx_t = d->midx + (size_t)t * 2 * M;
+        ger(G + Y->Wo.off, M, V, M, dlog, Y->MLP == 2 ? mo_t + 2 * M : mo_t); for (int i = 0; i < V; i++) G[Y->bo.off + i] += dlog[i];
         gemv_t(P + Y->Wo.off, M, V, M, dlog, dmo, 0);
+        if (Y->MLP == 2) {                                          /* Maxout 2 and Linear(M,M) backward (model_vgg.lua:78-79) */
+            memset(dm, 0, sizeof(real) * M * MW);
+            for (int i = 0; i < M; i++) dm[i * MW + midx_t[M + i]] = dmo[i];
+            ger(G + Y->Wm2.off, M, M * MW, M, dm, mo_t + M); for (int i = 0; i < M * MW; i++) G[Y->bm2.off + i] += dm[i];
+            real* dl1 = (real*)malloc(sizeof(real) * M);
+            gemv_t(P + Y->Wm2.off, M, M * MW, M, dm, dl1, 0);
+            ger(G + Y->Wl.off, M, M, M, dl1, mo_t); for (int i = 0; i < M; i++) G[Y->bl.off + i] += dl1[i];
+            gemv_t(P + Y->Wl.off, M, M, M, dl1, dmo, 0);
+            free(dl1);
+        }
         /* Maxout bwd (gradient to the arg-max unit of each window) */
         memset(dm, 0, sizeof(real) * M * MW);
-        for (int i = 0; i < M; i++) dm[i * MW + d->midx[(size_t)t * M + i]] = dmo[i];
+        for (int i = 0; i < M; i++) dm[i * MW + midx_t[i]] = dmo[i];
         memcpy(sc, st, sizeof(real) * ST); memcpy(sc + ST, ct, sizeof(real) * A);
         if (dropm) for (int i = 0; i < ST + A; i++) sc[i] *= dropm[i];
         ger(G + Y->Wm.off, ST + A, M * MW, ST + A, dm, sc); for (int i = 0; i < M * MW; i++) G[Y->bm.off + i] += dm[i];
@@ -727,7 +754,7 @@ EXPORT int orc_beam_search(const int* cfg, const real* P, const real* h, int L, 
     real *c = (real*)malloc(sizeof(real) * A), *q = (real*)malloc(sizeof(real) * S), *F = (real*)malloc(sizeof(real) * ((size_t)L * Y.K + 1));
     real *cin = (real*)malloc(sizeof(real) * ST), *yin = (real*)malloc(sizeof(real) * ST), *u = (real*)malloc(sizeof(real) * ST);
     real *gz = (real*)malloc(sizeof(real) * ST), *gr = (real*)malloc(sizeof(real) * ST), *gh = (real*)malloc(sizeof(real) * ST);
-    real *mpre = (real*)malloc(sizeof(real) * Y.M * Y.MW), *mo = (real*)malloc(sizeof(real) * Y.M); int* midx = (int*)malloc(sizeof(int) * Y.M);
+    real *mpre = (real*)malloc(sizeof(real) * 2 * Y.M * Y.MW), *mo = (real*)malloc(sizeof(real) * 3 * Y.M); int* midx = (int*)malloc(sizeof(int) * 2 * Y.M);
     real pen;
     int cap = maxlen + 2;
     beam_t* beams = (beam_t*)calloc(Kb, sizeof(beam_t)); beam_t* nxt = (beam_t*)calloc(Kb, sizeof(beam_t));

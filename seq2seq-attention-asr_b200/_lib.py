@@ -12,7 +12,8 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "libs2s_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "s2s_b200.h")
 
-CFG_FIELDS = ("D", "H", "NL", "S", "ST", "V", "K", "KF", "M", "MW")
+CFG_FIELDS = ("D", "H", "NL", "S", "ST", "V", "K", "KF", "M", "MW", "MLP")
+CFG_DEFAULTS = {"MLP": 1}
 
 
 class VggCfg(C.Structure):
@@ -29,7 +30,7 @@ class ModelCfg(C.Structure):
 
     @classmethod
     def from_dict(cls, d):
-        return cls(*[int(d[k]) for k in CFG_FIELDS])
+        return cls(*[int(d.get(k, CFG_DEFAULTS.get(k))) for k in CFG_FIELDS])
 
 
 class S2SError(RuntimeError):

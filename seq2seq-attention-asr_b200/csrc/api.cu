@@ -160,6 +160,7 @@ int s2s_model_forward(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, co
     S2S_REQUIRE(ctx && P && X && labels, "model_forward: null argument");
     Layout Y;
     S2S_TRY(make_layout(cfg, &Y));
+    S2S_REQUIRE(Y.NL > 0, "model_forward needs the GRU encoder (NL > 0); decoder-only layouts go through s2s_attention_forward");
     graph_drop(ctx);
     ctx->arena.reset();
     ctx->persist.reset();
@@ -177,6 +178,7 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
     S2S_REQUIRE(ctx && P && G && X && labels, "model_fwdbwd: null argument");
     Layout Y;
     S2S_TRY(make_layout(cfg, &Y));
+    S2S_REQUIRE(Y.NL > 0, "model_fwdbwd needs the GRU encoder (NL > 0); decoder-only layouts go through s2s_attention_forward / _backward");
     auto run = [&]() -> int {
         ctx->arena.reset();
         ctx->persist.reset();
@@ -189,7 +191,7 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
     }
     uint32_t lam_bits; memcpy(&lam_bits, &lambda, 4);
     std::vector<uint64_t> key = {(uint64_t)cfg->D, (uint64_t)cfg->H, (uint64_t)cfg->NL, (uint64_t)cfg->S, (uint64_t)cfg->ST, (uint64_t)cfg->V,
-                                 (uint64_t)cfg->K, (uint64_t)cfg->KF, (uint64_t)cfg->M, (uint64_t)cfg->MW, (uint64_t)B, (uint64_t)Lmax, (uint64_t)Tmax,
+                                 (uint64_t)cfg->K, (uint64_t)cfg->KF, (uint64_t)cfg->M, (uint64_t)cfg->MW + ((uint64_t)cfg->MLP << 32), (uint64_t)B, (uint64_t)Lmax, (uint64_t)Tmax,
                                  (uint64_t)lam_bits, (uint64_t)flags, (uint64_t)P, (uint64_t)G, (uint64_t)X, (uint64_t)lengths, (uint64_t)labels,
                                  (uint64_t)tlens, (uint64_t)dropmask, (uint64_t)nll, (uint64_t)logp, (uint64_t)dX, (uint64_t)ctx->stream};
     if (key != ctx->graph.key) { graph_drop(ctx); ctx->graph.key = key; }

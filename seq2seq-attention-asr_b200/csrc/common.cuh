@@ -129,9 +129,9 @@ void prof_end(s2s_ctx* ctx, int cls, double work);
 // ---------------------------------------------------------------------------------------------
 struct Seg { int64_t off = 0; int rows = 0, cols = 0; };
 struct Layout {
-    int D, H, NL, S, A, ST, V, K, KF, M, MW;
+    int D, H, NL, S, A, ST, V, K, KF, M, MW, MLP;
     Seg enc[8][2][3];   // layer, direction (0 fwd, 1 reverse), gate (z, r, h~): [H, H+Din]  GRU.lua:23-26
-    Seg WV, bV, Ws, bs, WF, bF, U, bU, we, be, Wy, by, Wc, bc, Wj, bj, Gz, Gr, Gh, Wm, bm, Wo, bo;
+    Seg WV, bV, Ws, bs, WF, bF, U, bU, we, be, Wy, by, Wc, bc, Wj, bj, Gz, Gr, Gh, Wm, bm, Wl, bl, Wm2, bm2, Wo, bo;
     int64_t n;
 };
 int make_layout(const s2s_model_cfg* cfg, Layout* Y);   // validates cfg; 0 on success

@@ -89,12 +89,13 @@ static void seg(Seg* s, int64_t* off, int rows, int cols) {
 }
 int make_layout(const s2s_model_cfg* c, Layout* Y) {
     S2S_REQUIRE(c != nullptr, "cfg is NULL");
-    S2S_REQUIRE(c->D > 0 && c->H > 0 && c->NL > 0 && c->NL <= 8 && c->S > 0 && c->ST > 0 && c->V > 1 && c->K >= 0 && c->M > 0 && c->MW > 0,
+    S2S_REQUIRE(c->D > 0 && c->H > 0 && c->NL >= 0 && c->NL <= 8 && c->S > 0 && c->ST > 0 && c->V > 1 && c->K >= 0 && c->M > 0 && c->MW > 0,
                 "invalid model cfg (D=%d H=%d NL=%d S=%d ST=%d V=%d K=%d KF=%d M=%d MW=%d)", c->D, c->H, c->NL, c->S, c->ST, c->V, c->K, c->KF, c->M, c->MW);
     S2S_REQUIRE(c->K == 0 || c->KF > 0, "K>0 needs KF>0");
+    S2S_REQUIRE(c->MLP >= 0 && c->MLP <= 2, "invalid model cfg: MLP=%d (0/1 = Maxout-Linear, 2 = Maxout-Linear-Maxout-Linear)", c->MLP);
     memset(Y, 0, sizeof(*Y));
     Y->D = c->D; Y->H = c->H; Y->NL = c->NL; Y->S = c->S; Y->A = 2 * c->H; Y->ST = c->ST; Y->V = c->V;
-    Y->K = c->K; Y->KF = c->KF; Y->M = c->M; Y->MW = c->MW;
+    Y->K = c->K; Y->KF = c->KF; Y->M = c->M; Y->MW = c->MW; Y->MLP = c->MLP == 2 ? 2 : 1;
     int64_t o = 0;
     for (int l = 0; l < Y->NL; l++) {
         int din = l == 0 ? Y->D : 2 * Y->H;
@@ -113,6 +114,10 @@ int make_layout(const s2s_model_cfg* c, Layout* Y) {
     seg(&Y->Wj, &o, Y->ST, 2 * Y->ST); seg(&Y->bj, &o, Y->ST, 1);
     seg(&Y->Gz, &o, Y->ST, 2 * Y->ST); seg(&Y->Gr, &o, Y->ST, 2 * Y->ST); seg(&Y->Gh, &o, Y->ST, 2 * Y->ST);
     seg(&Y->Wm, &o, Y->M * Y->MW, Y->ST + Y->A); seg(&Y->bm, &o, Y->M * Y->MW, 1);
+    if (Y->MLP == 2) {   // librispeech/model_vgg.lua:78-79
+        seg(&Y->Wl, &o, Y->M, Y->M); seg(&Y->bl, &o, Y->M, 1);
+        seg(&Y->Wm2, &o, Y->M * Y->MW, Y->M); seg(&Y->bm2, &o, Y->M * Y->MW, 1);
+    }
     seg(&Y->Wo, &o, Y->V, Y->M); seg(&Y->bo, &o, Y->V, 1);
     Y->n = o;
     return 0;
@@ -273,7 +278,7 @@ int s2s_param_segments(const s2s_model_cfg* cfg, int64_t* out, int max) {
     for (int l = 0; l < Y.NL; l++) for (int d = 0; d < 2; d++) for (int g = 0; g < 3; g++) put(Y.enc[l][d][g]);
     put(Y.WV); put(Y.bV); put(Y.Ws); put(Y.bs); put(Y.WF); put(Y.bF); put(Y.U); put(Y.bU); put(Y.we); put(Y.be);
     put(Y.Wy); put(Y.by); put(Y.Wc); put(Y.bc); put(Y.Wj); put(Y.bj); put(Y.Gz); put(Y.Gr); put(Y.Gh);
-    put(Y.Wm); put(Y.bm); put(Y.Wo); put(Y.bo);
+    put(Y.Wm); put(Y.bm); put(Y.Wl); put(Y.bl); put(Y.Wm2); put(Y.bm2); put(Y.Wo); put(Y.bo);
     return n;
 }
 

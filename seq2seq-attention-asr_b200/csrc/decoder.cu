@@ -545,6 +545,7 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
     S2S_ALLOC(d.gates, pa, float, BT * 3 * ST);
     S2S_ALLOC(d.mo, pa, float, BT * M);
     S2S_ALLOC(d.midx, pa, int, BT * M);
+    if (Y.MLP == 2) { S2S_ALLOC(d.l1, pa, float, BT * M); S2S_ALLOC(d.mo2, pa, float, BT * M); S2S_ALLOC(d.midx2, pa, int, BT * M); }
     S2S_ALLOC(d.logp, pa, float, BT * V);
     if (dropmask) S2S_ALLOC(d.scm, pa, float, BT * (ST + A)); else d.scm = d.sc;
     S2S_ALLOC(d.qbias, pa, float, S);
@@ -643,7 +644,17 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
     S2S_TRY(gemm_f32(ctx, false, true, (int)BT, M * MW, ST + A, 1.f, d.scm, ST + A, P + Y.Wm.off, ST + A, 0.f, mpre, M * MW, P + Y.bm.off));
     maxout_fwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(mpre, (int64_t)BT, M, MW, d.mo, d.midx);
     S2S_LAUNCH_CHECK(ctx);
-    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, V, M, 1.f, d.mo, M, P + Y.Wo.off, M, 0.f, d.logp, V, P + Y.bo.off));
+    const float* top = d.mo;
+    if (Y.MLP == 2) {   // Linear(M,M) -> Maxout(M,M,MW)   (librispeech/model_vgg.lua:78-79)
+        float* mpre2;
+        S2S_ALLOC(mpre2, ar, float, BT * M * MW);
+        S2S_TRY(gemm_f32(ctx, false, true, (int)BT, M, M, 1.f, d.mo, M, P + Y.Wl.off, M, 0.f, d.l1, M, P + Y.bl.off));
+        S2S_TRY(gemm_f32(ctx, false, true, (int)BT, M * MW, M, 1.f, d.l1, M, P + Y.Wm2.off, M, 0.f, mpre2, M * MW, P + Y.bm2.off));
+        maxout_fwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(mpre2, (int64_t)BT, M, MW, d.mo2, d.midx2);
+        S2S_LAUNCH_CHECK(ctx);
+        top = d.mo2;
+    }
+    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, V, M, 1.f, top, M, P + Y.Wo.off, M, 0.f, d.logp, V, P + Y.bo.off));
     logsoftmax_kernel<<<(unsigned)ceil_div64((int64_t)BT, 8), 256, 0, st>>>(d.logp, (int64_t)BT, V, logp_out);
     S2S_LAUNCH_CHECK(ctx);
     d.valid = true;
@@ -700,9 +711,21 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     // ---- time-batched MLP backward (model_chorowski_baseline.lua:53-59 reversed) ----------------
     logsoftmax_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT, 8), 256, 0, st>>>(d.logp, dlogp, (int64_t)BT, V, tlens, T, dlogits);
     S2S_LAUNCH_CHECK(ctx);
-    S2S_TRY(gemm_f32(ctx, true, false, V, M, iBT, 1.f, dlogits, V, d.mo, M, 1.f, G + Y.Wo.off, M));
+    S2S_TRY(gemm_f32(ctx, true, false, V, M, iBT, 1.f, dlogits, V, Y.MLP == 2 ? d.mo2 : d.mo, M, 1.f, G + Y.Wo.off, M));
     S2S_TRY(colsum_add(ctx, dlogits, BT, V, V, G + Y.bo.off));
     S2S_TRY(gemm_f32(ctx, false, false, iBT, M, V, 1.f, dlogits, V, P + Y.Wo.off, M, 0.f, dmo, M));
+    if (Y.MLP == 2) {   // second Maxout and Linear(M,M) backward (librispeech/model_vgg.lua:78-79)
+        float* dl1;
+        S2S_ALLOC(dl1, ar, float, BT * M);
+        maxout_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(dmo, d.midx2, (int64_t)BT, M, MW, dm);
+        S2S_LAUNCH_CHECK(ctx);
+        S2S_TRY(gemm_f32(ctx, true, false, M * MW, M, iBT, 1.f, dm, M * MW, d.l1, M, 1.f, G + Y.Wm2.off, M));
+        S2S_TRY(colsum_add(ctx, dm, BT, M * MW, M * MW, G + Y.bm2.off));
+        S2S_TRY(gemm_f32(ctx, false, false, iBT, M, M * MW, 1.f, dm, M * MW, P + Y.Wm2.off, M, 0.f, dl1, M));
+        S2S_TRY(gemm_f32(ctx, true, false, M, M, iBT, 1.f, dl1, M, d.mo, M, 1.f, G + Y.Wl.off, M));
+        S2S_TRY(colsum_add(ctx, dl1, BT, M, M, G + Y.bl.off));
+        S2S_TRY(gemm_f32(ctx, false, false, iBT, M, M, 1.f, dl1, M, P + Y.Wl.off, M, 0.f, dmo, M));
+    }
     maxout_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(dmo, d.midx, (int64_t)BT, M, MW, dm);
     S2S_LAUNCH_CHECK(ctx);
     S2S_TRY(gemm_f32(ctx, true, false, M * MW, ST + A, iBT, 1.f, dm, M * MW, d.scm, ST + A, 1.f, G + Y.Wm.off, ST + A, nullptr, GemmBatch(), 4));
@@ -887,6 +910,14 @@ int attention_step_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const flo
     { DenseEpi e; e.bias = P + Y.bm.off; e.out = mpre; e.ld_out = M * MW; S2S_TRY(dense_small(ctx, sc, ST + A, B, ST + A, P + Y.Wm.off, ST + A, M * MW, e)); }
     maxout_fwd_kernel<<<(unsigned)ceil_div64((int64_t)B * M, 256), 256, 0, st>>>(mpre, B, M, MW, mo, midx);
     S2S_LAUNCH_CHECK(ctx);
+    if (Y.MLP == 2) {   // Linear(M,M) -> Maxout(M,M,MW)   (librispeech/model_vgg.lua:78-79); mpre is reused for the second stage
+        float* l1;
+        S2S_ALLOC(l1, ar, float, (size_t)B * M);
+        { DenseEpi e; e.bias = P + Y.bl.off; e.out = l1; e.ld_out = M; S2S_TRY(dense_small(ctx, mo, M, B, M, P + Y.Wl.off, M, M, e)); }
+        { DenseEpi e; e.bias = P + Y.bm2.off; e.out = mpre; e.ld_out = M * MW; S2S_TRY(dense_small(ctx, l1, M, B, M, P + Y.Wm2.off, M, M * MW, e)); }
+        maxout_fwd_kernel<<<(unsigned)ceil_div64((int64_t)B * M, 256), 256, 0, st>>>(mpre, B, M, MW, mo, midx);
+        S2S_LAUNCH_CHECK(ctx);
+    }
     { DenseEpi e; e.bias = P + Y.bo.off; e.out = logp; e.ld_out = V; S2S_TRY(dense_small(ctx, mo, M, B, M, P + Y.Wo.off, M, V, e)); }
     logsoftmax_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(logp, B, V, nullptr);
     S2S_LAUNCH_CHECK(ctx);

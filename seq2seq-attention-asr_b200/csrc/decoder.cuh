@@ -25,6 +25,9 @@ struct DecoderState {
     float* gates = nullptr;   // [B, T, 3ST]             z | r | h~
     float* mo = nullptr;      // [B, T, M]
     int* midx = nullptr;      // [B, T, M]
+    float* l1 = nullptr;      // [B, T, M]   Linear(M,M) output          (MLP == 2, model_vgg.lua:78)
+    float* mo2 = nullptr;     // [B, T, M]   second Maxout output
+    int* midx2 = nullptr;     // [B, T, M]
     float* scm = nullptr;     // [B, T, ST+A] masked copy (dropout) or == sc
     float* logp = nullptr;    // [B, T, V]
     float* uw = nullptr;      // [KF, S]   U W_F   (location path)

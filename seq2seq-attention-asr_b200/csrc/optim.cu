@@ -332,7 +332,7 @@ int s2s_model_rownorm_constraint(s2s_ctx* ctx, const s2s_model_cfg* cfg, float* 
     for (int l = 0; l < Y.NL; l++) for (int d = 0; d < 2; d++) for (int g = 0; g < 3; g++) S2S_TRY(go(Y.enc[l][d][g]));
     S2S_TRY(go(Y.WV)); S2S_TRY(go(Y.Ws)); S2S_TRY(go(Y.WF)); S2S_TRY(go(Y.U)); S2S_TRY(go(Y.we));
     S2S_TRY(go(Y.Wy)); S2S_TRY(go(Y.Wc)); S2S_TRY(go(Y.Wj)); S2S_TRY(go(Y.Gz)); S2S_TRY(go(Y.Gr)); S2S_TRY(go(Y.Gh));
-    S2S_TRY(go(Y.Wm)); S2S_TRY(go(Y.Wo));
+    S2S_TRY(go(Y.Wm)); S2S_TRY(go(Y.Wl)); S2S_TRY(go(Y.Wm2)); S2S_TRY(go(Y.Wo));
     rownorm_multi_kernel<<<(unsigned)ceil_div(t.first[t.nseg], 8), 256, 0, ctx->stream>>>(P, t, (float)maxval, flag);
     S2S_LAUNCH_CHECK(ctx);
     if (nan_host) {

@@ -7,7 +7,7 @@ local ffi = require 'ffi'
 
 ffi.cdef[[
 typedef struct s2s_ctx s2s_ctx;
-typedef struct s2s_model_cfg { int D, H, NL, S, ST, V, K, KF, M, MW; } s2s_model_cfg;
+typedef struct s2s_model_cfg { int D, H, NL, S, ST, V, K, KF, M, MW, MLP; } s2s_model_cfg;
 int  s2s_ctx_create(int device, void* stream, s2s_ctx** out);
 int  s2s_ctx_destroy(s2s_ctx* ctx);
 int  s2s_ctx_set_stream(s2s_ctx* ctx, void* stream);

@@ -431,7 +431,10 @@ def segment_names(cfg):
     names += ["WV", "bV", "Ws", "bs"]
     if cfg["K"] > 0:
         names += ["WF", "bF", "U", "bU"]
-    names += ["we", "be", "Wy", "by", "Wc", "bc", "Wj", "bj", "Gz", "Gr", "Gh", "Wm", "bm", "Wo", "bo"]
+    names += ["we", "be", "Wy", "by", "Wc", "bc", "Wj", "bj", "Gz", "Gr", "Gh", "Wm", "bm"]
+    if cfg.get("MLP", 1) == 2:                     # librispeech/model_vgg.lua:78-79
+        names += ["Wl", "bl", "Wm2", "bm2"]
+    names += ["Wo", "bo"]
     return names
 
 

@@ -24,10 +24,12 @@ def _seg_errs(cfg, orc, G, Gref):
     return out
 
 
-@pytest.mark.parametrize("K,KF,lam,drop", [(0, 4, 0.0, False), (0, 4, 0.0, True), (3, 4, 0.0, False), (4, 5, 0.0, False),
-                                           (2, 10, 0.02, False), (0, 4, 0.05, False)])
-def test_attention_module_matches_oracle(s2s, gctx, orc64, K, KF, lam, drop):
-    cfg = dict(MID, K=K, KF=KF)
+@pytest.mark.parametrize("K,KF,lam,drop,extra", [(0, 4, 0.0, False, {}), (0, 4, 0.0, True, {}), (3, 4, 0.0, False, {}), (4, 5, 0.0, False, {}),
+                                                 (2, 10, 0.02, False, {}), (0, 4, 0.05, False, {}),
+                                                 # librispeech/model_vgg.lua decoder: two Maxout stages; decoder-only parameter vector
+                                                 (0, 4, 0.0, True, dict(MLP=2)), (0, 10, 0.0, False, dict(MLP=2, NL=0))])
+def test_attention_module_matches_oracle(s2s, gctx, orc64, K, KF, lam, drop, extra):
+    cfg = dict(MID, K=K, KF=KF, **extra)
     B, L, T = 4, 45, 7
     P = init_params(cfg, seed=5, dtype=np.float64, oracle=orc64) * 1.5
     rng = np.random.default_rng(1)
@@ -139,8 +141,9 @@ def test_optimizer_and_noise_match_oracle(s2s, gctx, orc32, orc64):
     assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
 
 
-def test_beam_search_matches_oracle(s2s, gctx, orc32, orc64):
-    cfg = dict(MID, K=3, KF=4)
+@pytest.mark.parametrize("extra", [{}, dict(MLP=2, NL=0)])
+def test_beam_search_matches_oracle(s2s, gctx, orc32, orc64, extra):
+    cfg = dict(MID, K=3, KF=4, **extra)
     P = init_params(cfg, seed=21, dtype=np.float64, oracle=orc64) * 3.0
     rng = np.random.default_rng(4)
     for trial in range(3):

@@ -43,6 +43,25 @@ def test_model_matches_autograd_f64(orc64, K, KF, lam):
     assert np.count_nonzero(gr) > 0.9 * (gr.size - 3 * cfg["S"])
 
 
+def test_model_vgg_decoder_mlp_matches_autograd_f64(orc64):
+    # MLP = 2: Maxout-Linear-Maxout-Linear-LogSoftMax of librispeech/model_vgg.lua:76-80
+    cfg = dict(SMALL, MLP=2, M=4, MW=3)
+    P = init_params(cfg, seed=3, dtype=np.float64, oracle=orc64) * 2.0
+    assert P.size == orc64.param_count(dict(cfg, MLP=1)) + cfg["M"] * cfg["M"] + cfg["M"] + cfg["M"] * cfg["MW"] * (cfg["M"] + 1)
+    X, lengths, labels, tlens = _data(cfg, 3, 8, 5, seed=5)
+    ref = torch_ref.model_fwdbwd(cfg, P, X, lengths, labels, tlens)
+    out = orc64.model_fwdbwd(cfg, P, X, lengths, labels, tlens)
+    assert np.allclose(out["nll"], ref["nll"], rtol=1e-10, atol=1e-12)
+    for b in range(3):
+        assert np.allclose(out["logp"][b, :tlens[b]], ref["logp"][b], rtol=1e-9, atol=1e-11)
+    g, gr = out["G"], ref["G"]
+    assert np.abs(g - gr).max() <= 1e-9 * max(1.0, np.abs(gr).max())
+    segs = dict(zip(torch_ref.segment_names(cfg), orc64.param_segments(cfg)))
+    for name in ("Wl", "bl", "Wm2", "bm2"):
+        off, rows, cols = segs[name]
+        assert np.count_nonzero(gr[off:off + rows * cols]) > 0, name
+
+
 def test_model_flags_and_dropout(orc64):
     cfg = dict(SMALL, K=2, KF=3)
     P = init_params(cfg, seed=3, dtype=np.float64, oracle=orc64)

@@ -146,6 +146,9 @@ def decoder(cfg, p, h, labels, lam=0.0, dropmask=None):
             sc = sc * dropmask[t]
         m = p["Wm"] @ sc + p["bm"]
         mo = m.view(M, MW).max(dim=1).values
+        if cfg.get("MLP", 1) == 2:                 # Linear(M,M) -> Maxout(M,M,7)   (librispeech/model_vgg.lua:78-79)
+            m2 = p["Wm2"] @ (p["Wl"] @ mo + p["bl"]) + p["bm2"]
+            mo = m2.view(M, MW).max(dim=1).values
         logp = torch.log_softmax(p["Wo"] @ mo + p["bo"], 0)
         logps.append(logp); alphas.append(a_new); ss.append(s_new); cs.append(c); qs.append(q)
         alpha, s = a_new, s_new
