@@ -177,6 +177,155 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# -------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: librispeech/model_vgg.lua -- VGG front-end + attention decoder (two-stage Maxout MLP), long
+# utterances.  Composed from the C-ABI pieces: s2s_vgg_forward -> s2s_attention_forward -> s2s_nll_grad_seed ->
+# s2s_attention_backward -> s2s_vgg_backward, then the gradient step.  Builder-chosen where BASELINE.json leaves it open
+# (SURVEY 8d): X [B,3,1600,40], L = 796, V = 29, T = 250 labels, batch 8 per GPU.
+def run_cfg4(args):
+    import torch
+    import torch.distributed as dist
+    import s2s_b200 as s2s
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = s2s.Context(local)
+    B, Tin, F, Tdec, V = 8, 1600, 40, 250, 29
+    vcfg = s2s.VGG_LIBRISPEECH
+    dcfg = dict(D=F, H=vcfg["OUT"] // 2, NL=0, S=512, ST=256, V=V, K=0, KF=10, M=64, MW=7, MLP=2)   # model_vgg.lua:57-69
+    Lenc = (Tin - 8) // 2
+    rng = np.random.default_rng(4000 + rank)
+    ne = s2s.vgg_param_count(vcfg, F); nd = s2s.param_count(dcfg)
+    prng = np.random.default_rng(1234)
+    P = torch.cat([torch.from_numpy((prng.uniform(-1, 1, ne) * 0.03).astype(np.float32)), torch.from_numpy(s2s.init_params(dcfg, seed=1234))]).to(dev)
+    G = torch.zeros_like(P); vs = torch.zeros_like(P); as_ = torch.zeros_like(P)
+    Pe, Pd, Ge, Gd = P[:ne], P[ne:], G[:ne], G[ne:]
+    Xh = rng.standard_normal((B, 3, Tin, F)).astype(np.float32)
+    yh = rng.integers(0, V - 1, (B, Tdec)).astype(np.int32); yh[:, -1] = V - 1
+    X = torch.from_numpy(Xh).to(dev); y = torch.from_numpy(yh).to(dev)
+    nll = torch.zeros(B, device=dev); dlogp = torch.zeros(B, Tdec, V, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def fwdbwd(Xd, yd):
+        h = s2s.vgg_forward(ctx, vcfg, Pe, Xd)
+        logp = s2s.attention_forward(ctx, dcfg, Pd, h, yd)
+        s2s.nll_grad_seed(ctx, logp, yd, flags=s2s.NORMALIZE_NLL, nll=nll, dlogp=dlogp)
+        dh = s2s.attention_backward(ctx, dcfg, Pd, Gd, h, yd, dlogp)
+        s2s.vgg_backward(ctx, vcfg, Pe, Xd, dh, dP=Ge)
+        return h, logp, dh                       # kept alive: a captured graph writes to these buffers
+
+    graph = {"id": None, "keep": None}
+
+    def step(Xd, yd):
+        G.zero_()
+        if graph["id"] is not None and Xd is X and yd is y:
+            ctx.graph_launch(graph["id"])        # the whole forward + backward as one replayed CUDA graph
+        else:
+            fwdbwd(Xd, yd)
+        s2s.dp.allreduce_gradients(G)
+        s2s.grad_finalize(ctx, G, P, B * world, 1e20, want_norm=False)
+        s2s.adadelta(ctx, P, G, vs, as_)
+        s2s.model_rownorm_constraint(ctx, dcfg, Pd, 1.0)
+        return nll
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step(X, y)                                   # eager once: sizes every workspace
+    torch.cuda.synchronize()
+    if not os.environ.get("S2S_BENCH_NOGRAPH"):
+        ctx.graph_begin()
+        graph["keep"] = fwdbwd(X, y)
+        graph["id"] = ctx.graph_end()
+    for _ in range(max(args.warmup, 3)):
+        step(X, y)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = ctx.launches
+    barrier()
+    for a, b in ev:
+        flush.fill_(1); a.record(); step(X, y); b.record()
+    barrier()
+    launches = ctx.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    frames = B * Tin * world
+    # e2e: pinned host inputs -> H2D -> step -> D2H(nll)
+    Xp = torch.from_numpy(Xh).pin_memory(); yp = torch.from_numpy(yh).pin_memory()
+    nll_h = torch.empty(B).pin_memory()
+
+    def e2e_step():
+        X.copy_(Xp, non_blocking=True); y.copy_(yp, non_blocking=True)      # the step's device input buffers
+        step(X, y)
+        nll_h.copy_(nll, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    # per-class breakdown of one extra pass
+    hbm, tf, how = peaks()
+    classes = {}
+    if graph["id"] is not None:
+        ctx.graph_destroy(graph["id"]); graph["id"] = None           # the instrumented pass runs eagerly
+    if rank == 0:
+        ctx.profile(True)
+    ev2 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    torch.cuda._sleep(int(60e6)); ev2[0].record(); step(X, y); ev2[1].record(); torch.cuda.synchronize()
+    total_ms = ev2[0].elapsed_time(ev2[1])
+    roof = None
+    if rank == 0:
+        prof = ctx.profile_read(); ctx.profile(False)
+        for k, (kms, cnt, work) in prof.items():
+            if cnt:
+                tensor = k == "gemm"
+                ach = work / (kms * 1e-3)
+                classes[k] = {"bound": "tensor" if tensor else "hbm", "ms_per_step": kms, "launches_per_step": cnt,
+                              "achieved": ach / (1e12 if tensor else 1e9), "peak": tf if tensor else hbm, "unit": "TFLOP/s" if tensor else "GB/s",
+                              "frac": ach / (1e12 if tensor else 1e9) / (tf if tensor else hbm), "share": kms / total_ms}
+        top = max(classes, key=lambda k: classes[k]["ms_per_step"])
+        c = classes[top]
+        roof = {"kernel": top, "bound": c["bound"], "achieved": c["achieved"], "peak": c["peak"], "unit": c["unit"], "frac": c["frac"], "traffic": None,
+                "peak_source": how, "share_of_step": c["share"], "instrumented_step_ms": total_ms,
+                "note": "fp32-equivalent FLOPs of the 3xTF32 tcgen05 GEMMs (3 tensor-core passes per product) against the measured bf16 peak; "
+                        "the unfold/fold/ReLU/pooling kernels of the first VGG path are not in a profiled class"}
+        line = {"metric": "librispeech_vgg_fwd_bwd_frames_per_sec", "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "cfg4: librispeech/model_vgg.lua (4 conv3x3 + 2 poolings + 4 1x1 layers -> 796 annotations of 512; content attention, "
+                                       "GRU-256 decoder, Maxout-Linear-Maxout-Linear MLP), X [8,3,1600,40] per GPU, 250 labels of 29 classes; step = zero-grad + "
+                                       "fwd + NLL + bwd + [all-reduce] + /B + clip + adadelta + row-norm (decoder)",
+                           "global_batch": B * world, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB write)"},
+                "e2e": {"value": frames / (e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": Xp.numel() * 4 + yp.numel() * 4, "d2h_bytes_per_step": B * 4},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": classes,
+                "cpu_baseline": None}
+        emit_json(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def dbg(msg):
     if os.environ.get("S2S_BENCH_DEBUG"):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
@@ -401,11 +550,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"],
-                    help="cfg2 = the metric's configuration (default); cfg3 = dropout model + AdaptiveWeightNoise (BASELINE.json configs[2])")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
+                    help="cfg2 = the metric's configuration (default); cfg3 = dropout model + AdaptiveWeightNoise (BASELINE.json configs[2]); "
+                         "cfg4 = librispeech/model_vgg.lua, VGG front-end + attention decoder (configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "cfg4":
+        run_cfg4(args)
     else:
         run_ours(args)
 

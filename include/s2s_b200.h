@@ -71,6 +71,13 @@ int  s2s_version(void);
 int64_t s2s_ctx_launch_count(s2s_ctx* ctx);
 /* enable (1) / disable (0) CUDA-graph replay of s2s_model_fwdbwd for repeated shapes */
 int  s2s_ctx_set_graphs(s2s_ctx* ctx, int enable);
+/* Caller-defined graphs: every library call on this context between _begin and _end is captured (not executed) and
+ * replayed by _launch in the order of the context's stream.  Same pointers and shapes on every replay; run the
+ * sequence eagerly once before capturing; no host read-backs inside.  Workspaces cannot grow while a graph is alive. */
+int  s2s_graph_begin(s2s_ctx* ctx);
+int  s2s_graph_end(s2s_ctx* ctx, int* graph_id);
+int  s2s_graph_launch(s2s_ctx* ctx, int graph_id);
+int  s2s_graph_destroy(s2s_ctx* ctx, int graph_id);
 
 /* Per-kernel-class device timing with CUDA events on the context's stream (bench.py roofline).
  * enable != 0 clears the counters and starts recording; read synchronises the stream and returns, per
@@ -208,6 +215,10 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
                      float* nll, float* logp, float* dX);
 /* encoder annotations of the last model call [B,Lmax,A] (encoder.output, timit.lua:397) */
 int s2s_model_get_annotations(s2s_ctx* ctx, float* dst);
+/* Loss and gradient seed on their own (timit/timit.lua:262-282), for callers that compose an encoder
+ * (e.g. s2s_vgg_forward) with s2s_attention_forward / _backward: nll [B] and/or dlogp [B,T,V] (either may be NULL) */
+int s2s_nll_grad_seed(s2s_ctx* ctx, const float* logp, const int* labels, const int* tlens, int B, int T, int V,
+                      int flags, float* nll, float* dlogp);
 
 /* ---- weight noise (WeightNoise.lua:17-35, AdaptiveWeightNoise.lua:27-104) ------------------- */
 /* eps: injected N(0,1) buffer [n] for parity; NULL = Philox counter RNG seeded by (seed, call counter) */

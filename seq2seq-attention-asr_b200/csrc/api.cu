@@ -23,10 +23,15 @@ int attention_step_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const flo
 static void graph_drop(s2s_ctx* ctx) {
     if (ctx->graph.exec) { cudaGraphExecDestroy(ctx->graph.exec); ctx->graph.exec = nullptr; }
     ctx->graph.key.clear(); ctx->graph.seen = 0; ctx->graph.launches = 0; ctx->graph.nocapture = false;
-    ctx->arena.frozen = false; ctx->persist.frozen = false;
+    bool user_alive = false;
+    for (cudaGraphExec_t g : ctx->user_graphs) user_alive = user_alive || g != nullptr;
+    ctx->arena.frozen = user_alive; ctx->persist.frozen = user_alive;      // memory referenced by a live graph must not move
 }
 
-namespace s2s { void vgg_state_free(s2s_ctx* ctx); }
+namespace s2s {
+void vgg_state_free(s2s_ctx* ctx);
+int nll_and_seed(s2s_ctx* ctx, const float* logp, const int* labels, const int* tlens, int B, int T, int V, int flags, float* nll, float* dlogp);
+}
 
 extern "C" {
 
@@ -35,6 +40,7 @@ int s2s_ctx_destroy(s2s_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->graph.exec) cudaGraphExecDestroy(ctx->graph.exec);
+    for (cudaGraphExec_t g : ctx->user_graphs) if (g) cudaGraphExecDestroy(g);
     ctx->arena.release();
     ctx->persist.release();
     if (ctx->counters) cudaFree(ctx->counters);
@@ -185,8 +191,8 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
         S2S_TRY(model_forward(ctx, Y, P, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, nll, logp));
         return model_backward(ctx, Y, P, G, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, dX);
     };
-    if (!ctx->graphs || ctx->prof.on) {
-        if (ctx->graph.exec) graph_drop(ctx);
+    if (!ctx->graphs || ctx->prof.on || ctx->capturing) {
+        if (ctx->graph.exec && !ctx->capturing) graph_drop(ctx);
         return run();
     }
     uint32_t lam_bits; memcpy(&lam_bits, &lambda, 4);
@@ -235,6 +241,70 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
     ctx->launches += ctx->graph.launches;
     // forward state recorded by the capture pass stays valid: same shapes, same arena pointers
     return 0;
+}
+// ---- caller-defined CUDA graphs ----------------------------------------------------------------------------------
+// Everything the library launches for this context between _begin and _end is captured into one graph (on an internal
+// stream) instead of being executed; _launch replays it in the order of the context's stream.  The decoder time loop is
+// hundreds of microsecond-sized launches, so a replayed step costs about half of the eager one.  Rules for the captured
+// region: same pointers and shapes on every replay; run the sequence eagerly once first (workspaces must already be
+// large enough -- they cannot grow while a graph references them); no calls that read results back to the host.
+int s2s_graph_begin(s2s_ctx* ctx) {
+    S2S_REQUIRE(ctx && !ctx->capturing, "graph_begin: bad context or already capturing");
+    if (ctx->graph.exec) graph_drop(ctx);
+    ctx->capture_user_stream = ctx->stream;
+    ctx->capture_l0 = ctx->launches;
+    ctx->arena.frozen = true; ctx->persist.frozen = true;
+    cudaError_t e = cudaStreamBeginCapture(ctx->side[0], cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { graph_drop(ctx); return fail("graph_begin: cudaStreamBeginCapture: %s", cudaGetErrorString(e)); }
+    ctx->stream = ctx->side[0];
+    ctx->capturing = true;
+    return 0;
+}
+int s2s_graph_end(s2s_ctx* ctx, int* graph_id) {
+    S2S_REQUIRE(ctx && ctx->capturing && graph_id, "graph_end: not capturing");
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->side[0], &graph);
+    ctx->stream = ctx->capture_user_stream;
+    ctx->capturing = false;
+    const int64_t n = ctx->launches - ctx->capture_l0;
+    ctx->launches = ctx->capture_l0;
+    cudaGraphExec_t exec = nullptr;
+    if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || !exec) { cudaGetLastError(); graph_drop(ctx); return fail("graph_end: capture failed: %s", cudaGetErrorString(e)); }
+    ctx->user_graphs.push_back(exec);
+    ctx->user_graph_launches.push_back(n);
+    *graph_id = (int)ctx->user_graphs.size() - 1;
+    return 0;
+}
+int s2s_graph_launch(s2s_ctx* ctx, int graph_id) {
+    S2S_REQUIRE(ctx && !ctx->capturing && graph_id >= 0 && graph_id < (int)ctx->user_graphs.size() && ctx->user_graphs[graph_id],
+                "graph_launch: invalid graph id %d", graph_id);
+    cudaStream_t user = ctx->stream, side = ctx->side[0];
+    S2S_CUDA(cudaEventRecord(ctx->ev[0], user));
+    S2S_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
+    S2S_CUDA(cudaGraphLaunch(ctx->user_graphs[graph_id], side));
+    S2S_CUDA(cudaEventRecord(ctx->ev[1], side));
+    S2S_CUDA(cudaStreamWaitEvent(user, ctx->ev[1], 0));
+    ctx->launches += ctx->user_graph_launches[graph_id];
+    return 0;
+}
+int s2s_graph_destroy(s2s_ctx* ctx, int graph_id) {
+    S2S_REQUIRE(ctx && graph_id >= 0 && graph_id < (int)ctx->user_graphs.size(), "graph_destroy: invalid graph id %d", graph_id);
+    if (ctx->user_graphs[graph_id]) {
+        cudaStreamSynchronize(ctx->side[0]);
+        cudaGraphExecDestroy(ctx->user_graphs[graph_id]);
+        ctx->user_graphs[graph_id] = nullptr;
+    }
+    if (!ctx->graph.exec) graph_drop(ctx);      // unfreezes the workspaces when no graph is left
+    return 0;
+}
+
+// nll[b] = -sum_t logp[b,t,y_t] (/T_b) and dlogp = -labelmask (/T_b), zero beyond T_b   (timit/timit.lua:262-282)
+int s2s_nll_grad_seed(s2s_ctx* ctx, const float* logp, const int* labels, const int* tlens, int B, int T, int V, int flags, float* nll,
+                      float* dlogp) {
+    S2S_REQUIRE(ctx && logp && labels && B > 0 && T > 0 && V > 1 && (nll || dlogp), "nll_grad_seed: bad arguments");
+    return nll_and_seed(ctx, logp, labels, tlens, B, T, V, flags, nll, dlogp);
 }
 int s2s_model_get_annotations(s2s_ctx* ctx, float* dst) {
     S2S_REQUIRE(ctx && dst, "model_get_annotations: null argument");

@@ -99,6 +99,12 @@ struct s2s_ctx {
     uint64_t rng_calls = 0;
     s2s::Prof prof;
     s2s::GraphCache graph;
+    // caller-defined graphs (s2s_graph_begin / _end / _launch): sequences of library calls captured once and replayed
+    std::vector<cudaGraphExec_t> user_graphs;
+    std::vector<int64_t> user_graph_launches;
+    bool capturing = false;
+    cudaStream_t capture_user_stream = nullptr;
+    int64_t capture_l0 = 0;
     bool tc_cache_on = false;
     std::vector<s2s::TcCacheEntry> tc_cache;
 };

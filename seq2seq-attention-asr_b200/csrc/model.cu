@@ -30,6 +30,19 @@ __global__ void nll_seed_kernel(const int* __restrict__ labels, const int* __res
     for (int v = threadIdx.x; v < V; v += blockDim.x) dlogp[(size_t)bt * V + v] = (v == y) ? g : 0.f;
 }
 
+// standalone loss + gradient seed for callers that compose encoder and decoder themselves (timit/timit.lua:262-282)
+int nll_and_seed(s2s_ctx* ctx, const float* logp, const int* labels, const int* tlens, int B, int T, int V, int flags, float* nll, float* dlogp) {
+    if (nll) {
+        nll_kernel<<<B, 32, 0, ctx->stream>>>(logp, labels, tlens, T, V, flags, nll);
+        S2S_LAUNCH_CHECK(ctx);
+    }
+    if (dlogp) {
+        nll_seed_kernel<<<B * T, 64, 0, ctx->stream>>>(labels, tlens, T, V, flags, dlogp);
+        S2S_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
 int model_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* X, const int* lengths, int B, int Lmax,
                   const int* labels, const int* tlens, int T, const float* dropmask, float lambda, int flags, float* nll, float* logp) {
     S2S_REQUIRE(B > 0 && Lmax > 0 && T > 0, "model_forward: empty batch");

@@ -29,6 +29,12 @@ int s2s_dropout_mask(s2s_ctx*, float p, uint64_t seed, int64_t n, float* mask);
 int s2s_lstm_step_forward(s2s_ctx*, const float* P, int Din, int H, int peepholes, const float* x, const float* hprev, const float* cprev, int B, float* hnext, float* cnext, float* acts);
 int s2s_lstm_step_backward(s2s_ctx*, const float* P, float* dP, int Din, int H, int peepholes, const float* x, const float* hprev, const float* cprev, int B, const float* acts, const float* cnext, const float* dhnext, const float* dcnext, float* dx, float* dhprev, float* dcprev);
 int s2s_edit_distance(const int* a, int na, const int* b, int nb, int* dist_host);
+int s2s_nll_grad_seed(s2s_ctx*, const float* logp, const int* labels, const int* tlens, int B, int T, int V, int flags, float* nll, float* dlogp);
+typedef struct s2s_vgg_cfg { int C1, C2, HID, OUT; } s2s_vgg_cfg;
+int64_t s2s_vgg_param_count(const s2s_vgg_cfg* cfg, int F);
+int s2s_vgg_out_len(int T);
+int s2s_vgg_forward(s2s_ctx*, const s2s_vgg_cfg*, const float* P, const float* X, int B, int T, int F, float* h);
+int s2s_vgg_backward(s2s_ctx*, const s2s_vgg_cfg*, const float* P, float* dP, int B, int T, int F, const float* dh, float* dX);
 int s2s_attention_forward(s2s_ctx*, const s2s_model_cfg*, const float* P, const float* h, const int* lengths, int B, int Lmax, const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda, float* logp);
 int s2s_attention_backward(s2s_ctx*, const s2s_model_cfg*, const float* P, float* G, const float* h, const int* lengths, int B, int Lmax, const int* labels, const int* tlens, int Tmax, const float* dropmask, float lambda, const float* dlogp, float* dh);
 int s2s_attention_get(s2s_ctx*, int what, float* dst);

@@ -71,6 +71,22 @@ class Context:
     def set_graphs(self, enable):
         check(self.lib.s2s_ctx_set_graphs(self.h, int(bool(enable))))
 
+    # caller-defined graphs: capture a sequence of library calls once, replay it with one launch.  The tensors the
+    # captured calls wrote to must stay alive (and be the ones read afterwards); run the sequence eagerly once first.
+    def graph_begin(self):
+        check(self.lib.s2s_graph_begin(self.h))
+
+    def graph_end(self):
+        gid = C.c_int(-1)
+        check(self.lib.s2s_graph_end(self.h, C.byref(gid)))
+        return int(gid.value)
+
+    def graph_launch(self, gid):
+        check(self.lib.s2s_graph_launch(self.h, gid))
+
+    def graph_destroy(self, gid):
+        check(self.lib.s2s_graph_destroy(self.h, gid))
+
     PROF_CLASSES = ("attn_fwd", "attn_bwd", "attn_dvh", "gru_fwd", "gru_bwd", "gemm", "dense_small")
 
     def profile(self, enable=True):
@@ -391,6 +407,17 @@ def vgg_backward(ctx, cfg, P, X, dh, dP=None, need_dx=False):
     dX = torch.empty_like(X) if need_dx else None
     check(ctx.lib.s2s_vgg_backward(ctx.h, C.byref(c), _f(P), _f(dP), B, T, F, _f(dh), _f(dX)))
     return dP, dX
+
+
+def nll_grad_seed(ctx, logp, labels, tlens=None, flags=0, nll=None, dlogp=None, want_grad=True):
+    """per-utterance NLL [B] and the gradient seed dlogp = -labelmask [B,T,V] (timit/timit.lua:262-282)"""
+    B, T, V = logp.shape
+    if nll is None:
+        nll = ctx.new(B)
+    if dlogp is None and want_grad:
+        dlogp = ctx.new(B, T, V)
+    check(ctx.lib.s2s_nll_grad_seed(ctx.h, _f(logp), _i(labels), _i(tlens), B, T, V, flags, _f(nll), _f(dlogp)))
+    return nll, dlogp
 
 
 def edit_distance(a, b):

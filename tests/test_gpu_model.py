@@ -153,3 +153,38 @@ def test_beam_search_matches_oracle(s2s, gctx, orc32, orc64, extra):
         y, lp = s2s.beam_search(gctx, cfg, dev(P, torch.float32), dev(h, torch.float32), eos=cfg["V"] - 1, beam=4, maxlen=12)
         assert list(ref_y) == y            # bit-exact label sequence
         assert abs(lp - ref_lp) < 1e-3 * max(1.0, abs(ref_lp))
+
+
+def test_caller_defined_graph_replays_the_same_results(s2s, gctx, orc64):
+    # s2s_graph_begin / _end / _launch: a captured sequence of library calls (decoder forward + loss seed + backward)
+    # replayed on new input values must give what the eager calls give
+    cfg = dict(MID, NL=0, MLP=2)
+    B, L, T = 3, 40, 6
+    P = dev(init_params(cfg, seed=9, dtype=np.float64, oracle=orc64) * 1.5, torch.float32)
+    rng = np.random.default_rng(8)
+    h = dev(rng.standard_normal((B, L, 2 * cfg["H"])), torch.float32)
+    labels = dev(rng.integers(0, cfg["V"] - 1, (B, T)).astype(np.int32))
+    G = torch.zeros_like(P); nll = torch.zeros(B, device="cuda"); dlogp = torch.zeros(B, T, cfg["V"], device="cuda")
+
+    def run():
+        logp = s2s.attention_forward(gctx, cfg, P, h, labels)
+        s2s.nll_grad_seed(gctx, logp, labels, nll=nll, dlogp=dlogp)
+        return logp, s2s.attention_backward(gctx, cfg, P, G, h, labels, dlogp)
+
+    run()                                       # eager warm-up sizes the workspaces
+    gctx.graph_begin()
+    logp_g, dh_g = run()
+    gid = gctx.graph_end()
+    try:
+        h.copy_(dev(rng.standard_normal((B, L, 2 * cfg["H"])), torch.float32))     # new values, same buffers
+        G.zero_()
+        gctx.graph_launch(gid)
+        torch.cuda.synchronize()
+        got = (logp_g.clone(), dh_g.clone(), G.clone(), nll.clone())
+    finally:
+        gctx.graph_destroy(gid)
+    G.zero_()
+    logp_e, dh_e = run()
+    torch.cuda.synchronize()
+    for a, b in zip(got, (logp_e, dh_e, G, nll)):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
