@@ -5,6 +5,8 @@
 // Reference call sites this replaces: TemporalConvolutionZeroBias.lua:39,45,51 (Vh and its gradients),
 // LinearZeroBias.lua:42,58,70 (GRU gate products, time-batched here), the stock nn.Linear products of
 // Attention.lua:149-151 and model_chorowski_baseline.lua:56-57.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace s2s {
@@ -149,6 +151,11 @@ int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, c
         S2S_REQUIRE(impl != 2, "gemm: tcgen05 path requested but shape/alignment not supported (M=%d N=%d K=%d)", M, N, K);
     }
     if (K == 0) return 0;
+    if (splitk > 1) {   // few output tiles and a long K (weight gradients over all frames): split K until the grid fills the SMs
+        const long tiles64 = (long)ceil_div(M, 64) * ceil_div(N, 64);
+        const int want = (int)std::min<long>((long)ctx->sm_count * 2 / std::max(tiles64, 1L), (long)K / 512);
+        if (want > splitk) splitk = want;
+    }
     int z = splitk > 1 ? splitk : batch.count;
     prof_begin(ctx, S2S_PROF_GEMM);
     // pick the tile so the grid covers the SMs: big tiles only when they still give >= 1 wave

@@ -31,15 +31,17 @@
 namespace s2s {
 
 namespace tc {
-constexpr int BM = 128, BN = 256, BK = 32;          // BK floats = 128 bytes = one swizzle row
-constexpr int STAGES = 2;
+constexpr int BM = 128, BK = 32;                    // BK floats = 128 bytes = one swizzle row
 constexpr int A_BYTES = BM * BK * 4;                // 16 KB
-constexpr int B_BYTES = BN * BK * 4;                // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi, A_lo, B_hi, B_lo = 96 KB
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int SCR_FLOATS = 32 * 33;                 // per-warp transpose scratch
-constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * SCR_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
+// tile width BN in {64, 128, 256}: narrow outputs (64- / 128-plane convolutions, K = 123 weight gradients) do not pay for
+// 256-wide MMAs, and their smaller stages buy a deeper pipeline
+constexpr int b_bytes(int BN) { return BN * BK * 4; }
+constexpr int stage_bytes(int BN) { return 2 * A_BYTES + 2 * b_bytes(BN); }        // A_hi, A_lo, B_hi, B_lo
+constexpr int stages(int BN) { return BN == 256 ? 2 : (BN == 128 ? 3 : 4); }       // 192 KB of stages in every case
+constexpr size_t smem_bytes(int BN) { return (size_t)stages(BN) * stage_bytes(BN) + (size_t)EPI_WARPS * SCR_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/; }
 constexpr int MIN_SHARE = 4;                        // a stream-K share is at least this many slabs
 
 struct Sched {
@@ -96,7 +98,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D = f32, A = B = tf32, both K-major, N = 256, M = 128
+// instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
+template <int BN>
 __device__ __forceinline__ uint32_t make_idesc() {
     uint32_t d = 0;
     d |= 1u << 4;                       // c_format = F32
@@ -126,11 +129,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 }  // namespace tc
 
+template <int BN>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const tc::Sched sched,
                int M, int N, float alpha, float beta, float* __restrict__ C, int ldc, const float* __restrict__ bias) {
     using namespace tc;
+    constexpr int STAGES = stages(BN), B_BYTES = b_bytes(BN), STAGE_BYTES = stage_bytes(BN);
     Span seg;
     if (!get_seg(sched, blockIdx.x, 0, seg)) return;       // nothing dealt to this CTA (uniform per CTA)
 
@@ -153,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         fence_mbar_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(2 * BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -183,7 +188,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     } else if (warp == 1) {
         // ---- MMA issue --------------------------------------------------------------------------------------
         if (lane == 0) {
-            const uint32_t idesc = make_idesc();
+            const uint32_t idesc = make_idesc<BN>();
             int it = 0;
             for (int i = 0; get_seg(sched, g, i, seg); i++) {
                 const int acc = i & 1;
@@ -288,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
     }
 }
 
@@ -335,11 +340,11 @@ __global__ void transpose_split_kernel(const float* __restrict__ src, int K, int
         }
     }
 }
-__global__ void zero_tiles_kernel(float* __restrict__ C, int ldc, int M, int N, int tiles_n, int first_tile) {
+__global__ void zero_tiles_kernel(float* __restrict__ C, int ldc, int M, int N, int tiles_n, int first_tile, int BN) {
     const int tile = first_tile + blockIdx.x;
     const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
-    for (int idx = threadIdx.x; idx < tc::BM * tc::BN; idx += blockDim.x) {
-        const int r = tm * tc::BM + idx / tc::BN, c = tn * tc::BN + idx % tc::BN;
+    for (int idx = threadIdx.x; idx < tc::BM * BN; idx += blockDim.x) {
+        const int r = tm * tc::BM + idx / BN, c = tn * BN + idx % BN;
         if (r < M && c < N) C[(size_t)r * ldc + c] = 0.f;
     }
 }
@@ -439,6 +444,7 @@ int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha
     if (!force && (double)M * N * K < 5e8) return 0;
     if (!get_encode()) return 0;
 
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     Sched sc;
     sc.tiles_m = ceil_div(M, BM); sc.tiles_n = ceil_div(N, BN); sc.nk = ceil_div(K, BK);
     sc.G = ctx->sm_count;
@@ -462,15 +468,19 @@ int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha
         return fail("gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", M, N, K);
     static bool attr = false;
     if (!attr) {
-        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64)));
+        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128)));
+        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(256)));
         attr = true;
     }
     if (atomics && beta == 0.f) {
-        zero_tiles_kernel<<<sc.rem, 256, 0, ctx->stream>>>(C, ldc, M, N, sc.tiles_n, sc.R * sc.G);
+        zero_tiles_kernel<<<sc.rem, 256, 0, ctx->stream>>>(C, ldc, M, N, sc.tiles_n, sc.R * sc.G, BN);
         S2S_LAUNCH_CHECK(ctx);
     }
     prof_begin(ctx, S2S_PROF_GEMM);
-    gemm_tc_kernel<<<sc.G, THREADS, SMEM, ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
+    if (BN == 64) gemm_tc_kernel<64><<<sc.G, THREADS, smem_bytes(64), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
+    else if (BN == 128) gemm_tc_kernel<128><<<sc.G, THREADS, smem_bytes(128), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
+    else gemm_tc_kernel<256><<<sc.G, THREADS, smem_bytes(256), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
     prof_end(ctx, S2S_PROF_GEMM, 2.0 * M * N * (double)K);
     S2S_LAUNCH_CHECK(ctx);
     *handled = true;

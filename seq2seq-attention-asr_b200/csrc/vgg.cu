@@ -67,28 +67,37 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int C, int64_t 
     const int64_t b = i / (HW * C);
     y[i] = x[(b * HW + p) * C + c];
 }
-// patches: col[(b, y, x), (kh, kw, c)] = in[b, y + kh, x + kw, c]
+// patches: col[(b, y, x), (kh, kw, c)] = in[b, y + kh, x + kw, c].  VEC = 4: four channels per thread (C % 4 == 0), 16-byte
+// loads and stores; one 64-bit division per thread, the rest of the index arithmetic is 32-bit.
+template <int VEC>
 __global__ void unfold3_kernel(const float* __restrict__ in, int nb, int Hh, int Ww, int C, float* __restrict__ col) {
-    const int Ho = Hh - 2, Wo = Ww - 2, K = 9 * C;
-    const int64_t n = (int64_t)nb * Ho * Wo * K;
+    const int Ho = Hh - 2, Wo = Ww - 2, CV = C / VEC, KV = 9 * CV;
+    const int64_t n = (int64_t)nb * Ho * Wo * KV;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % K);
-        const int64_t m = i / K;
-        const int c = k % C, t = k / C, kh = t / 3, kw = t - 3 * kh;
-        const int x = (int)(m % Wo), y = (int)((m / Wo) % Ho);
-        const int64_t b = m / ((int64_t)Wo * Ho);
-        col[i] = __ldg(in + ((b * Hh + y + kh) * Ww + x + kw) * C + c);
+        const int64_t m = i / KV;
+        const int k = (int)(i - m * KV);
+        const int t = k / CV, c = (k - t * CV) * VEC, kh = t / 3, kw = t - 3 * kh;
+        const int64_t by = m / Wo;                       // b * Ho + y
+        const int x = (int)(m - by * Wo);
+        const int b = (int)(by / Ho), y = (int)(by - (int64_t)b * Ho);
+        const float* src = in + (((int64_t)b * Hh + y + kh) * Ww + x + kw) * C + c;
+        float* dst = col + m * (9 * C) + t * C + c;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
+        else *dst = __ldg(src);
     }
 }
 // din[b, y, x, c] = sum over taps of dcol[(b, y - kh, x - kw), (kh, kw, c)]
+template <int VEC>
 __global__ void fold3_kernel(const float* __restrict__ dcol, int nb, int Hh, int Ww, int C, float* __restrict__ din) {
-    const int Ho = Hh - 2, Wo = Ww - 2, K = 9 * C;
-    const int64_t n = (int64_t)nb * Hh * Ww * C;
+    const int Ho = Hh - 2, Wo = Ww - 2, K = 9 * C, CV = C / VEC;
+    const int64_t n = (int64_t)nb * Hh * Ww * CV;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int x = (int)((i / C) % Ww), y = (int)((i / ((int64_t)C * Ww)) % Hh);
-        const int64_t b = i / ((int64_t)C * Ww * Hh);
-        float s = 0.f;
+        const int64_t p = i / CV;                        // (b * Hh + y) * Ww + x
+        const int c = (int)(i - p * CV) * VEC;
+        const int64_t by = p / Ww;
+        const int x = (int)(p - by * Ww);
+        const int b = (int)(by / Hh), y = (int)(by - (int64_t)b * Hh);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kh = 0; kh < 3; kh++) {
             const int yo = y - kh;
@@ -97,10 +106,13 @@ __global__ void fold3_kernel(const float* __restrict__ dcol, int nb, int Hh, int
             for (int kw = 0; kw < 3; kw++) {
                 const int xo = x - kw;
                 if (xo < 0 || xo >= Wo) continue;
-                s += __ldg(dcol + ((b * Ho + yo) * Wo + xo) * K + (kh * 3 + kw) * C + c);
+                const float* src = dcol + (((int64_t)b * Ho + yo) * Wo + xo) * K + (kh * 3 + kw) * C + c;
+                if (VEC == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(src)); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+                else s.x += __ldg(src);
             }
         }
-        din[i] = s;
+        if (VEC == 4) *reinterpret_cast<float4*>(din + p * C + c) = s;
+        else din[p * C + c] = s.x;
     }
 }
 __global__ void relu_kernel(float* __restrict__ y, int64_t n) {
@@ -183,7 +195,8 @@ static int grid_for(s2s_ctx* ctx, int64_t n) {
 static int conv_relu_fwd(s2s_ctx* ctx, const float* in, int nb, int Hh, int Ww, int C, const float* Wp, const float* bias, int N, float* col,
                          float* out) {
     const int64_t M = (int64_t)nb * (Hh - 2) * (Ww - 2);
-    VGG_LAUNCH(unfold3_kernel, M * 9 * C, in, nb, Hh, Ww, C, col);
+    if (C % 4 == 0) VGG_LAUNCH(unfold3_kernel<4>, M * 9 * C / 4, in, nb, Hh, Ww, C, col);
+    else VGG_LAUNCH(unfold3_kernel<1>, M * 9 * C, in, nb, Hh, Ww, C, col);
     S2S_TRY(gemm_f32(ctx, false, true, (int)M, N, 9 * C, 1.f, col, 9 * C, Wp, 9 * C, 0.f, out, N, bias));
     VGG_LAUNCH(relu_kernel, M * N, out, M * N);
     return 0;
@@ -193,12 +206,14 @@ static int conv_relu_bwd(s2s_ctx* ctx, const float* in, const float* out, float*
                          float* col, float* dcol, float* dWp, float* db, float* din) {
     const int64_t M = (int64_t)nb * (Hh - 2) * (Ww - 2);
     VGG_LAUNCH(relu_bwd_kernel, M * N, dout, out, M * N);
-    VGG_LAUNCH(unfold3_kernel, M * 9 * C, in, nb, Hh, Ww, C, col);
+    if (C % 4 == 0) VGG_LAUNCH(unfold3_kernel<4>, M * 9 * C / 4, in, nb, Hh, Ww, C, col);
+    else VGG_LAUNCH(unfold3_kernel<1>, M * 9 * C, in, nb, Hh, Ww, C, col);
     S2S_TRY(gemm_f32(ctx, true, false, N, 9 * C, (int)M, 1.f, dout, N, col, 9 * C, 1.f, dWp, 9 * C, nullptr, GemmBatch(), 8));
     S2S_TRY(colsum_add(ctx, dout, M, N, N, db));
     if (din) {
         S2S_TRY(gemm_f32(ctx, false, false, (int)M, 9 * C, N, 1.f, dout, N, Wp, 9 * C, 0.f, dcol, 9 * C));
-        VGG_LAUNCH(fold3_kernel, (int64_t)nb * Hh * Ww * C, dcol, nb, Hh, Ww, C, din);
+        if (C % 4 == 0) VGG_LAUNCH(fold3_kernel<4>, (int64_t)nb * Hh * Ww * C / 4, dcol, nb, Hh, Ww, C, din);
+        else VGG_LAUNCH(fold3_kernel<1>, (int64_t)nb * Hh * Ww * C, dcol, nb, Hh, Ww, C, din);
     }
     return 0;
 }

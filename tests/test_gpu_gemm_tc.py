@@ -90,3 +90,20 @@ def test_gemm_tcgen05_unaligned_k(s2s, gctx):
     s2s.gemm(gctx, dev(A), dev(W)[:, 256:], tA=False, tB=True, C_out=Cd, impl=2)
     torch.cuda.synchronize()
     assert rel_err(Cd.cpu().numpy(), ref) < 2e-5
+
+
+@pytest.mark.parametrize("form,M,N,K", [("NT", 5000, 64, 576), ("NT", 3000, 128, 1152), ("NT", 2000, 100, 96), ("NN", 4000, 27, 64),
+                                        ("TN", 64, 576, 20000), ("TN", 128, 123, 9600)])
+def test_gemm_tcgen05_narrow_tiles(s2s, gctx, form, M, N, K):
+    # N <= 64 / <= 128 run on 64- / 128-wide tiles (the 64- and 128-plane convolutions of the VGG front-end)
+    rng = np.random.default_rng(M + N + K)
+    tA, tB = form[0] == "T", form[1] == "T"
+    A = rng.standard_normal((K, M) if tA else (M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tB else (K, N)).astype(np.float32)
+    beta = 1.0 if tA else 0.0
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64) + beta * C0
+    Cd = dev(C0)
+    s2s.gemm(gctx, dev(A), dev(B), tA=tA, tB=tB, beta=beta, C_out=Cd, impl=2)
+    torch.cuda.synchronize()
+    assert rel_err(Cd.cpu().numpy(), ref) < 2e-5
