@@ -25,6 +25,7 @@
 // along K into equal shares ("stream-K" tail) whose partial sums are added with atomics, so that e.g. 150 tiles
 // on 148 SMs cost ~1.25 tile times instead of 2.  Weight gradients (few tiles, K = B*L) are all tail.
 #include <cuda.h>
+#include <stdio.h>
 
 #include "common.cuh"
 
@@ -51,6 +52,13 @@ struct Sched {
     int rem;                      // tiles left for the stream-K tail
     int Gp;                       // CTAs that take a share of the tail
     int dbg;                      // timing experiments (S2S_TC_DBG): 1 = no MMAs (TMA stream only), 2 = no TMA (MMA issue only)
+    // implicit 3x3 convolution (channels-last activations on their full grid): K = taps * tap_slabs * 32; slab kb belongs to
+    // tap kb / tap_slabs and reads the A operand tap_row[tap] ROWS further down (forward: +(kh*W + kw) pixels, data gradient:
+    // minus that; rows outside the matrix read as zeros) at K offset (kb % tap_slabs) * 32.  b_col0: K offset added to the B
+    // operand's coordinate (weight gradient of one tap: the transposed activations shifted by the tap's pixel offset).
+    int tap_slabs;                // 0 = plain GEMM
+    int tap_row[9];
+    int b_col0;
 };
 struct Span { int tm, tn, kb0, kb1; };
 
@@ -178,10 +186,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                     unsigned char* st = base + (size_t)s * STAGE_BYTES;
                     if (sched.dbg == 2) { mbar_arrive(&full[s]); continue; }
                     mbar_expect_tx(&full[s], STAGE_BYTES);
-                    tma_load_2d(st, &mapAh, kb * BK, m0, &full[s]);
-                    tma_load_2d(st + A_BYTES, &mapAl, kb * BK, m0, &full[s]);
-                    tma_load_2d(st + 2 * A_BYTES, &mapBh, kb * BK, n0, &full[s]);
-                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, kb * BK, n0, &full[s]);
+                    int ak = kb * BK, am = m0;
+                    if (sched.tap_slabs > 0) {
+                        const int tap = kb / sched.tap_slabs;
+                        ak = (kb - tap * sched.tap_slabs) * BK;
+                        am = m0 + sched.tap_row[tap];
+                    }
+                    tma_load_2d(st, &mapAh, ak, am, &full[s]);
+                    tma_load_2d(st + A_BYTES, &mapAl, ak, am, &full[s]);
+                    tma_load_2d(st + 2 * A_BYTES, &mapBh, kb * BK + sched.b_col0, n0, &full[s]);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, kb * BK + sched.b_col0, n0, &full[s]);
                 }
             }
         }
@@ -321,12 +335,15 @@ __global__ void split_kernel(const float* __restrict__ src, int rows, int K, int
     }
 }
 // src is [K, rows] (pitch ld): transposed split into hi, lo [rows, Kp]
-__global__ void transpose_split_kernel(const float* __restrict__ src, int K, int rows, int ld, float* __restrict__ hi, float* __restrict__ lo, int Kp) {
+// shift: dst[r][k] = src[k + shift][r] (zeros beyond the end) -- TMA box origins must be 16-byte aligned, so an operand that
+// has to be read at arbitrary K offsets (the weight gradient of a convolution tap) is prepared in four phases
+__global__ void transpose_split_kernel(const float* __restrict__ src, int K, int rows, int ld, float* __restrict__ hi, float* __restrict__ lo, int Kp,
+                                       int shift) {
     __shared__ float t[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x;          // source column = output row
     for (int i = threadIdx.y; i < 32; i += 8) {
         const int k = blockIdx.y * 32 + i;
-        t[i][threadIdx.x] = (k < K && c < rows) ? __ldg(src + (size_t)k * ld + c) : 0.f;
+        t[i][threadIdx.x] = (k + shift < K && c < rows) ? __ldg(src + (size_t)(k + shift) * ld + c) : 0.f;
     }
     __syncthreads();
     const int k2 = blockIdx.y * 32 + threadIdx.x;
@@ -415,7 +432,7 @@ static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, b
     const bool raw = !transposed && tc_rawhi() && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     if (!raw) S2S_ALLOC(hi, ctx->arena, float, (size_t)rows * Kp);
     if (transposed) {
-        transpose_split_kernel<<<dim3(ceil_div(rows, 32), ceil_div(Kp, 32)), dim3(32, 8), 0, ctx->stream>>>(src, K, rows, ld, hi, lo, Kp);
+        transpose_split_kernel<<<dim3(ceil_div(rows, 32), ceil_div(Kp, 32)), dim3(32, 8), 0, ctx->stream>>>(src, K, rows, ld, hi, lo, Kp, 0);
     } else {
         const long long n4 = (long long)rows * (Kp >> 2);
         int blocks = (int)((n4 + 255) / 256);
@@ -426,6 +443,113 @@ static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, b
     op->hi = raw ? src : hi; op->ld_hi = raw ? ld : Kp;
     op->lo = lo; op->ld_lo = Kp;
     if (ctx->tc_cache_on) ctx->tc_cache.push_back(TcCacheEntry{src, K, rows, ld, transposed, op->hi, op->lo, op->ld_hi, op->ld_lo});
+    return 0;
+}
+
+struct TcConv { int tap_slabs = 0; int tap_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; int b_col0 = 0; int a_cols = 0; };
+
+// C[M,N] = alpha A' B^T (+beta C)(+bias) with prepared (K-contiguous, hi/lo) operands.  Plain GEMM: A' = A [M,K].  With
+// cv.tap_slabs > 0 the A operand is the [M, a_cols] activation matrix read at 9 row offsets (implicit 3x3 convolution).
+static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a, const TcOp& b, float beta, float* C, int ldc, const float* bias,
+                  const TcConv& cv) {
+    using namespace tc;
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    Sched sc;
+    sc.tiles_m = ceil_div(M, BM); sc.tiles_n = ceil_div(N, BN); sc.nk = ceil_div(K, BK);
+    sc.G = ctx->sm_count;
+    static const int dbg_mode = env_int("S2S_TC_DBG", 0), tail_on = env_int("S2S_TC_TAIL", 1);
+    sc.dbg = dbg_mode;
+    sc.tap_slabs = cv.tap_slabs; sc.b_col0 = cv.b_col0;
+    for (int t = 0; t < 9; t++) sc.tap_row[t] = cv.tap_row[t];
+    const int Tt = sc.tiles_m * sc.tiles_n;
+    sc.R = Tt / sc.G; sc.rem = Tt - sc.R * sc.G;
+    // tail: cut the left-over tiles along K into >= MIN_SHARE-slab shares; if that gives no more CTAs than tiles, or C
+    // cannot take atomic partial sums (beta other than 0 / 1), the tail is an ordinary partial round of whole tiles
+    const long long U = (long long)sc.rem * sc.nk;
+    sc.Gp = (int)(U / MIN_SHARE < sc.G ? U / MIN_SHARE : sc.G);
+    if (sc.Gp <= sc.rem || (beta != 0.f && beta != 1.f) || !tail_on) sc.Gp = sc.rem;
+    const bool atomics = sc.Gp > sc.rem;
+
+    const int aK = cv.tap_slabs > 0 ? cv.a_cols : K;           // extent of the A operand's K axis in memory
+    const int bK = K;                                          // true extent: shifted slabs beyond it read zeros
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if (!make_map(&mAh, a.hi, M, aK, a.ld_hi, BM) || !make_map(&mAl, a.lo, M, aK, a.ld_lo, BM) ||
+        !make_map(&mBh, b.hi, N, bK, b.ld_hi, BN) || !make_map(&mBl, b.lo, N, bK, b.ld_lo, BN))
+        return fail("gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", M, N, K);
+    static bool attr = false;
+    if (!attr) {
+        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64)));
+        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128)));
+        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(256)));
+        attr = true;
+    }
+    if (atomics && beta == 0.f) {
+        zero_tiles_kernel<<<sc.rem, 256, 0, ctx->stream>>>(C, ldc, M, N, sc.tiles_n, sc.R * sc.G, BN);
+        S2S_LAUNCH_CHECK(ctx);
+    }
+    if (dbg_mode == 9) {
+        fprintf(stderr, "[gemm_tc] M=%d N=%d K=%d BN=%d tiles=%dx%d nk=%d R=%d rem=%d Gp=%d taps=%d row0=%d row8=%d bcol=%d beta=%g\n", M, N, K, BN, sc.tiles_m,
+                sc.tiles_n, sc.nk, sc.R, sc.rem, sc.Gp, sc.tap_slabs, sc.tap_row[0], sc.tap_row[8], sc.b_col0, (double)beta);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    prof_begin(ctx, S2S_PROF_GEMM);
+    if (BN == 64) gemm_tc_kernel<64><<<sc.G, THREADS, smem_bytes(64), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
+    else if (BN == 128) gemm_tc_kernel<128><<<sc.G, THREADS, smem_bytes(128), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
+    else gemm_tc_kernel<256><<<sc.G, THREADS, smem_bytes(256), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
+    prof_end(ctx, S2S_PROF_GEMM, 2.0 * M * N * (double)K);
+    S2S_LAUNCH_CHECK(ctx);
+    if (dbg_mode == 9) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[gemm_tc]   -> %s\n", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+// ---- implicit 3x3 convolution on channels-last activations kept on their FULL grid [nb, Hh, Ww, C] -------------------------
+// (rows = pixels; the valid region shrinks by 2 per convolution, rows outside it hold don't-care values)
+//   forward        out[m, n]  = sum_t sum_c in[m + off_t, c] Wp[n, t*C + c] + bias[n]          off_t = kh*Ww + kw
+//   data gradient  din[m, c]  = sum_t sum_n dout[m - off_t, n] WpT[c, t*N + n]                  (dout zero outside its valid region)
+//   weight grad.   dWp[n, t*C + c] += sum_m dout[m, n] in[m + off_t, c]                         one launch per tap, K = pixels
+// C and N must be multiples of 32 (one tap = whole 128-byte slabs).
+int conv3_tc_forward(s2s_ctx* ctx, const float* in, int64_t Mg, int Ww, int C, const float* Wp, const float* bias, int N, float* out) {
+    S2S_REQUIRE(C % 32 == 0 && Mg < (1ll << 31), "conv3_tc_forward: C must be a multiple of 32");
+    if (!get_encode()) return fail("conv3_tc: cuTensorMapEncodeTiled unavailable");
+    TcOp a, b;
+    S2S_TRY(tc_prepare(ctx, in, (int)Mg, C, C, false, &a));
+    S2S_TRY(tc_prepare(ctx, Wp, N, 9 * C, 9 * C, false, &b));
+    TcConv cv; cv.tap_slabs = C / 32; cv.a_cols = C;
+    for (int t = 0; t < 9; t++) cv.tap_row[t] = (t / 3) * Ww + (t % 3);
+    return tc_run(ctx, (int)Mg, N, 9 * C, 1.f, a, b, 0.f, out, N, bias, cv);
+}
+// WpT [C, 9N]: WpT[c, t*N + n] = Wp[n, t*C + c] (prepared by the caller)
+int conv3_tc_dgrad(s2s_ctx* ctx, const float* dout, int64_t Mg, int Ww, int N, const float* WpT, int C, float* din) {
+    S2S_REQUIRE(N % 32 == 0 && Mg < (1ll << 31), "conv3_tc_dgrad: N must be a multiple of 32");
+    TcOp a, b;
+    S2S_TRY(tc_prepare(ctx, dout, (int)Mg, N, N, false, &a));
+    S2S_TRY(tc_prepare(ctx, WpT, C, 9 * N, 9 * N, false, &b));
+    TcConv cv; cv.tap_slabs = N / 32; cv.a_cols = N;
+    for (int t = 0; t < 9; t++) cv.tap_row[t] = -((t / 3) * Ww + (t % 3));
+    return tc_run(ctx, (int)Mg, C, 9 * N, 1.f, a, b, 0.f, din, C, nullptr, cv);
+}
+int conv3_tc_wgrad(s2s_ctx* ctx, const float* dout, const float* in, int64_t Mg, int Ww, int N, int C, float* dWp) {
+    S2S_REQUIRE(Mg < (1ll << 31), "conv3_tc_wgrad: too many pixels");
+    TcOp a, b[4];
+    S2S_TRY(tc_prepare(ctx, dout, N, (int)Mg, N, true, &a));          // dout^T [N, Mg]
+    // in^T [C, Mg] shifted by 0..3 pixels: tap offset = 4 q + phase, the aligned part goes into the TMA coordinate
+    const int K = (int)Mg, Kp = (K + 3) & ~3;
+    for (int ph = 0; ph < 4; ph++) {
+        float *hi, *lo;
+        S2S_ALLOC(hi, ctx->arena, float, (size_t)C * Kp);
+        S2S_ALLOC(lo, ctx->arena, float, (size_t)C * Kp);
+        transpose_split_kernel<<<dim3(ceil_div(C, 32), ceil_div(Kp, 32)), dim3(32, 8), 0, ctx->stream>>>(in, K, C, C, hi, lo, Kp, ph);
+        S2S_LAUNCH_CHECK(ctx);
+        b[ph].hi = hi; b[ph].lo = lo; b[ph].ld_hi = Kp; b[ph].ld_lo = Kp;
+    }
+    for (int t = 0; t < 9; t++) {
+        const int off = (t / 3) * Ww + (t % 3);
+        TcConv cv; cv.b_col0 = off & ~3;
+        S2S_TRY(tc_run(ctx, N, C, K, 1.f, a, b[off & 3], 1.f, dWp + (size_t)t * C, 9 * C, nullptr, cv));
+    }
     return 0;
 }
 
@@ -444,45 +568,10 @@ int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha
     if (!force && (double)M * N * K < 5e8) return 0;
     if (!get_encode()) return 0;
 
-    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    Sched sc;
-    sc.tiles_m = ceil_div(M, BM); sc.tiles_n = ceil_div(N, BN); sc.nk = ceil_div(K, BK);
-    sc.G = ctx->sm_count;
-    static const int dbg_mode = env_int("S2S_TC_DBG", 0), tail_on = env_int("S2S_TC_TAIL", 1);
-    sc.dbg = dbg_mode;
-    const int Tt = sc.tiles_m * sc.tiles_n;
-    sc.R = Tt / sc.G; sc.rem = Tt - sc.R * sc.G;
-    // tail: cut the left-over tiles along K into >= MIN_SHARE-slab shares; if that gives no more CTAs than tiles, or C
-    // cannot take atomic partial sums (beta other than 0 / 1), the tail is an ordinary partial round of whole tiles
-    const long long U = (long long)sc.rem * sc.nk;
-    sc.Gp = (int)(U / MIN_SHARE < sc.G ? U / MIN_SHARE : sc.G);
-    if (sc.Gp <= sc.rem || (beta != 0.f && beta != 1.f) || !tail_on) sc.Gp = sc.rem;
-    const bool atomics = sc.Gp > sc.rem;
-
     TcOp a, b;
     S2S_TRY(tc_prepare(ctx, A, M, K, lda, tA, &a));                       // tA: A is [K, M]
     S2S_TRY(tc_prepare(ctx, B, N, K, ldb, !tB, &b));                      // !tB: B is [K, N]
-    CUtensorMap mAh, mAl, mBh, mBl;
-    if (!make_map(&mAh, a.hi, M, K, a.ld_hi, BM) || !make_map(&mAl, a.lo, M, K, a.ld_lo, BM) ||
-        !make_map(&mBh, b.hi, N, K, b.ld_hi, BN) || !make_map(&mBl, b.lo, N, K, b.ld_lo, BN))
-        return fail("gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", M, N, K);
-    static bool attr = false;
-    if (!attr) {
-        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64)));
-        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128)));
-        S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(256)));
-        attr = true;
-    }
-    if (atomics && beta == 0.f) {
-        zero_tiles_kernel<<<sc.rem, 256, 0, ctx->stream>>>(C, ldc, M, N, sc.tiles_n, sc.R * sc.G, BN);
-        S2S_LAUNCH_CHECK(ctx);
-    }
-    prof_begin(ctx, S2S_PROF_GEMM);
-    if (BN == 64) gemm_tc_kernel<64><<<sc.G, THREADS, smem_bytes(64), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
-    else if (BN == 128) gemm_tc_kernel<128><<<sc.G, THREADS, smem_bytes(128), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
-    else gemm_tc_kernel<256><<<sc.G, THREADS, smem_bytes(256), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
-    prof_end(ctx, S2S_PROF_GEMM, 2.0 * M * N * (double)K);
-    S2S_LAUNCH_CHECK(ctx);
+    S2S_TRY(tc_run(ctx, M, N, K, alpha, a, b, beta, C, ldc, bias, TcConv()));
     *handled = true;
     return 0;
 }

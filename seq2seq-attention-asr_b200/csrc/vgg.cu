@@ -10,6 +10,8 @@
 // order are permuted per call into the channels-last order the GEMMs read, and their gradients are permuted back.
 // Utterances are processed in chunks so the patch matrix stays bounded.  Next: implicit GEMM (TMA tap offsets, no patch
 // matrix), 64/128-wide GEMM tiles for the 64- and 128-plane layers, ReLU in the GEMM epilogue.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -40,7 +42,7 @@ static int vgg_dims(const s2s_vgg_cfg* cfg, int B, int T, int F, VggDims* d) {
 
 struct VggState {
     Arena mem;
-    bool valid = false;
+    bool valid = false, implicit = false;
     VggDims d;
     float *a0 = nullptr, *a1 = nullptr, *a2 = nullptr, *p1 = nullptr, *a3 = nullptr, *a4 = nullptr, *f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -123,9 +125,10 @@ __global__ void relu_bwd_kernel(float* __restrict__ dy, const float* __restrict_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dy[i] = y[i] > 0.f ? dy[i] : 0.f;
 }
-// SpatialMaxPooling(kW, kH, kW, kH), floor mode
-__global__ void pool_fwd_kernel(const float* __restrict__ in, int nb, int Hh, int Ww, int C, int kH, int kW, float* __restrict__ out) {
-    const int Ho = Hh / kH, Wo = Ww / kW;
+// SpatialMaxPooling(kW, kH, kW, kH), floor mode.  The input lives on a grid of pitch (Hh, Ww) of which (Hv, Wv) is valid
+// (the implicit convolutions keep their outputs on the input's grid); the output is compact.
+__global__ void pool_fwd_kernel(const float* __restrict__ in, int nb, int Hh, int Ww, int Hv, int Wv, int C, int kH, int kW, float* __restrict__ out) {
+    const int Ho = Hv / kH, Wo = Wv / kW;
     const int64_t n = (int64_t)nb * Ho * Wo * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -137,10 +140,11 @@ __global__ void pool_fwd_kernel(const float* __restrict__ in, int nb, int Hh, in
         out[i] = m;
     }
 }
-// the gradient goes to the first maximum of the window in (kh, kw) scan order
-__global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, int nb, int Hh, int Ww, int C, int kH, int kW,
-                                float* __restrict__ din) {
-    const int Ho = Hh / kH, Wo = Ww / kW;
+// the gradient goes to the first maximum of the window in (kh, kw) scan order; written on the input's grid, zero outside
+// the pooled region (so the convolution below sees zeros wherever its output is not valid)
+__global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, int nb, int Hh, int Ww, int Hv, int Wv, int C, int kH,
+                                int kW, float* __restrict__ din) {
+    const int Ho = Hv / kH, Wo = Wv / kW;
     const int64_t n = (int64_t)nb * Hh * Ww * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -159,6 +163,13 @@ __global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __res
         }
         din[i] = g;
     }
+}
+// WpT[c, t*N + n] = Wp[n, t*C + c]   (the data-gradient operand of the implicit convolution)
+__global__ void wperm_t_kernel(const float* __restrict__ Wp, int N, int C, float* __restrict__ WpT) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // over WpT [C, 9, N]
+    if (i >= (int64_t)N * C * 9) return;
+    const int n = (int)(i % N), t = (int)((i / N) % 9), c = (int)(i / ((int64_t)N * 9));
+    WpT[i] = Wp[((int64_t)n * 9 + t) * C + c];
 }
 // module weight [N, C*S] in (c, s) column order  <->  channels-last [N, S*C] in (s, c) order   (S = 9 taps, or the freq bins)
 __global__ void wperm_kernel(const float* __restrict__ W, int N, int C, int S, float* __restrict__ Wp) {
@@ -218,6 +229,20 @@ static int conv_relu_bwd(s2s_ctx* ctx, const float* in, const float* out, float*
     return 0;
 }
 
+int conv3_tc_forward(s2s_ctx* ctx, const float* in, int64_t Mg, int Ww, int C, const float* Wp, const float* bias, int N, float* out);
+int conv3_tc_dgrad(s2s_ctx* ctx, const float* dout, int64_t Mg, int Ww, int N, const float* WpT, int C, float* din);
+int conv3_tc_wgrad(s2s_ctx* ctx, const float* dout, const float* in, int64_t Mg, int Ww, int N, int C, float* dWp);
+
+// Implicit-GEMM path (default when the plane counts are multiples of 32): conv2-4 read their input through nine TMA row
+// offsets instead of a patch matrix, and keep their output on the INPUT's grid -- conv2 on the (H1, W1) grid of conv1's
+// output, conv3 and conv4 on the (H2, Wp1) grid of the first pooling -- with a valid region that shrinks by two per layer;
+// the poolings compact.  conv1 (3 planes) keeps the explicit patch path.
+static bool vgg_implicit(const VggDims& d) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("S2S_VGG_IMPLICIT"); enabled = e ? atoi(e) : 1; }
+    return enabled && d.C1 % 32 == 0 && d.C2 % 32 == 0;
+}
+
 static int vgg_chunk(const VggDims& d) {
     // patch matrices of the largest layer for one utterance, in floats
     const int64_t per = std::max((int64_t)d.H2 * d.W2 * 9 * d.C1, (int64_t)d.H4 * d.W4 * 9 * d.C2);
@@ -252,10 +277,16 @@ int s2s_vgg_forward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, const 
     const int C1 = d.C1, C2 = d.C2;
     S2S_ALLOC(s.a0, s.mem, float, (size_t)B * T * F * 3);
     S2S_ALLOC(s.a1, s.mem, float, (size_t)B * d.H1 * d.W1 * C1);
-    S2S_ALLOC(s.a2, s.mem, float, (size_t)B * d.H2 * d.W2 * C1);
+    const bool imp = vgg_implicit(d);
+    s.implicit = imp;
+    // per-utterance sizes: compact (explicit path) or on the producing grid (implicit path)
+    const size_t n_a2 = imp ? (size_t)d.H1 * d.W1 * C1 : (size_t)d.H2 * d.W2 * C1;
+    const size_t n_a3 = imp ? (size_t)d.H2 * d.Wp1 * C2 : (size_t)d.H3 * d.W3 * C2;
+    const size_t n_a4 = imp ? (size_t)d.H2 * d.Wp1 * C2 : (size_t)d.H4 * d.W4 * C2;
+    S2S_ALLOC(s.a2, s.mem, float, (size_t)B * n_a2);
     S2S_ALLOC(s.p1, s.mem, float, (size_t)B * d.H2 * d.Wp1 * C1);
-    S2S_ALLOC(s.a3, s.mem, float, (size_t)B * d.H3 * d.W3 * C2);
-    S2S_ALLOC(s.a4, s.mem, float, (size_t)B * d.H4 * d.W4 * C2);
+    S2S_ALLOC(s.a3, s.mem, float, (size_t)B * n_a3);
+    S2S_ALLOC(s.a4, s.mem, float, (size_t)B * n_a4);
     const int64_t rows = (int64_t)B * d.L;
     S2S_ALLOC(s.f[0], s.mem, float, (size_t)rows * d.view);
     for (int k = 1; k <= 3; k++) S2S_ALLOC(s.f[k], s.mem, float, (size_t)rows * d.HID);
@@ -272,25 +303,38 @@ int s2s_vgg_forward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, const 
     VGG_LAUNCH_FLAT(wperm_kernel, (int64_t)d.HID * d.view, P + d.off[8], d.HID, C2, d.Wq, W1p);
     VGG_LAUNCH_FLAT(nchw_to_nhwc_kernel, (int64_t)B * T * F * 3, X, 3, (int64_t)T * F, (int64_t)B * T * F * 3, s.a0);
 
-    const int chunk = vgg_chunk(d);
+    const int chunk = imp ? std::min(B, 8) : vgg_chunk(d);
     float* col;
-    S2S_ALLOC(col, ar, float, (size_t)chunk * std::max((int64_t)d.H2 * d.W2 * 9 * C1, (int64_t)d.H4 * d.W4 * 9 * C2));
+    S2S_ALLOC(col, ar, float, imp ? (size_t)chunk * d.H1 * d.W1 * 27 : (size_t)chunk * std::max((int64_t)d.H2 * d.W2 * 9 * C1, (int64_t)d.H4 * d.W4 * 9 * C2));
     const std::vector<size_t> mk = ar.mark();
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         ar.rewind(mk);                                   // the GEMMs' operand copies of the previous chunk
-        S2S_TRY(conv_relu_fwd(ctx, s.a0 + (size_t)b0 * T * F * 3, nb, T, F, 3, Wp[0], P + d.off[1], C1, col, s.a1 + (size_t)b0 * d.H1 * d.W1 * C1));
-        S2S_TRY(conv_relu_fwd(ctx, s.a1 + (size_t)b0 * d.H1 * d.W1 * C1, nb, d.H1, d.W1, C1, Wp[1], P + d.off[3], C1, col,
-                              s.a2 + (size_t)b0 * d.H2 * d.W2 * C1));
-        VGG_LAUNCH(pool_fwd_kernel, (int64_t)nb * d.H2 * d.Wp1 * C1, s.a2 + (size_t)b0 * d.H2 * d.W2 * C1, nb, d.H2, d.W2, C1, 1, 2,
-                   s.p1 + (size_t)b0 * d.H2 * d.Wp1 * C1);
-        S2S_TRY(conv_relu_fwd(ctx, s.p1 + (size_t)b0 * d.H2 * d.Wp1 * C1, nb, d.H2, d.Wp1, C1, Wp[2], P + d.off[5], C2, col,
-                              s.a3 + (size_t)b0 * d.H3 * d.W3 * C2));
-        S2S_TRY(conv_relu_fwd(ctx, s.a3 + (size_t)b0 * d.H3 * d.W3 * C2, nb, d.H3, d.W3, C2, Wp[3], P + d.off[7], C2, col,
-                              s.a4 + (size_t)b0 * d.H4 * d.W4 * C2));
-        // pooled [nb, L, Wq, C2] is the flattened feature matrix [nb*L, view] in (freq, feature) column order
-        VGG_LAUNCH(pool_fwd_kernel, (int64_t)nb * d.L * d.view, s.a4 + (size_t)b0 * d.H4 * d.W4 * C2, nb, d.H4, d.W4, C2, 2, 2,
-                   s.f[0] + (size_t)b0 * d.L * d.view);
+        float* a1 = s.a1 + (size_t)b0 * d.H1 * d.W1 * C1;
+        float* a2 = s.a2 + (size_t)b0 * n_a2;
+        float* p1 = s.p1 + (size_t)b0 * d.H2 * d.Wp1 * C1;
+        float* a3 = s.a3 + (size_t)b0 * n_a3;
+        float* a4 = s.a4 + (size_t)b0 * n_a4;
+        float* f0 = s.f[0] + (size_t)b0 * d.L * d.view;
+        S2S_TRY(conv_relu_fwd(ctx, s.a0 + (size_t)b0 * T * F * 3, nb, T, F, 3, Wp[0], P + d.off[1], C1, col, a1));
+        if (imp) {
+            const int64_t M1 = (int64_t)nb * d.H1 * d.W1, M2 = (int64_t)nb * d.H2 * d.Wp1;
+            S2S_TRY(conv3_tc_forward(ctx, a1, M1, d.W1, C1, Wp[1], P + d.off[3], C1, a2));                  // grid (H1, W1), valid (H2, W2)
+            VGG_LAUNCH(relu_kernel, M1 * C1, a2, M1 * C1);
+            VGG_LAUNCH(pool_fwd_kernel, (int64_t)nb * d.H2 * d.Wp1 * C1, a2, nb, d.H1, d.W1, d.H2, d.W2, C1, 1, 2, p1);
+            S2S_TRY(conv3_tc_forward(ctx, p1, M2, d.Wp1, C1, Wp[2], P + d.off[5], C2, a3));                 // grid (H2, Wp1), valid (H3, W3)
+            VGG_LAUNCH(relu_kernel, M2 * C2, a3, M2 * C2);
+            S2S_TRY(conv3_tc_forward(ctx, a3, M2, d.Wp1, C2, Wp[3], P + d.off[7], C2, a4));                 // same grid, valid (H4, W4)
+            VGG_LAUNCH(relu_kernel, M2 * C2, a4, M2 * C2);
+            VGG_LAUNCH(pool_fwd_kernel, (int64_t)nb * d.L * d.view, a4, nb, d.H2, d.Wp1, d.H4, d.W4, C2, 2, 2, f0);
+        } else {
+            S2S_TRY(conv_relu_fwd(ctx, a1, nb, d.H1, d.W1, C1, Wp[1], P + d.off[3], C1, col, a2));
+            VGG_LAUNCH(pool_fwd_kernel, (int64_t)nb * d.H2 * d.Wp1 * C1, a2, nb, d.H2, d.W2, d.H2, d.W2, C1, 1, 2, p1);
+            S2S_TRY(conv_relu_fwd(ctx, p1, nb, d.H2, d.Wp1, C1, Wp[2], P + d.off[5], C2, col, a3));
+            S2S_TRY(conv_relu_fwd(ctx, a3, nb, d.H3, d.W3, C2, Wp[3], P + d.off[7], C2, col, a4));
+            // pooled [nb, L, Wq, C2] is the flattened feature matrix [nb*L, view] in (freq, feature) column order
+            VGG_LAUNCH(pool_fwd_kernel, (int64_t)nb * d.L * d.view, a4, nb, d.H4, d.W4, d.H4, d.W4, C2, 2, 2, f0);
+        }
     }
     ar.rewind(mk);
     // 1x1 stack over all frames: TemporalConvolution(k = 1) + ReLU   (model_vgg.lua:47-54)
@@ -349,14 +393,24 @@ int s2s_vgg_backward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, float
     // ga = d f0 [B*L, view] = d pooled [B, L, Wq, C2]
 
     // ---- convolutional part, chunk by chunk ------------------------------------------------------------------------------
-    const int chunk = vgg_chunk(d);
-    const int64_t colmax = std::max((int64_t)d.H2 * d.W2 * 9 * C1, (int64_t)d.H4 * d.W4 * 9 * C2);
-    const int64_t actmax = std::max(std::max((int64_t)d.H1 * d.W1 * C1, (int64_t)d.H3 * d.W3 * C2), (int64_t)T * F * 3);
-    float *col, *dcol, *da, *db_;
+    const bool imp = s.implicit;
+    const size_t n_a2 = imp ? (size_t)d.H1 * d.W1 * C1 : (size_t)d.H2 * d.W2 * C1;
+    const size_t n_a3 = imp ? (size_t)d.H2 * d.Wp1 * C2 : (size_t)d.H3 * d.W3 * C2;
+    const size_t n_a4 = imp ? (size_t)d.H2 * d.Wp1 * C2 : (size_t)d.H4 * d.W4 * C2;
+    const int chunk = imp ? std::min(B, 8) : vgg_chunk(d);
+    const int64_t colmax = imp ? (int64_t)d.H1 * d.W1 * 27 : std::max((int64_t)d.H2 * d.W2 * 9 * C1, (int64_t)d.H4 * d.W4 * 9 * C2);
+    const int64_t actmax = std::max(std::max((int64_t)d.H1 * d.W1 * C1, (int64_t)d.H2 * d.Wp1 * C2), (int64_t)T * F * 3);
+    float *col, *dcol, *da, *db_, *WpT[4] = {nullptr, nullptr, nullptr, nullptr};
     S2S_ALLOC(col, ar, float, (size_t)chunk * colmax);
     S2S_ALLOC(dcol, ar, float, (size_t)chunk * colmax);
     S2S_ALLOC(da, ar, float, (size_t)chunk * actmax);
     S2S_ALLOC(db_, ar, float, (size_t)chunk * actmax);
+    if (imp) {
+        for (int l = 1; l < 4; l++) {
+            S2S_ALLOC(WpT[l], ar, float, (size_t)cout[l] * cin[l] * 9);
+            VGG_LAUNCH_FLAT(wperm_t_kernel, (int64_t)cout[l] * cin[l] * 9, Wp[l], cout[l], cin[l], WpT[l]);
+        }
+    }
     float* dXc = nullptr;
     if (dX) S2S_ALLOC(dXc, ar, float, (size_t)B * T * F * 3);
     const std::vector<size_t> mk = ar.mark();
@@ -365,16 +419,37 @@ int s2s_vgg_backward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, float
         ar.rewind(mk);
         const float* a0 = s.a0 + (size_t)b0 * T * F * 3;
         const float* a1 = s.a1 + (size_t)b0 * d.H1 * d.W1 * C1;
-        const float* a2 = s.a2 + (size_t)b0 * d.H2 * d.W2 * C1;
+        const float* a2 = s.a2 + (size_t)b0 * n_a2;
         const float* p1 = s.p1 + (size_t)b0 * d.H2 * d.Wp1 * C1;
-        const float* a3 = s.a3 + (size_t)b0 * d.H3 * d.W3 * C2;
-        const float* a4 = s.a4 + (size_t)b0 * d.H4 * d.W4 * C2;
-        // pool2 backward: d pooled -> d a4
-        VGG_LAUNCH(pool_bwd_kernel, (int64_t)nb * d.H4 * d.W4 * C2, a4, ga + (size_t)b0 * d.L * d.view, nb, d.H4, d.W4, C2, 2, 2, da);
-        S2S_TRY(conv_relu_bwd(ctx, a3, a4, da, nb, d.H3, d.W3, C2, Wp[3], C2, col, dcol, dWp[3], dP + d.off[7], db_));      // conv4 -> d a3
-        S2S_TRY(conv_relu_bwd(ctx, p1, a3, db_, nb, d.H2, d.Wp1, C1, Wp[2], C2, col, dcol, dWp[2], dP + d.off[5], da));      // conv3 -> d p1
-        VGG_LAUNCH(pool_bwd_kernel, (int64_t)nb * d.H2 * d.W2 * C1, a2, da, nb, d.H2, d.W2, C1, 1, 2, db_);                  // pool1 -> d a2
-        S2S_TRY(conv_relu_bwd(ctx, a1, a2, db_, nb, d.H1, d.W1, C1, Wp[1], C1, col, dcol, dWp[1], dP + d.off[3], da));       // conv2 -> d a1
+        const float* a3 = s.a3 + (size_t)b0 * n_a3;
+        const float* a4 = s.a4 + (size_t)b0 * n_a4;
+        const float* gf0 = ga + (size_t)b0 * d.L * d.view;
+        if (imp) {
+            const int64_t M1 = (int64_t)nb * d.H1 * d.W1, M2 = (int64_t)nb * d.H2 * d.Wp1;
+            // pool2 backward onto the (H2, Wp1) grid: zero outside the valid (H4, W4) region, which is what keeps the
+            // wrap-around rows of the implicit data / weight gradients out of the sums
+            VGG_LAUNCH(pool_bwd_kernel, M2 * C2, a4, gf0, nb, d.H2, d.Wp1, d.H4, d.W4, C2, 2, 2, da);
+            VGG_LAUNCH(relu_bwd_kernel, M2 * C2, da, a4, M2 * C2);
+            S2S_TRY(conv3_tc_wgrad(ctx, da, a3, M2, d.Wp1, C2, C2, dWp[3]));
+            S2S_TRY(colsum_add(ctx, da, M2, C2, C2, dP + d.off[7]));
+            S2S_TRY(conv3_tc_dgrad(ctx, da, M2, d.Wp1, C2, WpT[3], C2, db_));                               // d a3 (zero outside (H3, W3))
+            VGG_LAUNCH(relu_bwd_kernel, M2 * C2, db_, a3, M2 * C2);
+            S2S_TRY(conv3_tc_wgrad(ctx, db_, p1, M2, d.Wp1, C2, C1, dWp[2]));
+            S2S_TRY(colsum_add(ctx, db_, M2, C2, C2, dP + d.off[5]));
+            S2S_TRY(conv3_tc_dgrad(ctx, db_, M2, d.Wp1, C2, WpT[2], C1, da));                               // d p1
+            VGG_LAUNCH(pool_bwd_kernel, M1 * C1, a2, da, nb, d.H1, d.W1, d.H2, d.W2, C1, 1, 2, db_);         // d a2 on the (H1, W1) grid
+            VGG_LAUNCH(relu_bwd_kernel, M1 * C1, db_, a2, M1 * C1);
+            S2S_TRY(conv3_tc_wgrad(ctx, db_, a1, M1, d.W1, C1, C1, dWp[1]));
+            S2S_TRY(colsum_add(ctx, db_, M1, C1, C1, dP + d.off[3]));
+            S2S_TRY(conv3_tc_dgrad(ctx, db_, M1, d.W1, C1, WpT[1], C1, da));                                // d a1
+        } else {
+            // pool2 backward: d pooled -> d a4
+            VGG_LAUNCH(pool_bwd_kernel, (int64_t)nb * d.H4 * d.W4 * C2, a4, gf0, nb, d.H4, d.W4, d.H4, d.W4, C2, 2, 2, da);
+            S2S_TRY(conv_relu_bwd(ctx, a3, a4, da, nb, d.H3, d.W3, C2, Wp[3], C2, col, dcol, dWp[3], dP + d.off[7], db_));      // conv4 -> d a3
+            S2S_TRY(conv_relu_bwd(ctx, p1, a3, db_, nb, d.H2, d.Wp1, C1, Wp[2], C2, col, dcol, dWp[2], dP + d.off[5], da));      // conv3 -> d p1
+            VGG_LAUNCH(pool_bwd_kernel, (int64_t)nb * d.H2 * d.W2 * C1, a2, da, nb, d.H2, d.W2, d.H2, d.W2, C1, 1, 2, db_);      // pool1 -> d a2
+            S2S_TRY(conv_relu_bwd(ctx, a1, a2, db_, nb, d.H1, d.W1, C1, Wp[1], C1, col, dcol, dWp[1], dP + d.off[3], da));       // conv2 -> d a1
+        }
         S2S_TRY(conv_relu_bwd(ctx, a0, a1, da, nb, T, F, 3, Wp[0], C1, col, dcol, dWp[0], dP + d.off[1],
                               dX ? dXc + (size_t)b0 * T * F * 3 : nullptr));                                                  // conv1 -> d x
     }
