@@ -25,6 +25,7 @@ struct VggDims {
 };
 static int vgg_dims(const s2s_vgg_cfg* cfg, int B, int T, int F, VggDims* d) {
     S2S_REQUIRE(cfg && cfg->C1 > 0 && cfg->C2 > 0 && cfg->HID > 0 && cfg->OUT > 0, "vgg: bad configuration");
+    S2S_REQUIRE(cfg->C1 % 4 == 0 && cfg->C2 % 4 == 0, "vgg: plane counts must be multiples of 4 (C1=%d C2=%d)", cfg->C1, cfg->C2);
     S2S_REQUIRE(T >= 10 && F >= 12, "vgg: input [T=%d, F=%d] too small for four 3x3 convolutions and two poolings", T, F);
     d->C1 = cfg->C1; d->C2 = cfg->C2; d->HID = cfg->HID; d->OUT = cfg->OUT; d->B = B; d->T = T; d->F = F;
     d->H1 = T - 2; d->W1 = F - 2; d->H2 = T - 4; d->W2 = F - 4; d->Wp1 = d->W2 / 2;
@@ -141,27 +142,42 @@ __global__ void pool_fwd_kernel(const float* __restrict__ in, int nb, int Hh, in
     }
 }
 // the gradient goes to the first maximum of the window in (kh, kw) scan order; written on the input's grid, zero outside
-// the pooled region (so the convolution below sees zeros wherever its output is not valid)
+// the pooled region (so the convolution below sees zeros wherever its output is not valid).  RELU: the pooled tensor is a
+// ReLU output, so its backward mask (in > 0) is applied in the same pass.  Four channels per thread (C % 4 == 0).
+template <bool RELU>
 __global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, int nb, int Hh, int Ww, int Hv, int Wv, int C, int kH,
                                 int kW, float* __restrict__ din) {
-    const int Ho = Hv / kH, Wo = Wv / kW;
-    const int64_t n = (int64_t)nb * Hh * Ww * C;
+    const int Ho = Hv / kH, Wo = Wv / kW, CV = C >> 2;
+    const int64_t n = (int64_t)nb * Hh * Ww * CV;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int x = (int)((i / C) % Ww), y = (int)((i / ((int64_t)C * Ww)) % Hh);
-        const int64_t b = i / ((int64_t)C * Ww * Hh);
+        const int64_t p = i / CV;                        // (b * Hh + y) * Ww + x
+        const int c = (int)(i - p * CV) * 4;
+        const int64_t by = p / Ww;
+        const int x = (int)(p - by * Ww);
+        const int b = (int)(by / Hh), y = (int)(by - (int64_t)b * Hh);
         const int yo = y / kH, xo = x / kW;
-        float g = 0.f;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (yo < Ho && xo < Wo) {
-            int best = 0; float bv = -INFINITY;
+            const int me = (y - yo * kH) * kW + (x - xo * kW);
+            int4 best = make_int4(0, 0, 0, 0);
+            float4 bv = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), mine = bv;
             for (int kh = 0; kh < kH; kh++)
                 for (int kw = 0; kw < kW; kw++) {
-                    const float v = in[((b * Hh + yo * kH + kh) * Ww + xo * kW + kw) * C + c];
-                    if (v > bv) { bv = v; best = kh * kW + kw; }
+                    const float4 v = *reinterpret_cast<const float4*>(in + (((int64_t)b * Hh + yo * kH + kh) * Ww + xo * kW + kw) * C + c);
+                    const int k = kh * kW + kw;
+                    if (v.x > bv.x) { bv.x = v.x; best.x = k; }
+                    if (v.y > bv.y) { bv.y = v.y; best.y = k; }
+                    if (v.z > bv.z) { bv.z = v.z; best.z = k; }
+                    if (v.w > bv.w) { bv.w = v.w; best.w = k; }
+                    if (k == me) mine = v;
                 }
-            if (best == (y - yo * kH) * kW + (x - xo * kW)) g = dout[((b * Ho + yo) * Wo + xo) * C + c];
+            const float4 d = *reinterpret_cast<const float4*>(dout + (((int64_t)b * Ho + yo) * Wo + xo) * C + c);
+            g.x = (best.x == me && (!RELU || mine.x > 0.f)) ? d.x : 0.f;
+            g.y = (best.y == me && (!RELU || mine.y > 0.f)) ? d.y : 0.f;
+            g.z = (best.z == me && (!RELU || mine.z > 0.f)) ? d.z : 0.f;
+            g.w = (best.w == me && (!RELU || mine.w > 0.f)) ? d.w : 0.f;
         }
-        din[i] = g;
+        *reinterpret_cast<float4*>(din + p * C + c) = g;
     }
 }
 // WpT[c, t*N + n] = Wp[n, t*C + c]   (the data-gradient operand of the implicit convolution)
@@ -428,8 +444,7 @@ int s2s_vgg_backward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, float
             const int64_t M1 = (int64_t)nb * d.H1 * d.W1, M2 = (int64_t)nb * d.H2 * d.Wp1;
             // pool2 backward onto the (H2, Wp1) grid: zero outside the valid (H4, W4) region, which is what keeps the
             // wrap-around rows of the implicit data / weight gradients out of the sums
-            VGG_LAUNCH(pool_bwd_kernel, M2 * C2, a4, gf0, nb, d.H2, d.Wp1, d.H4, d.W4, C2, 2, 2, da);
-            VGG_LAUNCH(relu_bwd_kernel, M2 * C2, da, a4, M2 * C2);
+            VGG_LAUNCH(pool_bwd_kernel<true>, M2 * C2 / 4, a4, gf0, nb, d.H2, d.Wp1, d.H4, d.W4, C2, 2, 2, da);   // + ReLU mask of a4
             S2S_TRY(conv3_tc_wgrad(ctx, da, a3, M2, d.Wp1, C2, C2, dWp[3]));
             S2S_TRY(colsum_add(ctx, da, M2, C2, C2, dP + d.off[7]));
             S2S_TRY(conv3_tc_dgrad(ctx, da, M2, d.Wp1, C2, WpT[3], C2, db_));                               // d a3 (zero outside (H3, W3))
@@ -437,17 +452,16 @@ int s2s_vgg_backward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, float
             S2S_TRY(conv3_tc_wgrad(ctx, db_, p1, M2, d.Wp1, C2, C1, dWp[2]));
             S2S_TRY(colsum_add(ctx, db_, M2, C2, C2, dP + d.off[5]));
             S2S_TRY(conv3_tc_dgrad(ctx, db_, M2, d.Wp1, C2, WpT[2], C1, da));                               // d p1
-            VGG_LAUNCH(pool_bwd_kernel, M1 * C1, a2, da, nb, d.H1, d.W1, d.H2, d.W2, C1, 1, 2, db_);         // d a2 on the (H1, W1) grid
-            VGG_LAUNCH(relu_bwd_kernel, M1 * C1, db_, a2, M1 * C1);
+            VGG_LAUNCH(pool_bwd_kernel<true>, M1 * C1 / 4, a2, da, nb, d.H1, d.W1, d.H2, d.W2, C1, 1, 2, db_);   // d a2 on the (H1, W1) grid, + ReLU mask
             S2S_TRY(conv3_tc_wgrad(ctx, db_, a1, M1, d.W1, C1, C1, dWp[1]));
             S2S_TRY(colsum_add(ctx, db_, M1, C1, C1, dP + d.off[3]));
             S2S_TRY(conv3_tc_dgrad(ctx, db_, M1, d.W1, C1, WpT[1], C1, da));                                // d a1
         } else {
             // pool2 backward: d pooled -> d a4
-            VGG_LAUNCH(pool_bwd_kernel, (int64_t)nb * d.H4 * d.W4 * C2, a4, gf0, nb, d.H4, d.W4, d.H4, d.W4, C2, 2, 2, da);
+            VGG_LAUNCH(pool_bwd_kernel<false>, (int64_t)nb * d.H4 * d.W4 * C2 / 4, a4, gf0, nb, d.H4, d.W4, d.H4, d.W4, C2, 2, 2, da);
             S2S_TRY(conv_relu_bwd(ctx, a3, a4, da, nb, d.H3, d.W3, C2, Wp[3], C2, col, dcol, dWp[3], dP + d.off[7], db_));      // conv4 -> d a3
             S2S_TRY(conv_relu_bwd(ctx, p1, a3, db_, nb, d.H2, d.Wp1, C1, Wp[2], C2, col, dcol, dWp[2], dP + d.off[5], da));      // conv3 -> d p1
-            VGG_LAUNCH(pool_bwd_kernel, (int64_t)nb * d.H2 * d.W2 * C1, a2, da, nb, d.H2, d.W2, d.H2, d.W2, C1, 1, 2, db_);      // pool1 -> d a2
+            VGG_LAUNCH(pool_bwd_kernel<false>, (int64_t)nb * d.H2 * d.W2 * C1 / 4, a2, da, nb, d.H2, d.W2, d.H2, d.W2, C1, 1, 2, db_);      // pool1 -> d a2
             S2S_TRY(conv_relu_bwd(ctx, a1, a2, db_, nb, d.H1, d.W1, C1, Wp[1], C1, col, dcol, dWp[1], dP + d.off[3], da));       // conv2 -> d a1
         }
         S2S_TRY(conv_relu_bwd(ctx, a0, a1, da, nb, T, F, 3, Wp[0], C1, col, dcol, dWp[0], dP + d.off[1],
