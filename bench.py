@@ -17,6 +17,8 @@ gradient over NCCL] -> /B, clip, adadelta, row-norm constraint (timit/timit.lua:
             library's profiling hook on an instrumented extra pass (s2s_ctx_profile)
   cpu_baseline: the CPU oracle (a C restatement of the reference; Torch7 cannot run here) on a
             bounded sample of the same workload, all host threads
+`--config cfg3` / `--config cfg4` run the other training configurations of BASELINE.json (dropout + AdaptiveWeightNoise;
+librispeech/model_vgg.lua with its VGG front-end) with the same contract; the driver's default is cfg2.
 `--impl reference` times that CPU oracle alone (the reference's own implementation is Lua/Torch7 and
 cannot be installed in this image: see DESIGN.md).
 """
