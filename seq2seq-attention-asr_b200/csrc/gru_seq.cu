@@ -411,16 +411,18 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
     cluster_sync_all();
 }
 
-// rows t >= L_b of a [B, Lmax, W] tensor := 0 (padding must not leak NaNs into the time-batched GEMMs)
+// rows t >= L_b of a [B, Lmax, W] tensor := 0 (padding must not leak NaNs into the time-batched GEMMs).  The tail of an
+// utterance is one contiguous span; a few CTAs per utterance stream zeros over it (and exit at once when there is none).
 __global__ void zero_tail_rows_kernel(float* __restrict__ x, const int* __restrict__ lengths, int Lmax, int W) {
-    const int b = blockIdx.y, t = blockIdx.x;
-    if (t < lengths[b]) return;
-    float* r = x + ((size_t)b * Lmax + t) * W;
-    for (int i = threadIdx.x; i < W; i += blockDim.x) r[i] = 0.f;
+    const int b = blockIdx.y;
+    const int len = min(max(lengths[b], 0), Lmax);
+    const size_t n = (size_t)(Lmax - len) * W;
+    float* r = x + ((size_t)b * Lmax + len) * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) r[i] = 0.f;
 }
 int zero_tail_rows(s2s_ctx* ctx, float* x, const int* lengths, int B, int Lmax, int W) {
     if (!lengths) return 0;
-    zero_tail_rows_kernel<<<dim3(Lmax, B), 128, 0, ctx->stream>>>(x, lengths, Lmax, W);
+    zero_tail_rows_kernel<<<dim3(8, B), 256, 0, ctx->stream>>>(x, lengths, Lmax, W);
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
