@@ -51,6 +51,7 @@ struct AttnFwdParams {
     int64_t ld_app;
     const int* tlens;   // padded decoder steps (tstep >= T_b) record no penalty
     int tstep;
+    int dbg;            // timing experiments (S2S_ATT_DBG): 1 = no combine, 2 = no scoring, 4 = no context
 };
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -91,7 +92,7 @@ attn_fwd_kernel(const AttnFwdParams p) {
     pdl_trigger();
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !(p.dbg & 4)) {
         const unsigned bytes = (unsigned)nrows * A * 4u;
         mbar_expect_tx(&bar, bytes);
         bulk_g2s(hs, p.h + ((size_t)b * p.Lmax + l0) * A, bytes, &bar);
@@ -110,7 +111,7 @@ attn_fwd_kernel(const AttnFwdParams p) {
 #pragma unroll
     for (int j = 0; j < RIF; j++) {
         const int r = warp + 8 * j;
-        if (r < nrows) {
+        if (r < nrows && !(p.dbg & 2)) {
 #pragma unroll
             for (int i = 0; i < NS; i++) v[j][i] = ldg_stream(vbase + (size_t)r * S + i * 128);
         }
@@ -207,7 +208,7 @@ attn_fwd_kernel(const AttnFwdParams p) {
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const int r = warp + 8 * (2 + j);
-                if (r < nrows) {
+                if (r < nrows && !(p.dbg & 2)) {
 #pragma unroll
                     for (int i = 0; i < NS; i++) v[j][i] = ldg_stream(vbase + (size_t)r * S + i * 128);
                 }
@@ -234,7 +235,7 @@ attn_fwd_kernel(const AttnFwdParams p) {
     __syncthreads();
 
     // ---- partial context from the TMA-staged h tile ---------------------------------------------
-    mbar_wait(&bar, 0);
+    if (!(p.dbg & 4)) mbar_wait(&bar, 0);
     {
         const int g = tid / (A / 4), c4 = tid % (A / 4);
         float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -263,7 +264,7 @@ attn_fwd_kernel(const AttnFwdParams p) {
         is_last = (prev == (unsigned)(nchb - 1));
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last || (p.dbg & 1)) { if (is_last && tid == 0) p.counters[b] = 0u; return; }
     __threadfence();
 
     // every warp: chunk statistics -> registers (<= 4 chunks per lane), one L2 round trip
@@ -847,6 +848,7 @@ int attn_step_fwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const fl
     p.E = sc.E; p.part_ms = sc.part_ms; p.part_c = sc.part_c; p.counters = sc.counters;
     p.alpha = alpha; p.c = c; p.pen = pen; p.ld_alpha = ld_alpha; p.ld_c = ld_c; p.ld_pen = ld_pen; p.lambda = lambda;
     p.app = app; p.ld_app = ld_app; p.tlens = tlens; p.tstep = tstep;
+    { static const int dbg = []() { const char* e = getenv("S2S_ATT_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
     if (loc.KF == 10) ATT_DISPATCH(launch_fwd, 10, ctx, p, loc.KF);      // the reference's default filter size (Attention.lua:17)
     else if (loc.KF > 0) ATT_DISPATCH(launch_fwd, 1, ctx, p, loc.KF);
     else ATT_DISPATCH(launch_fwd, 0, ctx, p, 0);
