@@ -273,6 +273,14 @@ int s2s_attn_step_forward(s2s_ctx* ctx, const float* Vh, const float* h, const f
 int s2s_attn_step_backward(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w,
                            const int* lengths, int B, int Lmax, int S, int A, const float* alpha,
                            const float* dc, const float* dalpha_in, float* dq, float* de);
+/* implicit 3x3 convolution on the tcgen05 GEMM, channels-last activations flattened over their grid (rows = pixels, row
+ * pitch Ww): out[m,n] = bias[n] + sum_t sum_c in[m + off_t, c] Wp[n, t*C + c], off_t = (t/3)*Ww + t%3, rows past the end
+ * read as zeros; dgrad: din[m,c] = sum_t sum_n dout[m - off_t, n] WpT[c, t*N + n]; wgrad: dWp[n, t*C + c] += sum_m
+ * dout[m,n] in[m + off_t, c].  C and N multiples of 32.  (The VGG front-end's building blocks, s2s_vgg_forward.) */
+int s2s_conv3_forward(s2s_ctx* ctx, const float* in, int64_t Mg, int Ww, int C, const float* Wp, const float* bias,
+                      int N, float* out, int relu);
+int s2s_conv3_dgrad(s2s_ctx* ctx, const float* dout, int64_t Mg, int Ww, int N, const float* WpT, int C, float* din);
+int s2s_conv3_wgrad(s2s_ctx* ctx, const float* dout, const float* in, int64_t Mg, int Ww, int N, int C, float* dWp);
 /* location-aware variants (Attention.lua:75-99 with the two convolutions folded into UW [KF,S]):
  * Z[l] = q + Vh[l] + sum_j UW[j] alpha_prev[l + j - pad_left]; the backward also returns d alpha_prev [B,Lmax] */
 int s2s_attn_step_forward_loc(s2s_ctx* ctx, const float* Vh, const float* h, const float* q, const float* w,

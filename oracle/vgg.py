@@ -110,20 +110,41 @@ def pool_bwd(x_shape, idx, dy, kW, kH):
     return dx
 
 
-def forward(cfg, P, X):
-    """X [3, T, F] -> (h [L, OUT], cache)"""
+def _pool_margin(x, kW, kH):
+    """smallest (max - runner-up) over the pooling windows whose maximum is positive, relative to the tensor's RMS"""
+    C, Hh, Ww = x.shape
+    Ho, Wo = Hh // kH, Ww // kW
+    v = np.sort(x[:, :Ho * kH, :Wo * kW].reshape(C, Ho, kH, Wo, kW).transpose(0, 1, 3, 2, 4).reshape(C, Ho, Wo, kH * kW), -1)
+    act = v[..., -1] > 0
+    return float((v[..., -1] - v[..., -2])[act].min() / np.sqrt(np.mean(x * x) + 1e-300)) if act.any() else np.inf
+
+
+def forward(cfg, P, X, margins=None):
+    """X [3, T, F] -> (h [L, OUT], cache).  margins (a list) collects, per ReLU and per pooling, how close the closest
+    decision of this utterance is to flipping (|pre-activation| / RMS, window max - runner-up / RMS): the network is
+    piecewise linear, and a float32 evaluation that lands on the other side of such a decision has different gradients."""
     p = unflatten(cfg, X.shape[2], P)
     c = {"x0": X}
-    a, c["col1"] = conv_fwd(X, p["conv1.W"], p["conv1.b"]); a = np.maximum(a, 0); c["a1"] = a
-    a, c["col2"] = conv_fwd(a, p["conv2.W"], p["conv2.b"]); a = np.maximum(a, 0); c["a2"] = a
+
+    def relu(z):
+        if margins is not None:
+            margins.append(float(np.abs(z).min() / np.sqrt(np.mean(z * z) + 1e-300)))
+        return np.maximum(z, 0)
+
+    a, c["col1"] = conv_fwd(X, p["conv1.W"], p["conv1.b"]); a = relu(a); c["a1"] = a
+    a, c["col2"] = conv_fwd(a, p["conv2.W"], p["conv2.b"]); a = relu(a); c["a2"] = a
+    if margins is not None:
+        margins.append(_pool_margin(a, 2, 1))
     a, c["i1"] = pool_fwd(a, 2, 1); c["p1"] = a                                  # SpatialMaxPooling(2, 1, 2, 1)
-    a, c["col3"] = conv_fwd(a, p["conv3.W"], p["conv3.b"]); a = np.maximum(a, 0); c["a3"] = a
-    a, c["col4"] = conv_fwd(a, p["conv4.W"], p["conv4.b"]); a = np.maximum(a, 0); c["a4"] = a
+    a, c["col3"] = conv_fwd(a, p["conv3.W"], p["conv3.b"]); a = relu(a); c["a3"] = a
+    a, c["col4"] = conv_fwd(a, p["conv4.W"], p["conv4.b"]); a = relu(a); c["a4"] = a
+    if margins is not None:
+        margins.append(_pool_margin(a, 2, 2))
     a, c["i2"] = pool_fwd(a, 2, 2); c["p2"] = a                                  # SpatialMaxPooling(2, 2, 2, 2)
     f = np.ascontiguousarray(a.transpose(1, 0, 2)).reshape(a.shape[1], -1)        # Transpose2 + View: [L, nFeat*H]
     c["f0"] = f
     for k in (1, 2, 3, 4):
-        f = np.maximum(f @ p[f"t{k}.W"].T + p[f"t{k}.b"], 0)
+        f = relu(f @ p[f"t{k}.W"].T + p[f"t{k}.b"])
         c[f"f{k}"] = f
     return f, c
 

@@ -115,6 +115,9 @@ def load():
         "s2s_graph_end": (i32, [vp, vp]),
         "s2s_graph_launch": (i32, [vp, i32]),
         "s2s_graph_destroy": (i32, [vp, i32]),
+        "s2s_conv3_forward": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, vp, i32]),
+        "s2s_conv3_dgrad": (i32, [vp, vp, i64, i32, i32, vp, i32, vp]),
+        "s2s_conv3_wgrad": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
         "s2s_nll_grad_seed": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
         "s2s_edit_distance": (i32, [vp, i32, vp, i32, vp]),
         "s2s_attn_step_forward_loc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),

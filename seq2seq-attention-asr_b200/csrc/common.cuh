@@ -150,7 +150,7 @@ struct GemmBatch { int count = 1; int64_t sA = 0, sB = 0, sC = 0; };
 // (requires beta == 1, i.e. accumulate-into-C semantics).
 int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* B, int ldb, float beta, float* C, int ldc, const float* bias = nullptr,
-             GemmBatch batch = GemmBatch(), int splitk = 1, int impl = 0);
+             GemmBatch batch = GemmBatch(), int splitk = 1, int impl = 0, bool relu = false);   // relu: C = max(., 0) (needs splitk == 1)
 
 // While a scope is alive, operands prepared for the tcgen05 GEMM are remembered and reused by later gemm_f32 calls that
 // read the same matrix (or a column block of it, in the transposed forms).  The caller guarantees that the source

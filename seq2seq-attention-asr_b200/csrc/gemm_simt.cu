@@ -17,8 +17,10 @@ template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_simt_kernel(bool tA, bool tB, int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                  const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc,
-                 const float* __restrict__ bias, int64_t sA, int64_t sB, int64_t sC, int splitk) {
+                 const float* __restrict__ bias, int64_t sA, int64_t sB, int64_t sC, int splitk_relu) {
     constexpr int NT = (BM / TM) * (BN / TN);
+    const bool relu = splitk_relu < 0;              // splitk_relu = -1: no split-K, ReLU epilogue
+    const int splitk = relu ? 1 : splitk_relu;
     constexpr int LA = BM * GEMM_BK / NT;   // elements of A per thread per tile
     constexpr int LB = BN * GEMM_BK / NT;
     __shared__ __align__(16) float As[2][GEMM_BK][BM + 4];
@@ -129,24 +131,25 @@ gemm_simt_kernel(bool tA, bool tB, int M, int N, int K, float alpha, const float
             } else {
                 if (bias) v += bias[gn];
                 if (beta != 0.f) v += beta * (*c);
-                *c = v;
+                *c = relu ? fmaxf(v, 0.f) : v;
             }
         }
     }
 }
 
 int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
-                const float* B, int ldb, float beta, float* C, int ldc, const float* bias, bool* handled, bool force);
+                const float* B, int ldb, float beta, float* C, int ldc, const float* bias, bool* handled, bool force, bool relu);
 
 int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
-             int ldb, float beta, float* C, int ldc, const float* bias, GemmBatch batch, int splitk, int impl) {
+             int ldb, float beta, float* C, int ldc, const float* bias, GemmBatch batch, int splitk, int impl, bool relu) {
     if (M <= 0 || N <= 0) return 0;
     S2S_REQUIRE(K >= 0, "gemm: K<0");
     S2S_REQUIRE(!(splitk > 1 && batch.count > 1), "gemm: split-K and batching are exclusive");
     S2S_REQUIRE(!(splitk > 1 && beta != 1.f), "gemm: split-K requires beta == 1 (accumulate)");
+    S2S_REQUIRE(!(relu && splitk > 1), "gemm: the ReLU epilogue cannot be combined with split-K");
     if (impl != 1 && batch.count == 1) {
         bool handled = false;
-        S2S_TRY(gemm_tc_f32(ctx, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &handled, impl == 2));
+        S2S_TRY(gemm_tc_f32(ctx, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &handled, impl == 2, relu));
         if (handled) return 0;
         S2S_REQUIRE(impl != 2, "gemm: tcgen05 path requested but shape/alignment not supported (M=%d N=%d K=%d)", M, N, K);
     }
@@ -163,11 +166,11 @@ int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, c
     if (tiles128 >= ctx->sm_count) {
         dim3 grid(ceil_div(N, 128), ceil_div(M, 128), z);
         gemm_simt_kernel<128, 128, 8, 8><<<grid, 256, 0, ctx->stream>>>(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias,
-                                                                       batch.sA, batch.sB, batch.sC, splitk);
+                                                                       batch.sA, batch.sB, batch.sC, relu ? -1 : splitk);
     } else {
         dim3 grid(ceil_div(N, 64), ceil_div(M, 64), z);
         gemm_simt_kernel<64, 64, 4, 4><<<grid, 256, 0, ctx->stream>>>(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias,
-                                                                     batch.sA, batch.sB, batch.sC, splitk);
+                                                                     batch.sA, batch.sB, batch.sC, relu ? -1 : splitk);
     }
     prof_end(ctx, S2S_PROF_GEMM, 2.0 * M * N * (double)K * batch.count);
     S2S_LAUNCH_CHECK(ctx);

@@ -59,6 +59,7 @@ struct Sched {
     int tap_slabs;                // 0 = plain GEMM
     int tap_row[9];
     int b_col0;
+    int relu;                     // C = max(., 0) in the epilogue (whole tiles only: no atomic tail)
 };
 struct Span { int tm, tn, kb0, kb1; };
 
@@ -269,6 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                                         const float4 o = *reinterpret_cast<const float4*>(cp);
                                         v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w;
                                     }
+                                    if (sched.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                                     *reinterpret_cast<float4*>(cp) = v;
                                 } else {
                                     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -288,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                                 float v = alpha * scr[rr * 33 + lane] + bv;
                                 if (direct) {
                                     if (beta != 0.f) v += beta * (*cp);
-                                    *cp = v;
+                                    *cp = sched.relu ? fmaxf(v, 0.f) : v;
                                 } else {
                                     atomicAdd(cp, v);
                                 }
@@ -446,7 +448,7 @@ static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, b
     return 0;
 }
 
-struct TcConv { int tap_slabs = 0; int tap_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; int b_col0 = 0; int a_cols = 0; };
+struct TcConv { bool relu = false; int tap_slabs = 0; int tap_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; int b_col0 = 0; int a_cols = 0; };
 
 // C[M,N] = alpha A' B^T (+beta C)(+bias) with prepared (K-contiguous, hi/lo) operands.  Plain GEMM: A' = A [M,K].  With
 // cv.tap_slabs > 0 the A operand is the [M, a_cols] activation matrix read at 9 row offsets (implicit 3x3 convolution).
@@ -459,7 +461,7 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
     sc.G = ctx->sm_count;
     static const int dbg_mode = env_int("S2S_TC_DBG", 0), tail_on = env_int("S2S_TC_TAIL", 1);
     sc.dbg = dbg_mode;
-    sc.tap_slabs = cv.tap_slabs; sc.b_col0 = cv.b_col0;
+    sc.tap_slabs = cv.tap_slabs; sc.b_col0 = cv.b_col0; sc.relu = cv.relu ? 1 : 0;
     for (int t = 0; t < 9; t++) sc.tap_row[t] = cv.tap_row[t];
     const int Tt = sc.tiles_m * sc.tiles_n;
     sc.R = Tt / sc.G; sc.rem = Tt - sc.R * sc.G;
@@ -467,7 +469,7 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
     // cannot take atomic partial sums (beta other than 0 / 1), the tail is an ordinary partial round of whole tiles
     const long long U = (long long)sc.rem * sc.nk;
     sc.Gp = (int)(U / MIN_SHARE < sc.G ? U / MIN_SHARE : sc.G);
-    if (sc.Gp <= sc.rem || (beta != 0.f && beta != 1.f) || !tail_on) sc.Gp = sc.rem;
+    if (sc.Gp <= sc.rem || (beta != 0.f && beta != 1.f) || !tail_on || cv.relu) sc.Gp = sc.rem;
     const bool atomics = sc.Gp > sc.rem;
 
     const int aK = cv.tap_slabs > 0 ? cv.a_cols : K;           // extent of the A operand's K axis in memory
@@ -511,13 +513,13 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
 //   data gradient  din[m, c]  = sum_t sum_n dout[m - off_t, n] WpT[c, t*N + n]                  (dout zero outside its valid region)
 //   weight grad.   dWp[n, t*C + c] += sum_m dout[m, n] in[m + off_t, c]                         one launch per tap, K = pixels
 // C and N must be multiples of 32 (one tap = whole 128-byte slabs).
-int conv3_tc_forward(s2s_ctx* ctx, const float* in, int64_t Mg, int Ww, int C, const float* Wp, const float* bias, int N, float* out) {
+int conv3_tc_forward(s2s_ctx* ctx, const float* in, int64_t Mg, int Ww, int C, const float* Wp, const float* bias, int N, float* out, bool relu) {
     S2S_REQUIRE(C % 32 == 0 && Mg < (1ll << 31), "conv3_tc_forward: C must be a multiple of 32");
     if (!get_encode()) return fail("conv3_tc: cuTensorMapEncodeTiled unavailable");
     TcOp a, b;
     S2S_TRY(tc_prepare(ctx, in, (int)Mg, C, C, false, &a));
     S2S_TRY(tc_prepare(ctx, Wp, N, 9 * C, 9 * C, false, &b));
-    TcConv cv; cv.tap_slabs = C / 32; cv.a_cols = C;
+    TcConv cv; cv.tap_slabs = C / 32; cv.a_cols = C; cv.relu = relu;
     for (int t = 0; t < 9; t++) cv.tap_row[t] = (t / 3) * Ww + (t % 3);
     return tc_run(ctx, (int)Mg, N, 9 * C, 1.f, a, b, 0.f, out, N, bias, cv);
 }
@@ -559,7 +561,7 @@ int conv3_tc_wgrad(s2s_ctx* ctx, const float* dout, const float* in, int64_t Mg,
 //   TN  C += A^T B     (weight gradients, K = B*L)                      both transposed by the split pre-pass
 // Small products stay on the exact-fp32 SIMT kernel (launch-bound anyway); `force` (test hook) lifts the size threshold.
 int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
-                float beta, float* C, int ldc, const float* bias, bool* handled, bool force) {
+                float beta, float* C, int ldc, const float* bias, bool* handled, bool force, bool relu) {
     using namespace tc;
     *handled = false;
     if (!tc_enabled() && !force) return 0;
@@ -571,9 +573,31 @@ int gemm_tc_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha
     TcOp a, b;
     S2S_TRY(tc_prepare(ctx, A, M, K, lda, tA, &a));                       // tA: A is [K, M]
     S2S_TRY(tc_prepare(ctx, B, N, K, ldb, !tB, &b));                      // !tB: B is [K, N]
-    S2S_TRY(tc_run(ctx, M, N, K, alpha, a, b, beta, C, ldc, bias, TcConv()));
+    TcConv plain; plain.relu = relu;
+    S2S_TRY(tc_run(ctx, M, N, K, alpha, a, b, beta, C, ldc, bias, plain));
     *handled = true;
     return 0;
 }
 
 }  // namespace s2s
+
+// ---- test hooks for the implicit convolution (flattened-grid semantics, see above) ------------------------------------
+using namespace s2s;
+extern "C" {
+__attribute__((visibility("default"))) int s2s_conv3_forward(s2s_ctx* ctx, const float* in, int64_t Mg, int Ww, int C, const float* Wp, const float* bias,
+                                                             int N, float* out, int relu) {
+    S2S_REQUIRE(ctx && in && Wp && out, "conv3_forward: null argument");
+    ctx->arena.reset();
+    return conv3_tc_forward(ctx, in, Mg, Ww, C, Wp, bias, N, out, relu != 0);
+}
+__attribute__((visibility("default"))) int s2s_conv3_dgrad(s2s_ctx* ctx, const float* dout, int64_t Mg, int Ww, int N, const float* WpT, int C, float* din) {
+    S2S_REQUIRE(ctx && dout && WpT && din, "conv3_dgrad: null argument");
+    ctx->arena.reset();
+    return conv3_tc_dgrad(ctx, dout, Mg, Ww, N, WpT, C, din);
+}
+__attribute__((visibility("default"))) int s2s_conv3_wgrad(s2s_ctx* ctx, const float* dout, const float* in, int64_t Mg, int Ww, int N, int C, float* dWp) {
+    S2S_REQUIRE(ctx && dout && in && dWp, "conv3_wgrad: null argument");
+    ctx->arena.reset();
+    return conv3_tc_wgrad(ctx, dout, in, Mg, Ww, N, C, dWp);
+}
+}

@@ -224,8 +224,7 @@ static int conv_relu_fwd(s2s_ctx* ctx, const float* in, int nb, int Hh, int Ww, 
     const int64_t M = (int64_t)nb * (Hh - 2) * (Ww - 2);
     if (C % 4 == 0) VGG_LAUNCH(unfold3_kernel<4>, M * 9 * C / 4, in, nb, Hh, Ww, C, col);
     else VGG_LAUNCH(unfold3_kernel<1>, M * 9 * C, in, nb, Hh, Ww, C, col);
-    S2S_TRY(gemm_f32(ctx, false, true, (int)M, N, 9 * C, 1.f, col, 9 * C, Wp, 9 * C, 0.f, out, N, bias));
-    VGG_LAUNCH(relu_kernel, M * N, out, M * N);
+    S2S_TRY(gemm_f32(ctx, false, true, (int)M, N, 9 * C, 1.f, col, 9 * C, Wp, 9 * C, 0.f, out, N, bias, GemmBatch(), 1, 0, true));   // bias + ReLU
     return 0;
 }
 // dout [M, N] (gradient w.r.t. the ReLU output; masked here) -> dWp += , db += , din (nullable)
@@ -245,7 +244,7 @@ static int conv_relu_bwd(s2s_ctx* ctx, const float* in, const float* out, float*
     return 0;
 }
 
-int conv3_tc_forward(s2s_ctx* ctx, const float* in, int64_t Mg, int Ww, int C, const float* Wp, const float* bias, int N, float* out);
+int conv3_tc_forward(s2s_ctx* ctx, const float* in, int64_t Mg, int Ww, int C, const float* Wp, const float* bias, int N, float* out, bool relu);
 int conv3_tc_dgrad(s2s_ctx* ctx, const float* dout, int64_t Mg, int Ww, int N, const float* WpT, int C, float* din);
 int conv3_tc_wgrad(s2s_ctx* ctx, const float* dout, const float* in, int64_t Mg, int Ww, int N, int C, float* dWp);
 
@@ -335,13 +334,14 @@ int s2s_vgg_forward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, const 
         S2S_TRY(conv_relu_fwd(ctx, s.a0 + (size_t)b0 * T * F * 3, nb, T, F, 3, Wp[0], P + d.off[1], C1, col, a1));
         if (imp) {
             const int64_t M1 = (int64_t)nb * d.H1 * d.W1, M2 = (int64_t)nb * d.H2 * d.Wp1;
-            S2S_TRY(conv3_tc_forward(ctx, a1, M1, d.W1, C1, Wp[1], P + d.off[3], C1, a2));                  // grid (H1, W1), valid (H2, W2)
-            VGG_LAUNCH(relu_kernel, M1 * C1, a2, M1 * C1);
+            static const int fused = []() { const char* e = getenv("S2S_VGG_FUSED"); return e ? atoi(e) : 7; }();
+            S2S_TRY(conv3_tc_forward(ctx, a1, M1, d.W1, C1, Wp[1], P + d.off[3], C1, a2, fused & 1));       // + ReLU; grid (H1, W1), valid (H2, W2)
+            if (!(fused & 1)) VGG_LAUNCH(relu_kernel, M1 * C1, a2, M1 * C1);
             VGG_LAUNCH(pool_fwd_kernel, (int64_t)nb * d.H2 * d.Wp1 * C1, a2, nb, d.H1, d.W1, d.H2, d.W2, C1, 1, 2, p1);
-            S2S_TRY(conv3_tc_forward(ctx, p1, M2, d.Wp1, C1, Wp[2], P + d.off[5], C2, a3));                 // grid (H2, Wp1), valid (H3, W3)
-            VGG_LAUNCH(relu_kernel, M2 * C2, a3, M2 * C2);
-            S2S_TRY(conv3_tc_forward(ctx, a3, M2, d.Wp1, C2, Wp[3], P + d.off[7], C2, a4));                 // same grid, valid (H4, W4)
-            VGG_LAUNCH(relu_kernel, M2 * C2, a4, M2 * C2);
+            S2S_TRY(conv3_tc_forward(ctx, p1, M2, d.Wp1, C1, Wp[2], P + d.off[5], C2, a3, fused & 2));      // grid (H2, Wp1), valid (H3, W3)
+            if (!(fused & 2)) VGG_LAUNCH(relu_kernel, M2 * C2, a3, M2 * C2);
+            S2S_TRY(conv3_tc_forward(ctx, a3, M2, d.Wp1, C2, Wp[3], P + d.off[7], C2, a4, fused & 4));      // same grid, valid (H4, W4)
+            if (!(fused & 4)) VGG_LAUNCH(relu_kernel, M2 * C2, a4, M2 * C2);
             VGG_LAUNCH(pool_fwd_kernel, (int64_t)nb * d.L * d.view, a4, nb, d.H2, d.Wp1, d.H4, d.W4, C2, 2, 2, f0);
         } else {
             S2S_TRY(conv_relu_fwd(ctx, a1, nb, d.H1, d.W1, C1, Wp[1], P + d.off[3], C1, col, a2));
@@ -357,8 +357,8 @@ int s2s_vgg_forward(s2s_ctx* ctx, const s2s_vgg_cfg* cfg, const float* P, const 
     const float* Wk[4] = {W1p, P + d.off[10], P + d.off[12], P + d.off[14]};
     const int kin[4] = {d.view, d.HID, d.HID, d.HID}, kout[4] = {d.HID, d.HID, d.HID, d.OUT};
     for (int k = 0; k < 4; k++) {
-        S2S_TRY(gemm_f32(ctx, false, true, (int)rows, kout[k], kin[k], 1.f, s.f[k], kin[k], Wk[k], kin[k], 0.f, s.f[k + 1], kout[k], P + d.off[9 + 2 * k]));
-        VGG_LAUNCH(relu_kernel, rows * kout[k], s.f[k + 1], rows * kout[k]);
+        S2S_TRY(gemm_f32(ctx, false, true, (int)rows, kout[k], kin[k], 1.f, s.f[k], kin[k], Wk[k], kin[k], 0.f, s.f[k + 1], kout[k], P + d.off[9 + 2 * k],
+                         GemmBatch(), 1, 0, true));                                   // bias + ReLU in the epilogue
     }
     S2S_CUDA(cudaMemcpyAsync(h, s.f[4], (size_t)rows * d.OUT * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     s.valid = true;

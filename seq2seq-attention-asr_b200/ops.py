@@ -420,6 +420,29 @@ def nll_grad_seed(ctx, logp, labels, tlens=None, flags=0, nll=None, dlogp=None, 
     return nll, dlogp
 
 
+def conv3_forward(ctx, x, Ww, Wp, bias=None, relu=False):
+    """implicit 3x3 convolution test hook: x [Mg, C] (pixels of a grid with row pitch Ww), Wp [N, 9*C] -> [Mg, N]"""
+    Mg, Cc = x.shape
+    N = Wp.shape[0]
+    out = ctx.new(Mg, N)
+    check(ctx.lib.s2s_conv3_forward(ctx.h, _f(x), Mg, Ww, Cc, _f(Wp), _f(bias), N, _f(out), int(relu)))
+    return out
+
+
+def conv3_dgrad(ctx, dout, Ww, WpT):
+    Mg, N = dout.shape
+    Cc = WpT.shape[0]
+    din = ctx.new(Mg, Cc)
+    check(ctx.lib.s2s_conv3_dgrad(ctx.h, _f(dout), Mg, Ww, N, _f(WpT), Cc, _f(din)))
+    return din
+
+
+def conv3_wgrad(ctx, dout, x, Ww, dWp):
+    Mg, N = dout.shape
+    check(ctx.lib.s2s_conv3_wgrad(ctx.h, _f(dout), _f(x), Mg, Ww, N, x.shape[1], _f(dWp)))
+    return dWp
+
+
 def edit_distance(a, b):
     """WagnerFischer(a, b) of utils.lua:3-27 on two host label sequences."""
     import numpy as np

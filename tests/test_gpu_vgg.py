@@ -1,4 +1,11 @@
-"""VGG front-end (librispeech/model_vgg.lua:23-54) on the GPU against the numpy restatement (oracle/vgg.py)."""
+"""VGG front-end (librispeech/model_vgg.lua:23-54) on the GPU against the numpy restatement (oracle/vgg.py).
+
+The network is piecewise linear (ReLU, max pooling): a float32 evaluation whose pre-activation lands on the other side of
+zero, or whose pooling window picks the runner-up, has a legitimately different gradient from the float64 oracle.  The
+strict 1e-4 comparisons therefore run on data whose closest decision (oracle/vgg.py `margins`) is well above the float32
+evaluation error (3xTF32 tensor-core GEMM: ~3e-6 of the output scale), chosen deterministically among a few seeds; the
+linear building blocks (implicit 3x3 convolution forward / dgrad / wgrad) are checked strictly at multi-tile sizes, where
+no decision is involved; and the full-width network at a larger size is checked with a flip-tolerant criterion."""
 import numpy as np
 import pytest
 import torch
@@ -8,23 +15,48 @@ from tests.util import dev, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+MARGIN = 2.5e-5
+
+
+def make_case(cfg, B, T, F, Tb=None, seeds=24, want=MARGIN):
+    """first seed (of `seeds`) whose closest ReLU / pooling decision over the whole batch is at least `want` away"""
+    best = None
+    for seed in range(seeds):
+        rng = np.random.default_rng(1000 + seed)
+        P = vgg.init_params(cfg, F, seed=seed) * 1.5
+        X = rng.standard_normal((B, 3, T, F))
+        m = []
+        for b in range(B):
+            vgg.forward(cfg, P, X[b] if Tb is None else X[b, :, :Tb[b]], margins=m)
+        if best is None or min(m) > best[0]:
+            best = (min(m), P, X, rng)
+        if min(m) >= want:
+            break
+    return best
+
+
+def oracle_batch(cfg, P, X, dh, Tb=None):
+    B = X.shape[0]
+    h_ref = np.zeros(dh.shape); dP_ref = np.zeros_like(P); dX_ref = np.zeros_like(X)
+    for b in range(B):
+        Tq = X.shape[2] if Tb is None else Tb[b]
+        Lb = vgg.out_len(Tq)
+        hb, cache = vgg.forward(cfg, P, X[b, :, :Tq])
+        h_ref[b, :Lb] = hb
+        dPb, dXb = vgg.backward(cfg, P, cache, dh[b, :Lb])
+        dP_ref += dPb; dX_ref[b, :, :Tq] = dXb
+    return h_ref, dP_ref, dX_ref
 
 
 @pytest.mark.parametrize("cfg,B,T,F", [(dict(C1=8, C2=12, HID=40, OUT=16), 3, 22, 24), (dict(C1=16, C2=32, HID=64, OUT=32), 2, 37, 40),
-                                       (dict(C1=64, C2=128, HID=256, OUT=128), 5, 48, 40)])
+                                       (dict(C1=64, C2=128, HID=256, OUT=128), 2, 14, 24)])
 def test_vgg_forward_backward_matches_oracle(s2s, gctx, cfg, B, T, F):
-    rng = np.random.default_rng(B + T + F)
-    P = vgg.init_params(cfg, F, seed=T) * 1.5
+    margin, P, X, rng = make_case(cfg, B, T, F)
+    assert margin > MARGIN, margin
     assert s2s.vgg_param_count(cfg, F) == P.size == vgg.param_count(cfg, F)
-    X = rng.standard_normal((B, 3, T, F))
     L = vgg.out_len(T)
     dh = rng.standard_normal((B, L, cfg["OUT"]))
-    h_ref = np.zeros((B, L, cfg["OUT"])); dP_ref = np.zeros_like(P); dX_ref = np.zeros_like(X)
-    for b in range(B):
-        hb, cache = vgg.forward(cfg, P, X[b])
-        h_ref[b] = hb
-        dPb, dXb = vgg.backward(cfg, P, cache, dh[b])
-        dP_ref += dPb; dX_ref[b] = dXb
+    h_ref, dP_ref, dX_ref = oracle_batch(cfg, P, X, dh)
     Pd, Xd = dev(P, torch.float32), dev(X, torch.float32)
     h = s2s.vgg_forward(gctx, cfg, Pd, Xd)
     assert rel_err(h.cpu().numpy(), h_ref) < TOL
@@ -38,26 +70,46 @@ def test_vgg_forward_backward_matches_oracle(s2s, gctx, cfg, B, T, F):
     assert rel_err(dX.cpu().numpy(), dX_ref) < TOL
 
 
+def test_vgg_full_width_larger_batch_flip_tolerant(s2s, gctx):
+    # 64/128 planes at a size that spans several GEMM tiles and stream-K rounds.  With ~1.5e6 ReLU / pooling decisions the
+    # closest one is within 1e-7 of flipping, so individual gradient entries may differ from float64; the forward value is
+    # continuous in the decisions (strict), the gradients are compared in the L2 sense.
+    cfg, B, T, F = dict(C1=64, C2=128, HID=256, OUT=128), 5, 48, 40
+    rng = np.random.default_rng(B + T + F)
+    P = vgg.init_params(cfg, F, seed=T) * 1.5
+    X = rng.standard_normal((B, 3, T, F))
+    dh = rng.standard_normal((B, vgg.out_len(T), cfg["OUT"]))
+    h_ref, dP_ref, dX_ref = oracle_batch(cfg, P, X, dh)
+    Pd, Xd = dev(P, torch.float32), dev(X, torch.float32)
+    h = s2s.vgg_forward(gctx, cfg, Pd, Xd)
+    assert rel_err(h.cpu().numpy(), h_ref) < TOL
+    dP, dX = s2s.vgg_backward(gctx, cfg, Pd, Xd, dev(dh, torch.float32), need_dx=True)
+
+    def l2(a, b):
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+    segs, o = vgg.segments(cfg, F), 0
+    dPg = dP.cpu().numpy()
+    for name, shape in segs:
+        n = int(np.prod(shape))
+        assert l2(dPg[o:o + n], dP_ref[o:o + n]) < 2e-3, name
+        o += n
+    assert l2(dX.cpu().numpy(), dX_ref) < 2e-3
+
+
 def test_vgg_padded_batch_equals_per_utterance(s2s, gctx):
     # the reference runs one utterance at a time; a padded batch must give every utterance the result it gets alone:
     # annotations l < L_b = (T_b - 8) // 2 only see input frames < T_b, and zero dh beyond L_b keeps the gradients exact
     cfg = dict(C1=32, C2=64, HID=48, OUT=32)          # multiples of 32: the implicit-GEMM path
-    F, T, Tb = 24, 44, (44, 31, 26)
+    F, T, Tb = 24, 30, (30, 23, 18)
     B = len(Tb)
-    rng = np.random.default_rng(12)
-    P = vgg.init_params(cfg, F, seed=2) * 1.5
-    X = rng.standard_normal((B, 3, T, F))
+    margin, P, X, rng = make_case(cfg, B, T, F, Tb=Tb)
+    assert margin > MARGIN, margin
     L = vgg.out_len(T)
     dh = rng.standard_normal((B, L, cfg["OUT"]))
-    h_ref = np.zeros((B, L, cfg["OUT"])); dP_ref = np.zeros_like(P); dX_ref = np.zeros_like(X)
     for b in range(B):
         X[b, :, Tb[b]:] = 0
-        Lb = vgg.out_len(Tb[b])
-        dh[b, Lb:] = 0
-        hb, cache = vgg.forward(cfg, P, X[b, :, :Tb[b]])
-        h_ref[b, :Lb] = hb
-        dPb, dXb = vgg.backward(cfg, P, cache, dh[b, :Lb])
-        dP_ref += dPb; dX_ref[b, :, :Tb[b]] = dXb
+        dh[b, vgg.out_len(Tb[b]):] = 0
+    h_ref, dP_ref, dX_ref = oracle_batch(cfg, P, X, dh, Tb)
     Pd, Xd = dev(P, torch.float32), dev(X, torch.float32)
     h = s2s.vgg_forward(gctx, cfg, Pd, Xd).cpu().numpy()
     for b in range(B):
@@ -69,3 +121,48 @@ def test_vgg_padded_batch_equals_per_utterance(s2s, gctx):
     assert rel_err(dXg, dX_ref) < TOL
     for b in range(B):
         assert np.abs(dXg[b, :, Tb[b]:]).max() == 0.0 if Tb[b] < T else True
+
+
+def _shifted(x, off):
+    """rows m -> x[m + off] (zeros past either end)"""
+    y = np.zeros_like(x)
+    if off >= 0:
+        y[:x.shape[0] - off] = x[off:]
+    else:
+        y[-off:] = x[:x.shape[0] + off]
+    return y
+
+
+@pytest.mark.parametrize("Mg,Ww,C,N", [(3 * 40 * 36, 36, 64, 64), (2 * 70 * 18, 18, 64, 128), (20000, 36, 128, 128), (777, 11, 32, 96)])
+def test_implicit_conv3_linear_ops(s2s, gctx, Mg, Ww, C, N):
+    # flattened-grid semantics of include/s2s_b200.h: no decision anywhere, so float64 numpy is matched to 1e-4 at sizes
+    # that span many tiles, both accumulators and the stream-K tail
+    rng = np.random.default_rng(Mg + C)
+    x = rng.standard_normal((Mg, C)); Wp = rng.standard_normal((N, 9 * C)) / np.sqrt(9 * C); bias = rng.standard_normal(N)
+    dout = rng.standard_normal((Mg, N))
+    offs = [(t // 3) * Ww + t % 3 for t in range(9)]
+    ref = np.tile(bias, (Mg, 1))
+    for t, off in enumerate(offs):
+        ref += _shifted(x, off) @ Wp[:, t * C:(t + 1) * C].T
+    xd, Wd, bd, dd = (dev(a, torch.float32) for a in (x, Wp, bias, dout))
+    out = s2s.conv3_forward(gctx, xd, Ww, Wd, bd).cpu().numpy()
+    assert rel_err(out, ref) < TOL
+    out = s2s.conv3_forward(gctx, xd, Ww, Wd, bd, relu=True).cpu().numpy()
+    # the fused ReLU: exact zeros where the oracle is clearly negative, the value where clearly positive
+    sc = np.abs(ref).max()
+    clear = np.abs(ref) > 1e-4 * sc
+    assert np.abs(out - np.maximum(ref, 0))[clear].max() < TOL * sc and (out >= 0).all()
+    # dgrad: din[m, c] = sum_t dout[m - off_t] @ W_t  (WpT [C, 9N] holds W_t^T per tap)
+    WpT = np.concatenate([Wp[:, t * C:(t + 1) * C].T for t in range(9)], 1)      # [C, 9*N]
+    ref = np.zeros((Mg, C))
+    for t, off in enumerate(offs):
+        ref += _shifted(dout, -off) @ Wp[:, t * C:(t + 1) * C]
+    din = s2s.conv3_dgrad(gctx, dd, Ww, dev(WpT, torch.float32)).cpu().numpy()
+    assert rel_err(din, ref) < TOL
+    # wgrad accumulates into dWp
+    acc0 = rng.standard_normal((N, 9 * C))
+    ref = acc0.copy()
+    for t, off in enumerate(offs):
+        ref[:, t * C:(t + 1) * C] += dout.T @ _shifted(x, off)
+    dWp = s2s.conv3_wgrad(gctx, dd, xd, Ww, dev(acc0, torch.float32)).cpu().numpy()
+    assert rel_err(dWp, ref) < TOL
