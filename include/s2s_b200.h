@@ -90,7 +90,8 @@ int  s2s_graph_destroy(s2s_ctx* ctx, int graph_id);
 #define S2S_PROF_GRU_BWD     4
 #define S2S_PROF_GEMM        5
 #define S2S_PROF_DENSE_SMALL 6
-#define S2S_PROF_N           7
+#define S2S_PROF_DEC_FWD     7   /* the decoder time loop as one cluster kernel (decoder_cluster.cu) */
+#define S2S_PROF_N           8
 int  s2s_ctx_profile(s2s_ctx* ctx, int enable);
 int  s2s_ctx_profile_read(s2s_ctx* ctx, double* ms_host, int64_t* count_host, double* work_host);
 

@@ -584,11 +584,13 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
     S2S_CUDA(cudaMemsetAsync(d.su, 0, BT * 2 * ST * sizeof(float), st));     // s_0 = 0 (Recurrent.lua:112)
 
     const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST;
-    {   // q_0 = W_s s_0 + b_s with s_0 = 0   (Attention.lua:65-67, Recurrent.lua:112)
+    bool clustered = false;     // the whole time loop in one persistent cluster kernel (decoder_cluster.cu) when the shapes allow
+    S2S_TRY(decoder_cluster_forward(ctx, Y, P, h, lengths, B, Lmax, tlens, T, lambda, uy, d, &clustered));
+    if (!clustered) {   // q_0 = W_s s_0 + b_s with s_0 = 0   (Attention.lua:65-67, Recurrent.lua:112)
         DenseEpi e; e.bias = d.qbias; e.out = d.q; e.ld_out = (int64_t)T * S;
         S2S_TRY(dense_small(ctx, zeros, ST, B, ST, P + Y.Ws.off, ST, S, e));
     }
-    for (int t = 0; t < T; t++) {
+    for (int t = 0; t < T && !clustered; t++) {
         {   // attention step (Attention.lua:95-135)
             AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw;
             loc.alpha_prev = t ? d.alpha + (size_t)(t - 1) * Lmax : nullptr; loc.ld_aprev = (int64_t)T * Lmax;

@@ -1,0 +1,575 @@
+// decoder_cluster.cu -- the teacher-forced decoder TIME LOOP as one persistent thread-block-cluster kernel.
+//
+// Per decoder step the reference runs (Attention.lua:95-151, RNNAttention.lua:144-190, GRU.lua:22-30)
+//     e_l = w . tanh(q_t + Vh_l)      alpha = softmax_l(e)      c_t = sum_l alpha_l h_l
+//     u_t = (W_j W_c) c_t + uy_t      {z, r} = sigmoid(G_zr {s_{t-1}, u_t})      h~ = tanh(G_h {r s_{t-1}, u_t})
+//     s_t = (1-z) s_{t-1} + z h~      q_{t+1} = W_s s_t + b_s
+// which decoder.cu issues as one attention launch + four dense launches per step: five dependent kernels whose
+// fixed latencies (~40 us per step) are the largest single item of the training step.  Here a cluster of 16 CTAs owns
+// BG utterances for ALL T steps:
+//   * the step's weights (W_jc, G_zr, G_h: 512 KB + 1 MB + 512 KB, W_s: 512 KB) stay on chip for the whole call -- every CTA
+//     keeps the rows of its 16 decoder units (32 rows of q) in shared memory (128 KB, k-major so lanes = rows read
+//     conflict-free) and registers (W_s);
+//   * the encoder frames of an utterance are split over the 16 CTAs (flash-decoding style): each CTA streams its rows of
+//     Vh and h from L2 once per step, forms local softmax statistics and a partial context, and the partials are
+//     reduce-scattered over distributed shared memory (st.async + mbarrier complete_tx) so that CTA j normalises the
+//     context slice j and all-gathers it;
+//   * the mat-vec phases run with lanes = rows, warps = K-slices (x read as warp-uniform broadcasts), partial sums are
+//     combined through shared memory, the gate math is fused, and each phase's slice is all-gathered with one DSMEM
+//     exchange (6 exchanges per step, ~0.5 us each, instead of 5 kernel boundaries).
+// Everything the backward pass reads (alpha, {s,c}, q, {s,u}, {r s,u}, gates, penalty) is written exactly as the
+// per-step path writes it, so decoder_backward is unchanged.
+// Supported: ST = 256, S = A = 512 (the Chorowski / VGG model sizes), content attention (K = 0), Lmax <= 1024.
+#include <cooperative_groups.h>
+
+#include "cluster_rnn.cuh"
+#include "decoder.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace s2s {
+
+constexpr int DC_CS = 16;          // CTAs per cluster
+constexpr int DC_THREADS = 512;
+constexpr int DC_ST = 256, DC_A = 512, DC_S = 512;
+constexpr int DC_RMAX = 64;        // encoder frames of one utterance per CTA: Lmax <= 16 * 64
+
+struct DecClusterParams {
+    const float *Vh, *h, *w, *qbias, *Ws, *Wjc, *Gz, *Gh, *uy;
+    const int *lengths, *tlens;
+    int B, Lmax, T;
+    float lambda;
+    float *alpha, *sc, *q, *pen, *su, *rhu, *gates;
+    long long* clk;                // optional per-phase clock accumulators (S2S_DEC_PROF)
+};
+
+template <int BG>
+struct DcSmem {
+    // weights, k-major: Wt[(k4 * ROWS + r) * 4 + kk] = W[row0 + r][4 k4 + kk]
+    float wjc[128 * 16 * 4];
+    float gz[128 * 32 * 4];
+    float gh[128 * 16 * 4];
+    // all-gathered vectors
+    float q_full[BG][DC_S];
+    float c_full[BG][DC_A];
+    float s_full[BG][DC_ST];
+    float u_full[BG][DC_ST];
+    float rs_full[BG][DC_ST];
+    // reduce-scatter receive: slice of every CTA's partial context + its softmax statistics {m, s, w1, w2}
+    float recv_c[DC_CS][BG][32];
+    float4 recv_st[DC_CS][BG];
+    float part[16][BG][32];        // per-warp (K-slice) partial sums of a mat-vec phase
+    float e_s[BG][DC_RMAX], p_s[BG][DC_RMAX], ap_s[BG][DC_RMAX];
+    float w_s[DC_S];
+    float stage[BG][32];
+    float zbuf[BG][16];
+    float scl_own[BG];
+    int l0_s[BG], nr_s[BG], len_s[BG];
+    int frow[BG * DC_RMAX];        // this CTA's frames, flattened over its utterances: row of Vh / h ((b0+b) Lmax + l)
+    short fb[BG * DC_RMAX], fr[BG * DC_RMAX];      // utterance and frame-within-slice of a flattened frame
+    uint64_t bar[6];               // q, cp, c, u, rs, s
+};
+enum { BAR_Q = 0, BAR_CP, BAR_C, BAR_U, BAR_RS, BAR_S };
+
+// all-gather: this CTA's [BG][UC] slice (staged in shared memory, row pitch 32) -> columns [UC*crank, +UC) of `buf` ([BG][H]) of
+// every CTA of the cluster; warp w serves rank w
+template <int H, int UC, int BG>
+__device__ __forceinline__ void dc_bcast(const float (*stage)[32], uint32_t buf_a, uint32_t bar_a, unsigned crank, int warp, int lane) {
+    constexpr int CPB = UC / 4;
+    const uint32_t rbar = mapa_rank(bar_a, warp);
+    for (int ch = lane; ch < BG * CPB; ch += 32) {
+        const int b = ch / CPB, off = (ch % CPB) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(&stage[b][off]);
+        st_async_v4(mapa_rank(buf_a + (uint32_t)(b * H + crank * UC + off) * 4u, warp), v, rbar);
+    }
+}
+
+// one K-slice (32 k per warp) of a mat-vec phase.  ROWS = 32: lane = row, 8 k4 per lane; ROWS = 16: lane = (row, half), 4 k4 per lane.
+// Wt is k-major ([k4][ROWS][4]); x rows are read as warp-uniform broadcasts; the warp's partial sums go to part[warp][b][row].
+template <int BG, int ROWS>
+__device__ __forceinline__ void dc_mv(const float* __restrict__ Wt, const float* __restrict__ x, int xpitch, int k4w, int k4x, int warp, int lane,
+                                      float (*part)[BG][32]) {
+    constexpr int NK = ROWS == 32 ? 8 : 4;
+    const int r = ROWS == 32 ? lane : (lane & 15), sub = ROWS == 32 ? 0 : (lane >> 4) * 4;
+    float acc[BG];
+#pragma unroll
+    for (int b = 0; b < BG; b++) acc[b] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NK; i++) {
+        const float4 wv = *reinterpret_cast<const float4*>(Wt + ((size_t)(k4w + sub + i) * ROWS + r) * 4);
+#pragma unroll
+        for (int b = 0; b < BG; b++) acc[b] = dot4(wv, *reinterpret_cast<const float4*>(x + (size_t)b * xpitch + (k4x + sub + i) * 4), acc[b]);
+    }
+    if (ROWS == 16) {
+#pragma unroll
+        for (int b = 0; b < BG; b++) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
+    }
+    if (ROWS == 32 || lane < 16) {
+#pragma unroll
+        for (int b = 0; b < BG; b++) part[warp][b][r] = acc[b];
+    }
+}
+
+// acc + w . tanh(z) for four elements with ONE reciprocal: tanh(x) = 1 - 2 / (e^{2x} + 1); the four denominators are inverted
+// together (1 / d_i = (product of the others) / (d_0 d_1 d_2 d_3)), 5 MUFU operations per 4 elements instead of 8 -- the scoring
+// phase is MUFU-bound.  x is clamped to 10 (tanh(10) rounds to 1.0f), so the product stays below 6e34.
+__device__ __forceinline__ float dc_tanh4_dot(const float4 w, const float4 z, float acc) {
+    const float k = 2.885390081777927f;                      // 2 log2(e)
+    const float d0 = exp2f(k * fminf(z.x, 10.f)) + 1.f, d1 = exp2f(k * fminf(z.y, 10.f)) + 1.f;
+    const float d2 = exp2f(k * fminf(z.z, 10.f)) + 1.f, d3 = exp2f(k * fminf(z.w, 10.f)) + 1.f;
+    const float p01 = d0 * d1, p23 = d2 * d3;
+    const float r = __fdividef(-2.0f, p01 * p23);
+    const float r01 = r * p23, r23 = r * p01;                // -2 / (d0 d1), -2 / (d2 d3)
+    acc = fmaf(w.x, fmaf(r01, d1, 1.f), acc);
+    acc = fmaf(w.y, fmaf(r01, d0, 1.f), acc);
+    acc = fmaf(w.z, fmaf(r23, d3, 1.f), acc);
+    return fmaf(w.w, fmaf(r23, d2, 1.f), acc);
+}
+
+template <int BG>
+__global__ void __launch_bounds__(DC_THREADS, 1)
+dec_cluster_fwd_kernel(const DecClusterParams p) {
+    extern __shared__ __align__(128) unsigned char dc_smem_raw[];
+    DcSmem<BG>& sm = *reinterpret_cast<DcSmem<BG>*>(dc_smem_raw);
+    constexpr int ST = DC_ST, A = DC_A, S = DC_S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = cg::this_cluster().block_rank();
+    const int b0 = (blockIdx.x / DC_CS) * BG;
+    const int T = p.T, Lmax = p.Lmax;
+
+    // ---- one-time staging -------------------------------------------------------------------------------------------
+    {   // weights: global rows are k-contiguous (coalesced scalar reads: segments of the flat parameter vector are not
+        // 16-byte aligned in general), shared layout is k-major
+        for (int i = tid; i < 16 * 512; i += DC_THREADS) {
+            const int r = i >> 9, k = i & 511;
+            sm.wjc[((size_t)(k >> 2) * 16 + r) * 4 + (k & 3)] = p.Wjc[(size_t)(16 * crank + r) * A + k];
+            sm.gh[((size_t)(k >> 2) * 16 + r) * 4 + (k & 3)] = p.Gh[(size_t)(16 * crank + r) * 2 * ST + k];
+        }
+        for (int i = tid; i < 32 * 512; i += DC_THREADS) {
+            const int r = i >> 9, k = i & 511;
+            const int n = r < 16 ? 16 * crank + r : ST + 16 * crank + r - 16;        // z rows, then r rows of this CTA's units
+            sm.gz[((size_t)(k >> 2) * 32 + r) * 4 + (k & 3)] = p.Gz[(size_t)n * 2 * ST + k];
+        }
+        for (int i = tid; i < S; i += DC_THREADS) sm.w_s[i] = p.w[i];
+        for (int i = tid; i < BG * S; i += DC_THREADS) (&sm.q_full[0][0])[i] = p.qbias[i % S];      // q_0 = W_s 0 + b_s
+        for (int i = tid; i < BG * ST; i += DC_THREADS) (&sm.s_full[0][0])[i] = 0.f;               // s_0 = 0 (Recurrent.lua:112)
+        for (int i = tid; i < BG * DC_RMAX; i += DC_THREADS) (&sm.ap_s[0][0])[i] = 0.f;            // alpha_{-1} = 0
+        if (tid < BG) {
+            const int b = b0 + tid;
+            const int Lb = b < p.B ? (p.lengths ? p.lengths[b] : Lmax) : 0;
+            const int Rb = (Lb + DC_CS - 1) / DC_CS;
+            const int l0 = (int)crank * Rb;
+            sm.len_s[tid] = Lb; sm.l0_s[tid] = l0; sm.nr_s[tid] = max(0, min(Rb, Lb - l0));
+        }
+        if (tid == 0) {
+            for (int i = 0; i < 6; i++) mbar_init(&sm.bar[i], 1);
+            fence_mbar_init();
+        }
+    }
+    // W_s rows of this CTA's q slice: lane = row, warp = K-slice of 16
+    float4 wq[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float* wr = p.Ws + (size_t)(32 * crank + lane) * ST + 16 * warp + 4 * i;
+        wq[i] = make_float4(__ldg(wr), __ldg(wr + 1), __ldg(wr + 2), __ldg(wr + 3));
+    }
+    __syncthreads();
+    if (tid < BG * 32) {   // q_0 slice of the saved state
+        const int b = tid >> 5, k = tid & 31;
+        if (b0 + b < p.B) p.q[((size_t)(b0 + b) * T) * S + 32 * crank + k] = p.qbias[32 * crank + k];
+    }
+    int NR = 0;
+#pragma unroll
+    for (int b = 0; b < BG; b++) NR += sm.nr_s[b];
+    for (int f = tid; f < NR; f += DC_THREADS) {
+        int r = f, b = 0;
+#pragma unroll
+        for (int bb = 0; bb < BG - 1; bb++)
+            if (b == bb && r >= sm.nr_s[bb]) { r -= sm.nr_s[bb]; b = bb + 1; }
+        sm.frow[f] = (b0 + b) * Lmax + sm.l0_s[b] + r; sm.fb[f] = (short)b; sm.fr[f] = (short)r;
+    }
+
+    const uint32_t q_a = smem_u32(&sm.q_full[0][0]), c_a = smem_u32(&sm.c_full[0][0]), s_a = smem_u32(&sm.s_full[0][0]);
+    const uint32_t u_a = smem_u32(&sm.u_full[0][0]), rs_a = smem_u32(&sm.rs_full[0][0]);
+    const uint32_t rc_a = smem_u32(&sm.recv_c[0][0][0]), rst_a = smem_u32(&sm.recv_st[0][0]);
+    uint32_t bar_a[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) bar_a[i] = smem_u32(&sm.bar[i]);
+    cluster_sync_all();   // every CTA of the cluster is resident and has initialised its barriers / buffers
+
+    constexpr unsigned TX_CP = DC_CS * BG * (128 + 16), TX_512 = BG * 512 * 4, TX_256 = BG * 256 * 4;
+    long long tck = 0;
+    const bool prof = p.clk != nullptr && blockIdx.x == 0 && tid == 0;
+#define DC_TICK(i) do { if (prof) { const long long n_ = clock64(); p.clk[i] += n_ - tck; tck = n_; } } while (0)
+    if (prof) tck = clock64();
+
+    float4 va[2][4], vb[2][4];
+    auto load_pair = [&](int f0, float4 (&v)[2][4]) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int f = f0 + 16 * j < NR ? f0 + 16 * j : f0;
+            const float* vp = p.Vh + (size_t)sm.frow[f] * S + lane * 4;
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[j][i] = ldg_stream(vp + 128 * i);
+        }
+    };
+    auto score_pair = [&](int f0, const float4 (&v)[2][4]) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int f = f0 + 16 * j < NR ? f0 + 16 * j : f0;
+            const int b = sm.fb[f];
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 qv = *reinterpret_cast<const float4*>(&sm.q_full[b][lane * 4 + 128 * i]);
+                const float4 wv = *reinterpret_cast<const float4*>(&sm.w_s[lane * 4 + 128 * i]);
+                acc = dc_tanh4_dot(wv, make_float4(v[j][i].x + qv.x, v[j][i].y + qv.y, v[j][i].z + qv.z, v[j][i].w + qv.w), acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) sm.e_s[b][sm.fr[f]] = acc;        // (a duplicated tail frame rewrites the same value)
+        }
+    };
+    __syncthreads();                                         // frame table
+    if (warp < NR) load_pair(warp, va);
+
+    unsigned parity = 0;
+    for (int t = 0; t < T; t++) {
+        if (tid == 0) {
+            mbar_expect_tx(&sm.bar[BAR_CP], TX_CP); mbar_expect_tx(&sm.bar[BAR_C], TX_512);
+            mbar_expect_tx(&sm.bar[BAR_U], TX_256); mbar_expect_tx(&sm.bar[BAR_RS], TX_256); mbar_expect_tx(&sm.bar[BAR_S], TX_256);
+            if (t + 1 < T) mbar_expect_tx(&sm.bar[BAR_Q], TX_512);
+        }
+        // uy_t of the u rows this thread finalises (fetched early)
+        float uyv = 0.f;
+        if (tid < BG * 16 && b0 + (tid >> 4) < p.B) uyv = __ldg(p.uy + ((size_t)(b0 + (tid >> 4)) * T + t) * ST + 16 * crank + (tid & 15));
+
+        // ---- scoring: warp per encoder frame; two frames per pass, the next pass's rows already in flight (the first pass
+        // of a step was issued before the wait for q_t) (Attention.lua:95-121) --------------------------------------------
+        {
+            int f0 = warp;
+            while (f0 < NR) {
+                if (f0 + 32 < NR) load_pair(f0 + 32, vb);
+                score_pair(f0, va);
+                f0 += 32;
+                if (f0 >= NR) break;
+                if (f0 + 32 < NR) load_pair(f0 + 32, va);
+                score_pair(f0, vb);
+                f0 += 32;
+            }
+        }
+        __syncthreads();
+        DC_TICK(0);
+
+        // ---- partial context: thread = (float4 column c4, row group g), warp w holds the 8 columns of CTA w's slice x 4 row groups; the
+        // frames of two utterances (up to 2 x 20 rows) are in flight at once, the first pair is issued before the statistics ----
+        const int c4 = 8 * warp + (lane & 7), g = lane >> 3;     // a quarter-warp reads 128 contiguous bytes of one frame
+        float4 hx[2][5];
+        auto ctx_load = [&](int bp) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (bp + j >= BG) continue;
+                const int b = bp + j, nr = sm.nr_s[b];
+                if (nr == 0) continue;                               // (uniform) no frames of this utterance here: hx unused, p_s = 0
+                const float* hp = p.h + ((size_t)(b0 + b) * Lmax + sm.l0_s[b]) * A + c4 * 4;
+#pragma unroll
+                for (int u = 0; u < 5; u++) hx[j][u] = ldg_stream(hp + (size_t)min(g + 4 * u, nr - 1) * A);   // clamped: p_s is 0 past the slice
+            }
+        };
+        ctx_load(0);
+
+        // ---- local softmax statistics: warp b -> utterance b --------------------------------------------------------------
+        if (warp < BG) {
+            const int b = warp, nr = sm.nr_s[b], Lb = sm.len_s[b], l0 = sm.l0_s[b];
+            const float e0 = lane < nr ? sm.e_s[b][lane] : -INFINITY, e1 = lane + 32 < nr ? sm.e_s[b][lane + 32] : -INFINITY;
+            const float m = warp_max(fmaxf(e0, e1));
+            const float p0 = lane < nr ? expf(e0 - m) : 0.f, p1 = lane + 32 < nr ? expf(e1 - m) : 0.f;
+            sm.p_s[b][lane] = p0; sm.p_s[b][lane + 32] = p1;
+            const float ssum = warp_sum(p0 + p1);
+            // penalty terms (Attention.lua:123-135): sum_l (L_b - l) alpha_l and sum_l (L_b - l) alpha_{t-1,l}
+            const float k0 = (float)(Lb - l0 - lane), k1 = (float)(Lb - l0 - lane - 32);
+            const float w1 = warp_sum(k0 * p0 + k1 * p1);
+            const float w2 = warp_sum((lane < nr ? k0 * sm.ap_s[b][lane] : 0.f) + (lane + 32 < nr ? k1 * sm.ap_s[b][lane + 32] : 0.f));
+            if (lane < DC_CS)   // statistics to every CTA of the cluster
+                st_async_v4(mapa_rank(rst_a + (uint32_t)(crank * BG + b) * 16u, lane), make_float4(m, ssum, w1, w2), mapa_rank(bar_a[BAR_CP], lane));
+        }
+        __syncthreads();
+        DC_TICK(8);
+        {
+            const int dst = warp;                                    // owner of this warp's columns
+            const uint32_t dbar = mapa_rank(bar_a[BAR_CP], dst);
+#pragma unroll
+            for (int bp = 0; bp < BG; bp += 2) {
+                float4 acc[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bp + j < BG) {
+                        const int b = bp + j;
+                        if (sm.nr_s[b] > 0) {
+#pragma unroll
+                            for (int u = 0; u < 5; u++) {
+                                const float pv = sm.p_s[b][g + 4 * u];
+                                acc[j].x = fmaf(pv, hx[j][u].x, acc[j].x); acc[j].y = fmaf(pv, hx[j][u].y, acc[j].y);
+                                acc[j].z = fmaf(pv, hx[j][u].z, acc[j].z); acc[j].w = fmaf(pv, hx[j][u].w, acc[j].w);
+                            }
+                        }
+                    }
+                }
+                if (bp + 2 < BG) ctx_load(bp + 2);                   // next pair in flight during the tail / reduction of this one
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    if (bp + j < BG) {
+                        const int b = bp + j, nr = sm.nr_s[b];
+                        if (nr > 20) {                               // long utterances: the remaining frames of the slice
+                            const float* hp = p.h + ((size_t)(b0 + b) * Lmax + sm.l0_s[b]) * A + c4 * 4;
+                            for (int r0 = g + 20; r0 < nr; r0 += 16) {
+                                float4 x[4];
+#pragma unroll
+                                for (int u = 0; u < 4; u++) x[u] = r0 + 4 * u < nr ? ldg_stream(hp + (size_t)(r0 + 4 * u) * A) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    const float pv = r0 + 4 * u < nr ? sm.p_s[b][r0 + 4 * u] : 0.f;
+                                    acc[j].x = fmaf(pv, x[u].x, acc[j].x); acc[j].y = fmaf(pv, x[u].y, acc[j].y);
+                                    acc[j].z = fmaf(pv, x[u].z, acc[j].z); acc[j].w = fmaf(pv, x[u].w, acc[j].w);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int o = 8; o <= 16; o <<= 1) {
+                            acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o); acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
+                            acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o); acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
+                        }
+                        if (g == 0) st_async_v4(mapa_rank(rc_a + (uint32_t)((crank * BG + b) * 32 + (c4 & 7) * 4) * 4u, dst), acc[j], dbar);
+                    }
+                }
+            }
+        }
+        DC_TICK(1);
+        mbar_wait(&sm.bar[BAR_CP], parity);
+        DC_TICK(2);
+
+        // ---- combine: this CTA normalises context columns [32 crank, +32) of every utterance ----------------------------------
+        if (tid < BG * 32) {
+            const int b = tid >> 5, k = tid & 31;
+            float M = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < DC_CS; i++) M = fmaxf(M, sm.recv_st[i][b].x);
+            float den = 0.f, cv = 0.f, w1 = 0.f, w2 = 0.f, own = 0.f;
+#pragma unroll
+            for (int i = 0; i < DC_CS; i++) {
+                const float4 st = sm.recv_st[i][b];
+                const float sc = M > -INFINITY ? expf(st.x - M) : 0.f;
+                den = fmaf(st.y, sc, den);
+                cv = fmaf(sc, sm.recv_c[i][b][k], cv);
+                w1 = fmaf(sc, st.z, w1); w2 += st.w;
+                if (i == (int)crank) own = sc;
+            }
+            const float inv = den > 0.f ? 1.0f / den : 0.f;
+            cv *= inv;
+            sm.stage[b][k] = cv;
+            if (k == 0) sm.scl_own[b] = own * inv;
+            if (b0 + b < p.B) {
+                p.sc[((size_t)(b0 + b) * T + t) * (ST + A) + ST + 32 * crank + k] = cv;
+                if (k == 0 && crank == 0) {
+                    const bool padded = p.tlens && t >= p.tlens[b0 + b];
+                    p.pen[(size_t)(b0 + b) * T + t] = padded ? 0.f : p.lambda * fmaxf(w1 * inv - w2, 0.f);
+                }
+            }
+        }
+        __syncthreads();
+        dc_bcast<A, 32, BG>(sm.stage, c_a, bar_a[BAR_C], crank, warp, lane);
+        // alpha_t of this CTA's frames (the broadcast is in flight meanwhile)
+        for (int i = tid; i < BG * DC_RMAX; i += DC_THREADS) {
+            const int b = i / DC_RMAX, r = i % DC_RMAX;
+            if (r < sm.nr_s[b]) {
+                const float a = sm.p_s[b][r] * sm.scl_own[b];
+                sm.ap_s[b][r] = a;
+                p.alpha[((size_t)(b0 + b) * T + t) * Lmax + sm.l0_s[b] + r] = a;
+            }
+        }
+        mbar_wait(&sm.bar[BAR_C], parity);
+        DC_TICK(3);
+
+        // ---- u_t = W_jc c_t + uy_t   (Attention.lua:150-151, folded) --------------------------------------------------------
+        dc_mv<BG, 16>(sm.wjc, &sm.c_full[0][0], A, 8 * warp, 8 * warp, warp, lane, sm.part);
+        __syncthreads();
+        if (tid < BG * 16) {
+            const int b = tid >> 4, r = tid & 15;
+            float v = uyv;
+#pragma unroll
+            for (int w = 0; w < 16; w++) v += sm.part[w][b][r];
+            sm.stage[b][r] = v;
+            if (b0 + b < p.B) {
+                const size_t row = (size_t)(b0 + b) * T + t;
+                p.su[row * 2 * ST + ST + 16 * crank + r] = v;
+                p.rhu[row * 2 * ST + ST + 16 * crank + r] = v;
+            }
+        }
+        __syncthreads();
+        dc_bcast<ST, 16, BG>(sm.stage, u_a, bar_a[BAR_U], crank, warp, lane);
+        mbar_wait(&sm.bar[BAR_U], parity);
+        DC_TICK(4);
+
+        // ---- z, r = sigmoid(G_zr {s_{t-1}, u_t}) ; r * s_{t-1}   (GRU.lua:22-25) -----------------------------------------------
+        if (warp < 8) dc_mv<BG, 32>(sm.gz, &sm.s_full[0][0], ST, 8 * warp, 8 * warp, warp, lane, sm.part);
+        else dc_mv<BG, 32>(sm.gz, &sm.u_full[0][0], ST, 8 * warp, 8 * warp - 64, warp, lane, sm.part);
+        __syncthreads();
+        if (tid < BG * 32) {
+            const int b = tid >> 5, rr = tid & 31;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; w++) v += sm.part[w][b][rr];
+            const float g = sigmoid_acc(v);
+            const size_t row = (size_t)(b0 + b) * T + t;
+            const bool live = b0 + b < p.B;
+            if (rr < 16) {
+                sm.zbuf[b][rr] = g;
+                if (live) p.gates[row * 3 * ST + 16 * crank + rr] = g;
+            } else {
+                const int j = 16 * crank + rr - 16;
+                const float rs = g * sm.s_full[b][j];
+                sm.stage[b][rr - 16] = rs;
+                if (live) { p.gates[row * 3 * ST + ST + j] = g; p.rhu[row * 2 * ST + j] = rs; }
+            }
+        }
+        __syncthreads();
+        dc_bcast<ST, 16, BG>(sm.stage, rs_a, bar_a[BAR_RS], crank, warp, lane);
+        mbar_wait(&sm.bar[BAR_RS], parity);
+        DC_TICK(5);
+
+        // ---- h~ = tanh(G_h {r s_{t-1}, u_t}) ; s_t = (1-z) s_{t-1} + z h~   (GRU.lua:26-30) ------------------------------------
+        if (warp < 8) dc_mv<BG, 16>(sm.gh, &sm.rs_full[0][0], ST, 8 * warp, 8 * warp, warp, lane, sm.part);
+        else dc_mv<BG, 16>(sm.gh, &sm.u_full[0][0], ST, 8 * warp, 8 * warp - 64, warp, lane, sm.part);
+        __syncthreads();
+        if (tid < BG * 16) {
+            const int b = tid >> 4, r = tid & 15, j = 16 * crank + r;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; w++) v += sm.part[w][b][r];
+            const float hc = tanh_acc(v), z = sm.zbuf[b][r], sp = sm.s_full[b][j];
+            const float sn = (1.f - z) * sp + z * hc;
+            sm.stage[b][r] = sn;
+            if (b0 + b < p.B) {
+                const size_t row = (size_t)(b0 + b) * T + t;
+                p.gates[row * 3 * ST + 2 * ST + j] = hc;
+                p.sc[row * (ST + A) + j] = sn;
+                if (t + 1 < T) p.su[(row + 1) * 2 * ST + j] = sn;
+            }
+        }
+        __syncthreads();
+        dc_bcast<ST, 16, BG>(sm.stage, s_a, bar_a[BAR_S], crank, warp, lane);
+        mbar_wait(&sm.bar[BAR_S], parity);
+        DC_TICK(6);
+
+        // ---- q_{t+1} = W_s s_t + b_s   (Attention.lua:65-67) -------------------------------------------------------------------
+        if (t + 1 < T) {
+            float acc[BG];
+#pragma unroll
+            for (int b = 0; b < BG; b++) {
+                acc[b] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[b] = dot4(wq[i], *reinterpret_cast<const float4*>(&sm.s_full[b][16 * warp + 4 * i]), acc[b]);
+                sm.part[warp][b][lane] = acc[b];
+            }
+            __syncthreads();
+            if (tid < BG * 32) {
+                const int b = tid >> 5, k = tid & 31;
+                float v = __ldg(p.qbias + 32 * crank + k);
+#pragma unroll
+                for (int w = 0; w < 16; w++) v += sm.part[w][b][k];
+                sm.stage[b][k] = v;
+                if (b0 + b < p.B) p.q[((size_t)(b0 + b) * T + t + 1) * S + 32 * crank + k] = v;
+            }
+            __syncthreads();
+            dc_bcast<S, 32, BG>(sm.stage, q_a, bar_a[BAR_Q], crank, warp, lane);
+            if (warp < NR) load_pair(warp, va);              // Vh does not depend on q: the next step's first frames are fetched under the exchange
+            mbar_wait(&sm.bar[BAR_Q], parity);
+        }
+        DC_TICK(7);
+        parity ^= 1;
+    }
+#undef DC_TICK
+    cluster_sync_all();
+}
+
+
+template <int BG>
+static int dc_launch(s2s_ctx* ctx, const DecClusterParams& p, int* max_clusters) {
+    static bool attr = false;
+    const size_t smem = sizeof(DcSmem<BG>);
+    if (!attr) {
+        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_fwd_kernel<BG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_fwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(DC_CS * ceil_div(p.B, BG));
+    cfg.blockDim = dim3(DC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = DC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (max_clusters) {
+        if (cudaOccupancyMaxActiveClusters(max_clusters, dec_cluster_fwd_kernel<BG>, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
+        return 0;
+    }
+    S2S_CUDA(cudaLaunchKernelEx(&cfg, dec_cluster_fwd_kernel<BG>, p));
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int dc_enabled() {
+    const char* e = getenv("S2S_DEC_CLUSTER");      // read per call: tests and benchmarks compare both paths in one process
+    return e ? atoi(e) : 1;
+}
+
+// The decoder time loop of decoder_forward on the cluster kernel.  *handled = false (nothing launched) when the shapes are
+// not the ones the kernel is built for or clusters of 16 cannot be scheduled; the caller then runs the per-step path.
+int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, const int* tlens,
+                            int T, float lambda, const float* uy, DecoderState& d, bool* handled) {
+    *handled = false;
+    const int KF = Y.K > 0 ? Y.KF : 0;
+    if (!dc_enabled() || Y.ST != DC_ST || Y.A != DC_A || Y.S != DC_S || KF != 0 || Lmax > DC_CS * DC_RMAX) return 0;
+    static int cap = -1;
+    DecClusterParams p = {};
+    p.Vh = d.Vh; p.h = h; p.w = P + Y.we.off; p.qbias = d.qbias; p.Ws = P + Y.Ws.off; p.Wjc = d.Wjc; p.Gz = P + Y.Gz.off; p.Gh = P + Y.Gh.off;
+    p.uy = uy; p.lengths = lengths; p.tlens = tlens; p.B = B; p.Lmax = Lmax; p.T = T; p.lambda = lambda;
+    p.alpha = d.alpha; p.sc = d.sc; p.q = d.q; p.pen = d.pen; p.su = d.su; p.rhu = d.rhu; p.gates = d.gates;
+    if (cap < 0) { int n = 0; S2S_TRY(dc_launch<5>(ctx, p, &n)); cap = n; }
+    if (cap < 1) return 0;
+    static long long* clk = nullptr;
+    static int prof = -1;
+    if (prof < 0) { const char* e = getenv("S2S_DEC_PROF"); prof = e ? atoi(e) : 0; }
+    if (prof && !ctx->capturing) {
+        if (!clk) { S2S_CUDA(cudaMalloc(&clk, 16 * sizeof(long long))); }
+        S2S_CUDA(cudaMemsetAsync(clk, 0, 16 * sizeof(long long), ctx->stream));
+        p.clk = clk;
+    }
+    // frames past an utterance's length keep alpha = 0 (the per-step kernel writes those zeros every step)
+    S2S_CUDA(cudaMemsetAsync(d.alpha, 0, (size_t)B * T * Lmax * sizeof(float), ctx->stream));
+    int bg = 1;
+    while (bg < 5 && ceil_div(B, bg) > cap) bg++;          // one wave of clusters when possible
+    { const char* e = getenv("S2S_DEC_BG"); if (e && atoi(e) >= 1 && atoi(e) <= 5) bg = atoi(e); }
+    prof_begin(ctx, S2S_PROF_DEC_FWD);
+    switch (bg) {
+        case 1: S2S_TRY(dc_launch<1>(ctx, p, nullptr)); break;
+        case 2: S2S_TRY(dc_launch<2>(ctx, p, nullptr)); break;
+        case 3: S2S_TRY(dc_launch<3>(ctx, p, nullptr)); break;
+        case 4: S2S_TRY(dc_launch<4>(ctx, p, nullptr)); break;
+        default: S2S_TRY(dc_launch<5>(ctx, p, nullptr)); break;
+    }
+    prof_end(ctx, S2S_PROF_DEC_FWD, 4.0 * B * T * ((double)Lmax * (DC_S + DC_A)));
+    if (p.clk) {
+        long long hclk[16];
+        S2S_CUDA(cudaStreamSynchronize(ctx->stream));
+        S2S_CUDA(cudaMemcpy(hclk, clk, sizeof(hclk), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[dec_cluster] B=%d L=%d T=%d BG=%d clocks/step: score %lld | stats %lld | ctx %lld | wait cp %lld | combine+c %lld | u %lld | zr %lld | h %lld | q %lld\n",
+                B, Lmax, T, bg, hclk[0] / T, hclk[8] / T, hclk[1] / T, hclk[2] / T, hclk[3] / T, hclk[4] / T, hclk[5] / T, hclk[6] / T, hclk[7] / T);
+    }
+    *handled = true;
+    return 0;
+}
+
+}  // namespace s2s

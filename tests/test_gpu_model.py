@@ -29,13 +29,25 @@ def _seg_errs(cfg, orc, G, Gref):
                                                  # librispeech/model_vgg.lua decoder: two Maxout stages; decoder-only parameter vector
                                                  (0, 4, 0.0, True, dict(MLP=2)), (0, 10, 0.0, False, dict(MLP=2, NL=0))])
 def test_attention_module_matches_oracle(s2s, gctx, orc64, K, KF, lam, drop, extra):
-    cfg = dict(MID, K=K, KF=KF, **extra)
-    B, L, T = 4, 45, 7
+    _check_attention_module(s2s, gctx, orc64, dict(MID, K=K, KF=KF, **extra), 4, 45, 7, lam, drop)
+
+
+# the model's own decoder sizes (ST = 256, S = A = 512): the time loop runs as ONE persistent cluster kernel
+# (csrc/decoder_cluster.cu); B picks the utterances-per-cluster variant, short utterances leave CTAs without frames
+@pytest.mark.parametrize("B,L,T,lam,extra", [(3, 70, 6, 0.03, {}), (9, 40, 5, 0.0, {}), (16, 33, 4, 0.02, dict(MLP=2)), (37, 24, 3, 0.0, {})])
+def test_attention_module_cluster_decoder(s2s, gctx, orc64, B, L, T, lam, extra):
+    cfg = dict(D=13, H=256, NL=0, S=512, ST=256, V=11, K=0, KF=4, M=8, MW=3, **extra)
+    _check_attention_module(s2s, gctx, orc64, cfg, B, L, T, lam, False, short=True)
+
+
+def _check_attention_module(s2s, gctx, orc64, cfg, B, L, T, lam, drop, short=False):
     P = init_params(cfg, seed=5, dtype=np.float64, oracle=orc64) * 1.5
     rng = np.random.default_rng(1)
     A = 2 * cfg["H"]
     h = rng.standard_normal((B, L, A)) * 0.7
     _, lengths, labels, tlens = make_batch(cfg, B, L, T, seed=2)
+    if short:
+        lengths[1] = 5; lengths[B - 1] = 17
     dm = ((rng.random((B, T, cfg["ST"] + A)) > 0.5) / 0.5) if drop else None
     dlogp = rng.standard_normal((B, T, cfg["V"]))
     for b in range(B):
