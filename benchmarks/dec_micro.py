@@ -26,5 +26,14 @@ for it in range(3 + N):
     torch.cuda.synchronize()
     if it >= 3:
         tf += ev[0].elapsed_time(ev[1]) / N; tb += ev[1].elapsed_time(ev[2]) / N
+ctx.profile(True)
+for _ in range(5):
+    s2s.attention_forward(ctx, cfg, P, h, y)
+pr = ctx.profile_read(); ctx.profile(False)
+if pr["dec_fwd"][1]:
+    print(f"dec_cluster_fwd_kernel: {pr['dec_fwd'][0] / pr['dec_fwd'][1] * 1e3:.1f} us per launch = {pr['dec_fwd'][0] / pr['dec_fwd'][1] * 1e3 / T:.2f} us per decoder step (events around the launch)")
+else:
+    per = sum(pr[k][0] for k in ("attn_fwd", "dense_small")) / 5
+    print(f"per-step path: attention + dense launches {per * 1e3:.1f} us per call = {per * 1e3 / T:.2f} us per decoder step (events around each launch)")
 print(f"S2S_DEC_CLUSTER={os.environ.get('S2S_DEC_CLUSTER', '1')} B={B} L={L} T={T}: attention_forward {tf:.3f} ms, attention_backward {tb:.3f} ms "
       f"(eager launches); logp checksum {float(logp.double().sum()):.6f} dh checksum {float(dh.double().abs().sum()):.6f}")

@@ -50,7 +50,7 @@ struct DcSmem {
     float gz[128 * 32 * 4];
     float gh[128 * 16 * 4];
     // all-gathered vectors
-    float q_full[BG][DC_S];
+    float q_full[BG][DC_S];        // holds 2 log2(e) q (see dc_tanh4_dot)
     float c_full[BG][DC_A];
     float s_full[BG][DC_ST];
     float u_full[BG][DC_ST];
@@ -59,7 +59,7 @@ struct DcSmem {
     float recv_c[DC_CS][BG][32];
     float4 recv_st[DC_CS][BG];
     float part[16][BG][32];        // per-warp (K-slice) partial sums of a mat-vec phase
-    float e_s[BG][DC_RMAX], p_s[BG][DC_RMAX], ap_s[BG][DC_RMAX];
+    float e_s[BG][DC_RMAX], p_s[BG][DC_RMAX + 16], ap_s[BG][DC_RMAX];     // p_s: zero past the slice (the context loop reads blocks of 20)
     float w_s[DC_S];
     float stage[BG][32];
     float zbuf[BG][16];
@@ -110,15 +110,18 @@ __device__ __forceinline__ void dc_mv(const float* __restrict__ Wt, const float*
     }
 }
 
-// acc + w . tanh(z) for four elements with ONE reciprocal: tanh(x) = 1 - 2 / (e^{2x} + 1); the four denominators are inverted
-// together (1 / d_i = (product of the others) / (d_0 d_1 d_2 d_3)), 5 MUFU operations per 4 elements instead of 8 -- the scoring
-// phase is MUFU-bound.  x is clamped to 10 (tanh(10) rounds to 1.0f), so the product stays below 6e34.
-__device__ __forceinline__ float dc_tanh4_dot(const float4 w, const float4 z, float acc) {
-    const float k = 2.885390081777927f;                      // 2 log2(e)
-    const float d0 = exp2f(k * fminf(z.x, 10.f)) + 1.f, d1 = exp2f(k * fminf(z.y, 10.f)) + 1.f;
-    const float d2 = exp2f(k * fminf(z.z, 10.f)) + 1.f, d3 = exp2f(k * fminf(z.w, 10.f)) + 1.f;
+// acc + w . tanh(x) for four elements with ONE reciprocal, x given as y = 2 log2(e) x (the factor is folded into the staged q and
+// one FFMA per element): tanh(x) = 1 - 2 / (2^y + 1); the four denominators are inverted together
+// (1 / d_i = (product of the others) / (d_0 d_1 d_2 d_3)), 5 MUFU operations per 4 elements instead of 8, raw ex2.approx / rcp.approx
+// (no range fix-up code: y is clamped to 10 k, tanh(10) rounds to 1.0f, so the product stays below 6e34 and nothing is denormal).
+constexpr float DC_K = 2.885390081777927f;                   // 2 log2(e)
+__device__ __forceinline__ float dc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float dc_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float dc_tanh4_dot(const float4 w, const float4 v, const float4 qk, float acc) {
+    const float d0 = dc_ex2(fminf(fmaf(DC_K, v.x, qk.x), 10.f * DC_K)) + 1.f, d1 = dc_ex2(fminf(fmaf(DC_K, v.y, qk.y), 10.f * DC_K)) + 1.f;
+    const float d2 = dc_ex2(fminf(fmaf(DC_K, v.z, qk.z), 10.f * DC_K)) + 1.f, d3 = dc_ex2(fminf(fmaf(DC_K, v.w, qk.w), 10.f * DC_K)) + 1.f;
     const float p01 = d0 * d1, p23 = d2 * d3;
-    const float r = __fdividef(-2.0f, p01 * p23);
+    const float r = -2.0f * dc_rcp(p01 * p23);
     const float r01 = r * p23, r23 = r * p01;                // -2 / (d0 d1), -2 / (d2 d3)
     acc = fmaf(w.x, fmaf(r01, d1, 1.f), acc);
     acc = fmaf(w.y, fmaf(r01, d0, 1.f), acc);
@@ -151,9 +154,10 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
             sm.gz[((size_t)(k >> 2) * 32 + r) * 4 + (k & 3)] = p.Gz[(size_t)n * 2 * ST + k];
         }
         for (int i = tid; i < S; i += DC_THREADS) sm.w_s[i] = p.w[i];
-        for (int i = tid; i < BG * S; i += DC_THREADS) (&sm.q_full[0][0])[i] = p.qbias[i % S];      // q_0 = W_s 0 + b_s
+        for (int i = tid; i < BG * S; i += DC_THREADS) (&sm.q_full[0][0])[i] = DC_K * p.qbias[i % S];      // q_0 = W_s 0 + b_s
         for (int i = tid; i < BG * ST; i += DC_THREADS) (&sm.s_full[0][0])[i] = 0.f;               // s_0 = 0 (Recurrent.lua:112)
         for (int i = tid; i < BG * DC_RMAX; i += DC_THREADS) (&sm.ap_s[0][0])[i] = 0.f;            // alpha_{-1} = 0
+        for (int i = tid; i < BG * (DC_RMAX + 16); i += DC_THREADS) (&sm.p_s[0][0])[i] = 0.f;
         if (tid < BG) {
             const int b = b0 + tid;
             const int Lb = b < p.B ? (p.lengths ? p.lengths[b] : Lmax) : 0;
@@ -223,7 +227,7 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
             for (int i = 0; i < 4; i++) {
                 const float4 qv = *reinterpret_cast<const float4*>(&sm.q_full[b][lane * 4 + 128 * i]);
                 const float4 wv = *reinterpret_cast<const float4*>(&sm.w_s[lane * 4 + 128 * i]);
-                acc = dc_tanh4_dot(wv, make_float4(v[j][i].x + qv.x, v[j][i].y + qv.y, v[j][i].z + qv.z, v[j][i].w + qv.w), acc);
+                acc = dc_tanh4_dot(wv, v[j][i], qv, acc);
             }
             acc = warp_sum(acc);
             if (lane == 0) sm.e_s[b][sm.fr[f]] = acc;        // (a duplicated tail frame rewrites the same value)
@@ -260,22 +264,27 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
         __syncthreads();
         DC_TICK(0);
 
-        // ---- partial context: thread = (float4 column c4, row group g), warp w holds the 8 columns of CTA w's slice x 4 row groups; the
-        // frames of two utterances (up to 2 x 20 rows) are in flight at once, the first pair is issued before the statistics ----
+        // ---- partial context: thread = (float4 column c4, row group g), warp w holds the 8 columns of CTA w's slice x 4 row groups;
+        // blocks of 20 frames of two utterances (2 x 5 loads per thread) are in flight at once, the first block is issued before the
+        // statistics.  Row indices are clamped instead of predicated: p_s is zero past the slice. ---------------------------------
         const int c4 = 8 * warp + (lane & 7), g = lane >> 3;     // a quarter-warp reads 128 contiguous bytes of one frame
         float4 hx[2][5];
-        auto ctx_load = [&](int bp) {
+        auto ctx_load = [&](int bp, int base) {
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 if (bp + j >= BG) continue;
                 const int b = bp + j, nr = sm.nr_s[b];
-                if (nr == 0) continue;                               // (uniform) no frames of this utterance here: hx unused, p_s = 0
+                if (nr <= base) {                                    // (uniform) nothing left of this utterance here
+#pragma unroll
+                    for (int u = 0; u < 5; u++) hx[j][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    continue;
+                }
                 const float* hp = p.h + ((size_t)(b0 + b) * Lmax + sm.l0_s[b]) * A + c4 * 4;
 #pragma unroll
-                for (int u = 0; u < 5; u++) hx[j][u] = ldg_stream(hp + (size_t)min(g + 4 * u, nr - 1) * A);   // clamped: p_s is 0 past the slice
+                for (int u = 0; u < 5; u++) hx[j][u] = ldg_stream(hp + (size_t)min(base + g + 4 * u, nr - 1) * A);
             }
         };
-        ctx_load(0);
+        ctx_load(0, 0);
 
         // ---- local softmax statistics: warp b -> utterance b --------------------------------------------------------------
         if (warp < BG) {
@@ -300,40 +309,27 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
 #pragma unroll
             for (int bp = 0; bp < BG; bp += 2) {
                 float4 acc[2];
+                acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int nrm = max(sm.nr_s[bp], bp + 1 < BG ? sm.nr_s[bp + 1] : 0);
+                for (int base = 0; base < nrm || base == 0; base += 20) {
+                    if (base > 0) ctx_load(bp, base);
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bp + j < BG) {
-                        const int b = bp + j;
-                        if (sm.nr_s[b] > 0) {
+                    for (int j = 0; j < 2; j++) {
+                        if (bp + j < BG) {
 #pragma unroll
                             for (int u = 0; u < 5; u++) {
-                                const float pv = sm.p_s[b][g + 4 * u];
+                                const float pv = sm.p_s[bp + j][base + g + 4 * u];
                                 acc[j].x = fmaf(pv, hx[j][u].x, acc[j].x); acc[j].y = fmaf(pv, hx[j][u].y, acc[j].y);
                                 acc[j].z = fmaf(pv, hx[j][u].z, acc[j].z); acc[j].w = fmaf(pv, hx[j][u].w, acc[j].w);
                             }
                         }
                     }
                 }
-                if (bp + 2 < BG) ctx_load(bp + 2);                   // next pair in flight during the tail / reduction of this one
+                if (bp + 2 < BG) ctx_load(bp + 2, 0);                // next pair in flight during the reduction of this one
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     if (bp + j < BG) {
-                        const int b = bp + j, nr = sm.nr_s[b];
-                        if (nr > 20) {                               // long utterances: the remaining frames of the slice
-                            const float* hp = p.h + ((size_t)(b0 + b) * Lmax + sm.l0_s[b]) * A + c4 * 4;
-                            for (int r0 = g + 20; r0 < nr; r0 += 16) {
-                                float4 x[4];
-#pragma unroll
-                                for (int u = 0; u < 4; u++) x[u] = r0 + 4 * u < nr ? ldg_stream(hp + (size_t)(r0 + 4 * u) * A) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const float pv = r0 + 4 * u < nr ? sm.p_s[b][r0 + 4 * u] : 0.f;
-                                    acc[j].x = fmaf(pv, x[u].x, acc[j].x); acc[j].y = fmaf(pv, x[u].y, acc[j].y);
-                                    acc[j].z = fmaf(pv, x[u].z, acc[j].z); acc[j].w = fmaf(pv, x[u].w, acc[j].w);
-                                }
-                            }
-                        }
+                        const int b = bp + j;
 #pragma unroll
                         for (int o = 8; o <= 16; o <<= 1) {
                             acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o); acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
@@ -477,7 +473,7 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
                 float v = __ldg(p.qbias + 32 * crank + k);
 #pragma unroll
                 for (int w = 0; w < 16; w++) v += sm.part[w][b][k];
-                sm.stage[b][k] = v;
+                sm.stage[b][k] = DC_K * v;
                 if (b0 + b < p.B) p.q[((size_t)(b0 + b) * T + t + 1) * S + 32 * crank + k] = v;
             }
             __syncthreads();
