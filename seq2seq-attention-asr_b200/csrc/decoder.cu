@@ -21,7 +21,7 @@ namespace s2s {
 // warp-uniform broadcasts (one pass per LDS.128), so there is no shuffle reduction and no re-read of X;
 // the eight K-slices are summed through shared memory and the GRU gate math is fused into the epilogue.
 // =================================================================================================
-enum { EPI_LINEAR = 0, EPI_GRU_ZR = 1, EPI_GRU_H = 2, EPI_BWD_DRHU = 3, EPI_BWD_DS = 4 };
+enum { EPI_LINEAR = 0, EPI_GRU_ZR = 1, EPI_GRU_H = 2, EPI_BWD_DRHU = 3, EPI_BWD_DS = 4, EPI_BWD_DSU_DC = 5 };
 struct DenseEpi {
     int mode = EPI_LINEAR;
     const float* bias = nullptr;
@@ -71,6 +71,15 @@ __device__ __forceinline__ void dense_epilogue(const DenseEpi& e, int b, int n, 
         } else {
             e.dsu[(size_t)b * 2 * e.ST + n] = v;
         }
+    } else if (e.mode == EPI_BWD_DSU_DC) {
+        // rows n < 2ST: d{s_{t-1}, u} += {daz, dar} . G_zr ; rows n >= 2ST: dc_t = dc_mlp + du . W_jc with du substituted (folded weights)
+        if (n < 2 * e.ST) {
+            v += __ldcg(e.dsu + (size_t)b * 2 * e.ST + n);
+            e.dsu[(size_t)b * 2 * e.ST + n] = v;
+            if (n >= e.ST) e.out2[(size_t)b * e.ld_out2 + n - e.ST] = v;
+        } else {
+            e.out[(size_t)b * e.ld_out + n - 2 * e.ST] = v + __ldcg(e.dsc + (size_t)b * e.ld_dsc + n - 2 * e.ST);
+        }
     } else {   // EPI_BWD_DS: v = (dq . W_s)[n]; ds_{t-1} complete -> elementwise GRU backward of step t-1
         const float ds = v + __ldcg(e.dsu + (size_t)b * 2 * e.ST + n) + __ldcg(e.dsc + (size_t)b * e.ld_dsc + n);
         const float z = __ldcg(e.gates_n + (size_t)b * e.ld_gates + n), hc = __ldcg(e.gates_n + (size_t)b * e.ld_gates + 2 * e.ST + n);
@@ -99,6 +108,8 @@ __device__ __forceinline__ EpiOps dense_prefetch(const DenseEpi& e, int b, int n
             o.b = __ldcg(e.sprev + (size_t)b * e.ld_sprev + n);
             o.c = __ldcg(e.dsu + (size_t)b * 2 * e.ST + n);
         }
+    } else if (e.mode == EPI_BWD_DSU_DC) {
+        o.a = n < 2 * e.ST ? __ldcg(e.dsu + (size_t)b * 2 * e.ST + n) : __ldcg(e.dsc + (size_t)b * e.ld_dsc + n - 2 * e.ST);
     } else {
         o.a = __ldcg(e.dsu + (size_t)b * 2 * e.ST + n);
         o.b = __ldcg(e.dsc + (size_t)b * e.ld_dsc + n);
@@ -130,6 +141,14 @@ __device__ __forceinline__ void dense_epilogue_pf(const DenseEpi& e, int b, int 
             e.dsu[(size_t)b * 2 * e.ST + n] = o.c + v * o.a;
         } else {
             e.dsu[(size_t)b * 2 * e.ST + n] = v;
+        }
+    } else if (e.mode == EPI_BWD_DSU_DC) {
+        v += o.a;
+        if (n < 2 * e.ST) {
+            e.dsu[(size_t)b * 2 * e.ST + n] = v;
+            if (n >= e.ST) e.out2[(size_t)b * e.ld_out2 + n - e.ST] = v;
+        } else {
+            e.out[(size_t)b * e.ld_out + n - 2 * e.ST] = v;
         }
     } else {
         const float ds = v + o.a + o.b;
@@ -342,6 +361,11 @@ dense_chain_kernel(const __grid_constant__ ChainParams p) {
 
 struct ChainLink { const float* X; int64_t ldx; int K; const float* W; int ldw; int N; DenseEpi e; };
 
+static bool dense_chain_on() {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("S2S_CHAIN"); enabled = e ? atoi(e) : 0; }
+    return enabled != 0;
+}
 static bool dense_chain_supported(const ChainLink* l, int n) {
     static int enabled = -1;
     // Measured on B200 (cfg2, CUDA-graph replay): one chain launch = 29.5 us against 4 x 5.5 us for the separate
@@ -709,6 +733,21 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     S2S_TRY(transpose_f32(ctx, P + Y.Gz.off, 2 * ST, 2 * ST, 2 * ST, GzrT, 2 * ST)); // rows: z then r (contiguous segments)
     S2S_TRY(transpose_f32(ctx, d.Wjc, ST, A, A, WjcT, ST));                          // (W_j[:, :ST] W_c)^T  [A, ST]
     S2S_TRY(transpose_f32(ctx, P + Y.Ws.off, S, ST, ST, WsT, S));                    // WsT [ST, S]
+    // The last two links of the chain, d{s_{t-1},u} += {daz,dar} G_zr and dc_t = dc_mlp + du W_jc, as ONE product: du is linear in
+    // {daz, dar, dah} (du = dah G_h[:, ST:] + {daz,dar} G_zr[:, ST:]), so dc_t = dc_mlp + {daz,dar,dah} . W3[2ST:] with
+    //   W3 [(2ST + A), 3ST] = [ G_zr^T | 0 ;  W_jc^T G_zr^T[ST:] | W_jc^T G_h^T[ST:] ]
+    // -- one dependent launch less per decoder step.
+    float* W3 = nullptr;
+    const bool fuse3 = 3 * ST <= 1024 && !dense_chain_on();
+    if (fuse3) {
+        S2S_ALLOC(W3, ar, float, (size_t)(2 * ST + A) * 3 * ST);
+        S2S_CUDA(cudaMemsetAsync(W3, 0, (size_t)(2 * ST + A) * 3 * ST * sizeof(float), st));
+        S2S_CUDA(cudaMemcpy2DAsync(W3, (size_t)3 * ST * sizeof(float), GzrT, (size_t)2 * ST * sizeof(float), (size_t)2 * ST * sizeof(float), 2 * ST,
+                                   cudaMemcpyDeviceToDevice, st));
+        float* W3c = W3 + (size_t)2 * ST * 3 * ST;
+        S2S_TRY(gemm_f32(ctx, false, false, A, 2 * ST, ST, 1.f, WjcT, ST, GzrT + (size_t)ST * 2 * ST, 2 * ST, 0.f, W3c, 3 * ST, nullptr, GemmBatch(), 1, 1));
+        S2S_TRY(gemm_f32(ctx, false, false, A, ST, ST, 1.f, WjcT, ST, GhT + (size_t)ST * ST, ST, 0.f, W3c + 2 * ST, 3 * ST, nullptr, GemmBatch(), 1, 1));
+    }
 
     // ---- time-batched MLP backward (model_chorowski_baseline.lua:53-59 reversed) ----------------
     logsoftmax_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT, 8), 256, 0, st>>>(d.logp, dlogp, (int64_t)BT, V, tlens, T, dlogits);
@@ -769,13 +808,18 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
             e.sprev = d.su + (size_t)t * 2 * ST; e.ld_sprev = ldsu; e.dA = dA + (size_t)t * 3 * ST; e.ld_dA = lddA; e.dsu = dsu;
             k.X = dA + (size_t)t * 3 * ST + 2 * ST; k.ldx = lddA; k.K = ST; k.W = GhT; k.ldw = ST; k.N = 2 * ST;
         }
-        {   // d{s_{t-1}, u} += {daz, dar} . G_{z,r}
+        if (fuse3) {   // d{s_{t-1}, u} += {daz, dar} . G_{z,r}  and  dc_t, one launch (see W3 above)
+            ChainLink& k = L[nl++]; DenseEpi& e = k.e;
+            e.mode = EPI_BWD_DSU_DC; e.ST = ST; e.dsu = dsu; e.out2 = du_all + (size_t)t * ST; e.ld_out2 = (int64_t)T * ST;
+            e.dsc = dsc + (size_t)t * (ST + A) + ST; e.ld_dsc = ldsc; e.out = dc_all + (size_t)t * A; e.ld_out = (int64_t)T * A;
+            k.X = dA + (size_t)t * 3 * ST; k.ldx = lddA; k.K = 3 * ST; k.W = W3; k.ldw = 3 * ST; k.N = 2 * ST + A;
+        } else {   // d{s_{t-1}, u} += {daz, dar} . G_{z,r}
             ChainLink& k = L[nl++]; DenseEpi& e = k.e;
             e.add = dsu; e.ld_add = 2 * ST; e.out = dsu; e.ld_out = 2 * ST;
             e.out2 = du_all + (size_t)t * ST; e.ld_out2 = (int64_t)T * ST; e.n2_start = ST;
             k.X = dA + (size_t)t * 3 * ST; k.ldx = lddA; k.K = 2 * ST; k.W = GzrT; k.ldw = 2 * ST; k.N = 2 * ST;
         }
-        {   // dc_t = dc_mlp + du . (W_j[:, :ST] W_c)
+        if (!fuse3) {   // dc_t = dc_mlp + du . (W_j[:, :ST] W_c)
             ChainLink& k = L[nl++]; DenseEpi& e = k.e;
             e.add = dsc + (size_t)t * (ST + A) + ST; e.ld_add = ldsc; e.out = dc_all + (size_t)t * A; e.ld_out = (int64_t)T * A;
             k.X = dsu + ST; k.ldx = 2 * ST; k.K = ST; k.W = WjcT; k.ldw = ST; k.N = A;
