@@ -29,7 +29,10 @@ for it in range(3 + N):
 ctx.profile(True)
 for _ in range(5):
     s2s.attention_forward(ctx, cfg, P, h, y)
+    s2s.attention_backward(ctx, cfg, P, G, h, y, dlogp)
 pr = ctx.profile_read(); ctx.profile(False)
+if pr["dec_bwd"][1]:
+    print(f"dec_cluster_bwd_kernel: {pr['dec_bwd'][0] / pr['dec_bwd'][1] * 1e3:.1f} us per launch = {pr['dec_bwd'][0] / pr['dec_bwd'][1] * 1e3 / T:.2f} us per decoder step")
 if pr["dec_fwd"][1]:
     print(f"dec_cluster_fwd_kernel: {pr['dec_fwd'][0] / pr['dec_fwd'][1] * 1e3:.1f} us per launch = {pr['dec_fwd'][0] / pr['dec_fwd'][1] * 1e3 / T:.2f} us per decoder step (events around the launch)")
 else:

@@ -785,11 +785,14 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     if (KF > 0) pad_lr(KF, &padl);
     const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST, lddA = (int64_t)T * 3 * ST;
     const int eb = ceil_div(B * ST, 256);
+    bool clustered = false;      // the whole loop in one persistent cluster kernel (decoder_cluster.cu) when the shapes allow
+    if (!carry_alpha)
+        S2S_TRY(decoder_cluster_backward(ctx, Y, P, h, lengths, B, Lmax, T, lambda, d, WsT, GhT, GzrT, WjcT, dsc, dA, du_all, dc_all, dq_all, de_all, &clustered));
     // elementwise GRU backward of the LAST step (ds_carry = 0); later steps get it fused into the W_s product
-    gru_bwd_e1_kernel<<<eb, 256, 0, st>>>(dsc + (size_t)(T - 1) * (ST + A), ldsc, ds_carry, d.gates + (size_t)(T - 1) * 3 * ST, ldg,
+    if (!clustered) gru_bwd_e1_kernel<<<eb, 256, 0, st>>>(dsc + (size_t)(T - 1) * (ST + A), ldsc, ds_carry, d.gates + (size_t)(T - 1) * 3 * ST, ldg,
                                            d.su + (size_t)(T - 1) * 2 * ST, ldsu, B, ST, dA + (size_t)(T - 1) * 3 * ST, lddA, dsu);
     S2S_LAUNCH_CHECK(ctx);
-    for (int t = T - 1; t >= 0; t--) {
+    for (int t = T - 1; t >= 0 && !clustered; t--) {
         const int cur = (T - 1 - t) & 1;
         // the dependent chain between two attention backward steps:
         //   [ds_t and the elementwise GRU backward of step t] -> d{r*s, u} -> d{s_{t-1}, u} -> dc_t

@@ -489,6 +489,407 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
 }
 
 
+
+// =================================================================================================================================
+// backward time loop (RNNAttention.lua:233-253 with the deferred accumulations of decoder.cu), t = T-1 .. 0, same cluster geometry:
+//   A  ds_t[own 16]  = carry + ds_mlp + dq_{t+1} . W_s[:, own]          dah, daz, carry = ds (1-z)           -> all-gather {dah, daz}
+//   B  d(r s)[own], du_h[own] = dah . G_h[:, own | ST+own]                dar, carry += d(r s) r               -> all-gather dar
+//   C  carry += {daz,dar} . G_zr[:, own] ; du[own] = du_h + {daz,dar} . G_zr[:, ST+own]                        -> all-gather du
+//   D  dc_t[own 32]  = dc_mlp + du . W_jc[:, own]                                                              -> all-gather dc
+//   E  own frames: dalpha_l = dc . h_l ; dot = sum alpha dalpha (cluster all-reduce) ; de_l = alpha_l (dalpha_l - dot)
+//   F  own frames: dq += de_l w (1 - tanh^2(Vh_l + q_t))  -> reduce-scatter, CTA j sums dq[32j, +32)              -> all-gather dq_t
+// The transposed weights (K-contiguous rows of the per-call copies W_s^T, G_h^T, G_zr^T, W_jc^T) stay on chip: 128 KB of shared memory
+// (k-major) + W_s^T in registers.  Outputs are the arrays the deferred GEMMs / attn_dvh of decoder_backward read: dA = daz|dar|dah,
+// du, dc, dq, de.  Content attention without the monotonicity penalty (no alpha carry).
+struct DecClusterBwdParams {
+    const float *Vh, *h, *w, *q, *alpha, *gates, *su, *dsc;
+    const float *WsT, *GhT, *GzrT, *WjcT;
+    const int* lengths;
+    int B, Lmax, T;
+    float *dA, *du_all, *dc_all, *dq_all, *de_all;
+    long long* clk;
+};
+
+template <int BG>
+struct DcBwdSmem {
+    float wb[64 * 32 * 4];         // phase B rows: G_h^T   [own 16 | ST + own 16] x K = ST,   k-major
+    float wc[128 * 32 * 4];        // phase C rows: G_zr^T  [own 16 | ST + own 16] x K = 2 ST
+    float wd[64 * 32 * 4];         // phase D rows: W_jc^T  [own 32]               x K = ST
+    float dq_full[BG][DC_S];
+    float dahz_full[BG][2 * DC_ST];        // dah | daz
+    float dar_full[BG][DC_ST];
+    float du_full[BG][DC_ST];
+    float dc_full[BG][DC_A];
+    float q_full[BG][DC_S];        // 2 log2(e) q_t
+    union {
+        float part[16][BG][32];    // mat-vec partial sums (phases A-D)
+        float recv_dq[DC_CS][BG][32];      // reduce-scatter receive (phase F): never live at the same time (see the exchange order)
+    };
+    float4 recv_dot[DC_CS][BG];
+    float al_s[BG][DC_RMAX], dal_s[BG][DC_RMAX], de_s[BG][DC_RMAX + 16];    // de_s: zero past the slice (phase F reads blocks of 20)
+    float w_s[DC_S];
+    float stage[BG][32], stage2[BG][32];
+    float carry_s[BG][16], duh_s[BG][16];
+    int l0_s[BG], nr_s[BG];
+    int frow[BG * DC_RMAX];
+    short fb[BG * DC_RMAX], fr[BG * DC_RMAX];
+    uint64_t bar[7];
+};
+enum { BB_X1 = 0, BB_X2, BB_X3, BB_X4, BB_X5, BB_X6A, BB_X6B };
+
+// generic K-slice of a mat-vec phase: the warp covers NK * (ROWS == 32 ? 1 : 2) k4 starting at k4w (weights) / k4x (x)
+template <int BG, int ROWS, int NK>
+__device__ __forceinline__ void dc_mvg(const float* __restrict__ Wt, const float* __restrict__ x, int xpitch, int k4w, int k4x, int warp, int lane,
+                                       float (*part)[BG][32]) {
+    const int r = ROWS == 32 ? lane : (lane & 15), sub = ROWS == 32 ? 0 : (lane >> 4) * NK;
+    float acc[BG];
+#pragma unroll
+    for (int b = 0; b < BG; b++) acc[b] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NK; i++) {
+        const float4 wv = *reinterpret_cast<const float4*>(Wt + ((size_t)(k4w + sub + i) * ROWS + r) * 4);
+#pragma unroll
+        for (int b = 0; b < BG; b++) acc[b] = dot4(wv, *reinterpret_cast<const float4*>(x + (size_t)b * xpitch + (k4x + sub + i) * 4), acc[b]);
+    }
+    if (ROWS == 16) {
+#pragma unroll
+        for (int b = 0; b < BG; b++) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
+    }
+    if (ROWS == 32 || lane < 16) {
+#pragma unroll
+        for (int b = 0; b < BG; b++) part[warp][b][r] = acc[b];
+    }
+}
+
+// w (1 - tanh^2(x)) for four elements, x given through y = 2 log2(e) x as in dc_tanh4_dot: with d = 2^y + 1 and r = 2 / d,
+// 1 - tanh^2 = r (2 - r); one reciprocal per four elements
+__device__ __forceinline__ float4 dc_dtanh4(const float4 w, const float4 v, const float4 qk) {
+    const float d0 = dc_ex2(fminf(fmaf(DC_K, v.x, qk.x), 10.f * DC_K)) + 1.f, d1 = dc_ex2(fminf(fmaf(DC_K, v.y, qk.y), 10.f * DC_K)) + 1.f;
+    const float d2 = dc_ex2(fminf(fmaf(DC_K, v.z, qk.z), 10.f * DC_K)) + 1.f, d3 = dc_ex2(fminf(fmaf(DC_K, v.w, qk.w), 10.f * DC_K)) + 1.f;
+    const float p01 = d0 * d1, p23 = d2 * d3;
+    const float R = 2.0f * dc_rcp(p01 * p23);
+    const float r01 = R * p23, r23 = R * p01;
+    const float r0 = r01 * d1, r1 = r01 * d0, r2 = r23 * d3, r3 = r23 * d2;
+    return make_float4(w.x * r0 * (2.f - r0), w.y * r1 * (2.f - r1), w.z * r2 * (2.f - r2), w.w * r3 * (2.f - r3));
+}
+
+template <int BG>
+__global__ void __launch_bounds__(DC_THREADS, 1)
+dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
+    extern __shared__ __align__(128) unsigned char dc_smem_raw[];
+    DcBwdSmem<BG>& sm = *reinterpret_cast<DcBwdSmem<BG>*>(dc_smem_raw);
+    constexpr int ST = DC_ST, A = DC_A, S = DC_S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = cg::this_cluster().block_rank();
+    const int b0 = (blockIdx.x / DC_CS) * BG;
+    const int T = p.T, Lmax = p.Lmax;
+
+    // ---- one-time staging (the per-call transposed copies are K-contiguous and 16-byte aligned) ----------------------------------
+    for (int i = tid; i < 32 * 64; i += DC_THREADS) {          // K = ST phases: 64 k4
+        const int r = i >> 6, k4 = i & 63;
+        const int nb = r < 16 ? 16 * crank + r : ST + 16 * crank + r - 16;
+        *reinterpret_cast<float4*>(sm.wb + ((size_t)k4 * 32 + r) * 4) = *reinterpret_cast<const float4*>(p.GhT + (size_t)nb * ST + 4 * k4);
+        *reinterpret_cast<float4*>(sm.wd + ((size_t)k4 * 32 + r) * 4) = *reinterpret_cast<const float4*>(p.WjcT + (size_t)(32 * crank + r) * ST + 4 * k4);
+    }
+    for (int i = tid; i < 32 * 128; i += DC_THREADS) {         // K = 2 ST: 128 k4
+        const int r = i >> 7, k4 = i & 127;
+        const int nb = r < 16 ? 16 * crank + r : ST + 16 * crank + r - 16;
+        *reinterpret_cast<float4*>(sm.wc + ((size_t)k4 * 32 + r) * 4) = *reinterpret_cast<const float4*>(p.GzrT + (size_t)nb * 2 * ST + 4 * k4);
+    }
+    for (int i = tid; i < S; i += DC_THREADS) sm.w_s[i] = p.w[i];
+    for (int i = tid; i < BG * S; i += DC_THREADS) (&sm.dq_full[0][0])[i] = 0.f;          // dq_T = 0
+    for (int i = tid; i < BG * 16; i += DC_THREADS) (&sm.carry_s[0][0])[i] = 0.f;         // Recurrent.lua:134
+    for (int i = tid; i < BG * (DC_RMAX + 16); i += DC_THREADS) (&sm.de_s[0][0])[i] = 0.f;
+    if (tid < BG) {
+        const int b = b0 + tid;
+        const int Lb = b < p.B ? (p.lengths ? p.lengths[b] : Lmax) : 0;
+        const int Rb = (Lb + DC_CS - 1) / DC_CS;
+        const int l0 = (int)crank * Rb;
+        sm.l0_s[tid] = l0; sm.nr_s[tid] = max(0, min(Rb, Lb - l0));
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 7; i++) mbar_init(&sm.bar[i], 1);
+        fence_mbar_init();
+    }
+    // W_s^T rows of this CTA's 16 units, phase-A mapping: lane = (row, half), warp = 32 k
+    float4 wa[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        wa[i] = *reinterpret_cast<const float4*>(p.WsT + (size_t)(16 * crank + (lane & 15)) * S + (8 * warp + 4 * (lane >> 4) + i) * 4);
+    __syncthreads();
+    int NR = 0;
+#pragma unroll
+    for (int b = 0; b < BG; b++) NR += sm.nr_s[b];
+    for (int f = tid; f < NR; f += DC_THREADS) {
+        int r = f, b = 0;
+#pragma unroll
+        for (int bb = 0; bb < BG - 1; bb++)
+            if (b == bb && r >= sm.nr_s[bb]) { r -= sm.nr_s[bb]; b = bb + 1; }
+        sm.frow[f] = (b0 + b) * Lmax + sm.l0_s[b] + r; sm.fb[f] = (short)b; sm.fr[f] = (short)r;
+    }
+    uint32_t bar_a[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) bar_a[i] = smem_u32(&sm.bar[i]);
+    const uint32_t dahz_a = smem_u32(&sm.dahz_full[0][0]), dar_a = smem_u32(&sm.dar_full[0][0]), du_a = smem_u32(&sm.du_full[0][0]);
+    const uint32_t dc_a = smem_u32(&sm.dc_full[0][0]), dq_a = smem_u32(&sm.dq_full[0][0]);
+    const uint32_t rdot_a = smem_u32(&sm.recv_dot[0][0]), rdq_a = smem_u32(&sm.recv_dq[0][0][0]);
+    cluster_sync_all();
+
+    constexpr unsigned TX_256 = BG * 256 * 4, TX_512 = BG * 512 * 4, TX_DOT = DC_CS * BG * 16, TX_DQ = DC_CS * BG * 128;
+    long long tck = 0;
+    const bool prof = p.clk != nullptr && blockIdx.x == 0 && tid == 0;
+#define DC_TICK(i) do { if (prof) { const long long n_ = clock64(); p.clk[i] += n_ - tck; tck = n_; } } while (0)
+    if (prof) tck = clock64();
+
+    unsigned parity = 0;
+    for (int t = T - 1; t >= 0; t--) {
+        if (tid == 0) {
+            mbar_expect_tx(&sm.bar[BB_X1], TX_512); mbar_expect_tx(&sm.bar[BB_X2], TX_256); mbar_expect_tx(&sm.bar[BB_X3], TX_256);
+            mbar_expect_tx(&sm.bar[BB_X4], TX_512); mbar_expect_tx(&sm.bar[BB_X5], TX_DOT); mbar_expect_tx(&sm.bar[BB_X6A], TX_DQ);
+            mbar_expect_tx(&sm.bar[BB_X6B], TX_512);
+        }
+        // ---- operands saved by the forward pass, fetched early -------------------------------------------------------------------
+        float pa_z = 0.f, pa_hc = 0.f, pa_sp = 0.f, pa_ds = 0.f, pb_r = 0.f, pb_sp = 0.f, pd_dc = 0.f;
+        if (tid < BG * 16 && b0 + (tid >> 4) < p.B) {
+            const size_t row = (size_t)(b0 + (tid >> 4)) * T + t;
+            const int j = 16 * crank + (tid & 15);
+            pa_z = __ldg(p.gates + row * 3 * ST + j); pa_hc = __ldg(p.gates + row * 3 * ST + 2 * ST + j);
+            pa_sp = __ldg(p.su + row * 2 * ST + j); pa_ds = __ldg(p.dsc + row * (ST + A) + j);
+        }
+        if (tid < BG * 32 && b0 + (tid >> 5) < p.B) {
+            const size_t row = (size_t)(b0 + (tid >> 5)) * T + t;
+            const int rr = tid & 31;
+            if (rr < 16) { pb_r = __ldg(p.gates + row * 3 * ST + ST + 16 * crank + rr); pb_sp = __ldg(p.su + row * 2 * ST + 16 * crank + rr); }
+            pd_dc = __ldg(p.dsc + row * (ST + A) + ST + 32 * crank + rr);
+        }
+
+        // ---- A: ds_t, elementwise GRU backward ----------------------------------------------------------------------------------
+        {
+            const int r = lane & 15, half = lane >> 4;
+            float acc[BG];
+#pragma unroll
+            for (int b = 0; b < BG; b++) {
+                acc[b] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[b] = dot4(wa[i], *reinterpret_cast<const float4*>(&sm.dq_full[b][(8 * warp + 4 * half + i) * 4]), acc[b]);
+                acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
+                if (lane < 16) sm.part[warp][b][r] = acc[b];
+            }
+        }
+        __syncthreads();
+        if (tid < BG * 16) {
+            const int b = tid >> 4, r = tid & 15, j = 16 * crank + r;
+            float v = sm.carry_s[b][r] + pa_ds;
+#pragma unroll
+            for (int w = 0; w < 16; w++) v += sm.part[w][b][r];
+            const float z = pa_z, hc = pa_hc;
+            const float dah = v * z * (1.f - hc * hc), daz = v * (hc - pa_sp) * z * (1.f - z);      // GRU.lua:26-30 reversed
+            sm.carry_s[b][r] = v * (1.f - z);
+            sm.stage[b][r] = dah; sm.stage2[b][r] = daz;
+            if (b0 + b < p.B) {
+                const size_t row = (size_t)(b0 + b) * T + t;
+                p.dA[row * 3 * ST + 2 * ST + j] = dah; p.dA[row * 3 * ST + j] = daz;
+            }
+        }
+        __syncthreads();
+        dc_bcast<2 * ST, 16, BG>(sm.stage, dahz_a, bar_a[BB_X1], crank, warp, lane);
+        dc_bcast<2 * ST, 16, BG>(sm.stage2, dahz_a + ST * 4u, bar_a[BB_X1], crank, warp, lane);
+        // q_t and alpha_t of this CTA's frames (saved by the forward pass), staged under the exchange
+        for (int i = tid; i < BG * DC_RMAX; i += DC_THREADS) {
+            const int b = i / DC_RMAX, r = i % DC_RMAX;
+            sm.al_s[b][r] = r < sm.nr_s[b] ? __ldg(p.alpha + ((size_t)(b0 + b) * T + t) * Lmax + sm.l0_s[b] + r) : 0.f;
+        }
+        for (int i = tid; i < BG * S; i += DC_THREADS) {
+            const int b = i / S, k = i % S;
+            (&sm.q_full[0][0])[i] = b0 + b < p.B ? DC_K * __ldg(p.q + ((size_t)(b0 + b) * T + t) * S + k) : 0.f;
+        }
+        mbar_wait(&sm.bar[BB_X1], parity);
+        DC_TICK(0);
+
+        // ---- B: d(r s), du_h = dah . G_h ; dar -----------------------------------------------------------------------------------
+        dc_mvg<BG, 32, 4>(sm.wb, &sm.dahz_full[0][0], 2 * ST, 4 * warp, 4 * warp, warp, lane, sm.part);
+        __syncthreads();
+        if (tid < BG * 32) {
+            const int b = tid >> 5, rr = tid & 31;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; w++) v += sm.part[w][b][rr];
+            if (rr < 16) {
+                const float dar = v * pb_sp * pb_r * (1.f - pb_r);                                 // GRU.lua:24-25 reversed
+                sm.carry_s[b][rr] += v * pb_r;
+                sm.stage[b][rr] = dar;
+                if (b0 + b < p.B) p.dA[((size_t)(b0 + b) * T + t) * 3 * ST + ST + 16 * crank + rr] = dar;
+            } else {
+                sm.duh_s[b][rr - 16] = v;
+            }
+        }
+        __syncthreads();
+        dc_bcast<ST, 16, BG>(sm.stage, dar_a, bar_a[BB_X2], crank, warp, lane);
+        mbar_wait(&sm.bar[BB_X2], parity);
+        DC_TICK(1);
+
+        // ---- C: d{s_{t-1}, u} += {daz, dar} . G_zr ----------------------------------------------------------------------------------
+        if (warp < 8) dc_mvg<BG, 32, 8>(sm.wc, &sm.dahz_full[0][0] + ST, 2 * ST, 8 * warp, 8 * warp, warp, lane, sm.part);
+        else dc_mvg<BG, 32, 8>(sm.wc, &sm.dar_full[0][0], ST, 8 * warp, 8 * warp - 64, warp, lane, sm.part);
+        __syncthreads();
+        if (tid < BG * 32) {
+            const int b = tid >> 5, rr = tid & 31;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; w++) v += sm.part[w][b][rr];
+            if (rr < 16) {
+                sm.carry_s[b][rr] += v;
+            } else {
+                const float du = v + sm.duh_s[b][rr - 16];
+                sm.stage[b][rr - 16] = du;
+                if (b0 + b < p.B) p.du_all[((size_t)(b0 + b) * T + t) * ST + 16 * crank + rr - 16] = du;
+            }
+        }
+        __syncthreads();
+        dc_bcast<ST, 16, BG>(sm.stage, du_a, bar_a[BB_X3], crank, warp, lane);
+        mbar_wait(&sm.bar[BB_X3], parity);
+        DC_TICK(2);
+
+        // ---- D: dc_t = dc_mlp + du . W_jc ---------------------------------------------------------------------------------------------
+        dc_mvg<BG, 32, 4>(sm.wd, &sm.du_full[0][0], ST, 4 * warp, 4 * warp, warp, lane, sm.part);
+        __syncthreads();
+        if (tid < BG * 32) {
+            const int b = tid >> 5, k = tid & 31;
+            float v = pd_dc;
+#pragma unroll
+            for (int w = 0; w < 16; w++) v += sm.part[w][b][k];
+            sm.stage[b][k] = v;
+            if (b0 + b < p.B) p.dc_all[((size_t)(b0 + b) * T + t) * A + 32 * crank + k] = v;
+        }
+        __syncthreads();
+        dc_bcast<A, 32, BG>(sm.stage, dc_a, bar_a[BB_X4], crank, warp, lane);
+        mbar_wait(&sm.bar[BB_X4], parity);
+        DC_TICK(3);
+
+        // ---- E: dalpha_l = dc . h_l over this CTA's frames (Attention.lua:132-134 reversed) ----------------------------------------
+        for (int f0 = warp; f0 < NR; f0 += 32) {
+            float4 hv[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int f = f0 + 16 * j < NR ? f0 + 16 * j : f0;
+                const float* hp = p.h + (size_t)sm.frow[f] * A + lane * 4;
+#pragma unroll
+                for (int i = 0; i < 4; i++) hv[j][i] = ldg_stream(hp + 128 * i);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int f = f0 + 16 * j < NR ? f0 + 16 * j : f0;
+                const int b = sm.fb[f];
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc = dot4(hv[j][i], *reinterpret_cast<const float4*>(&sm.dc_full[b][lane * 4 + 128 * i]), acc);
+                acc = warp_sum(acc);
+                if (lane == 0) sm.dal_s[b][sm.fr[f]] = acc;
+            }
+        }
+        __syncthreads();
+        if (warp < BG) {   // sum_l alpha dalpha over this CTA's frames -> every CTA of the cluster
+            const int b = warp, nr = sm.nr_s[b];
+            const float d0 = lane < nr ? sm.al_s[b][lane] * sm.dal_s[b][lane] : 0.f;
+            const float d1 = lane + 32 < nr ? sm.al_s[b][lane + 32] * sm.dal_s[b][lane + 32] : 0.f;
+            const float dotp = warp_sum(d0 + d1);
+            if (lane < DC_CS)
+                st_async_v4(mapa_rank(rdot_a + (uint32_t)(crank * BG + b) * 16u, lane), make_float4(dotp, 0.f, 0.f, 0.f), mapa_rank(bar_a[BB_X5], lane));
+        }
+        mbar_wait(&sm.bar[BB_X5], parity);
+        if (warp < BG) {   // de_l = alpha_l (dalpha_l - <alpha, dalpha>)   (SoftMax backward)
+            const int b = warp, nr = sm.nr_s[b];
+            const float dot = warp_sum(lane < DC_CS ? sm.recv_dot[lane][b].x : 0.f);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const int r = lane + 32 * hh;
+                const float de = r < nr ? sm.al_s[b][r] * (sm.dal_s[b][r] - dot) : 0.f;
+                sm.de_s[b][r] = de;
+                if (r < nr) p.de_all[((size_t)(b0 + b) * T + t) * Lmax + sm.l0_s[b] + r] = de;
+            }
+        }
+        __syncthreads();
+        DC_TICK(4);
+
+        // ---- F: dq_t = sum_l de_l w (1 - tanh^2(Vh_l + q_t))   (Attention.lua:95-121 reversed) -------------------------------------------
+        // thread = (float4 column c4, row group g) like the context phase of the forward kernel: warp w holds the 8 columns of CTA w's
+        // slice x 4 row groups, so the CTA's partial needs no shared-memory accumulation: two shuffles, then straight to the owner.
+        {
+            const int c4 = 8 * warp + (lane & 7), g = lane >> 3, dst = warp;
+            const uint32_t dbar = mapa_rank(bar_a[BB_X6A], dst);
+            const float4 w4 = *reinterpret_cast<const float4*>(&sm.w_s[c4 * 4]);
+            float4 vx[2][5];
+            auto f_load = [&](int bp, int base) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    if (bp + j >= BG) continue;
+                    const int b = bp + j, nr = sm.nr_s[b];
+                    if (nr <= base) {
+#pragma unroll
+                        for (int u = 0; u < 5; u++) vx[j][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        continue;
+                    }
+                    const float* vp = p.Vh + ((size_t)(b0 + b) * Lmax + sm.l0_s[b]) * S + c4 * 4;
+#pragma unroll
+                    for (int u = 0; u < 5; u++) vx[j][u] = ldg_stream(vp + (size_t)min(base + g + 4 * u, nr - 1) * S);
+                }
+            };
+            f_load(0, 0);
+#pragma unroll
+            for (int bp = 0; bp < BG; bp += 2) {
+                float4 acc[2];
+                acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int nrm = max(sm.nr_s[bp], bp + 1 < BG ? sm.nr_s[bp + 1] : 0);
+                for (int base = 0; base < nrm || base == 0; base += 20) {
+                    if (base > 0) f_load(bp, base);
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        if (bp + j < BG) {
+                            const float4 qk = *reinterpret_cast<const float4*>(&sm.q_full[bp + j][c4 * 4]);
+#pragma unroll
+                            for (int u = 0; u < 5; u++) {
+                                const float de = sm.de_s[bp + j][base + g + 4 * u];           // zero past the slice
+                                const float4 gv = dc_dtanh4(w4, vx[j][u], qk);
+                                acc[j].x = fmaf(de, gv.x, acc[j].x); acc[j].y = fmaf(de, gv.y, acc[j].y);
+                                acc[j].z = fmaf(de, gv.z, acc[j].z); acc[j].w = fmaf(de, gv.w, acc[j].w);
+                            }
+                        }
+                    }
+                }
+                if (bp + 2 < BG) f_load(bp + 2, 0);
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    if (bp + j < BG) {
+#pragma unroll
+                        for (int o = 8; o <= 16; o <<= 1) {
+                            acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o); acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
+                            acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o); acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
+                        }
+                        if (g == 0) st_async_v4(mapa_rank(rdq_a + (uint32_t)((crank * BG + bp + j) * 32 + (c4 & 7) * 4) * 4u, dst), acc[j], dbar);
+                    }
+                }
+            }
+        }
+        mbar_wait(&sm.bar[BB_X6A], parity);
+        DC_TICK(5);
+        if (tid < BG * 32) {
+            const int b = tid >> 5, k = tid & 31;
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < DC_CS; i++) v += sm.recv_dq[i][b][k];
+            sm.stage[b][k] = v;
+            if (b0 + b < p.B) p.dq_all[((size_t)(b0 + b) * T + t) * S + 32 * crank + k] = v;
+        }
+        __syncthreads();
+        dc_bcast<S, 32, BG>(sm.stage, dq_a, bar_a[BB_X6B], crank, warp, lane);
+        mbar_wait(&sm.bar[BB_X6B], parity);
+        DC_TICK(6);
+        parity ^= 1;
+    }
+#undef DC_TICK
+    cluster_sync_all();
+}
+
 template <int BG>
 static int dc_launch(s2s_ctx* ctx, const DecClusterParams& p, int* max_clusters) {
     static bool attr = false;
@@ -563,6 +964,81 @@ int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const
         S2S_CUDA(cudaMemcpy(hclk, clk, sizeof(hclk), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[dec_cluster] B=%d L=%d T=%d BG=%d clocks/step: score %lld | stats %lld | ctx %lld | wait cp %lld | combine+c %lld | u %lld | zr %lld | h %lld | q %lld\n",
                 B, Lmax, T, bg, hclk[0] / T, hclk[8] / T, hclk[1] / T, hclk[2] / T, hclk[3] / T, hclk[4] / T, hclk[5] / T, hclk[6] / T, hclk[7] / T);
+    }
+    *handled = true;
+    return 0;
+}
+
+
+template <int BG>
+static int dcb_launch(s2s_ctx* ctx, const DecClusterBwdParams& p, int* max_clusters) {
+    static bool attr = false;
+    const size_t smem = sizeof(DcBwdSmem<BG>);
+    if (!attr) {
+        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_bwd_kernel<BG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_bwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(DC_CS * ceil_div(p.B, BG));
+    cfg.blockDim = dim3(DC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = DC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (max_clusters) {
+        if (cudaOccupancyMaxActiveClusters(max_clusters, dec_cluster_bwd_kernel<BG>, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
+        return 0;
+    }
+    S2S_CUDA(cudaLaunchKernelEx(&cfg, dec_cluster_bwd_kernel<BG>, p));
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// The time loop of decoder_backward on the cluster kernel (same conditions as the forward one, and no alpha carry: K = 0, lambda = 0).
+int decoder_cluster_backward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, int T, float lambda,
+                             const DecoderState& d, const float* WsT, const float* GhT, const float* GzrT, const float* WjcT, const float* dsc,
+                             float* dA, float* du_all, float* dc_all, float* dq_all, float* de_all, bool* handled) {
+    *handled = false;
+    const int KF = Y.K > 0 ? Y.KF : 0;
+    { const char* e = getenv("S2S_DEC_CLUSTER_BWD"); if (e && !atoi(e)) return 0; }
+    if (!dc_enabled() || Y.ST != DC_ST || Y.A != DC_A || Y.S != DC_S || KF != 0 || lambda != 0.f || Lmax > DC_CS * DC_RMAX) return 0;
+    static int cap = -1;
+    DecClusterBwdParams p = {};
+    p.Vh = d.Vh; p.h = h; p.w = P + Y.we.off; p.q = d.q; p.alpha = d.alpha; p.gates = d.gates; p.su = d.su; p.dsc = dsc;
+    p.WsT = WsT; p.GhT = GhT; p.GzrT = GzrT; p.WjcT = WjcT; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.T = T;
+    p.dA = dA; p.du_all = du_all; p.dc_all = dc_all; p.dq_all = dq_all; p.de_all = de_all;
+    if (cap < 0) { int n = 0; S2S_TRY(dcb_launch<5>(ctx, p, &n)); cap = n; }
+    if (cap < 1) return 0;
+    static long long* clk = nullptr;
+    static int prof = -1;
+    if (prof < 0) { const char* e = getenv("S2S_DEC_PROF"); prof = e ? atoi(e) : 0; }
+    if (prof && !ctx->capturing) {
+        if (!clk) { S2S_CUDA(cudaMalloc(&clk, 16 * sizeof(long long))); }
+        S2S_CUDA(cudaMemsetAsync(clk, 0, 16 * sizeof(long long), ctx->stream));
+        p.clk = clk;
+    }
+    S2S_CUDA(cudaMemsetAsync(de_all, 0, (size_t)B * T * Lmax * sizeof(float), ctx->stream));       // frames past an utterance's length
+    int bg = 1;
+    while (bg < 5 && ceil_div(B, bg) > cap) bg++;
+    { const char* e = getenv("S2S_DEC_BG"); if (e && atoi(e) >= 1 && atoi(e) <= 5) bg = atoi(e); }
+    prof_begin(ctx, S2S_PROF_DEC_BWD);
+    switch (bg) {
+        case 1: S2S_TRY(dcb_launch<1>(ctx, p, nullptr)); break;
+        case 2: S2S_TRY(dcb_launch<2>(ctx, p, nullptr)); break;
+        case 3: S2S_TRY(dcb_launch<3>(ctx, p, nullptr)); break;
+        case 4: S2S_TRY(dcb_launch<4>(ctx, p, nullptr)); break;
+        default: S2S_TRY(dcb_launch<5>(ctx, p, nullptr)); break;
+    }
+    prof_end(ctx, S2S_PROF_DEC_BWD, 4.0 * B * T * ((double)Lmax * (DC_S + DC_A)));
+    if (p.clk) {
+        long long hclk[16];
+        S2S_CUDA(cudaStreamSynchronize(ctx->stream));
+        S2S_CUDA(cudaMemcpy(hclk, clk, sizeof(hclk), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[dec_cluster bwd] B=%d L=%d T=%d BG=%d clocks/step: A %lld | B %lld | C %lld | D %lld | E (dalpha, dot, de) %lld | F (dq) %lld | dq gather %lld\n",
+                B, Lmax, T, bg, hclk[0] / T, hclk[1] / T, hclk[2] / T, hclk[3] / T, hclk[4] / T, hclk[5] / T, hclk[6] / T);
     }
     *handled = true;
     return 0;
