@@ -738,7 +738,7 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     //   W3 [(2ST + A), 3ST] = [ G_zr^T | 0 ;  W_jc^T G_zr^T[ST:] | W_jc^T G_h^T[ST:] ]
     // -- one dependent launch less per decoder step.
     float* W3 = nullptr;
-    const bool fuse3 = 3 * ST <= 1024 && !dense_chain_on();
+    const bool fuse3 = 3 * ST <= 1024 && !dense_chain_on() && !decoder_cluster_backward_eligible(Y, Lmax, lambda);   // (the cluster kernel keeps its own weights)
     if (fuse3) {
         S2S_ALLOC(W3, ar, float, (size_t)(2 * ST + A) * 3 * ST);
         S2S_CUDA(cudaMemsetAsync(W3, 0, (size_t)(2 * ST + A) * 3 * ST * sizeof(float), st));

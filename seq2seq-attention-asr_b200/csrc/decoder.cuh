@@ -44,6 +44,7 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
 // decoder_cluster.cu: the time loop of decoder_forward as one persistent cluster kernel (ST = 256, S = A = 512, K = 0)
 int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, const int* tlens,
                             int T, float lambda, const float* uy, DecoderState& d, bool* handled);
+bool decoder_cluster_backward_eligible(const Layout& Y, int Lmax, float lambda);
 int decoder_cluster_backward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, int T, float lambda,
                              const DecoderState& d, const float* WsT, const float* GhT, const float* GzrT, const float* WjcT, const float* dsc,
                              float* dA, float* du_all, float* dc_all, float* dq_all, float* de_all, bool* handled);

@@ -570,7 +570,7 @@ __device__ __forceinline__ float4 dc_dtanh4(const float4 w, const float4 v, cons
     const float R = 2.0f * dc_rcp(p01 * p23);
     const float r01 = R * p23, r23 = R * p01;
     const float r0 = r01 * d1, r1 = r01 * d0, r2 = r23 * d3, r3 = r23 * d2;
-    return make_float4(w.x * r0 * (2.f - r0), w.y * r1 * (2.f - r1), w.z * r2 * (2.f - r2), w.w * r3 * (2.f - r3));
+    return make_float4(r0 * fmaf(-w.x, r0, 2.f * w.x), r1 * fmaf(-w.y, r1, 2.f * w.y), r2 * fmaf(-w.z, r2, 2.f * w.z), r3 * fmaf(-w.w, r3, 2.f * w.w));
 }
 
 template <int BG>
@@ -699,9 +699,12 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
             const int b = i / DC_RMAX, r = i % DC_RMAX;
             sm.al_s[b][r] = r < sm.nr_s[b] ? __ldg(p.alpha + ((size_t)(b0 + b) * T + t) * Lmax + sm.l0_s[b] + r) : 0.f;
         }
-        for (int i = tid; i < BG * S; i += DC_THREADS) {
-            const int b = i / S, k = i % S;
-            (&sm.q_full[0][0])[i] = b0 + b < p.B ? DC_K * __ldg(p.q + ((size_t)(b0 + b) * T + t) * S + k) : 0.f;
+        {
+            float qv[BG];
+#pragma unroll
+            for (int b = 0; b < BG; b++) qv[b] = b0 + b < p.B ? __ldg(p.q + ((size_t)(b0 + b) * T + t) * S + tid) : 0.f;      // S == DC_THREADS
+#pragma unroll
+            for (int b = 0; b < BG; b++) sm.q_full[b][tid] = DC_K * qv[b];
         }
         mbar_wait(&sm.bar[BB_X1], parity);
         DC_TICK(0);
@@ -997,14 +1000,18 @@ static int dcb_launch(s2s_ctx* ctx, const DecClusterBwdParams& p, int* max_clust
     return 0;
 }
 
+bool decoder_cluster_backward_eligible(const Layout& Y, int Lmax, float lambda) {
+    const int KF = Y.K > 0 ? Y.KF : 0;
+    { const char* e = getenv("S2S_DEC_CLUSTER_BWD"); if (e && !atoi(e)) return false; }
+    return dc_enabled() && Y.ST == DC_ST && Y.A == DC_A && Y.S == DC_S && KF == 0 && lambda == 0.f && Lmax <= DC_CS * DC_RMAX;
+}
+
 // The time loop of decoder_backward on the cluster kernel (same conditions as the forward one, and no alpha carry: K = 0, lambda = 0).
 int decoder_cluster_backward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, int T, float lambda,
                              const DecoderState& d, const float* WsT, const float* GhT, const float* GzrT, const float* WjcT, const float* dsc,
                              float* dA, float* du_all, float* dc_all, float* dq_all, float* de_all, bool* handled) {
     *handled = false;
-    const int KF = Y.K > 0 ? Y.KF : 0;
-    { const char* e = getenv("S2S_DEC_CLUSTER_BWD"); if (e && !atoi(e)) return 0; }
-    if (!dc_enabled() || Y.ST != DC_ST || Y.A != DC_A || Y.S != DC_S || KF != 0 || lambda != 0.f || Lmax > DC_CS * DC_RMAX) return 0;
+    if (!decoder_cluster_backward_eligible(Y, Lmax, lambda)) return 0;
     static int cap = -1;
     DecClusterBwdParams p = {};
     p.Vh = d.Vh; p.h = h; p.w = P + Y.we.off; p.q = d.q; p.alpha = d.alpha; p.gates = d.gates; p.su = d.su; p.dsc = dsc;
