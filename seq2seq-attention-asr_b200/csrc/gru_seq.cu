@@ -25,6 +25,8 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "cluster_rnn.cuh"
 #include "gru_seq.cuh"
@@ -225,6 +227,172 @@ gru_seq_fwd_kernel(const GruSeqParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward, two software-pipelined half-batches per cluster: the utterances of a cluster are split into sub-batches
+// 0 = [0, NA) and 1 = [NA, BG) with their own mbarriers; while the r*h (or h') slices of one half are in flight over
+// DSMEM the CTA runs the other half's mat-vec, so most of the ~0.55 us exchange latency of each of the two dependent
+// phases of a step is covered by useful work instead of a wait:
+//     P1(0) send | P1(1) send | wait(0) P2(0) send | wait(1) P2(1) send | [next step] wait(0) P1(0) ...
+// ---------------------------------------------------------------------------------------------
+template <int UC, int NB>
+__device__ __forceinline__ void bcast_rows(const float (*stage)[UC], int lo, uint32_t buf_a, uint32_t bar_a, unsigned crank, int warp, int lane, int Hh) {
+    constexpr int CPB = UC / 4;
+    const int CS = Hh / UC;
+    for (int d = warp; d < CS; d += 8) {
+        const uint32_t rbar = mapa_rank(bar_a, d);
+        for (int ch = lane; ch < NB * CPB; ch += 32) {
+            const int b = lo + ch / CPB, off = (ch % CPB) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(&stage[b][off]);
+            st_async_v4(mapa_rank(buf_a + (uint32_t)(b * Hh + crank * UC + off) * 4u, d), v, rbar);
+        }
+    }
+}
+
+template <int H, int UC, int BG>
+__global__ void __launch_bounds__(256, 1)
+gru_seq_fwd_pipe_kernel(const GruSeqParams p) {
+    using G = Geo<H, UC, BG>;
+    constexpr int CS = G::CS, R1 = G::R1, R2 = G::R2, NBP = G::NBP, NI = G::NI;
+    constexpr int NA = (BG + 1) / 2, NBb = BG - NA;          // sub-batch sizes (NA <= NBP)
+    static_assert(NA <= NBP && NBb >= 1, "pipelined GRU: 2 <= BG <= 2 NBP");
+    __shared__ __align__(16) float hbuf[BG][H];
+    __shared__ __align__(16) float rhbuf[BG][H];
+    __shared__ __align__(16) float stage[BG][UC];
+    __shared__ float zbuf[BG][UC];
+    __shared__ uint64_t barA[2], barB[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = cg::this_cluster().block_rank();
+    const int cluster_id = blockIdx.x / CS;
+    const int ngroups = (p.B + BG - 1) / BG;
+    const int dir = cluster_id / ngroups, grp = cluster_id % ngroups;
+    const bool rev = p.ndir == 2 ? dir == 1 : p.reverse0 != 0;
+    const int b0 = grp * BG;
+    const int H3 = 3 * H;
+
+    const int g1 = warp >> 2;
+    float4 w1[R1][NI], w2[R2][NI];
+    {
+        const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw;
+#pragma unroll
+        for (int r = 0; r < R1; r++) {
+            const float* row = Wd + ((size_t)g1 * H + crank * UC + R1 * (warp & 3) + r) * p.ldw;
+#pragma unroll
+            for (int i = 0; i < NI; i++) { const float* s = row + lane * 4 + 128 * i; w1[r][i] = make_float4(s[0], s[1], s[2], s[3]); }
+        }
+#pragma unroll
+        for (int r = 0; r < R2; r++) {
+            const float* row = Wd + ((size_t)2 * H + crank * UC + R2 * warp + r) * p.ldw;
+#pragma unroll
+            for (int i = 0; i < NI; i++) { const float* s = row + lane * 4 + 128 * i; w2[r][i] = make_float4(s[0], s[1], s[2], s[3]); }
+        }
+    }
+    for (int i = tid; i < BG * H; i += 256) { (&hbuf[0][0])[i] = 0.f; (&rhbuf[0][0])[i] = 0.f; }
+    if (tid == 0) { mbar_init(&barA[0], 1); mbar_init(&barA[1], 1); mbar_init(&barB[0], 1); mbar_init(&barB[1], 1); fence_mbar_init(); }
+
+    const int bbl = lane % NBP;                                 // utterance within a sub-batch
+    const int ju1 = R1 * (warp & 3) + lane / NBP;
+    const int ju2 = R2 * warp + (lane & 15) / NBP;
+    const int j1 = crank * UC + ju1, j2 = crank * UC + ju2;
+    int Lf[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+        const int bl = (hf ? NA : 0) + bbl, b = b0 + bl;
+        Lf[hf] = (bbl < (hf ? NBb : NA) && b < p.B) ? (p.lengths ? p.lengths[b] : p.Lmax) : 0;
+    }
+    int Lgrp = 0;
+#pragma unroll
+    for (int b = 0; b < BG; b++)
+        if (b0 + b < p.B) Lgrp = max(Lgrp, p.lengths ? p.lengths[b0 + b] : p.Lmax);
+
+    const uint32_t hbuf_a = smem_u32(&hbuf[0][0]), rhbuf_a = smem_u32(&rhbuf[0][0]);
+    cluster_sync_all();
+
+    auto load_xp = [&](int s, int hf, int gate, int j) -> float {
+        if (s >= Lf[hf]) return 0.f;
+        const int t = rev ? Lf[hf] - 1 - s : s;
+        return __ldg(p.xp + ((size_t)(b0 + (hf ? NA : 0) + bbl) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + gate * H + j);
+    };
+    float xp1n[2], xp2n[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) { xp1n[hf] = load_xp(0, hf, g1, j1); xp2n[hf] = lane < 16 ? load_xp(0, hf, 2, j2) : 0.f; }
+
+    // phase 1 / phase 2 of one sub-batch
+    auto phase1 = [&](auto HF, int s, float xp1) {
+        constexpr int hf = decltype(HF)::value;
+        constexpr int NBH = hf ? NBb : NA, LO = hf ? NA : 0;
+        const float tot = matvec<H, R1, NBH, NBP>(w1, hbuf, LO, lane);
+        const float g = sigmoid_acc(tot + xp1);                                    // GRU.lua:23-24
+        if (bbl < NBH) {
+            const int bl = LO + bbl;
+            const bool act = s < Lf[hf];
+            const int t = rev ? Lf[hf] - 1 - s : s;
+            float* sv = p.save + (((size_t)(b0 + bl) * p.Lmax + t) * p.ndir + dir) * 4 * H;
+            if (g1 == 0) {
+                zbuf[bl][ju1] = g;
+            } else {
+                const float rh = g * hbuf[bl][j1];                                 // GRU.lua:25
+                stage[bl][ju1] = rh;
+                if (act) sv[3 * H + j1] = rh;
+            }
+            if (act) sv[g1 * H + j1] = g;
+        }
+        __syncthreads();
+        bcast_rows<UC, NBH>(stage, LO, rhbuf_a, smem_u32(&barA[hf]), crank, warp, lane, H);
+    };
+    auto phase2 = [&](auto HF, int s, float xp2) {
+        constexpr int hf = decltype(HF)::value;
+        constexpr int NBH = hf ? NBb : NA, LO = hf ? NA : 0;
+        const float tot = matvec<H, R2, NBH, NBP>(w2, rhbuf, LO, lane);
+        const float hc = tanh_acc(tot + xp2);                                      // GRU.lua:26
+        if (lane < 16 && bbl < NBH) {
+            const int bl = LO + bbl;
+            const bool act = s < Lf[hf];
+            const int t = rev ? Lf[hf] - 1 - s : s;
+            const float hp = hbuf[bl][j2];
+            float hn = hp;                                                         // inactive: state frozen
+            if (act) {
+                const float z = zbuf[bl][ju2];
+                hn = (1.f - z) * hp + z * hc;                                      // GRU.lua:27-30
+                const size_t row = (size_t)(b0 + bl) * p.Lmax + t;
+                p.save[(row * p.ndir + dir) * 4 * H + 2 * H + j2] = hc;
+                p.y[row * (p.ndir * H) + dir * H + j2] = hn;
+            }
+            stage[bl][ju2] = hn;
+        }
+        __syncthreads();
+        bcast_rows<UC, NBH>(stage, LO, hbuf_a, smem_u32(&barB[hf]), crank, warp, lane, H);
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+
+    unsigned parity = 0;
+    for (int s = 0; s < Lgrp; s++) {
+        float xp1[2], xp2[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            xp1[hf] = xp1n[hf]; xp2[hf] = xp2n[hf];
+            xp1n[hf] = load_xp(s + 1, hf, g1, j1);
+            xp2n[hf] = lane < 16 ? load_xp(s + 1, hf, 2, j2) : 0.f;
+        }
+        // a barrier is re-armed only after its previous phase has been observed complete by the arming thread
+        if (tid == 0) { mbar_expect_tx(&barA[0], NA * H * 4); mbar_expect_tx(&barA[1], NBb * H * 4); }
+        if (s > 0) mbar_wait(&barB[0], parity ^ 1);             // h' of sub-batch 0 from the previous step
+        if (tid == 0) mbar_expect_tx(&barB[0], NA * H * 4);
+        phase1(I0(), s, xp1[0]);
+        if (s > 0) mbar_wait(&barB[1], parity ^ 1);
+        if (tid == 0) mbar_expect_tx(&barB[1], NBb * H * 4);
+        phase1(I1(), s, xp1[1]);
+        mbar_wait(&barA[0], parity);
+        phase2(I0(), s, xp2[0]);
+        mbar_wait(&barA[1], parity);
+        phase2(I1(), s, xp2[1]);
+        parity ^= 1;
+    }
+    if (Lgrp > 0) { mbar_wait(&barB[0], parity ^ 1); mbar_wait(&barB[1], parity ^ 1); }
+    cluster_sync_all();   // no CTA exits while a peer may still address its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
 template <int H, int UC, int BG>
@@ -411,6 +579,184 @@ gru_seq_bwd_kernel(const GruSeqParams p) {
     cluster_sync_all();
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward, two software-pipelined half-batches per cluster (see gru_seq_fwd_pipe_kernel):
+//     E(0) send | E(1) send | wait P1(0) send | wait P1(1) send | wait P2(0) | wait P2(1)      (P2 leaves the carry in registers)
+// ---------------------------------------------------------------------------------------------
+template <int H, int UC, int BG>
+__global__ void __launch_bounds__(256, 1)
+gru_seq_bwd_pipe_kernel(const GruSeqParams p) {
+    using G = Geo<H, UC, BG>;
+    constexpr int CS = G::CS, R1 = G::R1, R2 = G::R2, NBP = G::NBP, NI = G::NI;
+    constexpr int NA = (BG + 1) / 2, NBb = BG - NA;
+    static_assert(NA <= NBP && NBb >= 1, "pipelined GRU: 2 <= BG <= 2 NBP");
+    __shared__ __align__(16) float ahbuf[BG][H];   // dah (all units)
+    __shared__ __align__(16) float azbuf[BG][H];   // daz
+    __shared__ __align__(16) float arbuf[BG][H];   // dar
+    __shared__ __align__(16) float stage_h[BG][UC], stage_z[BG][UC], stage_r[BG][UC];
+    __shared__ float stash_r[BG][UC], stash_hp[BG][UC];
+    __shared__ float part1[BG][UC], part2[BG][UC];
+    __shared__ uint64_t barA[2], barB[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = cg::this_cluster().block_rank();
+    const int cluster_id = blockIdx.x / CS;
+    const int ngroups = (p.B + BG - 1) / BG;
+    const int dir = cluster_id / ngroups, grp = cluster_id % ngroups;
+    const bool rev = p.ndir == 2 ? dir == 1 : p.reverse0 != 0;
+    const int b0 = grp * BG;
+    const int H3 = 3 * H;
+
+    const int g1 = warp >> 2;
+    float4 w1[R1][NI], w2[R2][NI];
+    {
+        const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw;
+        const float* Wg = Wd + (size_t)(g1 == 0 ? 2 : 0) * H * p.ldw + crank * UC + R1 * (warp & 3);
+#pragma unroll
+        for (int r = 0; r < R1; r++)
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                const size_t j = lane * 4 + 128 * i;
+                w1[r][i] = make_float4(Wg[j * p.ldw + r], Wg[(j + 1) * p.ldw + r], Wg[(j + 2) * p.ldw + r], Wg[(j + 3) * p.ldw + r]);
+            }
+        const float* Wr = Wd + (size_t)H * p.ldw + crank * UC + R2 * warp;
+#pragma unroll
+        for (int r = 0; r < R2; r++)
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                const size_t j = lane * 4 + 128 * i;
+                w2[r][i] = make_float4(Wr[j * p.ldw + r], Wr[(j + 1) * p.ldw + r], Wr[(j + 2) * p.ldw + r], Wr[(j + 3) * p.ldw + r]);
+            }
+    }
+    for (int i = tid; i < BG * H; i += 256) { (&ahbuf[0][0])[i] = 0.f; (&azbuf[0][0])[i] = 0.f; (&arbuf[0][0])[i] = 0.f; }
+    if (tid == 0) { mbar_init(&barA[0], 1); mbar_init(&barA[1], 1); mbar_init(&barB[0], 1); mbar_init(&barB[1], 1); fence_mbar_init(); }
+
+    const int bbl = lane % NBP;
+    const int ju1 = R1 * (warp & 3) + lane / NBP;
+    const int ju2 = R2 * warp + (lane & 15) / NBP;
+    const int j1 = crank * UC + ju1, j2 = crank * UC + ju2;
+    const bool owner_lane = lane < 16;
+    int Lf[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+        const int bl = (hf ? NA : 0) + bbl, b = b0 + bl;
+        Lf[hf] = (bbl < (hf ? NBb : NA) && b < p.B) ? (p.lengths ? p.lengths[b] : p.Lmax) : 0;
+    }
+    int Lgrp = 0;
+#pragma unroll
+    for (int b = 0; b < BG; b++)
+        if (b0 + b < p.B) Lgrp = max(Lgrp, p.lengths ? p.lengths[b0 + b] : p.Lmax);
+
+    const uint32_t ah_a = smem_u32(&ahbuf[0][0]), az_a = smem_u32(&azbuf[0][0]), ar_a = smem_u32(&arbuf[0][0]);
+    float carry[2] = {0.f, 0.f};            // dE/dh flowing to the previous recurrence step (owner lanes)
+    float dhp_part[2] = {0.f, 0.f};
+    cluster_sync_all();
+
+    struct Pre { float z, r, hc, hp, dy; };
+    auto load_pre = [&](int s, int hf) -> Pre {
+        Pre q = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (!owner_lane || s < 0 || s >= Lf[hf]) return q;
+        const int t = rev ? Lf[hf] - 1 - s : s;
+        const int b = b0 + (hf ? NA : 0) + bbl;
+        const size_t row = (size_t)b * p.Lmax + t;
+        const float* sv = p.save + (row * p.ndir + dir) * 4 * H;
+        q.z = __ldg(sv + j2); q.r = __ldg(sv + H + j2); q.hc = __ldg(sv + 2 * H + j2);
+        if (s > 0) {                                                                  // RNN.lua:186-192
+            const int tp = rev ? t + 1 : t - 1;
+            q.hp = __ldg(p.y + ((size_t)b * p.Lmax + tp) * (p.ndir * H) + dir * H + j2);
+        }
+        q.dy = __ldg(p.dy + row * (p.ndir * H) + dir * H + j2);
+        return q;
+    };
+    Pre nxt[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) nxt[hf] = load_pre(Lgrp - 1, hf);
+
+    auto elementwise = [&](auto HF, int s) {
+        constexpr int hf = decltype(HF)::value;
+        constexpr int NBH = hf ? NBb : NA, LO = hf ? NA : 0;
+        const Pre cur = nxt[hf];
+        nxt[hf] = load_pre(s - 1, hf);
+        dhp_part[hf] = 0.f;
+        if (owner_lane && bbl < NBH) {
+            const int bl = LO + bbl;
+            float dah = 0.f, daz = 0.f;
+            if (s < Lf[hf]) {
+                const int t = rev ? Lf[hf] - 1 - s : s;
+                const size_t row = (size_t)(b0 + bl) * p.Lmax + t;
+                const float z = cur.z, r = cur.r, hc = cur.hc, hp = cur.hp;
+                const float dh = cur.dy + carry[hf];                              // RNN.lua:193-194
+                dah = dh * z * (1.f - hc * hc);
+                daz = dh * (hc - hp) * z * (1.f - z);
+                dhp_part[hf] = dh * (1.f - z);
+                float* da = p.dA + row * (p.ndir * H3) + dir * H3;
+                da[j2] = daz; da[2 * H + j2] = dah;
+                p.hp_all[(row * p.ndir + dir) * H + j2] = hp;
+                stash_r[bl][ju2] = r; stash_hp[bl][ju2] = hp;
+            }
+            stage_h[bl][ju2] = dah; stage_z[bl][ju2] = daz;
+        }
+        __syncthreads();
+        bcast_rows<UC, NBH>(stage_h, LO, ah_a, smem_u32(&barA[hf]), crank, warp, lane, H);
+        bcast_rows<UC, NBH>(stage_z, LO, az_a, smem_u32(&barA[hf]), crank, warp, lane, H);
+    };
+    auto phase1 = [&](auto HF, int s) {
+        constexpr int hf = decltype(HF)::value;
+        constexpr int NBH = hf ? NBb : NA, LO = hf ? NA : 0;
+        const float (*src1)[H] = g1 == 0 ? ahbuf : azbuf;
+        const float tot = matvec<H, R1, NBH, NBP>(w1, src1, LO, lane);
+        if (bbl < NBH) {
+            const int bl = LO + bbl;
+            const bool act = s < Lf[hf];
+            const int t = rev ? Lf[hf] - 1 - s : s;
+            if (g1 == 0) {
+                float dar = 0.f, pr = 0.f;
+                if (act) {
+                    const float r = stash_r[bl][ju1], hp = stash_hp[bl][ju1];
+                    dar = tot * hp * r * (1.f - r);
+                    pr = tot * r;
+                    p.dA[((size_t)(b0 + bl) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + H + j1] = dar;
+                }
+                part1[bl][ju1] = pr;
+                stage_r[bl][ju1] = dar;
+            } else {
+                part2[bl][ju1] = act ? tot : 0.f;
+            }
+        }
+        __syncthreads();
+        bcast_rows<UC, NBH>(stage_r, LO, ar_a, smem_u32(&barB[hf]), crank, warp, lane, H);
+    };
+    auto phase2 = [&](auto HF, int s) {
+        constexpr int hf = decltype(HF)::value;
+        constexpr int NBH = hf ? NBb : NA, LO = hf ? NA : 0;
+        const float tot = matvec<H, R2, NBH, NBP>(w2, arbuf, LO, lane);
+        const int bl = LO + bbl;
+        if (owner_lane && bbl < NBH && s < Lf[hf]) carry[hf] = dhp_part[hf] + part1[bl][ju2] + part2[bl][ju2] + tot;
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+
+    unsigned parity = 0;
+    for (int s = Lgrp - 1; s >= 0; s--) {                                           // RNN.lua:183
+        if (tid == 0) {
+            mbar_expect_tx(&barA[0], 2 * NA * H * 4); mbar_expect_tx(&barA[1], 2 * NBb * H * 4);
+            mbar_expect_tx(&barB[0], NA * H * 4); mbar_expect_tx(&barB[1], NBb * H * 4);
+        }
+        elementwise(I0(), s);
+        elementwise(I1(), s);
+        mbar_wait(&barA[0], parity);
+        phase1(I0(), s);
+        mbar_wait(&barA[1], parity);
+        phase1(I1(), s);
+        mbar_wait(&barB[0], parity);
+        phase2(I0(), s);
+        mbar_wait(&barB[1], parity);
+        phase2(I1(), s);
+        parity ^= 1;
+    }
+    cluster_sync_all();
+}
+
 // rows t >= L_b of a [B, Lmax, W] tensor := 0 (padding must not leak NaNs into the time-batched GEMMs).  The tail of an
 // utterance is one contiguous span; a few CTAs per utterance stream zeros over it (and exit at once when there is none).
 __global__ void zero_tail_rows_kernel(float* __restrict__ x, const int* __restrict__ lengths, int Lmax, int W) {
@@ -454,9 +800,25 @@ static int launch_cluster_geo(s2s_ctx* ctx, bool backward, const GruSeqParams& p
         if (e != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
         return 0;
     }
+    static int pipe = -1;
+    if (pipe < 0) { const char* e = getenv("S2S_GRU_PIPE"); pipe = e ? atoi(e) : 0; }
     prof_begin(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD);
-    if (backward) S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<H, UC, BG>, p));
-    else S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_fwd_kernel<H, UC, BG>, p));
+    static int pipeb = -1;
+    if (pipeb < 0) { const char* e = getenv("S2S_GRU_PIPE_BWD"); pipeb = e ? atoi(e) : pipe; }
+    if (backward && pipeb) {
+        if (CS > 8) {
+            static bool setb = false;
+            if (!setb) { S2S_CUDA(cudaFuncSetAttribute(gru_seq_bwd_pipe_kernel<H, UC, BG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); setb = true; }
+        }
+        S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_bwd_pipe_kernel<H, UC, BG>, p));
+    } else if (backward) S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<H, UC, BG>, p));
+    else if (pipe) {
+        if (CS > 8) {
+            static bool setp = false;
+            if (!setp) { S2S_CUDA(cudaFuncSetAttribute(gru_seq_fwd_pipe_kernel<H, UC, BG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); setp = true; }
+        }
+        S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_fwd_pipe_kernel<H, UC, BG>, p));
+    } else S2S_CUDA(cudaLaunchKernelEx(&cfg, gru_seq_fwd_kernel<H, UC, BG>, p));
     {   // algorithmic bytes per launch: fwd reads xp (3H) and writes y (H) + save (4H) per direction;
         // bwd reads save z,r,h~ (3H) + h_prev (H) + dy (H) and writes dA (3H) + h_prev (H)
         const double per = backward ? 9.0 * H : 8.0 * H;
