@@ -561,16 +561,16 @@ __device__ __forceinline__ void dc_mvg(const float* __restrict__ Wt, const float
     }
 }
 
-// w (1 - tanh^2(x)) for four elements, x given through y = 2 log2(e) x as in dc_tanh4_dot: with d = 2^y + 1 and r = 2 / d,
-// 1 - tanh^2 = r (2 - r); one reciprocal per four elements
-__device__ __forceinline__ float4 dc_dtanh4(const float4 w, const float4 v, const float4 qk) {
+// (1 - tanh^2(x)) / 4 for four elements, x given through y = 2 log2(e) x as in dc_tanh4_dot: with d = 2^y + 1 and r = 1 / d,
+// 1 - tanh^2 = 4 r (1 - r); one reciprocal per four elements.  The factor 4 w is applied once per column after the frame sum.
+__device__ __forceinline__ float4 dc_dtanh4(const float4 v, const float4 qk) {
     const float d0 = dc_ex2(fminf(fmaf(DC_K, v.x, qk.x), 10.f * DC_K)) + 1.f, d1 = dc_ex2(fminf(fmaf(DC_K, v.y, qk.y), 10.f * DC_K)) + 1.f;
     const float d2 = dc_ex2(fminf(fmaf(DC_K, v.z, qk.z), 10.f * DC_K)) + 1.f, d3 = dc_ex2(fminf(fmaf(DC_K, v.w, qk.w), 10.f * DC_K)) + 1.f;
     const float p01 = d0 * d1, p23 = d2 * d3;
-    const float R = 2.0f * dc_rcp(p01 * p23);
+    const float R = dc_rcp(p01 * p23);
     const float r01 = R * p23, r23 = R * p01;
     const float r0 = r01 * d1, r1 = r01 * d0, r2 = r23 * d3, r3 = r23 * d2;
-    return make_float4(r0 * fmaf(-w.x, r0, 2.f * w.x), r1 * fmaf(-w.y, r1, 2.f * w.y), r2 * fmaf(-w.z, r2, 2.f * w.z), r3 * fmaf(-w.w, r3, 2.f * w.w));
+    return make_float4(fmaf(-r0, r0, r0), fmaf(-r1, r1, r1), fmaf(-r2, r2, r2), fmaf(-r3, r3, r3));
 }
 
 template <int BG>
@@ -641,26 +641,35 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
 #define DC_TICK(i) do { if (prof) { const long long n_ = clock64(); p.clk[i] += n_ - tck; tck = n_; } } while (0)
     if (prof) tck = clock64();
 
+    // operands saved by the forward pass, per epilogue thread; each set is re-fetched for step t-1 as soon as its epilogue of step t
+    // has consumed it, a whole step ahead of its use
+    float pa_z = 0.f, pa_hc = 0.f, pa_sp = 0.f, pa_ds = 0.f, pb_r = 0.f, pb_sp = 0.f, pd_dc = 0.f;
+    auto load_pa = [&](int t) {
+        if (t >= 0 && tid < BG * 16 && b0 + (tid >> 4) < p.B) {
+            const size_t row = (size_t)(b0 + (tid >> 4)) * T + t;
+            const int j = 16 * crank + (tid & 15);
+            pa_z = __ldg(p.gates + row * 3 * ST + j); pa_hc = __ldg(p.gates + row * 3 * ST + 2 * ST + j);
+            pa_sp = __ldg(p.su + row * 2 * ST + j); pa_ds = __ldg(p.dsc + row * (ST + A) + j);
+        }
+    };
+    auto load_pb = [&](int t) {
+        if (t >= 0 && tid < BG * 32 && (tid & 31) < 16 && b0 + (tid >> 5) < p.B) {
+            const size_t row = (size_t)(b0 + (tid >> 5)) * T + t;
+            pb_r = __ldg(p.gates + row * 3 * ST + ST + 16 * crank + (tid & 31)); pb_sp = __ldg(p.su + row * 2 * ST + 16 * crank + (tid & 31));
+        }
+    };
+    auto load_pd = [&](int t) {
+        if (t >= 0 && tid < BG * 32 && b0 + (tid >> 5) < p.B)
+            pd_dc = __ldg(p.dsc + ((size_t)(b0 + (tid >> 5)) * T + t) * (ST + A) + ST + 32 * crank + (tid & 31));
+    };
+    load_pa(T - 1); load_pb(T - 1); load_pd(T - 1);
+
     unsigned parity = 0;
     for (int t = T - 1; t >= 0; t--) {
         if (tid == 0) {
             mbar_expect_tx(&sm.bar[BB_X1], TX_512); mbar_expect_tx(&sm.bar[BB_X2], TX_256); mbar_expect_tx(&sm.bar[BB_X3], TX_256);
             mbar_expect_tx(&sm.bar[BB_X4], TX_512); mbar_expect_tx(&sm.bar[BB_X5], TX_DOT); mbar_expect_tx(&sm.bar[BB_X6A], TX_DQ);
             mbar_expect_tx(&sm.bar[BB_X6B], TX_512);
-        }
-        // ---- operands saved by the forward pass, fetched early -------------------------------------------------------------------
-        float pa_z = 0.f, pa_hc = 0.f, pa_sp = 0.f, pa_ds = 0.f, pb_r = 0.f, pb_sp = 0.f, pd_dc = 0.f;
-        if (tid < BG * 16 && b0 + (tid >> 4) < p.B) {
-            const size_t row = (size_t)(b0 + (tid >> 4)) * T + t;
-            const int j = 16 * crank + (tid & 15);
-            pa_z = __ldg(p.gates + row * 3 * ST + j); pa_hc = __ldg(p.gates + row * 3 * ST + 2 * ST + j);
-            pa_sp = __ldg(p.su + row * 2 * ST + j); pa_ds = __ldg(p.dsc + row * (ST + A) + j);
-        }
-        if (tid < BG * 32 && b0 + (tid >> 5) < p.B) {
-            const size_t row = (size_t)(b0 + (tid >> 5)) * T + t;
-            const int rr = tid & 31;
-            if (rr < 16) { pb_r = __ldg(p.gates + row * 3 * ST + ST + 16 * crank + rr); pb_sp = __ldg(p.su + row * 2 * ST + 16 * crank + rr); }
-            pd_dc = __ldg(p.dsc + row * (ST + A) + ST + 32 * crank + rr);
         }
 
         // ---- A: ds_t, elementwise GRU backward ----------------------------------------------------------------------------------
@@ -691,6 +700,7 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
                 p.dA[row * 3 * ST + 2 * ST + j] = dah; p.dA[row * 3 * ST + j] = daz;
             }
         }
+        load_pa(t - 1);
         __syncthreads();
         dc_bcast<2 * ST, 16, BG>(sm.stage, dahz_a, bar_a[BB_X1], crank, warp, lane);
         dc_bcast<2 * ST, 16, BG>(sm.stage2, dahz_a + ST * 4u, bar_a[BB_X1], crank, warp, lane);
@@ -726,6 +736,7 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
                 sm.duh_s[b][rr - 16] = v;
             }
         }
+        load_pb(t - 1);
         __syncthreads();
         dc_bcast<ST, 16, BG>(sm.stage, dar_a, bar_a[BB_X2], crank, warp, lane);
         mbar_wait(&sm.bar[BB_X2], parity);
@@ -764,6 +775,7 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
             sm.stage[b][k] = v;
             if (b0 + b < p.B) p.dc_all[((size_t)(b0 + b) * T + t) * A + 32 * crank + k] = v;
         }
+        load_pd(t - 1);
         __syncthreads();
         dc_bcast<A, 32, BG>(sm.stage, dc_a, bar_a[BB_X4], crank, warp, lane);
         mbar_wait(&sm.bar[BB_X4], parity);
@@ -820,7 +832,8 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
         {
             const int c4 = 8 * warp + (lane & 7), g = lane >> 3, dst = warp;
             const uint32_t dbar = mapa_rank(bar_a[BB_X6A], dst);
-            const float4 w4 = *reinterpret_cast<const float4*>(&sm.w_s[c4 * 4]);
+            float4 w4 = *reinterpret_cast<const float4*>(&sm.w_s[c4 * 4]);
+            w4.x *= 4.f; w4.y *= 4.f; w4.z *= 4.f; w4.w *= 4.f;
             float4 vx[2][5];
             auto f_load = [&](int bp, int base) {
 #pragma unroll
@@ -852,7 +865,7 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
 #pragma unroll
                             for (int u = 0; u < 5; u++) {
                                 const float de = sm.de_s[bp + j][base + g + 4 * u];           // zero past the slice
-                                const float4 gv = dc_dtanh4(w4, vx[j][u], qk);
+                                const float4 gv = dc_dtanh4(vx[j][u], qk);
                                 acc[j].x = fmaf(de, gv.x, acc[j].x); acc[j].y = fmaf(de, gv.y, acc[j].y);
                                 acc[j].z = fmaf(de, gv.z, acc[j].z); acc[j].w = fmaf(de, gv.w, acc[j].w);
                             }
@@ -868,7 +881,9 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
                             acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o); acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
                             acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o); acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
                         }
-                        if (g == 0) st_async_v4(mapa_rank(rdq_a + (uint32_t)((crank * BG + bp + j) * 32 + (c4 & 7) * 4) * 4u, dst), acc[j], dbar);
+                        if (g == 0)
+                            st_async_v4(mapa_rank(rdq_a + (uint32_t)((crank * BG + bp + j) * 32 + (c4 & 7) * 4) * 4u, dst),
+                                        make_float4(w4.x * acc[j].x, w4.y * acc[j].y, w4.z * acc[j].z, w4.w * acc[j].w), dbar);
                     }
                 }
             }
