@@ -582,10 +582,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
-                    help="cfg2 = the metric's configuration (default); cfg3 = dropout model + AdaptiveWeightNoise (BASELINE.json configs[2]); "
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2loc", "cfg3", "cfg4"],
+                    help="cfg2 = the metric's configuration (default); cfg2loc = the same model with the location-aware term switched on "
+                         "(hybridAttendFeatureMaps = 16, filter 10: SURVEY Q1); cfg3 = dropout model + AdaptiveWeightNoise (BASELINE.json configs[2]); "
                          "cfg4 = librispeech/model_vgg.lua, VGG front-end + attention decoder (configs[3])")
     args = ap.parse_args()
+    if args.config == "cfg2loc":   # opt.hybridAttendFeatureMaps = 16 (timit/timit.lua:130), filter size 10 (model_chorowski_baseline.lua:39)
+        CFG["K"] = 16
+        globals()["WORKLOAD"] = WORKLOAD.replace("cfg2:", "cfg2loc:").replace("content attention K=0", "location-aware attention K=16, k=10")
     if args.impl == "reference":
         run_reference(args)
     elif args.config == "cfg4":

@@ -678,9 +678,11 @@ struct DvhParams {
     float *dVh, *dwe, *duw;
 };
 
-template <bool LOC>
+// LOC: 0 = content attention, 1 = location term with a run-time filter size (<= LOC_MAXKF), > 1 = exact filter size
+template <int LOC>
 __global__ void __launch_bounds__(128)
 attn_dvh_kernel(const DvhParams p) {
+    constexpr int KFC = LOC > 1 ? LOC : LOC_MAXKF;            // filter taps held in registers
     extern __shared__ float sm[];
     float* de_s = sm;                                         // [T][DVH_R]
     float* ap_s = de_s + p.T * DVH_R;                         // [T][DVH_R+KF-1]  (LOC)
@@ -713,22 +715,28 @@ attn_dvh_kernel(const DvhParams p) {
     for (int r = 0; r < DVH_R; r++) { v[r] = r < nrows ? vb[(size_t)r * S] : 0.f; acc[r] = 0.f; }
     const float wi = p.w[i];
     float dw = 0.f;
-    float uwr[LOC ? LOC_MAXKF : 1], duwr[LOC ? LOC_MAXKF : 1];
+    float uwr[LOC ? KFC : 1], duwr[LOC ? KFC : 1];
     if (LOC) {
 #pragma unroll
-        for (int jj = 0; jj < LOC_MAXKF; jj++) { uwr[jj] = jj < p.KF ? p.uw[jj * S + i] : 0.f; duwr[jj] = 0.f; }
+        for (int jj = 0; jj < KFC; jj++) { uwr[jj] = jj < p.KF ? p.uw[jj * S + i] : 0.f; duwr[jj] = 0.f; }
     }
     const float* qb = p.q_all + (size_t)b * p.T * S + i;
     for (int t = 0; t < Tb; t++) {
         const float q = qb[(size_t)t * S];
+        // the alpha_{t-1} window of this CTA's frames: read once per step (warp-uniform broadcasts) and reused by every frame and tap
+        // (one LDS per FMA before: the kernel was bound by shared-memory instruction issue); taps past KF have zero weights
+        float a[LOC ? DVH_R + KFC - 1 : 1];
+        if (LOC) {
+#pragma unroll
+            for (int x = 0; x < DVH_R + KFC - 1; x++) a[x] = (LOC > 1 || x < W) ? ap_s[t * W + x] : 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < DVH_R; r++) {
             const float d = de_s[t * DVH_R + r];
             float z = q + v[r];
             if (LOC) {
 #pragma unroll
-                for (int jj = 0; jj < LOC_MAXKF; jj++)
-                    if (jj < p.KF) z = fmaf(uwr[jj], ap_s[t * W + r + jj], z);
+                for (int jj = 0; jj < KFC; jj++) z = fmaf(uwr[jj], a[r + jj], z);
             }
             const float th = tanh_acc(z);
             const float dz = d * wi * (1.f - th * th);
@@ -736,8 +744,7 @@ attn_dvh_kernel(const DvhParams p) {
             dw = fmaf(d, th, dw);
             if (LOC) {
 #pragma unroll
-                for (int jj = 0; jj < LOC_MAXKF; jj++)
-                    if (jj < p.KF) duwr[jj] = fmaf(dz, ap_s[t * W + r + jj], duwr[jj]);
+                for (int jj = 0; jj < KFC; jj++) duwr[jj] = fmaf(dz, a[r + jj], duwr[jj]);
             }
         }
     }
@@ -747,7 +754,7 @@ attn_dvh_kernel(const DvhParams p) {
     atomicAdd(p.dwe + i, dw);
     if (LOC) {
 #pragma unroll
-        for (int jj = 0; jj < LOC_MAXKF; jj++)
+        for (int jj = 0; jj < KFC; jj++)
             if (jj < p.KF) atomicAdd(p.duw + jj * S + i, duwr[jj]);
     }
 }
@@ -883,12 +890,15 @@ int attn_dvh(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* de_
     S2S_REQUIRE(smem <= 200 * 1024, "attn_dvh: T=%d too large for the shared-memory staging", T);
     dim3 grid(ceil_div(Lmax, DVH_R), B, S / 128);
     prof_begin(ctx, S2S_PROF_ATTN_DVH);
-    if (loc.KF > 0) {
-        S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_dvh_kernel<true><<<grid, 128, smem, ctx->stream>>>(p);
+    if (loc.KF == 10) {
+        S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_dvh_kernel<10><<<grid, 128, smem, ctx->stream>>>(p);
+    } else if (loc.KF > 0) {
+        S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_dvh_kernel<1><<<grid, 128, smem, ctx->stream>>>(p);
     } else {
-        if (smem > 48 * 1024) S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_dvh_kernel<false><<<grid, 128, smem, ctx->stream>>>(p);
+        if (smem > 48 * 1024) S2S_CUDA(cudaFuncSetAttribute(attn_dvh_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_dvh_kernel<0><<<grid, 128, smem, ctx->stream>>>(p);
     }
     prof_end(ctx, S2S_PROF_ATTN_DVH, 4.0 * B * ((double)2 * Lmax * S + (double)T * S + (double)T * Lmax));   // one read of Vh, one write of dVh
     S2S_LAUNCH_CHECK(ctx);
