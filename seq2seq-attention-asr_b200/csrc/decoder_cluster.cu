@@ -41,9 +41,12 @@ struct DecClusterParams {
     float lambda;
     float *alpha, *sc, *q, *pen, *su, *rhu, *gates;
     long long* clk;                // optional per-phase clock accumulators (S2S_DEC_PROF)
+    const float* uw;               // location term (LOC): folded weights U W_F [KF][S], filter size, left padding
+    int KF, padl;
 };
+constexpr int DC_KFMAX = 10;       // filter taps of the location term the cluster kernel holds in shared memory
 
-template <int BG>
+template <int BG, int LOC = 0>
 struct DcSmem {
     // weights, k-major: Wt[(k4 * ROWS + r) * 4 + kk] = W[row0 + r][4 k4 + kk]
     float wjc[128 * 16 * 4];
@@ -68,6 +71,9 @@ struct DcSmem {
     int frow[BG * DC_RMAX];        // this CTA's frames, flattened over its utterances: row of Vh / h ((b0+b) Lmax + l)
     short fb[BG * DC_RMAX], fr[BG * DC_RMAX];      // utterance and frame-within-slice of a flattened frame
     uint64_t bar[6];               // q, cp, c, u, rs, s
+    // location-aware term (Attention.lua:75-99, folded): 2 log2(e) U W_F, and alpha_{t-1} over this CTA's frames plus the filter halo
+    float uw_s[LOC ? DC_KFMAX * DC_S : 4];
+    float aph_s[LOC ? BG : 1][DC_RMAX + 16];
 };
 enum { BAR_Q = 0, BAR_CP, BAR_C, BAR_U, BAR_RS, BAR_S };
 
@@ -129,11 +135,11 @@ __device__ __forceinline__ float dc_tanh4_dot(const float4 w, const float4 v, co
     return fmaf(w.w, fmaf(r23, d2, 1.f), acc);
 }
 
-template <int BG>
+template <int BG, int LOC>
 __global__ void __launch_bounds__(DC_THREADS, 1)
 dec_cluster_fwd_kernel(const DecClusterParams p) {
     extern __shared__ __align__(128) unsigned char dc_smem_raw[];
-    DcSmem<BG>& sm = *reinterpret_cast<DcSmem<BG>*>(dc_smem_raw);
+    DcSmem<BG, LOC>& sm = *reinterpret_cast<DcSmem<BG, LOC>*>(dc_smem_raw);
     constexpr int ST = DC_ST, A = DC_A, S = DC_S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned crank = cg::this_cluster().block_rank();
@@ -154,6 +160,10 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
             sm.gz[((size_t)(k >> 2) * 32 + r) * 4 + (k & 3)] = p.Gz[(size_t)n * 2 * ST + k];
         }
         for (int i = tid; i < S; i += DC_THREADS) sm.w_s[i] = p.w[i];
+        if constexpr (LOC != 0) {
+            for (int i = tid; i < DC_KFMAX * S; i += DC_THREADS) sm.uw_s[i] = i < p.KF * S ? DC_K * p.uw[i] : 0.f;     // taps past KF: zero weights
+            for (int i = tid; i < BG * (DC_RMAX + 16); i += DC_THREADS) (&sm.aph_s[0][0])[i] = 0.f;                      // alpha_{-1} = 0
+        }
         for (int i = tid; i < BG * S; i += DC_THREADS) (&sm.q_full[0][0])[i] = DC_K * p.qbias[i % S];      // q_0 = W_s 0 + b_s
         for (int i = tid; i < BG * ST; i += DC_THREADS) (&sm.s_full[0][0])[i] = 0.f;               // s_0 = 0 (Recurrent.lua:112)
         for (int i = tid; i < BG * DC_RMAX; i += DC_THREADS) (&sm.ap_s[0][0])[i] = 0.f;            // alpha_{-1} = 0
@@ -225,7 +235,16 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
             float acc = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float4 qv = *reinterpret_cast<const float4*>(&sm.q_full[b][lane * 4 + 128 * i]);
+                float4 qv = *reinterpret_cast<const float4*>(&sm.q_full[b][lane * 4 + 128 * i]);
+                if constexpr (LOC != 0) {   // + U W_F alpha_{t-1}[l + j - pad_left]   (Attention.lua:86-99)
+                    const float* ap = &sm.aph_s[b][sm.fr[f]];
+#pragma unroll 2
+                    for (int jj = 0; jj < DC_KFMAX; jj++) {
+                        const float4 u4 = *reinterpret_cast<const float4*>(&sm.uw_s[jj * S + lane * 4 + 128 * i]);
+                        const float a = ap[jj];
+                        qv.x = fmaf(a, u4.x, qv.x); qv.y = fmaf(a, u4.y, qv.y); qv.z = fmaf(a, u4.z, qv.z); qv.w = fmaf(a, u4.w, qv.w);
+                    }
+                }
                 const float4 wv = *reinterpret_cast<const float4*>(&sm.w_s[lane * 4 + 128 * i]);
                 acc = dc_tanh4_dot(wv, v[j][i], qv, acc);
             }
@@ -243,6 +262,7 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
             mbar_expect_tx(&sm.bar[BAR_U], TX_256); mbar_expect_tx(&sm.bar[BAR_RS], TX_256); mbar_expect_tx(&sm.bar[BAR_S], TX_256);
             if (t + 1 < T) mbar_expect_tx(&sm.bar[BAR_Q], TX_512);
         }
+        if constexpr (LOC != 0) __syncthreads();                 // alpha_{t-1} window staged at the end of the previous step
         // uy_t of the u rows this thread finalises (fetched early)
         float uyv = 0.f;
         if (tid < BG * 16 && b0 + (tid >> 4) < p.B) uyv = __ldg(p.uy + ((size_t)(b0 + (tid >> 4)) * T + t) * ST + 16 * crank + (tid & 15));
@@ -383,6 +403,7 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
                 p.alpha[((size_t)(b0 + b) * T + t) * Lmax + sm.l0_s[b] + r] = a;
             }
         }
+        if constexpr (LOC != 0) __threadfence();                 // the neighbours read this slice's alpha_t (filter halo) through L2
         mbar_wait(&sm.bar[BAR_C], parity);
         DC_TICK(3);
 
@@ -479,6 +500,15 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
             __syncthreads();
             dc_bcast<S, 32, BG>(sm.stage, q_a, bar_a[BAR_Q], crank, warp, lane);
             if (warp < NR) load_pair(warp, va);              // Vh does not depend on q: the next step's first frames are fetched under the exchange
+            if constexpr (LOC != 0) {   // alpha_t over this CTA's frames and the filter halo (written by the neighbours three exchanges ago)
+                for (int i = tid; i < BG * (DC_RMAX + 16); i += DC_THREADS) {
+                    const int b = i / (DC_RMAX + 16), x = i % (DC_RMAX + 16);
+                    const int l = sm.l0_s[b] + x - p.padl;
+                    float a = 0.f;
+                    if (x < sm.nr_s[b] + p.KF - 1 && l >= 0 && l < sm.len_s[b]) a = __ldcg(p.alpha + ((size_t)(b0 + b) * T + t) * Lmax + l);
+                    sm.aph_s[b][x] = a;
+                }
+            }
             mbar_wait(&sm.bar[BAR_Q], parity);
         }
         DC_TICK(7);
@@ -908,13 +938,13 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
     cluster_sync_all();
 }
 
-template <int BG>
+template <int BG, int LOC>
 static int dc_launch(s2s_ctx* ctx, const DecClusterParams& p, int* max_clusters) {
     static bool attr = false;
-    const size_t smem = sizeof(DcSmem<BG>);
+    const size_t smem = sizeof(DcSmem<BG, LOC>);
     if (!attr) {
-        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_fwd_kernel<BG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_fwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_fwd_kernel<BG, LOC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_fwd_kernel<BG, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -927,10 +957,10 @@ static int dc_launch(s2s_ctx* ctx, const DecClusterParams& p, int* max_clusters)
     at[0].val.clusterDim.x = DC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     if (max_clusters) {
-        if (cudaOccupancyMaxActiveClusters(max_clusters, dec_cluster_fwd_kernel<BG>, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
+        if (cudaOccupancyMaxActiveClusters(max_clusters, dec_cluster_fwd_kernel<BG, LOC>, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
         return 0;
     }
-    S2S_CUDA(cudaLaunchKernelEx(&cfg, dec_cluster_fwd_kernel<BG>, p));
+    S2S_CUDA(cudaLaunchKernelEx(&cfg, dec_cluster_fwd_kernel<BG, LOC>, p));
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -946,13 +976,15 @@ int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const
                             int T, float lambda, const float* uy, DecoderState& d, bool* handled) {
     *handled = false;
     const int KF = Y.K > 0 ? Y.KF : 0;
-    if (!dc_enabled() || Y.ST != DC_ST || Y.A != DC_A || Y.S != DC_S || KF != 0 || Lmax > DC_CS * DC_RMAX) return 0;
+    if (!dc_enabled() || Y.ST != DC_ST || Y.A != DC_A || Y.S != DC_S || KF > DC_KFMAX || Lmax > DC_CS * DC_RMAX) return 0;
+    if (KF > 0) { const char* e = getenv("S2S_DEC_CLUSTER_LOC"); if (e && !atoi(e)) return 0; }
     static int cap = -1;
     DecClusterParams p = {};
     p.Vh = d.Vh; p.h = h; p.w = P + Y.we.off; p.qbias = d.qbias; p.Ws = P + Y.Ws.off; p.Wjc = d.Wjc; p.Gz = P + Y.Gz.off; p.Gh = P + Y.Gh.off;
     p.uy = uy; p.lengths = lengths; p.tlens = tlens; p.B = B; p.Lmax = Lmax; p.T = T; p.lambda = lambda;
     p.alpha = d.alpha; p.sc = d.sc; p.q = d.q; p.pen = d.pen; p.su = d.su; p.rhu = d.rhu; p.gates = d.gates;
-    if (cap < 0) { int n = 0; S2S_TRY(dc_launch<5>(ctx, p, &n)); cap = n; }
+    p.uw = d.uw; p.KF = KF; p.padl = KF > 0 ? ((KF % 2 == 1) ? (KF - 1) / 2 : KF / 2) : 0;          // Attention.lua:77-85
+    if (cap < 0) { int n = 0; S2S_TRY((dc_launch<5, 1>(ctx, p, &n))); cap = n; }
     if (cap < 1) return 0;
     static long long* clk = nullptr;
     static int prof = -1;
@@ -968,12 +1000,22 @@ int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const
     while (bg < 5 && ceil_div(B, bg) > cap) bg++;          // one wave of clusters when possible
     { const char* e = getenv("S2S_DEC_BG"); if (e && atoi(e) >= 1 && atoi(e) <= 5) bg = atoi(e); }
     prof_begin(ctx, S2S_PROF_DEC_FWD);
-    switch (bg) {
-        case 1: S2S_TRY(dc_launch<1>(ctx, p, nullptr)); break;
-        case 2: S2S_TRY(dc_launch<2>(ctx, p, nullptr)); break;
-        case 3: S2S_TRY(dc_launch<3>(ctx, p, nullptr)); break;
-        case 4: S2S_TRY(dc_launch<4>(ctx, p, nullptr)); break;
-        default: S2S_TRY(dc_launch<5>(ctx, p, nullptr)); break;
+    if (KF > 0) {
+        switch (bg) {
+            case 1: S2S_TRY((dc_launch<1, 1>(ctx, p, nullptr))); break;
+            case 2: S2S_TRY((dc_launch<2, 1>(ctx, p, nullptr))); break;
+            case 3: S2S_TRY((dc_launch<3, 1>(ctx, p, nullptr))); break;
+            case 4: S2S_TRY((dc_launch<4, 1>(ctx, p, nullptr))); break;
+            default: S2S_TRY((dc_launch<5, 1>(ctx, p, nullptr))); break;
+        }
+    } else {
+        switch (bg) {
+            case 1: S2S_TRY((dc_launch<1, 0>(ctx, p, nullptr))); break;
+            case 2: S2S_TRY((dc_launch<2, 0>(ctx, p, nullptr))); break;
+            case 3: S2S_TRY((dc_launch<3, 0>(ctx, p, nullptr))); break;
+            case 4: S2S_TRY((dc_launch<4, 0>(ctx, p, nullptr))); break;
+            default: S2S_TRY((dc_launch<5, 0>(ctx, p, nullptr))); break;
+        }
     }
     prof_end(ctx, S2S_PROF_DEC_FWD, 4.0 * B * T * ((double)Lmax * (DC_S + DC_A)));
     if (p.clk) {

@@ -36,9 +36,11 @@ def test_attention_module_matches_oracle(s2s, gctx, orc64, K, KF, lam, drop, ext
 # (csrc/decoder_cluster.cu), and so does the backward loop when there is no alpha carry (lam = 0); B picks the
 # utterances-per-cluster variant, short utterances leave CTAs without frames
 @pytest.mark.parametrize("B,L,T,lam,extra", [(3, 70, 6, 0.03, {}), (3, 70, 6, 0.0, {}), (9, 40, 5, 0.0, {}), (16, 33, 4, 0.02, dict(MLP=2)),
-                                             (16, 33, 4, 0.0, dict(MLP=2)), (37, 24, 3, 0.0, {}), (2, 400, 3, 0.0, {})])
+                                             (16, 33, 4, 0.0, dict(MLP=2)), (37, 24, 3, 0.0, {}), (2, 400, 3, 0.0, {}),
+                                             # location-aware term inside the forward cluster kernel (filter halo across CTAs)
+                                             (4, 70, 6, 0.0, dict(K=16, KF=10)), (7, 45, 5, 0.02, dict(K=3, KF=5)), (2, 300, 4, 0.0, dict(K=2, KF=4))])
 def test_attention_module_cluster_decoder(s2s, gctx, orc64, B, L, T, lam, extra):
-    cfg = dict(D=13, H=256, NL=0, S=512, ST=256, V=11, K=0, KF=4, M=8, MW=3, **extra)
+    cfg = dict(dict(D=13, H=256, NL=0, S=512, ST=256, V=11, K=0, KF=4, M=8, MW=3), **extra)
     _check_attention_module(s2s, gctx, orc64, cfg, B, L, T, lam, False, short=True)
 
 
