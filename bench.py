@@ -58,7 +58,7 @@ def ncu_traffic(cls):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel class, from the committed `ncu --set full`
     capture (profiles/r01_ncu_full.json); None when there is no capture for it."""
     names = {"attn_fwd": "attn_fwd_kernel", "attn_bwd": "attn_bwd_kernel", "attn_dvh": "attn_dvh_kernel", "gru_fwd": "gru_seq_fwd_kernel",
-             "gru_bwd": "gru_seq_bwd_kernel", "gemm": "gemm_tc_kernel", "dense_small": "dense_small_kernel", "dec_fwd": "dec_cluster_fwd_kernel", "dec_bwd": "dec_cluster_bwd_kernel"}
+             "gru_bwd": "gru_seq_bwd", "gemm": "gemm_tc_kernel", "dense_small": "dense_small_kernel", "dec_fwd": "dec_cluster_fwd_kernel", "dec_bwd": "dec_cluster_bwd_kernel"}
     try:
         rows = [r for r in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full.json"))) if r["kernel"].startswith(names[cls])]
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
