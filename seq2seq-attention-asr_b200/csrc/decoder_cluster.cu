@@ -73,7 +73,7 @@ struct DcSmem {
     uint64_t bar[6];               // q, cp, c, u, rs, s
     // location-aware term (Attention.lua:75-99, folded): 2 log2(e) U W_F, and alpha_{t-1} over this CTA's frames plus the filter halo
     float uw_s[LOC ? DC_KFMAX * DC_S : 4];
-    float aph_s[LOC ? BG : 1][DC_RMAX + 16];
+    unsigned long long aph_s[LOC ? BG : 1][DC_RMAX + 16];    // {a, a} pairs (packed FFMA2 operands)
 };
 enum { BAR_Q = 0, BAR_CP, BAR_C, BAR_U, BAR_RS, BAR_S };
 
@@ -121,6 +121,10 @@ __device__ __forceinline__ void dc_mv(const float* __restrict__ Wt, const float*
 // (1 / d_i = (product of the others) / (d_0 d_1 d_2 d_3)), 5 MUFU operations per 4 elements instead of 8, raw ex2.approx / rcp.approx
 // (no range fix-up code: y is clamped to 10 k, tanh(10) rounds to 1.0f, so the product stays below 6e34 and nothing is denormal).
 constexpr float DC_K = 2.885390081777927f;                   // 2 log2(e)
+typedef unsigned long long dc_f2;                            // packed fp32 pair (fma.rn.f32x2 operands)
+__device__ __forceinline__ dc_f2 dc_pack2(float a, float b) { dc_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void dc_unpack2(dc_f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ dc_f2 dc_ffma2(dc_f2 a, dc_f2 b, dc_f2 c) { dc_f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ float dc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float dc_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float dc_tanh4_dot(const float4 w, const float4 v, const float4 qk, float acc) {
@@ -162,7 +166,7 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
         for (int i = tid; i < S; i += DC_THREADS) sm.w_s[i] = p.w[i];
         if constexpr (LOC != 0) {
             for (int i = tid; i < DC_KFMAX * S; i += DC_THREADS) sm.uw_s[i] = i < p.KF * S ? DC_K * p.uw[i] : 0.f;     // taps past KF: zero weights
-            for (int i = tid; i < BG * (DC_RMAX + 16); i += DC_THREADS) (&sm.aph_s[0][0])[i] = 0.f;                      // alpha_{-1} = 0
+            for (int i = tid; i < BG * (DC_RMAX + 16); i += DC_THREADS) (&sm.aph_s[0][0])[i] = 0ull;                     // alpha_{-1} = 0
         }
         for (int i = tid; i < BG * S; i += DC_THREADS) (&sm.q_full[0][0])[i] = DC_K * p.qbias[i % S];      // q_0 = W_s 0 + b_s
         for (int i = tid; i < BG * ST; i += DC_THREADS) (&sm.s_full[0][0])[i] = 0.f;               // s_0 = 0 (Recurrent.lua:112)
@@ -228,28 +232,49 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
         }
     };
     auto score_pair = [&](int f0, const float4 (&v)[2][4]) {
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int f = f0 + 16 * j < NR ? f0 + 16 * j : f0;
-            const int b = sm.fb[f];
-            float acc = 0.f;
+        if constexpr (LOC != 0) {
+            // both frames of the pass together: every U W_F load is shared by the two frames, alpha_{t-1} comes as broadcast {a, a}
+            // pairs, and the taps are packed FFMA2 (Attention.lua:86-99: + U W_F alpha_{t-1}[l + j - pad_left])
+            const int fA = f0, fB = f0 + 16 < NR ? f0 + 16 : f0;
+            const int bA = sm.fb[fA], bB = sm.fb[fB];
+            const dc_f2* apA = &sm.aph_s[bA][sm.fr[fA]];
+            const dc_f2* apB = &sm.aph_s[bB][sm.fr[fB]];
+            float accA = 0.f, accB = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                float4 qv = *reinterpret_cast<const float4*>(&sm.q_full[b][lane * 4 + 128 * i]);
-                if constexpr (LOC != 0) {   // + U W_F alpha_{t-1}[l + j - pad_left]   (Attention.lua:86-99)
-                    const float* ap = &sm.aph_s[b][sm.fr[f]];
+                const float4 qA = *reinterpret_cast<const float4*>(&sm.q_full[bA][lane * 4 + 128 * i]);
+                const float4 qB = *reinterpret_cast<const float4*>(&sm.q_full[bB][lane * 4 + 128 * i]);
+                dc_f2 zA0 = dc_pack2(qA.x, qA.y), zA1 = dc_pack2(qA.z, qA.w), zB0 = dc_pack2(qB.x, qB.y), zB1 = dc_pack2(qB.z, qB.w);
 #pragma unroll 2
-                    for (int jj = 0; jj < DC_KFMAX; jj++) {
-                        const float4 u4 = *reinterpret_cast<const float4*>(&sm.uw_s[jj * S + lane * 4 + 128 * i]);
-                        const float a = ap[jj];
-                        qv.x = fmaf(a, u4.x, qv.x); qv.y = fmaf(a, u4.y, qv.y); qv.z = fmaf(a, u4.z, qv.z); qv.w = fmaf(a, u4.w, qv.w);
-                    }
+                for (int jj = 0; jj < DC_KFMAX; jj++) {
+                    const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(&sm.uw_s[jj * S + lane * 4 + 128 * i]);
+                    const dc_f2 aA = apA[jj], aB = apB[jj];
+                    zA0 = dc_ffma2(aA, u.x, zA0); zA1 = dc_ffma2(aA, u.y, zA1);
+                    zB0 = dc_ffma2(aB, u.x, zB0); zB1 = dc_ffma2(aB, u.y, zB1);
                 }
+                float4 zA, zB;
+                dc_unpack2(zA0, zA.x, zA.y); dc_unpack2(zA1, zA.z, zA.w); dc_unpack2(zB0, zB.x, zB.y); dc_unpack2(zB1, zB.z, zB.w);
                 const float4 wv = *reinterpret_cast<const float4*>(&sm.w_s[lane * 4 + 128 * i]);
-                acc = dc_tanh4_dot(wv, v[j][i], qv, acc);
+                accA = dc_tanh4_dot(wv, v[0][i], zA, accA);
+                accB = dc_tanh4_dot(wv, v[1][i], zB, accB);
             }
-            acc = warp_sum(acc);
-            if (lane == 0) sm.e_s[b][sm.fr[f]] = acc;        // (a duplicated tail frame rewrites the same value)
+            accA = warp_sum(accA); accB = warp_sum(accB);
+            if (lane == 0) { sm.e_s[bA][sm.fr[fA]] = accA; sm.e_s[bB][sm.fr[fB]] = accB; }   // (a duplicated tail frame rewrites the same value)
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int f = f0 + 16 * j < NR ? f0 + 16 * j : f0;
+                const int b = sm.fb[f];
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 qv = *reinterpret_cast<const float4*>(&sm.q_full[b][lane * 4 + 128 * i]);
+                    const float4 wv = *reinterpret_cast<const float4*>(&sm.w_s[lane * 4 + 128 * i]);
+                    acc = dc_tanh4_dot(wv, v[j][i], qv, acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) sm.e_s[b][sm.fr[f]] = acc;        // (a duplicated tail frame rewrites the same value)
+            }
         }
     };
     __syncthreads();                                         // frame table
@@ -506,7 +531,7 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
                     const int l = sm.l0_s[b] + x - p.padl;
                     float a = 0.f;
                     if (x < sm.nr_s[b] + p.KF - 1 && l >= 0 && l < sm.len_s[b]) a = __ldcg(p.alpha + ((size_t)(b0 + b) * T + t) * Lmax + l);
-                    sm.aph_s[b][x] = a;
+                    sm.aph_s[b][x] = dc_pack2(a, a);
                 }
             }
             mbar_wait(&sm.bar[BAR_Q], parity);
