@@ -49,3 +49,17 @@ def test_vgg_oracle_matches_torch_autograd(T, F):
     assert np.allclose(dP, Pt.grad.numpy(), rtol=1e-9, atol=1e-11)
     assert np.allclose(dX, Xt.grad.numpy(), rtol=1e-9, atol=1e-11)
     assert (h > 0).mean() > 0.05          # the test is not vacuous: some units are active
+
+
+def test_decision_margins_are_reported():
+    # forward(..., margins=[]) collects one margin per ReLU (8) and per pooling (2): positive, and tiny at realistic sizes --
+    # the reason the GPU parity tests pick their data by margin (tests/test_gpu_vgg.py)
+    cfg = dict(C1=8, C2=12, HID=40, OUT=16)
+    rng = np.random.default_rng(0)
+    P = vgg.init_params(cfg, 24, seed=0) * 1.5
+    X = rng.standard_normal((3, 22, 24))
+    m = []
+    h, _ = vgg.forward(cfg, P, X, margins=m)
+    h2, _ = vgg.forward(cfg, P, X)
+    assert len(m) == 10 and all(v > 0 for v in m) and min(m) < 1e-2
+    assert np.array_equal(h, h2)
