@@ -107,6 +107,10 @@ struct s2s_ctx {
     int64_t capture_l0 = 0;
     bool tc_cache_on = false;
     std::vector<s2s::TcCacheEntry> tc_cache;
+    // weight-gradient GEMMs of one encoder layer overlapped with the next layer's recurrence (S2S_OVERLAP=1): they run on side[1]
+    // with a persistent grid limited to the SMs the cluster kernels leave idle
+    int gemm_sm_limit = 0;
+    bool wgrad_join_pending = false;
 };
 
 namespace s2s {

@@ -210,7 +210,12 @@ int s2s_ctx_create(int device, void* stream, s2s_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->stream = (cudaStream_t)stream;   // NULL = the legacy default stream (what cutorch uses, timit/timit.lua:39)
     c->own_stream = false;
-    for (int i = 0; i < 2; i++) S2S_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    {   // side[0] (graph capture origin) at the highest priority, side[1] (overlapped branches) at the lowest
+        int lo = 0, hi = 0;
+        S2S_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        S2S_CUDA(cudaStreamCreateWithPriority(&c->side[0], cudaStreamNonBlocking, hi));
+        S2S_CUDA(cudaStreamCreateWithPriority(&c->side[1], cudaStreamNonBlocking, lo));
+    }
     for (int i = 0; i < 4; i++) S2S_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
     S2S_CUDA(cudaMalloc((void**)&c->counters, 4096 * sizeof(unsigned)));
     S2S_CUDA(cudaMemset(c->counters, 0, 4096 * sizeof(unsigned)));

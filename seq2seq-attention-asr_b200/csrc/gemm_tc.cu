@@ -458,7 +458,7 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
     const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     Sched sc;
     sc.tiles_m = ceil_div(M, BM); sc.tiles_n = ceil_div(N, BN); sc.nk = ceil_div(K, BK);
-    sc.G = ctx->sm_count;
+    sc.G = ctx->gemm_sm_limit > 0 ? std::min(ctx->sm_count, ctx->gemm_sm_limit) : ctx->sm_count;
     static const int dbg_mode = env_int("S2S_TC_DBG", 0), tail_on = env_int("S2S_TC_TAIL", 1);
     sc.dbg = dbg_mode;
     sc.tap_slabs = cv.tap_slabs; sc.b_col0 = cv.b_col0; sc.relu = cv.relu ? 1 : 0;

@@ -897,7 +897,7 @@ int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int 
 }
 
 int gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, int ndir, int reverse, const float* x, int ldx,
-                     const int* lengths, int B, int Lmax, const float* y, const float* save, const float* dy, float* dx) {
+                     const int* lengths, int B, int Lmax, const float* y, const float* save, const float* dy, float* dx, bool defer_wgrad) {
     S2S_REQUIRE(H == 128 || H == 256, "gru_seq: hidden size %d not supported by the cluster kernel (128 or 256)", H);
     S2S_REQUIRE(ndir == 1 || ndir == 2, "gru_seq: ndir must be 1 or 2");
     const int ldw = H + Din, N = ndir * 3 * H, BL = B * Lmax;
@@ -914,21 +914,52 @@ int gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, in
     { const char* e = getenv("S2S_GRU_DBG"); p.dbg = e ? atoi(e) : 0; }
     if (H == 128) S2S_TRY(launch_cluster<128>(ctx, true, p));
     else S2S_TRY(launch_cluster<256>(ctx, true, p));
-    // time-batched gradients (K = B*L) instead of one rank-1 update per frame (LinearZeroBias.lua:67-74)
-    const int sk = 8;
-    TcCacheScope tc_scope(ctx);        // dA^T is prepared once by the x-column product and reused by the h-column blocks
-    // x columns of all gates, both directions:  dW[:, H:] += dA^T X
-    S2S_TRY(gemm_f32(ctx, true, false, N, Din, BL, 1.f, dA, N, x, ldx, 1.f, dW + H, ldw, nullptr, GemmBatch(), sk));
-    for (int d = 0; d < ndir; d++) {
-        float* dWd = dW + (size_t)d * 3 * H * ldw;
-        // z, r gates see h_prev; the candidate sees r*h_prev (GRU.lua:23-26)
-        S2S_TRY(gemm_f32(ctx, true, false, 2 * H, H, BL, 1.f, dA + (size_t)d * 3 * H, N, hp_all + (size_t)d * H, ndir * H, 1.f, dWd, ldw,
-                         nullptr, GemmBatch(), sk));
-        S2S_TRY(gemm_f32(ctx, true, false, H, H, BL, 1.f, dA + (size_t)d * 3 * H + 2 * H, N, save + (size_t)d * 4 * H + 3 * H, ndir * 4 * H, 1.f,
-                         dWd + (size_t)2 * H * ldw, ldw, nullptr, GemmBatch(), sk));
-    }
-    // dX = dA . W[:, H:]   (LinearZeroBias.lua:50-65, x columns), both directions summed as nngraph does
+    // dX = dA . W[:, H:]   (LinearZeroBias.lua:50-65, x columns), both directions summed as nngraph does: the next layer's recurrence
+    // waits for it, so it goes first
     if (dx) S2S_TRY(gemm_f32(ctx, false, false, BL, Din, N, 1.f, dA, N, W + H, ldw, 0.f, dx, Din));
+    // time-batched weight gradients (K = B*L) instead of one rank-1 update per frame (LinearZeroBias.lua:67-74).  Nothing downstream
+    // reads them before the gradient step: with defer_wgrad they run on a low-priority side stream with a persistent grid limited
+    // to the SMs the cluster kernels leave idle, under the NEXT layer's recurrence (S2S_OVERLAP=1).
+    static int overlap = -1;
+    if (overlap < 0) { const char* e = getenv("S2S_OVERLAP"); overlap = e ? atoi(e) : 1; }
+    const bool fork = defer_wgrad && overlap && ctx->side[1] && ctx->stream != ctx->side[1];
+    cudaStream_t main_stream = ctx->stream;
+    if (fork) {
+        S2S_CUDA(cudaEventRecord(ctx->ev[2], main_stream));
+        S2S_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev[2], 0));
+        ctx->stream = ctx->side[1];
+        ctx->gemm_sm_limit = ctx->sm_count - 112 > 16 ? ctx->sm_count - 112 : 0;
+    }
+    int rc = 0;
+    {
+        const int sk = 8;
+        TcCacheScope tc_scope(ctx);        // dA^T is prepared once by the x-column product and reused by the h-column blocks
+        // x columns of all gates, both directions:  dW[:, H:] += dA^T X
+        rc = gemm_f32(ctx, true, false, N, Din, BL, 1.f, dA, N, x, ldx, 1.f, dW + H, ldw, nullptr, GemmBatch(), sk);
+        for (int d = 0; d < ndir && !rc; d++) {
+            float* dWd = dW + (size_t)d * 3 * H * ldw;
+            // z, r gates see h_prev; the candidate sees r*h_prev (GRU.lua:23-26)
+            rc = gemm_f32(ctx, true, false, 2 * H, H, BL, 1.f, dA + (size_t)d * 3 * H, N, hp_all + (size_t)d * H, ndir * H, 1.f, dWd, ldw,
+                          nullptr, GemmBatch(), sk);
+            if (!rc)
+                rc = gemm_f32(ctx, true, false, H, H, BL, 1.f, dA + (size_t)d * 3 * H + 2 * H, N, save + (size_t)d * 4 * H + 3 * H, ndir * 4 * H, 1.f,
+                              dWd + (size_t)2 * H * ldw, ldw, nullptr, GemmBatch(), sk);
+        }
+    }
+    if (fork) {
+        ctx->stream = main_stream;
+        ctx->gemm_sm_limit = 0;
+        S2S_CUDA(cudaEventRecord(ctx->ev[3], ctx->side[1]));
+        ctx->wgrad_join_pending = true;
+    }
+    return rc;
+}
+
+int gru_seq_wgrad_join(s2s_ctx* ctx) {
+    if (ctx->wgrad_join_pending) {
+        S2S_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev[3], 0));
+        ctx->wgrad_join_pending = false;
+    }
     return 0;
 }
 

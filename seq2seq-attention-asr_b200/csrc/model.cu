@@ -89,9 +89,10 @@ int model_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, cons
         if (l > 0) S2S_ALLOC(dprev, ctx->arena, float, (size_t)B * Lmax * A);
         else dprev = dX;
         S2S_TRY(gru_seq_backward(ctx, P + Y.enc[l][0][0].off, G + Y.enc[l][0][0].off, din, H, 2, 0, m.acts[l], din, lengths, B, Lmax,
-                                 m.acts[l + 1], m.saves[l], dcur, dprev));
+                                 m.acts[l + 1], m.saves[l], dcur, dprev, /*defer_wgrad=*/l > 0));
         dcur = dprev;
     }
+    S2S_TRY(gru_seq_wgrad_join(ctx));
     return 0;
 }
 
