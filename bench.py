@@ -12,11 +12,13 @@ gradient over NCCL] -> /B, clip, adadelta, row-norm constraint (timit/timit.lua:
   value   : frames/s with inputs resident in HBM (CUDA events on the launching stream, per-step events,
             L2 flushed between steps by a 256 MiB write outside the event pairs; max over ranks)
   e2e     : the same metric through the public host API with HOST buffers (pinned): H2D of the
-            batch and D2H of the per-utterance NLL inside the timed region
+            batch and D2H of the per-utterance NLL inside the timed region, as a training loop's input
+            pipeline (the next step's copies on a copy stream, the result read one step late)
   roofline: the kernel class with the largest share of the step, timed live with CUDA events by the
             library's profiling hook on an instrumented extra pass (s2s_ctx_profile)
   cpu_baseline: the CPU oracle (a C restatement of the reference; Torch7 cannot run here) on a
             bounded sample of the same workload, all host threads
+`--config cfg2loc` switches the location-aware term on (hybridAttendFeatureMaps = 16, filter 10: off in the shipped model);
 `--config cfg3` / `--config cfg4` run the other training configurations of BASELINE.json (dropout + AdaptiveWeightNoise;
 librispeech/model_vgg.lua with its VGG front-end) with the same contract; the driver's default is cfg2.
 `--impl reference` times that CPU oracle alone (the reference's own implementation is Lua/Torch7 and
