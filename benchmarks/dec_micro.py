@@ -12,7 +12,7 @@ n = s2s.param_count(cfg)
 g = torch.Generator(device="cuda").manual_seed(0)
 P = (torch.rand(n, device="cuda", generator=g) - 0.5) * 0.1
 h = torch.randn(B, L, 512, device="cuda", generator=g) * 0.5
-y = torch.randint(0, 61, (B, T), device="cuda", dtype=torch.int32)
+y = torch.randint(0, 61, (B, T), device="cuda", dtype=torch.int32, generator=g)   # seeded: runs of the two paths are comparable
 G = torch.zeros_like(P); dlogp = torch.randn(B, T, 62, device="cuda", generator=g)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 tf = tb = 0.0

@@ -69,6 +69,17 @@ const char* s2s_last_error(void);
 int  s2s_version(void);
 /* number of kernels launched by this context since creation (bench.py `gpu_launches`) */
 int64_t s2s_ctx_launch_count(s2s_ctx* ctx);
+/* launches per kernel class since creation: lets tests and the bench assert WHICH path ran (tcgen05 vs SIMT GEMM,
+ * persistent cluster loops vs per-step chains); replayed CUDA graphs add the counts recorded at capture */
+#define S2S_KC_GEMM_TC          0   /* gemm_tc_kernel (tcgen05 / TMEM / TMA)                          */
+#define S2S_KC_GEMM_SIMT        1   /* gemm_simt_kernel (exact fp32)                                   */
+#define S2S_KC_GRU_CLUSTER      2   /* persistent GRU recurrence (one launch per layer and pass)       */
+#define S2S_KC_DEC_CLUSTER_FWD  3   /* decoder time loop as one cluster kernel                         */
+#define S2S_KC_DEC_CLUSTER_BWD  4   /* decoder backward time loop as one cluster kernel                */
+#define S2S_KC_ATTN_STEP        5   /* per-step attention kernels (attn_fwd_kernel / attn_bwd_kernel)  */
+#define S2S_KC_LSTM_CLUSTER     6   /* persistent LSTM recurrence                                       */
+#define S2S_KC_N                7
+int64_t s2s_ctx_kernel_count(s2s_ctx* ctx, int kernel_class);
 /* enable (1) / disable (0) CUDA-graph replay of s2s_model_fwdbwd for repeated shapes */
 int  s2s_ctx_set_graphs(s2s_ctx* ctx, int enable);
 /* Caller-defined graphs: every library call on this context between _begin and _end is captured (not executed) and

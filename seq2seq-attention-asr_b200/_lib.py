@@ -66,6 +66,7 @@ def load():
         "s2s_last_error": (C.c_char_p, []),
         "s2s_version": (i32, []),
         "s2s_ctx_launch_count": (i64, [vp]),
+        "s2s_ctx_kernel_count": (i64, [vp, i32]),
         "s2s_ctx_set_graphs": (i32, [vp, i32]),
         "s2s_ctx_profile": (i32, [vp, i32]),
         "s2s_ctx_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(f64)]),

@@ -207,6 +207,8 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
         // capture on the internal stream
         ctx->arena.frozen = true; ctx->persist.frozen = true;         // a cudaMalloc inside a capture is an error
         const int64_t l0 = ctx->launches;
+        int64_t k0[S2S_KC_N];
+        for (int i = 0; i < S2S_KC_N; i++) k0[i] = ctx->kcount[i];
         cudaGraph_t graph = nullptr;
         ctx->stream = side;
         cudaError_t e = cudaStreamBeginCapture(side, cudaStreamCaptureModeThreadLocal);
@@ -218,6 +220,7 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
         ctx->stream = user;
         ctx->graph.launches = ctx->launches - l0;
         ctx->launches = l0;
+        for (int i = 0; i < S2S_KC_N; i++) { ctx->graph.kc[i] = ctx->kcount[i] - k0[i]; ctx->kcount[i] = k0[i]; }
         if (rc != 0 || e != cudaSuccess || !graph) {
             std::string why = rc != 0 ? last_error() : std::string(cudaGetErrorString(e));
             if (graph) cudaGraphDestroy(graph);
@@ -239,6 +242,7 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
     S2S_CUDA(cudaEventRecord(ctx->ev[1], side));
     S2S_CUDA(cudaStreamWaitEvent(user, ctx->ev[1], 0));
     ctx->launches += ctx->graph.launches;
+    for (int i = 0; i < S2S_KC_N; i++) ctx->kcount[i] += ctx->graph.kc[i];
     // forward state recorded by the capture pass stays valid: same shapes, same arena pointers
     return 0;
 }
@@ -253,6 +257,7 @@ int s2s_graph_begin(s2s_ctx* ctx) {
     if (ctx->graph.exec) graph_drop(ctx);
     ctx->capture_user_stream = ctx->stream;
     ctx->capture_l0 = ctx->launches;
+    ctx->capture_k0.assign(ctx->kcount, ctx->kcount + S2S_KC_N);
     ctx->arena.frozen = true; ctx->persist.frozen = true;
     cudaError_t e = cudaStreamBeginCapture(ctx->side[0], cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { graph_drop(ctx); return fail("graph_begin: cudaStreamBeginCapture: %s", cudaGetErrorString(e)); }
@@ -268,12 +273,15 @@ int s2s_graph_end(s2s_ctx* ctx, int* graph_id) {
     ctx->capturing = false;
     const int64_t n = ctx->launches - ctx->capture_l0;
     ctx->launches = ctx->capture_l0;
+    std::vector<int64_t> kc(S2S_KC_N, 0);
+    for (int i = 0; i < S2S_KC_N && i < (int)ctx->capture_k0.size(); i++) { kc[i] = ctx->kcount[i] - ctx->capture_k0[i]; ctx->kcount[i] = ctx->capture_k0[i]; }
     cudaGraphExec_t exec = nullptr;
     if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
     if (e != cudaSuccess || !exec) { cudaGetLastError(); graph_drop(ctx); return fail("graph_end: capture failed: %s", cudaGetErrorString(e)); }
     ctx->user_graphs.push_back(exec);
     ctx->user_graph_launches.push_back(n);
+    ctx->user_graph_kc.push_back(kc);
     *graph_id = (int)ctx->user_graphs.size() - 1;
     return 0;
 }
@@ -287,6 +295,7 @@ int s2s_graph_launch(s2s_ctx* ctx, int graph_id) {
     S2S_CUDA(cudaEventRecord(ctx->ev[1], side));
     S2S_CUDA(cudaStreamWaitEvent(user, ctx->ev[1], 0));
     ctx->launches += ctx->user_graph_launches[graph_id];
+    for (int i = 0; i < S2S_KC_N; i++) ctx->kcount[i] += ctx->user_graph_kc[graph_id][i];
     return 0;
 }
 int s2s_graph_destroy(s2s_ctx* ctx, int graph_id) {

@@ -794,6 +794,7 @@ static int launch_fwd_rif(s2s_ctx* ctx, const AttnFwdParams& p, int KF) {
         const double S = NS * 128.0, A = NA * 128.0, L = p.Lmax;
         prof_end(ctx, S2S_PROF_ATTN_FWD, 4.0 * p.B * (L * S + L * A + 2 * L + S + A));
     }
+    ctx->kcount[S2S_KC_ATTN_STEP]++;
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -822,6 +823,7 @@ static int launch_bwd(s2s_ctx* ctx, const AttnBwdParams& p, int KF) {
         const double S = NS * 128.0, A = NA * 128.0, L = p.Lmax;
         prof_end(ctx, S2S_PROF_ATTN_BWD, 4.0 * p.B * (L * S + L * A + 6 * L + 2 * S + 2 * A));
     }
+    ctx->kcount[S2S_KC_ATTN_STEP]++;
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }

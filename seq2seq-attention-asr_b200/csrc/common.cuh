@@ -68,6 +68,7 @@ struct GraphCache {
     bool nocapture = false;        // capture failed once for this key: stay eager
     cudaGraphExec_t exec = nullptr;
     int64_t launches = 0;          // kernel launches recorded in the graph
+    int64_t kc[S2S_KC_N] = {0};    // per-class launch counts recorded in the graph
 };
 
 // prepared (hi/lo-split, K-contiguous) GEMM operands that stay valid for the duration of a TcCacheScope (gemm_tc.cu)
@@ -87,6 +88,7 @@ struct s2s_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     int64_t launches = 0;
+    int64_t kcount[S2S_KC_N] = {0};   // launches per kernel class (s2s_ctx_kernel_count): which path ran is testable
     bool graphs = true;
     bool pdl = false;          // programmatic dependent launch for the decoder's per-step kernel chain (S2S_PDL=1 enables;
                                // measured neutral-to-negative under CUDA-graph replay, so off by default)
@@ -102,9 +104,11 @@ struct s2s_ctx {
     // caller-defined graphs (s2s_graph_begin / _end / _launch): sequences of library calls captured once and replayed
     std::vector<cudaGraphExec_t> user_graphs;
     std::vector<int64_t> user_graph_launches;
+    std::vector<std::vector<int64_t>> user_graph_kc;
     bool capturing = false;
     cudaStream_t capture_user_stream = nullptr;
     int64_t capture_l0 = 0;
+    std::vector<int64_t> capture_k0;
     bool tc_cache_on = false;
     std::vector<s2s::TcCacheEntry> tc_cache;
     // weight-gradient GEMMs of one encoder layer overlapped with the next layer's recurrence (S2S_OVERLAP=1): they run on side[1]

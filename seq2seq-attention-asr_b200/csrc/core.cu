@@ -234,6 +234,7 @@ int s2s_ctx_synchronize(s2s_ctx* ctx) {
     return 0;
 }
 int64_t s2s_ctx_launch_count(s2s_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t s2s_ctx_kernel_count(s2s_ctx* ctx, int k) { return (ctx && k >= 0 && k < S2S_KC_N) ? ctx->kcount[k] : -1; }
 int s2s_ctx_set_graphs(s2s_ctx* ctx, int enable) {
     S2S_REQUIRE(ctx, "ctx is NULL");
     ctx->graphs = enable != 0;

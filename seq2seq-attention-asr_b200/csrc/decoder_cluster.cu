@@ -986,6 +986,7 @@ static int dc_launch(s2s_ctx* ctx, const DecClusterParams& p, int* max_clusters)
         return 0;
     }
     S2S_CUDA(cudaLaunchKernelEx(&cfg, dec_cluster_fwd_kernel<BG, LOC>, p));
+    ctx->kcount[S2S_KC_DEC_CLUSTER_FWD]++;
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1078,6 +1079,7 @@ static int dcb_launch(s2s_ctx* ctx, const DecClusterBwdParams& p, int* max_clust
         return 0;
     }
     S2S_CUDA(cudaLaunchKernelEx(&cfg, dec_cluster_bwd_kernel<BG>, p));
+    ctx->kcount[S2S_KC_DEC_CLUSTER_BWD]++;
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }

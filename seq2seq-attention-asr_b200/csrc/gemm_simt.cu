@@ -173,6 +173,7 @@ int gemm_f32(s2s_ctx* ctx, bool tA, bool tB, int M, int N, int K, float alpha, c
                                                                      batch.sA, batch.sB, batch.sC, relu ? -1 : splitk);
     }
     prof_end(ctx, S2S_PROF_GEMM, 2.0 * M * N * (double)K * batch.count);
+    ctx->kcount[S2S_KC_GEMM_SIMT]++;
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -499,6 +499,7 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
     else if (BN == 128) gemm_tc_kernel<128><<<sc.G, THREADS, smem_bytes(128), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
     else gemm_tc_kernel<256><<<sc.G, THREADS, smem_bytes(256), ctx->stream>>>(mAh, mAl, mBh, mBl, sc, M, N, alpha, beta, C, ldc, bias);
     prof_end(ctx, S2S_PROF_GEMM, 2.0 * M * N * (double)K);
+    ctx->kcount[S2S_KC_GEMM_TC]++;
     S2S_LAUNCH_CHECK(ctx);
     if (dbg_mode == 9) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream);

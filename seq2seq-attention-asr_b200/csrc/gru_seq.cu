@@ -826,6 +826,7 @@ static int launch_cluster_geo(s2s_ctx* ctx, bool backward, const GruSeqParams& p
         const double per = backward ? 9.0 * H : 8.0 * H;
         prof_end(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD, 4.0 * p.B * p.Lmax * p.ndir * per);
     }
+    ctx->kcount[S2S_KC_GRU_CLUSTER]++;
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -305,6 +305,7 @@ static int lc_launch(s2s_ctx* ctx, bool backward, const LstmClusterParams& p, in
     prof_begin(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD);      // reported with the recurrence classes
     if (backward) S2S_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_bwd_kernel<H, BG>, p));
     else S2S_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_fwd_kernel<H, BG>, p));
+    ctx->kcount[S2S_KC_LSTM_CLUSTER]++;
     // algorithmic bytes: fwd reads xp (4H), writes y, c (2H) and the gates (4H); bwd reads gates, c, c_prev, dy (7H), writes dA (4H)
     prof_end(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD, 4.0 * p.B * p.Lmax * (backward ? 11.0 : 10.0) * H);
     S2S_LAUNCH_CHECK(ctx);

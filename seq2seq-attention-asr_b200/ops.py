@@ -68,6 +68,12 @@ class Context:
     def launches(self):
         return int(self.lib.s2s_ctx_launch_count(self.h))
 
+    KERNEL_CLASSES = ("gemm_tc", "gemm_simt", "gru_cluster", "dec_cluster_fwd", "dec_cluster_bwd", "attn_step", "lstm_cluster")
+
+    def kernel_counts(self):
+        """{kernel class: launches since creation} -- which path ran (tcgen05 vs SIMT GEMM, cluster loops vs per-step chains)"""
+        return {k: int(self.lib.s2s_ctx_kernel_count(self.h, i)) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     def set_graphs(self, enable):
         check(self.lib.s2s_ctx_set_graphs(self.h, int(bool(enable))))
 
