@@ -197,6 +197,8 @@ def run_cfg4(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = s2s.Context(local)
+    if world > 1:
+        s2s.dp.init(ctx, rank, world)             # the C ABI's NCCL plane (csrc/dp_nccl.cu)
     B, Tin, F, Tdec, V = 8, 1600, 40, 250, 29
     vcfg = s2s.VGG_LIBRISPEECH
     dcfg = dict(D=F, H=vcfg["OUT"] // 2, NL=0, S=512, ST=256, V=V, K=0, KF=10, M=64, MW=7, MLP=2)   # model_vgg.lua:57-69
@@ -229,7 +231,8 @@ def run_cfg4(args):
             ctx.graph_launch(graph["id"])        # the whole forward + backward as one replayed CUDA graph
         else:
             fwdbwd(Xd, yd)
-        s2s.dp.allreduce_gradients(G)
+        if world > 1:
+            s2s.dp.allreduce(ctx, G)
         s2s.grad_finalize(ctx, G, P, B * world, 1e20, want_norm=False)
         s2s.adadelta(ctx, P, G, vs, as_)
         s2s.model_rownorm_constraint(ctx, dcfg, Pd, 1.0)
@@ -354,6 +357,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dbg("process group up")
     ctx = s2s.Context(local)
+    # the data path's collective is the C ABI's own NCCL plane (csrc/dp_nccl.cu); torch.distributed only ships the 128-byte id
+    # and carries the barrier / max-over-ranks of the timing
+    dp_overlap = not os.environ.get("S2S_BENCH_DP_PLAIN")
+    if world > 1:
+        s2s.dp.init(ctx, rank, world, overlap=dp_overlap)
     B = B_PER_GPU
     n = s2s.param_count(CFG)
 
@@ -383,7 +391,8 @@ def run_ours(args):
         s2s.dropout_mask(ctx, mask.shape, 0.5, seed=seed, out=mask)   # nn.Dropout on {s,c}  (model_chorowski_baseline_dropout.lua:56)
         G.zero_()
         s2s.model_fwdbwd(ctx, CFG, Pn, G, Xd, yd, lengths=lnd, tlens=tld, dropmask=mask, flags=s2s.NORMALIZE_NLL, nll=nll)
-        s2s.dp.allreduce_gradients(G)
+        if world > 1 and not dp_overlap:
+            s2s.dp.allreduce(ctx, G)
         s2s.grad_finalize(ctx, G, Pn, B * world, 1e20, want_norm=False)
         s2s.awn_accgrad(ctx, W2, G, 1.0, out=gW2)                     # AWN:backward(nll, gradients)    (timit.lua:318-327)
         s2s.adadelta(ctx, W2, gW2, v2, a2)                            # optimMethod(optimfunc, adaparameters, ...)  (:336)
@@ -395,7 +404,8 @@ def run_ours(args):
             return step_cfg3(Xd, yd, lnd, tld)
         G.zero_()                                                     # zeroGradParameters (timit.lua:233)
         s2s.model_fwdbwd(ctx, CFG, P, G, Xd, yd, lengths=lnd, tlens=tld, flags=s2s.NORMALIZE_NLL, nll=nll)
-        s2s.dp.allreduce_gradients(G)                                 # data-parallel gradient sum over NVLink (no-op at N = 1)
+        if world > 1 and not dp_overlap:                              # (with overlap the library reduced the buckets under the backward pass)
+            s2s.dp.allreduce(ctx, G)                                  # data-parallel gradient sum over NVLink: s2s_dp_allreduce
         s2s.dp.gradient_step(ctx, s2s, CFG, P, G, v_state, a_state, B * world)   # /B, clip, adadelta, row-norm (timit.lua:292-348)
         return nll
 

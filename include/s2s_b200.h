@@ -107,6 +107,27 @@ int  s2s_graph_destroy(s2s_ctx* ctx, int graph_id);
 int  s2s_ctx_profile(s2s_ctx* ctx, int enable);
 int  s2s_ctx_profile_read(s2s_ctx* ctx, double* ms_host, int64_t* count_host, double* work_host);
 
+/* ---- data-parallel plane: NCCL over NVLink 5 / NVSwitch (no counterpart in the reference: single device, timit/timit.lua:39) ----
+ * Only the minibatch shards (timit/timit.lua:240-295 sums per-utterance gradients): every rank holds the full parameters and
+ * optimiser state, runs s2s_model_fwdbwd on its shard, the flat gradient is summed over the ranks, and the gradient step
+ * (s2s_grad_finalize with the GLOBAL batch size, s2s_adadelta, s2s_model_rownorm_constraint; timit.lua:291-348) is replicated.
+ * libnccl.so.2 is opened at run time ($S2S_NCCL_LIB overrides the search); hosts that never call these need no NCCL.
+ *   rank 0: s2s_dp_unique_id(id)  ->  the host ships the 128 bytes to every rank  ->  all ranks: s2s_dp_init(ctx, rank, world, id)   */
+int  s2s_dp_available(void);                                           /* 1 when libnccl could be opened */
+int  s2s_dp_unique_id(void* id_host_128);                              /* ncclGetUniqueId: 128 bytes, host memory */
+int  s2s_dp_init(s2s_ctx* ctx, int rank, int world, const void* id_host_128);
+int  s2s_dp_rank(s2s_ctx* ctx);
+int  s2s_dp_world(s2s_ctx* ctx);
+/* G[0, n) := sum over ranks, in place, on the context's stream ("gradients" of timit.lua:229 before :292-295).  No-op for world 1. */
+int  s2s_dp_allreduce(s2s_ctx* ctx, float* G, int64_t n);
+/* P[0, n) := rank `root`'s copy (initial parameter synchronisation) */
+int  s2s_dp_broadcast(s2s_ctx* ctx, float* P, int64_t n, int root);
+/* enable != 0: s2s_model_fwdbwd itself sums G over the ranks, bucket by bucket (decoder, then each encoder layer) on a low-priority
+ * side stream under the remaining backward pass; on return (in stream order) G is the global gradient sum and s2s_dp_allreduce must
+ * not be called again for it. */
+int  s2s_dp_set_overlap(s2s_ctx* ctx, int enable);
+int  s2s_dp_destroy(s2s_ctx* ctx);
+
 /* ---- flat parameter layout (what module:getParameters() flattens to; timit/timit.lua:172) -- */
 int64_t s2s_param_count(const s2s_model_cfg* cfg);
 /* writes (offset, rows, cols) triples in flat order into out_host[3*max]; returns the count */

@@ -70,6 +70,15 @@ def load():
         "s2s_ctx_set_graphs": (i32, [vp, i32]),
         "s2s_ctx_profile": (i32, [vp, i32]),
         "s2s_ctx_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(f64)]),
+        "s2s_dp_available": (i32, []),
+        "s2s_dp_unique_id": (i32, [vp]),
+        "s2s_dp_init": (i32, [vp, i32, i32, vp]),
+        "s2s_dp_rank": (i32, [vp]),
+        "s2s_dp_world": (i32, [vp]),
+        "s2s_dp_allreduce": (i32, [vp, vp, i64]),
+        "s2s_dp_broadcast": (i32, [vp, vp, i64, i32]),
+        "s2s_dp_set_overlap": (i32, [vp, i32]),
+        "s2s_dp_destroy": (i32, [vp]),
         "s2s_param_count": (i64, [cfgp]),
         "s2s_param_segments": (i32, [cfgp, vp, i32]),
         "s2s_decoder_param_offset": (i64, [cfgp]),

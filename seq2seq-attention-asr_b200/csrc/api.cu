@@ -47,6 +47,7 @@ int s2s_ctx_destroy(s2s_ctx* ctx) {
     for (int i = 0; i < 2; i++) if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    dp_state_free(ctx);
     delete ctx->dec;
     delete ctx->model;
     vgg_state_free(ctx);

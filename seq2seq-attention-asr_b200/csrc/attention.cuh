@@ -52,4 +52,9 @@ int attn_step_bwd(s2s_ctx* ctx, const AttnScratch& sc, const float* Vh, const fl
 int attn_dvh(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* de_all, const float* w, const int* lengths,
              const int* tlens, int B, int Lmax, int T, int S, const AttnLoc& loc_all, float* dVh, float* dwe, float* duw);
 
+// location path, all decoder steps at once: V1[b,t,l,j] = sum_s UW[j,s] w_s (1 - tanh^2 Z_t[l,s])  (t >= 1; row t = 0 is not written).
+// The alignment carry of the backward time loop is dalpha_{t-1}[i] = sum_j de_t[x] V1[t,x,j], x = i - j + pad_left.
+int attn_v1(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* w, const float* uw, const float* alpha_all, const int* lengths,
+            const int* tlens, int B, int Lmax, int T, int S, int KF, int padl, float* V1);
+
 }  // namespace s2s

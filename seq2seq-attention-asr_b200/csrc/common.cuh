@@ -77,6 +77,7 @@ struct TcCacheEntry { const float* src; int K, cols, ld; bool transposed; const 
 struct DecoderState;   // decoder.cu
 struct VggState;       // vgg.cu
 struct ModelState;     // model.cu
+struct DpState;        // dp_nccl.cu
 
 }  // namespace s2s
 
@@ -97,6 +98,8 @@ struct s2s_ctx {
     s2s::DecoderState* dec = nullptr;
     s2s::ModelState* model = nullptr;
     s2s::VggState* vgg = nullptr;
+    s2s::DpState* dp = nullptr;     // NCCL communicator of the data-parallel plane (s2s_dp_init)
+    bool dp_overlap = false;        // s2s_model_fwdbwd reduces the gradient buckets itself, under the remaining backward pass
     unsigned* counters = nullptr;   // zero-initialised device counters for last-block-done patterns
     uint64_t rng_calls = 0;
     s2s::Prof prof;
@@ -173,6 +176,12 @@ struct TcCacheScope {
 int colsum_add(s2s_ctx* ctx, const float* X, int64_t M, int N, int ldx, float* out);
 int transpose_f32(s2s_ctx* ctx, const float* in, int rows, int cols, int ld_in, float* out, int ld_out);   // out[c][r] = in[r][c]
 int fill_f32(s2s_ctx* ctx, float* p, int64_t n, float v);
+
+// data-parallel plane (dp_nccl.cu)
+void dp_state_free(s2s_ctx* ctx);
+int dp_allreduce_bucket(s2s_ctx* ctx, float* G, int64_t n, bool on_side_stream);   // sum over ranks, in place; no-op without a communicator
+int dp_join(s2s_ctx* ctx);                                                          // context stream waits for the side-stream buckets
+int dp_world(const s2s_ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

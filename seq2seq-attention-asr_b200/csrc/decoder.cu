@@ -786,8 +786,17 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST, lddA = (int64_t)T * 3 * ST;
     const int eb = ceil_div(B * ST, 256);
     bool clustered = false;      // the whole loop in one persistent cluster kernel (decoder_cluster.cu) when the shapes allow
-    if (!carry_alpha)
-        S2S_TRY(decoder_cluster_backward(ctx, Y, P, h, lengths, B, Lmax, T, lambda, d, WsT, GhT, GzrT, WjcT, dsc, dA, du_all, dc_all, dq_all, de_all, &clustered));
+    if (decoder_cluster_backward_eligible(Y, Lmax, lambda)) {
+        float* V1 = nullptr;
+        if (KF > 0) {
+            // location path: the Jacobian of the energies w.r.t. alpha_{t-1} does not depend on any gradient -> one throughput-bound launch
+            // over all steps before the latency-bound loop (rows t = 0 and padded steps stay zero: they only ever multiply de = 0)
+            S2S_ALLOC(V1, ar, float, BT * Lmax * KF);
+            S2S_CUDA(cudaMemsetAsync(V1, 0, BT * Lmax * KF * sizeof(float), st));
+            S2S_TRY(attn_v1(ctx, d.Vh, d.q, P + Y.we.off, d.uw, d.alpha, lengths, tlens, B, Lmax, T, S, KF, padl, V1));
+        }
+        S2S_TRY(decoder_cluster_backward(ctx, Y, P, h, lengths, B, Lmax, T, lambda, d, WsT, GhT, GzrT, WjcT, dsc, V1, dA, du_all, dc_all, dq_all, de_all, &clustered));
+    }
     // elementwise GRU backward of the LAST step (ds_carry = 0); later steps get it fused into the W_s product
     if (!clustered) gru_bwd_e1_kernel<<<eb, 256, 0, st>>>(dsc + (size_t)(T - 1) * (ST + A), ldsc, ds_carry, d.gates + (size_t)(T - 1) * 3 * ST, ldg,
                                            d.su + (size_t)(T - 1) * 2 * ST, ldsu, B, ST, dA + (size_t)(T - 1) * 3 * ST, lddA, dsu);

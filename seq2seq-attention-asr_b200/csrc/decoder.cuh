@@ -47,6 +47,6 @@ int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const
 bool decoder_cluster_backward_eligible(const Layout& Y, int Lmax, float lambda);
 int decoder_cluster_backward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, int T, float lambda,
                              const DecoderState& d, const float* WsT, const float* GhT, const float* GzrT, const float* WjcT, const float* dsc,
-                             float* dA, float* du_all, float* dc_all, float* dq_all, float* de_all, bool* handled);
+                             const float* V1, float* dA, float* du_all, float* dc_all, float* dq_all, float* de_all, bool* handled);
 
 }  // namespace s2s

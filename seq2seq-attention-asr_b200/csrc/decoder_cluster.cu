@@ -563,9 +563,14 @@ struct DecClusterBwdParams {
     int B, Lmax, T;
     float *dA, *du_all, *dc_all, *dq_all, *de_all;
     long long* clk;
+    // alignment carry d alpha_{t-1} (RNNAttention.lua:246 through Attention.lua:86-99 and MonotonicAlignment.lua:49-75): location term
+    // (folded weights U W_F [KF][S], left padding, the hoisted Jacobian V1 [B,T,Lmax,KF] of attn_v1) and / or the monotonicity penalty
+    const float *uw, *V1, *pen;
+    int KF, padl, carry;
+    float lambda;
 };
 
-template <int BG>
+template <int BG, int LOC = 0>
 struct DcBwdSmem {
     float wb[64 * 32 * 4];         // phase B rows: G_h^T   [own 16 | ST + own 16] x K = ST,   k-major
     float wc[128 * 32 * 4];        // phase C rows: G_zr^T  [own 16 | ST + own 16] x K = 2 ST
@@ -585,10 +590,14 @@ struct DcBwdSmem {
     float w_s[DC_S];
     float stage[BG][32], stage2[BG][32];
     float carry_s[BG][16], duh_s[BG][16];
-    int l0_s[BG], nr_s[BG];
+    int l0_s[BG], nr_s[BG], len_s[BG];
     int frow[BG * DC_RMAX];
     short fb[BG * DC_RMAX], fr[BG * DC_RMAX];
     uint64_t bar[7];
+    float cin_s[BG][DC_RMAX];      // carry into d alpha_t of this CTA's frames: penalty of step t, penalty and location term of step t+1
+    float pg_s[2][BG];             // lambda where the penalty of step t (slot t & 1) is active
+    float uw_s[LOC ? DC_KFMAX * DC_S : 4];             // 2 log2(e) U W_F
+    float apw_s[LOC ? BG : 1][DC_RMAX + 32];           // alpha_{t-1} over this CTA's frames plus the filter halo
 };
 enum { BB_X1 = 0, BB_X2, BB_X3, BB_X4, BB_X5, BB_X6A, BB_X6B };
 
@@ -628,11 +637,11 @@ __device__ __forceinline__ float4 dc_dtanh4(const float4 v, const float4 qk) {
     return make_float4(fmaf(-r0, r0, r0), fmaf(-r1, r1, r1), fmaf(-r2, r2, r2), fmaf(-r3, r3, r3));
 }
 
-template <int BG>
+template <int BG, int LOC>
 __global__ void __launch_bounds__(DC_THREADS, 1)
 dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
     extern __shared__ __align__(128) unsigned char dc_smem_raw[];
-    DcBwdSmem<BG>& sm = *reinterpret_cast<DcBwdSmem<BG>*>(dc_smem_raw);
+    DcBwdSmem<BG, LOC>& sm = *reinterpret_cast<DcBwdSmem<BG, LOC>*>(dc_smem_raw);
     constexpr int ST = DC_ST, A = DC_A, S = DC_S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned crank = cg::this_cluster().block_rank();
@@ -655,12 +664,17 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
     for (int i = tid; i < BG * S; i += DC_THREADS) (&sm.dq_full[0][0])[i] = 0.f;          // dq_T = 0
     for (int i = tid; i < BG * 16; i += DC_THREADS) (&sm.carry_s[0][0])[i] = 0.f;         // Recurrent.lua:134
     for (int i = tid; i < BG * (DC_RMAX + 16); i += DC_THREADS) (&sm.de_s[0][0])[i] = 0.f;
+    for (int i = tid; i < BG * DC_RMAX; i += DC_THREADS) (&sm.cin_s[0][0])[i] = 0.f;
+    if constexpr (LOC != 0) {
+        for (int i = tid; i < DC_KFMAX * S; i += DC_THREADS) sm.uw_s[i] = i < p.KF * S ? DC_K * p.uw[i] : 0.f;     // taps past KF: zero weights
+    }
     if (tid < BG) {
         const int b = b0 + tid;
         const int Lb = b < p.B ? (p.lengths ? p.lengths[b] : Lmax) : 0;
         const int Rb = (Lb + DC_CS - 1) / DC_CS;
         const int l0 = (int)crank * Rb;
-        sm.l0_s[tid] = l0; sm.nr_s[tid] = max(0, min(Rb, Lb - l0));
+        sm.l0_s[tid] = l0; sm.nr_s[tid] = max(0, min(Rb, Lb - l0)); sm.len_s[tid] = Lb;
+        sm.pg_s[0][tid] = 0.f; sm.pg_s[1][tid] = 0.f;
     }
     if (tid == 0) {
         for (int i = 0; i < 7; i++) mbar_init(&sm.bar[i], 1);
@@ -726,6 +740,8 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
             mbar_expect_tx(&sm.bar[BB_X4], TX_512); mbar_expect_tx(&sm.bar[BB_X5], TX_DOT); mbar_expect_tx(&sm.bar[BB_X6A], TX_DQ);
             mbar_expect_tx(&sm.bar[BB_X6B], TX_512);
         }
+        if (p.carry && tid < BG)     // MonotonicAlignment.lua:49-75: the penalty of step t feeds d alpha_t (+) and d alpha_{t-1} (-) where it is active
+            sm.pg_s[t & 1][tid] = (p.lambda != 0.f && b0 + tid < p.B && __ldg(p.pen + (size_t)(b0 + tid) * T + t) > 0.f) ? p.lambda : 0.f;
 
         // ---- A: ds_t, elementwise GRU backward ----------------------------------------------------------------------------------
         {
@@ -763,6 +779,36 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
         for (int i = tid; i < BG * DC_RMAX; i += DC_THREADS) {
             const int b = i / DC_RMAX, r = i % DC_RMAX;
             sm.al_s[b][r] = r < sm.nr_s[b] ? __ldg(p.alpha + ((size_t)(b0 + b) * T + t) * Lmax + sm.l0_s[b] + r) : 0.f;
+        }
+        if (p.carry) {
+            // d alpha_t of this CTA's frames from outside the context path: + g_t (penalty of step t), and from step t+1: - g_{t+1} and
+            // the location term sum_j de_{t+1}[x] V1_{t+1}[x][j], x = l - j + pad_left (de_{t+1} of the neighbours' frames through L2:
+            // written, fenced and followed by two cluster exchanges in step t+1)
+            for (int i = tid; i < BG * DC_RMAX; i += DC_THREADS) {
+                const int b = i / DC_RMAX, r = i % DC_RMAX;
+                if (r < sm.nr_s[b]) {
+                    const int Lb = sm.len_s[b], l = sm.l0_s[b] + r;
+                    float c = sm.pg_s[t & 1][b] * (float)(Lb - l);
+                    if (t + 1 < T) {
+                        c -= sm.pg_s[(t + 1) & 1][b] * (float)(Lb - l);
+                        if constexpr (LOC != 0) {
+                            const size_t row = ((size_t)(b0 + b) * T + t + 1) * Lmax;
+                            for (int jj = 0; jj < p.KF; jj++) {
+                                const int x = l - jj + p.padl;
+                                if (x >= 0 && x < Lb) c = fmaf(__ldcg(p.de_all + row + x), __ldg(p.V1 + (row + x) * p.KF + jj), c);
+                            }
+                        }
+                    }
+                    sm.cin_s[b][r] = c;
+                }
+            }
+        }
+        if constexpr (LOC != 0) {
+            for (int i = tid; i < BG * (DC_RMAX + 32); i += DC_THREADS) {
+                const int b = i / (DC_RMAX + 32), x = i % (DC_RMAX + 32);
+                const int l = sm.l0_s[b] + x - p.padl;
+                sm.apw_s[b][x] = (t > 0 && b0 + b < p.B && l >= 0 && l < sm.len_s[b]) ? __ldg(p.alpha + ((size_t)(b0 + b) * T + t - 1) * Lmax + l) : 0.f;
+            }
         }
         {
             float qv[BG];
@@ -854,7 +900,7 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) acc = dot4(hv[j][i], *reinterpret_cast<const float4*>(&sm.dc_full[b][lane * 4 + 128 * i]), acc);
                 acc = warp_sum(acc);
-                if (lane == 0) sm.dal_s[b][sm.fr[f]] = acc;
+                if (lane == 0) sm.dal_s[b][sm.fr[f]] = acc + sm.cin_s[b][sm.fr[f]];
             }
         }
         __syncthreads();
@@ -877,6 +923,7 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
                 sm.de_s[b][r] = de;
                 if (r < nr) p.de_all[((size_t)(b0 + b) * T + t) * Lmax + sm.l0_s[b] + r] = de;
             }
+            if constexpr (LOC != 0) __threadfence();             // the neighbours read these de_t (filter halo) through L2 in step t-1
         }
         __syncthreads();
         DC_TICK(4);
@@ -884,7 +931,55 @@ dec_cluster_bwd_kernel(const DecClusterBwdParams p) {
         // ---- F: dq_t = sum_l de_l w (1 - tanh^2(Vh_l + q_t))   (Attention.lua:95-121 reversed) -------------------------------------------
         // thread = (float4 column c4, row group g) like the context phase of the forward kernel: warp w holds the 8 columns of CTA w's
         // slice x 4 row groups, so the CTA's partial needs no shared-memory accumulation: two shuffles, then straight to the owner.
-        {
+        if constexpr (LOC != 0) {
+            // location-aware energies: Z_l = q_t + Vh_l + U W_F alpha_{t-1}[l + j - pad_left].  One utterance at a time; a thread's five
+            // frames are CONSECUTIVE so their filter windows share a 14-value run of alpha_{t-1}; the thread's columns of U W_F stay in
+            // registers for the whole phase.
+            const int c4 = 8 * warp + (lane & 7), g = lane >> 3, dst = warp;
+            const uint32_t dbar = mapa_rank(bar_a[BB_X6A], dst);
+            float4 w4 = *reinterpret_cast<const float4*>(&sm.w_s[c4 * 4]);
+            w4.x *= 4.f; w4.y *= 4.f; w4.z *= 4.f; w4.w *= 4.f;
+            float4 uwr[DC_KFMAX];
+#pragma unroll
+            for (int jj = 0; jj < DC_KFMAX; jj++) uwr[jj] = *reinterpret_cast<const float4*>(&sm.uw_s[jj * S + c4 * 4]);
+#pragma unroll 1
+            for (int b = 0; b < BG; b++) {
+                const int nr = sm.nr_s[b];
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 qk = *reinterpret_cast<const float4*>(&sm.q_full[b][c4 * 4]);
+                const float* vp = p.Vh + ((size_t)(b0 + b) * Lmax + sm.l0_s[b]) * S + c4 * 4;
+                for (int base = 0; base < nr; base += 20) {
+                    const int r0 = base + 5 * g;
+                    float4 vx[5];
+#pragma unroll
+                    for (int u = 0; u < 5; u++) vx[u] = ldg_stream(vp + (size_t)min(r0 + u, nr - 1) * S);
+                    float a[DC_KFMAX + 4];
+#pragma unroll
+                    for (int x = 0; x < DC_KFMAX + 4; x++) a[x] = sm.apw_s[b][r0 + x];
+#pragma unroll
+                    for (int u = 0; u < 5; u++) {
+                        float4 z = qk;
+#pragma unroll
+                        for (int jj = 0; jj < DC_KFMAX; jj++) {
+                            z.x = fmaf(a[u + jj], uwr[jj].x, z.x); z.y = fmaf(a[u + jj], uwr[jj].y, z.y);
+                            z.z = fmaf(a[u + jj], uwr[jj].z, z.z); z.w = fmaf(a[u + jj], uwr[jj].w, z.w);
+                        }
+                        const float de = sm.de_s[b][r0 + u];                           // zero past the slice
+                        const float4 gv = dc_dtanh4(vx[u], z);
+                        acc.x = fmaf(de, gv.x, acc.x); acc.y = fmaf(de, gv.y, acc.y);
+                        acc.z = fmaf(de, gv.z, acc.z); acc.w = fmaf(de, gv.w, acc.w);
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                }
+                if (g == 0)
+                    st_async_v4(mapa_rank(rdq_a + (uint32_t)((crank * BG + b) * 32 + (c4 & 7) * 4) * 4u, dst),
+                                make_float4(w4.x * acc.x, w4.y * acc.y, w4.z * acc.z, w4.w * acc.w), dbar);
+            }
+        } else {
             const int c4 = 8 * warp + (lane & 7), g = lane >> 3, dst = warp;
             const uint32_t dbar = mapa_rank(bar_a[BB_X6A], dst);
             float4 w4 = *reinterpret_cast<const float4*>(&sm.w_s[c4 * 4]);
@@ -1056,13 +1151,14 @@ int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const
 }
 
 
-template <int BG>
+template <int BG, int LOC>
 static int dcb_launch(s2s_ctx* ctx, const DecClusterBwdParams& p, int* max_clusters) {
     static bool attr = false;
-    const size_t smem = sizeof(DcBwdSmem<BG>);
+    const size_t smem = sizeof(DcBwdSmem<BG, LOC>);
+    static_assert(sizeof(DcBwdSmem<BG, LOC>) <= 227 * 1024, "decoder cluster backward: shared memory");
     if (!attr) {
-        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_bwd_kernel<BG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_bwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_bwd_kernel<BG, LOC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        S2S_CUDA(cudaFuncSetAttribute(dec_cluster_bwd_kernel<BG, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -1075,10 +1171,10 @@ static int dcb_launch(s2s_ctx* ctx, const DecClusterBwdParams& p, int* max_clust
     at[0].val.clusterDim.x = DC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     if (max_clusters) {
-        if (cudaOccupancyMaxActiveClusters(max_clusters, dec_cluster_bwd_kernel<BG>, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
+        if (cudaOccupancyMaxActiveClusters(max_clusters, dec_cluster_bwd_kernel<BG, LOC>, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
         return 0;
     }
-    S2S_CUDA(cudaLaunchKernelEx(&cfg, dec_cluster_bwd_kernel<BG>, p));
+    S2S_CUDA(cudaLaunchKernelEx(&cfg, dec_cluster_bwd_kernel<BG, LOC>, p));
     ctx->kcount[S2S_KC_DEC_CLUSTER_BWD]++;
     S2S_LAUNCH_CHECK(ctx);
     return 0;
@@ -1087,21 +1183,27 @@ static int dcb_launch(s2s_ctx* ctx, const DecClusterBwdParams& p, int* max_clust
 bool decoder_cluster_backward_eligible(const Layout& Y, int Lmax, float lambda) {
     const int KF = Y.K > 0 ? Y.KF : 0;
     { const char* e = getenv("S2S_DEC_CLUSTER_BWD"); if (e && !atoi(e)) return false; }
-    return dc_enabled() && Y.ST == DC_ST && Y.A == DC_A && Y.S == DC_S && KF == 0 && lambda == 0.f && Lmax <= DC_CS * DC_RMAX;
+    (void)lambda;                // the alignment carry (location term, monotonicity penalty) runs inside the cluster kernel
+    return dc_enabled() && Y.ST == DC_ST && Y.A == DC_A && Y.S == DC_S && KF <= DC_KFMAX && Lmax <= DC_CS * DC_RMAX;
 }
 
-// The time loop of decoder_backward on the cluster kernel (same conditions as the forward one, and no alpha carry: K = 0, lambda = 0).
+// The time loop of decoder_backward on the cluster kernel (same conditions as the forward one).  V1 (location path): the hoisted
+// Jacobian of attn_v1, [B, T, Lmax, KF].
 int decoder_cluster_backward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, int T, float lambda,
                              const DecoderState& d, const float* WsT, const float* GhT, const float* GzrT, const float* WjcT, const float* dsc,
-                             float* dA, float* du_all, float* dc_all, float* dq_all, float* de_all, bool* handled) {
+                             const float* V1, float* dA, float* du_all, float* dc_all, float* dq_all, float* de_all, bool* handled) {
     *handled = false;
     if (!decoder_cluster_backward_eligible(Y, Lmax, lambda)) return 0;
     static int cap = -1;
+    const int KF = Y.K > 0 ? Y.KF : 0;
+    S2S_REQUIRE(KF == 0 || V1 != nullptr, "decoder_cluster_backward: the location path needs V1");
     DecClusterBwdParams p = {};
+    p.uw = d.uw; p.V1 = V1; p.pen = d.pen; p.KF = KF; p.padl = KF > 0 ? ((KF % 2 == 1) ? (KF - 1) / 2 : KF / 2) : 0;      // Attention.lua:77-85
+    p.lambda = lambda; p.carry = (KF > 0 || lambda != 0.f) ? 1 : 0;
     p.Vh = d.Vh; p.h = h; p.w = P + Y.we.off; p.q = d.q; p.alpha = d.alpha; p.gates = d.gates; p.su = d.su; p.dsc = dsc;
     p.WsT = WsT; p.GhT = GhT; p.GzrT = GzrT; p.WjcT = WjcT; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.T = T;
     p.dA = dA; p.du_all = du_all; p.dc_all = dc_all; p.dq_all = dq_all; p.de_all = de_all;
-    if (cap < 0) { int n = 0; S2S_TRY(dcb_launch<5>(ctx, p, &n)); cap = n; }
+    if (cap < 0) { int n = 0; S2S_TRY((dcb_launch<5, 1>(ctx, p, &n))); cap = n; }
     if (cap < 1) return 0;
     static long long* clk = nullptr;
     static int prof = -1;
@@ -1116,12 +1218,22 @@ int decoder_cluster_backward(s2s_ctx* ctx, const Layout& Y, const float* P, cons
     while (bg < 5 && ceil_div(B, bg) > cap) bg++;
     { const char* e = getenv("S2S_DEC_BG"); if (e && atoi(e) >= 1 && atoi(e) <= 5) bg = atoi(e); }
     prof_begin(ctx, S2S_PROF_DEC_BWD);
-    switch (bg) {
-        case 1: S2S_TRY(dcb_launch<1>(ctx, p, nullptr)); break;
-        case 2: S2S_TRY(dcb_launch<2>(ctx, p, nullptr)); break;
-        case 3: S2S_TRY(dcb_launch<3>(ctx, p, nullptr)); break;
-        case 4: S2S_TRY(dcb_launch<4>(ctx, p, nullptr)); break;
-        default: S2S_TRY(dcb_launch<5>(ctx, p, nullptr)); break;
+    if (KF > 0) {
+        switch (bg) {
+            case 1: S2S_TRY((dcb_launch<1, 1>(ctx, p, nullptr))); break;
+            case 2: S2S_TRY((dcb_launch<2, 1>(ctx, p, nullptr))); break;
+            case 3: S2S_TRY((dcb_launch<3, 1>(ctx, p, nullptr))); break;
+            case 4: S2S_TRY((dcb_launch<4, 1>(ctx, p, nullptr))); break;
+            default: S2S_TRY((dcb_launch<5, 1>(ctx, p, nullptr))); break;
+        }
+    } else {
+        switch (bg) {
+            case 1: S2S_TRY((dcb_launch<1, 0>(ctx, p, nullptr))); break;
+            case 2: S2S_TRY((dcb_launch<2, 0>(ctx, p, nullptr))); break;
+            case 3: S2S_TRY((dcb_launch<3, 0>(ctx, p, nullptr))); break;
+            case 4: S2S_TRY((dcb_launch<4, 0>(ctx, p, nullptr))); break;
+            default: S2S_TRY((dcb_launch<5, 0>(ctx, p, nullptr))); break;
+        }
     }
     prof_end(ctx, S2S_PROF_DEC_BWD, 4.0 * B * T * ((double)Lmax * (DC_S + DC_A)));
     if (p.clk) {

@@ -35,20 +35,6 @@ namespace cg = cooperative_groups;
 
 namespace s2s {
 
-struct GruSeqParams {
-    const float* W;        // [ndir][3][H][ldw]  (forward: rows used as-is; backward: read transposed)
-    int ldw;               // H + Din
-    const float* xp;       // [B, Lmax, ndir*3H] time-batched input projections (forward only)
-    const int* lengths;
-    int B, Lmax, ndir, reverse0;   // reverse0: direction of dir index 0 (ndir == 1 case)
-    float* y;              // [B, Lmax, ndir*H]
-    float* save;           // [B, Lmax, ndir, 4H]: z | r | h~ | r*h_prev
-    // backward
-    const float* dy;       // [B, Lmax, ndir*H]
-    float* dA;             // [B, Lmax, ndir*3H]: daz | dar | dah   (same column order as xp)
-    float* hp_all;         // [B, Lmax, ndir, H]
-    int dbg;               // timing experiments only (S2S_GRU_DBG): 1 = skip the DSMEM exchange, 2 = skip the mat-vec loops
-};
 
 // Geometry of one cluster.  UC hidden units per CTA (cluster of H/UC CTAs), BG utterances per cluster.
 //   UC = 32: clusters of 8 (portable), butterflies of 8 rows x 4 utterances -> groups of 4 utterances are optimal
@@ -837,6 +823,16 @@ static int launch_cluster_geo(s2s_ctx* ctx, bool backward, const GruSeqParams& p
 // 8 utterances on clusters of 16 (one butterfly pass); else larger groups on clusters of 8 (two passes).
 template <int H>
 static int launch_cluster(s2s_ctx* ctx, bool backward, const GruSeqParams& p) {
+    static int v2 = -1;
+    if (v2 < 0) { const char* e = getenv("S2S_GRU_V2"); v2 = e ? atoi(e) : 1; }
+    if (v2) {   // second-generation kernels (gru_seq2.cu): per-source barriers, row-per-lane mat-vec, one block barrier per phase
+        prof_begin(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD);
+        S2S_TRY(gru_cluster2_launch(ctx, backward, p, H));
+        prof_end(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD, 4.0 * p.B * p.Lmax * p.ndir * (backward ? 9.0 : 8.0) * H);
+        ctx->kcount[S2S_KC_GRU_CLUSTER]++;
+        S2S_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     static int cap8[2] = {0, 0}, cap16[2] = {-1, -1};
     if (cap8[backward] == 0) {
         int n = 0;

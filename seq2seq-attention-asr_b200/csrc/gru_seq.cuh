@@ -4,6 +4,24 @@
 
 namespace s2s {
 
+struct GruSeqParams {
+    const float* W;        // [ndir][3][H][ldw]  (forward: rows used as-is; backward: read transposed)
+    int ldw;               // H + Din
+    const float* xp;       // [B, Lmax, ndir*3H] time-batched input projections (forward only)
+    const int* lengths;
+    int B, Lmax, ndir, reverse0;   // reverse0: direction of dir index 0 (ndir == 1 case)
+    float* y;              // [B, Lmax, ndir*H]
+    float* save;           // [B, Lmax, ndir, 4H]: z | r | h~ | r*h_prev
+    // backward
+    const float* dy;       // [B, Lmax, ndir*H]
+    float* dA;             // [B, Lmax, ndir*3H]: daz | dar | dah   (same column order as xp)
+    float* hp_all;         // [B, Lmax, ndir, H]
+    long long* clk;        // optional per-phase clock accumulators of CTA 0 (S2S_GRU_PROF)
+    int dbg;               // timing experiments only (S2S_GRU_DBG): 1 = skip the DSMEM exchange, 2 = skip the mat-vec loops
+};
+
+// second-generation cluster kernels (gru_seq2.cu)
+int gru_cluster2_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
 
 // y [B,Lmax,ndir*H]; save [B,Lmax,ndir,4H] (z | r | h~ | r*h_prev)
 int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int reverse, const float* x, int ldx,

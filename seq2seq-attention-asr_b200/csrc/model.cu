@@ -83,6 +83,11 @@ int model_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, cons
     nll_seed_kernel<<<B * T, 64, 0, ctx->stream>>>(labels, tlens, T, Y.V, flags, dlogp);
     S2S_LAUNCH_CHECK(ctx);
     S2S_TRY(decoder_backward(ctx, Y, P, G, m.acts[Y.NL], lengths, B, Lmax, labels, tlens, T, dropmask, lambda, dlogp, dcur));
+    // data-parallel overlap (s2s_dp_set_overlap): a bucket of the flat gradient is summed over the ranks as soon as it is complete, on the
+    // low-priority side stream, while the remaining recurrences run: the decoder's parameters under the whole encoder backward, encoder
+    // layer l under the recurrences of layers l-1 .. 0 (its weight-gradient GEMMs already run there)
+    const bool dpo = ctx->dp_overlap && dp_world(ctx) > 1;
+    if (dpo) S2S_TRY(dp_allreduce_bucket(ctx, G + Y.WV.off, Y.n - Y.WV.off, true));
     for (int l = Y.NL - 1; l >= 0; l--) {
         const int din = l == 0 ? Y.D : A;
         float* dprev = nullptr;
@@ -91,8 +96,22 @@ int model_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, cons
         S2S_TRY(gru_seq_backward(ctx, P + Y.enc[l][0][0].off, G + Y.enc[l][0][0].off, din, H, 2, 0, m.acts[l], din, lengths, B, Lmax,
                                  m.acts[l + 1], m.saves[l], dcur, dprev, /*defer_wgrad=*/l > 0));
         dcur = dprev;
+        if (dpo) {
+            const int64_t off = Y.enc[l][0][0].off, end = l + 1 < Y.NL ? Y.enc[l + 1][0][0].off : Y.WV.off;
+            if (l > 0) {            // behind the layer's weight-gradient GEMMs on the side stream
+                cudaStream_t main_stream = ctx->stream;
+                ctx->stream = ctx->side[1];
+                const int rc = dp_allreduce_bucket(ctx, G + off, end - off, false);
+                ctx->stream = main_stream;
+                S2S_TRY(rc);
+                S2S_CUDA(cudaEventRecord(ctx->ev[3], ctx->side[1]));        // the join event of gru_seq_wgrad_join now also covers the reduce
+            } else {
+                S2S_TRY(dp_allreduce_bucket(ctx, G + off, end - off, false));
+            }
+        }
     }
     S2S_TRY(gru_seq_wgrad_join(ctx));
+    if (dpo) S2S_TRY(dp_join(ctx));
     return 0;
 }
 

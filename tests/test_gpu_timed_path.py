@@ -37,13 +37,32 @@ def _threads():
         return 8
 
 
-@pytest.mark.parametrize("name,extra,ragged,lam", [("cfg2", {}, False, 0.0), ("cfg2loc", dict(K=16), False, 0.0),
-                                                   ("cfg2loc-ragged-penalty", dict(K=16), True, 0.02)])
-def test_timed_configuration_matches_oracle(s2s, orc64, name, extra, ragged, lam):
+def _penalty_margin(ref, lengths, tlens):
+    """smallest |sum_l (L-l)(alpha_t - alpha_{t-1})| / (L/2) over all utterances and steps: the argument of the
+    MonotonicAlignment max(0, .) (MonotonicAlignment.lua:27-41), whose SIGN decides whether the +-lambda (L+1-l) gradient
+    is injected.  With freshly initialised weights alpha is nearly uniform and the argument is below fp32 resolution
+    (1e-8 relative: the float32 and float64 ORACLES then disagree by 80% on dW_s), so the penalty case runs on weights
+    scaled to give peaked, moving alignments and asserts its own decision margin."""
+    m = np.inf
+    for b in range(len(lengths)):
+        Lb, Tb = int(lengths[b]), int(tlens[b])
+        if Tb < 2:
+            continue
+        w = (ref["alpha"][b, :Tb, :Lb] * (Lb - np.arange(Lb))).sum(1)
+        m = min(m, float(np.abs(w[1:] - w[:-1]).min() / (Lb / 2)))
+    return m
+
+
+@pytest.mark.parametrize("name,extra,ragged,lam,scale", [("cfg2", {}, False, 0.0, 1.0), ("cfg2loc", dict(K=16), False, 0.0, 1.0),
+                                                         ("cfg2loc-ragged", dict(K=16), True, 0.0, 1.0),
+                                                         ("cfg2loc-ragged-penalty", dict(K=16), True, 0.02, 4.0)])
+def test_timed_configuration_matches_oracle(s2s, orc64, name, extra, ragged, lam, scale):
     cfg = dict(CFG2, **extra)
-    P = init_params(cfg, seed=1234, dtype=np.float64, oracle=orc64)
+    P = init_params(cfg, seed=1234, dtype=np.float64, oracle=orc64) * scale
     X, lengths, labels, tlens = make_batch(cfg, B, L, T, seed=1000, ragged=ragged)
     ref = orc64.model_fwdbwd(cfg, P, X, lengths, labels, tlens, lam=lam, normalize_nll=True, nthreads=_threads())
+    if lam != 0.0:
+        assert _penalty_margin(ref, lengths, tlens) > 5e-6
     ctx = s2s.Context(0)
     try:
         Pd = dev(P, torch.float32); G = torch.zeros_like(Pd)
@@ -110,12 +129,15 @@ def test_cluster_decoder_backward_equals_per_step_chain(s2s, orc64, extra, lam):
             os.environ.pop("S2S_DEC_CLUSTER_BWD", None)
         else:
             os.environ["S2S_DEC_CLUSTER_BWD"] = old
-    assert rel_err(res["1"][0], res["0"][0]) < 1e-5
+    # with the penalty, d alpha carries +-lambda (L - l) terms of size ~10 beside a 1e-3 signal and the softmax backward cancels them:
+    # the two evaluation orders then differ by the cancellation noise, not by 1e-7
+    tol = 1e-5 if lam == 0.0 else 1e-3
+    assert rel_err(res["1"][0], res["0"][0]) < tol
     segs = list(zip(orc64.param_segments(cfg), segment_names(cfg)))
     for (off, rows, cols), name in segs:
         a, b = res["1"][1][off:off + rows * cols], res["0"][1][off:off + rows * cols]
         scale = max(np.abs(b).max(), 1e-6 * np.abs(res["0"][1]).max())
-        assert np.abs(a - b).max() / scale < 2e-5, name
+        assert np.abs(a - b).max() / scale < 2 * tol, name
 
 
 def test_normalize_grad_flag(s2s, gctx, orc64):
