@@ -5,10 +5,11 @@ Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl refere
   N > 1 is launched by torch.distributed.run (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
 
 Workload ("step"): one pass of the training hot path over one synthetic minibatch of BASELINE.json
-configs[1]: timit/model_chorowski_baseline.lua, batch 32 PER GPU (weak scaling), L = 300 log-mel
-frames of D = 123, T = 50 labels of V = 62, content-only attention (the shipped default, K = 0):
-zero grads -> encoder/decoder forward -> per-utterance NLL -> backward -> [all-reduce of the flat
-gradient over NCCL] -> /B, clip, adadelta, row-norm constraint (timit/timit.lua:233-348).
+configs[1] ("Chorowski TIMIT baseline batch 32, location-aware attention + GRU encoder/decoder"):
+timit/model_chorowski_baseline.lua with hybridAttendFeatureMaps = 16, filter 10 (`cfg2loc`), batch 32 PER GPU (weak
+scaling), L = 300 log-mel frames of D = 123, T = 50 labels of V = 62:
+zero grads -> encoder/decoder forward -> per-utterance NLL -> backward -> [sum of the flat gradient over the ranks:
+the C ABI's NCCL plane, bucketed under the backward pass] -> /B, clip, adadelta, row-norm constraint (timit/timit.lua:233-348).
   value   : frames/s with inputs resident in HBM (CUDA events on the launching stream, per-step events,
             L2 flushed between steps by a 256 MiB write outside the event pairs; max over ranks)
   e2e     : the same metric through the public host API with HOST buffers (pinned): H2D of the
@@ -16,11 +17,12 @@ gradient over NCCL] -> /B, clip, adadelta, row-norm constraint (timit/timit.lua:
             pipeline (the next step's copies on a copy stream, the result read one step late)
   roofline: the kernel class with the largest share of the step, timed live with CUDA events by the
             library's profiling hook on an instrumented extra pass (s2s_ctx_profile)
-  cpu_baseline: the CPU oracle (a C restatement of the reference; Torch7 cannot run here) on a
-            bounded sample of the same workload, all host threads
-`--config cfg2loc` switches the location-aware term on (hybridAttendFeatureMaps = 16, filter 10: off in the shipped model);
-`--config cfg3` / `--config cfg4` run the other training configurations of BASELINE.json (dropout + AdaptiveWeightNoise;
-librispeech/model_vgg.lua with its VGG front-end) with the same contract; the driver's default is cfg2.
+  variants: the same contract (K steps, L2 flush, device events, max over ranks) for cfg2 (the shipped default, content-only
+            attention K = 0), cfg3 (dropout model + AdaptiveWeightNoise) and, for N > 1, strong scaling at GLOBAL batch 32
+  cpu_baseline: the CPU oracle (a C restatement of the reference; Torch7 cannot run here) on the same 32-utterance
+            minibatch, all host threads
+`--config cfg2` / `cfg3` / `cfg4` run one of the other training configurations of BASELINE.json as the headline (content-only;
+dropout + AdaptiveWeightNoise; librispeech/model_vgg.lua with its VGG front-end); `--config cfg5` is the attention-step sweep.
 `--impl reference` times that CPU oracle alone (the reference's own implementation is Lua/Torch7 and
 cannot be installed in this image: see DESIGN.md).
 """
@@ -37,13 +39,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(D=123, H=256, NL=3, S=512, ST=256, V=62, K=0, KF=10, M=64, MW=7)
+CFG = dict(D=123, H=256, NL=3, S=512, ST=256, V=62, K=16, KF=10, M=64, MW=7)   # headline: location-aware (hybridAttendFeatureMaps = 16, filter 10)
 B_PER_GPU, L, T = 32, 300, 50
 METRIC = "chorowski_timit_fwd_bwd_frames_per_sec"
-WORKLOAD_CFG3 = ("cfg3: timit/model_chorowski_baseline_dropout.lua (cfg2 model + Dropout(0.5) on {s,c}) with AdaptiveWeightNoise "
+WORKLOAD_CFG3 = ("cfg3: timit/model_chorowski_baseline_dropout.lua (cfg2loc model + Dropout(0.5) on {s,c}) with AdaptiveWeightNoise "
                  "(lambda=1, sigma_init=0.075), batch 32/GPU, L=300, T=50; step = AWN sample (one per shard) + dropout mask + zero-grad + "
                  "fwd + NLL + bwd + [all-reduce] + /B + clip + AWN forward/backward + adadelta over {mu, log sigma^2} + row-norm")
-WORKLOAD = ("cfg2: timit/model_chorowski_baseline.lua (3x biGRU-256 encoder, content attention K=0, GRU-256 decoder, "
+WORKLOAD = ("cfg2loc: timit/model_chorowski_baseline.lua (3x biGRU-256 encoder, location-aware attention K=16 k=10, GRU-256 decoder, "
             "maxout 64x7), batch 32/GPU, L=300, D=123, T=50, V=62; step = zero-grad + fwd + NLL + bwd + "
             "[all-reduce] + /B + clip + adadelta + row-norm")
 
@@ -110,7 +112,7 @@ def run_reference(args):
         return
     cores = host_threads()
     nthreads = max(1, min(cores, 32))
-    nutt = nthreads   # one utterance per thread per step: a bounded sample of the batch-32 workload
+    nutt = B_PER_GPU  # the GPU arm's step: the same 32-utterance minibatch (OpenMP over utterances)
     for _ in range(min(args.warmup, 1)):
         cpu_oracle_run(nutt, nthreads)
     times = []
@@ -123,7 +125,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_arm": "CPU oracle (oracle/s2s_oracle.c, C restatement of the Torch7 path; "
+        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "parallelism": "cpu",
+                   "reference_arm": "CPU oracle (oracle/s2s_oracle.c, C restatement of the Torch7 path; "
                    "the Lua reference cannot be installed: no LuaJIT/Torch7 in the image)"},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": nthreads, "kind": "port",
                          "sample": f"{nutt} utterances (L={L}, T={T}) per step, fwd+bwd, OpenMP over utterances"},
@@ -357,95 +360,114 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dbg("process group up")
     ctx = s2s.Context(local)
-    # the data path's collective is the C ABI's own NCCL plane (csrc/dp_nccl.cu); torch.distributed only ships the 128-byte id
-    # and carries the barrier / max-over-ranks of the timing
+    # the data path's collective is the C ABI's own NCCL plane (csrc/dp_nccl.cu): s2s_model_fwdbwd reduces the gradient buckets
+    # itself on a side stream under the remaining backward pass; torch.distributed only ships the 128-byte id and carries the
+    # barrier / max-over-ranks of the timing
     dp_overlap = not os.environ.get("S2S_BENCH_DP_PLAIN")
     if world > 1:
         s2s.dp.init(ctx, rank, world, overlap=dp_overlap)
-    B = B_PER_GPU
-    n = s2s.param_count(CFG)
-
-    P = torch.from_numpy(s2s.init_params(CFG, seed=1234)).to(dev)
-    G = torch.zeros(n, device=dev)
-    v_state = torch.zeros(n, device=dev); a_state = torch.zeros(n, device=dev)
-    Xh, yh, lh, th = synth(1000 + rank, B)
-    X = torch.from_numpy(Xh).to(dev); y = torch.from_numpy(yh).to(dev)
-    ln = torch.from_numpy(lh).to(dev); tl = torch.from_numpy(th).to(dev)
-    nll = torch.zeros(B, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    cfg3 = args.config == "cfg3"
-    if cfg3:
-        # AdaptiveWeightNoise.lua:8-25: weight = {mu, s = log sigma^2}, s initialised to log(sigma_init^2) (timit.lua:35-36,198-205)
-        W2 = torch.cat([P, torch.full((n,), float(np.log(0.075 ** 2)), device=dev)])
-        gW2 = torch.zeros(2 * n, device=dev)
-        v2 = torch.zeros(2 * n, device=dev); a2 = torch.zeros(2 * n, device=dev)
-        Pn = torch.empty(n, device=dev)
-        mask = torch.empty(B, T, CFG["ST"] + 2 * CFG["H"], device=dev)
-        counter = [0]
-
-    def step_cfg3(Xd, yd, lnd, tld):
-        counter[0] += 1
-        seed = (counter[0] << 8) | rank                              # a different sample per rank and step
-        s2s.awn_sample(ctx, W2, seed=seed, out=Pn)                    # parameters:copy(AWN:Sample())   (timit.lua:247-253)
-        s2s.dropout_mask(ctx, mask.shape, 0.5, seed=seed, out=mask)   # nn.Dropout on {s,c}  (model_chorowski_baseline_dropout.lua:56)
-        G.zero_()
-        s2s.model_fwdbwd(ctx, CFG, Pn, G, Xd, yd, lengths=lnd, tlens=tld, dropmask=mask, flags=s2s.NORMALIZE_NLL, nll=nll)
-        if world > 1 and not dp_overlap:
-            s2s.dp.allreduce(ctx, G)
-        s2s.grad_finalize(ctx, G, Pn, B * world, 1e20, want_norm=False)
-        s2s.awn_accgrad(ctx, W2, G, 1.0, out=gW2)                     # AWN:backward(nll, gradients)    (timit.lua:318-327)
-        s2s.adadelta(ctx, W2, gW2, v2, a2)                            # optimMethod(optimfunc, adaparameters, ...)  (:336)
-        s2s.model_rownorm_constraint(ctx, CFG, W2[:n], 1.0)           # the graph's weights are views of mu here (:346-348)
-        return nll
-
-    def step(Xd, yd, lnd, tld):
-        if cfg3:
-            return step_cfg3(Xd, yd, lnd, tld)
-        G.zero_()                                                     # zeroGradParameters (timit.lua:233)
-        s2s.model_fwdbwd(ctx, CFG, P, G, Xd, yd, lengths=lnd, tlens=tld, flags=s2s.NORMALIZE_NLL, nll=nll)
-        if world > 1 and not dp_overlap:                              # (with overlap the library reduced the buckets under the backward pass)
-            s2s.dp.allreduce(ctx, G)                                  # data-parallel gradient sum over NVLink: s2s_dp_allreduce
-        s2s.dp.gradient_step(ctx, s2s, CFG, P, G, v_state, a_state, B * world)   # /B, clip, adadelta, row-norm (timit.lua:292-348)
-        return nll
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(X, y, ln, tl)
-        torch.cuda.synchronize()
-        dbg(f"warmup step {i} done")
-    barrier()
-    dbg("warmup barrier passed")
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps ------------------------
+    class Workload:
+        """one configuration: parameters, optimiser state, a resident synthetic batch and its step function"""
+
+        def __init__(self, cfg, B, awn_dropout=False, seed=1000):
+            self.cfg, self.B, self.awn = dict(cfg), B, awn_dropout
+            n = s2s.param_count(cfg)
+            self.n = n
+            self.P = torch.from_numpy(s2s.init_params(cfg, seed=1234)).to(dev)
+            self.G = torch.zeros(n, device=dev)
+            self.v = torch.zeros(n, device=dev); self.a = torch.zeros(n, device=dev)
+            self.host = synth(seed + rank, B)
+            Xh, yh, lh, th = self.host
+            self.X = torch.from_numpy(Xh).to(dev); self.y = torch.from_numpy(yh).to(dev)
+            self.ln = torch.from_numpy(lh).to(dev); self.tl = torch.from_numpy(th).to(dev)
+            self.nll = torch.zeros(B, device=dev)
+            if awn_dropout:
+                # AdaptiveWeightNoise.lua:8-25: weight = {mu, s = log sigma^2}, s initialised to log(sigma_init^2) (timit.lua:35-36,198-205)
+                self.W2 = torch.cat([self.P, torch.full((n,), float(np.log(0.075 ** 2)), device=dev)])
+                self.gW2 = torch.zeros(2 * n, device=dev)
+                self.v2 = torch.zeros(2 * n, device=dev); self.a2 = torch.zeros(2 * n, device=dev)
+                self.Pn = torch.empty(n, device=dev)
+                self.mask = torch.empty(B, T, cfg["ST"] + 2 * cfg["H"], device=dev)
+                self.counter = 0
+
+        def step(self, Xd=None, yd=None, lnd=None, tld=None):
+            Xd = self.X if Xd is None else Xd; yd = self.y if yd is None else yd
+            lnd = self.ln if lnd is None else lnd; tld = self.tl if tld is None else tld
+            cfg, G, Bg = self.cfg, self.G, self.B * world
+            if self.awn:
+                self.counter += 1
+                seed = (self.counter << 8) | rank                                  # a different sample per rank and step
+                s2s.awn_sample(ctx, self.W2, seed=seed, out=self.Pn)               # parameters:copy(AWN:Sample())   (timit.lua:247-253)
+                s2s.dropout_mask(ctx, self.mask.shape, 0.5, seed=seed, out=self.mask)   # nn.Dropout on {s,c}  (model_chorowski_baseline_dropout.lua:56)
+                G.zero_()
+                s2s.model_fwdbwd(ctx, cfg, self.Pn, G, Xd, yd, lengths=lnd, tlens=tld, dropmask=self.mask, flags=s2s.NORMALIZE_NLL, nll=self.nll)
+                if world > 1 and not dp_overlap:
+                    s2s.dp.allreduce(ctx, G)
+                s2s.grad_finalize(ctx, G, self.Pn, Bg, 1e20, want_norm=False)
+                s2s.awn_accgrad(ctx, self.W2, G, 1.0, out=self.gW2)                # AWN:backward(nll, gradients)    (timit.lua:318-327)
+                s2s.adadelta(ctx, self.W2, self.gW2, self.v2, self.a2)             # optimMethod(optimfunc, adaparameters, ...)  (:336)
+                s2s.model_rownorm_constraint(ctx, cfg, self.W2[:self.n], 1.0)      # the graph's weights are views of mu here (:346-348)
+                return self.nll
+            G.zero_()                                                             # zeroGradParameters (timit.lua:233)
+            s2s.model_fwdbwd(ctx, cfg, self.P, G, Xd, yd, lengths=lnd, tlens=tld, flags=s2s.NORMALIZE_NLL, nll=self.nll)
+            if world > 1 and not dp_overlap:                                      # (with overlap the library reduced the buckets under the backward pass)
+                s2s.dp.allreduce(ctx, G)                                          # data-parallel gradient sum over NVLink: s2s_dp_allreduce
+            s2s.dp.gradient_step(ctx, s2s, cfg, self.P, G, self.v, self.a, Bg)    # /B, clip, adadelta, row-norm (timit.lua:292-348)
+            return self.nll
+
+        def timed(self, steps, warmup):
+            """K steps, per-step CUDA events on the launching stream, L2 flushed between steps; max over ranks"""
+            for i in range(max(warmup, 3)):
+                self.step()
+                torch.cuda.synchronize()
+            barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            l0 = ctx.launches
+            barrier()
+            for a, b in ev:
+                flush.fill_(1)
+                a.record()
+                self.step()
+                b.record()
+            barrier()
+            launches = ctx.launches - l0
+            ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / steps)
+            return ms, launches
+
+    K16 = dict(CFG, K=16)
+    K0 = dict(CFG, K=0)
+    headline_cfg = dict(CFG)
+    cfg3 = args.config == "cfg3"
+    main_w = Workload(headline_cfg, B_PER_GPU, awn_dropout=cfg3)
+    B = B_PER_GPU
+    dbg("workload built")
+
+    # ---- timed region of the headline configuration ------------------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = ctx.launches
-    barrier()
-    for a, b in ev:
-        flush.fill_(1)
-        a.record()
-        step(X, y, ln, tl)
-        b.record()
-    barrier()
-    launches = ctx.launches - launches0
-    dbg("timed region done")
+    ms, launches = main_w.timed(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    dbg("timed region done")
     frames = B * L * world
     value = frames / (ms / 1e3)
 
     # ---- e2e: host buffers -> H2D -> step -> D2H(nll), wall clock with device sync, max over ranks ------
+    Xh, yh, lh, th = main_w.host
+    X, y, ln, tl, nll = main_w.X, main_w.y, main_w.ln, main_w.tl, main_w.nll
     Xp = torch.from_numpy(Xh).pin_memory(); yp = torch.from_numpy(yh).pin_memory()
     lp = torch.from_numpy(lh).pin_memory(); tp = torch.from_numpy(th).pin_memory()
     Xd = torch.empty_like(X); yd = torch.empty_like(y); lnd = torch.empty_like(ln); tld = torch.empty_like(tl)
@@ -479,7 +501,7 @@ def run_ours(args):
             for dst, src in zip((Xd, yd, lnd, tld), stg[k]):
                 dst.copy_(src, non_blocking=True)
             ev_free[k].record(cur)
-            step(Xd, yd, lnd, tld)
+            main_w.step(Xd, yd, lnd, tld)
             nll_hs[k].copy_(nll, non_blocking=True)
             ev_out[k].record(cur)
             if i > 0:
@@ -495,11 +517,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     e2e_run(args.steps)
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     h2d = Xp.numel() * 4 + yp.numel() * 4 + lp.numel() * 4 + tp.numel() * 4
     d2h = nll_hs[0].numel() * 4
 
@@ -520,7 +538,7 @@ def run_ours(args):
     for _ in range(nprof):
         torch.cuda._sleep(int(60e6))          # ~30 ms of spinning, not inside any event pair
         ev2[0].record()
-        step(X, y, ln, tl)
+        main_w.step()
         ev2[1].record()
         torch.cuda.synchronize()
         total_ms += ev2[0].elapsed_time(ev2[1]) / nprof
@@ -543,22 +561,39 @@ def run_ours(args):
         top = max(classes, key=lambda k: classes[k]["ms_per_step"])
         c = classes[top]
         roof = {"kernel": top, "bound": c["bound"], "achieved": c["achieved"], "peak": c["peak"], "unit": c["unit"], "frac": c["frac"],
-                "traffic": ncu_traffic(top), "traffic_source": "profiles/r01_ncu_full.json (ncu --set full, bytes per launch)",
+                "traffic": ncu_traffic(top), "traffic_source": "profiles/ ncu --set full capture (bytes per launch)",
                 "algorithmic_bytes_per_launch": prof[top][2] / max(prof[top][1], 1),
                 "peak_source": how, "share_of_step": c["share"], "instrumented_step_ms": total_ms,
                 "note": "the recurrence kernels are latency-bound (two dependent mat-vec phases per frame, DSMEM exchange): "
-                        "us/frame-step is the figure of merit; attention kernels: see `kernels` and profiles/r01_attn_sweep.json"}
+                        "us/frame-step is the figure of merit; attention kernels: see `kernels` and `--config cfg5`"}
+    kc = ctx.kernel_counts()
+
+    # ---- the other configurations of BASELINE.json, device-timed in the same run (same contract: K steps, L2 flush, max over ranks) ----
+    variants = {}
+    if not args.no_variants and args.config == "cfg2loc":
+        vsteps = max(3, min(args.steps, 10))
+        del main_w
+        specs = [("cfg2", K0, B_PER_GPU, False, "the shipped default hybridAttendFeatureMaps = 0 (content-only attention), batch 32/GPU"),
+                 ("cfg3", K16, B_PER_GPU, True, "model_chorowski_baseline_dropout.lua + AdaptiveWeightNoise (lambda 1, sigma_init 0.075), batch 32/GPU")]
+        if world > 1 and B_PER_GPU % world == 0:
+            specs.append(("cfg2loc_strong_b32", K16, B_PER_GPU // world, False, f"strong scaling: GLOBAL batch 32 = {B_PER_GPU // world}/GPU"))
+        for name, vcfg, vB, vawn, note in specs:
+            w = Workload(vcfg, vB, awn_dropout=vawn)
+            vms, vl = w.timed(vsteps, 3)
+            variants[name] = {"ms_per_step": vms, "value": vB * L * world / (vms / 1e3), "unit": "frames/s", "steps": vsteps,
+                              "global_batch": vB * world, "scaling": "strong" if "strong" in name else "weak", "gpu_launches": int(vl), "note": note}
+            del w
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_threads()
         nthreads = max(1, min(cores, 32))
-        nutt = nthreads * (2 if nthreads <= 16 else 1)
-        reps = 8                                                      # ~10 s of CPU work
+        nutt = 32
+        reps = 4 if nthreads >= 16 else 2                             # ~10-20 s of CPU work
         val, dt = cpu_oracle_run(nutt, nthreads, reps=reps)
         cpu = {"value": val, "unit": "frames/s", "cores": nthreads, "kind": "port",
-               "sample": f"{reps} passes of fwd+bwd over {nutt} utterances (L={L}, T={T}), fp32 C oracle, OpenMP over utterances, {dt:.1f} s per pass (mean)"}
+               "sample": f"{reps} passes of fwd+bwd over the same {nutt}-utterance minibatch (L={L}, T={T}), fp32 C oracle, OpenMP over utterances, {dt:.1f} s per pass (mean)"}
 
     if rank == 0:
         line = {
@@ -566,16 +601,22 @@ def run_ours(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_CFG3 if cfg3 else WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "flushed between timed steps (256 MiB write outside the per-step event pairs)",
-                       "e2e_pipeline": "step i+1's H2D on a copy stream during step i, result of step i read during step i+1"},
+                       "e2e_pipeline": "step i+1's H2D on a copy stream during step i, result of step i read during step i+1",
+                       "collective": ("none (1 rank)" if world == 1 else
+                                      ("s2s_dp_allreduce buckets inside s2s_model_fwdbwd (NCCL via the C ABI, side stream, under the backward pass)"
+                                       if dp_overlap else "s2s_dp_allreduce after s2s_model_fwdbwd (NCCL via the C ABI)"))},
             "e2e": {"value": frames / (e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
+            "kernel_launch_counts": kc,
             "clocks": clocks,
             "roofline": roof,
             "kernels": classes,
+            "variants": variants,
             "cpu_baseline": cpu,
         }
         emit_json(json.dumps(line))
     if world > 1:
+        s2s.dp.destroy(ctx)
         dist.destroy_process_group()
 
 
@@ -594,14 +635,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2loc", "cfg3", "cfg4"],
-                    help="cfg2 = the metric's configuration (default); cfg2loc = the same model with the location-aware term switched on "
-                         "(hybridAttendFeatureMaps = 16, filter 10: SURVEY Q1); cfg3 = dropout model + AdaptiveWeightNoise (BASELINE.json configs[2]); "
-                         "cfg4 = librispeech/model_vgg.lua, VGG front-end + attention decoder (configs[3])")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra configurations reported under `variants`")
+    ap.add_argument("--config", default="cfg2loc", choices=["cfg2", "cfg2loc", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2loc = the metric's configuration (default): BASELINE.json configs[1], location-aware attention (hybridAttendFeatureMaps = 16 "
+                         "as timit/timit.lua:130, filter 10 as model_chorowski_baseline.lua:39); its line also carries cfg2 / cfg3 / strong scaling under "
+                         "`variants`.  cfg2 = the shipped default hybridAttendFeatureMaps = 0 (content-only); cfg3 = dropout model + AdaptiveWeightNoise "
+                         "(configs[2]); cfg4 = librispeech/model_vgg.lua, VGG front-end + attention decoder (configs[3]); cfg5 = attention-step sweep (configs[4])")
     args = ap.parse_args()
-    if args.config == "cfg2loc":   # opt.hybridAttendFeatureMaps = 16 (timit/timit.lua:130), filter size 10 (model_chorowski_baseline.lua:39)
-        CFG["K"] = 16
-        globals()["WORKLOAD"] = WORKLOAD.replace("cfg2:", "cfg2loc:").replace("content attention K=0", "location-aware attention K=16, k=10")
+    if args.config == "cfg2":      # model.hybridAttendFeatureMaps = opt.hybridAttendFeatureMaps or 0 (model_chorowski_baseline.lua:40)
+        CFG["K"] = 0
+        globals()["WORKLOAD"] = WORKLOAD.replace("cfg2loc:", "cfg2:").replace("location-aware attention K=16 k=10", "content attention K=0")
     if args.impl == "reference":
         run_reference(args)
     elif args.config == "cfg4":

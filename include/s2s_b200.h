@@ -107,6 +107,12 @@ int  s2s_graph_destroy(s2s_ctx* ctx, int graph_id);
 int  s2s_ctx_profile(s2s_ctx* ctx, int enable);
 int  s2s_ctx_profile_read(s2s_ctx* ctx, double* ms_host, int64_t* count_host, double* work_host);
 
+/* ---- TrainUtils.orthogonalize (TrainUtils.lua:5-26; orthogonalizeGraph applies it to every module with a weight,
+ * librispeech/exp0_scriptchecker.lua:49-52).  In place: W [rows, cols] (and bias [rows] when not NULL, treated as one more column)
+ * := the orthonormal factor of the QR decomposition taken in the tall orientation (rows >= cols: qr(w).Q, else qr(w^T).Q^T), with
+ * LAPACK's Householder sign convention (what torch.qr returns). */
+int s2s_orthogonalize(s2s_ctx* ctx, float* W, int64_t rows, int64_t cols, float* bias);
+
 /* ---- data-parallel plane: NCCL over NVLink 5 / NVSwitch (no counterpart in the reference: single device, timit/timit.lua:39) ----
  * Only the minibatch shards (timit/timit.lua:240-295 sums per-utterance gradients): every rank holds the full parameters and
  * optimiser state, runs s2s_model_fwdbwd on its shard, the flat gradient is summed over the ranks, and the gradient step
@@ -249,6 +255,11 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
                      float* nll, float* logp, float* dX);
 /* encoder annotations of the last model call [B,Lmax,A] (encoder.output, timit.lua:397) */
 int s2s_model_get_annotations(s2s_ctx* ctx, float* dst);
+/* labelmask <-> labels on the device (timit/timit.lua:262 builds labelmask = one-hot(Y) [T,V] / [B,T,V] and feeds it to nn.Attention):
+ * labels[r] = index of the positive entry of row r, -1 for an all-zero row (a padded step, or prev_y at t = 1: RNNAttention.lua:172-176) */
+int s2s_labels_from_onehot(s2s_ctx* ctx, const float* onehot, int64_t rows, int V, int* labels);
+int s2s_onehot(s2s_ctx* ctx, const int* labels, int64_t rows, int V, float* onehot);
+
 /* Loss and gradient seed on their own (timit/timit.lua:262-282), for callers that compose an encoder
  * (e.g. s2s_vgg_forward) with s2s_attention_forward / _backward: nll [B] and/or dlogp [B,T,V] (either may be NULL) */
 int s2s_nll_grad_seed(s2s_ctx* ctx, const float* logp, const int* labels, const int* tlens, int B, int T, int V,

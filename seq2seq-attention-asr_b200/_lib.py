@@ -70,6 +70,7 @@ def load():
         "s2s_ctx_set_graphs": (i32, [vp, i32]),
         "s2s_ctx_profile": (i32, [vp, i32]),
         "s2s_ctx_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(f64)]),
+        "s2s_orthogonalize": (i32, [vp, vp, i64, i64, vp]),
         "s2s_dp_available": (i32, []),
         "s2s_dp_unique_id": (i32, [vp]),
         "s2s_dp_init": (i32, [vp, i32, i32, vp]),
@@ -128,6 +129,8 @@ def load():
         "s2s_conv3_forward": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, vp, i32]),
         "s2s_conv3_dgrad": (i32, [vp, vp, i64, i32, i32, vp, i32, vp]),
         "s2s_conv3_wgrad": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
+        "s2s_labels_from_onehot": (i32, [vp, vp, i64, i32, vp]),
+        "s2s_onehot": (i32, [vp, vp, i64, i32, vp]),
         "s2s_nll_grad_seed": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
         "s2s_edit_distance": (i32, [vp, i32, vp, i32, vp]),
         "s2s_attn_step_forward_loc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),

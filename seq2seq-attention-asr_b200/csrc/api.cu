@@ -23,12 +23,15 @@ int attention_step_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const flo
 static void graph_drop(s2s_ctx* ctx) {
     if (ctx->graph.exec) { cudaGraphExecDestroy(ctx->graph.exec); ctx->graph.exec = nullptr; }
     ctx->graph.key.clear(); ctx->graph.seen = 0; ctx->graph.launches = 0; ctx->graph.nocapture = false;
+    ctx->wgrad_join_pending = false;      // an event recorded inside a dropped / failed capture must not be waited on by an eager call
     bool user_alive = false;
     for (cudaGraphExec_t g : ctx->user_graphs) user_alive = user_alive || g != nullptr;
     ctx->arena.frozen = user_alive; ctx->persist.frozen = user_alive;      // memory referenced by a live graph must not move
 }
 
 namespace s2s {
+int labels_from_onehot(s2s_ctx* ctx, const float* onehot, int64_t rows, int V, int* labels);
+int onehot_from_labels(s2s_ctx* ctx, const int* labels, int64_t rows, int V, float* onehot);
 void vgg_state_free(s2s_ctx* ctx);
 int nll_and_seed(s2s_ctx* ctx, const float* logp, const int* labels, const int* tlens, int B, int T, int V, int flags, float* nll, float* dlogp);
 }
@@ -308,6 +311,15 @@ int s2s_graph_destroy(s2s_ctx* ctx, int graph_id) {
     }
     if (!ctx->graph.exec) graph_drop(ctx);      // unfreezes the workspaces when no graph is left
     return 0;
+}
+
+int s2s_labels_from_onehot(s2s_ctx* ctx, const float* onehot, int64_t rows, int V, int* labels) {
+    S2S_REQUIRE(ctx && onehot && labels && rows > 0 && V > 0, "labels_from_onehot: bad arguments");
+    return labels_from_onehot(ctx, onehot, rows, V, labels);
+}
+int s2s_onehot(s2s_ctx* ctx, const int* labels, int64_t rows, int V, float* onehot) {
+    S2S_REQUIRE(ctx && onehot && labels && rows > 0 && V > 0, "onehot: bad arguments");
+    return onehot_from_labels(ctx, labels, rows, V, onehot);
 }
 
 // nll[b] = -sum_t logp[b,t,y_t] (/T_b) and dlogp = -labelmask (/T_b), zero beyond T_b   (timit/timit.lua:262-282)

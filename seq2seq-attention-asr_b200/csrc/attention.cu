@@ -898,7 +898,7 @@ int attn_v1(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* w, c
 // =================================================================================================
 int attn_scratch_alloc(s2s_ctx* ctx, Arena& arena, int B, int Lmax, int S, int A, int KF, bool backward, AttnScratch* sc) {
     S2S_REQUIRE(Lmax <= ATT_MAXCH * ATT_R, "Lmax=%d exceeds the attention kernel limit %d", Lmax, ATT_MAXCH * ATT_R);
-    S2S_REQUIRE(B <= 4096, "B=%d exceeds the ticket-counter capacity 4096", B);
+    S2S_REQUIRE(B <= 4000, "B=%d exceeds the ticket-counter capacity 4000 (counters[4000..] are the dense-chain grid barrier, decoder.cu)", B);
     sc->nch = ceil_div(Lmax, ATT_R);
     S2S_ALLOC(sc->E, arena, float, (size_t)B * Lmax);
     S2S_ALLOC(sc->part_ms, arena, float, (size_t)B * sc->nch * 2);

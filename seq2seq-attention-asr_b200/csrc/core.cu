@@ -200,6 +200,11 @@ int s2s_ctx_create(int device, void* stream, s2s_ctx** out) {
     if (e != cudaSuccess || ndev == 0)
         return fail("no CUDA device available (%s); libs2s_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     S2S_REQUIRE(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+    // the per-kernel cudaFuncSetAttribute flags and cluster-occupancy figures are cached once per process, and they are per-device
+    // state: every context of a process must live on the same device (one process per GPU, as bench.py and the Lua host run)
+    static int process_device = -1;
+    if (process_device < 0) process_device = device;
+    S2S_REQUIRE(device == process_device, "this process already uses device %d: libs2s_b200 supports one device per process (one process per GPU)", process_device);
     S2S_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     S2S_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -207,6 +212,7 @@ int s2s_ctx_create(int device, void* stream, s2s_ctx** out) {
     s2s_ctx* c = new s2s_ctx();
     c->device = device;
     { const char* e = getenv("S2S_PDL"); if (e) c->pdl = atoi(e) != 0; }
+    { const char* e = getenv("S2S_GRAPHS"); if (e) c->graphs = atoi(e) != 0; }      // debugging: S2S_GRAPHS=0 keeps s2s_model_fwdbwd eager
     c->sm_count = prop.multiProcessorCount;
     c->stream = (cudaStream_t)stream;   // NULL = the legacy default stream (what cutorch uses, timit/timit.lua:39)
     c->own_stream = false;

@@ -921,9 +921,14 @@ int gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, in
     if (overlap < 0) { const char* e = getenv("S2S_OVERLAP"); overlap = e ? atoi(e) : 1; }
     const bool fork = defer_wgrad && overlap && ctx->side[1] && ctx->stream != ctx->side[1];
     cudaStream_t main_stream = ctx->stream;
+    struct SwapGuard {      // whatever path leaves this function, the context's stream and GEMM grid limit are restored
+        s2s_ctx* c; cudaStream_t s; bool on;
+        ~SwapGuard() { if (on) { c->stream = s; c->gemm_sm_limit = 0; } }
+    } guard{ctx, main_stream, false};
     if (fork) {
         S2S_CUDA(cudaEventRecord(ctx->ev[2], main_stream));
         S2S_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev[2], 0));
+        guard.on = true;
         ctx->stream = ctx->side[1];
         ctx->gemm_sm_limit = ctx->sm_count - 112 > 16 ? ctx->sm_count - 112 : 0;
     }
@@ -943,9 +948,7 @@ int gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, in
                               dWd + (size_t)2 * H * ldw, ldw, nullptr, GemmBatch(), sk);
         }
     }
-    if (fork) {
-        ctx->stream = main_stream;
-        ctx->gemm_sm_limit = 0;
+    if (fork && !rc) {
         S2S_CUDA(cudaEventRecord(ctx->ev[3], ctx->side[1]));
         ctx->wgrad_join_pending = true;
     }

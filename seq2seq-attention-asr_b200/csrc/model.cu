@@ -30,6 +30,38 @@ __global__ void nll_seed_kernel(const int* __restrict__ labels, const int* __res
     for (int v = threadIdx.x; v < V; v += blockDim.x) dlogp[(size_t)bt * V + v] = (v == y) ? g : 0.f;
 }
 
+// labelmask <-> labels (timit/timit.lua:262: labelmask = one-hot(Y) [T,V] is what the reference feeds nn.Attention and the loss).
+// labels[r] = argmax_v onehot[r, v] if that row has a positive entry, else -1 ("no label": padded step / all-zero prev_y at t = 0)
+__global__ void labels_from_onehot_kernel(const float* __restrict__ onehot, int64_t rows, int V, int* __restrict__ labels) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float best = 0.f; int bi = -1;
+    for (int v = lane; v < V; v += 32) { const float x = onehot[r * V + v]; if (x > best) { best = x; bi = v; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+    }
+    if (lane == 0) labels[r] = bi;
+}
+__global__ void onehot_kernel(const int* __restrict__ labels, int64_t rows, int V, float* __restrict__ onehot) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * V) return;
+    const int64_t r = i / V; const int v = (int)(i - r * V);
+    onehot[i] = labels[r] == v ? 1.f : 0.f;
+}
+int labels_from_onehot(s2s_ctx* ctx, const float* onehot, int64_t rows, int V, int* labels) {
+    labels_from_onehot_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, ctx->stream>>>(onehot, rows, V, labels);
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int onehot_from_labels(s2s_ctx* ctx, const int* labels, int64_t rows, int V, float* onehot) {
+    onehot_kernel<<<(unsigned)ceil_div64(rows * V, 256), 256, 0, ctx->stream>>>(labels, rows, V, onehot);
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 // standalone loss + gradient seed for callers that compose encoder and decoder themselves (timit/timit.lua:262-282)
 int nll_and_seed(s2s_ctx* ctx, const float* logp, const int* labels, const int* tlens, int B, int T, int V, int flags, float* nll, float* dlogp) {
     if (nll) {

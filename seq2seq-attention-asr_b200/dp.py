@@ -34,12 +34,28 @@ def shard_bounds(n_items, world_size, rank):
 
 
 # ---- NCCL plane behind the C ABI -------------------------------------------------------------------------
+def _prefer_bundled_nccl():
+    """The library dlopens libnccl.so.2 itself ($S2S_NCCL_LIB, a copy already mapped into the process, the system one).  Under a
+    Python host, point it at the NCCL wheel torch was built against so that one NCCL version serves the whole process."""
+    if os.environ.get("S2S_NCCL_LIB"):
+        return
+    try:
+        import nvidia.nccl as _n
+        cand = os.path.join(os.path.dirname(_n.__file__ or list(_n.__path__)[0]), "lib", "libnccl.so.2")
+    except Exception:
+        cand = os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib", "libnccl.so.2")
+    if os.path.exists(cand):
+        os.environ["S2S_NCCL_LIB"] = cand
+
+
 def nccl_available():
+    _prefer_bundled_nccl()
     return bool(_lib.load().s2s_dp_available())
 
 
 def unique_id():
     """ncclGetUniqueId through the C ABI: 128 bytes (call on rank 0, ship to every rank)."""
+    _prefer_bundled_nccl()
     buf = (C.c_char * 128)()
     check(_lib.load().s2s_dp_unique_id(buf))
     return bytes(buf.raw)
@@ -50,6 +66,7 @@ def init(ctx, rank, world_size, uid=None, store=None, overlap=False):
     `store` (a torch.distributed Store), or through the initialised torch.distributed process group."""
     if world_size <= 1:
         return
+    _prefer_bundled_nccl()
     if uid is None:
         if store is not None:
             if rank == 0:

@@ -17,7 +17,7 @@ function TCZB:__init(inputFrameSize, outputFrameSize, kW, dW)
 end
 
 function TCZB:reset(stdv)                     -- TemporalConvolutionZeroBias.lua:21-35
-   stdv = stdv or 1 / math.sqrt(self.kW * self.inputFrameSize)
+   if stdv then stdv = stdv * math.sqrt(3) else stdv = 1 / math.sqrt(self.kW * self.inputFrameSize) end
    self.weight:uniform(-stdv, stdv)
    self.bias:zero()
 end

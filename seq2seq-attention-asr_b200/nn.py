@@ -9,7 +9,8 @@ arguments, method names and error behaviour as the reference:
     nn.Attention(decoder_recurrent, decoder_mlp, scoreDepth, filterSize, featureMaps,
                  stateDepth, annotationDepth, outputDepth, monoAlignPenalty, penaltyLambda)   Attention.lua:15-24
     nn.WeightNoise(parameters, sigma) / nn.AdaptiveWeightNoise(parameters, lambda, sigma_init)
-    TrainUtils.columnNormConstraint(m, maxval)            TrainUtils.lua:52
+    nn.Maxout / nn.Linear / nn.Dropout / nn.Sequential    shape holders for the decoder_mlp graph nn.Attention inspects
+    TrainUtils.{apply2graph, columnNormConstraint(Graph), orthogonalize(Graph), optimConfigResets}   TrainUtils.lua:5-213, timit.lua:496-502
 
 Module protocol: updateOutput(input) -> self.output ; updateGradInput(input, gradOutput) -> self.gradInput ;
 accGradParameters(input, gradOutput, scale) ; forward / backward / zeroGradParameters / parameters().
@@ -29,6 +30,13 @@ class Module:
         self.output = None
         self.gradInput = None
         self.train = True
+        self.modules = None          # children TrainUtils.apply2graph descends into (TrainUtils.lua:142-145)
+
+    def findModules(self, cls):
+        out = [self] if isinstance(self, cls) else []
+        for m in self.modules or []:
+            out += m.findModules(cls)
+        return out
 
     def parameters(self):
         return [], []
@@ -50,9 +58,74 @@ class Module:
 
     def training(self):
         self.train = True
+        for m in self.modules or []:
+            m.training()
 
     def evaluate(self):
         self.train = False
+        for m in self.modules or []:
+            m.evaluate()
+
+
+class Param(Module):
+    """Leaf giving a slice of a flat parameter vector the .weight / .bias / .gradWeight / .gradBias fields that
+    TrainUtils.apply2graph looks for (lua/s2s_ffi.lua nn.S2SParam)."""
+
+    def __init__(self, ctx, name, weight, gradWeight, bias=None, gradBias=None):
+        super().__init__(ctx)
+        self.name, self.weight, self.gradWeight, self.bias, self.gradBias = name, weight, gradWeight, bias, gradBias
+
+    def parameters(self):
+        if self.bias is not None:
+            return [self.weight, self.bias], [self.gradWeight, self.gradBias]
+        return [self.weight], [self.gradWeight]
+
+
+def _bound(stdv, fan_in):
+    """reset(stdv) rule of LinearZeroBias.lua:12-29 / TemporalConvolutionZeroBias.lua:21-35: U(+-stdv sqrt 3) or U(+-1/sqrt(fan_in))"""
+    return stdv * math.sqrt(3.0) if stdv else 1.0 / math.sqrt(fan_in)
+
+
+# shape holders for the sub-graphs the model files hand to nn.Attention (model_chorowski_baseline.lua:53-59): they carry sizes and
+# initial values only -- the decoder MLP runs time-batched inside the library
+class Linear(Module):
+    def __init__(self, ctx, inputSize, outputSize):
+        super().__init__(ctx)
+        b = 1.0 / math.sqrt(inputSize)
+        self.weight = ctx.new(outputSize, inputSize).uniform_(-b, b)
+        self.bias = ctx.new(outputSize).uniform_(-b, b)
+
+
+class Maxout(Module):
+    """Maxout.lua:5-21: Linear(in, out*window) -> max over groups of `window` consecutive units"""
+
+    def __init__(self, ctx, inputDimension, outputDimension, window=4):
+        super().__init__(ctx)
+        assert inputDimension is not None, "must specify input dimension"
+        assert outputDimension is not None, "must specify output dimension"
+        self.inputDim, self.outputDim, self.window = inputDimension, outputDimension, window
+        self.linear = Linear(ctx, inputDimension, outputDimension * window)
+        self.modules = [self.linear]
+
+
+class Dropout(Module):
+    def __init__(self, ctx, p=0.5):
+        super().__init__(ctx)
+        self.p = p
+
+
+class LogSoftMax(Module):
+    pass
+
+
+class Sequential(Module):
+    def __init__(self, ctx, *mods):
+        super().__init__(ctx)
+        self.modules = list(mods)
+
+    def add(self, m):
+        self.modules.append(m)
+        return self
 
 
 class TemporalConvolutionZeroBias(Module):
@@ -70,8 +143,8 @@ class TemporalConvolutionZeroBias(Module):
         self.reset()
 
     def reset(self, stdv=None):
-        stdv = stdv or 1.0 / math.sqrt(self.inputFrameSize)
-        self.weight.uniform_(-stdv, stdv)
+        b = _bound(stdv, self.inputFrameSize)
+        self.weight.uniform_(-b, b)
         self.bias.zero_()
 
     def parameters(self):
@@ -106,14 +179,16 @@ class GRU(Module):
         self.diminput, self.dimoutput = diminput, dimoutput
         self.weight = ctx.new(3, dimoutput, dimoutput + diminput)
         self.gradWeight = ctx.zeros(3, dimoutput, dimoutput + diminput)
+        # the three LinearZeroBias leaves of the reference's GRU graph (GRU.lua:23-26): row-norm constraint / orthogonalize act per gate
+        self.modules = [Param(ctx, "GRU." + g, self.weight[i], self.gradWeight[i]) for i, g in enumerate("zrh")]
         self.reset()
 
     def reset(self, stdv=None):
-        stdv = stdv or 1.0 / math.sqrt(self.dimoutput + self.diminput)
-        self.weight.uniform_(-stdv, stdv)
+        b = _bound(stdv, self.dimoutput + self.diminput)
+        self.weight.uniform_(-b, b)
 
     def parameters(self):
-        return [self.weight[i] for i in range(3)], [self.gradWeight[i] for i in range(3)]
+        return [m.weight for m in self.modules], [m.gradWeight for m in self.modules]
 
     # single-step protocol through nn.Recurrent: input {x, prev_h} -> h (Recurrent.lua:104-127, GRU.lua:22-38)
     def updateOutput(self, input):
@@ -145,11 +220,17 @@ class LSTM(Module):
         n = ops.lstm_param_count(diminput, dimoutput, self.peepholes)
         self.weight = ctx.new(n)
         self.gradWeight = ctx.zeros(n)
+        # the nn.Linear leaves of the reference's LSTM graph (LSTM.lua:25-36), as views of the flat vector
+        self.modules = []
+        for name, (wo, rows, cols), bo in ops.lstm_segments(diminput, dimoutput, self.peepholes):
+            self.modules.append(Param(ctx, "LSTM." + name, self.weight[wo:wo + rows * cols].view(rows, cols), self.gradWeight[wo:wo + rows * cols].view(rows, cols),
+                                      self.weight[bo:bo + rows], self.gradWeight[bo:bo + rows]))
         self.reset()
 
     def reset(self, stdv=None):
-        stdv = stdv or 1.0 / math.sqrt(self.dimoutput)
-        self.weight.uniform_(-stdv, stdv)
+        for m in self.modules:                       # stock nn.Linear.reset: weight and bias U(+-1/sqrt(fan_in))
+            b = _bound(stdv, m.weight.shape[1])
+            m.weight.uniform_(-b, b); m.bias.uniform_(-b, b)
 
     def parameters(self):
         return [self.weight], [self.gradWeight]
@@ -216,33 +297,77 @@ class RNN(Module):
 
 
 class Attention(Module):
+    """nn.Attention (Attention.lua:15-24,214-438).  decoder_recurrent must contain one GRU(stateDepth, stateDepth);
+    decoder_mlp one or two Maxout stages (each followed by a Linear), optionally an nn.Dropout in front: their sizes select
+    cfg.M / cfg.MW / cfg.MLP and their weights initialise the corresponding segments (lua/Attention.lua does the same)."""
+
+    SEGS = ("WV", "bV", "Ws", "bs", "WF", "bF", "U", "bU", "we", "be", "Wy", "by", "Wc", "bc", "Wj", "bj", "Gz", "Gr", "Gh", "Wm", "bm",
+            "Wl", "bl", "Wm2", "bm2", "Wo", "bo")
+
     def __init__(self, ctx, decoder_recurrent, decoder_mlp, scoreDepth, hybridAttendFilterSize, hybridAttendFeatureMaps,
-                 stateDepth, annotationDepth, outputDepth, monoAlignPenalty=False, penalty_lambda=0.0, mlpDepth=64, maxoutWindow=7):
+                 stateDepth, annotationDepth, outputDepth, monoAlignPenalty=False, penalty_lambda=0.0):
         super().__init__(ctx)
         assert annotationDepth % 2 == 0
-        self.cfg = dict(D=1, H=annotationDepth // 2, NL=1, S=scoreDepth, ST=stateDepth, V=outputDepth,
-                        K=hybridAttendFeatureMaps or 0, KF=hybridAttendFilterSize or 10, M=mlpDepth, MW=maxoutWindow)
+        grus = decoder_recurrent.findModules(GRU)
+        if len(grus) != 1 or decoder_recurrent.findModules(LSTM):
+            raise ops.S2SError("nn.Attention (libs2s_b200): decoder_recurrent must wrap exactly one nn.GRU (LSTM decoders are not built)")
+        if grus[0].diminput != stateDepth or grus[0].dimoutput != stateDepth:
+            raise ops.S2SError("nn.Attention: decoder GRU must be GRU(stateDepth, stateDepth)")
+        maxouts = decoder_mlp.findModules(Maxout)
+        inner = [m.linear for m in maxouts]
+        linears = [l for l in decoder_mlp.findModules(Linear) if all(l is not i for i in inner)]
+        drops = decoder_mlp.findModules(Dropout)
+        if len(maxouts) not in (1, 2) or len(linears) != len(maxouts):
+            raise ops.S2SError("nn.Attention (libs2s_b200): decoder_mlp must be Maxout-Linear or Maxout-Linear-Maxout-Linear")
+        if maxouts[0].inputDim != stateDepth + annotationDepth:
+            raise ops.S2SError("nn.Attention: first Maxout must read {s, c}")
+        self.dropout = drops[0] if drops else None
+        self.cfg = dict(D=1, H=annotationDepth // 2, NL=0, S=scoreDepth, ST=stateDepth, V=outputDepth,
+                        K=hybridAttendFeatureMaps or 0, KF=hybridAttendFilterSize or 10, M=maxouts[0].outputDim, MW=maxouts[0].window,
+                        MLP=len(maxouts))
         self.scoreDepth, self.stateDepth, self.annotationDepth, self.outputDepth = scoreDepth, stateDepth, annotationDepth, outputDepth
+        self.monoAlignPenalty = bool(monoAlignPenalty)
         self.penalty_lambda = float(penalty_lambda) if monoAlignPenalty else 0.0
         n = ops.param_count(self.cfg)
-        self.off = ops.decoder_param_offset(self.cfg)
         self.flat = ctx.zeros(n)
         self.gradFlat = ctx.zeros(n)
+        names = [s for s in self.SEGS if (s not in ("WF", "bF", "U", "bU") or self.cfg["K"] > 0) and (s not in ("Wl", "bl", "Wm2", "bm2") or self.cfg["MLP"] == 2)]
+        segs = ops.param_segments(self.cfg)
+        assert len(segs) == len(names)
+        self._p, self._g = {}, {}
+        for name, (off, r, c) in zip(names, segs):
+            v = (lambda t: t[off:off + r * c].view(r, c) if c > 1 else t[off:off + r * c])
+            self._p[name], self._g[name] = v(self.flat), v(self.gradFlat)
+        self._order = names
+        pairs = [("WV", "bV"), ("Ws", "bs")] + ([("WF", "bF"), ("U", "bU")] if self.cfg["K"] > 0 else []) + \
+                [("we", "be"), ("Wy", "by"), ("Wc", "bc"), ("Wj", "bj"), ("Gz", None), ("Gr", None), ("Gh", None), ("Wm", "bm")] + \
+                ([("Wl", "bl"), ("Wm2", "bm2")] if self.cfg["MLP"] == 2 else []) + [("Wo", "bo")]
+        self.modules = [Param(ctx, w, self._p[w], self._g[w], self._p.get(b), self._g.get(b)) for w, b in pairs]
         self.reset()
-
-    def _views(self, flat):
-        return [flat[off:off + r * c].view(r, c) for off, r, c in ops.param_segments(self.cfg) if off >= self.off]
+        # adopt the values the caller's modules were constructed with
+        for name, src in zip(("Gz", "Gr", "Gh"), grus[0].modules):
+            self._p[name].copy_(src.weight)
+        self._p["Wm"].copy_(maxouts[0].linear.weight); self._p["bm"].copy_(maxouts[0].linear.bias)
+        if self.cfg["MLP"] == 2:
+            self._p["Wl"].copy_(linears[0].weight); self._p["bl"].copy_(linears[0].bias)
+            self._p["Wm2"].copy_(maxouts[1].linear.weight); self._p["bm2"].copy_(maxouts[1].linear.bias)
+        self._p["Wo"].copy_(linears[-1].weight); self._p["bo"].copy_(linears[-1].bias)
+        self._dropseed = 0
 
     def parameters(self):
-        return self._views(self.flat), self._views(self.gradFlat)
+        return [self._p[k] for k in self._order], [self._g[k] for k in self._order]
 
     def reset(self, stdv=None):
-        full = torch.from_numpy(ops.init_params(self.cfg, seed=1234)).to(self.flat.device)
-        self.flat.copy_(full)
-
-    @staticmethod
-    def _labels(y):
-        return y.argmax(dim=-1).to(torch.int32).contiguous()
+        for m in self.modules:
+            w = m.weight
+            fan_in = self.cfg["KF"] if m.name == "WF" else (w.shape[1] if w.dim() == 2 else w.shape[0])
+            b = _bound(stdv, fan_in)
+            w.uniform_(-b, b)
+            if m.bias is not None:
+                if m.name in ("WV", "U", "we"):
+                    m.bias.zero_()                    # TemporalConvolutionZeroBias.lua:34
+                else:
+                    m.bias.uniform_(-b, b)
 
     def updateOutput(self, input, lengths=None, tlens=None, dropmask=None):
         x, y = input
@@ -250,7 +375,11 @@ class Attention(Module):
             raise ops.S2SError("x must be 2d or 3d")
         self._batched = x.dim() == 3
         h = x.contiguous() if self._batched else x.contiguous().unsqueeze(0)
-        yl = self._labels(y if self._batched else y.unsqueeze(0))
+        yl = ops.labels_from_onehot(self.ctx, (y if self._batched else y.unsqueeze(0)).contiguous())     # labelmask -> labels on the device
+        B, T = yl.shape
+        if dropmask is None and self.dropout is not None and self.train and self.dropout.p > 0:          # nn.Dropout v2, training mode only
+            self._dropseed += 1
+            dropmask = ops.dropout_mask(self.ctx, (B, T, self.stateDepth + self.annotationDepth), self.dropout.p, seed=self._dropseed)
         self._args = (h, yl, lengths, tlens, dropmask)
         logp = ops.attention_forward(self.ctx, self.cfg, self.flat, h, yl, lengths=lengths, tlens=tlens, dropmask=dropmask, lam=self.penalty_lambda)
         self.output = logp if self._batched else logp[0]
@@ -278,7 +407,16 @@ class Attention(Module):
     def penalty(self):
         return self._get(ops.GET_PENALTY, 1)
 
+    @property
+    def Vh(self):
+        """decoder.Vh.output (timit/timit.lua:521)"""
+        h = self._args[0]
+        out = ops.attention_get(self.ctx, ops.GET_VH, (h.shape[0], h.shape[1], self.scoreDepth))
+        return type("VhNode", (), {"output": out if self._batched else out[0]})()
+
     def setpenalty(self, penalty):
+        if not self.monoAlignPenalty:
+            raise ops.S2SError("could not find penalty node")         # Attention.lua:263
         self.penalty_lambda = float(penalty)
 
     def BeamSearch(self, annotations, eos, K, maxseqlength):
@@ -311,9 +449,9 @@ class WeightNoise(Module):
 
 
 class AdaptiveWeightNoise(Module):
-    """weight = [mu ; log sigma^2]  (AdaptiveWeightNoise.lua:5-56)"""
+    """weight = [mu ; log sigma^2]  (AdaptiveWeightNoise.lua:5-56); sigma_init defaults to 1 as in the reference (:13)"""
 
-    def __init__(self, ctx, parameters, lam=1.0, sigma_init=0.075):
+    def __init__(self, ctx, parameters, lam=1.0, sigma_init=1.0):
         super().__init__(ctx)
         self.n = parameters.numel()
         self.lam = lam
@@ -337,10 +475,51 @@ class AdaptiveWeightNoise(Module):
 
 
 class TrainUtils:
+    """TrainUtils.lua:202-213 -- graph walkers + per-module weight post-processing (the arithmetic is in the library)"""
+
+    @staticmethod
+    def apply2graph(graph, func):
+        """visit every leaf below `graph` (TrainUtils.lua:137-184): modules with children -> descend, else func(leaf)"""
+        kids = getattr(graph, "modules", None)
+        if kids:
+            for m in kids:
+                TrainUtils.apply2graph(m, func)
+        else:
+            func(graph)
+
     @staticmethod
     def columnNormConstraint(m, maxval=1.0):
-        if getattr(m, "weight", None) is None:
+        """every ROW of m.weight with L2 norm >= maxval is divided by norm / maxval (TrainUtils.lua:52-104: norm(2,2) per row)"""
+        w = getattr(m, "weight", None)
+        if w is None:
             return
-        w = m.weight.view(m.weight.shape[0], -1) if m.weight.dim() != 2 else m.weight
-        if w.dim() == 2 and ops.rownorm_constraint(m.ctx, w, maxval):
+        if w.dim() != 2:
+            raise ops.S2SError("columnNormConstraint: apply it to the 2-D leaves (TrainUtils.columnNormConstraintGraph walks them); "
+                               f"got a {w.dim()}-D weight on {type(m).__name__}")
+        if ops.rownorm_constraint(m.ctx, w, maxval):
             raise ops.S2SError("found a nan")            # TrainUtils.lua:55-62
+
+    @staticmethod
+    def columnNormConstraintGraph(graph, maxval=1.0):     # timit/timit.lua:346-348
+        TrainUtils.apply2graph(graph, lambda m: TrainUtils.columnNormConstraint(m, maxval))
+
+    @staticmethod
+    def orthogonalize(m):
+        """m.weight (with m.bias as one more column) := orthonormal QR factor in the tall orientation (TrainUtils.lua:5-26)"""
+        w = getattr(m, "weight", None)
+        if w is None or w.dim() != 2:
+            return
+        b = getattr(m, "bias", None)
+        ops.orthogonalize(m.ctx, w, b if (b is not None and b.numel() == w.shape[0]) else None)
+
+    @staticmethod
+    def orthogonalizeGraph(graph):                        # librispeech/exp0_scriptchecker.lua:49-52
+        TrainUtils.apply2graph(graph, TrainUtils.orthogonalize)
+
+    @staticmethod
+    def optimConfigResets(optimConfig, resets, epoch):
+        """the epoch-indexed optimiser schedule of timit/timit.lua:496-502: at the start of `epoch`, entries of resets[epoch]
+        overwrite optimConfig in place"""
+        if resets and epoch in resets:
+            optimConfig.update(resets[epoch])
+        return optimConfig

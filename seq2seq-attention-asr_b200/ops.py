@@ -225,6 +225,19 @@ def lstm_param_count(din, H, peepholes):
     return int(_lib.load().s2s_lstm_param_count(din, H, int(peepholes)))
 
 
+def lstm_segments(din, H, peepholes):
+    """[(name, (weight offset, rows, cols), bias offset)] of the flat LSTM parameter block, in the order the reference module's
+    parameters() yields (LSTM.lua:25-36): per gate i, f, g, o: Linear(in,out), Linear(out,out) [, peephole Linear(out,out)], each with bias"""
+    segs, o = [], 0
+    for gi, g in enumerate("ifgo"):
+        segs.append((g + ".x", (o, H, din), o + H * din)); o += H * din + H
+        segs.append((g + ".h", (o, H, H), o + H * H)); o += H * H + H
+        if peepholes and g != "g":
+            segs.append((g + ".c", (o, H, H), o + H * H)); o += H * H + H
+    assert o == lstm_param_count(din, H, peepholes)
+    return segs
+
+
 def lstm_seq_forward(ctx, P, x, H, peepholes=False, lengths=None, reverse=False):
     B, L, Din = x.shape
     assert P.numel() == lstm_param_count(Din, H, peepholes)
@@ -355,6 +368,13 @@ def adadelta(ctx, x, g, v, a, rho=0.95, eps=1e-8):
     check(ctx.lib.s2s_adadelta(ctx.h, _f(x), _f(g), _f(v), _f(a), x.numel(), rho, eps))
 
 
+def orthogonalize(ctx, W, bias=None):
+    """TrainUtils.orthogonalize (TrainUtils.lua:5-26) in place on a 2-D weight (and its bias, appended as a column)."""
+    assert W.dim() == 2
+    check(ctx.lib.s2s_orthogonalize(ctx.h, _f(W), W.shape[0], W.shape[1], _f(bias)))
+    return W
+
+
 def rownorm_constraint(ctx, W, maxval=1.0):
     flag = C.c_int(0)
     check(ctx.lib.s2s_rownorm_constraint(ctx.h, _f(W), W.shape[0], W.shape[1], maxval, C.byref(flag)))
@@ -413,6 +433,20 @@ def vgg_backward(ctx, cfg, P, X, dh, dP=None, need_dx=False):
     dX = torch.empty_like(X) if need_dx else None
     check(ctx.lib.s2s_vgg_backward(ctx.h, C.byref(c), _f(P), _f(dP), B, T, F, _f(dh), _f(dX)))
     return dP, dX
+
+
+def labels_from_onehot(ctx, onehot):
+    """labelmask [..., V] (float one-hot, timit/timit.lua:262) -> int32 labels [...]; -1 for all-zero rows"""
+    V = onehot.shape[-1]
+    labels = torch.empty(onehot.shape[:-1], dtype=torch.int32, device=onehot.device)
+    check(ctx.lib.s2s_labels_from_onehot(ctx.h, _f(onehot), labels.numel(), V, _i(labels)))
+    return labels
+
+
+def onehot(ctx, labels, V):
+    out = torch.empty(*labels.shape, V, dtype=torch.float32, device=labels.device)
+    check(ctx.lib.s2s_onehot(ctx.h, _i(labels), labels.numel(), V, _f(out)))
+    return out
 
 
 def nll_grad_seed(ctx, logp, labels, tlens=None, flags=0, nll=None, dlogp=None, want_grad=True):

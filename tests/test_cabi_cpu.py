@@ -86,3 +86,45 @@ def test_edit_distance_matches_wagner_fischer():
     for _ in range(50):
         a = rng.integers(0, 5, rng.integers(0, 30)); b = rng.integers(0, 5, rng.integers(0, 30))
         assert s2s.edit_distance(a, b) == wf(list(a), list(b))
+
+
+def test_lua_ffi_cdef_matches_the_header():
+    """lua/s2s_ffi.lua's cdef block is generated from include/s2s_b200.h: every declared function appears there with the same
+    number of parameters (the shims cannot be executed in this image -- no LuaJIT / Torch7 -- so drift is caught textually)."""
+    import re
+    import s2s_b200 as s2s
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "s2s_b200.h")).read(), flags=re.S)
+    lua = open(os.path.join(root, "seq2seq-attention-asr_b200", "lua", "s2s_ffi.lua")).read()
+    cdef = lua[lua.index("ffi.cdef[["):lua.index("]]")]
+
+    def protos(txt):
+        out = {}
+        for m in re.finditer(r"\b(s2s_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", txt, flags=re.S):
+            args = m.group(2).strip()
+            out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+        return out
+    h, l = protos(hdr), protos(cdef)
+    assert set(s2s.declared_symbols()) <= set(l), sorted(set(s2s.declared_symbols()) - set(l))
+    assert all(h[k] == l[k] for k in h), {k: (h[k], l[k]) for k in h if h[k] != l.get(k)}
+
+
+def test_lua_shims_cover_the_reference_module_surface():
+    """every custom class of the reference's root library that is on the path has a shim that registers the same torch
+    class name, and lua/TrainUtils.lua exports the reference's table (TrainUtils.lua:202-213)"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lua = os.path.join(root, "seq2seq-attention-asr_b200", "lua")
+    want = {"Attention": "nn.Attention", "RNNAttention": "nn.RNNAttention", "Recurrent": "nn.Recurrent", "GRU": "nn.GRU", "LSTM": "nn.LSTM",
+            "RNN": "nn.RNN", "LinearZeroBias": "nn.LinearZeroBias", "TemporalConvolutionZeroBias": "nn.TemporalConvolutionZeroBias",
+            "WeightNoise": "nn.WeightNoise", "AdaptiveWeightNoise": "nn.AdaptiveWeightNoise"}
+    for f, cls in want.items():
+        txt = open(os.path.join(lua, f + ".lua")).read()
+        assert re.search(r"torch\.class\('%s'" % re.escape(cls), txt), f
+        for method in ("updateOutput", "updateGradInput"):
+            if f not in ("WeightNoise", "AdaptiveWeightNoise"):
+                assert ":" + method in txt, (f, method)
+    tu = open(os.path.join(lua, "TrainUtils.lua")).read()
+    for name in ("orthogonalize", "orthogonalizeGraph", "checkOrthogonalization", "columnNormConstraint", "columnNormConstraintGraph",
+                 "checkColumnNormConstraint", "checkColumnNormConstraintGraph", "apply2graph", "getnorms", "checkoutput"):
+        assert re.search(r"function T\.%s\b" % name, tu), name

@@ -81,7 +81,7 @@ def test_two_ranks_reproduce_the_single_rank_big_batch(overlap):
     procs = [mpc.Process(target=_run_rank, args=(r, 2, port, overlap, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
     for p in procs:
         p.join(120)
         assert p.exitcode == 0

@@ -36,7 +36,13 @@ def test_attention_module_sgd_equals_batch(s2s, gctx, orc64):
     # the reference notebook's invariant (Attention.ipynb:1202/1763): batch rows == SGD-mode result
     nn = s2s.nn
     rng = np.random.default_rng(1)
-    att = nn.Attention(gctx, None, None, 128, 4, 3, 64, 256, 11, False, 0.0, mlpDepth=8, maxoutWindow=3)
+    # built the way timit/model_chorowski_baseline.lua:48-71 builds it: a GRU(st, st) recurrent part and a Maxout-Linear-LogSoftMax MLP
+    decoder_recurrent = nn.Sequential(gctx, nn.GRU(gctx, 64, 64))
+    decoder_mlp = nn.Sequential(gctx, nn.Maxout(gctx, 64 + 256, 8, 3), nn.Linear(gctx, 8, 11), nn.LogSoftMax(gctx))
+    att = nn.Attention(gctx, decoder_recurrent, decoder_mlp, 128, 4, 3, 64, 256, 11, False, 0.0)
+    assert att.cfg["M"] == 8 and att.cfg["MW"] == 3 and att.cfg["MLP"] == 1 and att.cfg["NL"] == 0
+    # the sub-modules' initial values are adopted (a pre-loaded sub-module keeps its weights)
+    assert torch.equal(att._p["Gz"], decoder_recurrent.modules[0].weight[0]) and torch.equal(att._p["Wo"], decoder_mlp.modules[1].weight)
     L, T, V = 37, 5, 11
     h = rng.standard_normal((2, L, 256)) * 0.5
     lab = rng.integers(0, V, (2, T))
