@@ -335,6 +335,48 @@ def run_cfg4(args):
         dist.destroy_process_group()
 
 
+# -------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4] and the metric's second half ("attention HBM GB/s"): the attention-step sweep over encoder length and
+# batch (scoring + softmax + context, forward and backward), L2 flushed between launches, content (K = 0) and location-aware (k = 10)
+def run_cfg5(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    import attn_sweep
+    import s2s_b200 as s2s
+    ctx = s2s.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    l0 = ctx.launches
+    res = {kf: attn_sweep.run_sweep(kf, quick=False, verbose=False, ctx=ctx) for kf in (0, 10)}
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    hbm, tf, how = peaks()
+
+    def best(rows, key):
+        r = max(rows, key=lambda r: r[key])
+        return {"B": r["B"], "L": r["L"], "GB/s": r[key], "frac": r[key] / hbm}
+    loc, con = res[10]["rows"], res[0]["rows"]
+    top = max(loc, key=lambda r: (r["mbytes"] * 2) / (r["fwd_us"] + r["bwd_us"]))
+    value = 1e-3 * (4.0 * top["B"] * (2 * top["L"] * 1024 + 8 * top["L"] + 3 * 1024)) / ((top["fwd_us"] + top["bwd_us"]) * 1e-6) / 1e6
+    line = {"metric": "attention_step_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": 1, "steps": 10, "warmup": 3,
+            "ms_per_step": (top["fwd_us"] + top["bwd_us"]) * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "cfg5: attention-step sweep (scoring + softmax + context, forward + backward), S = A = 512, L in {100..2000} x B in {1..256}, "
+                                   "location-aware k = 10 (headline: best forward+backward point) and content-only; algorithmic bytes A_f + A_b,min (SURVEY 8d)",
+                       "l2": "flushed before every timed launch (256 MiB write)", "headline_point": {"B": top["B"], "L": top["L"]}},
+            "roofline": {"bound": "hbm", "achieved": value, "peak": hbm, "unit": "GB/s", "frac": value / hbm, "traffic": None, "peak_source": how},
+            "best": {"location_fwd": best(loc, "fwd_gbs"), "location_bwd": best(loc, "bwd_gbs"), "content_fwd": best(con, "fwd_gbs"), "content_bwd": best(con, "bwd_gbs")},
+            "points_at_or_above_60pct": {"location_fwd": sum(r["fwd_frac"] >= 0.6 for r in loc), "location_bwd": sum(r["bwd_frac"] >= 0.6 for r in loc),
+                                         "content_fwd": sum(r["fwd_frac"] >= 0.6 for r in con), "content_bwd": sum(r["bwd_frac"] >= 0.6 for r in con), "of": len(loc)},
+            "sweep": {"location_k10": loc, "content": con}, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": None,
+            "e2e": None}
+    emit_json(json.dumps(line))
+
+
 def dbg(msg):
     if os.environ.get("S2S_BENCH_DEBUG"):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
@@ -360,10 +402,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dbg("process group up")
     ctx = s2s.Context(local)
-    # the data path's collective is the C ABI's own NCCL plane (csrc/dp_nccl.cu): s2s_model_fwdbwd reduces the gradient buckets
-    # itself on a side stream under the remaining backward pass; torch.distributed only ships the 128-byte id and carries the
-    # barrier / max-over-ranks of the timing
-    dp_overlap = not os.environ.get("S2S_BENCH_DP_PLAIN")
+    # the data path's collective is the C ABI's own NCCL plane (csrc/dp_nccl.cu): one s2s_dp_allreduce of the flat gradient after the
+    # replayed forward+backward graph; torch.distributed only ships the 128-byte id and carries the barrier / max-over-ranks of the timing.
+    # S2S_BENCH_DP_OVERLAP=1 selects the bucketed overlap inside s2s_model_fwdbwd (verified eager; its captured NCCL nodes fault under graph
+    # replay with NCCL 2.28.9 -- DESIGN.md 4 -- so it is not the default)
+    dp_overlap = bool(os.environ.get("S2S_BENCH_DP_OVERLAP"))
     if world > 1:
         s2s.dp.init(ctx, rank, world, overlap=dp_overlap)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -649,6 +692,8 @@ def main():
         run_reference(args)
     elif args.config == "cfg4":
         run_cfg4(args)
+    elif args.config == "cfg5":
+        run_cfg5(args)
     else:
         run_ours(args)
 

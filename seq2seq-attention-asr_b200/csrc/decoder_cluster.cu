@@ -53,7 +53,7 @@ struct DcSmem {
     float gz[128 * 32 * 4];
     float gh[128 * 16 * 4];
     // all-gathered vectors
-    float q_full[BG][DC_S];        // holds 2 log2(e) q (see dc_tanh4_dot)
+    alignas(16) float q_full[BG][DC_S];        // holds 2 log2(e) q (see dc_tanh4_dot)
     float c_full[BG][DC_A];
     float s_full[BG][DC_ST];
     float u_full[BG][DC_ST];
@@ -62,18 +62,18 @@ struct DcSmem {
     float recv_c[DC_CS][BG][32];
     float4 recv_st[DC_CS][BG];
     float part[16][BG][32];        // per-warp (K-slice) partial sums of a mat-vec phase
-    float e_s[BG][DC_RMAX], p_s[BG][DC_RMAX + 16], ap_s[BG][DC_RMAX];     // p_s: zero past the slice (the context loop reads blocks of 20)
-    float w_s[DC_S];
-    float stage[BG][32];
-    float zbuf[BG][16];
+    alignas(16) float e_s[BG][DC_RMAX], p_s[BG][DC_RMAX + 16], ap_s[BG][DC_RMAX];     // p_s: zero past the slice (the context loop reads blocks of 20)
+    alignas(16) float w_s[DC_S];
+    alignas(16) float stage[BG][32];
+    alignas(16) float zbuf[BG][16];
     float scl_own[BG];
     int l0_s[BG], nr_s[BG], len_s[BG];
     int frow[BG * DC_RMAX];        // this CTA's frames, flattened over its utterances: row of Vh / h ((b0+b) Lmax + l)
     short fb[BG * DC_RMAX], fr[BG * DC_RMAX];      // utterance and frame-within-slice of a flattened frame
     uint64_t bar[6];               // q, cp, c, u, rs, s
     // location-aware term (Attention.lua:75-99, folded): 2 log2(e) U W_F, and alpha_{t-1} over this CTA's frames plus the filter halo
-    float uw_s[LOC ? DC_KFMAX * DC_S : 4];
-    unsigned long long aph_s[LOC ? BG : 1][DC_RMAX + 16];    // {a, a} pairs (packed FFMA2 operands)
+    alignas(16) float uw_s[LOC ? DC_KFMAX * DC_S : 4];
+    alignas(16) unsigned long long aph_s[LOC ? BG : 1][DC_RMAX + 16];    // {a, a} pairs (packed FFMA2 operands)
 };
 enum { BAR_Q = 0, BAR_CP, BAR_C, BAR_U, BAR_RS, BAR_S };
 
@@ -575,7 +575,7 @@ struct DcBwdSmem {
     float wb[64 * 32 * 4];         // phase B rows: G_h^T   [own 16 | ST + own 16] x K = ST,   k-major
     float wc[128 * 32 * 4];        // phase C rows: G_zr^T  [own 16 | ST + own 16] x K = 2 ST
     float wd[64 * 32 * 4];         // phase D rows: W_jc^T  [own 32]               x K = ST
-    float dq_full[BG][DC_S];
+    alignas(16) float dq_full[BG][DC_S];
     float dahz_full[BG][2 * DC_ST];        // dah | daz
     float dar_full[BG][DC_ST];
     float du_full[BG][DC_ST];
@@ -586,18 +586,18 @@ struct DcBwdSmem {
         float recv_dq[DC_CS][BG][32];      // reduce-scatter receive (phase F): never live at the same time (see the exchange order)
     };
     float4 recv_dot[DC_CS][BG];
-    float al_s[BG][DC_RMAX], dal_s[BG][DC_RMAX], de_s[BG][DC_RMAX + 16];    // de_s: zero past the slice (phase F reads blocks of 20)
-    float w_s[DC_S];
-    float stage[BG][32], stage2[BG][32];
-    float carry_s[BG][16], duh_s[BG][16];
+    alignas(16) float al_s[BG][DC_RMAX], dal_s[BG][DC_RMAX], de_s[BG][DC_RMAX + 16];    // de_s: zero past the slice (phase F reads blocks of 20)
+    alignas(16) float w_s[DC_S];
+    alignas(16) float stage[BG][32], stage2[BG][32];
+    alignas(16) float carry_s[BG][16], duh_s[BG][16];
     int l0_s[BG], nr_s[BG], len_s[BG];
     int frow[BG * DC_RMAX];
     short fb[BG * DC_RMAX], fr[BG * DC_RMAX];
     uint64_t bar[7];
-    float cin_s[BG][DC_RMAX];      // carry into d alpha_t of this CTA's frames: penalty of step t, penalty and location term of step t+1
+    alignas(16) float cin_s[BG][DC_RMAX];      // carry into d alpha_t of this CTA's frames: penalty of step t, penalty and location term of step t+1
     float pg_s[2][BG];             // lambda where the penalty of step t (slot t & 1) is active
-    float uw_s[LOC ? DC_KFMAX * DC_S : 4];             // 2 log2(e) U W_F
-    float apw_s[LOC ? BG : 1][DC_RMAX + 32];           // alpha_{t-1} over this CTA's frames plus the filter halo
+    alignas(16) float uw_s[LOC ? DC_KFMAX * DC_S : 4];             // 2 log2(e) U W_F  (read as float4: the members above it do not add up to a multiple of 16 bytes for every BG)
+    alignas(16) float apw_s[LOC ? BG : 1][DC_RMAX + 32];           // alpha_{t-1} over this CTA's frames plus the filter halo
 };
 enum { BB_X1 = 0, BB_X2, BB_X3, BB_X4, BB_X5, BB_X6A, BB_X6B };
 

@@ -22,6 +22,8 @@ struct GruSeqParams {
 
 // second-generation cluster kernels (gru_seq2.cu)
 int gru_cluster2_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
+// third-generation kernels: warp-specialised, software-pipelined sub-batches (gru_seq3.cu)
+int gru_cluster3_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
 
 // y [B,Lmax,ndir*H]; save [B,Lmax,ndir,4H] (z | r | h~ | r*h_prev)
 int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int reverse, const float* x, int ldx,

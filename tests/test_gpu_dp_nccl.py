@@ -29,6 +29,8 @@ def _run_rank(rank, world, port, overlap, q):
     torch.cuda.set_device(rank)
     store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0))
     ctx = s2s.Context(rank)
+    if overlap:
+        ctx.set_graphs(False)      # the bucketed overlap is verified eager: NCCL nodes captured into the step's CUDA graph fault on replay
     s2s.dp.init(ctx, rank, world, store=store, overlap=overlap)
     assert s2s.dp.nccl_world(ctx) == world
     dev = torch.device("cuda", rank)

@@ -38,7 +38,10 @@ def test_attention_module_matches_oracle(s2s, gctx, orc64, K, KF, lam, drop, ext
 @pytest.mark.parametrize("B,L,T,lam,extra", [(3, 70, 6, 0.03, {}), (3, 70, 6, 0.0, {}), (9, 40, 5, 0.0, {}), (16, 33, 4, 0.02, dict(MLP=2)),
                                              (16, 33, 4, 0.0, dict(MLP=2)), (37, 24, 3, 0.0, {}), (2, 400, 3, 0.0, {}),
                                              # location-aware term inside the forward cluster kernel (filter halo across CTAs)
-                                             (4, 70, 6, 0.0, dict(K=16, KF=10)), (7, 45, 5, 0.02, dict(K=3, KF=5)), (2, 300, 4, 0.0, dict(K=2, KF=4))])
+                                             (4, 70, 6, 0.0, dict(K=16, KF=10)), (7, 45, 5, 0.02, dict(K=3, KF=5)), (2, 300, 4, 0.0, dict(K=2, KF=4)),
+                                             # every utterances-per-cluster variant of the location-aware kernels (BG = 3, 4, 5: a shared-memory
+                                             # member read as float4 was 16-byte aligned only for some BG -- round-2 regression)
+                                             (17, 40, 4, 0.0, dict(K=16, KF=10)), (23, 33, 3, 0.02, dict(K=3, KF=5)), (30, 24, 3, 0.0, dict(K=16, KF=10))])
 def test_attention_module_cluster_decoder(s2s, gctx, orc64, B, L, T, lam, extra):
     cfg = dict(dict(D=13, H=256, NL=0, S=512, ST=256, V=11, K=0, KF=4, M=8, MW=3), **extra)
     _check_attention_module(s2s, gctx, orc64, cfg, B, L, T, lam, False, short=True)
