@@ -396,7 +396,8 @@ class _Writer:
         return off
 
     def dataset(self, arr):
-        arr = np.ascontiguousarray(arr)
+        arr = np.asarray(arr)
+        arr = arr if arr.ndim == 0 else np.ascontiguousarray(arr)     # (ascontiguousarray would promote a scalar to 1-d)
         if arr.dtype.byteorder == ">":
             arr = arr.astype(arr.dtype.newbyteorder("<"))
         k = arr.dtype.kind
