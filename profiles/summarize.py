@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns raw Nsight Compute output (gpurun_out/, scratch) into the small tracked summaries under profiles/.
   python profiles/summarize.py launches <launches.csv> <out.md>        per-kernel time shares of one bench run
-  python profiles/summarize.py full <tag> <prof_*.ncu-rep ...>         key counters of `ncu --set full` captures -> profiles/<tag>.json + .md
+  python profiles/summarize.py full <tag> <prof_*.ncu-rep | raw_*.csv ...>   key counters of `ncu --set full` captures -> profiles/<tag>.json + .md
 """
 import collections
 import csv
@@ -49,7 +49,8 @@ def launches(path, out):
 def full(tag, reps):
     out = []
     for rep in reps:
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # a .ncu-rep, or the `ncu -i X.ncu-rep --page raw --csv` export made on the GPU box (the reports themselves are too large to bring back)
+        txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         if len(rows) < 3:
             continue

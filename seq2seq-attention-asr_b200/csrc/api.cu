@@ -48,7 +48,7 @@ int s2s_ctx_destroy(s2s_ctx* ctx) {
     ctx->persist.release();
     if (ctx->counters) cudaFree(ctx->counters);
     for (int i = 0; i < 2; i++) if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
-    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 6; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     dp_state_free(ctx);
     delete ctx->dec;

@@ -72,7 +72,7 @@ struct GraphCache {
 };
 
 // prepared (hi/lo-split, K-contiguous) GEMM operands that stay valid for the duration of a TcCacheScope (gemm_tc.cu)
-struct TcCacheEntry { const float* src; int K, cols, ld; bool transposed; const float* hi; const float* lo; int ld_hi, ld_lo; };
+struct TcCacheEntry { const float* src; int K, cols, ld; bool transposed; const float* hi; const float* lo; int ld_hi, ld_lo; bool mn; };
 
 struct DecoderState;   // decoder.cu
 struct VggState;       // vgg.cu
@@ -86,7 +86,7 @@ struct s2s_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t side[2] = {nullptr, nullptr};     // internal streams for independent branches
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     int64_t launches = 0;
     int64_t kcount[S2S_KC_N] = {0};   // launches per kernel class (s2s_ctx_kernel_count): which path ran is testable

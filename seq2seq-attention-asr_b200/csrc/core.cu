@@ -222,7 +222,7 @@ int s2s_ctx_create(int device, void* stream, s2s_ctx** out) {
         S2S_CUDA(cudaStreamCreateWithPriority(&c->side[0], cudaStreamNonBlocking, hi));
         S2S_CUDA(cudaStreamCreateWithPriority(&c->side[1], cudaStreamNonBlocking, lo));
     }
-    for (int i = 0; i < 4; i++) S2S_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 6; i++) S2S_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
     S2S_CUDA(cudaMalloc((void**)&c->counters, 4096 * sizeof(unsigned)));
     S2S_CUDA(cudaMemset(c->counters, 0, 4096 * sizeof(unsigned)));
     *out = c;

@@ -526,19 +526,46 @@ __global__ void loc_fold_kernel(const float* __restrict__ U, const float* __rest
 }
 // gradients of the folded location parameters back to U, WF, bF:
 //   dU[i,m] += sum_j dUW[j][i] WF[m,j] + dUb[i] bF[m] ; dWF[m,j] += sum_i U[i,m] dUW[j][i] ; dbF[m] += sum_i U[i,m] dUb[i]
-__global__ void loc_unfold_kernel(const float* __restrict__ U, const float* __restrict__ WF, const float* __restrict__ bF,
-                                  const float* __restrict__ duw, const float* __restrict__ dub, int S, int K, int KF,
-                                  float* __restrict__ dU, float* __restrict__ dWF, float* __restrict__ dbF) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S) return;
-    const float db = dub[i];
-    for (int m = 0; m < K; m++) {
-        float a = db * bF[m];
-        for (int j = 0; j < KF; j++) a = fmaf(duw[(size_t)j * S + i], WF[(size_t)m * KF + j], a);
+// one block per feature map m: the sums over the S score units are block reductions (no atomics: 17 values per block)
+constexpr int LOC_MAXKF = 16;        // filter taps (attention.cu)
+__global__ void __launch_bounds__(256)
+loc_unfold_kernel(const float* __restrict__ U, const float* __restrict__ WF, const float* __restrict__ bF,
+                  const float* __restrict__ duw, const float* __restrict__ dub, int S, int K, int KF,
+                  float* __restrict__ dU, float* __restrict__ dWF, float* __restrict__ dbF) {
+    __shared__ float red[8][LOC_MAXKF + 1];
+    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float acc[LOC_MAXKF + 1];
+#pragma unroll
+    for (int j = 0; j <= LOC_MAXKF; j++) acc[j] = 0.f;
+    const float bm = bF[m];
+    for (int i = tid; i < S; i += 256) {
+        const float db = dub[i], u = U[(size_t)i * K + m];
+        float a = db * bm;
+#pragma unroll
+        for (int j = 0; j < LOC_MAXKF; j++) {
+            if (j < KF) {
+                const float g = duw[(size_t)j * S + i];
+                a = fmaf(g, WF[(size_t)m * KF + j], a);
+                acc[j] = fmaf(u, g, acc[j]);
+            }
+        }
+        acc[LOC_MAXKF] = fmaf(u, db, acc[LOC_MAXKF]);
         dU[(size_t)i * K + m] += a;
-        const float u = U[(size_t)i * K + m];
-        atomicAdd(dbF + m, u * db);
-        for (int j = 0; j < KF; j++) atomicAdd(dWF + (size_t)m * KF + j, u * duw[(size_t)j * S + i]);
+    }
+#pragma unroll
+    for (int j = 0; j <= LOC_MAXKF; j++) {
+        float v = acc[j];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+    if (tid <= LOC_MAXKF) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) v += red[w][tid];
+        if (tid < KF) dWF[(size_t)m * KF + tid] += v;
+        else if (tid == LOC_MAXKF) dbF[m] += v;
     }
 }
 
@@ -691,7 +718,8 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
 // backward
 // =================================================================================================
 int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, const float* h, const int* lengths, int B, int Lmax,
-                     const int* labels, const int* tlens, int T, const float* dropmask, float lambda, const float* dlogp, float* dh) {
+                     const int* labels, const int* tlens, int T, const float* dropmask, float lambda, const float* dlogp, float* dh,
+                     bool defer_wgrad) {
     S2S_REQUIRE(ctx->dec && ctx->dec->valid, "attention backward called without a preceding forward on this context");
     DecoderState& d = *ctx->dec;
     S2S_REQUIRE(d.B == B && d.Lmax == Lmax && d.T == T && d.Y.n == Y.n, "attention backward: shapes differ from the preceding forward");
@@ -749,28 +777,52 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
         S2S_TRY(gemm_f32(ctx, false, false, A, ST, ST, 1.f, WjcT, ST, GhT + (size_t)ST * ST, ST, 0.f, W3c + 2 * ST, 3 * ST, nullptr, GemmBatch(), 1, 1));
     }
 
+    // location path on the cluster kernel: the Jacobian of the energies w.r.t. alpha_{t-1} does not depend on any gradient -> one
+    // throughput-bound launch over all steps (rows t = 0 and padded steps stay zero: they only ever multiply de = 0).  It needs nothing from
+    // the MLP backward below, so with S2S_OVERLAP (default) it runs beside it on the side stream and joins before the time loop.
+    int padl = 0;
+    if (KF > 0) pad_lr(KF, &padl);
+    const bool cluster_ok = decoder_cluster_backward_eligible(Y, Lmax, lambda);
+    float* V1 = nullptr;
+    struct StreamGuard {      // whatever path leaves this function, the context's stream is restored
+        s2s_ctx* c; cudaStream_t s; bool on;
+        ~StreamGuard() { if (on) c->stream = s; }
+    } v1_guard{ctx, st, false};
+    if (cluster_ok && KF > 0) {
+        static int overlap = -1;
+        if (overlap < 0) { const char* e = getenv("S2S_OVERLAP"); overlap = e ? atoi(e) : 1; }
+        S2S_ALLOC(V1, ar, float, BT * Lmax * KF);
+        if (overlap && ctx->side[1] && st != ctx->side[1] && !ctx->wgrad_join_pending) {
+            S2S_CUDA(cudaEventRecord(ctx->ev[2], st));
+            S2S_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev[2], 0));
+            v1_guard.on = true;
+            ctx->stream = ctx->side[1];
+        }
+        S2S_CUDA(cudaMemsetAsync(V1, 0, BT * Lmax * KF * sizeof(float), ctx->stream));
+        S2S_TRY(attn_v1(ctx, d.Vh, d.q, P + Y.we.off, d.uw, d.alpha, lengths, tlens, B, Lmax, T, S, KF, padl, V1));
+        if (v1_guard.on) {
+            S2S_CUDA(cudaEventRecord(ctx->ev[3], ctx->side[1]));
+            ctx->stream = st;
+        }
+    }
+
     // ---- time-batched MLP backward (model_chorowski_baseline.lua:53-59 reversed) ----------------
     logsoftmax_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT, 8), 256, 0, st>>>(d.logp, dlogp, (int64_t)BT, V, tlens, T, dlogits);
     S2S_LAUNCH_CHECK(ctx);
-    S2S_TRY(gemm_f32(ctx, true, false, V, M, iBT, 1.f, dlogits, V, Y.MLP == 2 ? d.mo2 : d.mo, M, 1.f, G + Y.Wo.off, M));
-    S2S_TRY(colsum_add(ctx, dlogits, BT, V, V, G + Y.bo.off));
+    // (only the data path is on the critical chain to the time loop; the weight gradients of these layers are formed with the other
+    // deferred products after it)
     S2S_TRY(gemm_f32(ctx, false, false, iBT, M, V, 1.f, dlogits, V, P + Y.Wo.off, M, 0.f, dmo, M));
+    float *dl1 = nullptr, *dm2 = nullptr;
     if (Y.MLP == 2) {   // second Maxout and Linear(M,M) backward (librispeech/model_vgg.lua:78-79)
-        float* dl1;
         S2S_ALLOC(dl1, ar, float, BT * M);
-        maxout_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(dmo, d.midx2, (int64_t)BT, M, MW, dm);
+        S2S_ALLOC(dm2, ar, float, BT * M * MW);
+        maxout_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(dmo, d.midx2, (int64_t)BT, M, MW, dm2);
         S2S_LAUNCH_CHECK(ctx);
-        S2S_TRY(gemm_f32(ctx, true, false, M * MW, M, iBT, 1.f, dm, M * MW, d.l1, M, 1.f, G + Y.Wm2.off, M));
-        S2S_TRY(colsum_add(ctx, dm, BT, M * MW, M * MW, G + Y.bm2.off));
-        S2S_TRY(gemm_f32(ctx, false, false, iBT, M, M * MW, 1.f, dm, M * MW, P + Y.Wm2.off, M, 0.f, dl1, M));
-        S2S_TRY(gemm_f32(ctx, true, false, M, M, iBT, 1.f, dl1, M, d.mo, M, 1.f, G + Y.Wl.off, M));
-        S2S_TRY(colsum_add(ctx, dl1, BT, M, M, G + Y.bl.off));
+        S2S_TRY(gemm_f32(ctx, false, false, iBT, M, M * MW, 1.f, dm2, M * MW, P + Y.Wm2.off, M, 0.f, dl1, M));
         S2S_TRY(gemm_f32(ctx, false, false, iBT, M, M, 1.f, dl1, M, P + Y.Wl.off, M, 0.f, dmo, M));
     }
     maxout_bwd_kernel<<<(unsigned)ceil_div64((int64_t)BT * M, 256), 256, 0, st>>>(dmo, d.midx, (int64_t)BT, M, MW, dm);
     S2S_LAUNCH_CHECK(ctx);
-    S2S_TRY(gemm_f32(ctx, true, false, M * MW, ST + A, iBT, 1.f, dm, M * MW, d.scm, ST + A, 1.f, G + Y.Wm.off, ST + A, nullptr, GemmBatch(), 4));
-    S2S_TRY(colsum_add(ctx, dm, BT, M * MW, M * MW, G + Y.bm.off));
     S2S_TRY(gemm_f32(ctx, false, false, iBT, ST + A, M * MW, 1.f, dm, M * MW, P + Y.Wm.off, ST + A, 0.f, dsc, ST + A));
     if (dropmask) {
         const int64_t n = (int64_t)BT * (ST + A);
@@ -781,20 +833,11 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     // ---- time loop, t = T-1 .. 0 (RNNAttention.lua:233) -------------------------------------------
     S2S_CUDA(cudaMemsetAsync(ds_carry, 0, (size_t)B * ST * sizeof(float), st));      // Recurrent.lua:134
     if (carry_alpha) S2S_CUDA(cudaMemsetAsync(dac[0], 0, (size_t)B * Lmax * sizeof(float), st));
-    int padl = 0;
-    if (KF > 0) pad_lr(KF, &padl);
     const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST, lddA = (int64_t)T * 3 * ST;
     const int eb = ceil_div(B * ST, 256);
     bool clustered = false;      // the whole loop in one persistent cluster kernel (decoder_cluster.cu) when the shapes allow
-    if (decoder_cluster_backward_eligible(Y, Lmax, lambda)) {
-        float* V1 = nullptr;
-        if (KF > 0) {
-            // location path: the Jacobian of the energies w.r.t. alpha_{t-1} does not depend on any gradient -> one throughput-bound launch
-            // over all steps before the latency-bound loop (rows t = 0 and padded steps stay zero: they only ever multiply de = 0)
-            S2S_ALLOC(V1, ar, float, BT * Lmax * KF);
-            S2S_CUDA(cudaMemsetAsync(V1, 0, BT * Lmax * KF * sizeof(float), st));
-            S2S_TRY(attn_v1(ctx, d.Vh, d.q, P + Y.we.off, d.uw, d.alpha, lengths, tlens, B, Lmax, T, S, KF, padl, V1));
-        }
+    if (cluster_ok) {
+        if (v1_guard.on) { S2S_CUDA(cudaStreamWaitEvent(st, ctx->ev[3], 0)); v1_guard.on = false; }
         S2S_TRY(decoder_cluster_backward(ctx, Y, P, h, lengths, B, Lmax, T, lambda, d, WsT, GhT, GzrT, WjcT, dsc, V1, dA, du_all, dc_all, dq_all, de_all, &clustered));
     }
     // elementwise GRU backward of the LAST step (ds_carry = 0); later steps get it fused into the W_s product
@@ -852,7 +895,54 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
         }
     }
 
+    // Nothing downstream reads the decoder's weight gradients before the gradient step, only dh gates the encoder backward.  With
+    // defer_wgrad (model_backward, S2S_OVERLAP=1) the critical path below is attn_dvh -> dh and every weight-gradient product moves to the
+    // low-priority side stream with a grid limited to the SMs the cluster kernels leave idle, under the encoder's recurrences
+    // (same mechanism as gru_seq_backward; the caller joins through gru_seq_wgrad_join).
+    static int overlap = -1;
+    if (overlap < 0) { const char* e = getenv("S2S_OVERLAP"); overlap = e ? atoi(e) : 1; }
+    const bool fork = defer_wgrad && overlap && ctx->side[1] && st != ctx->side[1];
+    struct SwapGuard {
+        s2s_ctx* c; cudaStream_t s; bool on;
+        ~SwapGuard() { if (on) { c->stream = s; c->gemm_sm_limit = 0; } }
+    } guard{ctx, st, false};
+    const int side_limit = ctx->sm_count - 112 > 16 ? ctx->sm_count - 112 : 0;
+    auto to_side = [&]() { if (fork) { guard.on = true; ctx->stream = ctx->side[1]; ctx->gemm_sm_limit = side_limit; } };
+    auto to_main = [&]() { if (fork) { ctx->stream = st; ctx->gemm_sm_limit = 0; guard.on = false; } };
+    if (fork) {
+        S2S_CUDA(cudaEventRecord(ctx->ev[2], st));
+        S2S_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev[2], 0));
+    }
+
+    // ---- critical path: deferred dVh / dw_e (/ dUW), then dh ---------------------------------------
+    const int BL = B * Lmax;
+    {
+        AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw; loc.alpha_prev = d.alpha;
+        S2S_TRY(attn_dvh(ctx, d.Vh, d.q, de_all, P + Y.we.off, lengths, tlens, B, Lmax, T, S, loc, dVh, G + Y.we.off, duw));
+    }
+    if (fork) S2S_CUDA(cudaEventRecord(ctx->ev[4], st));
+    // TemporalConvolutionZeroBias backward, data part (TemporalConvolutionZeroBias.lua:42-48)
+    S2S_TRY(gemm_f32(ctx, false, false, BL, A, S, 1.f, dVh, S, P + Y.WV.off, A, 0.f, dh, A));
+    // context path, deferred: dh[b,l,:] += sum_t alpha_t[b,l] dc_t[b,:]   (Attention.lua:132-134)
+    {
+        GemmBatch gb; gb.count = B; gb.sA = (int64_t)T * Lmax; gb.sB = (int64_t)T * A; gb.sC = (int64_t)Lmax * A;
+        S2S_TRY(gemm_f32(ctx, true, false, Lmax, A, T, 1.f, d.alpha, Lmax, dc_all, A, 1.f, dh, A, nullptr, gb, 1, 1));
+    }
+
     // ---- deferred weight gradients over M = B*T rows ----------------------------------------------
+    to_side();
+    const cudaStream_t ws = ctx->stream;
+    // decoder MLP (model_chorowski_baseline.lua:53-59): Linear(M,V), [Maxout, Linear(M,M)], Maxout's Linear(ST+A, M*MW)
+    S2S_TRY(gemm_f32(ctx, true, false, V, M, iBT, 1.f, dlogits, V, Y.MLP == 2 ? d.mo2 : d.mo, M, 1.f, G + Y.Wo.off, M, nullptr, GemmBatch(), 8));
+    S2S_TRY(colsum_add(ctx, dlogits, BT, V, V, G + Y.bo.off));
+    if (Y.MLP == 2) {
+        S2S_TRY(gemm_f32(ctx, true, false, M * MW, M, iBT, 1.f, dm2, M * MW, d.l1, M, 1.f, G + Y.Wm2.off, M, nullptr, GemmBatch(), 4));
+        S2S_TRY(colsum_add(ctx, dm2, BT, M * MW, M * MW, G + Y.bm2.off));
+        S2S_TRY(gemm_f32(ctx, true, false, M, M, iBT, 1.f, dl1, M, d.mo, M, 1.f, G + Y.Wl.off, M, nullptr, GemmBatch(), 8));
+        S2S_TRY(colsum_add(ctx, dl1, BT, M, M, G + Y.bl.off));
+    }
+    S2S_TRY(gemm_f32(ctx, true, false, M * MW, ST + A, iBT, 1.f, dm, M * MW, d.scm, ST + A, 1.f, G + Y.Wm.off, ST + A, nullptr, GemmBatch(), 4));
+    S2S_TRY(colsum_add(ctx, dm, BT, M * MW, M * MW, G + Y.bm.off));
     // decoder GRU (GRU.lua:23-26): dG_{z,r} += {daz,dar}^T {s,u} ; dG_h += dah^T {r*s,u}
     S2S_TRY(gemm_f32(ctx, true, false, 2 * ST, 2 * ST, iBT, 1.f, dA, 3 * ST, d.su, 2 * ST, 1.f, G + Y.Gz.off, 2 * ST, nullptr, GemmBatch(), 4));
     S2S_TRY(gemm_f32(ctx, true, false, ST, 2 * ST, iBT, 1.f, dA + 2 * ST, 3 * ST, d.rhu, 2 * ST, 1.f, G + Y.Gh.off, 2 * ST, nullptr, GemmBatch(), 4));
@@ -867,35 +957,30 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     // Linear(V,ST) on the one-hot label (Attention.lua:149)
     S2S_TRY(gemm_f32(ctx, false, false, iBT, ST, ST, 1.f, du_all, ST, P + Y.Wj.off + ST, 2 * ST, 0.f, dyin, ST));
     S2S_TRY(colsum_add(ctx, dyin, BT, ST, ST, G + Y.by.off));
-    wy_scatter_kernel<<<(unsigned)BT, 128, 0, st>>>(dyin, labels, B, T, ST, V, G + Y.Wy.off);
+    wy_scatter_kernel<<<(unsigned)BT, 128, 0, ws>>>(dyin, labels, B, T, ST, V, G + Y.Wy.off);
     S2S_LAUNCH_CHECK(ctx);
     // Ws (Attention.lua:66): dW_s += dq^T s_{t-1} ; db_s += sum dq
     S2S_TRY(gemm_f32(ctx, true, false, S, ST, iBT, 1.f, dq_all, S, d.su, 2 * ST, 1.f, G + Y.Ws.off, ST, nullptr, GemmBatch(), 4));
     S2S_TRY(colsum_add(ctx, dq_all, BT, S, S, G + Y.bs.off));
 
-    // ---- deferred dVh / dw_e (/ dUW) then the Vh convolution backward -----------------------------
-    {
-        AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw; loc.alpha_prev = d.alpha;
-        S2S_TRY(attn_dvh(ctx, d.Vh, d.q, de_all, P + Y.we.off, lengths, tlens, B, Lmax, T, S, loc, dVh, G + Y.we.off, duw));
-    }
+    // ---- products that need attn_dvh's outputs ------------------------------------------------------
+    if (fork) S2S_CUDA(cudaStreamWaitEvent(ws, ctx->ev[4], 0));
     if (KF > 0) {
         float* dub;
         S2S_ALLOC(dub, ar, float, S);
-        S2S_CUDA(cudaMemsetAsync(dub, 0, S * sizeof(float), st));
+        S2S_CUDA(cudaMemsetAsync(dub, 0, S * sizeof(float), ws));
         S2S_TRY(colsum_add(ctx, dq_all, BT, S, S, dub));
-        loc_unfold_kernel<<<ceil_div(S, 128), 128, 0, st>>>(P + Y.U.off, P + Y.WF.off, P + Y.bF.off, duw, dub, S, Y.K, KF,
+        loc_unfold_kernel<<<Y.K, 256, 0, ws>>>(P + Y.U.off, P + Y.WF.off, P + Y.bF.off, duw, dub, S, Y.K, KF,
                                                             G + Y.U.off, G + Y.WF.off, G + Y.bF.off);
         S2S_LAUNCH_CHECK(ctx);
     }
-    // TemporalConvolutionZeroBias backward (TemporalConvolutionZeroBias.lua:42-54): gradBias stays zero
-    const int BL = B * Lmax;
+    // TemporalConvolutionZeroBias backward, weight part (TemporalConvolutionZeroBias.lua:50-54): gradBias stays zero
     S2S_TRY(gemm_f32(ctx, true, false, S, A, BL, 1.f, dVh, S, h, A, 1.f, G + Y.WV.off, A, nullptr, GemmBatch(), 8));
-    S2S_TRY(gemm_f32(ctx, false, false, BL, A, S, 1.f, dVh, S, P + Y.WV.off, A, 0.f, dh, A));
-    // context path, deferred: dh[b,l,:] += sum_t alpha_t[b,l] dc_t[b,:]   (Attention.lua:132-134)
-    {
-        GemmBatch gb; gb.count = B; gb.sA = (int64_t)T * Lmax; gb.sB = (int64_t)T * A; gb.sC = (int64_t)Lmax * A;
-        S2S_TRY(gemm_f32(ctx, true, false, Lmax, A, T, 1.f, d.alpha, Lmax, dc_all, A, 1.f, dh, A, nullptr, gb, 1, 1));
+    if (fork) {
+        S2S_CUDA(cudaEventRecord(ctx->ev[3], ctx->side[1]));
+        ctx->wgrad_join_pending = true;
     }
+    to_main();
     return 0;
 }
 

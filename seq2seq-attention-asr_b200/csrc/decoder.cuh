@@ -39,7 +39,8 @@ struct DecoderState {
 int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax,
                     const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out);
 int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, const float* h, const int* lengths, int B, int Lmax,
-                     const int* labels, const int* tlens, int T, const float* dropmask, float lambda, const float* dlogp, float* dh);
+                     const int* labels, const int* tlens, int T, const float* dropmask, float lambda, const float* dlogp, float* dh,
+                     bool defer_wgrad = false);
 
 // decoder_cluster.cu: the time loop of decoder_forward as one persistent cluster kernel (ST = 256, S = A = 512, K = 0)
 int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, const int* tlens,

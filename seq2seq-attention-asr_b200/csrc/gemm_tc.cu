@@ -60,6 +60,11 @@ struct Sched {
     int tap_row[9];
     int b_col0;
     int relu;                     // C = max(., 0) in the epilogue (whole tiles only: no atomic tail)
+    // MN-major operands (the NN data-gradient and TN weight-gradient forms): the operand lies in memory as [K, MN] (MN contiguous) and is
+    // fetched untransposed, one 2-D TMA box {32 MN-floats, 32 K-rows} per 32-wide MN chunk; shared memory then holds, per chunk, 32 K-rows
+    // of 128 bytes (4 KB, 128-byte swizzle with 32-byte atoms: the only MN-major layout the tensor core takes for 32-bit operands, see
+    // make_desc_mn).  Columns / rows beyond the matrix read as zeros.
+    int a_mn, b_mn;
 };
 struct Span { int tm, tn, kb0, kb1; };
 
@@ -97,6 +102,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
+// MN-major operand tile of `chunks` x 32 MN-columns starting at column mn0, K rows [k0, k0 + 32)
+__device__ __forceinline__ void tma_load_mn(unsigned char* smem_dst, const CUtensorMap* map, int mn0, int k0, int chunks, uint64_t* bar) {
+    for (int c = 0; c < chunks; c++) tma_load_2d(smem_dst + c * 4096, map, mn0 + 32 * c, k0, bar);
+}
 // shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -107,7 +116,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
+// MN-major operand (see Sched::a_mn).  For 32-bit (tf32) MN-major operands the tensor core accepts ONE swizzled layout: "128-byte swizzle
+// with 32-byte atomicity" (layout type 1): rows of 128 bytes = 32 MN-floats of one K index, the four 32-byte pieces of a row XOR-ed with
+// (K index & 3) -- what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The swizzle atom is 32 MN x 4 K (512 bytes):
+// stride offset = 512 (one group of 4 K-rows to the next), leading offset = 4096 (one 32-wide MN chunk to the next).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                                // SWIZZLE_128B_BASE32B
+    return d;
+}
+// instruction descriptor: D = f32, A = B = tf32, N = BN, M = 128; bits 15 / 16: A / B operand is MN-major (0 = K-major)
 template <int BN>
 __device__ __forceinline__ uint32_t make_idesc() {
     uint32_t d = 0;
@@ -193,17 +215,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                         ak = (kb - tap * sched.tap_slabs) * BK;
                         am = m0 + sched.tap_row[tap];
                     }
-                    tma_load_2d(st, &mapAh, ak, am, &full[s]);
-                    tma_load_2d(st + A_BYTES, &mapAl, ak, am, &full[s]);
-                    tma_load_2d(st + 2 * A_BYTES, &mapBh, kb * BK + sched.b_col0, n0, &full[s]);
-                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, kb * BK + sched.b_col0, n0, &full[s]);
+                    if (sched.a_mn) {
+                        tma_load_mn(st, &mapAh, m0, kb * BK, BM / 32, &full[s]);
+                        tma_load_mn(st + A_BYTES, &mapAl, m0, kb * BK, BM / 32, &full[s]);
+                    } else {
+                        tma_load_2d(st, &mapAh, ak, am, &full[s]);
+                        tma_load_2d(st + A_BYTES, &mapAl, ak, am, &full[s]);
+                    }
+                    if (sched.b_mn) {
+                        tma_load_mn(st + 2 * A_BYTES, &mapBh, n0, kb * BK, BN / 32, &full[s]);
+                        tma_load_mn(st + 2 * A_BYTES + B_BYTES, &mapBl, n0, kb * BK, BN / 32, &full[s]);
+                    } else {
+                        tma_load_2d(st + 2 * A_BYTES, &mapBh, kb * BK + sched.b_col0, n0, &full[s]);
+                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, kb * BK + sched.b_col0, n0, &full[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ---- MMA issue --------------------------------------------------------------------------------------
         if (lane == 0) {
-            const uint32_t idesc = make_idesc<BN>();
+            const uint32_t idesc = make_idesc<BN>() | (sched.a_mn ? 1u << 15 : 0u) | (sched.b_mn ? 1u << 16 : 0u);
+            // bytes (>> 4) from one K = 8 step to the next: 32 bytes inside the swizzle row (K-major) / one 8-row group (MN-major)
+            const uint64_t a_step = sched.a_mn ? 1024 >> 4 : 32 >> 4, b_step = sched.b_mn ? 1024 >> 4 : 32 >> 4;
             int it = 0;
             for (int i = 0; get_seg(sched, g, i, seg); i++) {
                 const int acc = i & 1;
@@ -215,15 +249,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                     mbar_wait_bounded(&full[s], ph & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sa = smem_u32(base + (size_t)s * STAGE_BYTES);
-                    const uint64_t dAh = make_desc(sa), dAl = make_desc(sa + A_BYTES);
-                    const uint64_t dBh = make_desc(sa + 2 * A_BYTES), dBl = make_desc(sa + 2 * A_BYTES + B_BYTES);
+                    const uint64_t dAh = sched.a_mn ? make_desc_mn(sa) : make_desc(sa);
+                    const uint64_t dAl = sched.a_mn ? make_desc_mn(sa + A_BYTES) : make_desc(sa + A_BYTES);
+                    const uint64_t dBh = sched.b_mn ? make_desc_mn(sa + 2 * A_BYTES) : make_desc(sa + 2 * A_BYTES);
+                    const uint64_t dBl = sched.b_mn ? make_desc_mn(sa + 2 * A_BYTES + B_BYTES) : make_desc(sa + 2 * A_BYTES + B_BYTES);
                     if (sched.dbg != 1)
 #pragma unroll
                     for (int k = 0; k < BK / 8; k++) {
-                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);            // 32 bytes per K = 8 step inside the swizzle row
-                        umma_tf32(td, dAl + adv, dBh + adv, idesc, (kb != seg.kb0 || k != 0) ? 1u : 0u);
-                        umma_tf32(td, dAh + adv, dBl + adv, idesc, 1);
-                        umma_tf32(td, dAh + adv, dBh + adv, idesc, 1);
+                        const uint64_t ka = (uint64_t)k * a_step, kb_ = (uint64_t)k * b_step;
+                        umma_tf32(td, dAl + ka, dBh + kb_, idesc, (kb != seg.kb0 || k != 0) ? 1u : 0u);
+                        umma_tf32(td, dAh + ka, dBl + kb_, idesc, 1);
+                        umma_tf32(td, dAh + ka, dBh + kb_, idesc, 1);
                     }
                     umma_commit(&empty[s]);                                           // stage reusable once these MMAs retire
                 }
@@ -359,12 +395,23 @@ __global__ void transpose_split_kernel(const float* __restrict__ src, int K, int
         }
     }
 }
+// zeroes the output tiles that take stream-K partial sums; blockIdx.y = one 16-row band of a tile
 __global__ void zero_tiles_kernel(float* __restrict__ C, int ldc, int M, int N, int tiles_n, int first_tile, int BN) {
     const int tile = first_tile + blockIdx.x;
     const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
-    for (int idx = threadIdx.x; idx < tc::BM * BN; idx += blockDim.x) {
-        const int r = tm * tc::BM + idx / BN, c = tn * BN + idx % BN;
-        if (r < M && c < N) C[(size_t)r * ldc + c] = 0.f;
+    const int r0 = tm * tc::BM + blockIdx.y * 16, c0 = tn * BN;
+    const bool vec = (ldc & 3) == 0 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    if (vec) {
+        const int q = BN >> 2;
+        for (int idx = threadIdx.x; idx < 16 * q; idx += blockDim.x) {
+            const int r = r0 + idx / q, c = c0 + (idx % q) * 4;
+            if (r < M && c < N) *reinterpret_cast<float4*>(C + (size_t)r * ldc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < 16 * BN; idx += blockDim.x) {
+            const int r = r0 + idx / BN, c = c0 + idx % BN;
+            if (r < M && c < N) C[(size_t)r * ldc + c] = 0.f;
+        }
     }
 }
 
@@ -395,6 +442,18 @@ static bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// MN-major operand: [K, rows] fp32 with `rows` contiguous (pitch ld floats): box = 32 columns x 32 K-rows (one chunk of Sched::a_mn)
+static bool make_map_mn(CUtensorMap* map, const float* ptr, int rows, int K, int ld) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)K};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)tc::BK};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -412,15 +471,31 @@ static int tc_rawhi() {
     return v;
 }
 
-struct TcOp { const float* hi; const float* lo; int ld_hi, ld_lo; };
+// S2S_TC_MN=1 (default): operands of the NN / TN forms whose MN extent and pitch are multiples of 4 floats (16-byte aligned) are consumed in place as
+// MN-major UMMA operands -- no transposing pre-pass, only the low part is written (in the operand's own layout); 0 = always transpose.
+static int tc_mn() {
+    static int v = -1;
+    if (v < 0) v = env_int("S2S_TC_MN", 0);
+    return v;
+}
+
+struct TcOp { const float* hi; const float* lo; int ld_hi, ld_lo; bool mn; };
 
 // src: K-contiguous [rows, K] (transposed == false) or [K, rows] (transposed == true), pitch ld
 static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, bool transposed, TcOp* op) {
     const int Kp = (K + 3) & ~3;
+    op->mn = false;
     if (ctx->tc_cache_on) {
         for (const TcCacheEntry& c : ctx->tc_cache) {
             if (c.transposed != transposed || c.K != K || c.ld != ld) continue;
             const ptrdiff_t off = src - c.src;
+            if (c.mn) {     // cached in place ([K, cols], low part with pitch c.ld_lo): any 16-byte-aligned block of columns
+                if (off >= 0 && off + rows <= c.cols && (off & 3) == 0) {
+                    op->hi = src; op->lo = c.lo + off; op->ld_hi = ld; op->ld_lo = c.ld_lo; op->mn = true;
+                    return 0;
+                }
+                continue;
+            }
             // transposed: a block of `rows` source columns starting `off` columns into the cached matrix
             if (transposed ? (off >= 0 && off + rows <= c.cols) : (off == 0 && rows <= c.cols)) {
                 const size_t r0 = transposed ? (size_t)off : 0;
@@ -430,6 +505,18 @@ static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, b
         }
     }
     float *hi = nullptr, *lo;
+    if (transposed && tc_mn() && (rows & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        // MN-major in place: hi = the raw operand (the tf32 MMA reads only the top 19 bits), lo in the same [K, rows] layout
+        S2S_ALLOC(lo, ctx->arena, float, (size_t)K * rows);
+        const long long n4 = (long long)K * (rows >> 2);
+        int blocks = (int)((n4 + 255) / 256);
+        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+        split_kernel<<<blocks, 256, 0, ctx->stream>>>(src, K, rows, ld, nullptr, lo, rows);
+        S2S_LAUNCH_CHECK(ctx);
+        op->hi = src; op->ld_hi = ld; op->lo = lo; op->ld_lo = rows; op->mn = true;
+        if (ctx->tc_cache_on) ctx->tc_cache.push_back(TcCacheEntry{src, K, rows, ld, transposed, op->hi, op->lo, op->ld_hi, op->ld_lo, true});
+        return 0;
+    }
     S2S_ALLOC(lo, ctx->arena, float, (size_t)rows * Kp);
     const bool raw = !transposed && tc_rawhi() && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     if (!raw) S2S_ALLOC(hi, ctx->arena, float, (size_t)rows * Kp);
@@ -444,7 +531,7 @@ static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, b
     S2S_LAUNCH_CHECK(ctx);
     op->hi = raw ? src : hi; op->ld_hi = raw ? ld : Kp;
     op->lo = lo; op->ld_lo = Kp;
-    if (ctx->tc_cache_on) ctx->tc_cache.push_back(TcCacheEntry{src, K, rows, ld, transposed, op->hi, op->lo, op->ld_hi, op->ld_lo});
+    if (ctx->tc_cache_on) ctx->tc_cache.push_back(TcCacheEntry{src, K, rows, ld, transposed, op->hi, op->lo, op->ld_hi, op->ld_lo, false});
     return 0;
 }
 
@@ -462,6 +549,8 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
     static const int dbg_mode = env_int("S2S_TC_DBG", 0), tail_on = env_int("S2S_TC_TAIL", 1);
     sc.dbg = dbg_mode;
     sc.tap_slabs = cv.tap_slabs; sc.b_col0 = cv.b_col0; sc.relu = cv.relu ? 1 : 0;
+    sc.a_mn = a.mn ? 1 : 0; sc.b_mn = b.mn ? 1 : 0;
+    S2S_REQUIRE(!(a.mn || b.mn) || (cv.tap_slabs == 0 && cv.b_col0 == 0), "gemm_tc: MN-major operands are not used by the implicit convolution");
     for (int t = 0; t < 9; t++) sc.tap_row[t] = cv.tap_row[t];
     const int Tt = sc.tiles_m * sc.tiles_n;
     sc.R = Tt / sc.G; sc.rem = Tt - sc.R * sc.G;
@@ -475,8 +564,11 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
     const int aK = cv.tap_slabs > 0 ? cv.a_cols : K;           // extent of the A operand's K axis in memory
     const int bK = K;                                          // true extent: shifted slabs beyond it read zeros
     CUtensorMap mAh, mAl, mBh, mBl;
-    if (!make_map(&mAh, a.hi, M, aK, a.ld_hi, BM) || !make_map(&mAl, a.lo, M, aK, a.ld_lo, BM) ||
-        !make_map(&mBh, b.hi, N, bK, b.ld_hi, BN) || !make_map(&mBl, b.lo, N, bK, b.ld_lo, BN))
+    const bool okA = a.mn ? make_map_mn(&mAh, a.hi, M, aK, a.ld_hi) && make_map_mn(&mAl, a.lo, M, aK, a.ld_lo)
+                          : make_map(&mAh, a.hi, M, aK, a.ld_hi, BM) && make_map(&mAl, a.lo, M, aK, a.ld_lo, BM);
+    const bool okB = b.mn ? make_map_mn(&mBh, b.hi, N, bK, b.ld_hi) && make_map_mn(&mBl, b.lo, N, bK, b.ld_lo)
+                          : make_map(&mBh, b.hi, N, bK, b.ld_hi, BN) && make_map(&mBl, b.lo, N, bK, b.ld_lo, BN);
+    if (!okA || !okB)
         return fail("gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", M, N, K);
     static bool attr = false;
     if (!attr) {
@@ -486,7 +578,7 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
         attr = true;
     }
     if (atomics && beta == 0.f) {
-        zero_tiles_kernel<<<sc.rem, 256, 0, ctx->stream>>>(C, ldc, M, N, sc.tiles_n, sc.R * sc.G, BN);
+        zero_tiles_kernel<<<dim3(sc.rem, BM / 16), 256, 0, ctx->stream>>>(C, ldc, M, N, sc.tiles_n, sc.R * sc.G, BN);
         S2S_LAUNCH_CHECK(ctx);
     }
     if (dbg_mode == 9) {

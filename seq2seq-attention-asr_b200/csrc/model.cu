@@ -114,7 +114,8 @@ int model_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, cons
     S2S_ALLOC(dcur, ctx->arena, float, (size_t)B * Lmax * A);
     nll_seed_kernel<<<B * T, 64, 0, ctx->stream>>>(labels, tlens, T, Y.V, flags, dlogp);
     S2S_LAUNCH_CHECK(ctx);
-    S2S_TRY(decoder_backward(ctx, Y, P, G, m.acts[Y.NL], lengths, B, Lmax, labels, tlens, T, dropmask, lambda, dlogp, dcur));
+    S2S_TRY(decoder_backward(ctx, Y, P, G, m.acts[Y.NL], lengths, B, Lmax, labels, tlens, T, dropmask, lambda, dlogp, dcur,
+                             /*defer_wgrad=*/Y.NL > 0));
     // data-parallel overlap (s2s_dp_set_overlap): a bucket of the flat gradient is summed over the ranks as soon as it is complete, on the
     // low-priority side stream, while the remaining recurrences run: the decoder's parameters under the whole encoder backward, encoder
     // layer l under the recurrences of layers l-1 .. 0 (its weight-gradient GEMMs already run there)

@@ -108,23 +108,24 @@ def test_cluster_decoder_backward_equals_per_step_chain(s2s, orc64, extra, lam):
     dlogp = dev(rng.standard_normal((B, T, cfg["V"])), torch.float32)
     res = {}
     old = os.environ.get("S2S_DEC_CLUSTER_BWD")
+    # ONE forward, two backward passes over its saved state: the monotonicity penalty is gated by the sign of sum(cumsum alpha_t -
+    # cumsum alpha_{t-1}) (MonotonicAlignment.lua:19-77), which at random initialisation is a sum of near-cancelling terms -- two forward
+    # runs whose fp32 sums differ in the last bit can flip a gate, and that is a property of the function, not of the backward kernels
+    ctx = s2s.Context(0)
     try:
+        s2s.attention_forward(ctx, cfg, P, h, y, lam=lam)
         for mode in ("1", "0"):
             os.environ["S2S_DEC_CLUSTER_BWD"] = mode
-            ctx = s2s.Context(0)
-            try:
-                G = torch.zeros_like(P)
-                k0 = ctx.kernel_counts()
-                s2s.attention_forward(ctx, cfg, P, h, y, lam=lam)
-                dh = s2s.attention_backward(ctx, cfg, P, G, h, y, dlogp, lam=lam)
-                torch.cuda.synchronize()
-                k1 = ctx.kernel_counts()
-                if os.environ.get("S2S_TEST_LOC_BWD_CLUSTER", "1") == "1" or (cfg["K"] == 0 and lam == 0.0):
-                    assert (k1["dec_cluster_bwd"] - k0["dec_cluster_bwd"]) == (1 if mode == "1" else 0)
-                res[mode] = (dh.cpu().numpy(), G.cpu().numpy())
-            finally:
-                ctx.close()
+            G = torch.zeros_like(P)
+            k0 = ctx.kernel_counts()
+            dh = s2s.attention_backward(ctx, cfg, P, G, h, y, dlogp, lam=lam)
+            torch.cuda.synchronize()
+            k1 = ctx.kernel_counts()
+            if os.environ.get("S2S_TEST_LOC_BWD_CLUSTER", "1") == "1" or (cfg["K"] == 0 and lam == 0.0):
+                assert (k1["dec_cluster_bwd"] - k0["dec_cluster_bwd"]) == (1 if mode == "1" else 0)
+            res[mode] = (dh.cpu().numpy().copy(), G.cpu().numpy().copy())
     finally:
+        ctx.close()
         if old is None:
             os.environ.pop("S2S_DEC_CLUSTER_BWD", None)
         else:
