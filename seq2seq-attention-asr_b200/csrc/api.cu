@@ -192,7 +192,7 @@ int s2s_model_fwdbwd(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, flo
     auto run = [&]() -> int {
         ctx->arena.reset();
         ctx->persist.reset();
-        S2S_TRY(model_forward(ctx, Y, P, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, nll, logp));
+        S2S_TRY(model_forward(ctx, Y, P, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, nll, logp, /*backward_follows=*/true));
         return model_backward(ctx, Y, P, G, X, lengths, B, Lmax, labels, tlens, Tmax, dropmask, lambda, flags, dX);
     };
     if (!ctx->graphs || ctx->prof.on || ctx->capturing) {

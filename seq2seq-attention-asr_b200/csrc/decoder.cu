@@ -575,13 +575,14 @@ static void pad_lr(int kf, int* pl) { *pl = (kf % 2 == 1) ? (kf - 1) / 2 : kf / 
 // forward
 // =================================================================================================
 int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax,
-                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out) {
+                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out, bool prefetch_v1) {
     const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V, M = Y.M, MW = Y.MW, KF = Y.K > 0 ? Y.KF : 0;
     S2S_REQUIRE(B > 0 && Lmax > 0 && T > 0, "decoder_forward: empty batch (B=%d Lmax=%d T=%d)", B, Lmax, T);
     S2S_REQUIRE(ST % 4 == 0 && A % 4 == 0, "decoder: ST and A must be multiples of 4");
     if (!ctx->dec) ctx->dec = new DecoderState();
     DecoderState& d = *ctx->dec;
     d.valid = false; d.B = B; d.Lmax = Lmax; d.T = T; d.Y = Y; d.lambda = lambda; d.has_drop = dropmask != nullptr;
+    d.V1 = nullptr; d.v1_pending = false;
     Arena& pa = ctx->persist;
     const size_t BT = (size_t)B * T;
     S2S_ALLOC(d.Vh, pa, float, (size_t)B * Lmax * S);
@@ -637,6 +638,25 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
     const int64_t ldsc = (int64_t)T * (ST + A), ldsu = (int64_t)T * 2 * ST, ldg = (int64_t)T * 3 * ST;
     bool clustered = false;     // the whole time loop in one persistent cluster kernel (decoder_cluster.cu) when the shapes allow
     S2S_TRY(decoder_cluster_forward(ctx, Y, P, h, lengths, B, Lmax, tlens, T, lambda, uy, d, &clustered));
+    if (clustered && prefetch_v1 && KF > 0 && decoder_cluster_backward_eligible(Y, Lmax, lambda) && ctx->side[1] && st != ctx->side[1] &&
+        !ctx->wgrad_join_pending) {
+        // A backward pass follows (s2s_model_fwdbwd): its location path needs V1 = d e_t / d alpha_{t-1}, which depends on forward results
+        // only.  Formed here on the low-priority side stream it runs beside the MLP, the loss and the MLP backward instead of in front of
+        // the backward time loop.
+        static int overlap = -1;
+        if (overlap < 0) { const char* e = getenv("S2S_OVERLAP"); overlap = e ? atoi(e) : 1; }
+        if (overlap) {
+            S2S_ALLOC(d.V1, pa, float, BT * Lmax * KF);
+            S2S_CUDA(cudaEventRecord(ctx->ev[2], st));
+            S2S_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev[2], 0));
+            struct StreamGuard { s2s_ctx* c; cudaStream_t s; ~StreamGuard() { c->stream = s; } } g{ctx, st};
+            ctx->stream = ctx->side[1];
+            S2S_CUDA(cudaMemsetAsync(d.V1, 0, BT * Lmax * KF * sizeof(float), ctx->stream));
+            S2S_TRY(attn_v1(ctx, d.Vh, d.q, P + Y.we.off, d.uw, d.alpha, lengths, tlens, B, Lmax, T, S, KF, padl, d.V1));
+            S2S_CUDA(cudaEventRecord(ctx->ev[5], ctx->side[1]));
+            d.v1_pending = true;
+        }
+    }
     if (!clustered) {   // q_0 = W_s s_0 + b_s with s_0 = 0   (Attention.lua:65-67, Recurrent.lua:112)
         DenseEpi e; e.bias = d.qbias; e.out = d.q; e.ld_out = (int64_t)T * S;
         S2S_TRY(dense_small(ctx, zeros, ST, B, ST, P + Y.Ws.off, ST, S, e));
@@ -788,7 +808,10 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
         s2s_ctx* c; cudaStream_t s; bool on;
         ~StreamGuard() { if (on) c->stream = s; }
     } v1_guard{ctx, st, false};
-    if (cluster_ok && KF > 0) {
+    if (cluster_ok && KF > 0 && d.V1) {
+        V1 = d.V1;                                   // formed behind the forward loop (decoder_forward(prefetch_v1))
+        if (d.v1_pending) { S2S_CUDA(cudaStreamWaitEvent(st, ctx->ev[5], 0)); d.v1_pending = false; }
+    } else if (cluster_ok && KF > 0) {
         static int overlap = -1;
         if (overlap < 0) { const char* e = getenv("S2S_OVERLAP"); overlap = e ? atoi(e) : 1; }
         S2S_ALLOC(V1, ar, float, BT * Lmax * KF);

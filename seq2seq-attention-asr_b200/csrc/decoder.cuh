@@ -33,11 +33,13 @@ struct DecoderState {
     float* uw = nullptr;      // [KF, S]   U W_F   (location path)
     float* qbias = nullptr;   // [S]       b_s (+ U b_F)
     float* Wjc = nullptr;     // [ST, A]   W_j[:, :ST] . W_c  (the two input Linears of Attention.lua:150-151 folded)
+    float* V1 = nullptr;      // [B, T, Lmax, KF]  d e_t / d alpha_{t-1} (location path), formed right after the forward loop when a backward
+    bool v1_pending = false;  //                   pass is known to follow (decoder_forward(prefetch_v1)): ev[5] on side[1] marks it complete
     AttnScratch att;
 };
 
 int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax,
-                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out);
+                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out, bool prefetch_v1 = false);
 int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, const float* h, const int* lengths, int B, int Lmax,
                      const int* labels, const int* tlens, int T, const float* dropmask, float lambda, const float* dlogp, float* dh,
                      bool defer_wgrad = false);

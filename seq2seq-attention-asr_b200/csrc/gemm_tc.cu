@@ -475,7 +475,7 @@ static int tc_rawhi() {
 // MN-major UMMA operands -- no transposing pre-pass, only the low part is written (in the operand's own layout); 0 = always transpose.
 static int tc_mn() {
     static int v = -1;
-    if (v < 0) v = env_int("S2S_TC_MN", 0);
+    if (v < 0) v = env_int("S2S_TC_MN", 1);
     return v;
 }
 

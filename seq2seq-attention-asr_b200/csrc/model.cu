@@ -76,7 +76,8 @@ int nll_and_seed(s2s_ctx* ctx, const float* logp, const int* labels, const int* 
 }
 
 int model_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* X, const int* lengths, int B, int Lmax,
-                  const int* labels, const int* tlens, int T, const float* dropmask, float lambda, int flags, float* nll, float* logp) {
+                  const int* labels, const int* tlens, int T, const float* dropmask, float lambda, int flags, float* nll, float* logp,
+                  bool backward_follows) {
     S2S_REQUIRE(B > 0 && Lmax > 0 && T > 0, "model_forward: empty batch");
     if (!ctx->model) ctx->model = new ModelState();
     ModelState& m = *ctx->model;
@@ -94,7 +95,7 @@ int model_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* X,
     }
     float* lp = logp;
     if (!lp) { S2S_ALLOC(m.logp, ctx->persist, float, (size_t)B * T * Y.V); lp = m.logp; }
-    S2S_TRY(decoder_forward(ctx, Y, P, m.acts[Y.NL], lengths, B, Lmax, labels, tlens, T, dropmask, lambda, lp));
+    S2S_TRY(decoder_forward(ctx, Y, P, m.acts[Y.NL], lengths, B, Lmax, labels, tlens, T, dropmask, lambda, lp, backward_follows));
     if (nll) {
         nll_kernel<<<B, 32, 0, ctx->stream>>>(lp, labels, tlens, T, Y.V, flags, nll);
         S2S_LAUNCH_CHECK(ctx);

@@ -15,7 +15,8 @@ struct ModelState {
 };
 
 int model_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* X, const int* lengths, int B, int Lmax,
-                  const int* labels, const int* tlens, int T, const float* dropmask, float lambda, int flags, float* nll, float* logp);
+                  const int* labels, const int* tlens, int T, const float* dropmask, float lambda, int flags, float* nll, float* logp,
+                  bool backward_follows = false);
 int model_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, const float* X, const int* lengths, int B, int Lmax,
                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, int flags, float* dX);
 
