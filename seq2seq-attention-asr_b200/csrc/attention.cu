@@ -772,14 +772,15 @@ struct V1Params {
     int B, Lmax, T, KF, padl;
     float* V1;                   // [B, T, Lmax, KF]
 };
-constexpr int V1_R = 16;         // frames per CTA: 8 warps x 2
+constexpr int V1_F = 4;                  // frames per warp: the 12 shared-memory vectors of one s-quad (q, w, 10 taps of U W_F) serve 4 frames
+constexpr int V1_R = 8 * V1_F;           // frames per CTA
 constexpr int V1_S = 512;
 
 template <int KFT>               // exact filter size (10) or 0 = run-time size <= LOC_MAXKF
 __global__ void __launch_bounds__(256, 1)
 attn_v1_kernel(const V1Params p) {
     constexpr int NT = KFT > 0 ? KFT : LOC_MAXKF;
-    constexpr int S = V1_S;
+    constexpr int S = V1_S, F = V1_F;
     extern __shared__ __align__(16) float v1_sm[];
     float* uw_s = v1_sm;                                   // [NT][S]   (taps past KF: zero weights)
     float* w_s = uw_s + NT * S;                            // [S]
@@ -789,83 +790,97 @@ attn_v1_kernel(const V1Params p) {
     const int Lb = p.lengths ? p.lengths[b] : p.Lmax;
     const int Tb = p.tlens ? min(p.tlens[b], p.T) : p.T;
     if (l0 >= Lb || Tb < 2) return;
+    // the steps are independent: blockIdx.z takes an equal share of [1, Tb) so that the grid is several waves deep (B * L / 32 frame
+    // blocks alone are ~2 waves of long CTAs: a third of the machine would idle through the last one)
+    const int tA = 1 + (int)(((long long)(Tb - 1) * blockIdx.z) / gridDim.z), tB = 1 + (int)(((long long)(Tb - 1) * (blockIdx.z + 1)) / gridDim.z);
+    if (tA >= tB) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int W = V1_R + NT;
     for (int i = tid; i < NT * S; i += 256) uw_s[i] = i < p.KF * S ? p.uw[i] : 0.f;
     for (int i = tid; i < S; i += 256) w_s[i] = p.w[i];
-    for (int e = tid; e < Tb * W; e += 256) {
-        const int t = e / W, x = e % W, l = l0 + x - p.padl;
-        ap_s[e] = (t > 0 && l >= 0 && l < Lb) ? p.alpha_all[((size_t)b * p.T + t - 1) * p.Lmax + l] : 0.f;
+    for (int e = tid; e < (tB - tA) * W; e += 256) {
+        const int t = tA + e / W, x = e % W, l = l0 + x - p.padl;
+        ap_s[e] = (l >= 0 && l < Lb) ? p.alpha_all[((size_t)b * p.T + t - 1) * p.Lmax + l] : 0.f;
     }
-    const int r0 = 2 * warp, la = l0 + r0;
-    const bool ok0 = la < Lb, ok1 = la + 1 < Lb;
-    float4 vv[2][4];
+    const int r0 = F * warp, la = l0 + r0;
+    float4 vv[F][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        vv[0][i] = ok0 ? ldg_stream(p.Vh + ((size_t)b * p.Lmax + la) * S + lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        vv[1][i] = ok1 ? ldg_stream(p.Vh + ((size_t)b * p.Lmax + la + 1) * S + lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int f = 0; f < F; f++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            vv[f][i] = la + f < Lb ? ldg_stream(p.Vh + ((size_t)b * p.Lmax + la + f) * S + lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float* qb = p.q_all + (size_t)b * p.T * S;
-    for (int i = tid; i < S; i += 256) q_s[S + i] = qb[(size_t)1 * S + i];           // q_1 -> buffer 1
+    // q_t is staged through registers one step ahead: the global load is issued before the step's arithmetic and stored behind it
+    float qn0 = qb[(size_t)tA * S + tid], qn1 = qb[(size_t)tA * S + 256 + tid];
+    q_s[(tA & 1) * S + tid] = qn0; q_s[(tA & 1) * S + 256 + tid] = qn1;
     __syncthreads();
-    for (int t = 1; t < Tb; t++) {
+    if (la >= Lb) {                                        // warp without frames: only helps staging q
+        for (int t = tA; t < tB; t++) {
+            if (t + 1 < tB) { q_s[((t + 1) & 1) * S + tid] = qb[(size_t)(t + 1) * S + tid]; q_s[((t + 1) & 1) * S + 256 + tid] = qb[(size_t)(t + 1) * S + 256 + tid]; }
+            __syncthreads();
+        }
+        return;
+    }
+    for (int t = tA; t < tB; t++) {
         const float* qs = q_s + (t & 1) * S;
-        if (t + 1 < Tb)
-            for (int i = tid; i < S; i += 256) q_s[((t + 1) & 1) * S + i] = qb[(size_t)(t + 1) * S + i];
-        float a[NT + 1];
+        if (t + 1 < tB) { qn0 = qb[(size_t)(t + 1) * S + tid]; qn1 = qb[(size_t)(t + 1) * S + 256 + tid]; }
+        float a[NT + F - 1];
 #pragma unroll
-        for (int x = 0; x <= NT; x++) a[x] = ap_s[t * W + r0 + x];
-        float v1a[2][NT];
+        for (int x = 0; x < NT + F - 1; x++) a[x] = ap_s[(t - tA) * W + r0 + x];
+        float v1a[F][NT];
 #pragma unroll
-        for (int jj = 0; jj < NT; jj++) { v1a[0][jj] = 0.f; v1a[1][jj] = 0.f; }
+        for (int f = 0; f < F; f++)
+#pragma unroll
+            for (int jj = 0; jj < NT; jj++) v1a[f][jj] = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const float4 qv = *reinterpret_cast<const float4*>(qs + lane * 4 + 128 * i);
-            float4 z0 = f4add(vv[0][i], qv), z1 = f4add(vv[1][i], qv);
+            float4 z[F];
+#pragma unroll
+            for (int f = 0; f < F; f++) z[f] = f4add(vv[f][i], qv);
             float4 u[NT];
 #pragma unroll
             for (int jj = 0; jj < NT; jj++) {
                 u[jj] = *reinterpret_cast<const float4*>(uw_s + jj * S + lane * 4 + 128 * i);
-                z0 = f4fma(a[jj], u[jj], z0);
-                z1 = f4fma(a[jj + 1], u[jj], z1);
+#pragma unroll
+                for (int f = 0; f < F; f++) z[f] = f4fma(a[f + jj], u[jj], z[f]);
             }
             const float4 wv = *reinterpret_cast<const float4*>(w_s + lane * 4 + 128 * i);
-            float4 g0, g1;
-            { float th = tanh_acc(z0.x); g0.x = wv.x * (1.f - th * th); }
-            { float th = tanh_acc(z0.y); g0.y = wv.y * (1.f - th * th); }
-            { float th = tanh_acc(z0.z); g0.z = wv.z * (1.f - th * th); }
-            { float th = tanh_acc(z0.w); g0.w = wv.w * (1.f - th * th); }
-            { float th = tanh_acc(z1.x); g1.x = wv.x * (1.f - th * th); }
-            { float th = tanh_acc(z1.y); g1.y = wv.y * (1.f - th * th); }
-            { float th = tanh_acc(z1.z); g1.z = wv.z * (1.f - th * th); }
-            { float th = tanh_acc(z1.w); g1.w = wv.w * (1.f - th * th); }
 #pragma unroll
-            for (int jj = 0; jj < NT; jj++) {
-                v1a[0][jj] = fmaf(g0.x, u[jj].x, fmaf(g0.y, u[jj].y, fmaf(g0.z, u[jj].z, fmaf(g0.w, u[jj].w, v1a[0][jj]))));
-                v1a[1][jj] = fmaf(g1.x, u[jj].x, fmaf(g1.y, u[jj].y, fmaf(g1.z, u[jj].z, fmaf(g1.w, u[jj].w, v1a[1][jj]))));
+            for (int f = 0; f < F; f++) {
+                float4 g;
+                { float th = tanh_acc(z[f].x); g.x = wv.x * (1.f - th * th); }
+                { float th = tanh_acc(z[f].y); g.y = wv.y * (1.f - th * th); }
+                { float th = tanh_acc(z[f].z); g.z = wv.z * (1.f - th * th); }
+                { float th = tanh_acc(z[f].w); g.w = wv.w * (1.f - th * th); }
+#pragma unroll
+                for (int jj = 0; jj < NT; jj++)
+                    v1a[f][jj] = fmaf(g.x, u[jj].x, fmaf(g.y, u[jj].y, fmaf(g.z, u[jj].z, fmaf(g.w, u[jj].w, v1a[f][jj]))));
             }
         }
-        // 2 x 16 partial sums over 32 lanes: transposed butterfly, lane x ends with value (x & 15) of frame (x >> 4)
-        float v[16];
+        // F x 16 partial sums over 32 lanes, two frames at a time: transposed butterfly, lane x ends with value (x & 15) of frame (x >> 4)
 #pragma unroll
-        for (int jj = 0; jj < 16; jj++) {
-            const float s0 = jj < NT ? v1a[0][jj < NT ? jj : 0] : 0.f, s1 = jj < NT ? v1a[1][jj < NT ? jj : 0] : 0.f;
-            const float send = (lane & 16) ? s0 : s1, keep = (lane & 16) ? s1 : s0;
-            v[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
+        for (int fp = 0; fp < F; fp += 2) {
+            float v[16];
 #pragma unroll
-        for (int sft = 8; sft >= 1; sft >>= 1) {
-#pragma unroll
-            for (int i = 0; i < sft; i++) {
-                const float send = (lane & sft) ? v[i] : v[i + sft];
-                const float keep = (lane & sft) ? v[i + sft] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            for (int jj = 0; jj < 16; jj++) {
+                const float s0 = jj < NT ? v1a[fp][jj < NT ? jj : 0] : 0.f, s1 = jj < NT ? v1a[fp + 1][jj < NT ? jj : 0] : 0.f;
+                const float send = (lane & 16) ? s0 : s1, keep = (lane & 16) ? s1 : s0;
+                v[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
+#pragma unroll
+            for (int sft = 8; sft >= 1; sft >>= 1) {
+#pragma unroll
+                for (int i = 0; i < sft; i++) {
+                    const float send = (lane & sft) ? v[i] : v[i + sft];
+                    const float keep = (lane & sft) ? v[i + sft] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                }
+            }
+            const int fr = fp + (lane >> 4), jj = lane & 15;
+            if (la + fr < Lb && jj < p.KF) p.V1[(((size_t)b * p.T + t) * p.Lmax + la + fr) * p.KF + jj] = v[0];
         }
-        {
-            const int fr = lane >> 4, jj = lane & 15;
-            if ((fr ? ok1 : ok0) && jj < p.KF) p.V1[(((size_t)b * p.T + t) * p.Lmax + la + fr) * p.KF + jj] = v[0];
-        }
+        if (t + 1 < tB) { q_s[((t + 1) & 1) * S + tid] = qn0; q_s[((t + 1) & 1) * S + 256 + tid] = qn1; }
         __syncthreads();                                    // q_{t+1} staged; q_t buffer free for t+2
     }
 }
@@ -879,7 +894,7 @@ int attn_v1(s2s_ctx* ctx, const float* Vh, const float* q_all, const float* w, c
     const int NT = KF == 10 ? 10 : LOC_MAXKF;
     const size_t smem = ((size_t)NT * V1_S + 3 * V1_S + (size_t)T * (V1_R + NT)) * sizeof(float);
     S2S_REQUIRE(smem <= 200 * 1024, "attn_v1: T=%d too large for the shared-memory staging", T);
-    dim3 grid(ceil_div(Lmax, V1_R), B);
+    dim3 grid(ceil_div(Lmax, V1_R), B, T >= 12 ? 3 : 1);
     prof_begin(ctx, S2S_PROF_ATTN_DVH);
     if (KF == 10) {
         S2S_CUDA(cudaFuncSetAttribute(attn_v1_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1102,6 +1102,69 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
     for (int i = threadIdx.x; i < width; i += blockDim.x) dst[(size_t)k * width + i] = src[(size_t)s * width + i];
 }
 
+// ---- beam bookkeeping on the device (Attention.lua:390-432) --------------------------------------------------------------------
+// One block per label: adds the beams' scores to the step's log-probabilities (:404), takes the top (K0 - finished) candidates
+// (:406-408, highest first, lowest flat index on ties -- torch.topk's order on distinct values), moves candidates that end in <eos> or
+// hit the length limit to the finished list (:418-421) and makes the others the next beams (source row + label for the state gather).
+struct BeamState { int nb, nfin, done, count; };
+__global__ void __launch_bounds__(256)
+beam_select_kernel(const float* __restrict__ lp, int V, int K0, int eos, int maxlen, int first, int ML, BeamState* __restrict__ bs,
+                   const float* __restrict__ bp_in, float* __restrict__ bp_out, const int* __restrict__ seq_in, int* __restrict__ seq_out,
+                   float* __restrict__ fin_p, int* __restrict__ fin_len, int* __restrict__ fin_seq, float* __restrict__ work,
+                   unsigned char* __restrict__ used, int* __restrict__ ysel, int* __restrict__ ssel) {
+    __shared__ float rv[8];
+    __shared__ int ri[8];
+    __shared__ int sel_i[64];
+    __shared__ float sel_v[64];
+    __shared__ int dst_slot[64];         // >= 0: next beam slot, < 0: -(finished slot) - 1
+    __shared__ int s_nn, s_nfin;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!first && bs->done) return;
+    const int nb = first ? 1 : bs->nb, nfin0 = first ? 0 : bs->nfin, count = first ? 0 : bs->count + 1;
+    const int n = nb * V;
+    for (int i = tid; i < n; i += 256) { work[i] = first ? lp[i] : lp[i] + bp_in[i / V]; used[i] = 0; }
+    __syncthreads();
+    const int want = K0 - nfin0, kk = want < n ? want : n;
+    for (int a = 0; a < kk; a++) {
+        float bv = 0.f; int bi = -1;
+        for (int i = tid; i < n; i += 256)
+            if (!used[i]) { const float v = work[i]; if (bi < 0 || v > bv) { bv = v; bi = i; } }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { rv[warp] = bv; ri[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; w++)
+                if (ri[w] >= 0 && (bi < 0 || rv[w] > bv || (rv[w] == bv && ri[w] < bi))) { bv = rv[w]; bi = ri[w]; }
+            sel_i[a] = bi; sel_v[a] = bv; used[bi] = 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int nn = 0, nf = nfin0;
+        for (int k = 0; k < kk; k++) {
+            const int j = sel_i[k] % V;
+            if (j == eos || (!first && count == maxlen)) { dst_slot[k] = -nf - 1; fin_p[nf] = sel_v[k]; fin_len[nf] = count + 1; nf++; }
+            else { dst_slot[k] = nn; ssel[nn] = sel_i[k] / V; ysel[nn] = j; bp_out[nn] = sel_v[k]; nn++; }
+        }
+        for (int m = nn; m < K0; m++) { ssel[m] = nn ? ssel[0] : 0; ysel[m] = nn ? ysel[0] : 0; }      // dead rows repeat a live one
+        s_nn = nn; s_nfin = nf;
+        bs->nb = nn; bs->nfin = nf; bs->count = count; bs->done = (nf >= K0 || nn == 0 || count >= maxlen) ? 1 : 0;
+    }
+    __syncthreads();
+    // label sequences: the parent's `count` labels followed by the new one
+    for (int e = tid; e < kk * (count + 1); e += 256) {
+        const int k = e / (count + 1), t = e % (count + 1);
+        const int src = sel_i[k] / V, j = sel_i[k] % V;
+        const int v = t < count ? seq_in[(size_t)src * ML + t] : j;
+        if (dst_slot[k] >= 0) seq_out[(size_t)dst_slot[k] * ML + t] = v;
+        else fin_seq[(size_t)(-dst_slot[k] - 1) * ML + t] = v;
+    }
+}
+
 int beam_search_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, int L, int eos, int beam, int maxlen,
                      int* out_host, int* n_out_host, float* logp_out_host) {
     S2S_REQUIRE(L > 0 && beam > 0 && beam <= 64 && maxlen > 0, "beam_search: bad arguments (L=%d beam=%d maxlen=%d)", L, beam, maxlen);
@@ -1122,9 +1185,71 @@ int beam_search_impl(s2s_ctx* ctx, const Layout& Y, const float* P, const float*
     S2S_ALLOC(lp, pa, float, (size_t)K0 * V);
     S2S_ALLOC(ysel, pa, int, K0);
     S2S_ALLOC(ssel, pa, int, K0);
+    int host_topk = 0;              // S2S_BEAM_HOST=1: the first version (scores to the host every label), kept for A/B tests
+    { const char* e = getenv("S2S_BEAM_HOST"); if (e) host_topk = atoi(e); }
     replicate_rows_kernel<<<(unsigned)ceil_div64((int64_t)L * A, 256), 256, 0, st>>>(h, (int64_t)L * A, K0, hK);
     S2S_LAUNCH_CHECK(ctx);
     S2S_TRY(gemm_f32(ctx, false, true, K0 * L, S, A, 1.f, hK, A, P + Y.WV.off, A, 0.f, VhK, S));       // Attention.lua:355
+
+    if (!host_topk) {
+        // ---- device-resident search: no score ever leaves the GPU; the host reads 16 bytes of status every 8 labels ----------------
+        const int ML = maxlen + 2;
+        BeamState* bs; float *bp[2], *fin_p, *work; int *seq[2], *fin_len, *fin_seq; unsigned char* used;
+        S2S_ALLOC(bs, pa, BeamState, 1);
+        for (int i = 0; i < 2; i++) { S2S_ALLOC(bp[i], pa, float, K0); S2S_ALLOC(seq[i], pa, int, (size_t)K0 * ML); }
+        S2S_ALLOC(fin_p, pa, float, K0); S2S_ALLOC(fin_len, pa, int, K0); S2S_ALLOC(fin_seq, pa, int, (size_t)K0 * ML);
+        S2S_ALLOC(work, pa, float, (size_t)K0 * V); S2S_ALLOC(used, pa, unsigned char, (size_t)K0 * V);
+        S2S_CUDA(cudaMemsetAsync(bs, 0, sizeof(BeamState), st));
+        BeamState hs = {0, 0, 0, 0};
+        auto status = [&]() -> int {
+            S2S_CUDA(cudaMemcpyAsync(&hs, bs, sizeof(BeamState), cudaMemcpyDeviceToHost, st));
+            S2S_CUDA(cudaStreamSynchronize(st));
+            return 0;
+        };
+        // first step from the zero state (Attention.lua:366-387): one row, then its state replicated to every beam
+        ctx->arena.reset();
+        S2S_TRY(attention_step_impl(ctx, Y, P, hK, VhK, nullptr, 1, L, nullptr, nullptr, nullptr, alpha[0], sst[0], lp));
+        int sp = 0;
+        beam_select_kernel<<<1, 256, 0, st>>>(lp, V, K0, eos, maxlen, 1, ML, bs, bp[sp], bp[sp ^ 1], seq[sp], seq[sp ^ 1], fin_p, fin_len, fin_seq,
+                                              work, used, ysel, ssel);
+        S2S_LAUNCH_CHECK(ctx);
+        sp ^= 1;
+        gather_rows_kernel<<<K0, 128, 0, st>>>(alpha[0], ssel, L, alpha[1]);
+        S2S_LAUNCH_CHECK(ctx);
+        gather_rows_kernel<<<K0, 128, 0, st>>>(sst[0], ssel, ST, sst[1]);
+        S2S_LAUNCH_CHECK(ctx);
+        S2S_TRY(status());
+        const int cur = 1;
+        for (int count = 1; count <= maxlen && !hs.done; count++) {                        // Attention.lua:390
+            ctx->arena.reset();
+            // all K0 rows every label (finished beams leave dead rows that repeat a live one): the batch shape never depends on device state
+            S2S_TRY(attention_step_impl(ctx, Y, P, hK, VhK, nullptr, K0, L, ysel, alpha[cur], sst[cur], alpha[cur ^ 1], sst[cur ^ 1], lp));
+            beam_select_kernel<<<1, 256, 0, st>>>(lp, V, K0, eos, maxlen, 0, ML, bs, bp[sp], bp[sp ^ 1], seq[sp], seq[sp ^ 1], fin_p, fin_len,
+                                                  fin_seq, work, used, ysel, ssel);
+            S2S_LAUNCH_CHECK(ctx);
+            sp ^= 1;
+            gather_rows_kernel<<<K0, 128, 0, st>>>(alpha[cur ^ 1], ssel, L, alpha[cur]);
+            S2S_LAUNCH_CHECK(ctx);
+            gather_rows_kernel<<<K0, 128, 0, st>>>(sst[cur ^ 1], ssel, ST, sst[cur]);
+            S2S_LAUNCH_CHECK(ctx);
+            if ((count & 7) == 0 || count == maxlen) S2S_TRY(status());                     // (steps issued after `done` change nothing)
+        }
+        if (!hs.done) S2S_TRY(status());
+        *n_out_host = 0;
+        if (hs.nfin > 0) {
+            std::vector<float> fp(hs.nfin); std::vector<int> fl(hs.nfin), fs((size_t)hs.nfin * ML);
+            S2S_CUDA(cudaMemcpyAsync(fp.data(), fin_p, hs.nfin * sizeof(float), cudaMemcpyDeviceToHost, st));
+            S2S_CUDA(cudaMemcpyAsync(fl.data(), fin_len, hs.nfin * sizeof(int), cudaMemcpyDeviceToHost, st));
+            S2S_CUDA(cudaMemcpyAsync(fs.data(), fin_seq, (size_t)hs.nfin * ML * sizeof(int), cudaMemcpyDeviceToHost, st));
+            S2S_CUDA(cudaStreamSynchronize(st));
+            int best = 0;
+            for (int k = 1; k < hs.nfin; k++) if (fp[k] > fp[best]) best = k;               // Attention.lua:435
+            *n_out_host = fl[best];
+            for (int i = 0; i < fl[best]; i++) out_host[i] = fs[(size_t)best * ML + i];
+            if (logp_out_host) *logp_out_host = fp[best];
+        }
+        return 0;
+    }
 
     struct Hyp { std::vector<int> y; float p; };
     std::vector<Hyp> beams, fin;

@@ -223,8 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                         tma_load_2d(st + A_BYTES, &mapAl, ak, am, &full[s]);
                     }
                     if (sched.b_mn) {
-                        tma_load_mn(st + 2 * A_BYTES, &mapBh, n0, kb * BK, BN / 32, &full[s]);
-                        tma_load_mn(st + 2 * A_BYTES + B_BYTES, &mapBl, n0, kb * BK, BN / 32, &full[s]);
+                        // (b_col0 shifts along K = the ROW coordinate of an MN-major operand: any offset, no alignment constraint)
+                        tma_load_mn(st + 2 * A_BYTES, &mapBh, n0, kb * BK + sched.b_col0, BN / 32, &full[s]);
+                        tma_load_mn(st + 2 * A_BYTES + B_BYTES, &mapBl, n0, kb * BK + sched.b_col0, BN / 32, &full[s]);
                     } else {
                         tma_load_2d(st + 2 * A_BYTES, &mapBh, kb * BK + sched.b_col0, n0, &full[s]);
                         tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, kb * BK + sched.b_col0, n0, &full[s]);
@@ -479,7 +480,7 @@ static int tc_mn() {
     return v;
 }
 
-struct TcOp { const float* hi; const float* lo; int ld_hi, ld_lo; bool mn; };
+struct TcOp { const float* hi = nullptr; const float* lo = nullptr; int ld_hi = 0, ld_lo = 0; bool mn = false; };
 
 // src: K-contiguous [rows, K] (transposed == false) or [K, rows] (transposed == true), pitch ld
 static int tc_prepare(s2s_ctx* ctx, const float* src, int rows, int K, int ld, bool transposed, TcOp* op) {
@@ -550,7 +551,7 @@ static int tc_run(s2s_ctx* ctx, int M, int N, int K, float alpha, const TcOp& a,
     sc.dbg = dbg_mode;
     sc.tap_slabs = cv.tap_slabs; sc.b_col0 = cv.b_col0; sc.relu = cv.relu ? 1 : 0;
     sc.a_mn = a.mn ? 1 : 0; sc.b_mn = b.mn ? 1 : 0;
-    S2S_REQUIRE(!(a.mn || b.mn) || (cv.tap_slabs == 0 && cv.b_col0 == 0), "gemm_tc: MN-major operands are not used by the implicit convolution");
+    S2S_REQUIRE(!(a.mn && cv.tap_slabs > 0), "gemm_tc: the tap-shifted A operand of the implicit convolution is K-major");
     for (int t = 0; t < 9; t++) sc.tap_row[t] = cv.tap_row[t];
     const int Tt = sc.tiles_m * sc.tiles_n;
     sc.R = Tt / sc.G; sc.rem = Tt - sc.R * sc.G;
@@ -628,11 +629,24 @@ int conv3_tc_dgrad(s2s_ctx* ctx, const float* dout, int64_t Mg, int Ww, int N, c
 }
 int conv3_tc_wgrad(s2s_ctx* ctx, const float* dout, const float* in, int64_t Mg, int Ww, int N, int C, float* dWp) {
     S2S_REQUIRE(Mg < (1ll << 31), "conv3_tc_wgrad: too many pixels");
-    TcOp a, b[4];
+    TcOp a, bm;
     S2S_TRY(tc_prepare(ctx, dout, N, (int)Mg, N, true, &a));          // dout^T [N, Mg]
-    // in^T [C, Mg] shifted by 0..3 pixels: tap offset = 4 q + phase, the aligned part goes into the TMA coordinate
     const int K = (int)Mg, Kp = (K + 3) & ~3;
-    for (int ph = 0; ph < 4; ph++) {
+    S2S_TRY(tc_prepare(ctx, in, C, K, C, true, &bm));                 // in^T [C, Mg]
+    if (bm.mn) {
+        // consumed in place as an MN-major operand: a tap is a shift along K = the row coordinate of the TMA box, so the nine products
+        // share one prepared operand
+        for (int t = 0; t < 9; t++) {
+            TcConv cv; cv.b_col0 = (t / 3) * Ww + (t % 3);
+            S2S_TRY(tc_run(ctx, N, C, K, 1.f, a, bm, 1.f, dWp + (size_t)t * C, 9 * C, nullptr, cv));
+        }
+        return 0;
+    }
+    // K-major copies: TMA box origins must be 16-byte aligned along the contiguous axis, so in^T is prepared shifted by 0..3 pixels:
+    // tap offset = 4 q + phase, the aligned part goes into the TMA coordinate
+    TcOp b[4];
+    b[0] = bm;
+    for (int ph = 1; ph < 4; ph++) {
         float *hi, *lo;
         S2S_ALLOC(hi, ctx->arena, float, (size_t)C * Kp);
         S2S_ALLOC(lo, ctx->arena, float, (size_t)C * Kp);

@@ -174,6 +174,39 @@ def test_beam_search_matches_oracle(s2s, gctx, orc32, orc64, extra):
         assert abs(lp - ref_lp) < 1e-3 * max(1.0, abs(ref_lp))
 
 
+@pytest.mark.parametrize("beam,maxlen", [(1, 12), (4, 3), (5, 20), (8, 40), (16, 25)])
+def test_beam_search_device_bookkeeping_equals_host_and_oracle(s2s, gctx, orc64, beam, maxlen):
+    """The device-resident search (top-k, finished list, label sequences and beam scores in HBM; the host reads 16 bytes of
+    status every 8 labels) against the first version that copied the scores to the host every label (S2S_BEAM_HOST=1) and
+    against the oracle's Attention:BeamSearch (Attention.lua:332-438): identical label sequences, equal scores.  Covers
+    the greedy case, termination by the length limit (maxlen 3), beams wider than the surviving hypotheses and maxlen not a
+    multiple of the status interval."""
+    import os
+    cfg = dict(MID, K=3, KF=4)
+    P = init_params(cfg, seed=33, dtype=np.float64, oracle=orc64) * 3.0
+    rng = np.random.default_rng(beam * 100 + maxlen)
+    eos = cfg["V"] - 1
+    old = os.environ.get("S2S_BEAM_HOST")
+    try:
+        for trial in range(2):
+            L = 17 + 9 * trial
+            h = rng.standard_normal((L, 2 * cfg["H"]))
+            Pd, hd = dev(P, torch.float32), dev(h, torch.float32)
+            os.environ["S2S_BEAM_HOST"] = "0"
+            y_dev, lp_dev = s2s.beam_search(gctx, cfg, Pd, hd, eos=eos, beam=beam, maxlen=maxlen)
+            os.environ["S2S_BEAM_HOST"] = "1"
+            y_host, lp_host = s2s.beam_search(gctx, cfg, Pd, hd, eos=eos, beam=beam, maxlen=maxlen)
+            assert y_dev == y_host and lp_dev == lp_host          # same kernels, same fp32 adds: bit-identical
+            ref_y, ref_lp = orc64.beam_search(cfg, P, h, eos=eos, K=beam, maxlen=maxlen)
+            assert list(ref_y) == y_dev
+            assert abs(lp_dev - ref_lp) < 1e-3 * max(1.0, abs(ref_lp))
+    finally:
+        if old is None:
+            os.environ.pop("S2S_BEAM_HOST", None)
+        else:
+            os.environ["S2S_BEAM_HOST"] = old
+
+
 def test_caller_defined_graph_replays_the_same_results(s2s, gctx, orc64):
     # s2s_graph_begin / _end / _launch: a captured sequence of library calls (decoder forward + loss seed + backward)
     # replayed on new input values must give what the eager calls give
