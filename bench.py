@@ -402,11 +402,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dbg("process group up")
     ctx = s2s.Context(local)
-    # the data path's collective is the C ABI's own NCCL plane (csrc/dp_nccl.cu): one s2s_dp_allreduce of the flat gradient after the
-    # replayed forward+backward graph; torch.distributed only ships the 128-byte id and carries the barrier / max-over-ranks of the timing.
-    # S2S_BENCH_DP_OVERLAP=1 selects the bucketed overlap inside s2s_model_fwdbwd (verified eager; its captured NCCL nodes fault under graph
-    # replay with NCCL 2.28.9 -- DESIGN.md 4 -- so it is not the default)
-    dp_overlap = bool(os.environ.get("S2S_BENCH_DP_OVERLAP"))
+    # the data path's collective is the C ABI's own NCCL plane (csrc/dp_nccl.cu); torch.distributed only ships the 128-byte id and carries
+    # the barrier / max-over-ranks of the timing.  Default: the bucketed overlap inside s2s_model_fwdbwd -- the gradient buckets are reduced
+    # on the low-priority side stream under the remaining backward pass, as nodes of the replayed CUDA graph (N=8: 8.15 vs
+    # 8.20 ms per step).  S2S_BENCH_DP_OVERLAP=0: one s2s_dp_allreduce of the flat gradient after the graph.
+    dp_overlap = os.environ.get("S2S_BENCH_DP_OVERLAP", "1") not in ("0", "")
     if world > 1:
         s2s.dp.init(ctx, rank, world, overlap=dp_overlap)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

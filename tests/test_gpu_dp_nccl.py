@@ -1,7 +1,7 @@
 """Data parallelism through the C ABI's own NCCL plane (s2s_dp_init / s2s_dp_allreduce, csrc/dp_nccl.cu) on real GPUs:
 two ranks x 16 utterances must reproduce one rank x 32 utterances -- the summed gradient and the parameters after the
 replicated gradient step (/B_global, clip, adadelta, row-norm; timit/timit.lua:291-348) -- with the plain all-reduce and
-with the bucketed overlap inside s2s_model_fwdbwd (incl. the replayed CUDA graph).  Needs >= 2 GPUs (gpurun --gpus 2);
+with the bucketed overlap inside s2s_model_fwdbwd, eager and as nodes of the captured / replayed CUDA graph.  Needs >= 2 GPUs (gpurun --gpus 2);
 the 128-byte NCCL unique id travels through a gloo store, nothing else does."""
 import os
 import socket
@@ -29,9 +29,9 @@ def _run_rank(rank, world, port, overlap, q):
     torch.cuda.set_device(rank)
     store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0))
     ctx = s2s.Context(rank)
-    if overlap:
-        ctx.set_graphs(False)      # the bucketed overlap is verified eager: NCCL nodes captured into the step's CUDA graph fault on replay
-    s2s.dp.init(ctx, rank, world, store=store, overlap=overlap)
+    if overlap == "eager":
+        ctx.set_graphs(False)      # "graph": the collectives are nodes of the step's captured CUDA graph (call 2 captures, call 3 replays)
+    s2s.dp.init(ctx, rank, world, store=store, overlap=bool(overlap))
     assert s2s.dp.nccl_world(ctx) == world
     dev = torch.device("cuda", rank)
     P0 = torch.from_numpy(s2s.init_params(CFG, seed=1234)).to(dev)
@@ -72,7 +72,7 @@ def _run_rank(rank, world, port, overlap, q):
     ctx.close()
 
 
-@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("overlap", [False, "eager", "graph"])
 def test_two_ranks_reproduce_the_single_rank_big_batch(overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
