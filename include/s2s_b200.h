@@ -103,7 +103,9 @@ int  s2s_graph_destroy(s2s_ctx* ctx, int graph_id);
 #define S2S_PROF_DENSE_SMALL 6
 #define S2S_PROF_DEC_FWD     7   /* the decoder time loop as one cluster kernel (decoder_cluster.cu) */
 #define S2S_PROF_DEC_BWD     8   /* the decoder backward time loop as one cluster kernel */
-#define S2S_PROF_N           9
+#define S2S_PROF_GEMM_SIDE   9   /* GEMMs issued on the low-priority side stream (weight gradients on the SMs the cluster kernels leave idle):
+                                    overlapped with the recurrences, not on the critical path of the step */
+#define S2S_PROF_N           10
 int  s2s_ctx_profile(s2s_ctx* ctx, int enable);
 int  s2s_ctx_profile_read(s2s_ctx* ctx, double* ms_host, int64_t* count_host, double* work_host);
 

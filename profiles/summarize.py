@@ -30,6 +30,7 @@ def short(name):
 
 def launches(path, out):
     rows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[0].isdigit()]
+    rows = [r for r in rows if "spin_kernel" not in r[4] and "at::native" not in r[4]]     # torch.cuda._sleep / L2-flush fills of bench.py: not the library's
     agg = collections.OrderedDict()
     for r in rows:
         k = short(r[4])
@@ -38,6 +39,12 @@ def launches(path, out):
     tot = sum(v[1] for v in agg.values())
     with open(out, "w") as f:
         f.write(f"# ncu launch list ({path.split('/')[-1]}): {len(rows)} launches, {tot / 1e6:.2f} ms of kernel time (cold-cache, serialised: compare SHARES)\n\n")
+        streams = collections.Counter()
+        for r in rows:
+            streams[r[6]] += float(r[14])
+        f.write("kernel time per CUDA stream id as ncu reports it (eager warm-up steps, the captured step and the graph replays appear under different ids; "
+                "within one step the recurrence kernels run on the main stream and the deferred weight gradients / V1 on the low-priority side stream): "
+                + ", ".join(f"stream {k}: {v / 1e6:.2f} ms" for k, v in streams.most_common()) + "\n\n")
         f.write("| kernel | launches | total ms | share | avg us |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             if v[1] / tot < 0.002:

@@ -61,14 +61,19 @@ static cudaEvent_t prof_event(s2s_ctx* ctx) {
     cudaEventCreate(&e);
     return e;
 }
+static int prof_class(const s2s_ctx* ctx, int cls) {
+    return (cls == S2S_PROF_GEMM && ctx->side[1] && ctx->stream == ctx->side[1]) ? S2S_PROF_GEMM_SIDE : cls;
+}
 void prof_begin(s2s_ctx* ctx, int cls) {
     if (!ctx->prof.on) return;
+    cls = prof_class(ctx, cls);
     ProfRec r; r.cls = cls; r.a = prof_event(ctx); r.b = prof_event(ctx);
     cudaEventRecord(r.a, ctx->stream);
     ctx->prof.recs.push_back(r);
 }
 void prof_end(s2s_ctx* ctx, int cls, double work) {
     if (!ctx->prof.on || ctx->prof.recs.empty()) return;
+    cls = prof_class(ctx, cls);
     cudaEventRecord(ctx->prof.recs.back().b, ctx->stream);
     ctx->prof.work[cls] += work;
     ctx->prof.count[cls] += 1;

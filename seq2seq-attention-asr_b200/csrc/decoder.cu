@@ -938,19 +938,27 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     }
 
     // ---- critical path: deferred dVh / dw_e (/ dUW), then dh ---------------------------------------
+    // dh = alpha^T dc (context path, Attention.lua:132-134: dh[b,l,:] = sum_t alpha_t[b,l] dc_t[b,:]) + dVh W_V.  The first term needs
+    // the time loop only, so with the side stream it is formed beside attn_dvh and the data-gradient product accumulates onto it.
     const int BL = B * Lmax;
+    {
+        to_side();
+        ctx->gemm_sm_limit = 0;
+        GemmBatch gb; gb.count = B; gb.sA = (int64_t)T * Lmax; gb.sB = (int64_t)T * A; gb.sC = (int64_t)Lmax * A;
+        S2S_TRY(gemm_f32(ctx, true, false, Lmax, A, T, 1.f, d.alpha, Lmax, dc_all, A, 0.f, dh, A, nullptr, gb, 1, 1));
+        if (fork) S2S_CUDA(cudaEventRecord(ctx->ev[5], ctx->side[1]));
+        to_main();
+    }
     {
         AttnLoc loc; loc.KF = KF; loc.padl = padl; loc.uw = d.uw; loc.alpha_prev = d.alpha;
         S2S_TRY(attn_dvh(ctx, d.Vh, d.q, de_all, P + Y.we.off, lengths, tlens, B, Lmax, T, S, loc, dVh, G + Y.we.off, duw));
     }
-    if (fork) S2S_CUDA(cudaEventRecord(ctx->ev[4], st));
-    // TemporalConvolutionZeroBias backward, data part (TemporalConvolutionZeroBias.lua:42-48)
-    S2S_TRY(gemm_f32(ctx, false, false, BL, A, S, 1.f, dVh, S, P + Y.WV.off, A, 0.f, dh, A));
-    // context path, deferred: dh[b,l,:] += sum_t alpha_t[b,l] dc_t[b,:]   (Attention.lua:132-134)
-    {
-        GemmBatch gb; gb.count = B; gb.sA = (int64_t)T * Lmax; gb.sB = (int64_t)T * A; gb.sC = (int64_t)Lmax * A;
-        S2S_TRY(gemm_f32(ctx, true, false, Lmax, A, T, 1.f, d.alpha, Lmax, dc_all, A, 1.f, dh, A, nullptr, gb, 1, 1));
+    if (fork) {
+        S2S_CUDA(cudaEventRecord(ctx->ev[4], st));
+        S2S_CUDA(cudaStreamWaitEvent(st, ctx->ev[5], 0));
     }
+    // TemporalConvolutionZeroBias backward, data part (TemporalConvolutionZeroBias.lua:42-48)
+    S2S_TRY(gemm_f32(ctx, false, false, BL, A, S, 1.f, dVh, S, P + Y.WV.off, A, 1.f, dh, A));
 
     // ---- deferred weight gradients over M = B*T rows ----------------------------------------------
     to_side();

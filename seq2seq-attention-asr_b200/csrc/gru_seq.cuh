@@ -24,6 +24,8 @@ struct GruSeqParams {
 int gru_cluster2_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
 // third-generation kernels: warp-specialised, software-pipelined sub-batches (gru_seq3.cu)
 int gru_cluster3_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
+// gru_seq4.cu: generation 3 with sub-batches of at most two utterances (three or four independent chains per cluster)
+int gru_cluster4_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
 
 // y [B,Lmax,ndir*H]; save [B,Lmax,ndir,4H] (z | r | h~ | r*h_prev)
 int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int reverse, const float* x, int ldx,

@@ -93,7 +93,7 @@ class Context:
     def graph_destroy(self, gid):
         check(self.lib.s2s_graph_destroy(self.h, gid))
 
-    PROF_CLASSES = ("attn_fwd", "attn_bwd", "attn_dvh", "gru_fwd", "gru_bwd", "gemm", "dense_small", "dec_fwd", "dec_bwd")
+    PROF_CLASSES = ("attn_fwd", "attn_bwd", "attn_dvh", "gru_fwd", "gru_bwd", "gemm", "dense_small", "dec_fwd", "dec_bwd", "gemm_side")
 
     def profile(self, enable=True):
         check(self.lib.s2s_ctx_profile(self.h, int(bool(enable))))
