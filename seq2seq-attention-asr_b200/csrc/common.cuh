@@ -44,7 +44,8 @@ struct Arena {
     size_t total = 0;
     bool frozen = false;   // set while a CUDA graph that references arena memory exists
     void* alloc(size_t bytes);            // returns nullptr on failure (message in last_error)
-    void reset() { for (auto& c : chunks) c.used = 0; }
+    uint64_t epoch = 0;    // number of resets: pointers handed out in an earlier epoch are stale
+    void reset() { for (auto& c : chunks) c.used = 0; epoch++; }
     // bump-pointer snapshot / restore: scratch of a loop iteration is handed back for the next one (same stream => ordered)
     std::vector<size_t> mark() const { std::vector<size_t> m; for (auto& c : chunks) m.push_back(c.used); return m; }
     void rewind(const std::vector<size_t>& m) { for (size_t i = 0; i < chunks.size(); i++) chunks[i].used = i < m.size() ? m[i] : 0; }

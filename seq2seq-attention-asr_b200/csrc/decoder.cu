@@ -574,50 +574,27 @@ static void pad_lr(int kf, int* pl) { *pl = (kf % 2 == 1) ? (kf - 1) / 2 : kf / 
 // =================================================================================================
 // forward
 // =================================================================================================
-int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax,
-                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out, bool prefetch_v1) {
-    const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V, M = Y.M, MW = Y.MW, KF = Y.K > 0 ? Y.KF : 0;
-    S2S_REQUIRE(B > 0 && Lmax > 0 && T > 0, "decoder_forward: empty batch (B=%d Lmax=%d T=%d)", B, Lmax, T);
-    S2S_REQUIRE(ST % 4 == 0 && A % 4 == 0, "decoder: ST and A must be multiples of 4");
+// The part of the decoder forward that does not depend on the annotations h: the folded location weights U W_F and q bias, the folded
+// context Linears W_j[:, :ST] W_c, and the teacher-forced label path y_in / its share of u for all steps.  model_forward issues it on the
+// side stream at the START of the step, so it runs under the encoder instead of between the encoder and the decoder time loop;
+// decoder_forward runs it inline when nobody did.  Buffers: persistent arena (read again by the backward pass) + per-call scratch (uy).
+int decoder_prepare(s2s_ctx* ctx, const Layout& Y, const float* P, const int* labels, int B, int T) {
+    const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V, KF = Y.K > 0 ? Y.KF : 0;
     if (!ctx->dec) ctx->dec = new DecoderState();
     DecoderState& d = *ctx->dec;
-    d.valid = false; d.B = B; d.Lmax = Lmax; d.T = T; d.Y = Y; d.lambda = lambda; d.has_drop = dropmask != nullptr;
-    d.V1 = nullptr; d.v1_pending = false;
+    d.valid = false; d.prepared = false; d.prep_pending = false;
     Arena& pa = ctx->persist;
     const size_t BT = (size_t)B * T;
-    S2S_ALLOC(d.Vh, pa, float, (size_t)B * Lmax * S);
-    S2S_ALLOC(d.alpha, pa, float, BT * Lmax);
-    S2S_ALLOC(d.sc, pa, float, BT * (ST + A));
-    S2S_ALLOC(d.q, pa, float, BT * S);
-    S2S_ALLOC(d.pen, pa, float, BT);
-    S2S_ALLOC(d.cin, pa, float, BT * ST);
-    S2S_ALLOC(d.yin, pa, float, BT * ST);
-    S2S_ALLOC(d.su, pa, float, BT * 2 * ST);
-    S2S_ALLOC(d.rhu, pa, float, BT * 2 * ST);
-    S2S_ALLOC(d.gates, pa, float, BT * 3 * ST);
-    S2S_ALLOC(d.mo, pa, float, BT * M);
-    S2S_ALLOC(d.midx, pa, int, BT * M);
-    if (Y.MLP == 2) { S2S_ALLOC(d.l1, pa, float, BT * M); S2S_ALLOC(d.mo2, pa, float, BT * M); S2S_ALLOC(d.midx2, pa, int, BT * M); }
-    S2S_ALLOC(d.logp, pa, float, BT * V);
-    if (dropmask) S2S_ALLOC(d.scm, pa, float, BT * (ST + A)); else d.scm = d.sc;
+    cudaStream_t st = ctx->stream;
+    float* bjc;
     S2S_ALLOC(d.qbias, pa, float, S);
     S2S_ALLOC(d.Wjc, pa, float, (size_t)ST * A);
     if (KF > 0) S2S_ALLOC(d.uw, pa, float, (size_t)KF * S); else d.uw = nullptr;
-    S2S_TRY(attn_scratch_alloc(ctx, pa, B, Lmax, S, A, KF, false, &d.att));
-    Arena& ar = ctx->arena;
-    float *uy, *mpre, *zeros, *bjc;
-    S2S_ALLOC(uy, ar, float, BT * ST);
-    S2S_ALLOC(bjc, ar, float, ST);
-    S2S_ALLOC(mpre, ar, float, BT * M * MW);
-    S2S_ALLOC(zeros, ar, float, (size_t)B * ST);
-    cudaStream_t st = ctx->stream;
-
-    // Vh = TemporalConvolutionZeroBias(A,S,1)(h)   (Attention.lua:44; bias pinned to zero)
-    S2S_TRY(gemm_f32(ctx, false, true, B * Lmax, S, A, 1.f, h, A, P + Y.WV.off, A, 0.f, d.Vh, S));
+    S2S_ALLOC(d.yin, pa, float, BT * ST);
+    S2S_ALLOC(d.uy, ctx->arena, float, BT * ST);
+    S2S_ALLOC(bjc, ctx->arena, float, ST);
     // location fold / q bias
-    int padl = 0;
     if (KF > 0) {
-        pad_lr(KF, &padl);
         loc_fold_kernel<<<ceil_div(S, 128), 128, 0, st>>>(P + Y.U.off, P + Y.WF.off, P + Y.bF.off, P + Y.bs.off, S, Y.K, KF, d.uw, d.qbias);
         S2S_LAUNCH_CHECK(ctx);
     } else {
@@ -631,7 +608,55 @@ int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* 
     // teacher-forced input path, hoisted out of the loop: y_in (Attention.lua:149) and its share of u
     yin_gather_kernel<<<(unsigned)BT, 128, 0, st>>>(P + Y.Wy.off, P + Y.by.off, labels, B, T, ST, V, d.yin);
     S2S_LAUNCH_CHECK(ctx);
-    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, ST, ST, 1.f, d.yin, ST, P + Y.Wj.off + ST, 2 * ST, 0.f, uy, ST, bjc));
+    S2S_TRY(gemm_f32(ctx, false, true, (int)BT, ST, ST, 1.f, d.yin, ST, P + Y.Wj.off + ST, 2 * ST, 0.f, d.uy, ST, bjc));
+    d.prepared = true; d.prep_B = B; d.prep_T = T; d.prep_n = Y.n; d.prep_epoch = ctx->persist.epoch; d.prep_epoch_scratch = ctx->arena.epoch;
+    return 0;
+}
+
+int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax,
+                    const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out, bool prefetch_v1) {
+    const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V, M = Y.M, MW = Y.MW, KF = Y.K > 0 ? Y.KF : 0;
+    S2S_REQUIRE(B > 0 && Lmax > 0 && T > 0, "decoder_forward: empty batch (B=%d Lmax=%d T=%d)", B, Lmax, T);
+    S2S_REQUIRE(ST % 4 == 0 && A % 4 == 0, "decoder: ST and A must be multiples of 4");
+    if (!(ctx->dec && ctx->dec->prepared && ctx->dec->prep_B == B && ctx->dec->prep_T == T && ctx->dec->prep_n == Y.n &&
+          ctx->dec->prep_epoch == ctx->persist.epoch && ctx->dec->prep_epoch_scratch == ctx->arena.epoch))
+        S2S_TRY(decoder_prepare(ctx, Y, P, labels, B, T));           // nobody ran the h-independent part ahead of time
+    DecoderState& d = *ctx->dec;
+    d.prepared = false;
+    d.valid = false; d.B = B; d.Lmax = Lmax; d.T = T; d.Y = Y; d.lambda = lambda; d.has_drop = dropmask != nullptr;
+    d.V1 = nullptr; d.v1_pending = false;
+    Arena& pa = ctx->persist;
+    const size_t BT = (size_t)B * T;
+    S2S_ALLOC(d.Vh, pa, float, (size_t)B * Lmax * S);
+    S2S_ALLOC(d.alpha, pa, float, BT * Lmax);
+    S2S_ALLOC(d.sc, pa, float, BT * (ST + A));
+    S2S_ALLOC(d.q, pa, float, BT * S);
+    S2S_ALLOC(d.pen, pa, float, BT);
+    S2S_ALLOC(d.cin, pa, float, BT * ST);
+    S2S_ALLOC(d.su, pa, float, BT * 2 * ST);
+    S2S_ALLOC(d.rhu, pa, float, BT * 2 * ST);
+    S2S_ALLOC(d.gates, pa, float, BT * 3 * ST);
+    S2S_ALLOC(d.mo, pa, float, BT * M);
+    S2S_ALLOC(d.midx, pa, int, BT * M);
+    if (Y.MLP == 2) { S2S_ALLOC(d.l1, pa, float, BT * M); S2S_ALLOC(d.mo2, pa, float, BT * M); S2S_ALLOC(d.midx2, pa, int, BT * M); }
+    S2S_ALLOC(d.logp, pa, float, BT * V);
+    if (dropmask) S2S_ALLOC(d.scm, pa, float, BT * (ST + A)); else d.scm = d.sc;
+    S2S_TRY(attn_scratch_alloc(ctx, pa, B, Lmax, S, A, KF, false, &d.att));
+    Arena& ar = ctx->arena;
+    float *mpre, *zeros;
+    float* const uy = d.uy;
+    S2S_ALLOC(mpre, ar, float, BT * M * MW);
+    S2S_ALLOC(zeros, ar, float, (size_t)B * ST);
+    cudaStream_t st = ctx->stream;
+
+    // Vh = TemporalConvolutionZeroBias(A,S,1)(h)   (Attention.lua:44; bias pinned to zero)
+    S2S_TRY(gemm_f32(ctx, false, true, B * Lmax, S, A, 1.f, h, A, P + Y.WV.off, A, 0.f, d.Vh, S));
+    int padl = 0;
+    if (KF > 0) pad_lr(KF, &padl);
+    if (d.prep_pending) {        // the h-independent part ran on the side stream (model_forward): join
+        S2S_CUDA(cudaStreamWaitEvent(st, ctx->ev[4], 0));
+        d.prep_pending = false;
+    }
     S2S_CUDA(cudaMemsetAsync(zeros, 0, (size_t)B * ST * sizeof(float), st));
     S2S_CUDA(cudaMemsetAsync(d.su, 0, BT * 2 * ST * sizeof(float), st));     // s_0 = 0 (Recurrent.lua:112)
 

@@ -84,6 +84,21 @@ int model_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* X,
     m.valid = false; m.B = B; m.Lmax = Lmax; m.T = T; m.Y = Y;
     const int H = Y.H, A = Y.A;
     m.acts[0] = X;
+    {   // the decoder's h-independent preparation (folded weights, label inputs of all steps) under the encoder, on the side stream
+        static int overlap = -1;
+        if (overlap < 0) { const char* e = getenv("S2S_OVERLAP"); overlap = e ? atoi(e) : 1; }
+        if (overlap && ctx->side[1] && ctx->stream != ctx->side[1] && !ctx->wgrad_join_pending) {
+            cudaStream_t main_stream = ctx->stream;
+            S2S_CUDA(cudaEventRecord(ctx->ev[2], main_stream));
+            S2S_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev[2], 0));
+            ctx->stream = ctx->side[1];
+            const int rc = decoder_prepare(ctx, Y, P, labels, B, T);
+            ctx->stream = main_stream;
+            S2S_TRY(rc);
+            S2S_CUDA(cudaEventRecord(ctx->ev[4], ctx->side[1]));
+            ctx->dec->prep_pending = true;
+        }
+    }
     for (int l = 0; l < Y.NL; l++) {
         const int din = l == 0 ? Y.D : A;
         float* out;
