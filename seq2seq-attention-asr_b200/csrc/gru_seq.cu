@@ -823,13 +823,14 @@ static int launch_cluster_geo(s2s_ctx* ctx, bool backward, const GruSeqParams& p
 // 8 utterances on clusters of 16 (one butterfly pass); else larger groups on clusters of 8 (two passes).
 template <int H>
 static int launch_cluster(s2s_ctx* ctx, bool backward, const GruSeqParams& p) {
-    // S2S_GRU_GEN: 4 = sub-batches of at most two utterances (gru_seq4.cu, default); 3 = warp-specialised, two pipelined sub-batches
-    // (gru_seq3.cu); 2 = gru_seq2.cu; 1 = first generation
+    // S2S_GRU_GEN: 5 = generation 3 with two units per lane over half the K-slice (gru_seq5.cu); 4 = sub-batches of at most two utterances
+    // (gru_seq4.cu, a negative result); 3 = warp-specialised, two pipelined sub-batches (gru_seq3.cu); 2 = gru_seq2.cu; 1 = first generation
     static int gen = -1;
     if (gen < 0) { const char* e = getenv("S2S_GRU_GEN"); gen = e ? atoi(e) : 3; }
     if (gen >= 2) {
         prof_begin(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD);
-        if (gen >= 4) S2S_TRY(gru_cluster4_launch(ctx, backward, p, H));
+        if (gen >= 5) S2S_TRY(gru_cluster5_launch(ctx, backward, p, H));
+        else if (gen == 4) S2S_TRY(gru_cluster4_launch(ctx, backward, p, H));
         else if (gen == 3) S2S_TRY(gru_cluster3_launch(ctx, backward, p, H));
         else S2S_TRY(gru_cluster2_launch(ctx, backward, p, H));
         prof_end(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD, 4.0 * p.B * p.Lmax * p.ndir * (backward ? 9.0 : 8.0) * H);

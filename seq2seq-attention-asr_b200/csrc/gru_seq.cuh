@@ -26,6 +26,8 @@ int gru_cluster2_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int 
 int gru_cluster3_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
 // gru_seq4.cu: generation 3 with sub-batches of at most two utterances (three or four independent chains per cluster)
 int gru_cluster4_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
+// gru_seq5.cu: generation 3 with two units per lane over half the K-slice (half the shared-memory reads of the mat-vec)
+int gru_cluster5_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H);
 
 // y [B,Lmax,ndir*H]; save [B,Lmax,ndir,4H] (z | r | h~ | r*h_prev)
 int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int reverse, const float* x, int ldx,

@@ -1,19 +1,15 @@
-// gru_seq3.cu -- third generation of the persistent cluster GRU recurrence (nn.RNN(nn.GRU), RNN.lua:120-201, GRU.lua:22-30):
-// warp-specialised and software-pipelined.
+// gru_seq5.cu -- fifth generation of the persistent cluster GRU recurrence (nn.RNN(nn.GRU), RNN.lua:120-201, GRU.lua:22-30):
+// generation 3 (gru_seq3.cu: warp-specialised, two pipelined sub-batches, dedicated owner warps) with the mat-vec re-mapped so that it
+// reads HALF as much shared memory.
 //
-// gru_seq2.cu showed where a step goes once the mat-vec is at the FMA floor of its SM (phase 1 = 640 cycles of FFMA at BG = 5):
-// two all-gathers over distributed shared memory (~450 cycles each: 5 KB per CTA at ~20 B/cycle plus the hop), two block barriers
-// whose skew the mat-vec warps sit out, and two serial finalisations (~250 cycles each) -- 3800 cycles per step for 960 cycles of FMA.
-// None of that is work for the FMA pipe, so it can hide behind it:
-//   * the BG utterances of a cluster are split into sub-batches A and B with their own per-source mbarriers.  Their recurrences are
-//     independent chains; while A's r*h (or h') slices are in flight, the mat-vec warps run B, and vice versa.
-//   * the quad owners (gate math + sends) are DEDICATED warps, two per sub-batch.  The eight mat-vec warps never wait on a block barrier: they publish
-//     their K-slice partials, `bar.arrive` on a named barrier and move on to the other sub-batch; the owner warps `bar.sync` on it.
-//     Partial buffers need no free-signal: the next writer of a buffer depends, through the exchange, on its last reader.
-// Per CTA: warp w < CS owns the K-slice [32w, 32w+32) = the slice CTA w produces, lane = row (weights in registers, state read as
-// warp-uniform 16-byte broadcasts, packed fma.rn.f32x2); warps CS..CS+1 (sub-batch A) and CS+2..CS+3 (B) own the (gate, utterance, unit
-// quad) finalisations; remote addresses are local address + a per-destination delta computed once (mapa is linear in the offset).
-// Backward mirrors it: the owner warps also run the elementwise part and keep r, h_prev and the dh carry of their quads in registers.
+// The timeline of generation 3 (S2S_GRU_TRACE, profiles/r02_gru_trace.txt) shows the four mat-vec phases of a step taking 2190 of its
+// 3140 cycles against an FMA floor of 960, whatever the accumulator layout -- and 640 warp-wide LDS.128 per step per CTA: a 16-byte
+// shared-memory read is served in four passes even when all 32 lanes read the same address, so the state broadcasts alone keep the
+// shared-memory pipe busy for ~2200 cycles of every step.  The FMA : LDS ratio was 4 packed FMAs per load in phase 1 and 2 in phase 2
+// because a lane owned ONE unit (row) of each gate over the warp's 32-wide K-slice.
+// Here a lane owns TWO units over HALF the K-slice (lane = (k-half, unit pair)): the same 96 weights per lane, the same FMAs, but every
+// state load now feeds twice as many of them and a phase needs 4 instead of 8 loads per utterance; the two k-halves are added with one
+// shuffle per output and the lower half-warp writes the partial sums.  Everything else is generation 3's.
 #include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,59 +22,85 @@ namespace cg = cooperative_groups;
 
 namespace s2s {
 
-typedef unsigned long long g3_f2;
-__device__ __forceinline__ g3_f2 g3_pack(float a, float b) { g3_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float g3_hsum(g3_f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a + b; }
-__device__ __forceinline__ g3_f2 g3_fma2(g3_f2 a, g3_f2 b, g3_f2 c) { g3_f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ void g3_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void g3_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+typedef unsigned long long g5_f2;
+__device__ __forceinline__ g5_f2 g5_pack(float a, float b) { g5_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float g5_hsum(g5_f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a + b; }
+__device__ __forceinline__ g5_f2 g5_fma2(g5_f2 a, g5_f2 b, g5_f2 c) { g5_f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ void g5_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void g5_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// out[b][lane] (b in [LO, LO+N)) = sum_{k<32} w[k] x[b][k0+k]: this lane's row over the warp's K-slice
+// lane = (hf = lane >> 4: k-half, up = lane & 15: unit pair).  w2[8 j + kk] = weights of unit 2 up + j for k = k0 + 2 kk, 2 kk + 1
+// (k0 = start of this lane's 16-wide k-half).  out[(LO + b) * ostride + 2 up + j] = sum over the warp's 32-wide K-slice.
 template <int H, int LO, int N>
-__device__ __forceinline__ void g3_mv(const g3_f2 (&w2)[16], const float (*x)[H], int k0, float* out, int ostride, int lane) {
-    g3_f2 a[N > 0 ? N : 1];
+__device__ __forceinline__ void g5_mv(const g5_f2 (&w2)[16], const float (*x)[H], int k0, float* out, int ostride, int lane) {
+    g5_f2 a0[2][N > 0 ? N : 1], a1[2][N > 0 ? N : 1];
 #pragma unroll
-    for (int b = 0; b < N; b++) a[b] = 0ull;
+    for (int b = 0; b < N; b++) { a0[0][b] = 0ull; a0[1][b] = 0ull; a1[0][b] = 0ull; a1[1][b] = 0ull; }
 #pragma unroll
-    for (int k4 = 0; k4 < 8; k4++) {
+    for (int k4 = 0; k4 < 4; k4++) {
+        ulonglong2 xv[N > 0 ? N : 1];
 #pragma unroll
-        for (int b = 0; b < N; b++) {
-            const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&x[LO + b][k0 + 4 * k4]);
-            a[b] = g3_fma2(w2[2 * k4], xv.x, a[b]);
-            a[b] = g3_fma2(w2[2 * k4 + 1], xv.y, a[b]);
+        for (int b = 0; b < N; b++) xv[b] = *reinterpret_cast<const ulonglong2*>(&x[LO + b][k0 + 4 * k4]);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+#pragma unroll
+            for (int b = 0; b < N; b++) a0[j][b] = g5_fma2(w2[8 * j + 2 * k4], xv[b].x, a0[j][b]);
+#pragma unroll
+            for (int b = 0; b < N; b++) a1[j][b] = g5_fma2(w2[8 * j + 2 * k4 + 1], xv[b].y, a1[j][b]);
         }
     }
 #pragma unroll
-    for (int b = 0; b < N; b++) out[(size_t)(LO + b) * ostride + lane] = g3_hsum(a[b]);
+    for (int b = 0; b < N; b++) {
+        float v0 = g5_hsum(a0[0][b]) + g5_hsum(a1[0][b]), v1 = g5_hsum(a0[1][b]) + g5_hsum(a1[1][b]);
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 16); v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
+        if (lane < 16) *reinterpret_cast<float2*>(&out[(size_t)(LO + b) * ostride + 2 * lane]) = make_float2(v0, v1);
+    }
 }
 // two gates that read the same state slice: the broadcasts are shared
 template <int H, int LO, int N, bool SAME>
-__device__ __forceinline__ void g3_mv2(const g3_f2 (&wa)[16], const g3_f2 (&wb)[16], const float (*xa)[H], const float (*xb)[H], int k0,
+__device__ __forceinline__ void g5_mv2(const g5_f2 (&wa)[16], const g5_f2 (&wb)[16], const float (*xa)[H], const float (*xb)[H], int k0,
                                        float* outa, float* outb, int ostride, int lane) {
-    g3_f2 a[N > 0 ? N : 1], c[N > 0 ? N : 1];
+    g5_f2 a[2][N > 0 ? N : 1], c[2][N > 0 ? N : 1];
 #pragma unroll
-    for (int b = 0; b < N; b++) { a[b] = 0ull; c[b] = 0ull; }
+    for (int b = 0; b < N; b++) { a[0][b] = 0ull; a[1][b] = 0ull; c[0][b] = 0ull; c[1][b] = 0ull; }
 #pragma unroll
-    for (int k4 = 0; k4 < 8; k4++) {
+    for (int k4 = 0; k4 < 4; k4++) {
+        ulonglong2 xv[N > 0 ? N : 1], yv[N > 0 ? N : 1];
 #pragma unroll
         for (int b = 0; b < N; b++) {
-            const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&xa[LO + b][k0 + 4 * k4]);
-            const ulonglong2 yv = SAME ? xv : *reinterpret_cast<const ulonglong2*>(&xb[LO + b][k0 + 4 * k4]);
-            a[b] = g3_fma2(wa[2 * k4], xv.x, a[b]); a[b] = g3_fma2(wa[2 * k4 + 1], xv.y, a[b]);
-            c[b] = g3_fma2(wb[2 * k4], yv.x, c[b]); c[b] = g3_fma2(wb[2 * k4 + 1], yv.y, c[b]);
+            xv[b] = *reinterpret_cast<const ulonglong2*>(&xa[LO + b][k0 + 4 * k4]);
+            yv[b] = SAME ? xv[b] : *reinterpret_cast<const ulonglong2*>(&xb[LO + b][k0 + 4 * k4]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+#pragma unroll
+            for (int b = 0; b < N; b++) { a[j][b] = g5_fma2(wa[8 * j + 2 * k4], xv[b].x, a[j][b]); c[j][b] = g5_fma2(wb[8 * j + 2 * k4], yv[b].x, c[j][b]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+#pragma unroll
+            for (int b = 0; b < N; b++) { a[j][b] = g5_fma2(wa[8 * j + 2 * k4 + 1], xv[b].y, a[j][b]); c[j][b] = g5_fma2(wb[8 * j + 2 * k4 + 1], yv[b].y, c[j][b]); }
         }
     }
 #pragma unroll
-    for (int b = 0; b < N; b++) { outa[(size_t)(LO + b) * ostride + lane] = g3_hsum(a[b]); outb[(size_t)(LO + b) * ostride + lane] = g3_hsum(c[b]); }
+    for (int b = 0; b < N; b++) {
+        float a0 = g5_hsum(a[0][b]), a1 = g5_hsum(a[1][b]), c0 = g5_hsum(c[0][b]), c1 = g5_hsum(c[1][b]);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+        c0 += __shfl_xor_sync(0xffffffffu, c0, 16); c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
+        if (lane < 16) {
+            *reinterpret_cast<float2*>(&outa[(size_t)(LO + b) * ostride + 2 * lane]) = make_float2(a0, a1);
+            *reinterpret_cast<float2*>(&outb[(size_t)(LO + b) * ostride + 2 * lane]) = make_float2(c0, c1);
+        }
+    }
 }
 
 template <int CS>
-__device__ __forceinline__ void g3_send(const uint32_t (&delta)[CS], uint32_t buf_a, uint32_t bar_a, float4 v) {
+__device__ __forceinline__ void g5_send(const uint32_t (&delta)[CS], uint32_t buf_a, uint32_t bar_a, float4 v) {
 #pragma unroll
     for (int d = 0; d < CS; d++) st_async_v4(buf_a + delta[d], v, bar_a + delta[d]);
 }
 template <int CS>
-__device__ __forceinline__ float4 g3_sum4(const float* part, int stride) {
+__device__ __forceinline__ float4 g5_sum4(const float* part, int stride) {
     float4 s = *reinterpret_cast<const float4*>(part);
 #pragma unroll
     for (int w = 1; w < CS; w++) {
@@ -88,7 +110,7 @@ __device__ __forceinline__ float4 g3_sum4(const float* part, int stride) {
     return s;
 }
 
-enum { G3_BAR_P1A = 1, G3_BAR_P1B, G3_BAR_P2A, G3_BAR_P2B };
+enum { G5_BAR_P1A = 1, G5_BAR_P1B, G5_BAR_P2A, G5_BAR_P2B };
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // forward.  Sub-batch A = utterances [0, NA), B = [NA, NA + NB) of the cluster's group (NB may be 0).
@@ -97,7 +119,7 @@ enum { G3_BAR_P1A = 1, G3_BAR_P1B, G3_BAR_P2A, G3_BAR_P2B };
 // 100..103 into p.clk -- mat-vec warps 0 and 7: slots 0..7 / 8..15, owner warps of sub-batches A / B: slots 16..19 / 20..23
 template <int H, int NA, int NB, bool TRACE = false>
 __global__ void __launch_bounds__(H + 128, 1)
-gru3_fwd_kernel(const GruSeqParams p) {
+gru5_fwd_kernel(const GruSeqParams p) {
     constexpr int CS = H / 32, BG = NA + NB, NTB = H + 64, NT = H + 128;      // NTB: participants of one named barrier (mat-vec + one owner pair)
     __shared__ __align__(16) float hbuf[BG][H];
     __shared__ __align__(16) float rhbuf[BG][H];
@@ -122,7 +144,7 @@ gru3_fwd_kernel(const GruSeqParams p) {
     for (int b = 0; b < BG; b++)
         if (b0 + b < p.B) Lgrp = max(Lgrp, p.lengths ? p.lengths[b0 + b] : p.Lmax);
     const bool tr_on = TRACE && p.clk != nullptr && blockIdx.x == 0 && lane == (warp >= H / 32 ? 8 : 0);      // owner warps: lane 8 sends r*h
-#define G3_TR(slot) do { if (TRACE) { if (tr_on && s >= 100 && s < 104) p.clk[(s - 100) * 32 + (slot)] = clock64(); } } while (0)
+#define G5_TR(slot) do { if (TRACE) { if (tr_on && s >= 100 && s < 104) p.clk[(s - 100) * 32 + (slot)] = clock64(); } } while (0)
 
     for (int i = tid; i < BG * H; i += NT) { (&hbuf[0][0])[i] = 0.f; (&rhbuf[0][0])[i] = 0.f; }      // Recurrent.lua:13,112
     if (!owner && lane == 0) {
@@ -136,49 +158,52 @@ gru3_fwd_kernel(const GruSeqParams p) {
 
     if (!owner) {
         // =========================== mat-vec warps ===========================
-        g3_f2 wz2[16], wr2[16], wh2[16];      // row (32 crank + lane) of each gate, columns [32 warp, +32) of the h block
+        g5_f2 wz2[16], wr2[16], wh2[16];      // rows 32 crank + 2 (lane & 15) + {0, 1} of each gate, columns [32 warp + 16 (lane >> 4), +16) of the h block
         {
-            const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw + (size_t)(32 * crank + lane) * p.ldw + 32 * warp;
 #pragma unroll
-            for (int k = 0; k < 32; k += 2) {
-                wz2[k / 2] = g3_pack(Wd[k], Wd[k + 1]);
-                wr2[k / 2] = g3_pack(Wd[(size_t)H * p.ldw + k], Wd[(size_t)H * p.ldw + k + 1]);
-                wh2[k / 2] = g3_pack(Wd[(size_t)2 * H * p.ldw + k], Wd[(size_t)2 * H * p.ldw + k + 1]);
+            for (int j = 0; j < 2; j++) {
+                const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw + (size_t)(32 * crank + 2 * (lane & 15) + j) * p.ldw + 32 * warp + 16 * (lane >> 4);
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) {
+                    wz2[8 * j + k / 2] = g5_pack(Wd[k], Wd[k + 1]);
+                    wr2[8 * j + k / 2] = g5_pack(Wd[(size_t)H * p.ldw + k], Wd[(size_t)H * p.ldw + k + 1]);
+                    wh2[8 * j + k / 2] = g5_pack(Wd[(size_t)2 * H * p.ldw + k], Wd[(size_t)2 * H * p.ldw + k + 1]);
+                }
             }
         }
-        const int k0 = 32 * warp;
+        const int k0 = 32 * warp + 16 * (lane >> 4);
         for (int s = 0; s < Lgrp; s++) {
             const unsigned ph = (unsigned)(s - 1) & 1u, pr = (unsigned)s & 1u;
             // phase 1, sub-batch A then B: each as soon as its source CTA's slice of h_{s-1} has landed
             const int trb = warp == 0 ? 0 : (warp == CS - 1 ? 8 : 24);      // (slots 24.. : scratch of the other warps, never read)
             if (s > 0) { mbar_wait(&bar_h[0][warp], ph); if (lane == 0) mbar_expect_tx(&bar_h[0][warp], TXA); }
-            G3_TR(trb + 0);
-            g3_mv2<H, 0, NA, true>(wz2, wr2, hbuf, hbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
-            if (!(p.dbg & 4)) __threadfence_block();          // (S2S_GRU_DBG=4 drops these fences: bar.arrive already orders the partial sums; measured neutral)
-            g3_bar_arrive(G3_BAR_P1A, NTB);
-            G3_TR(trb + 1);
+            G5_TR(trb + 0);
+            g5_mv2<H, 0, NA, true>(wz2, wr2, hbuf, hbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
+            if (!(p.dbg & 4)) __threadfence_block();
+            g5_bar_arrive(G5_BAR_P1A, NTB);
+            G5_TR(trb + 1);
             if (NB > 0) {
                 if (s > 0) { mbar_wait(&bar_h[1][warp], ph); if (lane == 0) mbar_expect_tx(&bar_h[1][warp], TXB); }
-                G3_TR(trb + 2);
-                g3_mv2<H, NA, NB, true>(wz2, wr2, hbuf, hbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
+                G5_TR(trb + 2);
+                g5_mv2<H, NA, NB, true>(wz2, wr2, hbuf, hbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
                 if (!(p.dbg & 4)) __threadfence_block();
-                g3_bar_arrive(G3_BAR_P1B, NTB);
-                G3_TR(trb + 3);
+                g5_bar_arrive(G5_BAR_P1B, NTB);
+                G5_TR(trb + 3);
             }
             // phase 2
             mbar_wait(&bar_rh[0][warp], pr); if (lane == 0) mbar_expect_tx(&bar_rh[0][warp], TXA);
-            G3_TR(trb + 4);
-            g3_mv<H, 0, NA>(wh2, rhbuf, k0, &part2[warp][0][0], 32, lane);
+            G5_TR(trb + 4);
+            g5_mv<H, 0, NA>(wh2, rhbuf, k0, &part2[warp][0][0], 32, lane);
             if (!(p.dbg & 4)) __threadfence_block();
-            g3_bar_arrive(G3_BAR_P2A, NTB);
-            G3_TR(trb + 5);
+            g5_bar_arrive(G5_BAR_P2A, NTB);
+            G5_TR(trb + 5);
             if (NB > 0) {
                 mbar_wait(&bar_rh[1][warp], pr); if (lane == 0) mbar_expect_tx(&bar_rh[1][warp], TXB);
-                G3_TR(trb + 6);
-                g3_mv<H, NA, NB>(wh2, rhbuf, k0, &part2[warp][0][0], 32, lane);
+                G5_TR(trb + 6);
+                g5_mv<H, NA, NB>(wh2, rhbuf, k0, &part2[warp][0][0], 32, lane);
                 if (!(p.dbg & 4)) __threadfence_block();
-                g3_bar_arrive(G3_BAR_P2B, NTB);
-                G3_TR(trb + 7);
+                g5_bar_arrive(G5_BAR_P2B, NTB);
+                G5_TR(trb + 7);
             }
         }
         if (Lgrp > 0) {      // the last h' slices have landed: nothing is in flight towards this CTA
@@ -201,7 +226,7 @@ gru3_fwd_kernel(const GruSeqParams p) {
             for (int d = 0; d < CS; d++) delta[d] = mapa_rank(smem_u32(&hbuf[0][0]), d) - smem_u32(&hbuf[0][0]);
             const uint32_t rh_dst = smem_u32(&rhbuf[f1b][u1]), h_dst = smem_u32(&hbuf[f2b][u2]);
             const uint32_t barrh_a = smem_u32(&bar_rh[sb][crank]), barh_a = smem_u32(&bar_h[sb][crank]);    // "from CTA crank" slots
-            const int bar1 = sb ? G3_BAR_P1B : G3_BAR_P1A, bar2 = sb ? G3_BAR_P2B : G3_BAR_P2A;
+            const int bar1 = sb ? G5_BAR_P1B : G5_BAR_P1A, bar2 = sb ? G5_BAR_P2B : G5_BAR_P2A;
             // input projections do not depend on the recurrence: step s+1's values are fetched while step s runs
             auto load_xp = [&](int s, int b, int Lb, int gate, int u) -> float4 {
                 if (s >= Lb) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -214,10 +239,10 @@ gru3_fwd_kernel(const GruSeqParams p) {
                 xp1n = load_xp(s + 1, f1b, L1, f1g, u1);
                 xp2n = load_xp(s + 1, f2b, L2, 2, u2);
                 const int tro = ((warp - CS) & 1) ? 28 : 16 + 4 * sb;        // first warp of each owner pair
-                g3_bar_sync(bar1, NTB);
-                G3_TR(tro + 0);
+                g5_bar_sync(bar1, NTB);
+                G5_TR(tro + 0);
                 if (fin1) {
-                    float4 v = g3_sum4<CS>(&part1[0][f1g][f1b][4 * f1q], 2 * BG * 32);
+                    float4 v = g5_sum4<CS>(&part1[0][f1g][f1b][4 * f1q], 2 * BG * 32);
                     v.x = sigmoid_acc(v.x + xp1.x); v.y = sigmoid_acc(v.y + xp1.y); v.z = sigmoid_acc(v.z + xp1.z); v.w = sigmoid_acc(v.w + xp1.w);   // GRU.lua:23-24
                     const bool act = s < L1;
                     const int t = rev ? L1 - 1 - s : s;
@@ -228,15 +253,15 @@ gru3_fwd_kernel(const GruSeqParams p) {
                     } else {
                         const float4 hp = *reinterpret_cast<const float4*>(&hbuf[f1b][u1]);
                         const float4 rh = make_float4(v.x * hp.x, v.y * hp.y, v.z * hp.z, v.w * hp.w);   // GRU.lua:25
-                        g3_send<CS>(delta, rh_dst, barrh_a, rh);
+                        g5_send<CS>(delta, rh_dst, barrh_a, rh);
                         if (act) { *reinterpret_cast<float4*>(sv + H + u1) = v; *reinterpret_cast<float4*>(sv + 3 * H + u1) = rh; }
                     }
                 }
-                G3_TR(tro + 1);
-                g3_bar_sync(bar2, NTB);                      // (also orders the z quads written above before their readers below)
-                G3_TR(tro + 2);
+                G5_TR(tro + 1);
+                g5_bar_sync(bar2, NTB);                      // (also orders the z quads written above before their readers below)
+                G5_TR(tro + 2);
                 if (fin2) {
-                    const float4 v = g3_sum4<CS>(&part2[0][f2b][4 * f2q], BG * 32);
+                    const float4 v = g5_sum4<CS>(&part2[0][f2b][4 * f2q], BG * 32);
                     const float4 hp = *reinterpret_cast<const float4*>(&hbuf[f2b][u2]);
                     float4 hn = hp;                                                                    // inactive: state frozen
                     if (s < L2) {
@@ -249,13 +274,13 @@ gru3_fwd_kernel(const GruSeqParams p) {
                         *reinterpret_cast<float4*>(p.save + (row * p.ndir + dir) * 4 * H + 2 * H + u2) = hc;
                         *reinterpret_cast<float4*>(p.y + row * (p.ndir * H) + dir * H + u2) = hn;
                     }
-                    g3_send<CS>(delta, h_dst, barh_a, hn);
+                    g5_send<CS>(delta, h_dst, barh_a, hn);
                 }
-                G3_TR(tro + 3);
+                G5_TR(tro + 3);
             }
         }
     }
-#undef G3_TR
+#undef G5_TR
     __syncthreads();
     cluster_sync_all();   // no CTA exits while a peer may still address its shared memory
 }
@@ -268,7 +293,7 @@ gru3_fwd_kernel(const GruSeqParams p) {
 // ---------------------------------------------------------------------------------------------------------------------------------
 template <int H, int NA, int NB>
 __global__ void __launch_bounds__(H + 128, 1)
-gru3_bwd_kernel(const GruSeqParams p) {
+gru5_bwd_kernel(const GruSeqParams p) {
     constexpr int CS = H / 32, BG = NA + NB, NTB = H + 64, NT = H + 128;      // NTB: participants of one named barrier (mat-vec + one owner pair)
     __shared__ __align__(16) float ahbuf[BG][H];   // dah (all units)
     __shared__ __align__(16) float azbuf[BG][H];   // daz
@@ -304,38 +329,41 @@ gru3_bwd_kernel(const GruSeqParams p) {
 
     if (!owner) {
         // transposed recurrent weights: input unit (32 crank + lane), output units [32 warp, +32) of each gate
-        g3_f2 wz2[16], wr2[16], wh2[16];
+        g5_f2 wz2[16], wr2[16], wh2[16];
         {
-            const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw + (size_t)(32 * warp) * p.ldw + 32 * crank + lane;
 #pragma unroll
-            for (int k = 0; k < 32; k += 2) {
-                wz2[k / 2] = g3_pack(Wd[(size_t)k * p.ldw], Wd[(size_t)(k + 1) * p.ldw]);
-                wr2[k / 2] = g3_pack(Wd[(size_t)(H + k) * p.ldw], Wd[(size_t)(H + k + 1) * p.ldw]);
-                wh2[k / 2] = g3_pack(Wd[(size_t)(2 * H + k) * p.ldw], Wd[(size_t)(2 * H + k + 1) * p.ldw]);
+            for (int j = 0; j < 2; j++) {
+                const float* Wd = p.W + (size_t)dir * 3 * H * p.ldw + (size_t)(32 * warp + 16 * (lane >> 4)) * p.ldw + 32 * crank + 2 * (lane & 15) + j;
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) {
+                    wz2[8 * j + k / 2] = g5_pack(Wd[(size_t)k * p.ldw], Wd[(size_t)(k + 1) * p.ldw]);
+                    wr2[8 * j + k / 2] = g5_pack(Wd[(size_t)(H + k) * p.ldw], Wd[(size_t)(H + k + 1) * p.ldw]);
+                    wh2[8 * j + k / 2] = g5_pack(Wd[(size_t)(2 * H + k) * p.ldw], Wd[(size_t)(2 * H + k + 1) * p.ldw]);
+                }
             }
         }
-        const int k0 = 32 * warp;
+        const int k0 = 32 * warp + 16 * (lane >> 4);
         unsigned par = 0;
         for (int s = Lgrp - 1; s >= 0; s--, par ^= 1u) {                                      // RNN.lua:183
             mbar_wait(&bar_a[0][warp], par); if (lane == 0) mbar_expect_tx(&bar_a[0][warp], 2 * TXA);
-            g3_mv2<H, 0, NA, false>(wh2, wz2, ahbuf, azbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
+            g5_mv2<H, 0, NA, false>(wh2, wz2, ahbuf, azbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
             if (!(p.dbg & 4)) __threadfence_block();
-            g3_bar_arrive(G3_BAR_P1A, NTB);
+            g5_bar_arrive(G5_BAR_P1A, NTB);
             if (NB > 0) {
                 mbar_wait(&bar_a[1][warp], par); if (lane == 0) mbar_expect_tx(&bar_a[1][warp], 2 * TXB);
-                g3_mv2<H, NA, NB, false>(wh2, wz2, ahbuf, azbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
+                g5_mv2<H, NA, NB, false>(wh2, wz2, ahbuf, azbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
                 if (!(p.dbg & 4)) __threadfence_block();
-                g3_bar_arrive(G3_BAR_P1B, NTB);
+                g5_bar_arrive(G5_BAR_P1B, NTB);
             }
             mbar_wait(&bar_r[0][warp], par); if (lane == 0) mbar_expect_tx(&bar_r[0][warp], TXA);
-            g3_mv<H, 0, NA>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
+            g5_mv<H, 0, NA>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
             if (!(p.dbg & 4)) __threadfence_block();
-            g3_bar_arrive(G3_BAR_P2A, NTB);
+            g5_bar_arrive(G5_BAR_P2A, NTB);
             if (NB > 0) {
                 mbar_wait(&bar_r[1][warp], par); if (lane == 0) mbar_expect_tx(&bar_r[1][warp], TXB);
-                g3_mv<H, NA, NB>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
+                g5_mv<H, NA, NB>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
                 if (!(p.dbg & 4)) __threadfence_block();
-                g3_bar_arrive(G3_BAR_P2B, NTB);
+                g5_bar_arrive(G5_BAR_P2B, NTB);
             }
         }
     } else {
@@ -350,7 +378,7 @@ gru3_bwd_kernel(const GruSeqParams p) {
             for (int d = 0; d < CS; d++) delta[d] = mapa_rank(smem_u32(&ahbuf[0][0]), d) - smem_u32(&ahbuf[0][0]);
             const uint32_t ah_dst = smem_u32(&ahbuf[ob][uo]), az_dst = smem_u32(&azbuf[ob][uo]), ar_dst = smem_u32(&arbuf[ob][uo]);
             const uint32_t bara_a = smem_u32(&bar_a[sb][crank]), barr_a = smem_u32(&bar_r[sb][crank]);
-            const int bar1 = sb ? G3_BAR_P1B : G3_BAR_P1A, bar2 = sb ? G3_BAR_P2B : G3_BAR_P2A;
+            const int bar1 = sb ? G5_BAR_P1B : G5_BAR_P1A, bar2 = sb ? G5_BAR_P2B : G5_BAR_P2A;
             // saved activations / incoming gradients do not depend on the recurrence: prefetched one step ahead
             struct Pre { float4 z, r, hc, hp, dy; };
             auto load_pre = [&](int s) -> Pre {
@@ -381,42 +409,42 @@ gru3_bwd_kernel(const GruSeqParams p) {
                     const int t = rev ? Lo - 1 - s : s;
                     const size_t row = (size_t)(b0 + ob) * p.Lmax + t;
                     rr = cur.r; hpv = cur.hp;
-#define G3_E(c)                                                                               \
+#define G5_E(c)                                                                               \
                     {                                                                         \
                         const float dh = cur.dy.c + carry.c;              /* RNN.lua:193-194 */ \
                         dah.c = dh * cur.z.c * (1.f - cur.hc.c * cur.hc.c);                   \
                         daz.c = dh * (cur.hc.c - cur.hp.c) * cur.z.c * (1.f - cur.z.c);       \
                         dhp.c = dh * (1.f - cur.z.c);                                         \
                     }
-                    G3_E(x) G3_E(y) G3_E(z) G3_E(w)
-#undef G3_E
+                    G5_E(x) G5_E(y) G5_E(z) G5_E(w)
+#undef G5_E
                     float* da = p.dA + row * (p.ndir * H3) + dir * H3;
                     *reinterpret_cast<float4*>(da + uo) = daz; *reinterpret_cast<float4*>(da + 2 * H + uo) = dah;
                     *reinterpret_cast<float4*>(p.hp_all + (row * p.ndir + dir) * H + uo) = cur.hp;
                 }
-                g3_send<CS>(delta, ah_dst, bara_a, dah);
-                g3_send<CS>(delta, az_dst, bara_a, daz);
+                g5_send<CS>(delta, ah_dst, bara_a, dah);
+                g5_send<CS>(delta, az_dst, bara_a, daz);
             };
             if (Lgrp > 0) phase_e(Lgrp - 1);
             for (int s = Lgrp - 1; s >= 0; s--) {
-                g3_bar_sync(bar1, NTB);
+                g5_bar_sync(bar1, NTB);
                 float4 pr = make_float4(0.f, 0.f, 0.f, 0.f), tz = pr;
                 if (own) {
-                    const float4 th = g3_sum4<CS>(&part1[0][0][ob][4 * oq], 2 * BG * 32);
+                    const float4 th = g5_sum4<CS>(&part1[0][0][ob][4 * oq], 2 * BG * 32);
                     float4 dar = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s < Lo) {
-                        tz = g3_sum4<CS>(&part1[0][1][ob][4 * oq], 2 * BG * 32);
+                        tz = g5_sum4<CS>(&part1[0][1][ob][4 * oq], 2 * BG * 32);
                         dar = make_float4(th.x * hpv.x * rr.x * (1.f - rr.x), th.y * hpv.y * rr.y * (1.f - rr.y),
                                           th.z * hpv.z * rr.z * (1.f - rr.z), th.w * hpv.w * rr.w * (1.f - rr.w));
                         pr = make_float4(th.x * rr.x, th.y * rr.y, th.z * rr.z, th.w * rr.w);
                         const int t = rev ? Lo - 1 - s : s;
                         *reinterpret_cast<float4*>(p.dA + ((size_t)(b0 + ob) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + H + uo) = dar;
                     }
-                    g3_send<CS>(delta, ar_dst, barr_a, dar);
+                    g5_send<CS>(delta, ar_dst, barr_a, dar);
                 }
-                g3_bar_sync(bar2, NTB);
+                g5_bar_sync(bar2, NTB);
                 if (own && s < Lo) {
-                    const float4 tr = g3_sum4<CS>(&part2[0][ob][4 * oq], BG * 32);
+                    const float4 tr = g5_sum4<CS>(&part2[0][ob][4 * oq], BG * 32);
                     carry = make_float4(dhp.x + pr.x + tz.x + tr.x, dhp.y + pr.y + tz.y + tr.y, dhp.z + pr.z + tz.z + tr.z, dhp.w + pr.w + tz.w + tr.w);
                 }
                 if (s > 0) phase_e(s - 1);                   // the next step's E right behind the carry
@@ -429,7 +457,7 @@ gru3_bwd_kernel(const GruSeqParams p) {
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 template <int H, int BG, bool BWD>
-static int g3_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters) {
+static int g5_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters) {
     constexpr int CS = H / 32, NA = (BG + 1) / 2, NB = BG - NA;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS * ceil_div(p.B, BG) * p.ndir);
@@ -441,7 +469,7 @@ static int g3_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters)
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     void (*kern)(const GruSeqParams);
-    if constexpr (BWD) kern = gru3_bwd_kernel<H, NA, NB>; else kern = gru3_fwd_kernel<H, NA, NB>;
+    if constexpr (BWD) kern = gru5_bwd_kernel<H, NA, NB>; else kern = gru5_fwd_kernel<H, NA, NB>;
     if (max_clusters) {
         if (cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
         return 0;
@@ -454,7 +482,7 @@ static int g3_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters)
             if (!buf) S2S_CUDA(cudaMalloc(&buf, 4 * 32 * sizeof(long long)));
             S2S_CUDA(cudaMemsetAsync(buf, 0, 4 * 32 * sizeof(long long), ctx->stream));
             GruSeqParams q = p; q.clk = buf;
-            S2S_CUDA(cudaLaunchKernelEx(&cfg, gru3_fwd_kernel<H, NA, NB, true>, q));
+            S2S_CUDA(cudaLaunchKernelEx(&cfg, gru5_fwd_kernel<H, NA, NB, true>, q));
             long long hb[4 * 32];
             S2S_CUDA(cudaMemcpyAsync(hb, buf, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
             S2S_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -463,7 +491,7 @@ static int g3_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters)
                                             "mv7 hA landed", "mv7 P1A done", "mv7 hB landed", "mv7 P1B done", "mv7 rhA landed", "mv7 P2A done", "mv7 rhB landed", "mv7 P2B done",
                                             "ownA bar1", "ownA fin1 sent", "ownA bar2", "ownA fin2 sent", "ownB bar1", "ownB fin1 sent", "ownB bar2", "ownB fin2 sent"};
             for (int st = 0; st < 4; st++) {
-                fprintf(stderr, "[gru trace] step %d:", 100 + st);
+                fprintf(stderr, "[gru5 trace] step %d:", 100 + st);
                 for (int e = 0; e < 24; e++) fprintf(stderr, " %s=%lld", names[e], hb[st * 32 + e] - t0);
                 fprintf(stderr, "\n");
             }
@@ -475,11 +503,11 @@ static int g3_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters)
 }
 
 template <int H, bool BWD>
-static int g3_launch_hb(s2s_ctx* ctx, const GruSeqParams& p) {
+static int g5_launch_hb(s2s_ctx* ctx, const GruSeqParams& p) {
     static int cap = 0;            // co-resident clusters, queried once per process (one device per process: s2s_ctx_create)
     if (cap == 0) {
         int n = 0;
-        S2S_TRY((g3_launch_geo<H, 4, BWD>(ctx, p, &n)));
+        S2S_TRY((g5_launch_geo<H, 4, BWD>(ctx, p, &n)));
         cap = n > 0 ? n : 1;
     }
     // one wave of clusters: the smallest group size for which every cluster is co-resident (a second wave would double the time).
@@ -489,21 +517,21 @@ static int g3_launch_hb(s2s_ctx* ctx, const GruSeqParams& p) {
     while (bg < BGMAX && p.ndir * ceil_div(p.B, bg) > cap) bg++;
     { const char* e = getenv("S2S_GRU_BG"); if (e && atoi(e) >= 1 && atoi(e) <= BGMAX) bg = atoi(e); }
     switch (bg) {
-        case 1: return g3_launch_geo<H, 1, BWD>(ctx, p, nullptr);
-        case 2: return g3_launch_geo<H, 2, BWD>(ctx, p, nullptr);
-        case 3: return g3_launch_geo<H, 3, BWD>(ctx, p, nullptr);
-        case 4: return g3_launch_geo<H, 4, BWD>(ctx, p, nullptr);
-        case 5: return g3_launch_geo<H, 5, BWD>(ctx, p, nullptr);
-        case 6: return g3_launch_geo<H, 6, BWD>(ctx, p, nullptr);
-        case 7: return g3_launch_geo<H, 7, BWD>(ctx, p, nullptr);
-        default: return g3_launch_geo<H, BGMAX, BWD>(ctx, p, nullptr);
+        case 1: return g5_launch_geo<H, 1, BWD>(ctx, p, nullptr);
+        case 2: return g5_launch_geo<H, 2, BWD>(ctx, p, nullptr);
+        case 3: return g5_launch_geo<H, 3, BWD>(ctx, p, nullptr);
+        case 4: return g5_launch_geo<H, 4, BWD>(ctx, p, nullptr);
+        case 5: return g5_launch_geo<H, 5, BWD>(ctx, p, nullptr);
+        case 6: return g5_launch_geo<H, 6, BWD>(ctx, p, nullptr);
+        case 7: return g5_launch_geo<H, 7, BWD>(ctx, p, nullptr);
+        default: return g5_launch_geo<H, BGMAX, BWD>(ctx, p, nullptr);
     }
 }
 
 // launches the recurrence of one layer (all directions and utterances); H in {128, 256}
-int gru_cluster3_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H) {
-    if (H == 256) return backward ? g3_launch_hb<256, true>(ctx, p) : g3_launch_hb<256, false>(ctx, p);
-    return backward ? g3_launch_hb<128, true>(ctx, p) : g3_launch_hb<128, false>(ctx, p);
+int gru_cluster5_launch(s2s_ctx* ctx, bool backward, const GruSeqParams& p, int H) {
+    if (H == 256) return backward ? g5_launch_hb<256, true>(ctx, p) : g5_launch_hb<256, false>(ctx, p);
+    return backward ? g5_launch_hb<128, true>(ctx, p) : g5_launch_hb<128, false>(ctx, p);
 }
 
 }  // namespace s2s
