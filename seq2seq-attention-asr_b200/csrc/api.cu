@@ -30,6 +30,13 @@ static void graph_drop(s2s_ctx* ctx) {
 }
 
 namespace s2s {
+// every CUDA graph of the context (the cached s2s_model_fwdbwd graph and caller-defined ones): a graph that holds NCCL kernel nodes must be
+// gone before its communicator is destroyed (ncclCommDestroy waits for it otherwise)
+void graphs_release(s2s_ctx* ctx) {
+    graph_drop(ctx);
+    for (cudaGraphExec_t& g : ctx->user_graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    ctx->arena.frozen = false; ctx->persist.frozen = false;
+}
 int labels_from_onehot(s2s_ctx* ctx, const float* onehot, int64_t rows, int V, int* labels);
 int onehot_from_labels(s2s_ctx* ctx, const int* labels, int64_t rows, int V, float* onehot);
 void vgg_state_free(s2s_ctx* ctx);

@@ -17,6 +17,8 @@
 
 namespace s2s {
 
+void graphs_release(s2s_ctx* ctx);      // api.cu
+
 typedef struct ncclComm* nccl_comm_t;
 struct nccl_uid { char internal[128]; };          // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
 enum { NCCL_FLOAT32 = 7, NCCL_SUM = 0 };          // ncclFloat32, ncclSum (nccl.h)
@@ -184,6 +186,7 @@ int s2s_dp_destroy(s2s_ctx* ctx) {
     if (ctx->dp) {
         cudaStreamSynchronize(ctx->stream);
         if (ctx->side[1]) cudaStreamSynchronize(ctx->side[1]);
+        graphs_release(ctx);          // captured collectives reference the communicator
         dp_state_free(ctx);
     }
     return 0;

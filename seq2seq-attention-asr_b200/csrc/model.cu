@@ -155,7 +155,10 @@ int model_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, cons
                 S2S_TRY(rc);
                 S2S_CUDA(cudaEventRecord(ctx->ev[3], ctx->side[1]));        // the join event of gru_seq_wgrad_join now also covers the reduce
             } else {
-                S2S_TRY(dp_allreduce_bucket(ctx, G + off, end - off, false));
+                // layer 0's weight gradients ran on the main stream; its bucket still goes to the side stream so that EVERY collective of
+                // the step is issued on one stream, in one order, on every rank (a communicator must not be driven from two streams that
+                // are not ordered with respect to each other -- inside a captured graph nothing else would order them)
+                S2S_TRY(dp_allreduce_bucket(ctx, G + off, end - off, true));
             }
         }
     }
