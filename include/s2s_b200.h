@@ -134,7 +134,7 @@ int  s2s_dp_broadcast(s2s_ctx* ctx, float* P, int64_t n, int root);
  * side stream under the remaining backward pass; on return (in stream order) G is the global gradient sum and s2s_dp_allreduce must
  * not be called again for it. */
 int  s2s_dp_set_overlap(s2s_ctx* ctx, int enable);
-int  s2s_dp_destroy(s2s_ctx* ctx);
+int  s2s_dp_destroy(s2s_ctx* ctx);                                     /* releases the context's CUDA graphs first (captured collectives reference the communicator) */
 
 /* ---- flat parameter layout (what module:getParameters() flattens to; timit/timit.lua:172) -- */
 int64_t s2s_param_count(const s2s_model_cfg* cfg);
@@ -237,8 +237,11 @@ int s2s_attention_step(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P,
                        const float* h, const float* Vh, const int* lengths, int B, int Lmax,
                        const int* yprev, const float* alpha_prev, const float* s_prev,
                        float* alpha, float* s, float* logp);
-/* Attention:BeamSearch (Attention.lua:332-438) for one utterance, beams batched on the device.
- * h [L,A]; writes up to maxlen labels to out_host; returns the length through n_out_host. */
+/* Attention:BeamSearch (Attention.lua:332-438) for one utterance.  The beams are a batch through the decoder step and the whole
+ * search state (scores, top-k selection :406-408, finished list :418-421, label sequences) stays on the device; the host reads a
+ * 16-byte status every 8 labels and the winning hypothesis (:435) once.  h [L,A]; writes up to maxlen + 1 labels to out_host
+ * (the first label plus maxlen extensions); returns the length through n_out_host and the total log-probability through
+ * logp_out_host (may be NULL). */
 int s2s_beam_search(s2s_ctx* ctx, const s2s_model_cfg* cfg, const float* P, const float* h, int L,
                     int eos, int beam, int maxlen, int* out_host, int* n_out_host, float* logp_out_host);
 
