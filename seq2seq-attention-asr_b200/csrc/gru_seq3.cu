@@ -266,7 +266,11 @@ gru3_fwd_kernel(const GruSeqParams p) {
 //   P1  warp w: W_h[:, own]^T dah[slice w], W_z[:, own]^T daz[slice w]   ->  d(r h) ; dar = d(r h) h_prev r (1-r)    -> all-gather dar
 //   P2  warp w: W_r[:, own]^T dar[slice w]                               ->  carry = dh (1-z) + d(r h) r + W_z^T daz + W_r^T dar
 // ---------------------------------------------------------------------------------------------------------------------------------
-template <int H, int NA, int NB>
+// ZP2 (S2S_GRU_ZP2=1, experiment): the W_z^T daz product moves from phase 1 to phase 2.  Phase 1 then needs dah alone, so the first
+// exchange of a step is 8 instead of 16 sends per owner thread in front of the mat-vec.  daz is sent at the START of the step's first
+// finalisation (behind the named barrier of phase 1): by then every peer has finished phase 2 of the previous step -- its dah of this
+// step, which phase 1 waited for, was sent after it -- so the single daz buffer and the per-source barrier of phase 2 are free again.
+template <int H, int NA, int NB, bool ZP2 = false>
 __global__ void __launch_bounds__(H + 128, 1)
 gru3_bwd_kernel(const GruSeqParams p) {
     constexpr int CS = H / 32, BG = NA + NB, NTB = H + 64, NT = H + 128;      // NTB: participants of one named barrier (mat-vec + one owner pair)
@@ -296,8 +300,9 @@ gru3_bwd_kernel(const GruSeqParams p) {
     if (!owner && lane == 0) {
         mbar_init(&bar_a[0][warp], 1); mbar_init(&bar_r[0][warp], 1); mbar_init(&bar_a[1][warp], 1); mbar_init(&bar_r[1][warp], 1);
         fence_mbar_init();
-        mbar_expect_tx(&bar_a[0][warp], 2 * TXA); mbar_expect_tx(&bar_r[0][warp], TXA);
-        if (NB > 0) { mbar_expect_tx(&bar_a[1][warp], 2 * TXB); mbar_expect_tx(&bar_r[1][warp], TXB); }
+        constexpr unsigned MA = ZP2 ? 1 : 2, MR = ZP2 ? 2 : 1;      // slices per exchange on the two barriers
+        mbar_expect_tx(&bar_a[0][warp], MA * TXA); mbar_expect_tx(&bar_r[0][warp], MR * TXA);
+        if (NB > 0) { mbar_expect_tx(&bar_a[1][warp], MA * TXB); mbar_expect_tx(&bar_r[1][warp], MR * TXB); }
     }
     __syncthreads();
     cluster_sync_all();
@@ -316,24 +321,30 @@ gru3_bwd_kernel(const GruSeqParams p) {
         }
         const int k0 = 32 * warp;
         unsigned par = 0;
+        constexpr unsigned MA = ZP2 ? 1 : 2, MR = ZP2 ? 2 : 1;
         for (int s = Lgrp - 1; s >= 0; s--, par ^= 1u) {                                      // RNN.lua:183
-            mbar_wait(&bar_a[0][warp], par); if (lane == 0) mbar_expect_tx(&bar_a[0][warp], 2 * TXA);
-            g3_mv2<H, 0, NA, false>(wh2, wz2, ahbuf, azbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
+            const float (*az)[H] = azbuf;
+            mbar_wait(&bar_a[0][warp], par); if (lane == 0) mbar_expect_tx(&bar_a[0][warp], MA * TXA);
+            if (ZP2) g3_mv<H, 0, NA>(wh2, ahbuf, k0, &part1[warp][0][0][0], 32, lane);
+            else g3_mv2<H, 0, NA, false>(wh2, wz2, ahbuf, az, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
             if (!(p.dbg & 4)) __threadfence_block();
             g3_bar_arrive(G3_BAR_P1A, NTB);
             if (NB > 0) {
-                mbar_wait(&bar_a[1][warp], par); if (lane == 0) mbar_expect_tx(&bar_a[1][warp], 2 * TXB);
-                g3_mv2<H, NA, NB, false>(wh2, wz2, ahbuf, azbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
+                mbar_wait(&bar_a[1][warp], par); if (lane == 0) mbar_expect_tx(&bar_a[1][warp], MA * TXB);
+                if (ZP2) g3_mv<H, NA, NB>(wh2, ahbuf, k0, &part1[warp][0][0][0], 32, lane);
+                else g3_mv2<H, NA, NB, false>(wh2, wz2, ahbuf, az, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
                 if (!(p.dbg & 4)) __threadfence_block();
                 g3_bar_arrive(G3_BAR_P1B, NTB);
             }
-            mbar_wait(&bar_r[0][warp], par); if (lane == 0) mbar_expect_tx(&bar_r[0][warp], TXA);
-            g3_mv<H, 0, NA>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
+            mbar_wait(&bar_r[0][warp], par); if (lane == 0) mbar_expect_tx(&bar_r[0][warp], MR * TXA);
+            if (ZP2) g3_mv2<H, 0, NA, false>(wz2, wr2, az, arbuf, k0, &part1[warp][1][0][0], &part2[warp][0][0], 32, lane);
+            else g3_mv<H, 0, NA>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
             if (!(p.dbg & 4)) __threadfence_block();
             g3_bar_arrive(G3_BAR_P2A, NTB);
             if (NB > 0) {
-                mbar_wait(&bar_r[1][warp], par); if (lane == 0) mbar_expect_tx(&bar_r[1][warp], TXB);
-                g3_mv<H, NA, NB>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
+                mbar_wait(&bar_r[1][warp], par); if (lane == 0) mbar_expect_tx(&bar_r[1][warp], MR * TXB);
+                if (ZP2) g3_mv2<H, NA, NB, false>(wz2, wr2, az, arbuf, k0, &part1[warp][1][0][0], &part2[warp][0][0], 32, lane);
+                else g3_mv<H, NA, NB>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
                 if (!(p.dbg & 4)) __threadfence_block();
                 g3_bar_arrive(G3_BAR_P2B, NTB);
             }
@@ -349,6 +360,7 @@ gru3_bwd_kernel(const GruSeqParams p) {
 #pragma unroll
             for (int d = 0; d < CS; d++) delta[d] = mapa_rank(smem_u32(&ahbuf[0][0]), d) - smem_u32(&ahbuf[0][0]);
             const uint32_t ah_dst = smem_u32(&ahbuf[ob][uo]), az_dst = smem_u32(&azbuf[ob][uo]), ar_dst = smem_u32(&arbuf[ob][uo]);
+            float4 daz_keep = make_float4(0.f, 0.f, 0.f, 0.f);  // ZP2: daz of the current step, sent from the first finalisation
             const uint32_t bara_a = smem_u32(&bar_a[sb][crank]), barr_a = smem_u32(&bar_r[sb][crank]);
             const int bar1 = sb ? G3_BAR_P1B : G3_BAR_P1A, bar2 = sb ? G3_BAR_P2B : G3_BAR_P2A;
             // saved activations / incoming gradients do not depend on the recurrence: prefetched one step ahead
@@ -395,17 +407,19 @@ gru3_bwd_kernel(const GruSeqParams p) {
                     *reinterpret_cast<float4*>(p.hp_all + (row * p.ndir + dir) * H + uo) = cur.hp;
                 }
                 g3_send<CS>(delta, ah_dst, bara_a, dah);
-                g3_send<CS>(delta, az_dst, bara_a, daz);
+                if (ZP2) daz_keep = daz;
+                else g3_send<CS>(delta, az_dst, bara_a, daz);
             };
             if (Lgrp > 0) phase_e(Lgrp - 1);
             for (int s = Lgrp - 1; s >= 0; s--) {
                 g3_bar_sync(bar1, NTB);
                 float4 pr = make_float4(0.f, 0.f, 0.f, 0.f), tz = pr;
                 if (own) {
+                    if (ZP2) g3_send<CS>(delta, az_dst, barr_a, daz_keep);
                     const float4 th = g3_sum4<CS>(&part1[0][0][ob][4 * oq], 2 * BG * 32);
                     float4 dar = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s < Lo) {
-                        tz = g3_sum4<CS>(&part1[0][1][ob][4 * oq], 2 * BG * 32);
+                        if (!ZP2) tz = g3_sum4<CS>(&part1[0][1][ob][4 * oq], 2 * BG * 32);
                         dar = make_float4(th.x * hpv.x * rr.x * (1.f - rr.x), th.y * hpv.y * rr.y * (1.f - rr.y),
                                           th.z * hpv.z * rr.z * (1.f - rr.z), th.w * hpv.w * rr.w * (1.f - rr.w));
                         pr = make_float4(th.x * rr.x, th.y * rr.y, th.z * rr.z, th.w * rr.w);
@@ -416,6 +430,7 @@ gru3_bwd_kernel(const GruSeqParams p) {
                 }
                 g3_bar_sync(bar2, NTB);
                 if (own && s < Lo) {
+                    if (ZP2) tz = g3_sum4<CS>(&part1[0][1][ob][4 * oq], 2 * BG * 32);
                     const float4 tr = g3_sum4<CS>(&part2[0][ob][4 * oq], BG * 32);
                     carry = make_float4(dhp.x + pr.x + tz.x + tr.x, dhp.y + pr.y + tz.y + tr.y, dhp.z + pr.z + tz.z + tr.z, dhp.w + pr.w + tz.w + tr.w);
                 }
@@ -441,7 +456,11 @@ static int g3_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters)
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     void (*kern)(const GruSeqParams);
-    if constexpr (BWD) kern = gru3_bwd_kernel<H, NA, NB>; else kern = gru3_fwd_kernel<H, NA, NB>;
+    if constexpr (BWD) {
+        static int zp2 = -1;
+        if (zp2 < 0) { const char* e = getenv("S2S_GRU_ZP2"); zp2 = e ? atoi(e) : 0; }
+        kern = zp2 ? gru3_bwd_kernel<H, NA, NB, true> : gru3_bwd_kernel<H, NA, NB, false>;
+    } else kern = gru3_fwd_kernel<H, NA, NB>;
     if (max_clusters) {
         if (cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
         return 0;
