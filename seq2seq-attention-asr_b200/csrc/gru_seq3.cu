@@ -206,8 +206,10 @@ gru3_fwd_kernel(const GruSeqParams p) {
             auto load_xp = [&](int s, int b, int Lb, int gate, int u) -> float4 {
                 if (s >= Lb) return make_float4(0.f, 0.f, 0.f, 0.f);
                 const int t = rev ? Lb - 1 - s : s;
-                return __ldg(reinterpret_cast<const float4*>(p.xp + ((size_t)(b0 + b) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + gate * H + u));
+                return ldg_stream(p.xp + ((size_t)(b0 + b) * p.Lmax + t) * (p.ndir * H3) + dir * H3 + gate * H + u);
             };
+            // (issued at the top of a step and consumed 1300 / 2400 cycles later, behind the named barriers: the L2 round trip is hidden.
+            // The backward kernel needed more care -- see its phase_e.)
             float4 xp1n = load_xp(0, f1b, L1, f1g, u1), xp2n = load_xp(0, f2b, L2, 2, u2);
             for (int s = 0; s < Lgrp; s++) {
                 const float4 xp1 = xp1n, xp2 = xp2n;
@@ -270,7 +272,7 @@ gru3_fwd_kernel(const GruSeqParams p) {
 // exchange of a step is 8 instead of 16 sends per owner thread in front of the mat-vec.  daz is sent at the START of the step's first
 // finalisation (behind the named barrier of phase 1): by then every peer has finished phase 2 of the previous step -- its dah of this
 // step, which phase 1 waited for, was sent after it -- so the single daz buffer and the per-source barrier of phase 2 are free again.
-template <int H, int NA, int NB, bool ZP2 = false>
+template <int H, int NA, int NB, bool ZP2 = false, bool TRACE = false>
 __global__ void __launch_bounds__(H + 128, 1)
 gru3_bwd_kernel(const GruSeqParams p) {
     constexpr int CS = H / 32, BG = NA + NB, NTB = H + 64, NT = H + 128;      // NTB: participants of one named barrier (mat-vec + one owner pair)
@@ -296,6 +298,9 @@ gru3_bwd_kernel(const GruSeqParams p) {
 #pragma unroll
     for (int b = 0; b < BG; b++)
         if (b0 + b < p.B) Lgrp = max(Lgrp, p.lengths ? p.lengths[b0 + b] : p.Lmax);
+    // TRACE (S2S_GRU_TRACE=2): as in the forward kernel, steps Lgrp-101 .. Lgrp-104 (the 100th .. 103rd executed)
+    const bool tr_on = TRACE && p.clk != nullptr && blockIdx.x == 0 && lane == 0;
+#define G3_TRB(slot) do { if (TRACE) { const int e_ = Lgrp - 1 - s; if (tr_on && (slot) >= 0 && e_ >= 100 && e_ < 104) p.clk[(e_ - 100) * 32 + (slot)] = clock64(); } } while (0)
 
     if (!owner && lane == 0) {
         mbar_init(&bar_a[0][warp], 1); mbar_init(&bar_r[0][warp], 1); mbar_init(&bar_a[1][warp], 1); mbar_init(&bar_r[1][warp], 1);
@@ -324,29 +329,38 @@ gru3_bwd_kernel(const GruSeqParams p) {
         constexpr unsigned MA = ZP2 ? 1 : 2, MR = ZP2 ? 2 : 1;
         for (int s = Lgrp - 1; s >= 0; s--, par ^= 1u) {                                      // RNN.lua:183
             const float (*az)[H] = azbuf;
+            const int trb = warp == 0 ? 0 : (warp == CS - 1 ? 8 : -100);
             mbar_wait(&bar_a[0][warp], par); if (lane == 0) mbar_expect_tx(&bar_a[0][warp], MA * TXA);
+            G3_TRB(trb + 0);
             if (ZP2) g3_mv<H, 0, NA>(wh2, ahbuf, k0, &part1[warp][0][0][0], 32, lane);
             else g3_mv2<H, 0, NA, false>(wh2, wz2, ahbuf, az, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
             if (!(p.dbg & 4)) __threadfence_block();
             g3_bar_arrive(G3_BAR_P1A, NTB);
+            G3_TRB(trb + 1);
             if (NB > 0) {
                 mbar_wait(&bar_a[1][warp], par); if (lane == 0) mbar_expect_tx(&bar_a[1][warp], MA * TXB);
+                G3_TRB(trb + 2);
                 if (ZP2) g3_mv<H, NA, NB>(wh2, ahbuf, k0, &part1[warp][0][0][0], 32, lane);
                 else g3_mv2<H, NA, NB, false>(wh2, wz2, ahbuf, az, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
                 if (!(p.dbg & 4)) __threadfence_block();
                 g3_bar_arrive(G3_BAR_P1B, NTB);
+                G3_TRB(trb + 3);
             }
             mbar_wait(&bar_r[0][warp], par); if (lane == 0) mbar_expect_tx(&bar_r[0][warp], MR * TXA);
+            G3_TRB(trb + 4);
             if (ZP2) g3_mv2<H, 0, NA, false>(wz2, wr2, az, arbuf, k0, &part1[warp][1][0][0], &part2[warp][0][0], 32, lane);
             else g3_mv<H, 0, NA>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
             if (!(p.dbg & 4)) __threadfence_block();
             g3_bar_arrive(G3_BAR_P2A, NTB);
+            G3_TRB(trb + 5);
             if (NB > 0) {
                 mbar_wait(&bar_r[1][warp], par); if (lane == 0) mbar_expect_tx(&bar_r[1][warp], MR * TXB);
+                G3_TRB(trb + 6);
                 if (ZP2) g3_mv2<H, NA, NB, false>(wz2, wr2, az, arbuf, k0, &part1[warp][1][0][0], &part2[warp][0][0], 32, lane);
                 else g3_mv<H, NA, NB>(wr2, arbuf, k0, &part2[warp][0][0], 32, lane);
                 if (!(p.dbg & 4)) __threadfence_block();
                 g3_bar_arrive(G3_BAR_P2B, NTB);
+                G3_TRB(trb + 7);
             }
         }
     } else {
@@ -372,27 +386,35 @@ gru3_bwd_kernel(const GruSeqParams p) {
                 const int t = rev ? Lo - 1 - s : s;
                 const size_t row = (size_t)(b0 + ob) * p.Lmax + t;
                 const float* sv = p.save + (row * p.ndir + dir) * 4 * H;
-                q.z = __ldg(reinterpret_cast<const float4*>(sv + uo)); q.r = __ldg(reinterpret_cast<const float4*>(sv + H + uo));
-                q.hc = __ldg(reinterpret_cast<const float4*>(sv + 2 * H + uo));
+                // asm volatile loads: a plain __ldg may be re-executed / sunk to its use by the compiler, which would put the whole
+                // global-memory latency of these five vectors between the carry and the sends of the next step
+                q.z = ldg_stream(sv + uo); q.r = ldg_stream(sv + H + uo);
+                q.hc = ldg_stream(sv + 2 * H + uo);
                 if (s > 0) {                                                                      // RNN.lua:186-192
                     const int tp = rev ? t + 1 : t - 1;
-                    q.hp = __ldg(reinterpret_cast<const float4*>(p.y + ((size_t)(b0 + ob) * p.Lmax + tp) * (p.ndir * H) + dir * H + uo));
+                    q.hp = ldg_stream(p.y + ((size_t)(b0 + ob) * p.Lmax + tp) * (p.ndir * H) + dir * H + uo);
                 }
-                q.dy = __ldg(reinterpret_cast<const float4*>(p.dy + row * (p.ndir * H) + dir * H + uo));
+                q.dy = ldg_stream(p.dy + row * (p.ndir * H) + dir * H + uo);
                 return q;
             };
             Pre nxt = load_pre(Lgrp - 1);
             float4 carry = make_float4(0.f, 0.f, 0.f, 0.f), dhp = carry, rr = carry, hpv = carry;
-            auto phase_e = [&](int s) {          // elementwise part of step s; sends dah, daz
+            const int tro_e = ((warp - CS) & 1) ? -100 : 16 + 8 * sb;
+            auto phase_e = [&](int s_e) {        // elementwise part of step s_e; sends dah, daz
                 if (!own) return;
+                const int s = s_e + 1;           // (trace stamps are filed under the step whose carry feeds this E)
                 const Pre cur = nxt;
-                nxt = load_pre(s - 1);
+                G3_TRB(tro_e + 3);
                 float4 dah = make_float4(0.f, 0.f, 0.f, 0.f), daz = dah;
                 dhp = dah;
-                if (s < Lo) {
-                    const int t = rev ? Lo - 1 - s : s;
+                if (s_e < Lo) {
+                    const int t = rev ? Lo - 1 - s_e : s_e;
                     const size_t row = (size_t)(b0 + ob) * p.Lmax + t;
-                    rr = cur.r; hpv = cur.hp;
+                    // (forced register copies: the first finalisation must not read registers a younger load's scoreboard guards)
+                    asm volatile("mov.b32 %0, %4; mov.b32 %1, %5; mov.b32 %2, %6; mov.b32 %3, %7;"
+                                 : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w) : "f"(cur.r.x), "f"(cur.r.y), "f"(cur.r.z), "f"(cur.r.w));
+                    asm volatile("mov.b32 %0, %4; mov.b32 %1, %5; mov.b32 %2, %6; mov.b32 %3, %7;"
+                                 : "=f"(hpv.x), "=f"(hpv.y), "=f"(hpv.z), "=f"(hpv.w) : "f"(cur.hp.x), "f"(cur.hp.y), "f"(cur.hp.z), "f"(cur.hp.w));
 #define G3_E(c)                                                                               \
                     {                                                                         \
                         const float dh = cur.dy.c + carry.c;              /* RNN.lua:193-194 */ \
@@ -406,9 +428,19 @@ gru3_bwd_kernel(const GruSeqParams p) {
                     *reinterpret_cast<float4*>(da + uo) = daz; *reinterpret_cast<float4*>(da + 2 * H + uo) = dah;
                     *reinterpret_cast<float4*>(p.hp_all + (row * p.ndir + dir) * H + uo) = cur.hp;
                 }
+                if (TRACE) { if (tr_on && dah.x == 1e30f) p.clk[31] = 0; }
+                G3_TRB(tro_e + 4);
                 g3_send<CS>(delta, ah_dst, bara_a, dah);
+                G3_TRB(tro_e + 5);
                 if (ZP2) daz_keep = daz;
                 else g3_send<CS>(delta, az_dst, bara_a, daz);
+                // Prefetch discipline: the loads of the NEXT step's operands are issued only after this step's values have been consumed
+                // and sent.  A consumer waits for its scoreboard counter to drain, and the next iteration's loads -- the same static
+                // instructions -- count on the same scoreboard: issued at the top of this lambda, they made the elementwise part wait for a
+                // full global-memory round trip on the critical chain carry -> dah (S2S_GRU_TRACE=2: 1100-1600 cycles between "loads
+                // issued" and the first dependent store; 200 now; backward step 2.38 -> 1.78 us).  The loads are asm volatile, so the
+                // compiler keeps them where they are written.
+                nxt = load_pre(s_e - 1);
             };
             if (Lgrp > 0) phase_e(Lgrp - 1);
             for (int s = Lgrp - 1; s >= 0; s--) {
@@ -428,16 +460,22 @@ gru3_bwd_kernel(const GruSeqParams p) {
                     }
                     g3_send<CS>(delta, ar_dst, barr_a, dar);
                 }
+                const int tro = ((warp - CS) & 1) ? -100 : 16 + 8 * sb;      // first warp of each owner pair: slots 16..23 / 24..31
+                G3_TRB(tro + 0);
                 g3_bar_sync(bar2, NTB);
                 if (own && s < Lo) {
                     if (ZP2) tz = g3_sum4<CS>(&part1[0][1][ob][4 * oq], 2 * BG * 32);
                     const float4 tr = g3_sum4<CS>(&part2[0][ob][4 * oq], BG * 32);
                     carry = make_float4(dhp.x + pr.x + tz.x + tr.x, dhp.y + pr.y + tz.y + tr.y, dhp.z + pr.z + tz.z + tr.z, dhp.w + pr.w + tz.w + tr.w);
                 }
+                if (TRACE) { if (tr_on && carry.x == 1e30f) p.clk[31] = 0; }      // (keeps the stamp behind the carry)
+                G3_TRB(tro + 1);
                 if (s > 0) phase_e(s - 1);                   // the next step's E right behind the carry
+                G3_TRB(tro + 2);
             }
         }
     }
+#undef G3_TRB
     __syncthreads();
     cluster_sync_all();
 }
@@ -465,10 +503,35 @@ static int g3_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters)
         if (cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg) != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); }
         return 0;
     }
+    if constexpr (BWD && H == 256 && BG == 5) {
+        static int trace = -1;
+        if (trace < 0) { const char* e = getenv("S2S_GRU_TRACE"); trace = e ? atoi(e) : 0; }
+        if (trace == 2 && !ctx->capturing) {
+            static long long* buf = nullptr;
+            if (!buf) S2S_CUDA(cudaMalloc(&buf, 4 * 32 * sizeof(long long)));
+            S2S_CUDA(cudaMemsetAsync(buf, 0, 4 * 32 * sizeof(long long), ctx->stream));
+            GruSeqParams q = p; q.clk = buf;
+            S2S_CUDA(cudaLaunchKernelEx(&cfg, gru3_bwd_kernel<H, NA, NB, false, true>, q));
+            long long hb[4 * 32];
+            S2S_CUDA(cudaMemcpyAsync(hb, buf, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
+            S2S_CUDA(cudaStreamSynchronize(ctx->stream));
+            const long long t0 = hb[0];
+            static const char* names[32] = {"mv0 aA landed", "mv0 P1A done", "mv0 aB landed", "mv0 P1B done", "mv0 rA landed", "mv0 P2A done", "mv0 rB landed", "mv0 P2B done",
+                                            "mv7 aA landed", "mv7 P1A done", "mv7 aB landed", "mv7 P1B done", "mv7 rA landed", "mv7 P2A done", "mv7 rB landed", "mv7 P2B done",
+                                            "ownA dar sent", "ownA carry", "ownA E sent", "ownA E loads issued", "ownA E math+stores done", "ownA dah sent", "-", "-",
+                                            "ownB dar sent", "ownB carry", "ownB E sent", "ownB E loads issued", "ownB E math+stores done", "ownB dah sent", "-", "-"};
+            for (int st = 0; st < 4; st++) {
+                fprintf(stderr, "[gru bwd trace] step %d:", 100 + st);
+                for (int e = 0; e < 32; e++) if (names[e][0] != '-') fprintf(stderr, " %s=%lld", names[e], hb[st * 32 + e] - t0);
+                fprintf(stderr, "\n");
+            }
+            return 0;
+        }
+    }
     if constexpr (!BWD && H == 256 && BG == 5) {
         static int trace = -1;
         if (trace < 0) { const char* e = getenv("S2S_GRU_TRACE"); trace = e ? atoi(e) : 0; }
-        if (trace && !ctx->capturing) {      // timeline experiment: one traced launch, printed as cycles relative to the first event of step 100
+        if (trace == 1 && !ctx->capturing) {      // timeline experiment: one traced launch, printed as cycles relative to the first event of step 100
             static long long* buf = nullptr;
             if (!buf) S2S_CUDA(cudaMalloc(&buf, 4 * 32 * sizeof(long long)));
             S2S_CUDA(cudaMemsetAsync(buf, 0, 4 * 32 * sizeof(long long), ctx->stream));
