@@ -214,6 +214,13 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
     return r;
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// read-only scalar load the compiler may neither move nor re-execute (register prefetch of a later loop iteration: see the prefetch
+// discipline in gru_seq3.cu's backward kernel)
+__device__ __forceinline__ float ldg_pinned(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
 // 4 consecutive floats from a pointer that may not be 16-byte aligned (segments of the flat parameter
 // vector start at arbitrary float offsets, e.g. after the 1-element bias of the `e` convolution)
 __device__ __forceinline__ float4 ldg4_any(const float* p) {

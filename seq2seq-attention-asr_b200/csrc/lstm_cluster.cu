@@ -204,10 +204,10 @@ lstm_cluster_bwd_kernel(const LstmClusterParams p) {
         const int t = rev ? Lf[hf] - 1 - s : s;
         const size_t row = (size_t)(b0 + NBP * hf + bbl) * p.Lmax + t;
         const float* ar = p.acts + row * 4 * H;
-        v.ig = __ldg(ar + j); v.fg = __ldg(ar + H + j); v.gg = __ldg(ar + 2 * H + j); v.og = __ldg(ar + 3 * H + j);
-        v.c = __ldg(p.cseq + row * H + j);
-        v.dy = __ldg(p.dy + row * H + j);
-        if (s > 0) v.cp = __ldg(p.cseq + ((size_t)(b0 + NBP * hf + bbl) * p.Lmax + (rev ? t + 1 : t - 1)) * H + j);
+        v.ig = ldg_pinned(ar + j); v.fg = ldg_pinned(ar + H + j); v.gg = ldg_pinned(ar + 2 * H + j); v.og = ldg_pinned(ar + 3 * H + j);
+        v.c = ldg_pinned(p.cseq + row * H + j);
+        v.dy = ldg_pinned(p.dy + row * H + j);
+        if (s > 0) v.cp = ldg_pinned(p.cseq + ((size_t)(b0 + NBP * hf + bbl) * p.Lmax + (rev ? t + 1 : t - 1)) * H + j);
         return v;
     };
     Sv svn[NH];
@@ -219,7 +219,7 @@ lstm_cluster_bwd_kernel(const LstmClusterParams p) {
         const int cur = it & 1, nxt = cur ^ 1;
         Sv sv[NH];
 #pragma unroll
-        for (int hf = 0; hf < NH; hf++) { sv[hf] = svn[hf]; svn[hf] = load_sv(s - 1, hf); }
+        for (int hf = 0; hf < NH; hf++) sv[hf] = svn[hf];
         if (tid == 0) mbar_expect_tx(&bar, TX);
 
         // dh_t (recurrent part) = W_h^T dA_{t+1} for this CTA's units
@@ -248,6 +248,10 @@ lstm_cluster_bwd_kernel(const LstmClusterParams p) {
                 *reinterpret_cast<float4*>(&stage[bl][4 * ju]) = da;
             }
         }
+        // the next step's operands, issued only now that this step's have been consumed: issued at the top of the loop, these loads -- the
+        // same static instructions, hence the same scoreboard -- made the gate math above wait for their full round trip (gru_seq3.cu)
+#pragma unroll
+        for (int hf = 0; hf < NH; hf++) svn[hf] = load_sv(s - 1, hf);
         __syncthreads();
         bcast_slice<K4, SL, BG>(stage, dabuf_a + (uint32_t)(nxt * BG * K4) * 4u, bar_a, crank, warp, lane);
         mbar_wait(&bar, parity);
