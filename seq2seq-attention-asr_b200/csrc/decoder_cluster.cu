@@ -245,7 +245,7 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
                 const float4 qA = *reinterpret_cast<const float4*>(&sm.q_full[bA][lane * 4 + 128 * i]);
                 const float4 qB = *reinterpret_cast<const float4*>(&sm.q_full[bB][lane * 4 + 128 * i]);
                 dc_f2 zA0 = dc_pack2(qA.x, qA.y), zA1 = dc_pack2(qA.z, qA.w), zB0 = dc_pack2(qB.x, qB.y), zB1 = dc_pack2(qB.z, qB.w);
-#pragma unroll 2
+#pragma unroll 5
                 for (int jj = 0; jj < DC_KFMAX; jj++) {
                     const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(&sm.uw_s[jj * S + lane * 4 + 128 * i]);
                     const dc_f2 aA = apA[jj], aB = apB[jj];
