@@ -106,7 +106,12 @@ gru3_fwd_kernel(const GruSeqParams p) {
     __shared__ __align__(16) float zbuf[BG][32];
     __shared__ uint64_t bar_h[2][CS], bar_rh[2][CS];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // S2S_GRU_DBG & 8 (experiment): the four owner warps take the LOWEST warp ids of the CTA (hardware warps 0-3) instead of the highest,
+    // in case the issue arbiter favours one end when the mat-vec warps of the other sub-batch saturate the FMA pipe
+    const int lane = threadIdx.x & 31, hw_warp = threadIdx.x >> 5;
+    const bool owners_first = (p.dbg & 8) != 0;
+    const int warp = owners_first ? (hw_warp < 4 ? H / 32 + hw_warp : hw_warp - 4) : hw_warp;      // role index: < CS mat-vec (K-slice / source CTA), >= CS owner
+    const int tid = warp * 32 + lane;
     const unsigned crank = cg::this_cluster().block_rank();
     const int cluster_id = blockIdx.x / CS;
     const int ngroups = (p.B + BG - 1) / BG;
@@ -122,7 +127,7 @@ gru3_fwd_kernel(const GruSeqParams p) {
     for (int b = 0; b < BG; b++)
         if (b0 + b < p.B) Lgrp = max(Lgrp, p.lengths ? p.lengths[b0 + b] : p.Lmax);
     const bool tr_on = TRACE && p.clk != nullptr && blockIdx.x == 0 && lane == (warp >= H / 32 ? 8 : 0);      // owner warps: lane 8 sends r*h
-#define G3_TR(slot) do { if (TRACE) { if (tr_on && s >= 100 && s < 104) p.clk[(s - 100) * 32 + (slot)] = clock64(); } } while (0)
+#define G3_TR(slot) do { if (TRACE) { if (tr_on && (slot) >= 0 && s >= 100 && s < 104) p.clk[(s - 100) * 32 + (slot)] = clock64(); } } while (0)
 
     for (int i = tid; i < BG * H; i += NT) { (&hbuf[0][0])[i] = 0.f; (&rhbuf[0][0])[i] = 0.f; }      // Recurrent.lua:13,112
     if (!owner && lane == 0) {
@@ -150,7 +155,7 @@ gru3_fwd_kernel(const GruSeqParams p) {
         for (int s = 0; s < Lgrp; s++) {
             const unsigned ph = (unsigned)(s - 1) & 1u, pr = (unsigned)s & 1u;
             // phase 1, sub-batch A then B: each as soon as its source CTA's slice of h_{s-1} has landed
-            const int trb = warp == 0 ? 0 : (warp == CS - 1 ? 8 : 24);      // (slots 24.. : scratch of the other warps, never read)
+            const int trb = warp == 0 ? 0 : (warp == CS - 1 ? 8 : -100);
             if (s > 0) { mbar_wait(&bar_h[0][warp], ph); if (lane == 0) mbar_expect_tx(&bar_h[0][warp], TXA); }
             G3_TR(trb + 0);
             g3_mv2<H, 0, NA, true>(wz2, wr2, hbuf, hbuf, k0, &part1[warp][0][0][0], &part1[warp][1][0][0], 32, lane);
@@ -215,12 +220,16 @@ gru3_fwd_kernel(const GruSeqParams p) {
                 const float4 xp1 = xp1n, xp2 = xp2n;
                 xp1n = load_xp(s + 1, f1b, L1, f1g, u1);
                 xp2n = load_xp(s + 1, f2b, L2, 2, u2);
-                const int tro = ((warp - CS) & 1) ? 28 : 16 + 4 * sb;        // first warp of each owner pair
+                const int tro = ((warp - CS) & 1) ? -100 : 16 + 4 * sb;      // first warp of each owner pair
                 g3_bar_sync(bar1, NTB);
                 G3_TR(tro + 0);
                 if (fin1) {
                     float4 v = g3_sum4<CS>(&part1[0][f1g][f1b][4 * f1q], 2 * BG * 32);
-                    v.x = sigmoid_acc(v.x + xp1.x); v.y = sigmoid_acc(v.y + xp1.y); v.z = sigmoid_acc(v.z + xp1.z); v.w = sigmoid_acc(v.w + xp1.w);   // GRU.lua:23-24
+                    if (TRACE) { if (tr_on && v.x == 1e30f) p.clk[127] = 0; G3_TR(tro + 8); }          // partial sums in
+                    v.x += xp1.x;
+                    if (TRACE) { if (tr_on && v.x == 1e30f) p.clk[127] = 0; G3_TR(tro + 9); }          // input projection in
+                    v.x = sigmoid_acc(v.x); v.y = sigmoid_acc(v.y + xp1.y); v.z = sigmoid_acc(v.z + xp1.z); v.w = sigmoid_acc(v.w + xp1.w);   // GRU.lua:23-24
+                    if (TRACE) { if (tr_on && v.x + v.y + v.z + v.w == 1e30f) p.clk[127] = 0; G3_TR(tro + 10); }   // gates done
                     const bool act = s < L1;
                     const int t = rev ? L1 - 1 - s : s;
                     float* sv = p.save + (((size_t)(b0 + f1b) * p.Lmax + t) * p.ndir + dir) * 4 * H;
@@ -230,6 +239,7 @@ gru3_fwd_kernel(const GruSeqParams p) {
                     } else {
                         const float4 hp = *reinterpret_cast<const float4*>(&hbuf[f1b][u1]);
                         const float4 rh = make_float4(v.x * hp.x, v.y * hp.y, v.z * hp.z, v.w * hp.w);   // GRU.lua:25
+                        if (TRACE) { if (tr_on && rh.x == 1e30f) p.clk[127] = 0; G3_TR(tro + 11); }    // r * h ready
                         g3_send<CS>(delta, rh_dst, barrh_a, rh);
                         if (act) { *reinterpret_cast<float4*>(sv + H + u1) = v; *reinterpret_cast<float4*>(sv + 3 * H + u1) = rh; }
                     }
@@ -283,7 +293,12 @@ gru3_bwd_kernel(const GruSeqParams p) {
     __shared__ __align__(16) float part2[CS][BG][32];
     __shared__ uint64_t bar_a[2][CS], bar_r[2][CS];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // S2S_GRU_DBG & 8 (experiment): the four owner warps take the LOWEST warp ids of the CTA (hardware warps 0-3) instead of the highest,
+    // in case the issue arbiter favours one end when the mat-vec warps of the other sub-batch saturate the FMA pipe
+    const int lane = threadIdx.x & 31, hw_warp = threadIdx.x >> 5;
+    const bool owners_first = (p.dbg & 8) != 0;
+    const int warp = owners_first ? (hw_warp < 4 ? H / 32 + hw_warp : hw_warp - 4) : hw_warp;      // role index: < CS mat-vec (K-slice / source CTA), >= CS owner
+    const int tid = warp * 32 + lane;
     const unsigned crank = cg::this_cluster().block_rank();
     const int cluster_id = blockIdx.x / CS;
     const int ngroups = (p.B + BG - 1) / BG;
@@ -541,12 +556,13 @@ static int g3_launch_geo(s2s_ctx* ctx, const GruSeqParams& p, int* max_clusters)
             S2S_CUDA(cudaMemcpyAsync(hb, buf, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
             S2S_CUDA(cudaStreamSynchronize(ctx->stream));
             const long long t0 = hb[0];
-            static const char* names[24] = {"mv0 hA landed", "mv0 P1A done", "mv0 hB landed", "mv0 P1B done", "mv0 rhA landed", "mv0 P2A done", "mv0 rhB landed", "mv0 P2B done",
+            static const char* names[32] = {"mv0 hA landed", "mv0 P1A done", "mv0 hB landed", "mv0 P1B done", "mv0 rhA landed", "mv0 P2A done", "mv0 rhB landed", "mv0 P2B done",
                                             "mv7 hA landed", "mv7 P1A done", "mv7 hB landed", "mv7 P1B done", "mv7 rhA landed", "mv7 P2A done", "mv7 rhB landed", "mv7 P2B done",
-                                            "ownA bar1", "ownA fin1 sent", "ownA bar2", "ownA fin2 sent", "ownB bar1", "ownB fin1 sent", "ownB bar2", "ownB fin2 sent"};
+                                            "ownA bar1", "ownA fin1 sent", "ownA bar2", "ownA fin2 sent", "ownB bar1", "ownB fin1 sent", "ownB bar2", "ownB fin2 sent",
+                                            "ownA sums in", "ownA xp in", "ownA gates done", "ownA rh ready", "ownB sums in", "ownB xp in", "ownB gates done", "ownB rh ready"};
             for (int st = 0; st < 4; st++) {
                 fprintf(stderr, "[gru trace] step %d:", 100 + st);
-                for (int e = 0; e < 24; e++) fprintf(stderr, " %s=%lld", names[e], hb[st * 32 + e] - t0);
+                for (int e = 0; e < 32; e++) fprintf(stderr, " %s=%lld", names[e], hb[st * 32 + e] - t0);
                 fprintf(stderr, "\n");
             }
             return 0;
