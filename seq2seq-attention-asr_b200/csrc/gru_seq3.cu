@@ -77,14 +77,27 @@ __device__ __forceinline__ void g3_send(const uint32_t (&delta)[CS], uint32_t bu
 #pragma unroll
     for (int d = 0; d < CS; d++) st_async_v4(buf_a + delta[d], v, bar_a + delta[d]);
 }
+__device__ __forceinline__ g3_f2 g3_add2(g3_f2 a, g3_f2 b) { g3_f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// sum of the CS K-slice partials of one (gate, utterance, unit quad): packed adds in a tree -- 2 (CS - 1) instructions, log2 CS deep.
+// The owner warps' FP instructions queue on the FMA pipe that the other sub-batch's mat-vec saturates (profiles/r02_gru_trace.txt), so
+// their COUNT and dependent depth, not their flops, set the length of a finalisation (28 scalar adds, 7 deep, before).
 template <int CS>
 __device__ __forceinline__ float4 g3_sum4(const float* part, int stride) {
-    float4 s = *reinterpret_cast<const float4*>(part);
+    static_assert((CS & (CS - 1)) == 0, "power of two");
+    g3_f2 lo[CS], hi[CS];
 #pragma unroll
-    for (int w = 1; w < CS; w++) {
-        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)w * stride);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    for (int w = 0; w < CS; w++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(part + (size_t)w * stride);
+        lo[w] = v.x; hi[w] = v.y;
     }
+#pragma unroll
+    for (int n = CS; n > 1; n >>= 1) {
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) { lo[i] = g3_add2(lo[2 * i], lo[2 * i + 1]); hi[i] = g3_add2(hi[2 * i], hi[2 * i + 1]); }
+    }
+    float4 s;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(s.x), "=f"(s.y) : "l"(lo[0]));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(s.z), "=f"(s.w) : "l"(hi[0]));
     return s;
 }
 
