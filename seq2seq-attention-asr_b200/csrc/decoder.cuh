@@ -48,7 +48,7 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
                      const int* labels, const int* tlens, int T, const float* dropmask, float lambda, const float* dlogp, float* dh,
                      bool defer_wgrad = false);
 
-// decoder_cluster.cu: the time loop of decoder_forward as one persistent cluster kernel (ST = 256, S = A = 512, K = 0)
+// decoder_cluster.cu: the time loop of decoder_forward as one persistent cluster kernel (ST = 256, S = A = 512; content or location-aware, KF <= 10)
 int decoder_cluster_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax, const int* tlens,
                             int T, float lambda, const float* uy, DecoderState& d, bool* handled);
 bool decoder_cluster_backward_eligible(const Layout& Y, int Lmax, float lambda);

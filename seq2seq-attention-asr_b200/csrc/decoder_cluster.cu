@@ -19,7 +19,8 @@
 //     exchange (6 exchanges per step, ~0.5 us each, instead of 5 kernel boundaries).
 // Everything the backward pass reads (alpha, {s,c}, q, {s,u}, {r s,u}, gates, penalty) is written exactly as the
 // per-step path writes it, so decoder_backward is unchanged.
-// Supported: ST = 256, S = A = 512 (the Chorowski / VGG model sizes), content attention (K = 0), Lmax <= 1024.
+// Supported: ST = 256, S = A = 512 (the Chorowski / VGG model sizes), Lmax <= 1024; content attention or the location-aware term with a
+// filter of <= 10 taps (LOC template flag), with or without the monotonicity penalty -- forward and backward.
 #include <cooperative_groups.h>
 
 #include "cluster_rnn.cuh"
@@ -555,7 +556,8 @@ dec_cluster_fwd_kernel(const DecClusterParams p) {
 //   F  own frames: dq += de_l w (1 - tanh^2(Vh_l + q_t))  -> reduce-scatter, CTA j sums dq[32j, +32)              -> all-gather dq_t
 // The transposed weights (K-contiguous rows of the per-call copies W_s^T, G_h^T, G_zr^T, W_jc^T) stay on chip: 128 KB of shared memory
 // (k-major) + W_s^T in registers.  Outputs are the arrays the deferred GEMMs / attn_dvh of decoder_backward read: dA = daz|dar|dah,
-// du, dc, dq, de.  Content attention without the monotonicity penalty (no alpha carry).
+// du, dc, dq, de.  The alignment carry d alpha_{t-1} (location term through the hoisted Jacobian V1, monotonicity penalty) runs inside
+// the kernel when the model has one (LOC / p.carry).
 struct DecClusterBwdParams {
     const float *Vh, *h, *w, *q, *alpha, *gates, *su, *dsc;
     const float *WsT, *GhT, *GzrT, *WjcT;
