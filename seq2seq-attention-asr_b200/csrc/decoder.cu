@@ -578,11 +578,11 @@ static void pad_lr(int kf, int* pl) { *pl = (kf % 2 == 1) ? (kf - 1) / 2 : kf / 
 // context Linears W_j[:, :ST] W_c, and the teacher-forced label path y_in / its share of u for all steps.  model_forward issues it on the
 // side stream at the START of the step, so it runs under the encoder instead of between the encoder and the decoder time loop;
 // decoder_forward runs it inline when nobody did.  Buffers: persistent arena (read again by the backward pass) + per-call scratch (uy).
-int decoder_prepare(s2s_ctx* ctx, const Layout& Y, const float* P, const int* labels, int B, int T) {
+int decoder_prepare(s2s_ctx* ctx, const Layout& Y, const float* P, const int* labels, int B, int T, bool backward_follows) {
     const int S = Y.S, A = Y.A, ST = Y.ST, V = Y.V, KF = Y.K > 0 ? Y.KF : 0;
     if (!ctx->dec) ctx->dec = new DecoderState();
     DecoderState& d = *ctx->dec;
-    d.valid = false; d.prepared = false; d.prep_pending = false;
+    d.valid = false; d.prepared = false; d.prep_pending = false; d.tw_valid = false;
     Arena& pa = ctx->persist;
     const size_t BT = (size_t)B * T;
     cudaStream_t st = ctx->stream;
@@ -609,6 +609,17 @@ int decoder_prepare(s2s_ctx* ctx, const Layout& Y, const float* P, const int* la
     yin_gather_kernel<<<(unsigned)BT, 128, 0, st>>>(P + Y.Wy.off, P + Y.by.off, labels, B, T, ST, V, d.yin);
     S2S_LAUNCH_CHECK(ctx);
     S2S_TRY(gemm_f32(ctx, false, true, (int)BT, ST, ST, 1.f, d.yin, ST, P + Y.Wj.off + ST, 2 * ST, 0.f, d.uy, ST, bjc));
+    if (backward_follows) {      // the backward loop's transposed weights (K-contiguous rows): off the critical path of the backward pass
+        S2S_ALLOC(d.GhT, pa, float, (size_t)2 * ST * ST);
+        S2S_ALLOC(d.GzrT, pa, float, (size_t)2 * ST * 2 * ST);
+        S2S_ALLOC(d.WjcT, pa, float, (size_t)A * ST);
+        S2S_ALLOC(d.WsT, pa, float, (size_t)ST * S);
+        S2S_TRY(transpose_f32(ctx, P + Y.Gh.off, ST, 2 * ST, 2 * ST, d.GhT, ST));
+        S2S_TRY(transpose_f32(ctx, P + Y.Gz.off, 2 * ST, 2 * ST, 2 * ST, d.GzrT, 2 * ST));
+        S2S_TRY(transpose_f32(ctx, d.Wjc, ST, A, A, d.WjcT, ST));
+        S2S_TRY(transpose_f32(ctx, P + Y.Ws.off, S, ST, ST, d.WsT, S));
+        d.tw_valid = true;
+    }
     d.prepared = true; d.prep_B = B; d.prep_T = T; d.prep_n = Y.n; d.prep_epoch = ctx->persist.epoch; d.prep_epoch_scratch = ctx->arena.epoch;
     return 0;
 }
@@ -793,19 +804,24 @@ int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, co
     S2S_ALLOC(ds_carry, ar, float, (size_t)B * ST);
     S2S_ALLOC(dsu, ar, float, (size_t)B * 2 * ST);
     if (carry_alpha) { S2S_ALLOC(dac[0], ar, float, (size_t)B * Lmax); S2S_ALLOC(dac[1], ar, float, (size_t)B * Lmax); }
-    S2S_ALLOC(GhT, ar, float, (size_t)2 * ST * ST);
-    S2S_ALLOC(GzrT, ar, float, (size_t)2 * ST * 2 * ST);
-    S2S_ALLOC(WjcT, ar, float, (size_t)A * ST);
-    S2S_ALLOC(WsT, ar, float, (size_t)ST * S);
+    if (d.tw_valid) { GhT = d.GhT; GzrT = d.GzrT; WjcT = d.WjcT; WsT = d.WsT; }      // made by decoder_prepare, under the encoder
+    else {
+        S2S_ALLOC(GhT, ar, float, (size_t)2 * ST * ST);
+        S2S_ALLOC(GzrT, ar, float, (size_t)2 * ST * 2 * ST);
+        S2S_ALLOC(WjcT, ar, float, (size_t)A * ST);
+        S2S_ALLOC(WsT, ar, float, (size_t)ST * S);
+    }
     if (KF > 0) { S2S_ALLOC(duw, ar, float, (size_t)KF * S); S2S_CUDA(cudaMemsetAsync(duw, 0, (size_t)KF * S * sizeof(float), st)); }
     AttnScratch att;
     S2S_TRY(attn_scratch_alloc(ctx, ar, B, Lmax, S, A, KF, true, &att));
 
     // transposed copies of the recurrent-chain weights so every in-loop product is K-contiguous
-    S2S_TRY(transpose_f32(ctx, P + Y.Gh.off, ST, 2 * ST, 2 * ST, GhT, ST));          // GhT [2ST, ST]
-    S2S_TRY(transpose_f32(ctx, P + Y.Gz.off, 2 * ST, 2 * ST, 2 * ST, GzrT, 2 * ST)); // rows: z then r (contiguous segments)
-    S2S_TRY(transpose_f32(ctx, d.Wjc, ST, A, A, WjcT, ST));                          // (W_j[:, :ST] W_c)^T  [A, ST]
-    S2S_TRY(transpose_f32(ctx, P + Y.Ws.off, S, ST, ST, WsT, S));                    // WsT [ST, S]
+    if (!d.tw_valid) {
+        S2S_TRY(transpose_f32(ctx, P + Y.Gh.off, ST, 2 * ST, 2 * ST, GhT, ST));          // GhT [2ST, ST]
+        S2S_TRY(transpose_f32(ctx, P + Y.Gz.off, 2 * ST, 2 * ST, 2 * ST, GzrT, 2 * ST)); // rows: z then r (contiguous segments)
+        S2S_TRY(transpose_f32(ctx, d.Wjc, ST, A, A, WjcT, ST));                          // (W_j[:, :ST] W_c)^T  [A, ST]
+        S2S_TRY(transpose_f32(ctx, P + Y.Ws.off, S, ST, ST, WsT, S));                    // WsT [ST, S]
+    }
     // The last two links of the chain, d{s_{t-1},u} += {daz,dar} G_zr and dc_t = dc_mlp + du W_jc, as ONE product: du is linear in
     // {daz, dar, dah} (du = dah G_h[:, ST:] + {daz,dar} G_zr[:, ST:]), so dc_t = dc_mlp + {daz,dar,dah} . W3[2ST:] with
     //   W3 [(2ST + A), 3ST] = [ G_zr^T | 0 ;  W_jc^T G_zr^T[ST:] | W_jc^T G_h^T[ST:] ]

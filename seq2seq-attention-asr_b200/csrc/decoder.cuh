@@ -34,6 +34,10 @@ struct DecoderState {
     float* qbias = nullptr;   // [S]       b_s (+ U b_F)
     float* Wjc = nullptr;     // [ST, A]   W_j[:, :ST] . W_c  (the two input Linears of Attention.lua:150-151 folded)
     float* uy = nullptr;      // [B, T, ST]  W_j[:, ST:] y_in + folded biases (per-call scratch, forward only)
+    // transposed copies of the recurrent-chain weights for the backward time loop (K-contiguous products), made by decoder_prepare when a
+    // backward pass is known to follow (s2s_model_fwdbwd: under the encoder, on the side stream); decoder_backward makes them itself otherwise
+    float *GhT = nullptr, *GzrT = nullptr, *WjcT = nullptr, *WsT = nullptr;
+    bool tw_valid = false;
     bool prepared = false, prep_pending = false;      // decoder_prepare ran for (prep_B, prep_T, prep_n); its side-stream event ev[4] is not joined yet
     int prep_B = 0, prep_T = 0; int64_t prep_n = 0; uint64_t prep_epoch = 0, prep_epoch_scratch = 0;
     float* V1 = nullptr;      // [B, T, Lmax, KF]  d e_t / d alpha_{t-1} (location path), formed right after the forward loop when a backward
@@ -41,7 +45,7 @@ struct DecoderState {
     AttnScratch att;
 };
 
-int decoder_prepare(s2s_ctx* ctx, const Layout& Y, const float* P, const int* labels, int B, int T);
+int decoder_prepare(s2s_ctx* ctx, const Layout& Y, const float* P, const int* labels, int B, int T, bool backward_follows = false);
 int decoder_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* h, const int* lengths, int B, int Lmax,
                     const int* labels, const int* tlens, int T, const float* dropmask, float lambda, float* logp_out, bool prefetch_v1 = false);
 int decoder_backward(s2s_ctx* ctx, const Layout& Y, const float* P, float* G, const float* h, const int* lengths, int B, int Lmax,

@@ -745,16 +745,25 @@ gru_seq_bwd_pipe_kernel(const GruSeqParams p) {
 
 // rows t >= L_b of a [B, Lmax, W] tensor := 0 (padding must not leak NaNs into the time-batched GEMMs).  The tail of an
 // utterance is one contiguous span; a few CTAs per utterance stream zeros over it (and exit at once when there is none).
-__global__ void zero_tail_rows_kernel(float* __restrict__ x, const int* __restrict__ lengths, int Lmax, int W) {
+// blockIdx.z selects one of up to two buffers (the two padded outputs of a recurrence call are cleared by ONE launch)
+__global__ void zero_tail_rows_kernel(float* __restrict__ x0, int W0, float* __restrict__ x1, int W1, const int* __restrict__ lengths, int Lmax) {
     const int b = blockIdx.y;
+    float* x = blockIdx.z ? x1 : x0;
+    const int W = blockIdx.z ? W1 : W0;
     const int len = min(max(lengths[b], 0), Lmax);
     const size_t n = (size_t)(Lmax - len) * W;
     float* r = x + ((size_t)b * Lmax + len) * W;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) r[i] = 0.f;
 }
+int zero_tail_rows2(s2s_ctx* ctx, float* x0, int W0, float* x1, int W1, const int* lengths, int B, int Lmax) {
+    if (!lengths) return 0;
+    zero_tail_rows_kernel<<<dim3(8, B, 2), 256, 0, ctx->stream>>>(x0, W0, x1, W1, lengths, Lmax);
+    S2S_LAUNCH_CHECK(ctx);
+    return 0;
+}
 int zero_tail_rows(s2s_ctx* ctx, float* x, const int* lengths, int B, int Lmax, int W) {
     if (!lengths) return 0;
-    zero_tail_rows_kernel<<<dim3(8, B), 256, 0, ctx->stream>>>(x, lengths, Lmax, W);
+    zero_tail_rows_kernel<<<dim3(8, B, 1), 256, 0, ctx->stream>>>(x, W, nullptr, 0, lengths, Lmax);
     S2S_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -887,8 +896,7 @@ int gru_seq_forward(s2s_ctx* ctx, const float* W, int Din, int H, int ndir, int 
     // time-batched input projections for all gates and both directions (LinearZeroBias.lua:42, x columns)
     S2S_TRY(gemm_f32(ctx, false, true, B * Lmax, N, Din, 1.f, x, ldx, W + H, ldw, 0.f, xp, N));
     if (lengths) {
-        S2S_TRY(zero_tail_rows(ctx, y, lengths, B, Lmax, ndir * H));
-        S2S_TRY(zero_tail_rows(ctx, save, lengths, B, Lmax, ndir * 4 * H));
+        S2S_TRY(zero_tail_rows2(ctx, y, ndir * H, save, ndir * 4 * H, lengths, B, Lmax));
     }
     GruSeqParams p = {};
     p.W = W; p.ldw = ldw; p.xp = xp; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.ndir = ndir; p.reverse0 = reverse;
@@ -907,8 +915,7 @@ int gru_seq_backward(s2s_ctx* ctx, const float* W, float* dW, int Din, int H, in
     S2S_ALLOC(dA, ctx->arena, float, (size_t)BL * N);
     S2S_ALLOC(hp_all, ctx->arena, float, (size_t)BL * ndir * H);
     if (lengths) {
-        S2S_TRY(zero_tail_rows(ctx, dA, lengths, B, Lmax, N));
-        S2S_TRY(zero_tail_rows(ctx, hp_all, lengths, B, Lmax, ndir * H));
+        S2S_TRY(zero_tail_rows2(ctx, dA, N, hp_all, ndir * H, lengths, B, Lmax));
     }
     GruSeqParams p = {};
     p.W = W; p.ldw = ldw; p.lengths = lengths; p.B = B; p.Lmax = Lmax; p.ndir = ndir; p.reverse0 = reverse;

@@ -92,7 +92,7 @@ int model_forward(s2s_ctx* ctx, const Layout& Y, const float* P, const float* X,
             S2S_CUDA(cudaEventRecord(ctx->ev[2], main_stream));
             S2S_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev[2], 0));
             ctx->stream = ctx->side[1];
-            const int rc = decoder_prepare(ctx, Y, P, labels, B, T);
+            const int rc = decoder_prepare(ctx, Y, P, labels, B, T, backward_follows);
             ctx->stream = main_stream;
             S2S_TRY(rc);
             S2S_CUDA(cudaEventRecord(ctx->ev[4], ctx->side[1]));
