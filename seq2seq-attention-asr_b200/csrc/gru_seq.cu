@@ -838,9 +838,15 @@ static int launch_cluster(s2s_ctx* ctx, bool backward, const GruSeqParams& p) {
     if (gen < 0) { const char* e = getenv("S2S_GRU_GEN"); gen = e ? atoi(e) : 3; }
     if (gen >= 2) {
         prof_begin(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD);
-        if (gen >= 5) S2S_TRY(gru_cluster5_launch(ctx, backward, p, H));
-        else if (gen == 4) S2S_TRY(gru_cluster4_launch(ctx, backward, p, H));
-        else if (gen == 3) S2S_TRY(gru_cluster3_launch(ctx, backward, p, H));
+        static int gen_bwd = -1;       // S2S_GRU_GEN_BWD: generation of the backward kernel alone (default: same as S2S_GRU_GEN)
+        if (gen_bwd < 0) { const char* e = getenv("S2S_GRU_GEN_BWD"); gen_bwd = e ? atoi(e) : 0; }
+        // default: generation 3, except the backward kernel at H = 256, where generation 5's mapping (half the shared-memory reads of the
+        // two-buffer phase-1 product) is 6% faster once the prefetch discipline removed the larger stall (1.68 vs 1.78 us per frame-step;
+        // at H = 128 generation 3 is the faster one: 0.85 vs 0.88)
+        const int g = backward ? (gen_bwd >= 2 ? gen_bwd : (gen == 3 && H == 256 ? 5 : gen)) : gen;
+        if (g >= 5) S2S_TRY(gru_cluster5_launch(ctx, backward, p, H));
+        else if (g == 4) S2S_TRY(gru_cluster4_launch(ctx, backward, p, H));
+        else if (g == 3) S2S_TRY(gru_cluster3_launch(ctx, backward, p, H));
         else S2S_TRY(gru_cluster2_launch(ctx, backward, p, H));
         prof_end(ctx, backward ? S2S_PROF_GRU_BWD : S2S_PROF_GRU_FWD, 4.0 * p.B * p.Lmax * p.ndir * (backward ? 9.0 : 8.0) * H);
         ctx->kcount[S2S_KC_GRU_CLUSTER]++;

@@ -99,14 +99,27 @@ __device__ __forceinline__ void g5_send(const uint32_t (&delta)[CS], uint32_t bu
 #pragma unroll
     for (int d = 0; d < CS; d++) st_async_v4(buf_a + delta[d], v, bar_a + delta[d]);
 }
+__device__ __forceinline__ g5_f2 g5_add2(g5_f2 a, g5_f2 b) { g5_f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// sum of the CS K-slice partials of one (gate, utterance, unit quad): packed adds in a tree -- 2 (CS - 1) instructions, log2 CS deep.
+// The owner warps' FP instructions queue on the FMA pipe that the other sub-batch's mat-vec saturates (profiles/r02_gru_trace.txt), so
+// their COUNT and dependent depth, not their flops, set the length of a finalisation (28 scalar adds, 7 deep, before).
 template <int CS>
 __device__ __forceinline__ float4 g5_sum4(const float* part, int stride) {
-    float4 s = *reinterpret_cast<const float4*>(part);
+    static_assert((CS & (CS - 1)) == 0, "power of two");
+    g5_f2 lo[CS], hi[CS];
 #pragma unroll
-    for (int w = 1; w < CS; w++) {
-        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)w * stride);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    for (int w = 0; w < CS; w++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(part + (size_t)w * stride);
+        lo[w] = v.x; hi[w] = v.y;
     }
+#pragma unroll
+    for (int n = CS; n > 1; n >>= 1) {
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) { lo[i] = g5_add2(lo[2 * i], lo[2 * i + 1]); hi[i] = g5_add2(hi[2 * i], hi[2 * i + 1]); }
+    }
+    float4 s;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(s.x), "=f"(s.y) : "l"(lo[0]));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(s.z), "=f"(s.w) : "l"(hi[0]));
     return s;
 }
 
@@ -388,27 +401,29 @@ gru5_bwd_kernel(const GruSeqParams p) {
                 const int t = rev ? Lo - 1 - s : s;
                 const size_t row = (size_t)(b0 + ob) * p.Lmax + t;
                 const float* sv = p.save + (row * p.ndir + dir) * 4 * H;
-                q.z = __ldg(reinterpret_cast<const float4*>(sv + uo)); q.r = __ldg(reinterpret_cast<const float4*>(sv + H + uo));
-                q.hc = __ldg(reinterpret_cast<const float4*>(sv + 2 * H + uo));
+                q.z = ldg_stream(sv + uo); q.r = ldg_stream(sv + H + uo);
+                q.hc = ldg_stream(sv + 2 * H + uo);
                 if (s > 0) {                                                                      // RNN.lua:186-192
                     const int tp = rev ? t + 1 : t - 1;
-                    q.hp = __ldg(reinterpret_cast<const float4*>(p.y + ((size_t)(b0 + ob) * p.Lmax + tp) * (p.ndir * H) + dir * H + uo));
+                    q.hp = ldg_stream(p.y + ((size_t)(b0 + ob) * p.Lmax + tp) * (p.ndir * H) + dir * H + uo);
                 }
-                q.dy = __ldg(reinterpret_cast<const float4*>(p.dy + row * (p.ndir * H) + dir * H + uo));
+                q.dy = ldg_stream(p.dy + row * (p.ndir * H) + dir * H + uo);
                 return q;
             };
             Pre nxt = load_pre(Lgrp - 1);
             float4 carry = make_float4(0.f, 0.f, 0.f, 0.f), dhp = carry, rr = carry, hpv = carry;
             auto phase_e = [&](int s) {          // elementwise part of step s; sends dah, daz
                 if (!own) return;
-                const Pre cur = nxt;
-                nxt = load_pre(s - 1);
+                const Pre cur = nxt;                                     // (prefetch discipline: see gru_seq3.cu -- the next loads go behind the sends)
                 float4 dah = make_float4(0.f, 0.f, 0.f, 0.f), daz = dah;
                 dhp = dah;
                 if (s < Lo) {
                     const int t = rev ? Lo - 1 - s : s;
                     const size_t row = (size_t)(b0 + ob) * p.Lmax + t;
-                    rr = cur.r; hpv = cur.hp;
+                    asm volatile("mov.b32 %0, %4; mov.b32 %1, %5; mov.b32 %2, %6; mov.b32 %3, %7;"
+                                 : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w) : "f"(cur.r.x), "f"(cur.r.y), "f"(cur.r.z), "f"(cur.r.w));
+                    asm volatile("mov.b32 %0, %4; mov.b32 %1, %5; mov.b32 %2, %6; mov.b32 %3, %7;"
+                                 : "=f"(hpv.x), "=f"(hpv.y), "=f"(hpv.z), "=f"(hpv.w) : "f"(cur.hp.x), "f"(cur.hp.y), "f"(cur.hp.z), "f"(cur.hp.w));
 #define G5_E(c)                                                                               \
                     {                                                                         \
                         const float dh = cur.dy.c + carry.c;              /* RNN.lua:193-194 */ \
@@ -424,6 +439,7 @@ gru5_bwd_kernel(const GruSeqParams p) {
                 }
                 g5_send<CS>(delta, ah_dst, bara_a, dah);
                 g5_send<CS>(delta, az_dst, bara_a, daz);
+                nxt = load_pre(s - 1);
             };
             if (Lgrp > 0) phase_e(Lgrp - 1);
             for (int s = Lgrp - 1; s >= 0; s--) {
